@@ -1,0 +1,92 @@
+"""The CPU oracle replayed against the golden vectors produced by the UNMODIFIED
+reference (oracle/make_golden.py).  fp32, eval mode; tolerance 2e-4 relative to
+max(1, max|ref|) -- observed agreement is ~1e-6 (different op order only)."""
+import os
+
+import pytest
+import torch
+
+from oracle import egovlp_oracle as O
+
+TOL = 2e-4
+
+
+def _close(a, b, tol=TOL):
+    assert a.shape == b.shape
+    err = (a.float() - b.float()).abs().max().item()
+    assert err <= tol * max(1.0, b.abs().max().item()), err
+
+
+def test_egonce_golden(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "egonce.pt"))
+    sim = O.sim_matrix(fx["t"], fx["v"])
+    _close(sim, fx["sim"])
+    loss, mask = O.egonce(sim, O.sim_matrix(fx["verb"], fx["verb"]), O.sim_matrix(fx["noun"], fx["noun"]))
+    _close(loss, fx["loss"])
+    assert torch.equal(mask, fx["mask"])
+    assert fx["temperature"] == 0.05
+
+
+def test_fullwidth_blocks_golden(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "blocks_fullwidth.pt"))
+    C, h, T, Nf = fx["C"], fx["heads"], fx["T"], fx["Nf"]
+    shapes = O.key_shapes(C=C, heads=h, depth=7, n_fuse=1, T=T, img=48, patch=16, vocab=64, proj=64)
+    sd = O.seeded_state(shapes, seed=fx["weight_seed"])
+    vp, tp = "video_model.blocks.6.", "text_model.encoder.layer.6."
+    m = O.extended_mask(fx["attention_mask"])
+    _close(O.space_time_block(fx["x"], sd, vp, h, T, Nf), fx["video_plain"])
+    _close(O.space_time_block(fx["x"], sd, vp, h, T, Nf, y=fx["y"], y_mask=m), fx["video_fused"])
+    _close(O.roberta_layer(fx["y"], m, sd, tp, h), fx["text_plain"])
+    _close(O.roberta_layer(fx["y"], m, sd, tp, h, video=fx["x"]), fx["text_fused"])
+
+
+@pytest.fixture(scope="module")
+def tiny(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "tiny_step.pt"))
+    c = fx["cfg"]
+    shapes = O.key_shapes(C=c["C"], heads=c["heads"], depth=c["depth"], n_fuse=c["n_fuse"], T=c["T"],
+                          img=c["img"], patch=c["patch"], vocab=c["vocab"], proj=c["proj"])
+    sd = O.seeded_state(shapes, fx["weight_seed"])
+    data = O.synthetic_batch(c["B"], c["T"], c["img"], c["S"], seed=fx["data_seed"])
+    plan = O.synthetic_itm_plan(c["B"], seed=fx["plan_seed"])
+    return fx, c, sd, data, plan
+
+
+def test_tiny_step_golden(tiny):
+    fx, c, sd, data, plan = tiny
+    out = O.pretrain_step(data, sd, c["heads"], c["depth"], c["n_fuse"], plan)
+    for k in ("loss_total", "EgoNCE", "loss_mlm", "loss_itm", "sim_v2t", "text_embeds", "video_embeds"):
+        _close(out[k], fx[k])
+    _close(out["cross_attn_itm_logits"], fx["itm_logits"])
+    mlm = out["cross_attn_mlm_logits"]
+    _close(mlm[:, :, ::997], fx["mlm_logits_slice"])
+    _close(torch.logsumexp(mlm, -1), fx["mlm_logits_lse"])
+    _close(mlm.double().sum(-1).float(), fx["mlm_logits_sum"], tol=1e-3)
+
+
+def test_tiny_step_gradients_golden(tiny, golden_dir):
+    fx, c, sd, data, plan = tiny
+    gfx = torch.load(os.path.join(golden_dir, "tiny_step_grads.pt"))
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    O.pretrain_step(data, sdg, c["heads"], c["depth"], c["n_fuse"], plan)["loss_total"].backward()
+    for k, g in gfx["grads"].items():
+        mine = sdg[k].grad
+        if mine.numel() > 70000:
+            mine = mine.flatten()[::37]
+        err = (mine - g).abs().max().item()
+        assert err <= 5e-4 * max(g.abs().max().item(), 1e-6) + 1e-9, (k, err)
+
+
+def test_synthetic_batch_properties():
+    d = O.synthetic_batch(6, 2, 32, 16, seed=3)
+    ids, am = d["input_ids"], d["attention_mask"]
+    assert (ids[:, 0] == 0).all()
+    lens = am.sum(1)
+    for b in range(6):
+        L = int(lens[b])
+        assert ids[b, L - 1] == 2 and (ids[b, L:] == 1).all() and (ids[b, 1:L - 1] >= 3).all()
+    lab = d["text_mlm_labels"]
+    assert ((lab == -100) | (lab == ids)).all() and (lab != -100).any(1).all()
+    assert (d["noun_vec"].sum(1) >= 1).all() and (d["verb_vec"].sum(1) >= 1).all()
+    pos = O.roberta_embeddings  # position ids: cumsum over non-pad + pad_id (roberta.py:881-892)
+    assert callable(pos)
