@@ -1,0 +1,568 @@
+// egv_attention_fwd / egv_attention_bwd: strided multi-head attention, head_dim 64, bf16 in / fp32 softmax.
+//
+// One flash-style kernel family covers every attention on the EgoVLPv2 path (see include/egovlp_b200.h):
+// divided time / space attention with the shared CLS key, the CLS query, the gated video->text and
+// text->video cross-attention cores and RoBERTa self-attention.  A work item is
+// (batch b, head h, group g, 16*NW-row tile); the "row side" lives in registers as mma.sync A fragments,
+// the "stream side" is staged through shared memory in KC-row chunks:
+//     FWD : rows = queries, stream = keys      O = softmax(QK^T) V, lse
+//     DQ  : rows = queries, stream = keys      dQ (and delta = rowsum(dO*O))
+//     DKV : rows = keys,    stream = queries   dK, dV
+// Scores never touch HBM.  Small groups (time attention: T queries x T+1 keys) run one group per warp.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace egv {
+
+enum { MODE_FWD = 0, MODE_DQ = 1, MODE_DKV = 2 };
+constexpr int HD = 64;       // head dim
+constexpr int LDS = 72;      // smem row stride in bf16 (144 B: conflict-free ldmatrix)
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnP {
+  int B, H, G, Lq, LkT;  // LkT = keys per group including the optional CLS key
+  const bf16* q; long long ldq, q_bstride; int q_row0, q_gstride, q_istride;
+  const bf16* k; const bf16* v; long long ldkv, kv_bstride; int k_row0, k_gstride, k_istride;
+  int has_cls, cls_row;
+  const float* key_bias;
+  float scale;
+  bf16* o; long long ldo, o_bstride;
+  float* lse;
+  const bf16* d_o;
+  bf16* dq; long long lddq;
+  bf16* dk; bf16* dv; long long lddkv;
+  float* delta;
+  float* dkv_cls;
+  int dkv_accumulate;
+  int row_tiles;       // tiles of the row side per group
+  long long items;     // B*G*H*row_tiles
+};
+
+EGV_DEVINL long long q_row(const AttnP& a, int b, int g, int i) {
+  return (long long)b * a.q_bstride + a.q_row0 + (long long)g * a.q_gstride + (long long)i * a.q_istride;
+}
+EGV_DEVINL long long o_row(const AttnP& a, int b, int g, int i) {
+  return (long long)b * a.o_bstride + a.q_row0 + (long long)g * a.q_gstride + (long long)i * a.q_istride;
+}
+EGV_DEVINL long long k_row(const AttnP& a, int b, int g, int j) {
+  long long r;
+  if (a.has_cls) r = (j == 0) ? a.cls_row : a.k_row0 + (long long)g * a.k_gstride + (long long)(j - 1) * a.k_istride;
+  else r = a.k_row0 + (long long)g * a.k_gstride + (long long)j * a.k_istride;
+  return (long long)b * a.kv_bstride + r;
+}
+
+// which logical tensor a smem tile is filled from
+enum { T_Q = 0, T_K = 1, T_V = 2, T_DO = 3 };
+
+template <int WHAT>
+EGV_DEVINL const bf16* row_ptr(const AttnP& a, int b, int h, int g, int idx) {
+  if (WHAT == T_Q) return a.q + q_row(a, b, g, idx) * a.ldq + h * HD;
+  if (WHAT == T_DO) return a.d_o + o_row(a, b, g, idx) * a.ldo + h * HD;
+  if (WHAT == T_K) return a.k + k_row(a, b, g, idx) * a.ldkv + h * HD;
+  return a.v + k_row(a, b, g, idx) * a.ldkv + h * HD;
+}
+
+// cp.async a [ROWS x 64] bf16 tile (rows idx0 .. idx0+ROWS-1 of the logical tensor, zero-filled past `count`)
+template <int WHAT, int ROWS, int NT>
+EGV_DEVINL void load_tile(bf16* s, const AttnP& a, int b, int h, int g, int idx0, int count, int tid) {
+  for (int c = tid; c < ROWS * 8; c += NT) {
+    const int r = c >> 3, ch = c & 7;
+    const int idx = idx0 + r;
+    const bool ok = idx < count;
+    const bf16* src = ok ? row_ptr<WHAT>(a, b, h, g, idx) + ch * 8 : a.q;
+    cp_async_16(s + r * LDS + ch * 8, src, ok);
+  }
+}
+
+template <int NW>
+EGV_DEVINL void unit_sync() {
+  if (NW == 1) __syncwarp();
+  else __syncthreads();
+}
+
+// acc[nt] (16 x 8 fp32 tiles, nt < KC/8) = A(16 x 64, fragments af) * S^T, S = smem tile [KC rows][64] (row = n index)
+template <int KC>
+EGV_DEVINL void mma_a_stile_nt(float (&acc)[KC / 8][4], const uint32_t (&af)[4][4], const bf16* s, int lane) {
+#pragma unroll
+  for (int n2 = 0; n2 < KC / 16; ++n2) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t b0, b1, b2, b3;
+      const bf16* p = s + (n2 * 16 + (lane & 7) + ((lane >> 4) << 3)) * LDS + kk * 16 + ((lane >> 3) & 1) * 8;
+      ldmatrix_x4(b0, b1, b2, b3, smem_u32(p));
+      mma_16816(acc[2 * n2], af[kk], b0, b1);
+      mma_16816(acc[2 * n2 + 1], af[kk], b2, b3);
+    }
+  }
+}
+
+// out[dt] (16 x 8 fp32 tiles over the 64 columns, dt < 8) += P(16 x KC, taken from C-layout `pacc`) * S, S = smem [KC][64]
+template <int KC>
+EGV_DEVINL void mma_p_stile(float (&out)[8][4], const float (&pacc)[KC / 8][4], const bf16* s, int lane) {
+#pragma unroll
+  for (int k2 = 0; k2 < KC / 16; ++k2) {
+    uint32_t af[4];
+    af[0] = pack_bf16(pacc[2 * k2][0], pacc[2 * k2][1]);
+    af[1] = pack_bf16(pacc[2 * k2][2], pacc[2 * k2][3]);
+    af[2] = pack_bf16(pacc[2 * k2 + 1][0], pacc[2 * k2 + 1][1]);
+    af[3] = pack_bf16(pacc[2 * k2 + 1][2], pacc[2 * k2 + 1][3]);
+#pragma unroll
+    for (int d2 = 0; d2 < 4; ++d2) {
+      uint32_t b0, b1, b2, b3;
+      const bf16* p = s + (k2 * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + d2 * 16 + (lane >> 4) * 8;
+      ldmatrix_x4_trans(b0, b1, b2, b3, smem_u32(p));
+      mma_16816(out[2 * d2], af, b0, b1);
+      mma_16816(out[2 * d2 + 1], af, b2, b3);
+    }
+  }
+}
+
+// load the 16 x 64 A fragments of this warp's rows from a smem row tile
+EGV_DEVINL void load_a_frags(uint32_t (&af)[4][4], const bf16* s, int lane) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const bf16* p = s + ((lane & 7) + ((lane >> 3) & 1) * 8) * LDS + kk * 16 + (lane >> 4) * 8;
+    ldmatrix_x4(af[kk][0], af[kk][1], af[kk][2], af[kk][3], smem_u32(p));
+  }
+}
+
+// write a warp's 16 x 64 fp32 C-layout tile into smem as bf16 (rows r0.., stride LDS)
+EGV_DEVINL void c_to_smem(bf16* s, const float (&c)[8][4], float mul0, float mul1, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<uint32_t*>(s + g * LDS + nt * 8 + 2 * t) = pack_bf16(c[nt][0] * mul0, c[nt][1] * mul0);
+    *reinterpret_cast<uint32_t*>(s + (g + 8) * LDS + nt * 8 + 2 * t) = pack_bf16(c[nt][2] * mul1, c[nt][3] * mul1);
+  }
+}
+
+template <int MODE, int NW, int KC>
+struct AttnSmem {
+  static constexpr int ROWS = 16 * NW;
+  static constexpr int ROW_TILES = (MODE == MODE_FWD) ? 1 : 2;
+  static constexpr int BYTES = (ROW_TILES * ROWS + 2 * KC) * LDS * 2 + 2 * KC * 4;
+};
+
+template <int MODE, int NW, int KC>
+EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, int tid) {
+  constexpr int NT = NW * 32;
+  constexpr int ROWS = 16 * NW;
+  using SM = AttnSmem<MODE, NW, KC>;
+  bf16* rowA = reinterpret_cast<bf16*>(smem_unit);
+  bf16* rowB = rowA + (SM::ROW_TILES - 1) * ROWS * LDS;  // == rowA for FWD (unused)
+  bf16* strA = rowA + SM::ROW_TILES * ROWS * LDS;
+  bf16* strB = strA + KC * LDS;
+  float* sf0 = reinterpret_cast<float*>(strB + KC * LDS);  // FWD/DQ: key bias (log2 units); DKV: lse of stream queries
+  float* sf1 = sf0 + KC;                                   // DKV: delta of stream queries
+
+  const int lane = tid & 31;
+  const int wq = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+
+  const int tile = (int)(item % a.row_tiles);
+  long long rest = item / a.row_tiles;
+  const int h = (int)(rest % a.H);
+  rest /= a.H;
+  const int g = (int)(rest % a.G);
+  const int b = (int)(rest / a.G);
+
+  const int n_rows = (MODE == MODE_DKV) ? a.LkT : a.Lq;
+  const int n_str = (MODE == MODE_DKV) ? a.Lq : a.LkT;
+  const int row0 = tile * ROWS;
+  const float scale2 = a.scale * LOG2E;
+  const long long stat_base = (((long long)b * a.H + h) * a.G + g) * a.Lq;
+
+  // ---------------------------------------------------------------- row-side operands -> registers
+  if (MODE == MODE_FWD) {
+    load_tile<T_Q, ROWS, NT>(rowA, a, b, h, g, row0, n_rows, tid);
+  } else if (MODE == MODE_DQ) {
+    load_tile<T_Q, ROWS, NT>(rowA, a, b, h, g, row0, n_rows, tid);
+    load_tile<T_DO, ROWS, NT>(rowB, a, b, h, g, row0, n_rows, tid);
+  } else {
+    load_tile<T_K, ROWS, NT>(rowA, a, b, h, g, row0, n_rows, tid);
+    load_tile<T_V, ROWS, NT>(rowB, a, b, h, g, row0, n_rows, tid);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  unit_sync<NW>();
+
+  uint32_t fa[4][4];  // FWD/DQ: Q   DKV: K
+  uint32_t fb[4][4];  // DQ: dO      DKV: V
+  load_a_frags(fa, rowA + wq * 16 * LDS, lane);
+  if (MODE != MODE_FWD) load_a_frags(fb, rowB + wq * 16 * LDS, lane);
+
+  // per-row statistics for rows gq and gq+8 of this warp's tile
+  const int r_lo = row0 + wq * 16 + gq, r_hi = r_lo + 8;
+  float st0_lo = 0.f, st0_hi = 0.f, st1_lo = 0.f, st1_hi = 0.f;
+  if (MODE == MODE_DQ) {
+    // delta_i = sum_d dO[i,d] * O[i,d]; one row per iteration, 2 columns per lane
+    for (int r = 0; r < 16; ++r) {
+      const int idx = row0 + wq * 16 + r;
+      float part = 0.f;
+      if (idx < n_rows) {
+        const long long orow = o_row(a, b, g, idx) * a.ldo + h * HD + 2 * lane;
+        float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.d_o + orow));
+        float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.o + orow));
+        part = x.x * y.x + x.y * y.y;
+      }
+      part = warp_sum(part);
+      if (idx < n_rows && lane == 0) a.delta[stat_base + idx] = part;
+      if (r == gq) st1_lo = part;
+      if (r == gq + 8) st1_hi = part;
+    }
+    st0_lo = r_lo < n_rows ? a.lse[stat_base + r_lo] : 0.f;
+    st0_hi = r_hi < n_rows ? a.lse[stat_base + r_hi] : 0.f;
+  } else if (MODE == MODE_DKV) {
+    // key bias of this thread's two key rows (log2 units)
+    if (a.key_bias) {
+      st0_lo = r_lo < n_rows ? fmaxf(a.key_bias[(long long)b * a.LkT + r_lo], -1e30f) * LOG2E : 0.f;
+      st0_hi = r_hi < n_rows ? fmaxf(a.key_bias[(long long)b * a.LkT + r_hi], -1e30f) * LOG2E : 0.f;
+    }
+  }
+
+  float acc0[8][4];  // FWD: O    DQ: dQ   DKV: dK
+  float acc1[8][4];  // DKV: dV
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = 0.f;
+  float m_lo = -1e30f, m_hi = -1e30f, l_lo = 0.f, l_hi = 0.f;  // FWD online softmax state
+
+  // ---------------------------------------------------------------- stream loop
+  for (int c0 = 0; c0 < n_str; c0 += KC) {
+    unit_sync<NW>();  // previous chunk fully consumed
+    if (MODE == MODE_DKV) {
+      load_tile<T_Q, KC, NT>(strA, a, b, h, g, c0, n_str, tid);
+      load_tile<T_DO, KC, NT>(strB, a, b, h, g, c0, n_str, tid);
+      for (int j = tid; j < KC; j += NT) {
+        const int idx = c0 + j;
+        sf0[j] = idx < n_str ? a.lse[stat_base + idx] : 0.f;
+        sf1[j] = idx < n_str ? a.delta[stat_base + idx] : 0.f;
+      }
+    } else {
+      load_tile<T_K, KC, NT>(strA, a, b, h, g, c0, n_str, tid);
+      load_tile<T_V, KC, NT>(strB, a, b, h, g, c0, n_str, tid);
+      for (int j = tid; j < KC; j += NT) {
+        const int idx = c0 + j;
+        float bj = 0.f;
+        if (a.key_bias && idx < n_str) bj = fmaxf(a.key_bias[(long long)b * a.LkT + idx], -1e30f) * LOG2E;
+        sf0[j] = bj;
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    unit_sync<NW>();
+
+    float s[KC / 8][4];
+#pragma unroll
+    for (int i = 0; i < KC / 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+    mma_a_stile_nt<KC>(s, fa, strA, lane);  // FWD/DQ: Q K^T    DKV: K Q^T
+
+    if (MODE == MODE_FWD) {
+      float cm_lo = -1e30f, cm_hi = -1e30f;
+#pragma unroll
+      for (int nt = 0; nt < KC / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = nt * 8 + 2 * tq + (e & 1);
+          float v = (c0 + col < n_str) ? fmaf(s[nt][e], scale2, sf0[col]) : -1e30f;
+          s[nt][e] = v;
+          if (e < 2) cm_lo = fmaxf(cm_lo, v);
+          else cm_hi = fmaxf(cm_hi, v);
+        }
+      }
+      cm_lo = fmaxf(cm_lo, __shfl_xor_sync(0xffffffffu, cm_lo, 1));
+      cm_lo = fmaxf(cm_lo, __shfl_xor_sync(0xffffffffu, cm_lo, 2));
+      cm_hi = fmaxf(cm_hi, __shfl_xor_sync(0xffffffffu, cm_hi, 1));
+      cm_hi = fmaxf(cm_hi, __shfl_xor_sync(0xffffffffu, cm_hi, 2));
+      const float mn_lo = fmaxf(m_lo, cm_lo), mn_hi = fmaxf(m_hi, cm_hi);
+      const float al_lo = exp2f(m_lo - mn_lo), al_hi = exp2f(m_hi - mn_hi);
+      m_lo = mn_lo;
+      m_hi = mn_hi;
+      l_lo *= al_lo;
+      l_hi *= al_hi;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        acc0[nt][0] *= al_lo;
+        acc0[nt][1] *= al_lo;
+        acc0[nt][2] *= al_hi;
+        acc0[nt][3] *= al_hi;
+      }
+#pragma unroll
+      for (int nt = 0; nt < KC / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = nt * 8 + 2 * tq + (e & 1);
+          float pv = (c0 + col < n_str) ? exp2f(s[nt][e] - (e < 2 ? m_lo : m_hi)) : 0.f;
+          s[nt][e] = pv;
+          if (e < 2) l_lo += pv;
+          else l_hi += pv;
+        }
+      }
+      mma_p_stile<KC>(acc0, s, strB, lane);  // O += P V
+    } else {
+      // P (or P^T) from the saved log-sum-exp
+#pragma unroll
+      for (int nt = 0; nt < KC / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = nt * 8 + 2 * tq + (e & 1);
+          const bool ok = c0 + col < n_str;
+          float pv;
+          if (MODE == MODE_DQ) pv = exp2f(fmaf(s[nt][e], scale2, sf0[col]) - (e < 2 ? st0_lo : st0_hi));
+          else pv = exp2f(fmaf(s[nt][e], scale2, (e < 2 ? st0_lo : st0_hi)) - sf0[col]);
+          s[nt][e] = ok ? pv : 0.f;
+        }
+      }
+      if (MODE == MODE_DKV) mma_p_stile<KC>(acc1, s, strB, lane);  // dV += P^T dO
+      float dp[KC / 8][4];
+#pragma unroll
+      for (int i = 0; i < KC / 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dp[i][j] = 0.f;
+      mma_a_stile_nt<KC>(dp, fb, strB, lane);  // DQ: dO V^T    DKV: V dO^T
+#pragma unroll
+      for (int nt = 0; nt < KC / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = nt * 8 + 2 * tq + (e & 1);
+          const float dl = (MODE == MODE_DQ) ? (e < 2 ? st1_lo : st1_hi) : sf1[col];
+          s[nt][e] = s[nt][e] * (dp[nt][e] - dl);  // dS (or dS^T)
+        }
+      }
+      mma_p_stile<KC>(acc0, s, strA, lane);  // DQ: dQ += dS K    DKV: dK += dS^T Q
+    }
+  }
+
+  // ---------------------------------------------------------------- write-out (through smem for 16-byte stores)
+  unit_sync<NW>();
+  bf16* outA = rowA + wq * 16 * LDS;
+  if (MODE == MODE_FWD) {
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    c_to_smem(outA, acc0, 1.0f / l_lo, 1.0f / l_hi, lane);
+    if (tq == 0) {
+      if (r_lo < n_rows) a.lse[stat_base + r_lo] = m_lo + log2f(l_lo);
+      if (r_hi < n_rows) a.lse[stat_base + r_hi] = m_hi + log2f(l_hi);
+    }
+  } else if (MODE == MODE_DQ) {
+    c_to_smem(outA, acc0, a.scale, a.scale, lane);
+  } else {
+    c_to_smem(outA, acc0, a.scale, a.scale, lane);
+    c_to_smem(rowB + wq * 16 * LDS, acc1, 1.0f, 1.0f, lane);
+    if (a.has_cls && tile == 0 && wq == 0 && gq == 0 && a.dkv_cls) {
+      float* dst = a.dkv_cls + ((long long)b * a.H + h) * 2 * HD;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        atomicAdd(dst + nt * 8 + 2 * tq, acc0[nt][0] * a.scale);
+        atomicAdd(dst + nt * 8 + 2 * tq + 1, acc0[nt][1] * a.scale);
+        atomicAdd(dst + HD + nt * 8 + 2 * tq, acc1[nt][0]);
+        atomicAdd(dst + HD + nt * 8 + 2 * tq + 1, acc1[nt][1]);
+      }
+    }
+  }
+  unit_sync<NW>();
+  for (int c = tid; c < ROWS * 8; c += NT) {
+    const int r = c >> 3, ch = c & 7;
+    const int idx = row0 + r;
+    if (idx >= n_rows) continue;
+    if (MODE == MODE_FWD) {
+      bf16* dst = a.o + o_row(a, b, g, idx) * a.ldo + h * HD + ch * 8;
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(rowA + r * LDS + ch * 8);
+    } else if (MODE == MODE_DQ) {
+      bf16* dst = a.dq + q_row(a, b, g, idx) * a.lddq + h * HD + ch * 8;
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(rowA + r * LDS + ch * 8);
+    } else {
+      if (a.has_cls && idx == 0) continue;  // shared CLS key: accumulated in dkv_cls above
+      const long long off = k_row(a, b, g, idx) * a.lddkv + h * HD + ch * 8;
+      uint4 vk = *reinterpret_cast<const uint4*>(rowA + r * LDS + ch * 8);
+      uint4 vv = *reinterpret_cast<const uint4*>(rowB + r * LDS + ch * 8);
+      if (a.dkv_accumulate) {
+        uint4 ok = *reinterpret_cast<const uint4*>(a.dk + off);
+        uint4 ov = *reinterpret_cast<const uint4*>(a.dv + off);
+        uint32_t* pk = reinterpret_cast<uint32_t*>(&vk);
+        uint32_t* pv = reinterpret_cast<uint32_t*>(&vv);
+        const uint32_t* qk = reinterpret_cast<const uint32_t*>(&ok);
+        const uint32_t* qv = reinterpret_cast<const uint32_t*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 x = unpack_bf16(pk[e]), y = unpack_bf16(qk[e]);
+          pk[e] = pack_bf16(x.x + y.x, x.y + y.y);
+          x = unpack_bf16(pv[e]);
+          y = unpack_bf16(qv[e]);
+          pv[e] = pack_bf16(x.x + y.x, x.y + y.y);
+        }
+      }
+      *reinterpret_cast<uint4*>(a.dk + off) = vk;
+      *reinterpret_cast<uint4*>(a.dv + off) = vv;
+    }
+  }
+}
+
+// CTA-per-item variant (large groups): NW warps cooperate on one item.
+template <int MODE, int NW, int KC>
+__global__ void __launch_bounds__(NW * 32) attn_cta_kernel(const AttnP a) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  for (long long item = blockIdx.x; item < a.items; item += gridDim.x) {
+    attn_unit<MODE, NW, KC>(a, item, smem_attn, threadIdx.x);
+    __syncthreads();
+  }
+}
+
+// Warp-per-item variant (small groups): 4 independent warps per CTA, no block-level sync.
+template <int MODE, int KC>
+__global__ void __launch_bounds__(128) attn_warp_kernel(const AttnP a) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const int warp = threadIdx.x >> 5;
+  uint8_t* mine = smem_attn + warp * AttnSmem<MODE, 1, KC>::BYTES;
+  for (long long item = (long long)blockIdx.x * 4 + warp; item < a.items; item += (long long)gridDim.x * 4) {
+    attn_unit<MODE, 1, KC>(a, item, mine, threadIdx.x & 31);
+    __syncwarp();
+  }
+}
+
+// fp32 CLS accumulators -> bf16 rows of the dk / dv tensors
+__global__ void attn_cls_finalize_kernel(const float* __restrict__ dkv_cls, bf16* dk, bf16* dv, long long lddkv,
+                                         long long kv_bstride, int cls_row, int B, int H, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H * HD) return;
+  const int d = idx % HD, h = (idx / HD) % H, b = idx / (HD * H);
+  const float* src = dkv_cls + ((long long)b * H + h) * 2 * HD;
+  const long long off = ((long long)b * kv_bstride + cls_row) * lddkv + h * HD + d;
+  float vk = src[d], vv = src[HD + d];
+  if (accumulate) {
+    vk += __bfloat162float(dk[off]);
+    vv += __bfloat162float(dv[off]);
+  }
+  dk[off] = __float2bfloat16(vk);
+  dv[off] = __float2bfloat16(vv);
+}
+
+static int fill_params(const egv_attn_args* x, AttnP& a, bool bwd) {
+  if (!x || !x->q || !x->k || !x->v) return fail(EGV_ERR_ARG, "attention: null q/k/v");
+  if (x->B <= 0 || x->H <= 0 || x->G <= 0 || x->Lq <= 0 || x->Lk < 0) return fail(EGV_ERR_ARG, "attention: bad sizes");
+  if (!x->o || !x->lse) return fail(EGV_ERR_ARG, "attention: o and lse are required");
+  if ((x->ldq % 8) || (x->ldkv % 8) || (x->ldo % 8)) return fail(EGV_ERR_ARG, "attention: row strides must be multiples of 8");
+  auto al = [](const void* p) { return (((uintptr_t)p) & 15) == 0; };
+  if (!al(x->q) || !al(x->k) || !al(x->v) || !al(x->o)) return fail(EGV_ERR_ARG, "attention: pointers must be 16-byte aligned");
+  a.B = x->B; a.H = x->H; a.G = x->G; a.Lq = x->Lq; a.LkT = x->Lk + (x->has_cls_key ? 1 : 0);
+  if (a.LkT <= 0) return fail(EGV_ERR_ARG, "attention: no keys");
+  a.q = (const bf16*)x->q; a.ldq = x->ldq; a.q_bstride = x->q_bstride;
+  a.q_row0 = x->q_row0; a.q_gstride = x->q_gstride; a.q_istride = x->q_istride;
+  a.k = (const bf16*)x->k; a.v = (const bf16*)x->v; a.ldkv = x->ldkv; a.kv_bstride = x->kv_bstride;
+  a.k_row0 = x->k_row0; a.k_gstride = x->k_gstride; a.k_istride = x->k_istride;
+  a.has_cls = x->has_cls_key ? 1 : 0; a.cls_row = x->cls_row;
+  a.key_bias = x->key_bias; a.scale = x->scale;
+  a.o = (bf16*)x->o; a.ldo = x->ldo; a.o_bstride = x->o_bstride;
+  a.lse = x->lse;
+  a.d_o = (const bf16*)x->d_o; a.dq = (bf16*)x->dq; a.lddq = x->lddq;
+  a.dk = (bf16*)x->dk; a.dv = (bf16*)x->dv; a.lddkv = x->lddkv;
+  a.delta = x->delta; a.dkv_cls = x->dkv_cls; a.dkv_accumulate = x->dkv_accumulate;
+  if (bwd) {
+    if (!x->d_o || !x->dq || !x->dk || !x->dv || !x->delta) return fail(EGV_ERR_ARG, "attention bwd: null gradient buffer");
+    if ((x->lddq % 8) || (x->lddkv % 8)) return fail(EGV_ERR_ARG, "attention bwd: gradient strides must be multiples of 8");
+    if (!al(x->d_o) || !al(x->dq) || !al(x->dk) || !al(x->dv)) return fail(EGV_ERR_ARG, "attention bwd: unaligned gradient pointer");
+    if (a.has_cls && !x->dkv_cls) return fail(EGV_ERR_ARG, "attention bwd: dkv_cls required with has_cls_key");
+  }
+  return EGV_OK;
+}
+
+template <int MODE>
+static int launch_mode(AttnP a, cudaStream_t stream) {
+  const int n_rows = (MODE == MODE_DKV) ? a.LkT : a.Lq;
+  const int n_str = (MODE == MODE_DKV) ? a.Lq : a.LkT;
+  const long long groups = (long long)a.B * a.H * a.G;
+  const bool small = n_rows <= 32 && n_str <= 64 && groups >= 1024;
+  cudaError_t e = cudaSuccess;
+  if (small) {
+    constexpr int KC = 32;
+    a.row_tiles = (int)cdiv(n_rows, 16);
+    a.items = groups * a.row_tiles;
+    auto kern = attn_warp_kernel<MODE, KC>;
+    const int smem = 4 * AttnSmem<MODE, 1, KC>::BYTES;
+    static bool cfg = false;
+    if (!cfg) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cfg = true;
+    }
+    long long grid = cdiv(a.items, 4);
+    const long long cap = (long long)sm_count() * 64;
+    if (grid > cap) grid = cap;
+    if (e == cudaSuccess) kern<<<(unsigned)grid, 128, smem, stream>>>(a);
+  } else if (n_rows <= 16) {
+    // few rows, long stream (CLS query; tiny text batches): one warp is all the row side can use
+    constexpr int KC = 64;
+    a.row_tiles = (int)cdiv(n_rows, 16);
+    a.items = groups * a.row_tiles;
+    auto kern = attn_cta_kernel<MODE, 1, KC>;
+    const int smem = AttnSmem<MODE, 1, KC>::BYTES;
+    static bool cfg = false;
+    if (!cfg) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cfg = true;
+    }
+    long long grid = std::min<long long>(a.items, (long long)sm_count() * 32);
+    if (e == cudaSuccess) kern<<<(unsigned)grid, 32, smem, stream>>>(a);
+  } else if (n_rows <= 32) {
+    constexpr int KC = 64;
+    a.row_tiles = (int)cdiv(n_rows, 32);
+    a.items = groups * a.row_tiles;
+    auto kern = attn_cta_kernel<MODE, 2, KC>;
+    const int smem = AttnSmem<MODE, 2, KC>::BYTES;
+    static bool cfg = false;
+    if (!cfg) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cfg = true;
+    }
+    long long grid = std::min<long long>(a.items, (long long)sm_count() * 16);
+    if (e == cudaSuccess) kern<<<(unsigned)grid, 64, smem, stream>>>(a);
+  } else {
+    constexpr int KC = 64;
+    a.row_tiles = (int)cdiv(n_rows, 64);
+    a.items = groups * a.row_tiles;
+    auto kern = attn_cta_kernel<MODE, 4, KC>;
+    const int smem = AttnSmem<MODE, 4, KC>::BYTES;
+    static bool cfg = false;
+    if (!cfg) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cfg = true;
+    }
+    long long grid = std::min<long long>(a.items, (long long)sm_count() * 8);
+    if (e == cudaSuccess) kern<<<(unsigned)grid, 128, smem, stream>>>(a);
+  }
+  if (e != cudaSuccess) return fail(EGV_ERR_CUDA, "attention smem attribute: %s", cudaGetErrorString(e));
+  return check_launch("attention kernel");
+}
+
+}  // namespace egv
+
+using namespace egv;
+
+extern "C" int egv_attention_fwd(const egv_attn_args* x, egv_stream_t stream) {
+  AttnP a;
+  int rc = fill_params(x, a, false);
+  if (rc) return rc;
+  return launch_mode<MODE_FWD>(a, (cudaStream_t)stream);
+}
+
+extern "C" int egv_attention_bwd(const egv_attn_args* x, egv_stream_t stream) {
+  AttnP a;
+  int rc = fill_params(x, a, true);
+  if (rc) return rc;
+  rc = launch_mode<MODE_DQ>(a, (cudaStream_t)stream);   // also produces delta
+  if (rc) return rc;
+  return launch_mode<MODE_DKV>(a, (cudaStream_t)stream);
+}
+
+extern "C" int egv_attention_cls_finalize(const float* dkv_cls, void* dk, void* dv, int64_t lddkv, int64_t kv_bstride,
+                                          int cls_row, int B, int H, int accumulate, egv_stream_t stream) {
+  if (!dkv_cls || !dk || !dv) return fail(EGV_ERR_ARG, "cls_finalize: null pointer");
+  const int n = B * H * HD;
+  attn_cls_finalize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dkv_cls, (bf16*)dk, (bf16*)dv, lddkv,
+                                                                             kv_bstride, cls_row, B, H, accumulate);
+  return check_launch("attn_cls_finalize_kernel");
+}

@@ -1,0 +1,525 @@
+// egv_gemm_bf16: D = epilogue(A x B), bf16 operands, fp32 accumulation.
+//
+// Main path (sm_100a): persistent, warp-specialised tcgen05 kernel.
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, mbarrier complete_tx)
+//   warp 1      MMA issuer     (one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128 x N=BN x K=16)
+//   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
+//   warps 4-11  epilogue       (tcgen05.ld 32x32b -> smem transpose -> coalesced global I/O, fused
+//                               bias / activation / activation-gradient / scale / residual / split-K atomics)
+// Operands may be K-major or MN-major (UMMA descriptor "major" bits), which gives the three layouts
+// the training step needs without ever materialising a transpose:
+//   NT  y  = x W^T   (A K-major, B K-major)     nn.Linear forward
+//   NN  dx = dy W    (A K-major, B MN-major)
+//   TN  dW = dy^T x  (A MN-major, B MN-major)
+// Fallback path: a small SIMT kernel with identical semantics for shapes TMA cannot address
+// (row strides that are not multiples of 16 bytes) and for tiny problems.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace egv {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
+constexpr int EPI_STAGE_FLOATS = 32 * 33;
+
+struct GemmParams {
+  int M, N, K;
+  int num_n_tiles, total_items, split_k, k_blocks_total, k_blocks_per_split;
+  const float* bias;
+  const bf16* aux;
+  long long ld_aux;
+  const float* scale_dev;
+  float scale;
+  const float* residual;
+  long long ld_res;
+  float* out_f32;
+  long long ld_out_f32;
+  bf16* out_bf16;
+  long long ld_out_bf16;
+  bf16* out_pre;
+  long long ld_out_pre;
+  int act;
+  int accumulate;
+};
+
+// erf with |abs err| < 1.5e-7 (Abramowitz-Stegun 7.1.26): far below bf16 resolution, ~3x cheaper than erff.
+EGV_DEVINL float fast_erf(float x) {
+  float ax = fabsf(x);
+  float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  float r = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+
+// Shared epilogue math.  `lead` is false for split-K slices > 0 (they only add their partial sum).
+EGV_DEVINL void epilogue_store(const GemmParams& p, float v, int row, int col, bool lead, float resv, float auxv,
+                               float scale_total) {
+  if (lead && p.bias) v += __ldg(p.bias + col);
+  if (p.out_pre) p.out_pre[(long long)row * p.ld_out_pre + col] = __float2bfloat16(v);
+  switch (p.act) {
+    case EGV_ACT_GELU: v = 0.5f * v * (1.0f + fast_erf(v * 0.70710678118654752f)); break;
+    case EGV_ACT_RELU: v = fmaxf(v, 0.0f); break;
+    case EGV_ACT_TANH: v = tanhf(v); break;
+    case EGV_ACT_GELU_BWD: {
+      float cdf = 0.5f * (1.0f + fast_erf(auxv * 0.70710678118654752f));
+      float pdf = 0.3989422804014327f * __expf(-0.5f * auxv * auxv);
+      v *= fmaf(auxv, pdf, cdf);
+    } break;
+    case EGV_ACT_RELU_BWD: v = auxv > 0.0f ? v : 0.0f; break;
+    case EGV_ACT_TANH_BWD: v *= (1.0f - auxv * auxv); break;
+    default: break;
+  }
+  v *= scale_total;
+  if (lead) v += resv;
+  if (p.out_f32) {
+    float* o = p.out_f32 + (long long)row * p.ld_out_f32 + col;
+    if (p.accumulate) atomicAdd(o, v);
+    else *o = v;
+  }
+  if (p.out_bf16) p.out_bf16[(long long)row * p.ld_out_bf16 + col] = __float2bfloat16(v);
+}
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_FLOATS * 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+        const int ks = w % p.split_k;
+        const int tile = w / p.split_k;
+        const int m0 = (tile / p.num_n_tiles) * BM;
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        const int kb0 = ks * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      // encoded (>>4) start-address advance per UMMA_K step
+      constexpr uint32_t a_adv = A_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      constexpr uint32_t b_adv = B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++it) {
+        const int ks = w % p.split_k;
+        const int kb0 = ks * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+        const int as = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tmem_empty[as], use ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = A_MN ? umma_desc_sw128(sa, 8192, 1024) : umma_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = B_MN ? umma_desc_sw128(sb, 8192, 1024) : umma_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 4;
+    const int quad = warp & 3;       // TMEM lane quadrant this warp may read (warp id % 4)
+    const int chalf = ew >> 2;       // which half of the BN columns
+    float* stg = epi_smem + ew * EPI_STAGE_FLOATS;
+    const float scale_total = p.scale * (p.scale_dev ? __ldg(p.scale_dev) : 1.0f);
+    const bool need_aux = p.act >= EGV_ACT_GELU_BWD;
+    int it = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++it) {
+      const int ks = w % p.split_k;
+      const int tile = w / p.split_k;
+      const int m0 = (tile / p.num_n_tiles) * BM;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      const int as = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1) & 1u;
+      const bool lead = (ks == 0);
+      mbar_wait(&tmem_full[as], use);
+      tc_fence_after();
+      const int row_base = m0 + quad * 32;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int col0 = chalf * (BN / 2) + c * 32;
+        const int gcol = n0 + col0 + lane;
+        const bool col_ok = gcol < p.N;
+        // prefetch residual / aux for the 32 rows of this chunk while TMEM is being read
+        float resv[32];
+        float auxv[32];
+        if (p.residual && lead) {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const int row = row_base + r;
+            resv[r] = (col_ok && row < p.M) ? __ldg(p.residual + (long long)row * p.ld_res + gcol) : 0.0f;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) resv[r] = 0.0f;
+        }
+        if (need_aux) {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const int row = row_base + r;
+            auxv[r] = (col_ok && row < p.M) ? __bfloat162float(p.aux[(long long)row * p.ld_aux + gcol]) : 0.0f;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) auxv[r] = 0.0f;
+        }
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + col0), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const int row = row_base + r;
+          const float acc = stg[r * 33 + lane];
+          if (col_ok && row < p.M) epilogue_store(p, acc, row, gcol, lead, resv[r], auxv[r], scale_total);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// --------------------------------------------------------------------------------- SIMT fallback
+// C[m,n] = sum_k A(m,k) B(n,k) with arbitrary element strides; 32x32 tile, 16x16 threads, 2x2 per thread.
+struct SimtStrides {
+  long long a_m, a_k, b_n, b_k;
+};
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, SimtStrides st, const GemmParams p) {
+  __shared__ float sA[32][33];
+  __shared__ float sB[32][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int ks = blockIdx.z;
+  const int k_lo = ks * p.k_blocks_per_split;  // here: elements per split
+  const int k_hi = min(p.K, k_lo + p.k_blocks_per_split);
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = k_lo; k0 < k_hi; k0 += 32) {
+    for (int i = threadIdx.x; i < 1024; i += 256) {
+      int r, kk;
+      // pick the loop order that keeps the contiguous global dimension on adjacent threads
+      if (st.a_k == 1) { r = i >> 5; kk = i & 31; } else { kk = i >> 5; r = i & 31; }
+      int m = m0 + r, k = k0 + kk;
+      sA[r][kk] = (m < p.M && k < k_hi) ? __bfloat162float(A[m * st.a_m + k * st.a_k]) : 0.0f;
+      if (st.b_k == 1) { r = i >> 5; kk = i & 31; } else { kk = i >> 5; r = i & 31; }
+      int n = n0 + r;
+      k = k0 + kk;
+      sB[r][kk] = (n < p.N && k < k_hi) ? __bfloat162float(B[n * st.b_n + k * st.b_k]) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      float a0 = sA[ty][kk], a1 = sA[ty + 16][kk];
+      float b0 = sB[tx][kk], b1 = sB[tx + 16][kk];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]);
+      acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]);
+      acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+  const float scale_total = p.scale * (p.scale_dev ? __ldg(p.scale_dev) : 1.0f);
+  const bool lead = ks == 0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      int row = m0 + ty + 16 * i, col = n0 + tx + 16 * j;
+      if (row < p.M && col < p.N) {
+        float resv = (p.residual && lead) ? p.residual[(long long)row * p.ld_res + col] : 0.0f;
+        float auxv = (p.act >= EGV_ACT_GELU_BWD) ? __bfloat162float(p.aux[(long long)row * p.ld_aux + col]) : 0.0f;
+        epilogue_store(p, acc[i][j], row, col, lead, resv, auxv, scale_total);
+      }
+    }
+}
+
+// --------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t inner, outer, ld;
+  uint32_t box_inner, box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+           box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    auto mix = [&h](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer);
+    return h;
+  }
+};
+
+// bf16 2-D tensor map: `inner` contiguous elements, `outer` rows `ld` elements apart, 128B swizzle.
+static int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                          uint32_t box_outer, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return EGV_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(EGV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(EGV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%llu outer=%llu ld=%llu", (int)r, ptr,
+                (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache[key] = *out;
+  return EGV_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(EGV_ERR_CUDA, "gemm smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  int grid = p.total_items < sm_count() ? p.total_items : sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+template <int BN>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                          cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false>(ta, tb, p, s);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true>(ta, tb, p, s);
+  if (a_mn && b_mn) return launch_tc<BN, true, true>(ta, tb, p, s);
+  return launch_tc<BN, true, false>(ta, tb, p, s);
+}
+
+static int g_force_simt = 0;
+
+}  // namespace egv
+
+using namespace egv;
+
+extern "C" void egv_gemm_force_simt(int on) { g_force_simt = on; }
+
+extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a || !a->A || !a->B) return fail(EGV_ERR_ARG, "gemm: null operand");
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return fail(EGV_ERR_ARG, "gemm: bad shape %d %d %d", a->M, a->N, a->K);
+  if (a->layout < 0 || a->layout > 2) return fail(EGV_ERR_ARG, "gemm: bad layout %d", a->layout);
+  if (!a->out_f32 && !a->out_bf16 && !a->out_pre_bf16) return fail(EGV_ERR_ARG, "gemm: no output");
+  if (a->act >= EGV_ACT_GELU_BWD && !a->aux) return fail(EGV_ERR_ARG, "gemm: act %d needs aux", a->act);
+  int split_k = a->split_k < 1 ? 1 : a->split_k;
+  if (split_k > 1 && (!a->accumulate || !a->out_f32 || a->out_bf16 || a->out_pre_bf16 || a->act != EGV_ACT_NONE))
+    return fail(EGV_ERR_ARG, "gemm: split_k > 1 needs accumulate=1, f32 output only, no activation");
+
+  GemmParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.bias = a->bias;
+  p.aux = (const bf16*)a->aux; p.ld_aux = a->ld_aux;
+  p.scale_dev = a->scale_dev; p.scale = a->scale;
+  p.residual = a->residual; p.ld_res = a->ld_res;
+  p.out_f32 = a->out_f32; p.ld_out_f32 = a->ld_out_f32;
+  p.out_bf16 = (bf16*)a->out_bf16; p.ld_out_bf16 = a->ld_out_bf16;
+  p.out_pre = (bf16*)a->out_pre_bf16; p.ld_out_pre = a->ld_out_pre;
+  p.act = a->act; p.accumulate = a->accumulate;
+
+  const bool a_mn = a->layout == EGV_GEMM_TN;                           // A stored [K, M]
+  const bool b_mn = a->layout == EGV_GEMM_NN || a->layout == EGV_GEMM_TN;  // B stored [K, N]
+  auto aligned = [](const void* ptr, long long ld) { return (((uintptr_t)ptr) & 15) == 0 && (ld % 8) == 0; };
+  bool tma_ok = aligned(a->A, a->lda) && aligned(a->B, a->ldb);
+  // MN-major boxes are 64 elements wide along M/N: fine for any extent (OOB zero fill), but the contiguous
+  // extent must itself be addressable, which the ld % 8 test already guarantees.
+  const bool tiny = (long long)a->M * a->N * a->K < (1ll << 18);
+  if (!tma_ok || tiny || g_force_simt) {
+    SimtStrides st;
+    st.a_m = a_mn ? 1 : a->lda; st.a_k = a_mn ? a->lda : 1;
+    st.b_n = b_mn ? 1 : a->ldb; st.b_k = b_mn ? a->ldb : 1;
+    // split over K in chunks of >= 256 elements when the output grid alone cannot fill the GPU
+    long long tiles = cdiv(a->M, 32) * cdiv(a->N, 32);
+    int sk = 1;
+    if (a->accumulate && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && a->act == EGV_ACT_NONE) {
+      sk = split_k;
+      if (sk == 1 && tiles < sm_count() && a->K >= 1024) sk = (int)std::min<long long>(cdiv(a->K, 256), 64);
+    }
+    int per = (int)cdiv(cdiv(a->K, sk), 32) * 32;
+    sk = (int)cdiv(a->K, per);
+    p.split_k = sk; p.k_blocks_per_split = per; p.k_blocks_total = 0; p.num_n_tiles = 0; p.total_items = 0;
+    dim3 grid((unsigned)cdiv(a->N, 32), (unsigned)cdiv(a->M, 32), (unsigned)sk);
+    gemm_simt_kernel<<<grid, 256, 0, stream>>>((const bf16*)a->A, (const bf16*)a->B, st, p);
+    return check_launch("gemm_simt_kernel");
+  }
+
+  int BN = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  const int num_m_tiles = (int)cdiv(a->M, BM);
+  // prefer the 128-wide tile when the 256-wide one would leave most SMs idle
+  if (BN == 256 && (long long)num_m_tiles * cdiv(a->N, 256) * split_k < sm_count() / 2) BN = 128;
+  p.num_n_tiles = (int)cdiv(a->N, BN);
+  p.k_blocks_total = (int)cdiv(a->K, BK);
+  if (split_k > p.k_blocks_total) split_k = p.k_blocks_total;
+  p.k_blocks_per_split = (int)cdiv(p.k_blocks_total, split_k);
+  split_k = (int)cdiv(p.k_blocks_total, p.k_blocks_per_split);
+  p.split_k = split_k;
+  p.total_items = num_m_tiles * p.num_n_tiles * split_k;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_mn) rc = get_tensor_map(a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BK, &ta);
+  else rc = get_tensor_map(a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM, &ta);
+  if (rc) return rc;
+  if (b_mn) rc = get_tensor_map(a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK, &tb);
+  else rc = get_tensor_map(a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, (uint32_t)BN, &tb);
+  if (rc) return rc;
+
+  switch (BN) {
+    case 256: return dispatch_major<256>(a_mn, b_mn, ta, tb, p, stream);
+    case 128: return dispatch_major<128>(a_mn, b_mn, ta, tb, p, stream);
+    default: return dispatch_major<64>(a_mn, b_mn, ta, tb, p, stream);
+  }
+}

@@ -1,0 +1,207 @@
+// egv_layernorm_fwd / egv_layernorm_bwd: nn.LayerNorm over the last dimension, one warp per row, fp32 statistics.
+// HBM-bound: each row is read once (kept in registers for C <= 1024) and written once.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace egv {
+
+constexpr int LN_MAXV = 8;  // float4 per lane -> C <= 1024
+
+template <bool XBF>
+EGV_DEVINL float4 ld4(const void* base, long long idx) {
+  if (XBF) {
+    uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(base) + idx);
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+}
+EGV_DEVINL void st4_bf16(bf16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16(v.x, v.y);
+  u.y = pack_bf16(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <bool XBF>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps, long long rows, int C,
+                                                     bf16* __restrict__ y_bf16, float* __restrict__ y_f32,
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nv = C >> 2;  // float4 per row
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const long long base = row * C;
+    float4 v[LN_MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c4 = lane + i * 32;
+      if (c4 < nv) {
+        v[i] = ld4<XBF>(x, base + 4 * c4);
+        sum += v[i].x + v[i].y + v[i].z + v[i].w;
+      }
+    }
+    const float mean = warp_sum(sum) / C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c4 = lane + i * 32;
+      if (c4 < nv) {
+        float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += a * a + b * b + c * c + d * d;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / C + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c4 = lane + i * 32;
+      if (c4 < nv) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c4);
+        const float4 bb = *reinterpret_cast<const float4*>(beta + 4 * c4);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + bb.x;
+        o.y = (v[i].y - mean) * rstd * g.y + bb.y;
+        o.z = (v[i].z - mean) * rstd * g.z + bb.z;
+        o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+        if (y_f32) *reinterpret_cast<float4*>(y_f32 + base + 4 * c4) = o;
+        if (y_bf16) st4_bf16(y_bf16 + base + 4 * c4, o);
+      }
+    }
+  }
+}
+
+// val = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dx = (add ? add : 0) + val (add may alias dx);
+// dx_bf16 = bf16(bf16_total ? dx : val);  dgamma += sum dy*xhat;  dbeta += sum dy
+template <bool DYBF, bool XBF>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, long long rows, int C,
+                                                     const float* add, float* dx, int bf16_total, bf16* __restrict__ dx_bf16,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[8][32 * 4 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp0 = (long long)blockIdx.x * 8 + warp;
+  const long long nwarps = (long long)gridDim.x * 8;
+  const int nv = C >> 2;
+  float4 dg[LN_MAXV], db[LN_MAXV], g[LN_MAXV];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c4 = lane + i * 32;
+    g[i] = c4 < nv ? *reinterpret_cast<const float4*>(gamma + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const long long base = row * C;
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[LN_MAXV], gy[LN_MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c4 = lane + i * 32;
+      if (c4 < nv) {
+        const float4 xv = ld4<XBF>(x, base + 4 * c4);
+        const float4 d = ld4<DYBF>(dy, base + 4 * c4);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        gy[i] = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
+        s1 += gy[i].x + gy[i].y + gy[i].z + gy[i].w;
+        s2 += gy[i].x * xh[i].x + gy[i].y * xh[i].y + gy[i].z * xh[i].z + gy[i].w * xh[i].w;
+        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+      }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c4 = lane + i * 32;
+      if (c4 < nv) {
+        float4 o;
+        o.x = rs * (gy[i].x - s1 - xh[i].x * s2);
+        o.y = rs * (gy[i].y - s1 - xh[i].y * s2);
+        o.z = rs * (gy[i].z - s1 - xh[i].z * s2);
+        o.w = rs * (gy[i].w - s1 - xh[i].w * s2);
+        float4 tot = o;
+        if (add) {
+          const float4 old = *reinterpret_cast<const float4*>(add + base + 4 * c4);
+          tot.x += old.x; tot.y += old.y; tot.z += old.z; tot.w += old.w;
+        }
+        if (dx) *reinterpret_cast<float4*>(dx + base + 4 * c4) = tot;
+        if (dx_bf16) st4_bf16(dx_bf16 + base + 4 * c4, bf16_total ? tot : o);
+      }
+    }
+  }
+  // block reduction of the column sums, then one atomic per column per block
+  if (dgamma || dbeta) {
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c4 = lane + i * 32;  // uniform guard across warps
+      if (i * 32 >= nv) break;
+      for (int pass = 0; pass < 2; ++pass) {
+        const float4 val = pass == 0 ? dg[i] : db[i];
+        __syncthreads();
+        red[warp][lane * 4 + 0] = val.x;
+        red[warp][lane * 4 + 1] = val.y;
+        red[warp][lane * 4 + 2] = val.z;
+        red[warp][lane * 4 + 3] = val.w;
+        __syncthreads();
+        if (threadIdx.x < 128) {
+          float s = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+          const int col = 4 * (i * 32 + (threadIdx.x >> 2)) + (threadIdx.x & 3);
+          float* dst = pass == 0 ? dgamma : dbeta;
+          if (dst && col < C) atomicAdd(dst + col, s);
+        }
+      }
+      (void)c4;
+    }
+  }
+}
+
+}  // namespace egv
+
+using namespace egv;
+
+extern "C" int egv_layernorm_fwd(const void* x, int x_is_bf16, const float* gamma, const float* beta, float eps,
+                                 int64_t rows, int C, void* y_bf16, float* y_f32, float* mean, float* rstd,
+                                 egv_stream_t stream) {
+  if (!x || !gamma || !beta || (!y_bf16 && !y_f32)) return fail(EGV_ERR_ARG, "layernorm_fwd: null pointer");
+  if (C % 4 || C > 128 * LN_MAXV || C <= 0) return fail(EGV_ERR_UNSUPPORTED, "layernorm: C=%d must be a multiple of 4 and <= 1024", C);
+  if (rows <= 0) return EGV_OK;
+  long long blocks = cdiv(rows, 8);
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (x_is_bf16)
+    ln_fwd_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, rows, C, (bf16*)y_bf16, y_f32, mean, rstd);
+  else
+    ln_fwd_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, rows, C, (bf16*)y_bf16, y_f32, mean, rstd);
+  return check_launch("ln_fwd_kernel");
+}
+
+extern "C" int egv_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_bf16, const float* gamma,
+                                 const float* mean, const float* rstd, int64_t rows, int C, const float* add, float* dx,
+                                 void* dx_bf16, int bf16_total, float* dgamma, float* dbeta, egv_stream_t stream) {
+  if (!dy || !x || !gamma || !mean || !rstd) return fail(EGV_ERR_ARG, "layernorm_bwd: null pointer");
+  if (C % 4 || C > 128 * LN_MAXV || C <= 0) return fail(EGV_ERR_UNSUPPORTED, "layernorm: C=%d must be a multiple of 4 and <= 1024", C);
+  if (rows <= 0) return EGV_OK;
+  long long blocks = cdiv(rows, 8 * 8);  // >= 8 rows per warp amortises the column-sum atomics
+  const long long cap = (long long)sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cudaStream_t s = (cudaStream_t)stream;
+#define EGV_LN_BWD(DYB, XB) \
+  ln_bwd_kernel<DYB, XB><<<(unsigned)blocks, 256, 0, s>>>(dy, x, gamma, mean, rstd, rows, C, add, dx, bf16_total, (bf16*)dx_bf16, dgamma, dbeta)
+  if (dy_is_bf16 && x_is_bf16) EGV_LN_BWD(true, true);
+  else if (dy_is_bf16) EGV_LN_BWD(true, false);
+  else if (x_is_bf16) EGV_LN_BWD(false, true);
+  else EGV_LN_BWD(false, false);
+#undef EGV_LN_BWD
+  return check_launch("ln_bwd_kernel");
+}

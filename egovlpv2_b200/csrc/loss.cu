@@ -1,0 +1,253 @@
+// Losses of the pre-training step: softmax cross-entropy with ignore_index (MLM / ITM) and EgoNCE
+// (sim_matrix + positives mask + two-direction InfoNCE) with their gradients.  All fp32.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace egv {
+
+template <int NT>
+EGV_DEVINL float block_max(float v, float* red) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < NT / 32; ++i) r = fmaxf(r, red[i]);
+  __syncthreads();
+  return r;
+}
+template <int NT>
+EGV_DEVINL float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < NT / 32; ++i) r += red[i];
+  __syncthreads();
+  return r;
+}
+
+// one block per row: loss_sum += lse - logit[label], count += 1, dlogits = softmax - onehot (0 for ignored rows)
+__global__ void __launch_bounds__(256) xent_kernel(const float* __restrict__ logits, long long ld,
+                                                   const long long* __restrict__ labels, int V, int ignore_index,
+                                                   float* __restrict__ loss_sum, float* __restrict__ count,
+                                                   bf16* __restrict__ dlogits, long long ld_d) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  const long long label = labels[row];
+  const float* x = logits + row * ld;
+  bf16* d = dlogits ? dlogits + row * ld_d : nullptr;
+  if (label == ignore_index) {
+    if (d) for (int c = threadIdx.x; c < V; c += 256) d[c] = __float2bfloat16(0.f);
+    return;
+  }
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < V; c += 256) mx = fmaxf(mx, x[c]);
+  mx = block_max<256>(mx, red);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < V; c += 256) s += __expf(x[c] - mx);
+  s = block_sum<256>(s, red);
+  const float lse = mx + logf(s);
+  if (threadIdx.x == 0) {
+    atomicAdd(loss_sum, lse - x[label]);
+    atomicAdd(count, 1.0f);
+  }
+  if (d) {
+    const float inv = 1.0f / s;
+    for (int c = threadIdx.x; c < V; c += 256) {
+      float p = __expf(x[c] - mx) * inv;
+      if (c == label) p -= 1.0f;
+      d[c] = __float2bfloat16(p);
+    }
+  }
+}
+
+// loss = loss_sum / max(count,1); inv_count = 1 / max(count,1)
+__global__ void xent_finalize_kernel(const float* loss_sum, const float* count, float* loss, float* inv_count) {
+  const float c = fmaxf(count[0], 1.0f);
+  if (loss) loss[0] = loss_sum[0] / c;
+  if (inv_count) inv_count[0] = 1.0f / c;
+}
+
+// ------------------------------------------------------------------------------------------- EgoNCE
+// xn = x / max(||x||, eps); inv[i] = 1 / max(||x_i||, eps)
+__global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ x, int P, float eps, float* __restrict__ xn,
+                                                      float* __restrict__ inv) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  float s = 0.f;
+  for (int p = threadIdx.x; p < P; p += 256) {
+    const float v = x[row * P + p];
+    s = fmaf(v, v, s);
+  }
+  s = block_sum<256>(s, red);
+  const float r = 1.0f / fmaxf(sqrtf(s), eps);
+  if (threadIdx.x == 0 && inv) inv[row] = r;
+  for (int p = threadIdx.x; p < P; p += 256) xn[row * P + p] = x[row * P + p] * r;
+}
+
+// out[i, j] = sum_p a[i,p] * b[j,p]; one warp per (i,j)
+__global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, int Ga, int Gb,
+                                                     int P, float* __restrict__ out) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w >= Ga * Gb) return;
+  const int i = w / Gb, j = w % Gb;
+  float s = 0.f;
+  for (int p = threadIdx.x & 31; p < P; p += 32) s = fmaf(a[(long long)i * P + p], b[(long long)j * P + p], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) out[w] = s;
+}
+
+// single block. sim [G,G] rows=text. mask_ij = (simv_ij*simn_ij + delta_ij) > 0.
+// loss = -mean_i log sum_j M_ij softmax_j(sim_i./tau) - mean_i log sum_j M_ij softmax_j(sim_.i/tau)
+// dsim = dloss/dsim.
+__global__ void __launch_bounds__(256) egonce_loss_kernel(const float* __restrict__ sim, const float* __restrict__ simv,
+                                                          const float* __restrict__ simn, int G, float tau,
+                                                          uint8_t* __restrict__ mask, float* __restrict__ loss,
+                                                          float* __restrict__ dsim) {
+  __shared__ float red[8];
+  const float it = 1.0f / tau;
+  for (int e = threadIdx.x; e < G * G; e += 256) {
+    const int i = e / G, j = e % G;
+    const float m = simv[e] * simn[e] + (i == j ? 1.0f : 0.0f);
+    mask[e] = m > 0.0f ? 1 : 0;
+    dsim[e] = 0.f;
+  }
+  __syncthreads();
+  float part = 0.f;
+  // row direction: thread i owns row i
+  for (int i = threadIdx.x; i < G; i += 256) {
+    float mx = -INFINITY;
+    for (int j = 0; j < G; ++j) mx = fmaxf(mx, sim[i * G + j] * it);
+    float z = 0.f, a = 0.f;
+    for (int j = 0; j < G; ++j) {
+      const float ex = __expf(sim[i * G + j] * it - mx);
+      z += ex;
+      if (mask[i * G + j]) a += ex;
+    }
+    part -= logf(a / z);
+    for (int j = 0; j < G; ++j) {
+      const float ex = __expf(sim[i * G + j] * it - mx);
+      const float p = ex / z;
+      const float gr = p - (mask[i * G + j] ? ex / a : 0.f);
+      dsim[i * G + j] += gr * it / G;  // row i only touched by this thread in this phase
+    }
+  }
+  __syncthreads();
+  // column direction: thread i owns column i of sim (row i of sim^T); mask indexed [i][j] as in the reference
+  for (int i = threadIdx.x; i < G; i += 256) {
+    float mx = -INFINITY;
+    for (int j = 0; j < G; ++j) mx = fmaxf(mx, sim[j * G + i] * it);
+    float z = 0.f, a = 0.f;
+    for (int j = 0; j < G; ++j) {
+      const float ex = __expf(sim[j * G + i] * it - mx);
+      z += ex;
+      if (mask[i * G + j]) a += ex;
+    }
+    part -= logf(a / z);
+    for (int j = 0; j < G; ++j) {
+      const float ex = __expf(sim[j * G + i] * it - mx);
+      const float p = ex / z;
+      const float gr = p - (mask[i * G + j] ? ex / a : 0.f);
+      dsim[j * G + i] += gr * it / G;  // column i only touched by this thread in this phase
+    }
+  }
+  part = block_sum<256>(part, red);
+  if (threadIdx.x == 0) loss[0] = part / G;
+}
+
+// block (r, which): which=0 -> d t[row0+r] ; which=1 -> d v[row0+r].  Back-propagates through the L2 normalisation.
+__global__ void __launch_bounds__(256) egonce_grad_kernel(const float* __restrict__ dsim, const float* __restrict__ tn,
+                                                          const float* __restrict__ vn, const float* __restrict__ inv_t,
+                                                          const float* __restrict__ inv_v, int G, int P, int row0,
+                                                          float* __restrict__ dt, float* __restrict__ dv) {
+  __shared__ float red[8];
+  extern __shared__ float coef[];  // G coefficients
+  const int r = blockIdx.x, which = blockIdx.y;
+  const int i = row0 + r;
+  for (int j = threadIdx.x; j < G; j += 256) coef[j] = which == 0 ? dsim[i * G + j] : dsim[j * G + i];
+  __syncthreads();
+  const float* other = which == 0 ? vn : tn;
+  const float* self = which == 0 ? tn : vn;
+  float* out = which == 0 ? dt : dv;
+  if (!out) return;
+  const float inv = which == 0 ? inv_t[i] : inv_v[i];
+  float dot = 0.f;
+  for (int p = threadIdx.x; p < P; p += 256) {
+    float g = 0.f;
+    for (int j = 0; j < G; ++j) g = fmaf(coef[j], other[(long long)j * P + p], g);
+    out[(long long)r * P + p] = g;
+    dot = fmaf(g, self[(long long)i * P + p], dot);
+  }
+  dot = block_sum<256>(dot, red);
+  for (int p = threadIdx.x; p < P; p += 256) {
+    const float g = out[(long long)r * P + p];
+    out[(long long)r * P + p] = inv * (g - self[(long long)i * P + p] * dot);
+  }
+}
+
+}  // namespace egv
+
+using namespace egv;
+
+extern "C" int egv_softmax_xent(const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int V, int ignore_index,
+                                float* loss_sum, float* count, void* dlogits_bf16, int64_t ld_d, egv_stream_t stream) {
+  if (!logits || !labels || !loss_sum || !count) return fail(EGV_ERR_ARG, "softmax_xent: null pointer");
+  if (rows <= 0) return EGV_OK;
+  xent_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, (const long long*)labels, V, ignore_index, loss_sum,
+                                                                 count, (bf16*)dlogits_bf16, ld_d);
+  return check_launch("xent_kernel");
+}
+
+extern "C" int egv_xent_finalize(const float* loss_sum, const float* count, float* loss, float* inv_count, egv_stream_t stream) {
+  if (!loss_sum || !count) return fail(EGV_ERR_ARG, "xent_finalize: null pointer");
+  xent_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(loss_sum, count, loss, inv_count);
+  return check_launch("xent_finalize_kernel");
+}
+
+extern "C" int64_t egv_egonce_scratch_floats(int G, int P, int Dn, int Dv) {
+  return 2ll * G * P + 2ll * G + (long long)G * Dn + (long long)G * Dv + 3ll * G * G;
+}
+
+extern "C" int egv_egonce(const float* t, const float* v, int G, int P, const float* noun, int Dn, const float* verb, int Dv,
+                          float temperature, float* sim, uint8_t* mask, float* loss, int grad_row0, int grad_rows, float* dt,
+                          float* dv, float* scratch, egv_stream_t stream) {
+  if (!t || !v || !noun || !verb || !sim || !mask || !loss || !scratch) return fail(EGV_ERR_ARG, "egonce: null pointer");
+  if (G <= 0 || P <= 0 || G > 4096) return fail(EGV_ERR_ARG, "egonce: bad sizes");
+  if (grad_rows < 0 || grad_row0 < 0 || grad_row0 + grad_rows > G) return fail(EGV_ERR_ARG, "egonce: bad gradient row range");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* tn = scratch;
+  float* vn = tn + (long long)G * P;
+  float* inv_t = vn + (long long)G * P;
+  float* inv_v = inv_t + G;
+  float* nn = inv_v + G;
+  float* vb = nn + (long long)G * Dn;
+  float* simv = vb + (long long)G * Dv;
+  float* simn = simv + (long long)G * G;
+  float* dsim = simn + (long long)G * G;
+  int rc;
+  rownorm_kernel<<<G, 256, 0, s>>>(t, P, 1e-8f, tn, inv_t);
+  if ((rc = check_launch("rownorm_kernel"))) return rc;
+  rownorm_kernel<<<G, 256, 0, s>>>(v, P, 1e-8f, vn, inv_v);
+  if ((rc = check_launch("rownorm_kernel"))) return rc;
+  rownorm_kernel<<<G, 256, 0, s>>>(noun, Dn, 1e-8f, nn, nullptr);
+  if ((rc = check_launch("rownorm_kernel"))) return rc;
+  rownorm_kernel<<<G, 256, 0, s>>>(verb, Dv, 1e-8f, vb, nullptr);
+  if ((rc = check_launch("rownorm_kernel"))) return rc;
+  const unsigned gb = (unsigned)cdiv((long long)G * G, 8);
+  rowdot_kernel<<<gb, 256, 0, s>>>(tn, vn, G, G, P, sim);
+  if ((rc = check_launch("rowdot_kernel"))) return rc;
+  rowdot_kernel<<<gb, 256, 0, s>>>(nn, nn, G, G, Dn, simn);
+  if ((rc = check_launch("rowdot_kernel"))) return rc;
+  rowdot_kernel<<<gb, 256, 0, s>>>(vb, vb, G, G, Dv, simv);
+  if ((rc = check_launch("rowdot_kernel"))) return rc;
+  egonce_loss_kernel<<<1, 256, 0, s>>>(sim, simv, simn, G, temperature, mask, loss, dsim);
+  if ((rc = check_launch("egonce_loss_kernel"))) return rc;
+  if (grad_rows > 0 && (dt || dv)) {
+    dim3 grid((unsigned)grad_rows, 2);
+    egonce_grad_kernel<<<grid, 256, G * sizeof(float), s>>>(dsim, tn, vn, inv_t, inv_v, G, P, grad_row0, dt, dv);
+    if ((rc = check_launch("egonce_grad_kernel"))) return rc;
+  }
+  return EGV_OK;
+}

@@ -1,0 +1,426 @@
+// Library globals + the HBM-bound helper kernels of the path: casts, column sums (bias gradients), dot products
+// (gate gradients), axpy, im2col / token assembly for the patch embedding, RoBERTa embedding gather, AdamW.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace egv {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+static inline unsigned grid_for(long long work_items, int per_block, int max_waves = 16) {
+  long long b = cdiv(work_items, per_block);
+  const long long cap = (long long)sm_count() * max_waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+// ------------------------------------------------------------------------------------------- casts
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    uint2 u;
+    u.x = pack_bf16(v.x, v.y);
+    u.y = pack_bf16(v.z, v.w);
+    reinterpret_cast<uint2*>(y)[i] = u;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __float2bfloat16(x[i]);
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint2 u = reinterpret_cast<const uint2*>(x)[i];
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+    reinterpret_cast<float4*>(y)[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __bfloat162float(x[i]);
+}
+
+// y = a + alpha * (alpha_dev ? *alpha_dev : 1) * b ; writes f32 and/or bf16.  a may be NULL (treated as 0).
+__global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha,
+                                                   const float* __restrict__ alpha_dev, float* __restrict__ y,
+                                                   bf16* __restrict__ y_bf16, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float al = alpha * (alpha_dev ? __ldg(alpha_dev) : 1.0f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = (a ? a[i] : 0.0f) + al * b[i];
+    if (y) y[i] = v;
+    if (y_bf16) y_bf16[i] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- column sum
+// out[c] (+)= scale * sum_r x[r, c].  Block = 64 columns x 8 row lanes; grid.y splits the rows; fp32 atomics.
+template <bool XBF>
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x, long long rows, int C, long long ld,
+                                                     float* __restrict__ out, float scale,
+                                                     const float* __restrict__ scale_dev) {
+  __shared__ float red[8][65];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 64 + 2 * tx;
+  float s0 = 0.f, s1 = 0.f;
+  const bool pair_ok = (c0 + 1 < C) && ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & (XBF ? 3 : 7)) == 0);
+  for (long long r = (long long)blockIdx.y * 8 + ty; r < rows; r += (long long)gridDim.y * 8) {
+    if (pair_ok) {
+      if (XBF) {
+        const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(reinterpret_cast<const bf16*>(x) + r * ld + c0));
+        s0 += v.x;
+        s1 += v.y;
+      } else {
+        const float2 v = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(x) + r * ld + c0);
+        s0 += v.x;
+        s1 += v.y;
+      }
+    } else {
+      if (c0 < C) s0 += XBF ? __bfloat162float(reinterpret_cast<const bf16*>(x)[r * ld + c0]) : reinterpret_cast<const float*>(x)[r * ld + c0];
+      if (c0 + 1 < C) s1 += XBF ? __bfloat162float(reinterpret_cast<const bf16*>(x)[r * ld + c0 + 1]) : reinterpret_cast<const float*>(x)[r * ld + c0 + 1];
+    }
+  }
+  red[ty][2 * tx] = s0;
+  red[ty][2 * tx + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < C) atomicAdd(out + c, s * scale * (scale_dev ? __ldg(scale_dev) : 1.0f));
+  }
+}
+
+template <bool DYBF>
+__global__ void __launch_bounds__(256) act_grad_kernel(const void* __restrict__ dy, const bf16* __restrict__ aux, int act,
+                                                       float scale, const float* __restrict__ scale_dev,
+                                                       bf16* __restrict__ out, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.0f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = DYBF ? __bfloat162float(reinterpret_cast<const bf16*>(dy)[i]) : reinterpret_cast<const float*>(dy)[i];
+    if (act != EGV_ACT_NONE) {
+      const float a = __bfloat162float(aux[i]);
+      if (act == EGV_ACT_GELU_BWD) v *= gelu_erf_grad(a);
+      else if (act == EGV_ACT_RELU_BWD) v = a > 0.f ? v : 0.f;
+      else if (act == EGV_ACT_TANH_BWD) v *= (1.0f - a * a);
+    }
+    out[i] = __float2bfloat16(v * sc);
+  }
+}
+
+__global__ void zero_f32_kernel(float* p, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------- dot
+template <bool ABF, bool BBF>
+__global__ void __launch_bounds__(256) dot_kernel(const void* __restrict__ a, const void* __restrict__ b, long long n,
+                                                  float* __restrict__ out) {
+  __shared__ float red[8];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = ABF ? __bfloat162float(reinterpret_cast<const bf16*>(a)[i]) : reinterpret_cast<const float*>(a)[i];
+    const float y = BBF ? __bfloat162float(reinterpret_cast<const bf16*>(b)[i]) : reinterpret_cast<const float*>(b)[i];
+    s = fmaf(x, y, s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    s = red[threadIdx.x];
+    s += __shfl_xor_sync(0xffu, s, 4);
+    s += __shfl_xor_sync(0xffu, s, 2);
+    s += __shfl_xor_sync(0xffu, s, 1);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- patch embedding
+// im2col for a stride-p, kernel-p convolution: out[(bt*gh+gy)*gw+gx, c*p*p + i*p + j] = video[bt, c, gy*p+i, gx*p+j]
+// One thread moves 8 contiguous pixels (32 B read, 16 B write); threads walk the image row-major -> coalesced reads.
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ video, int BT, int Cin, int H, int W,
+                                                       int p, bf16* __restrict__ out) {
+  const int gw = W / p, gh = H / p;
+  const int w8 = W >> 3;
+  const long long total = (long long)BT * Cin * H * w8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int Kc = Cin * p * p;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int xc = (int)(i % w8);
+    long long r = i / w8;
+    const int y = (int)(r % H);
+    r /= H;
+    const int c = (int)(r % Cin);
+    const int bt = (int)(r / Cin);
+    const int x = xc << 3;
+    const float4* src = reinterpret_cast<const float4*>(video + (((long long)bt * Cin + c) * H + y) * W + x);
+    const float4 a = src[0], b = src[1];
+    const int gy = y / p, iy = y % p, gx = x / p, jx = x % p;
+    uint4 u;
+    u.x = pack_bf16(a.x, a.y);
+    u.y = pack_bf16(a.z, a.w);
+    u.z = pack_bf16(b.x, b.y);
+    u.w = pack_bf16(b.z, b.w);
+    bf16* dst = out + (((long long)bt * gh + gy) * gw + gx) * Kc + (c * p + iy) * p + jx;
+    *reinterpret_cast<uint4*>(dst) = u;
+  }
+}
+
+// tokens[b,0] = cls + pos[0]; tokens[b,1+f*Nf+n] = patch[(b*T+f)*Nf+n] + pos[1+n] + temporal[f]
+__global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+                                                              const float* __restrict__ pos, const float* __restrict__ temporal,
+                                                              int B, int T, int Nf, int C, float* __restrict__ tokens) {
+  const int c4n = C >> 2;
+  const long long N = 1 + (long long)T * Nf;
+  const long long total = (long long)B * N * c4n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c4 = (int)(i % c4n);
+    const long long tok = i / c4n;
+    const int n = (int)(tok % N);
+    const int b = (int)(tok / N);
+    float4 v;
+    if (n == 0) {
+      const float4 a = reinterpret_cast<const float4*>(cls)[c4], q = reinterpret_cast<const float4*>(pos)[c4];
+      v = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+    } else {
+      const int f = (n - 1) / Nf, pn = (n - 1) % Nf;
+      const float4 a = reinterpret_cast<const float4*>(patch)[(((long long)b * T + f) * Nf + pn) * c4n + c4];
+      const float4 q = reinterpret_cast<const float4*>(pos)[(long long)(1 + pn) * c4n + c4];
+      const float4 t = reinterpret_cast<const float4*>(temporal)[(long long)f * c4n + c4];
+      v = make_float4(a.x + q.x + t.x, a.y + q.y + t.y, a.z + q.z + t.z, a.w + q.w + t.w);
+    }
+    reinterpret_cast<float4*>(tokens)[i] = v;
+  }
+}
+
+// backward: d_patch (bf16) = d_tokens[:,1:]; d_cls / d_pos[0] += sum_b d_tokens[b,0];
+// d_pos[1+n] += sum_{b,f}; d_temporal[f] += sum_{b,n} (atomics: one per (block, f, c)).
+// grid.x = 1 + Nf reduction rows, threads over C.
+__global__ void __launch_bounds__(256) assemble_tokens_bwd_kernel(const float* __restrict__ d_tokens, int B, int T, int Nf,
+                                                                  int C, bf16* __restrict__ d_patch, float* __restrict__ d_cls,
+                                                                  float* __restrict__ d_pos, float* __restrict__ d_temporal) {
+  const long long N = 1 + (long long)T * Nf;
+  const int job = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (job == 0) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += d_tokens[(long long)b * N * C + c];
+      if (d_cls) d_cls[c] += s;
+      if (d_pos) d_pos[c] += s;
+    } else {
+      const int n = job - 1;
+      float s = 0.f;
+      for (int f = 0; f < T; ++f) {
+        float sf = 0.f;
+        for (int b = 0; b < B; ++b) {
+          const float v = d_tokens[((long long)b * N + 1 + (long long)f * Nf + n) * C + c];
+          sf += v;
+          if (d_patch) d_patch[(((long long)b * T + f) * Nf + n) * C + c] = __float2bfloat16(v);
+        }
+        s += sf;
+        if (d_temporal) atomicAdd(d_temporal + (long long)f * C + c, sf);
+      }
+      if (d_pos) d_pos[(long long)(1 + n) * C + c] += s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- RoBERTa embeddings
+// position id = (number of non-pad tokens up to and including s) * nonpad + pad_id   (roberta.py:881-892)
+__global__ void __launch_bounds__(128) text_embed_kernel(const long long* __restrict__ ids, int B, int S, int C, int pad_id,
+                                                         const float* __restrict__ word, const float* __restrict__ pos,
+                                                         const float* __restrict__ type0, float* __restrict__ out) {
+  const int tok = blockIdx.x;
+  const int b = tok / S, s = tok % S;
+  const long long id = ids[tok];
+  int cnt = 0;
+  for (int j = 0; j <= s; ++j) cnt += ids[b * S + j] != pad_id;
+  const long long pid = (id != pad_id) ? cnt + pad_id : pad_id;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    out[(long long)tok * C + c] = word[id * C + c] + pos[pid * C + c] + type0[c];
+}
+__global__ void __launch_bounds__(128) text_embed_bwd_kernel(const float* __restrict__ d_out, const long long* __restrict__ ids,
+                                                             int B, int S, int C, int pad_id, float* __restrict__ d_word,
+                                                             float* __restrict__ d_pos) {
+  const int tok = blockIdx.x;
+  const int b = tok / S, s = tok % S;
+  const long long id = ids[tok];
+  int cnt = 0;
+  for (int j = 0; j <= s; ++j) cnt += ids[b * S + j] != pad_id;
+  const long long pid = (id != pad_id) ? cnt + pad_id : pad_id;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = d_out[(long long)tok * C + c];
+    if (d_word) atomicAdd(d_word + id * C + c, g);
+    if (d_pos) atomicAdd(d_pos + pid * C + c, g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- AdamW (HF semantics)
+// transformers.AdamW (set_optim_schedule.py:108): eps added to sqrt(v) BEFORE bias correction, decoupled decay
+// applied after the Adam update with the already-updated parameter.  Also refreshes the bf16 operand copy.
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, bf16* __restrict__ p_bf16, long long n, float lr,
+                                                    float beta1, float beta2, float eps, float wd, float bias_c1, float bias_c2,
+                                                    float grad_scale) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float step = lr * sqrtf(bias_c2) / bias_c1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * grad_scale;
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    float pi = p[i] - step * mi / (sqrtf(vi) + eps);
+    pi -= lr * wd * pi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi;
+    if (p_bf16) p_bf16[i] = __float2bfloat16(pi);
+  }
+}
+
+}  // namespace egv
+
+using namespace egv;
+
+extern "C" int egv_version(void) { return 100; }
+extern "C" const char* egv_last_error(void) { return g_err; }
+extern "C" long long egv_launch_count(void) { return g_launches.load(); }
+extern "C" int egv_device_sm_count(void) { return sm_count(); }
+
+extern "C" int egv_cast_f32_bf16(const float* x, void* y, int64_t n, egv_stream_t stream) {
+  if (n <= 0) return EGV_OK;
+  if (!x || !y) return fail(EGV_ERR_ARG, "cast: null pointer");
+  if ((((uintptr_t)x) & 15) || (((uintptr_t)y) & 7)) return fail(EGV_ERR_ARG, "cast: unaligned pointer");
+  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, n);
+  return check_launch("cast_f32_bf16_kernel");
+}
+extern "C" int egv_cast_bf16_f32(const void* x, float* y, int64_t n, egv_stream_t stream) {
+  if (n <= 0) return EGV_OK;
+  if (!x || !y) return fail(EGV_ERR_ARG, "cast: null pointer");
+  if ((((uintptr_t)y) & 15) || (((uintptr_t)x) & 7)) return fail(EGV_ERR_ARG, "cast: unaligned pointer");
+  cast_bf16_f32_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, y, n);
+  return check_launch("cast_bf16_f32_kernel");
+}
+extern "C" int egv_axpy_f32(const float* a, const float* b, float alpha, const float* alpha_dev, float* y, void* y_bf16,
+                            int64_t n, egv_stream_t stream) {
+  if (n <= 0) return EGV_OK;
+  if (!b || (!y && !y_bf16)) return fail(EGV_ERR_ARG, "axpy: null pointer");
+  axpy_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(a, b, alpha, alpha_dev, y, (bf16*)y_bf16, n);
+  return check_launch("axpy_kernel");
+}
+extern "C" int egv_zero_f32(float* p, int64_t n, egv_stream_t stream) {
+  if (n <= 0) return EGV_OK;
+  if (!p) return fail(EGV_ERR_ARG, "zero: null pointer");
+  zero_f32_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(p, n);
+  return check_launch("zero_f32_kernel");
+}
+
+extern "C" int egv_act_grad(const void* dy, int dy_is_bf16, const void* aux_bf16, int act, float scale, const float* scale_dev,
+                            void* out_bf16, int64_t n, egv_stream_t stream) {
+  if (n <= 0) return EGV_OK;
+  if (!dy || !out_bf16) return fail(EGV_ERR_ARG, "act_grad: null pointer");
+  if (act != EGV_ACT_NONE && (act < EGV_ACT_GELU_BWD || act > EGV_ACT_TANH_BWD || !aux_bf16))
+    return fail(EGV_ERR_ARG, "act_grad: act must be NONE or a *_BWD code with aux");
+  if (dy_is_bf16)
+    act_grad_kernel<true><<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(dy, (const bf16*)aux_bf16, act, scale, scale_dev, (bf16*)out_bf16, n);
+  else
+    act_grad_kernel<false><<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(dy, (const bf16*)aux_bf16, act, scale, scale_dev, (bf16*)out_bf16, n);
+  return check_launch("act_grad_kernel");
+}
+
+extern "C" int egv_colsum(const void* x, int x_is_bf16, int64_t rows, int C, int64_t ld, float* out, int accumulate,
+                          float scale, const float* scale_dev, egv_stream_t stream) {
+  if (!x || !out || C <= 0) return fail(EGV_ERR_ARG, "colsum: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!accumulate) {
+    zero_f32_kernel<<<grid_for(C, 256), 256, 0, s>>>(out, C);
+    int rc = check_launch("zero_f32_kernel");
+    if (rc) return rc;
+  }
+  if (rows <= 0) return EGV_OK;
+  const unsigned gx = (unsigned)cdiv(C, 64);
+  long long gy = cdiv(rows, 8 * 16);
+  const long long cap = cdiv((long long)sm_count() * 8, gx);
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  dim3 grid(gx, (unsigned)gy);
+  if (x_is_bf16) colsum_kernel<true><<<grid, 256, 0, s>>>(x, rows, C, ld, out, scale, scale_dev);
+  else colsum_kernel<false><<<grid, 256, 0, s>>>(x, rows, C, ld, out, scale, scale_dev);
+  return check_launch("colsum_kernel");
+}
+
+extern "C" int egv_dot(const void* a, int a_is_bf16, const void* b, int b_is_bf16, int64_t n, float* out, int accumulate,
+                       egv_stream_t stream) {
+  if (!a || !b || !out) return fail(EGV_ERR_ARG, "dot: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!accumulate) {
+    zero_f32_kernel<<<1, 32, 0, s>>>(out, 1);
+    int rc = check_launch("zero_f32_kernel");
+    if (rc) return rc;
+  }
+  if (n <= 0) return EGV_OK;
+  const unsigned grid = grid_for(n, 256 * 8, 4);
+  if (a_is_bf16 && b_is_bf16) dot_kernel<true, true><<<grid, 256, 0, s>>>(a, b, n, out);
+  else if (a_is_bf16) dot_kernel<true, false><<<grid, 256, 0, s>>>(a, b, n, out);
+  else if (b_is_bf16) dot_kernel<false, true><<<grid, 256, 0, s>>>(a, b, n, out);
+  else dot_kernel<false, false><<<grid, 256, 0, s>>>(a, b, n, out);
+  return check_launch("dot_kernel");
+}
+
+extern "C" int egv_patchify(const float* video, int BT, int Cin, int H, int W, int p, void* out_bf16, egv_stream_t stream) {
+  if (!video || !out_bf16) return fail(EGV_ERR_ARG, "patchify: null pointer");
+  if (p % 8 || H % p || W % p || W % 8) return fail(EGV_ERR_UNSUPPORTED, "patchify: patch size must be a multiple of 8 and divide H, W");
+  if ((((uintptr_t)video) & 15) || (((uintptr_t)out_bf16) & 15)) return fail(EGV_ERR_ARG, "patchify: unaligned pointer");
+  const long long total = (long long)BT * Cin * H * (W / 8);
+  patchify_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(video, BT, Cin, H, W, p, (bf16*)out_bf16);
+  return check_launch("patchify_kernel");
+}
+
+extern "C" int egv_assemble_tokens(const float* patch, const float* cls, const float* pos, const float* temporal, int B,
+                                   int T, int Nf, int C, float* tokens, egv_stream_t stream) {
+  if (!patch || !cls || !pos || !temporal || !tokens) return fail(EGV_ERR_ARG, "assemble_tokens: null pointer");
+  if (C % 4) return fail(EGV_ERR_UNSUPPORTED, "assemble_tokens: C must be a multiple of 4");
+  const long long total = (long long)B * (1 + (long long)T * Nf) * (C / 4);
+  assemble_tokens_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(patch, cls, pos, temporal, B, T, Nf, C, tokens);
+  return check_launch("assemble_tokens_kernel");
+}
+
+extern "C" int egv_assemble_tokens_bwd(const float* d_tokens, int B, int T, int Nf, int C, void* d_patch_bf16, float* d_cls,
+                                       float* d_pos, float* d_temporal, egv_stream_t stream) {
+  if (!d_tokens) return fail(EGV_ERR_ARG, "assemble_tokens_bwd: null pointer");
+  assemble_tokens_bwd_kernel<<<1 + Nf, 256, 0, (cudaStream_t)stream>>>(d_tokens, B, T, Nf, C, (bf16*)d_patch_bf16, d_cls,
+                                                                          d_pos, d_temporal);
+  return check_launch("assemble_tokens_bwd_kernel");
+}
+
+extern "C" int egv_text_embed(const int64_t* ids, int B, int S, int C, int pad_id, const float* word, const float* pos,
+                              const float* type0, float* out, egv_stream_t stream) {
+  if (!ids || !word || !pos || !type0 || !out) return fail(EGV_ERR_ARG, "text_embed: null pointer");
+  text_embed_kernel<<<B * S, 128, 0, (cudaStream_t)stream>>>((const long long*)ids, B, S, C, pad_id, word, pos, type0, out);
+  return check_launch("text_embed_kernel");
+}
+
+extern "C" int egv_text_embed_bwd(const float* d_out, const int64_t* ids, int B, int S, int C, int pad_id, float* d_word,
+                                  float* d_pos, float* d_type0, egv_stream_t stream) {
+  if (!d_out || !ids) return fail(EGV_ERR_ARG, "text_embed_bwd: null pointer");
+  text_embed_bwd_kernel<<<B * S, 128, 0, (cudaStream_t)stream>>>(d_out, (const long long*)ids, B, S, C, pad_id, d_word, d_pos);
+  int rc = check_launch("text_embed_bwd_kernel");
+  if (rc || !d_type0) return rc;
+  return egv_colsum(d_out, 0, (int64_t)B * S, C, C, d_type0, 1, 1.0f, nullptr, stream);
+}
+
+extern "C" int egv_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, float bias_c1, float bias_c2, float grad_scale,
+                         egv_stream_t stream) {
+  if (n <= 0) return EGV_OK;
+  if (!p || !g || !m || !v) return fail(EGV_ERR_ARG, "adamw: null pointer");
+  adamw_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)p_bf16, n, lr, beta1, beta2, eps,
+                                                                      weight_decay, bias_c1, bias_c2, grad_scale);
+  return check_launch("adamw_kernel");
+}

@@ -1,0 +1,377 @@
+"""ctypes binding of libegovlp_b200.so (include/egovlp_b200.h) over torch tensors.
+
+torch is used here only for device memory and the current CUDA stream; every method validates its
+tensors, passes raw device pointers through the C ABI and raises on a non-zero return code.  There is
+no CPU fallback: if the library cannot be loaded the import of `Kernels` users fails loudly.
+"""
+import ctypes as C
+import dataclasses
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libegovlp_b200.so")
+
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH, ACT_GELU_BWD, ACT_RELU_BWD, ACT_TANH_BWD = range(7)
+
+c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("layout", c_int), ("M", c_int), ("N", c_int), ("K", c_int),
+                ("A", c_void_p), ("lda", c_int64), ("B", c_void_p), ("ldb", c_int64),
+                ("bias", c_void_p), ("aux", c_void_p), ("ld_aux", c_int64),
+                ("scale_dev", c_void_p), ("scale", c_float),
+                ("residual", c_void_p), ("ld_res", c_int64),
+                ("out_f32", c_void_p), ("ld_out_f32", c_int64),
+                ("out_bf16", c_void_p), ("ld_out_bf16", c_int64),
+                ("out_pre_bf16", c_void_p), ("ld_out_pre", c_int64),
+                ("act", c_int), ("accumulate", c_int), ("split_k", c_int)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("B", c_int), ("H", c_int), ("G", c_int), ("Lq", c_int), ("Lk", c_int),
+                ("q", c_void_p), ("ldq", c_int64), ("q_bstride", c_int64),
+                ("q_row0", c_int), ("q_gstride", c_int), ("q_istride", c_int),
+                ("k", c_void_p), ("v", c_void_p), ("ldkv", c_int64), ("kv_bstride", c_int64),
+                ("k_row0", c_int), ("k_gstride", c_int), ("k_istride", c_int),
+                ("has_cls_key", c_int), ("cls_row", c_int),
+                ("key_bias", c_void_p), ("scale", c_float),
+                ("o", c_void_p), ("ldo", c_int64), ("o_bstride", c_int64),
+                ("lse", c_void_p),
+                ("d_o", c_void_p), ("dq", c_void_p), ("lddq", c_int64),
+                ("dk", c_void_p), ("dv", c_void_p), ("lddkv", c_int64),
+                ("delta", c_void_p), ("dkv_cls", c_void_p), ("dkv_accumulate", c_int)]
+
+
+@dataclasses.dataclass(frozen=True)
+class AttnSpec:
+    """Group addressing of one attention call (see egv_attn_args in include/egovlp_b200.h)."""
+    H: int
+    G: int
+    Lq: int
+    Lk: int                 # regular keys per group (the shared CLS key is extra)
+    q_row0: int = 0
+    q_gstride: int = 0
+    q_istride: int = 1
+    k_row0: int = 0
+    k_gstride: int = 0
+    k_istride: int = 1
+    has_cls_key: bool = False
+    cls_row: int = 0
+    scale: float = 1.0
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "egovlpv2_b200: %s is missing -- build it with `python -m egovlpv2_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.egv_last_error.restype = C.c_char_p
+    lib.egv_launch_count.restype = C.c_longlong
+    lib.egv_egonce_scratch_floats.restype = c_int64
+    return lib
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk2d(t, dtype, name):
+    if t.dim() != 2 or t.stride(1) != 1 or t.dtype != dtype or not t.is_cuda:
+        raise ValueError("%s: expected 2-D %s CUDA tensor with unit inner stride, got %s %s %s" %
+                         (name, dtype, tuple(t.shape), t.stride(), t.dtype))
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+class Kernels:
+    """The device kernels of the hot path.  One instance per process (CUDA context of the current device)."""
+
+    def __init__(self):
+        self.lib = _load()
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("egovlp_b200 kernel error %d: %s" % (rc, self.lib.egv_last_error().decode()))
+
+    def launch_count(self):
+        return int(self.lib.egv_launch_count())
+
+    def sm_count(self):
+        return int(self.lib.egv_device_sm_count())
+
+    def force_simt(self, on):
+        self.lib.egv_gemm_force_simt(int(bool(on)))
+
+    # ------------------------------------------------------------------ GEMM
+    def gemm(self, layout, A, B, *, bias=None, aux=None, act=ACT_NONE, scale=1.0, scale_dev=None,
+             residual=None, out_f32=None, out_bf16=None, out_pre=None, accumulate=False, split_k=1):
+        lda = _chk2d(A, torch.bfloat16, "A")
+        ldb = _chk2d(B, torch.bfloat16, "B")
+        if layout == GEMM_NT:
+            (M, K), (N, K2) = A.shape, B.shape
+        elif layout == GEMM_NN:
+            (M, K), (K2, N) = A.shape, B.shape
+        else:
+            (K, M), (K2, N) = A.shape, B.shape
+        if K != K2:
+            raise ValueError("gemm: inner dimensions differ (%d vs %d)" % (K, K2))
+        a = GemmArgs()
+        a.layout, a.M, a.N, a.K = layout, M, N, K
+        a.A, a.lda, a.B, a.ldb = _p(A), lda, _p(B), ldb
+        if bias is not None:
+            assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+            a.bias = _p(bias)
+        for name, t, dt in (("aux", aux, torch.bfloat16), ("residual", residual, torch.float32),
+                            ("out_f32", out_f32, torch.float32), ("out_bf16", out_bf16, torch.bfloat16),
+                            ("out_pre", out_pre, torch.bfloat16)):
+            if t is None:
+                continue
+            ld = _chk2d(t, dt, name)
+            if tuple(t.shape) != (M, N):
+                raise ValueError("gemm: %s has shape %s, expected %s" % (name, tuple(t.shape), (M, N)))
+            if name == "aux":
+                a.aux, a.ld_aux = _p(t), ld
+            elif name == "residual":
+                a.residual, a.ld_res = _p(t), ld
+            elif name == "out_f32":
+                a.out_f32, a.ld_out_f32 = _p(t), ld
+            elif name == "out_bf16":
+                a.out_bf16, a.ld_out_bf16 = _p(t), ld
+            else:
+                a.out_pre_bf16, a.ld_out_pre = _p(t), ld
+        if scale_dev is not None:
+            assert scale_dev.dtype == torch.float32 and scale_dev.numel() == 1
+            a.scale_dev = _p(scale_dev)
+        a.scale = float(scale)
+        a.act, a.accumulate, a.split_k = int(act), int(bool(accumulate)), int(split_k)
+        self._check(self.lib.egv_gemm_bf16(C.byref(a), self._stream()))
+
+    # ------------------------------------------------------------------ LayerNorm
+    def layernorm_fwd(self, x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):
+        Cdim = x.shape[-1]
+        rows = x.numel() // Cdim
+        assert x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
+        for t in (y_bf16, y_f32):
+            assert t is None or (t.is_contiguous() and t.numel() == x.numel())
+        self._check(self.lib.egv_layernorm_fwd(_p(x), int(x.dtype == torch.bfloat16), _p(gamma), _p(beta), c_float(eps),
+                                               c_int64(rows), Cdim, _p(y_bf16), _p(y_f32), _p(mean), _p(rstd),
+                                               self._stream()))
+
+    def layernorm_bwd(self, dy, x, gamma, mean, rstd, add=None, dx=None, dx_bf16=None, bf16_total=True, dgamma=None,
+                      dbeta=None):
+        Cdim = x.shape[-1]
+        rows = x.numel() // Cdim
+        assert dy.is_contiguous() and x.is_contiguous() and dy.numel() == x.numel()
+        for t in (add, dx, dx_bf16):
+            assert t is None or (t.is_contiguous() and t.numel() == x.numel())
+        assert add is None or add.dtype == torch.float32
+        self._check(self.lib.egv_layernorm_bwd(_p(dy), int(dy.dtype == torch.bfloat16), _p(x),
+                                               int(x.dtype == torch.bfloat16), _p(gamma), _p(mean), _p(rstd),
+                                               c_int64(rows), Cdim, _p(add), _p(dx), _p(dx_bf16), int(bool(bf16_total)),
+                                               _p(dgamma), _p(dbeta), self._stream()))
+
+    # ------------------------------------------------------------------ attention
+    @staticmethod
+    def _rows3(t, name):
+        """[B, rows, width] view with unit inner stride -> (ld, batch stride in rows)."""
+        if t.dim() != 3 or t.stride(2) != 1 or t.dtype != torch.bfloat16:
+            raise ValueError("%s: expected [B, rows, W] bf16 view with unit inner stride" % name)
+        ld = t.stride(1)
+        if t.stride(0) % ld:
+            raise ValueError("%s: batch stride is not a whole number of rows" % name)
+        return ld, t.stride(0) // ld
+
+    def _attn_args(self, spec, q, k, v, o, lse, key_bias):
+        a = AttnArgs()
+        a.B, a.H, a.G, a.Lq, a.Lk = q.shape[0], spec.H, spec.G, spec.Lq, spec.Lk
+        a.ldq, a.q_bstride = self._rows3(q, "q")
+        a.ldkv, a.kv_bstride = self._rows3(k, "k")
+        assert self._rows3(v, "v") == (a.ldkv, a.kv_bstride)
+        a.ldo, a.o_bstride = self._rows3(o, "o")
+        a.q, a.k, a.v, a.o, a.lse = _p(q), _p(k), _p(v), _p(o), _p(lse)
+        a.q_row0, a.q_gstride, a.q_istride = spec.q_row0, spec.q_gstride, spec.q_istride
+        a.k_row0, a.k_gstride, a.k_istride = spec.k_row0, spec.k_gstride, spec.k_istride
+        a.has_cls_key, a.cls_row = int(spec.has_cls_key), spec.cls_row
+        a.scale = float(spec.scale)
+        assert lse.dtype == torch.float32 and lse.numel() == a.B * spec.H * spec.G * spec.Lq
+        if key_bias is not None:
+            assert key_bias.dtype == torch.float32 and key_bias.is_contiguous()
+            assert key_bias.numel() == a.B * (spec.Lk + int(spec.has_cls_key))
+            a.key_bias = _p(key_bias)
+        return a
+
+    def attention_fwd(self, spec, q, k, v, o, lse, key_bias=None):
+        a = self._attn_args(spec, q, k, v, o, lse, key_bias)
+        self._check(self.lib.egv_attention_fwd(C.byref(a), self._stream()))
+
+    def attention_bwd(self, spec, q, k, v, o, lse, d_o, dq, dk, dv, delta, dkv_cls=None, dkv_accumulate=False,
+                      key_bias=None):
+        a = self._attn_args(spec, q, k, v, o, lse, key_bias)
+        assert self._rows3(d_o, "d_o") == (a.ldo, a.o_bstride)
+        a.lddq, bq = self._rows3(dq, "dq")
+        assert bq == a.q_bstride
+        a.lddkv, bk = self._rows3(dk, "dk")
+        assert bk == a.kv_bstride and self._rows3(dv, "dv") == (a.lddkv, bk)
+        assert delta.dtype == torch.float32 and delta.numel() == lse.numel()
+        a.d_o, a.dq, a.dk, a.dv, a.delta = _p(d_o), _p(dq), _p(dk), _p(dv), _p(delta)
+        if dkv_cls is not None:
+            assert dkv_cls.dtype == torch.float32 and dkv_cls.numel() == a.B * spec.H * 128
+            a.dkv_cls = _p(dkv_cls)
+        a.dkv_accumulate = int(bool(dkv_accumulate))
+        self._check(self.lib.egv_attention_bwd(C.byref(a), self._stream()))
+
+    def attention_cls_finalize(self, dkv_cls, dk, dv, H, cls_row=0, accumulate=False):
+        ld, bs = self._rows3(dk, "dk")
+        assert self._rows3(dv, "dv") == (ld, bs)
+        self._check(self.lib.egv_attention_cls_finalize(_p(dkv_cls), _p(dk), _p(dv), c_int64(ld), c_int64(bs), cls_row,
+                                                        dk.shape[0], H, int(bool(accumulate)), self._stream()))
+
+    # ------------------------------------------------------------------ elementwise / reductions
+    def cast(self, x, y):
+        assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
+        if x.dtype == torch.float32 and y.dtype == torch.bfloat16:
+            self._check(self.lib.egv_cast_f32_bf16(_p(x), _p(y), c_int64(x.numel()), self._stream()))
+        elif x.dtype == torch.bfloat16 and y.dtype == torch.float32:
+            self._check(self.lib.egv_cast_bf16_f32(_p(x), _p(y), c_int64(x.numel()), self._stream()))
+        else:
+            raise ValueError("cast: unsupported dtypes %s -> %s" % (x.dtype, y.dtype))
+
+    def axpy(self, a, b, alpha=1.0, alpha_dev=None, y=None, y_bf16=None):
+        assert b.dtype == torch.float32 and b.is_contiguous()
+        for t in (a, y):
+            assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == b.numel())
+        assert y_bf16 is None or (y_bf16.dtype == torch.bfloat16 and y_bf16.is_contiguous())
+        self._check(self.lib.egv_axpy_f32(_p(a), _p(b), c_float(alpha), _p(alpha_dev), _p(y), _p(y_bf16),
+                                          c_int64(b.numel()), self._stream()))
+
+    def act_grad(self, dy, aux, act, out_bf16, scale=1.0, scale_dev=None):
+        assert dy.is_contiguous() and out_bf16.is_contiguous() and out_bf16.dtype == torch.bfloat16
+        assert dy.numel() == out_bf16.numel() and (aux is None or (aux.is_contiguous() and aux.dtype == torch.bfloat16))
+        self._check(self.lib.egv_act_grad(_p(dy), int(dy.dtype == torch.bfloat16), _p(aux), int(act), c_float(scale),
+                                          _p(scale_dev), _p(out_bf16), c_int64(dy.numel()), self._stream()))
+
+    def zero(self, p):
+        assert p.dtype == torch.float32 and p.is_contiguous()
+        self._check(self.lib.egv_zero_f32(_p(p), c_int64(p.numel()), self._stream()))
+
+    def colsum(self, x, out, accumulate=False, scale=1.0, scale_dev=None):
+        ld = x.stride(0)
+        assert x.dim() == 2 and x.stride(1) == 1 and out.dtype == torch.float32 and out.numel() == x.shape[1]
+        self._check(self.lib.egv_colsum(_p(x), int(x.dtype == torch.bfloat16), c_int64(x.shape[0]), x.shape[1], c_int64(ld),
+                                        _p(out), int(bool(accumulate)), c_float(scale), _p(scale_dev), self._stream()))
+
+    def dot(self, a, b, out, accumulate=False):
+        assert a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel() and out.numel() == 1
+        self._check(self.lib.egv_dot(_p(a), int(a.dtype == torch.bfloat16), _p(b), int(b.dtype == torch.bfloat16),
+                                     c_int64(a.numel()), _p(out), int(bool(accumulate)), self._stream()))
+
+    # ------------------------------------------------------------------ embeddings
+    def patchify(self, video, p, out):
+        BT, Cin, H, W = video.shape
+        assert video.dtype == torch.float32 and video.is_contiguous() and out.dtype == torch.bfloat16
+        assert out.is_contiguous() and out.numel() == video.numel()
+        self._check(self.lib.egv_patchify(_p(video), BT, Cin, H, W, p, _p(out), self._stream()))
+
+    def assemble_tokens(self, patch, cls, pos, temporal, B, T, Nf, tokens):
+        Cd = tokens.shape[-1]
+        for t in (patch, cls, pos, temporal, tokens):
+            assert t.dtype == torch.float32 and t.is_contiguous()
+        assert tokens.numel() == B * (1 + T * Nf) * Cd and patch.numel() == B * T * Nf * Cd
+        self._check(self.lib.egv_assemble_tokens(_p(patch), _p(cls), _p(pos), _p(temporal), B, T, Nf, Cd, _p(tokens),
+                                                 self._stream()))
+
+    def assemble_tokens_bwd(self, d_tokens, B, T, Nf, d_patch_bf16=None, d_cls=None, d_pos=None, d_temporal=None):
+        Cd = d_tokens.shape[-1]
+        assert d_tokens.dtype == torch.float32 and d_tokens.is_contiguous()
+        self._check(self.lib.egv_assemble_tokens_bwd(_p(d_tokens), B, T, Nf, Cd, _p(d_patch_bf16), _p(d_cls), _p(d_pos),
+                                                     _p(d_temporal), self._stream()))
+
+    def text_embed(self, ids, word, pos, type0, out, pad_id=1):
+        B, S = ids.shape
+        assert ids.dtype == torch.int64 and ids.is_contiguous() and out.is_contiguous()
+        self._check(self.lib.egv_text_embed(_p(ids), B, S, out.shape[-1], pad_id, _p(word), _p(pos), _p(type0), _p(out),
+                                            self._stream()))
+
+    def text_embed_bwd(self, d_out, ids, d_word=None, d_pos=None, d_type0=None, pad_id=1):
+        B, S = ids.shape
+        assert d_out.dtype == torch.float32 and d_out.is_contiguous()
+        self._check(self.lib.egv_text_embed_bwd(_p(d_out), _p(ids), B, S, d_out.shape[-1], pad_id, _p(d_word), _p(d_pos),
+                                                _p(d_type0), self._stream()))
+
+    # ------------------------------------------------------------------ losses
+    def softmax_xent(self, logits, labels, V, loss_sum, count, dlogits=None, ignore_index=-100):
+        assert logits.dim() == 2 and logits.stride(1) == 1 and logits.dtype == torch.float32
+        assert labels.dtype == torch.int64 and labels.is_contiguous() and labels.numel() == logits.shape[0]
+        ld_d = 0
+        if dlogits is not None:
+            assert dlogits.dtype == torch.bfloat16 and dlogits.stride(1) == 1 and dlogits.shape[0] == logits.shape[0]
+            ld_d = dlogits.stride(0)
+        self._check(self.lib.egv_softmax_xent(_p(logits), c_int64(logits.stride(0)), _p(labels), c_int64(logits.shape[0]),
+                                              V, ignore_index, _p(loss_sum), _p(count), _p(dlogits), c_int64(ld_d),
+                                              self._stream()))
+
+    def xent_finalize(self, loss_sum, count, loss=None, inv_count=None):
+        self._check(self.lib.egv_xent_finalize(_p(loss_sum), _p(count), _p(loss), _p(inv_count), self._stream()))
+
+    def egonce(self, t, v, noun, verb, temperature, sim, mask, loss, grad_row0=0, grad_rows=0, dt=None, dv=None):
+        G, P = t.shape
+        for x in (t, v, noun, verb, sim):
+            assert x.dtype == torch.float32 and x.is_contiguous()
+        assert mask.dtype == torch.uint8 and mask.numel() == G * G
+        n = int(self.lib.egv_egonce_scratch_floats(G, P, noun.shape[1], verb.shape[1]))
+        scratch = torch.empty(n, dtype=torch.float32, device=t.device)
+        self._check(self.lib.egv_egonce(_p(t), _p(v), G, P, _p(noun), noun.shape[1], _p(verb), verb.shape[1],
+                                        c_float(temperature), _p(sim), _p(mask), _p(loss), grad_row0, grad_rows, _p(dt),
+                                        _p(dv), _p(scratch), self._stream()))
+
+    # ------------------------------------------------------------------ optimiser
+    def adamw(self, p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+        for x in (p, g, m, v):
+            assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() == p.numel()
+        self._check(self.lib.egv_adamw(_p(p), _p(g), _p(m), _p(v), _p(p_bf16), c_int64(p.numel()), c_float(lr),
+                                       c_float(beta1), c_float(beta2), c_float(eps), c_float(weight_decay),
+                                       c_float(1.0 - beta1 ** step), c_float(1.0 - beta2 ** step), c_float(grad_scale),
+                                       self._stream()))
+
+    # ------------------------------------------------------------------ NVSwitch P2P all-gather
+    def p2p_alloc(self, nbytes):
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._check(self.lib.egv_p2p_alloc(c_int64(nbytes), C.byref(ptr), handle))
+        return ptr.value, handle.raw
+
+    def p2p_open(self, handle):
+        ptr = C.c_void_p()
+        self._check(self.lib.egv_p2p_open(C.c_char_p(handle), C.byref(ptr)))
+        return ptr.value
+
+    def p2p_allgather(self, src, nbytes, slot_bytes, slots, flags, rank, world, seq):
+        arr_s = (C.c_void_p * world)(*slots)
+        arr_f = (C.c_void_p * world)(*flags)
+        self._check(self.lib.egv_p2p_allgather(_p(src), c_int64(nbytes), c_int64(slot_bytes), arr_s, arr_f, rank, world,
+                                               C.c_uint32(seq), self._stream()))
+
+
+_KERNELS = None
+
+
+def kernels():
+    """Process-wide Kernels instance (raises if the CUDA library is missing)."""
+    global _KERNELS
+    if _KERNELS is None:
+        _KERNELS = Kernels()
+    return _KERNELS
+
+
+def set_kernels(k):
+    """Test hook: install a different implementation of the Kernels interface (tests/fake_kernels.py)."""
+    global _KERNELS
+    _KERNELS = k

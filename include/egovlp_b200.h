@@ -1,0 +1,202 @@
+/* egovlp_b200.h -- C ABI of libegovlp_b200.so: the B200 (sm_100a) kernels behind the
+ * EgoVLPv2 pre-training hot path (TimeSformer video tower + RoBERTa text tower + FIBER-style
+ * gated cross-attention + EgoNCE/MLM/ITM heads).
+ *
+ * The reference (facebookresearch/EgoVLPv2 @ 550c0596) is pure PyTorch and has no FFI; its
+ * operator surface is the nn.Module calls cited next to each entry point below (paths relative
+ * to EgoVLPv2/).  Every pointer is a DEVICE pointer unless it says "host"; sizes are element
+ * counts; `ld*` are row strides in ELEMENTS; `stream` is a cudaStream_t.  All functions are
+ * asynchronous on `stream`, return 0 on success and a negative code on error
+ * (egv_last_error() gives the message).  No torch types cross this boundary.
+ *
+ * dtypes: "bf16" = __nv_bfloat16 storage, "f32" = float.  GEMM operands are bf16 with fp32
+ * accumulation in TMEM; the residual stream, LayerNorm statistics, softmax and losses are fp32.
+ */
+#ifndef EGOVLP_B200_H_
+#define EGOVLP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* egv_stream_t;
+
+#define EGV_OK 0
+#define EGV_ERR_ARG (-1)
+#define EGV_ERR_CUDA (-2)
+#define EGV_ERR_UNSUPPORTED (-3)
+
+/* library / device ------------------------------------------------------------------------ */
+int egv_version(void);
+const char* egv_last_error(void);
+/* number of kernels this library has launched since load (bench.py's `gpu_launches`) */
+long long egv_launch_count(void);
+int egv_device_sm_count(void);
+
+/* GEMM ---------------------------------------------------------------------------------------
+ * D = epilogue(A x B) on tcgen05 tensor cores (TMA-fed, TMEM accumulators, persistent CTAs).
+ *   EGV_GEMM_NT: A[M,K] row-major, B[N,K] row-major      y = x W^T      nn.Linear forward
+ *                (video_transformer.py:53,56,120,152,160,166,183; roberta.py:268-278,339,407,420;
+ *                 model.py:105-115,279-284,361; heads.py:22,33,41,49)
+ *   EGV_GEMM_NN: A[M,K] row-major, B[K,N] row-major      dx = dy W      (autograd of the above)
+ *   EGV_GEMM_TN: A[K,M] row-major, B[K,N] row-major      dW = dy^T x    (autograd of the above)
+ * epilogue, in this order (each step optional):
+ *   v = acc + bias[n];  out_pre = bf16(v);  v = act(v)  or  v *= act'(aux[m,n]);
+ *   v *= scale * (scale_dev ? *scale_dev : 1);  v += residual[m,n];
+ *   out_f32[m,n] = v (or atomically += v when accumulate != 0);  out_bf16[m,n] = bf16(v)
+ */
+enum { EGV_GEMM_NT = 0, EGV_GEMM_NN = 1, EGV_GEMM_TN = 2 };
+enum {
+  EGV_ACT_NONE = 0,
+  EGV_ACT_GELU = 1,     /* exact erf GELU (nn.GELU / ACT2FN["gelu"]) */
+  EGV_ACT_RELU = 2,
+  EGV_ACT_TANH = 3,
+  EGV_ACT_GELU_BWD = 4, /* v *= gelu'(aux), aux = pre-activation   */
+  EGV_ACT_RELU_BWD = 5, /* v *= (aux > 0),  aux = post-activation  */
+  EGV_ACT_TANH_BWD = 6  /* v *= 1 - aux^2,  aux = tanh output      */
+};
+typedef struct egv_gemm_args {
+  int layout, M, N, K;
+  const void* A; int64_t lda;        /* bf16 */
+  const void* B; int64_t ldb;        /* bf16 */
+  const float* bias;                 /* [N] or NULL */
+  const void* aux; int64_t ld_aux;   /* bf16 [M,N] or NULL */
+  const float* scale_dev; float scale;
+  const float* residual; int64_t ld_res;
+  float* out_f32; int64_t ld_out_f32;
+  void* out_bf16; int64_t ld_out_bf16;
+  void* out_pre_bf16; int64_t ld_out_pre;
+  int act;
+  int accumulate;  /* 1: out_f32 += v with fp32 atomics (required when split_k > 1) */
+  int split_k;     /* >= 1; K is cut into split_k slices, one CTA pass each */
+} egv_gemm_args;
+int egv_gemm_bf16(const egv_gemm_args* args, egv_stream_t stream);
+/* test hook: route every GEMM through the SIMT fallback kernel (1) or restore normal dispatch (0) */
+void egv_gemm_force_simt(int on);
+
+/* LayerNorm ------------------------------------------------------------------------------------
+ * nn.LayerNorm over the last dim C (video_transformer.py:196,207,210,115,304; roberta.py:161,336,417;
+ * model.py:155; heads.py:41).  x is f32 or bf16 (x_is_bf16), y is written as bf16 and/or f32.
+ * mean/rstd [rows] are saved for the backward.  */
+int egv_layernorm_fwd(const void* x, int x_is_bf16, const float* gamma, const float* beta, float eps,
+                      int64_t rows, int C, void* y_bf16, float* y_f32, float* mean, float* rstd,
+                      egv_stream_t stream);
+/* val = LayerNorm'(dy);  dx (f32, may be NULL) = (add ? add : 0) + val, where add (f32, may be NULL) may alias dx;
+ * dx_bf16 (may be NULL) = bf16(bf16_total ? dx : val);  dgamma/dbeta [C] (f32, may be NULL) are always accumulated
+ * with atomics: zero them first for a plain result.  dy is f32 or bf16. */
+int egv_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_bf16, const float* gamma,
+                      const float* mean, const float* rstd, int64_t rows, int C, const float* add, float* dx,
+                      void* dx_bf16, int bf16_total, float* dgamma, float* dbeta, egv_stream_t stream);
+
+/* Strided multi-head attention (head_dim 64) ------------------------------------------------------
+ * One flash-style kernel family covers every attention on the path:
+ *   divided time / space attention and the CLS query   video_transformer.py:35-39,117-153
+ *   gated video->text cross-attention core              video_transformer.py:170-182
+ *   RoBERTa self-attention and text->video cross core   roberta.py:281-321
+ * Work unit = (batch b, head h, group g).  Query i of group g is row
+ *   q_row0 + g*q_gstride + i*q_istride of batch b (row stride ldq elements, batch stride
+ *   q_bstride rows); key/value j likewise with the k_* fields; when has_cls_key != 0 an extra
+ *   key/value (row `cls_row` of the batch) is prepended to every group.
+ * scores = scale * q.k + key_bias[b, j]  (key_bias: additive f32 [B, Lk], may be NULL).
+ * lse [B, H, G, Lq] f32 is written by fwd and consumed by bwd.  */
+typedef struct egv_attn_args {
+  int B, H, G, Lq, Lk;
+  const void* q; int64_t ldq, q_bstride; int q_row0, q_gstride, q_istride;
+  const void* k; const void* v; int64_t ldkv, kv_bstride; int k_row0, k_gstride, k_istride;
+  int has_cls_key, cls_row;
+  const float* key_bias;
+  float scale;
+  void* o; int64_t ldo, o_bstride;      /* bf16, rows addressed like q */
+  float* lse;
+  /* backward only */
+  const void* d_o;                      /* bf16, addressed like o */
+  void* dq; int64_t lddq;               /* bf16, addressed like q */
+  void* dk; void* dv; int64_t lddkv;    /* bf16, addressed like k/v */
+  float* delta;                         /* scratch [B,H,G,Lq] f32 */
+  float* dkv_cls;                       /* f32 [B, H, 2, 64] accumulator for the shared CLS key/value (or NULL) */
+  int dkv_accumulate;                   /* 1: dk/dv rows are read-modify-written (+=) */
+} egv_attn_args;
+int egv_attention_fwd(const egv_attn_args* a, egv_stream_t stream);
+int egv_attention_bwd(const egv_attn_args* a, egv_stream_t stream);
+/* dk/dv row `cls_row` of every batch (+)= the fp32 accumulators dkv_cls [B,H,2,64] filled by egv_attention_bwd */
+int egv_attention_cls_finalize(const float* dkv_cls, void* dk, void* dv, int64_t lddkv, int64_t kv_bstride, int cls_row,
+                               int B, int H, int accumulate, egv_stream_t stream);
+
+/* Elementwise / reductions --------------------------------------------------------------------- */
+/* fp32 -> bf16 cast (weights, activations); n elements */
+int egv_cast_f32_bf16(const float* x, void* y, int64_t n, egv_stream_t stream);
+int egv_cast_bf16_f32(const void* x, float* y, int64_t n, egv_stream_t stream);
+/* out[c] (+)= scale * (scale_dev ? *scale_dev : 1) * sum_r x[r, c]   -- bias gradients; x f32 or bf16 [rows, C], row stride ld */
+int egv_colsum(const void* x, int x_is_bf16, int64_t rows, int C, int64_t ld, float* out, int accumulate, float scale,
+               const float* scale_dev, egv_stream_t stream);
+int egv_zero_f32(float* p, int64_t n, egv_stream_t stream);
+/* out_bf16[i] = bf16( scale * (scale_dev ? *scale_dev : 1) * dy[i] * act'(aux[i]) )  -- gradient through a trailing
+ * activation (act = EGV_ACT_NONE: scaled cast; *_BWD: aux as in egv_gemm_bf16).  dy is f32 or bf16. */
+int egv_act_grad(const void* dy, int dy_is_bf16, const void* aux_bf16, int act, float scale, const float* scale_dev,
+                 void* out_bf16, int64_t n, egv_stream_t stream);
+/* out[0] (+)= sum_i a[i]*b[i]   (gradient of the scalar gates alpha_i2t / alpha_t2i) */
+int egv_dot(const void* a, int a_is_bf16, const void* b, int b_is_bf16, int64_t n, float* out, int accumulate,
+            egv_stream_t stream);
+/* y = a + alpha * (alpha_dev ? *alpha_dev : 1) * b  (f32, in-place allowed; a may be NULL = 0);
+ * writes y (f32) and/or y_bf16 */
+int egv_axpy_f32(const float* a, const float* b, float alpha, const float* alpha_dev, float* y, void* y_bf16, int64_t n,
+                 egv_stream_t stream);
+
+/* Patch embedding (video_transformer.py:78-83, 354-372; model.py:211-232) -------------------------
+ * im2col: video f32 [BT, 3, H, W] -> bf16 [BT*gh*gw, 3*p*p] (column order c,i,j = Conv2d weight order) */
+int egv_patchify(const float* video, int BT, int Cin, int H, int W, int p, void* out_bf16, egv_stream_t stream);
+/* tokens[b,0] = cls + pos[0]; tokens[b,1+f*Nf+n] = patch[b,f,n] + pos[1+n] + temporal[f]   (all f32) */
+int egv_assemble_tokens(const float* patch, const float* cls, const float* pos, const float* temporal, int B,
+                        int T, int Nf, int C, float* tokens, egv_stream_t stream);
+/* backward of the above: d_patch (bf16 [B*T*Nf, C]), d_cls [C], d_pos [1+Nf, C], d_temporal [T, C] (f32, +=) */
+int egv_assemble_tokens_bwd(const float* d_tokens, int B, int T, int Nf, int C, void* d_patch_bf16, float* d_cls,
+                            float* d_pos, float* d_temporal, egv_stream_t stream);
+
+/* RoBERTa embeddings (roberta.py:174-204, 881-892): word + type[0] + position(cumsum non-pad) (pre-LN sum) */
+int egv_text_embed(const int64_t* ids, int B, int S, int C, int pad_id, const float* word, const float* pos,
+                   const float* type0, float* out, egv_stream_t stream);
+int egv_text_embed_bwd(const float* d_out, const int64_t* ids, int B, int S, int C, int pad_id, float* d_word,
+                       float* d_pos, float* d_type0, egv_stream_t stream);
+
+/* Losses ------------------------------------------------------------------------------------------
+ * softmax cross-entropy with ignore_index (model.py:414-418, 478): per-row loss and dlogits.
+ * logits f32 [rows, ld] (V valid columns); writes loss_sum[0] += sum of valid-row losses,
+ * count[0] += valid rows; dlogits (bf16 [rows, ld_d], may be NULL) = softmax - onehot (unscaled). */
+int egv_softmax_xent(const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int V, int ignore_index,
+                     float* loss_sum, float* count, void* dlogits_bf16, int64_t ld_d, egv_stream_t stream);
+/* loss[0] = loss_sum / max(count, 1); inv_count[0] = 1 / max(count, 1)  (device scalars: no host sync) */
+int egv_xent_finalize(const float* loss_sum, const float* count, float* loss, float* inv_count, egv_stream_t stream);
+/* EgoNCE (model.py:385-394, 576-584 sim_matrix; loss.py:40-61).
+ * t, v: f32 [G, P] raw (gathered) embeddings; noun [G, Dn], verb [G, Dv] f32 multi-hot.
+ * Outputs: sim [G,G] f32 (rows = text), mask [G,G] uint8, loss[0]; dt, dv f32 [grad_rows, P] = dloss/dt, dloss/dv
+ * for rows grad_row0 .. grad_row0+grad_rows-1 (this rank's slice: trainer_egoclip.py:36-41).
+ * scratch: egv_egonce_scratch_floats(G, P, Dn, Dv) floats. */
+int64_t egv_egonce_scratch_floats(int G, int P, int Dn, int Dv);
+int egv_egonce(const float* t, const float* v, int G, int P, const float* noun, int Dn, const float* verb, int Dv,
+               float temperature, float* sim, uint8_t* mask, float* loss, int grad_row0, int grad_rows, float* dt,
+               float* dv, float* scratch, egv_stream_t stream);
+
+/* NVSwitch peer-to-peer all-gather (trainer_egoclip.py:25-41 AllGather_multi; model.py:385-388) ------------
+ * Symmetric buffers: every rank egv_p2p_alloc()s `slots` (W * slot_bytes, x2 for double buffering by the caller)
+ * and `flags` (32 uint32), exchanges the 64-byte IPC handles out of band (torch.distributed) and maps the peers'
+ * buffers with egv_p2p_open().  egv_p2p_allgather pushes `bytes` from src into slot `rank` of every peer, publishes
+ * the monotonically increasing `seq` and waits until all W local flags reached it.  Consecutive gathers must
+ * alternate between two slot sets (the caller offsets the `slots` pointers by parity of seq). */
+int egv_p2p_alloc(int64_t bytes, void** ptr, void* ipc_handle_64);
+int egv_p2p_open(const void* ipc_handle_64, void** ptr);
+int egv_p2p_close(void* ptr);
+int egv_p2p_free(void* ptr);
+int egv_p2p_allgather(const void* src, int64_t bytes, int64_t slot_bytes, void* const* slots, void* const* flags, int rank,
+                      int world, uint32_t seq, egv_stream_t stream);
+
+/* Optimiser (next row f-1): fused AdamW on one flat fp32 tensor; also refreshes the bf16 weight copy */
+int egv_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+              float beta2, float eps, float weight_decay, float bias_c1, float bias_c2, float grad_scale,
+              egv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGOVLP_B200_H_ */

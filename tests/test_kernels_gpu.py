@@ -1,0 +1,454 @@
+"""-m gpu: every CUDA kernel behind the C ABI against its fp32 torch restatement (tests/fake_kernels.py)
+and, where the oracle has the function, against oracle/egovlp_oracle.py.
+
+Tolerances (stated): GEMM / attention outputs are bf16-rounded products of bf16 operands with fp32
+accumulation -> relative-L2 <= 4e-3 (bf16 has 8 mantissa bits: eps = 3.9e-3) and max-abs within
+2 bf16 ulps of the largest magnitude; fp32-only kernels (LayerNorm, losses, reductions) <= 2e-5 relative.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from egovlpv2_b200 import lib as L  # noqa: E402
+from tests.fake_kernels import FakeKernels  # noqa: E402
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def K():
+    return L.Kernels()
+
+
+@pytest.fixture(scope="module")
+def R():
+    return FakeKernels()
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def check(a, b, tol, what="", atol=0.0):
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    assert torch.isfinite(a.float()).all(), what + ": non-finite output"
+    if atol and (a.float() - b.float()).abs().max().item() <= atol:
+        return
+    r = rel_l2(a, b)
+    assert r <= tol, "%s: rel-L2 %.3e > %.1e (max abs diff %.3e)" % (what, r, tol, (a.float() - b.float()).abs().max().item())
+
+
+def rnd(*shape, dtype=torch.bfloat16, scale=1.0, seed=None):
+    g = torch.Generator(device="cpu").manual_seed(seed if seed is not None else (hash(shape) & 0xFFFF))
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+GEMM_SHAPES = [
+    # M, N, K
+    (128, 64, 64),        # one tile, BN=64
+    (300, 200, 136),      # tails in every dimension
+    (1000, 768, 768),     # BN=128 (few tiles)
+    (4096, 768, 768),     # BN=256
+    (4100, 2304, 768),    # BN=256, > 148 tiles: persistent loop + TMEM double buffering, M tail
+    (256, 3072, 768),     # text-tower shape
+    (8, 4096, 768),       # projection head shape (M << tile)
+    (520, 50265, 128),    # MLM decoder: N tail, not a multiple of 8
+]
+
+
+def _operands(layout, M, N, Kd, seed=0):
+    pad = lambda n: (n + 7) // 8 * 8  # noqa: E731  (row strides must be multiples of 8 elements for TMA)
+    if layout == L.GEMM_NT:
+        A = rnd(M, pad(Kd), seed=seed)[:, :Kd]
+        B = rnd(N, pad(Kd), seed=seed + 1)[:, :Kd]
+    elif layout == L.GEMM_NN:
+        A = rnd(M, pad(Kd), seed=seed)[:, :Kd]
+        B = rnd(Kd, pad(N), seed=seed + 1)[:, :N]
+    else:
+        A = rnd(Kd, pad(M), seed=seed)[:, :M]
+        B = rnd(Kd, pad(N), seed=seed + 1)[:, :N]
+    return A, B
+
+
+@pytest.mark.parametrize("layout", [L.GEMM_NT, L.GEMM_NN, L.GEMM_TN])
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+def test_gemm_plain(K, R, layout, shape):
+    M, N, Kd = shape
+    A, B = _operands(layout, M, N, Kd)
+    out, ref = torch.full((M, N), float("nan"), device=DEV), torch.empty(M, N, device=DEV)
+    K.gemm(layout, A, B, out_f32=out)
+    R.gemm(layout, A, B, out_f32=ref)
+    check(out, ref, 1e-5 * math.sqrt(Kd) + 1e-5, "gemm layout %d %s" % (layout, shape))
+
+
+@pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_GELU, L.ACT_RELU, L.ACT_TANH, L.ACT_GELU_BWD, L.ACT_RELU_BWD,
+                                 L.ACT_TANH_BWD])
+def test_gemm_epilogue(K, R, act):
+    M, N, Kd = 700, 520, 264
+    A, B = _operands(L.GEMM_NT, M, N, Kd, seed=5)
+    A, B = A * 0.2, B * 0.2
+    bias = rnd(N, dtype=torch.float32, seed=9)
+    aux = rnd(M, N, seed=10) if act >= L.ACT_GELU_BWD else None
+    if act == L.ACT_TANH_BWD:
+        aux = torch.tanh(aux.float()).to(torch.bfloat16)
+    res = rnd(M, N, dtype=torch.float32, seed=11)
+    sdev = torch.tensor([0.37], device=DEV)
+    outs = []
+    for impl in (K, R):
+        o32 = torch.full((M, N), float("nan"), device=DEV)
+        o16 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        opre = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        impl.gemm(L.GEMM_NT, A, B, bias=bias, aux=aux, act=act, scale=1.5, scale_dev=sdev, residual=res, out_f32=o32,
+                  out_bf16=o16, out_pre=opre)
+        outs.append((o32, o16, opre))
+    check(outs[0][0], outs[1][0], 2e-5, "epilogue f32 act %d" % act)
+    check(outs[0][1], outs[1][1], 4e-3, "epilogue bf16 act %d" % act)
+    check(outs[0][2], outs[1][2], 4e-3, "epilogue pre act %d" % act)
+
+
+def test_gemm_inplace_residual_and_strided_outputs(K, R):
+    M, N, Kd = 390, 256, 128
+    A, B = _operands(L.GEMM_NT, M, N, Kd, seed=21)
+    big = rnd(M, 3 * N, dtype=torch.float32, seed=22)
+    big_ref = big.clone()
+    K.gemm(L.GEMM_NT, A, B, residual=big[:, N:2 * N], out_f32=big[:, N:2 * N])
+    R.gemm(L.GEMM_NT, A, B, residual=big_ref[:, N:2 * N], out_f32=big_ref[:, N:2 * N])
+    check(big, big_ref, 1e-5, "in-place residual into a column slice")
+
+
+@pytest.mark.parametrize("layout", [L.GEMM_NT, L.GEMM_NN, L.GEMM_TN])
+def test_gemm_split_k_accumulate(K, R, layout):
+    M, N, Kd = 96, 768, 4104
+    A, B = _operands(layout, M, N, Kd, seed=31)
+    bias = rnd(N, dtype=torch.float32, seed=32)
+    init = rnd(M, N, dtype=torch.float32, seed=33)
+    out, ref = init.clone(), init.clone()
+    K.gemm(layout, A, B, bias=bias, out_f32=out, accumulate=True, split_k=7)
+    R.gemm(layout, A, B, bias=bias, out_f32=ref, accumulate=True)
+    check(out, ref, 2e-5 * math.sqrt(Kd / 64), "split-k accumulate layout %d" % layout)
+
+
+@pytest.mark.parametrize("layout", [L.GEMM_NT, L.GEMM_NN, L.GEMM_TN])
+def test_gemm_simt_fallback(K, R, layout):
+    # odd row strides cannot be described by a TMA tensor map -> SIMT kernel, same semantics
+    M, N, Kd = 37, 50, 131
+    if layout == L.GEMM_NT:
+        A, B = rnd(M, Kd, seed=41), rnd(N, Kd, seed=42)
+    elif layout == L.GEMM_NN:
+        A, B = rnd(M, Kd, seed=41), rnd(Kd, N, seed=42)
+    else:
+        A, B = rnd(Kd, M, seed=41), rnd(Kd, N, seed=42)
+    bias = rnd(N, dtype=torch.float32, seed=43)
+    out, ref = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    K.gemm(layout, A, B, bias=bias, act=L.ACT_GELU, out_f32=out)
+    R.gemm(layout, A, B, bias=bias, act=L.ACT_GELU, out_f32=ref)
+    check(out, ref, 2e-5, "simt layout %d" % layout)
+    # and the forced-SIMT route must agree with the tensor-core route on an aligned problem
+    A, B = _operands(layout, 300, 200, 136, seed=44)
+    o1, o2 = torch.empty(300, 200, device=DEV), torch.empty(300, 200, device=DEV)
+    K.gemm(layout, A, B, out_f32=o1)
+    K.force_simt(True)
+    try:
+        K.gemm(layout, A, B, out_f32=o2)
+    finally:
+        K.force_simt(False)
+    check(o1, o2, 1e-5, "tcgen05 vs simt layout %d" % layout)
+
+
+def test_gemm_linearity_full_size(K):
+    """Size-independent property at the BASELINE cfg-3 shape (M = 8*3137): (A1+A2) W^T == A1 W^T + A2 W^T
+    up to bf16 rounding of the summed operand, and rows of a zero A block are exactly bias."""
+    M, N, Kd = 8 * 3137, 2304, 768
+    A = rnd(M, Kd, seed=51)
+    A[1000:1128] = 0
+    W = rnd(N, Kd, seed=52, scale=0.05)
+    bias = rnd(N, dtype=torch.float32, seed=53)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    K.gemm(L.GEMM_NT, A, W, bias=bias, out_bf16=out)
+    assert torch.equal(out[1000:1128].float(), bias.to(torch.bfloat16).float().expand(128, N))
+    idx = torch.tensor([0, 1, 127, 128, 5000, 12547, 12548, M - 9, M - 8, M - 1], device=DEV)
+    ref = A[idx].float() @ W.float().t() + bias
+    check(out[idx], ref.to(torch.bfloat16), 4e-3, "sampled rows of the full-size GEMM")
+
+
+def test_gemm_argument_errors(K):
+    A, B = rnd(64, 64), rnd(64, 64)
+    with pytest.raises(RuntimeError):
+        K.gemm(L.GEMM_NT, A, B)  # no output
+    with pytest.raises(RuntimeError):
+        K.gemm(L.GEMM_NT, A, B, act=L.ACT_GELU_BWD, out_f32=torch.empty(64, 64, device=DEV))  # aux missing
+    with pytest.raises(RuntimeError):
+        K.gemm(L.GEMM_NT, A, B, out_f32=torch.empty(64, 64, device=DEV), split_k=2)  # split-k without accumulate
+
+
+# ------------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows,C", [(5, 128), (1000, 768), (8 * 3137, 768), (77, 1024)])
+@pytest.mark.parametrize("xbf", [False, True])
+def test_layernorm(K, R, rows, C, xbf):
+    x = rnd(rows, C, dtype=torch.bfloat16 if xbf else torch.float32, seed=61, scale=2.0) + 0.5
+    g, b = rnd(C, dtype=torch.float32, seed=62) * 0.1 + 1, rnd(C, dtype=torch.float32, seed=63) * 0.1
+    dy = rnd(rows, C, dtype=torch.float32, seed=64)
+    res = []
+    for impl in (K, R):
+        y16 = torch.empty(rows, C, dtype=torch.bfloat16, device=DEV)
+        y32 = torch.empty(rows, C, device=DEV)
+        mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+        impl.layernorm_fwd(x, g, b, 1e-5, y_bf16=y16, y_f32=y32, mean=mean, rstd=rstd)
+        dx = torch.ones(rows, C, device=DEV)
+        dx16 = torch.empty(rows, C, dtype=torch.bfloat16, device=DEV)
+        dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        impl.layernorm_bwd(dy, x, g, mean, rstd, add=dx, dx=dx, dx_bf16=dx16, bf16_total=True, dgamma=dg, dbeta=db)
+        dx2 = torch.empty(rows, C, device=DEV)
+        dx216 = torch.empty(rows, C, dtype=torch.bfloat16, device=DEV)
+        impl.layernorm_bwd(dy.to(torch.bfloat16), x, g, mean, rstd, add=dx, dx=dx2, dx_bf16=dx216, bf16_total=False)
+        res.append((y16, y32, mean, rstd, dx, dx16, dg, db, dx2, dx216))
+    names = "y16 y32 mean rstd dx dx16 dgamma dbeta dx_from_bf16 dx16_partial".split()
+    for n, a, r in zip(names, res[0], res[1]):
+        check(a, r, 4e-3 if a.dtype == torch.bfloat16 else 3e-5, "layernorm " + n)
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), g, b, 1e-5)
+    check(res[0][1], ref, 1e-5, "layernorm vs torch")
+
+
+# ------------------------------------------------------------------------------------------- attention
+def _attn_case(name, B=2, H=2):
+    T, Nf = 4, 9
+    N = 1 + T * Nf
+    sc = 64 ** -0.5
+    if name == "time":
+        return N, N, L.AttnSpec(H=H, G=Nf, Lq=T, Lk=T, q_row0=1, q_gstride=1, q_istride=Nf, k_row0=1, k_gstride=1,
+                                k_istride=Nf, has_cls_key=True, cls_row=0, scale=sc), False
+    if name == "space":
+        return N, N, L.AttnSpec(H=H, G=T, Lq=Nf, Lk=Nf, q_row0=1, q_gstride=Nf, q_istride=1, k_row0=1, k_gstride=Nf,
+                                k_istride=1, has_cls_key=True, cls_row=0, scale=sc), False
+    if name == "cls":
+        return N, N, L.AttnSpec(H=H, G=1, Lq=1, Lk=N - 1, q_row0=0, k_row0=1, has_cls_key=True, cls_row=0, scale=sc), False
+    if name == "i2t":      # many queries, 11 keys with a pad mask
+        return 200, 11, L.AttnSpec(H=H, G=1, Lq=200, Lk=11, scale=sc), True
+    if name == "t2i":      # few queries, many keys
+        return 11, 333, L.AttnSpec(H=H, G=1, Lq=11, Lk=333, scale=sc), False
+    if name == "text":
+        return 32, 32, L.AttnSpec(H=H, G=1, Lq=32, Lk=32, scale=sc), True
+    if name == "space196":  # real per-frame size, 2 frames
+        Nf2, T2 = 196, 2
+        n = 1 + T2 * Nf2
+        return n, n, L.AttnSpec(H=H, G=T2, Lq=Nf2, Lk=Nf2, q_row0=1, q_gstride=Nf2, q_istride=1, k_row0=1,
+                                k_gstride=Nf2, k_istride=1, has_cls_key=True, cls_row=0, scale=sc), False
+    if name == "time16":    # 16 frames: 16 queries x 17 keys per group, many groups -> warp-per-group kernel
+        Nf2, T2 = 196, 16
+        n = 1 + T2 * Nf2
+        return n, n, L.AttnSpec(H=H, G=Nf2, Lq=T2, Lk=T2, q_row0=1, q_gstride=1, q_istride=Nf2, k_row0=1, k_gstride=1,
+                                k_istride=Nf2, has_cls_key=True, cls_row=0, scale=sc), False
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["time", "space", "cls", "i2t", "t2i", "text", "space196", "time16"])
+def test_attention_fwd_bwd(K, R, name):
+    B, H = (3, 3) if name == "time16" else (2, 2)
+    Nq, Nk, spec, masked = _attn_case(name, B, H)
+    C = H * 64
+    fused = Nq == Nk and spec.has_cls_key
+    if fused:   # q, k, v are column slices of one [B, N, 3C] tensor, like the video tower
+        qkv = rnd(B, Nq, 3 * C, seed=71)
+        q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    else:
+        q, k, v = rnd(B, Nq, C, seed=72), rnd(B, Nk, C, seed=73), rnd(B, Nk, C, seed=74)
+    kb = None
+    if masked:
+        lens = torch.tensor([Nk - 3, Nk][:B] if B == 2 else [Nk] * B, device=DEV)
+        kb = torch.where(torch.arange(Nk, device=DEV)[None] < lens[:, None], 0.0, torch.finfo(torch.float32).min)
+        kb = kb.float().contiguous()
+    d_o = rnd(B, Nq, C, seed=75)
+    outs = []
+    for impl in (K, R):
+        o = torch.zeros(B, Nq, C, dtype=torch.bfloat16, device=DEV)
+        lse = torch.zeros(B * H * spec.G * spec.Lq, device=DEV)
+        impl.attention_fwd(spec, q, k, v, o, lse, key_bias=kb)
+        if fused:
+            dqkv = torch.zeros(B, Nq, 3 * C, dtype=torch.bfloat16, device=DEV)
+            dq, dk, dv = dqkv[:, :, :C], dqkv[:, :, C:2 * C], dqkv[:, :, 2 * C:]
+        else:
+            dq = torch.zeros(B, Nq, C, dtype=torch.bfloat16, device=DEV)
+            dk = torch.zeros(B, Nk, C, dtype=torch.bfloat16, device=DEV)
+            dv = torch.zeros(B, Nk, C, dtype=torch.bfloat16, device=DEV)
+        delta = torch.zeros_like(lse)
+        cls = torch.zeros(B * H * 128, device=DEV) if spec.has_cls_key else None
+        impl.attention_bwd(spec, q, k, v, o, lse, d_o, dq, dk, dv, delta, dkv_cls=cls, key_bias=kb)
+        if spec.has_cls_key:
+            impl.attention_cls_finalize(cls, dk, dv, H, cls_row=0, accumulate=False)
+        outs.append((o, lse, dq, dk, dv, delta))
+    for n, a, r in zip("o lse dq dk dv delta".split(), outs[0], outs[1]):
+        tol = {"dq": 1.2e-2, "dk": 1.2e-2, "dv": 1.2e-2, "o": 8e-3, "delta": 2e-2, "lse": 1e-4}[n]
+        check(a, r, tol, "attention %s %s" % (name, n))
+
+
+def test_attention_dkv_accumulate(K, R):
+    """The CLS-query pass adds its dk/dv onto what the grouped pass wrote (read-modify-write rows)."""
+    B, H = 2, 2
+    Nq, Nk, spec, _ = _attn_case("cls", B, H)
+    C = H * 64
+    qkv = rnd(B, Nq, 3 * C, seed=81)
+    q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    d_o = rnd(B, Nq, C, seed=82)
+    base = rnd(B, Nq, 3 * C, seed=83)
+    outs = []
+    for impl in (K, R):
+        o = torch.zeros(B, Nq, C, dtype=torch.bfloat16, device=DEV)
+        lse = torch.zeros(B * H, device=DEV)
+        impl.attention_fwd(spec, q, k, v, o, lse)
+        dqkv = base.clone()
+        cls = torch.zeros(B * H * 128, device=DEV)
+        impl.attention_bwd(spec, q, k, v, o, lse, d_o, dqkv[:, :, :C], dqkv[:, :, C:2 * C], dqkv[:, :, 2 * C:],
+                           torch.zeros_like(lse), dkv_cls=cls, dkv_accumulate=True)
+        impl.attention_cls_finalize(cls, dqkv[:, :, C:2 * C], dqkv[:, :, 2 * C:], H, cls_row=0, accumulate=True)
+        outs.append(dqkv)
+    check(outs[0], outs[1], 8e-3, "dkv accumulate")
+
+
+# ------------------------------------------------------------------------------------------- elementwise & embeddings
+def test_elementwise(K, R):
+    x = rnd(1000003, dtype=torch.float32, seed=91)
+    y1, y2 = torch.empty_like(x, dtype=torch.bfloat16), torch.empty_like(x, dtype=torch.bfloat16)
+    K.cast(x, y1)
+    R.cast(x, y2)
+    assert torch.equal(y1, y2)
+    z1, z2 = torch.empty_like(x), torch.empty_like(x)
+    K.cast(y1, z1)
+    R.cast(y1, z2)
+    assert torch.equal(z1, z2)
+    b = rnd(1000003, dtype=torch.float32, seed=92)
+    al = torch.tensor([-0.25], device=DEV)
+    for impl, (o, o16) in ((K, (z1, y1)), (R, (z2, y2))):
+        impl.axpy(x, b, 2.0, al, y=o, y_bf16=o16)
+    check(z1, z2, 1e-6, "axpy")
+    assert torch.equal(y1, y2)
+    m = rnd(3001, 770, seed=93)
+    for dt in (torch.bfloat16, torch.float32):
+        mm = m.to(dt)
+        c1, c2 = torch.ones(770, device=DEV), torch.ones(770, device=DEV)
+        K.colsum(mm, c1, accumulate=True, scale=0.5, scale_dev=al)
+        R.colsum(mm, c2, accumulate=True, scale=0.5, scale_dev=al)
+        check(c1, c2, 2e-5, "colsum")
+        c1, c2 = torch.ones(768, device=DEV), torch.ones(768, device=DEV)
+        K.colsum(mm[:, 1:769], c1)
+        R.colsum(mm[:, 1:769], c2)
+        check(c1, c2, 2e-5, "colsum odd offset")
+    d1, d2 = torch.ones(1, device=DEV), torch.ones(1, device=DEV)
+    K.dot(x, y1, d1, accumulate=True)
+    R.dot(x, y1, d2, accumulate=True)
+    check(d1, d2, 1e-4, "dot")
+    K.zero(z1)
+    assert z1.abs().max().item() == 0
+    aux = rnd(1000003, seed=94)
+    for act in (L.ACT_NONE, L.ACT_GELU_BWD, L.ACT_RELU_BWD, L.ACT_TANH_BWD):
+        a = torch.tanh(aux.float()).to(torch.bfloat16) if act == L.ACT_TANH_BWD else aux
+        for dy in (x, y1):
+            K.act_grad(dy, None if act == L.ACT_NONE else a, act, y1.new_empty(0) if False else y2, scale=0.5, scale_dev=al)
+            ref = torch.empty_like(y2)
+            R.act_grad(dy, None if act == L.ACT_NONE else a, act, ref, scale=0.5, scale_dev=al)
+            check(y2, ref, 4e-3, "act_grad %d" % act)
+
+
+def test_patch_embed_and_text_embed(K, R):
+    B, T, Nf, C, p = 2, 3, 4, 128, 16
+    video = rnd(B * T, 3, 2 * p, 2 * p, dtype=torch.float32, seed=101)
+    o1, o2 = torch.empty(B * T * Nf, 3 * p * p, dtype=torch.bfloat16, device=DEV), torch.empty(B * T * Nf, 3 * p * p, dtype=torch.bfloat16, device=DEV)
+    K.patchify(video, p, o1)
+    R.patchify(video, p, o2)
+    assert torch.equal(o1, o2)
+    patch = rnd(B * T * Nf, C, dtype=torch.float32, seed=102)
+    cls, pos, tem = rnd(C, dtype=torch.float32, seed=103), rnd(1 + Nf, C, dtype=torch.float32, seed=104), rnd(T, C, dtype=torch.float32, seed=105)
+    t1, t2 = torch.empty(B, 1 + T * Nf, C, device=DEV), torch.empty(B, 1 + T * Nf, C, device=DEV)
+    K.assemble_tokens(patch, cls, pos, tem, B, T, Nf, t1)
+    R.assemble_tokens(patch, cls, pos, tem, B, T, Nf, t2)
+    check(t1, t2, 1e-7, "assemble")
+    d = rnd(B, 1 + T * Nf, C, dtype=torch.float32, seed=106)
+    g = []
+    for impl in (K, R):
+        dp = torch.empty(B * T * Nf, C, dtype=torch.bfloat16, device=DEV)
+        dc, dpos, dt = torch.ones(C, device=DEV), torch.ones(1 + Nf, C, device=DEV), torch.ones(T, C, device=DEV)
+        impl.assemble_tokens_bwd(d, B, T, Nf, dp, dc, dpos, dt)
+        g.append((dp, dc, dpos, dt))
+    for a, r in zip(*g):
+        check(a, r, 1e-5 if a.dtype == torch.float32 else 4e-3, "assemble bwd")
+    ids = torch.tensor([[0, 5, 9, 2, 1, 1], [0, 7, 7, 7, 8, 2]], device=DEV)
+    word, posw, ty = rnd(12, C, dtype=torch.float32, seed=107), rnd(10, C, dtype=torch.float32, seed=108), rnd(C, dtype=torch.float32, seed=109)
+    e1, e2 = torch.empty(2, 6, C, device=DEV), torch.empty(2, 6, C, device=DEV)
+    K.text_embed(ids, word, posw, ty, e1)
+    R.text_embed(ids, word, posw, ty, e2)
+    check(e1, e2, 1e-7, "text embed")
+    de = rnd(2, 6, C, dtype=torch.float32, seed=110)
+    g = []
+    for impl in (K, R):
+        dw, dp, dt = torch.zeros(12, C, device=DEV), torch.zeros(10, C, device=DEV), torch.zeros(C, device=DEV)
+        impl.text_embed_bwd(de, ids, dw, dp, dt)
+        g.append((dw, dp, dt))
+    for a, r in zip(*g):
+        check(a, r, 1e-5, "text embed bwd")
+
+
+# ------------------------------------------------------------------------------------------- losses / optimiser
+def test_softmax_xent(K, R):
+    rows, V = 37, 50265
+    ld = 50272
+    logits = rnd(rows, ld, dtype=torch.float32, seed=121, scale=3.0)[:, :V]
+    labels = torch.randint(0, V, (rows,), generator=torch.Generator().manual_seed(1)).to(DEV)
+    labels[::5] = -100
+    r = []
+    for impl in (K, R):
+        ls, cnt = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+        dl = torch.full((rows, ld), 7.0, dtype=torch.bfloat16, device=DEV)
+        impl.softmax_xent(logits, labels, V, ls, cnt, dlogits=dl[:, :V])
+        loss, inv = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+        impl.xent_finalize(ls, cnt, loss, inv)
+        r.append((loss, inv, dl))
+    check(r[0][0], r[1][0], 1e-5, "xent loss")
+    check(r[0][1], r[1][1], 1e-6, "xent inv count")
+    check(r[0][2], r[1][2], 4e-3, "xent dlogits")
+    ref = torch.nn.functional.cross_entropy(logits, labels, ignore_index=-100)
+    check(r[0][0], ref.reshape(1), 1e-5, "xent vs torch")
+
+
+@pytest.mark.parametrize("G", [4, 8, 64])
+def test_egonce_vs_oracle(K, R, G):
+    from oracle import egovlp_oracle as O
+    P = 4096 if G > 4 else 256
+    t, v = rnd(G, P, dtype=torch.float32, seed=131), rnd(G, P, dtype=torch.float32, seed=132)
+    v = v + 0.5 * t  # make the diagonal somewhat dominant, like trained embeddings
+    gen = torch.Generator().manual_seed(3)
+    noun = (torch.rand(G, 582, generator=gen) < 0.02).float()
+    verb = (torch.rand(G, 118, generator=gen) < 0.05).float()
+    noun[torch.arange(G), torch.randint(0, 582, (G,), generator=gen)] = 1
+    verb[torch.arange(G), torch.randint(0, 118, (G,), generator=gen)] = 1
+    noun, verb = noun.to(DEV), verb.to(DEV)
+    sim, mask, loss = torch.empty(G, G, device=DEV), torch.empty(G, G, dtype=torch.uint8, device=DEV), torch.empty(1, device=DEV)
+    r0, nr = G // 4, G // 2
+    dt, dv = torch.empty(nr, P, device=DEV), torch.empty(nr, P, device=DEV)
+    K.egonce(t, v, noun, verb, 0.05, sim, mask, loss, r0, nr, dt, dv)
+    tt, vv = t.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    osim = O.sim_matrix(tt, vv)
+    oloss, omask = O.egonce(osim, O.sim_matrix(verb, verb), O.sim_matrix(noun, noun))
+    oloss.backward()
+    check(sim, osim.detach(), 1e-5, "egonce sim")
+    assert torch.equal(mask.bool(), omask)
+    check(loss, oloss.detach().reshape(1), 1e-5, "egonce loss", atol=2e-6)
+    check(dt, tt.grad[r0:r0 + nr], 1e-4, "egonce dt")
+    check(dv, vv.grad[r0:r0 + nr], 1e-4, "egonce dv")
+
+
+def test_adamw(K, R):
+    n = 100003
+    p0, g = rnd(n, dtype=torch.float32, seed=141), rnd(n, dtype=torch.float32, seed=142)
+    st = []
+    for impl in (K, R):
+        p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+        p16 = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+        for step in (1, 2, 3):
+            impl.adamw(p, g * step, m, v, p16, 1e-3, 0.9, 0.98, 1e-8, 0.01, step, grad_scale=0.5)
+        st.append((p, m, v, p16))
+    for a, r in zip(*st):
+        check(a, r, 4e-3 if a.dtype == torch.bfloat16 else 1e-5, "adamw")
