@@ -474,21 +474,89 @@ def mlp_chain_fwd(K, x, layers, save=True):
     return out, (saved if save else None)
 
 
+_ACT_BWD = {ACT_NONE: ACT_NONE, ACT_GELU: ACT_GELU_BWD, ACT_RELU: ACT_RELU_BWD, ACT_TANH: ACT_TANH_BWD}
+
+
 def mlp_chain_bwd(K, saved, d_out, layers, scale_dev=None, need_dx=True):
-    """-> (dx f32 [M, Kd] or None, [(dW, db)] per layer).  `scale_dev` scales d_out (device scalar)."""
-    M = d_out.shape[0]
+    """-> (dx f32 [M, Kd] or None, [(dW, db)] per layer).  `scale_dev` scales d_out (device scalar).
+    The gradient of every activation is folded into the epilogue of the GEMM that produces it; only a
+    trailing activation of the LAST layer needs the stand-alone act_grad kernel."""
     grads = [None] * len(layers)
-    d_cur = _e(d_out, d_out.shape, BF16)          # gradient w.r.t. the layer OUTPUT (post-activation)
-    K.axpy(None, d_out.contiguous(), 1.0, scale_dev, y_bf16=d_cur)
+    last = len(layers) - 1
+    act = layers[last][2]
+    aux = None if act == ACT_NONE else (saved[last][2] if act == ACT_GELU else saved[last][1])
+    d_cur = _e(d_out, d_out.shape, BF16)          # gradient w.r.t. the PRE-activation output of layer i
+    K.act_grad(d_out.contiguous(), aux, _ACT_BWD[act], d_cur, scale_dev=scale_dev)
     dx = None
-    for i in range(len(layers) - 1, -1, -1):
-        wt, b, act = layers[i]
-        x_in, y_out, pre = saved[i]
-        N, Kd = wt.shape
-        if act != ACT_NONE:
-            # d_pre = d_cur * act'(.) : run it through an identity-free path: fold into the dx GEMM of the NEXT step is
-            # impossible for the last layer, so apply it with a dedicated tiny GEMM-free kernel: axpy cannot do it ->
-            # use the GEMM epilogue of a [M,N]x[N,N] identity?  No: activation gradients are folded below instead.
-            raise AssertionError("unreachable")  # replaced at import time; see _act_bwd below
+    for i in range(last, -1, -1):
+        wt, b, _ = layers[i]
+        x_in = saved[i][0]
         grads[i] = linear_bwd_params(K, d_cur, x_in, bias=b is not None)
+        if i > 0:
+            pact = layers[i - 1][2]
+            paux = None if pact == ACT_NONE else (saved[i - 1][2] if pact == ACT_GELU else saved[i - 1][1])
+            d_prev = _e(d_out, (d_cur.shape[0], wt.shape[1]), BF16)
+            K.gemm(GEMM_NN, d_cur, wt, aux=paux, act=_ACT_BWD[pact], out_bf16=d_prev)
+            d_cur = d_prev
+        elif need_dx:
+            dx = _e(d_out, (d_cur.shape[0], wt.shape[1]), F32)
+            K.gemm(GEMM_NN, d_cur, wt, out_f32=dx)
     return dx, grads
+
+
+# ----------------------------------------------------------------------------------------------- MLM head + CE
+def mlm_head_fwd(K, h, labels, p, w, save=True):
+    """cross_modal_text_transform -> MLMHead (heads.py:38-50: dense, erf-GELU, LayerNorm 1e-12, decoder + bias)
+    -> mean cross-entropy over labels != -100 (model.py:408-418).  h [B,S,C] f32.
+    Returns (logits f32 view [B*S, V] with padded row stride, loss_sum [1], count [1], saved)."""
+    B, S, C = h.shape
+    M = B * S
+    V = w["mlm_score.decoder.weight"].shape[0]
+    ldv = (V + 7) // 8 * 8
+    layers = [(w["cross_modal_text_transform.weight"], p["cross_modal_text_transform.bias"], ACT_NONE),
+              (w["mlm_score.transform.dense.weight"], p["mlm_score.transform.dense.bias"], ACT_GELU)]
+    t, chain = mlp_chain_fwd(K, h.reshape(M, C), layers)
+    tn = _e(h, (M, C), BF16)
+    mean, rstd = _e(h, (M,), F32), _e(h, (M,), F32)
+    K.layernorm_fwd(t, p["mlm_score.transform.LayerNorm.weight"], p["mlm_score.transform.LayerNorm.bias"], 1e-12, y_bf16=tn,
+                    mean=mean, rstd=rstd)
+    logits = _e(h, (M, ldv), F32)[:, :V]
+    K.gemm(GEMM_NT, tn, w["mlm_score.decoder.weight"], bias=p["mlm_score.bias"], out_f32=logits)
+    loss_sum, count = _z(h, (1,)), _z(h, (1,))
+    dlogits = None
+    if save:
+        dlogits = _e(h, (M, ldv), BF16)
+        if ldv != V:
+            dlogits[:, V:].zero_()
+        dlogits = dlogits[:, :V]
+    K.softmax_xent(logits, labels.reshape(-1).contiguous(), V, loss_sum, count, dlogits=dlogits)
+    s = types.SimpleNamespace(layers=layers, chain=chain, t=t, tn=tn, mean=mean, rstd=rstd, dlogits=dlogits,
+                              shape=(B, S, C)) if save else None
+    return logits, loss_sum, count, s
+
+
+def mlm_head_bwd(K, s, scale_dev, p, w):
+    """scale_dev: device scalar = d(loss)/d(loss_sum) (grad_out / global count).  -> (dh [B,S,C] f32, grads dict)."""
+    B, S, C = s.shape
+    M = B * S
+    g = {}
+    g["mlm_score.decoder.weight"], g["mlm_score.bias"] = linear_bwd_params(K, s.dlogits, s.tn, scale_dev=scale_dev)
+    d_tn = _e(s.t, (M, C), BF16)
+    K.gemm(GEMM_NN, s.dlogits, w["mlm_score.decoder.weight"], scale_dev=scale_dev, out_bf16=d_tn)
+    d_t = _e(s.t, (M, C), F32)
+    g["mlm_score.transform.LayerNorm.weight"], g["mlm_score.transform.LayerNorm.bias"] = _z(s.t, (C,)), _z(s.t, (C,))
+    K.layernorm_bwd(d_tn, s.t, p["mlm_score.transform.LayerNorm.weight"], s.mean, s.rstd, dx=d_t,
+                    dgamma=g["mlm_score.transform.LayerNorm.weight"], dbeta=g["mlm_score.transform.LayerNorm.bias"])
+    dh, grads = mlp_chain_bwd(K, s.chain, d_t, s.layers)
+    g["cross_modal_text_transform.weight"], g["cross_modal_text_transform.bias"] = grads[0]
+    g["mlm_score.transform.dense.weight"], g["mlm_score.transform.dense.bias"] = grads[1]
+    return dh.view(B, S, C), g
+
+
+def xent_rows_fwd(K, logits, labels, save=True):
+    """Plain CE on small [rows, V] f32 logits (ITM: model.py:478).  -> (loss_sum, count, dlogits bf16)."""
+    rows, V = logits.shape
+    loss_sum, count = _z(logits, (1,)), _z(logits, (1,))
+    dl = _e(logits, (rows, V), BF16) if save else None
+    K.softmax_xent(logits.contiguous(), labels.contiguous(), V, loss_sum, count, dlogits=dl)
+    return loss_sum, count, dl

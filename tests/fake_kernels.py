@@ -72,7 +72,7 @@ class FakeKernels:
         if bias is not None:
             v = v + bias
         if out_pre is not None:
-            out_pre.copy_(v.to(torch.bfloat16))
+            out_pre.copy_(v)
         if act == ACT_GELU:
             v = F.gelu(v)
         elif act == ACT_RELU:
@@ -98,7 +98,7 @@ class FakeKernels:
             else:
                 out_f32.copy_(v)
         if out_bf16 is not None:
-            out_bf16.copy_(v.to(torch.bfloat16))
+            out_bf16.copy_(v)
 
     # ------------------------------------------------------------------ LayerNorm
     def layernorm_fwd(self, x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):
@@ -111,7 +111,7 @@ class FakeKernels:
         if y_f32 is not None:
             y_f32.copy_(y.reshape(y_f32.shape))
         if y_bf16 is not None:
-            y_bf16.copy_(y.reshape(y_bf16.shape).to(torch.bfloat16))
+            y_bf16.copy_(y.reshape(y_bf16.shape))
         if mean is not None:
             mean.copy_(mu.reshape(mean.shape))
         if rstd is not None:
@@ -129,7 +129,7 @@ class FakeKernels:
         if dx is not None:
             dx.copy_(tot.reshape(dx.shape))
         if dx_bf16 is not None:
-            dx_bf16.copy_((tot if bf16_total else val).reshape(dx_bf16.shape).to(torch.bfloat16))
+            dx_bf16.copy_((tot if bf16_total else val).reshape(dx_bf16.shape))
         if dgamma is not None:
             dgamma.add_((d * xh).sum(0))
         if dbeta is not None:
@@ -192,7 +192,7 @@ class FakeKernels:
         if y is not None:
             y.copy_(r)
         if y_bf16 is not None:
-            y_bf16.copy_(r.reshape(y_bf16.shape).to(torch.bfloat16))
+            y_bf16.copy_(r.reshape(y_bf16.shape))
 
     def act_grad(self, dy, aux, act, out_bf16, scale=1.0, scale_dev=None):
         self._launches += 1
@@ -207,7 +207,7 @@ class FakeKernels:
         else:
             assert act == ACT_NONE
         v = v * scale * (float(scale_dev.item()) if scale_dev is not None else 1.0)
-        out_bf16.copy_(v.reshape(out_bf16.shape).to(torch.bfloat16))
+        out_bf16.copy_(v.reshape(out_bf16.shape))
 
     def zero(self, p):
         self._launches += 1
@@ -235,7 +235,7 @@ class FakeKernels:
         BT, Cin, H, W = video.shape
         gh, gw = H // p, W // p
         x = video.reshape(BT, Cin, gh, p, gw, p).permute(0, 2, 4, 1, 3, 5).reshape(BT * gh * gw, Cin * p * p)
-        out.copy_(x.reshape(out.shape).to(torch.bfloat16))
+        out.copy_(x.reshape(out.shape))
 
     def assemble_tokens(self, patch, cls, pos, temporal, B, T, Nf, tokens):
         self._launches += 1
@@ -252,7 +252,7 @@ class FakeKernels:
         d = d_tokens.reshape(B, 1 + T * Nf, Cd)
         dp = d[:, 1:].reshape(B, T, Nf, Cd)
         if d_patch_bf16 is not None:
-            d_patch_bf16.copy_(dp.reshape(d_patch_bf16.shape).to(torch.bfloat16))
+            d_patch_bf16.copy_(dp.reshape(d_patch_bf16.shape))
         if d_cls is not None:
             d_cls.add_(d[:, 0].sum(0).reshape(d_cls.shape))
         if d_pos is not None:
@@ -295,7 +295,7 @@ class FakeKernels:
             p = torch.softmax(x, -1)
             p[torch.arange(x.shape[0], device=x.device), lab] -= 1.0
             p = p * valid[:, None]
-            dlogits[:, :V] = p.to(torch.bfloat16)
+            dlogits[:, :V] = p.to(dlogits.dtype)
 
     def xent_finalize(self, loss_sum, count, loss=None, inv_count=None):
         self._launches += 1
@@ -339,4 +339,4 @@ class FakeKernels:
         p.addcdiv_(m, v.sqrt().add_(eps), value=-step_size)
         p.add_(p, alpha=-lr * weight_decay)
         if p_bf16 is not None:
-            p_bf16.copy_(p.to(torch.bfloat16))
+            p_bf16.copy_(p)
