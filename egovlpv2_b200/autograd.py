@@ -1,0 +1,247 @@
+"""torch.autograd.Function wrappers around egovlpv2_b200.functional: one autograd node per reference module
+(SpaceTimeBlock, RobertaLayer, embeddings, heads, losses), so the hand-written CUDA backward plugs into
+torch's autograd graph, DDP gradient hooks, GradScaler and torch.utils.checkpoint unchanged.
+
+Convention: Fn.apply(cfg, w, <activations...>, *params) where `cfg` is a static description (plain object),
+`w` the dict of bf16 operand copies, and `params` the fp32 nn.Parameters in the order of cfg.names; backward
+returns one gradient per parameter in that order."""
+import types
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import functional as F_
+from . import lib as _lib
+
+
+def _K():
+    return _lib.kernels()
+
+
+def _pdict(names, params):
+    return {n: t.detach() for n, t in zip(names, params)}
+
+
+def _f32c(t):
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class VideoBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, w, x, y, y_bias, *params):
+        p = _pdict(cfg.names, params)
+        save = torch.is_grad_enabled() or any(ctx.needs_input_grad)
+        out, s = F_.video_block_fwd(_K(), _f32c(x), p, w, cfg.H, cfg.T, cfg.Nf, y=None if y is None else _f32c(y),
+                                    y_bias=y_bias, eps=cfg.eps, save=True)
+        ctx.cfg, ctx.w, ctx.s, ctx.p = cfg, w, s, p
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        cfg = ctx.cfg
+        dx, dy, g = F_.video_block_bwd(_K(), ctx.s, _f32c(d_out), ctx.p, ctx.w, cfg.H, cfg.T, cfg.Nf,
+                                       need_dx=ctx.needs_input_grad[2])
+        ctx.s = None
+        grads = tuple(g[n].view(ctx.p[n].shape) for n in cfg.names)
+        return (None, None, dx, dy, None) + grads
+
+
+class TextLayerFn(torch.autograd.Function):
+    """cfg.names lists the reference parameter names; q/k/v (and cross k/v) are concatenated for the kernels and the
+    concatenated gradients are split back here."""
+
+    @staticmethod
+    def forward(ctx, cfg, w, pcat, h, key_bias, video, *params):
+        p = _pdict(cfg.names, params)
+        p.update(pcat)
+        out, s = F_.text_layer_fwd(_K(), _f32c(h), key_bias, p, w, cfg.H, video=None if video is None else _f32c(video),
+                                   eps=cfg.eps, save=True)
+        ctx.cfg, ctx.w, ctx.s, ctx.p = cfg, w, s, p
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        cfg = ctx.cfg
+        dh, dvid, g = F_.text_layer_bwd(_K(), ctx.s, _f32c(d_out), ctx.p, ctx.w, cfg.H, need_dh=ctx.needs_input_grad[3])
+        ctx.s = None
+        sa = "attention.self."
+        g[sa + "query.weight"], g[sa + "key.weight"], g[sa + "value.weight"] = g["qkv"].chunk(3, 0)
+        g[sa + "query.bias"], g[sa + "key.bias"], g[sa + "value.bias"] = g["qkv.bias"].chunk(3, 0)
+        if "cross.kv" in g:
+            ca = "crossattention_t2i.self."
+            g[ca + "key.weight"], g[ca + "value.weight"] = g["cross.kv"].chunk(2, 0)
+            g[ca + "key.bias"], g[ca + "value.bias"] = g["cross.kv.bias"].chunk(2, 0)
+        grads = tuple(g[n].reshape(ctx.p[n].shape) for n in cfg.names)
+        return (None, None, None, dh, None, dvid) + grads
+
+
+class VideoTokensFn(torch.autograd.Function):
+    """params: patch_embed.proj.weight [C,3,p,p], patch_embed.proj.bias, pos_embed, temporal_embed, cls_token"""
+
+    @staticmethod
+    def forward(ctx, cfg, w, video, pw, pb, pos, tem, cls):
+        p = {"patch_embed.proj.bias": pb.detach(), "pos_embed": pos.detach(), "temporal_embed": tem.detach()}
+        tokens, s = F_.video_tokens_fwd(_K(), _f32c(video), p, w, cls.detach(), cfg.patch, save=True)
+        ctx.s, ctx.shapes = s, (pw.shape, pos.shape, tem.shape, cls.shape)
+        return tokens
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_tokens):
+        g = F_.video_tokens_bwd(_K(), ctx.s, _f32c(d_tokens))
+        ctx.s = None
+        sw, sp, st, sc = ctx.shapes
+        return (None, None, None, g["patch_embed.proj.weight"].view(sw), g["patch_embed.proj.bias"],
+                g["pos_embed"].view(sp), g["temporal_embed"].view(st), g["cls_token"].view(sc))
+
+
+class TextEmbedFn(torch.autograd.Function):
+    NAMES = ["word_embeddings.weight", "position_embeddings.weight", "token_type_embeddings.weight", "LayerNorm.weight",
+             "LayerNorm.bias"]
+
+    @staticmethod
+    def forward(ctx, cfg, ids, *params):
+        p = _pdict(TextEmbedFn.NAMES, params)
+        out, s = F_.text_embeddings_fwd(_K(), ids, p, eps=cfg.eps, pad_id=cfg.pad_id, save=True)
+        ctx.s, ctx.p = s, p
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        g = F_.text_embeddings_bwd(_K(), ctx.s, _f32c(d_out), ctx.p)
+        ctx.s = None
+        return (None, None) + tuple(g[n] for n in TextEmbedFn.NAMES)
+
+
+class LayerNormRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        y, s = F_.layernorm_rows_fwd(_K(), _f32c(x), gamma.detach(), beta.detach(), eps)
+        ctx.s, ctx.gamma = s, gamma.detach()
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        dx, dg, db = F_.layernorm_rows_bwd(_K(), ctx.s, _f32c(dy), ctx.gamma)
+        ctx.s = None
+        return dx, dg, db, None
+
+
+class MlpChainFn(torch.autograd.Function):
+    """cfg.acts: activation code per layer; cfg.has_bias: bool per layer; w: list of bf16 weights;
+    params: (weight, [bias]) per layer, flattened."""
+
+    @staticmethod
+    def forward(ctx, cfg, w, x, *params):
+        layers, it = [], iter(params)
+        for i, act in enumerate(cfg.acts):
+            next(it)
+            b = next(it).detach() if cfg.has_bias[i] else None
+            layers.append((w[i], b, act))
+        out, s = F_.mlp_chain_fwd(_K(), x.detach() if x.dtype == torch.bfloat16 else _f32c(x), layers, save=True)
+        ctx.cfg, ctx.layers, ctx.s = cfg, layers, s
+        ctx.wshapes = [t.shape for t in params]
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        dx, grads = F_.mlp_chain_bwd(_K(), ctx.s, _f32c(d_out), ctx.layers, need_dx=ctx.needs_input_grad[2])
+        ctx.s = None
+        flat = []
+        for i, (dW, db) in enumerate(grads):
+            flat.append(dW)
+            if ctx.cfg.has_bias[i]:
+                flat.append(db)
+        flat = [gr.view(shp) for gr, shp in zip(flat, ctx.wshapes)]
+        return (None, None, dx) + tuple(flat)
+
+
+class MlmLossFn(torch.autograd.Function):
+    NAMES = ["cross_modal_text_transform.weight", "cross_modal_text_transform.bias", "mlm_score.transform.dense.weight",
+             "mlm_score.transform.dense.bias", "mlm_score.transform.LayerNorm.weight", "mlm_score.transform.LayerNorm.bias",
+             "mlm_score.decoder.weight", "mlm_score.bias"]
+
+    @staticmethod
+    def forward(ctx, w, h, labels, *params):
+        """-> (loss_sum [1], count [1], logits [B,S,V] (not differentiable)).  The caller divides by the (global)
+        count; d(loss)/d(loss_sum) arrives as the gradient of the first output."""
+        p = _pdict(MlmLossFn.NAMES, params)
+        logits, loss_sum, count, s = F_.mlm_head_fwd(_K(), _f32c(h), labels, p, w, save=True)
+        ctx.s, ctx.p, ctx.w = s, p, w
+        B, S, _ = h.shape
+        logits3 = logits.view(B, S, logits.shape[-1]) if logits.is_contiguous() else logits.unflatten(0, (B, S))
+        ctx.mark_non_differentiable(count, logits3)
+        return loss_sum, count, logits3
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_loss_sum, _dc, _dl):
+        dh, g = F_.mlm_head_bwd(_K(), ctx.s, _f32c(d_loss_sum).reshape(1), ctx.p, ctx.w)
+        ctx.s = None
+        return (None, dh, None) + tuple(g[n].view(ctx.p[n].shape) for n in MlmLossFn.NAMES)
+
+
+class XentFn(torch.autograd.Function):
+    """(loss_sum, count) of softmax cross-entropy on small fp32 logits (ITM head)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        K = _K()
+        lg = _f32c(logits)
+        rows, V = lg.shape
+        loss_sum = torch.zeros(1, device=lg.device)
+        count = torch.zeros(1, device=lg.device)
+        dl = torch.empty(rows, V, dtype=torch.float32, device=lg.device)
+        K.softmax_xent(lg, labels.contiguous(), V, loss_sum, count, dlogits=dl)
+        ctx.dl = dl
+        ctx.mark_non_differentiable(count)
+        return loss_sum, count
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_loss_sum, _dc):
+        out = torch.empty_like(ctx.dl)
+        _K().axpy(None, ctx.dl, 1.0, _f32c(d_loss_sum).reshape(1), y=out)
+        return out, None
+
+
+class EgoNceFn(torch.autograd.Function):
+    """sim_matrix + EgoNCE on gathered embeddings (model.py:385-394, loss.py:40-61); gradients for this rank's rows
+    only (trainer_egoclip.py:36-41: the all-gather's backward is the local slice)."""
+
+    @staticmethod
+    def forward(ctx, t_local, v_local, t_all, v_all, noun_all, verb_all, temperature, row0):
+        K = _K()
+        G, P = t_all.shape
+        n = t_local.shape[0]
+        dev = t_all.device
+        sim = torch.empty(G, G, device=dev)
+        mask = torch.empty(G, G, dtype=torch.uint8, device=dev)
+        loss = torch.empty(1, device=dev)
+        dt, dv = torch.empty(n, P, device=dev), torch.empty(n, P, device=dev)
+        K.egonce(_f32c(t_all), _f32c(v_all), _f32c(noun_all), _f32c(verb_all), temperature, sim, mask, loss, row0, n, dt, dv)
+        ctx.dt, ctx.dv = dt, dv
+        ctx.mark_non_differentiable(sim, mask)
+        return loss.reshape(()), sim, mask
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_loss, _ds, _dm):
+        K = _K()
+        g = _f32c(d_loss).reshape(1)
+        dt, dv = torch.empty_like(ctx.dt), torch.empty_like(ctx.dv)
+        K.axpy(None, ctx.dt, 1.0, g, y=dt)
+        K.axpy(None, ctx.dv, 1.0, g, y=dv)
+        return dt, dv, None, None, None, None, None, None
+
+
+def cfg(**kw):
+    return types.SimpleNamespace(**kw)

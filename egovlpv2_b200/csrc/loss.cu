@@ -29,17 +29,21 @@ EGV_DEVINL float block_sum(float v, float* red) {
 }
 
 // one block per row: loss_sum += lse - logit[label], count += 1, dlogits = softmax - onehot (0 for ignored rows)
+EGV_DEVINL void st_grad(bf16* p, float v) { *p = __float2bfloat16(v); }
+EGV_DEVINL void st_grad(float* p, float v) { *p = v; }
+
+template <typename DT>
 __global__ void __launch_bounds__(256) xent_kernel(const float* __restrict__ logits, long long ld,
                                                    const long long* __restrict__ labels, int V, int ignore_index,
                                                    float* __restrict__ loss_sum, float* __restrict__ count,
-                                                   bf16* __restrict__ dlogits, long long ld_d) {
+                                                   DT* __restrict__ dlogits, long long ld_d) {
   __shared__ float red[8];
   const long long row = blockIdx.x;
   const long long label = labels[row];
   const float* x = logits + row * ld;
-  bf16* d = dlogits ? dlogits + row * ld_d : nullptr;
+  DT* d = dlogits ? dlogits + row * ld_d : nullptr;
   if (label == ignore_index) {
-    if (d) for (int c = threadIdx.x; c < V; c += 256) d[c] = __float2bfloat16(0.f);
+    if (d) for (int c = threadIdx.x; c < V; c += 256) st_grad(d + c, 0.f);
     return;
   }
   float mx = -INFINITY;
@@ -58,7 +62,7 @@ __global__ void __launch_bounds__(256) xent_kernel(const float* __restrict__ log
     for (int c = threadIdx.x; c < V; c += 256) {
       float p = __expf(x[c] - mx) * inv;
       if (c == label) p -= 1.0f;
-      d[c] = __float2bfloat16(p);
+      st_grad(d + c, p);
     }
   }
 }
@@ -192,11 +196,16 @@ __global__ void __launch_bounds__(256) egonce_grad_kernel(const float* __restric
 using namespace egv;
 
 extern "C" int egv_softmax_xent(const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int V, int ignore_index,
-                                float* loss_sum, float* count, void* dlogits_bf16, int64_t ld_d, egv_stream_t stream) {
+                                float* loss_sum, float* count, void* dlogits, int dlogits_is_f32, int64_t ld_d,
+                                egv_stream_t stream) {
   if (!logits || !labels || !loss_sum || !count) return fail(EGV_ERR_ARG, "softmax_xent: null pointer");
   if (rows <= 0) return EGV_OK;
-  xent_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, (const long long*)labels, V, ignore_index, loss_sum,
-                                                                 count, (bf16*)dlogits_bf16, ld_d);
+  if (dlogits_is_f32)
+    xent_kernel<float><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, (const long long*)labels, V, ignore_index,
+                                                                          loss_sum, count, (float*)dlogits, ld_d);
+  else
+    xent_kernel<bf16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, (const long long*)labels, V, ignore_index,
+                                                                         loss_sum, count, (bf16*)dlogits, ld_d);
   return check_launch("xent_kernel");
 }
 

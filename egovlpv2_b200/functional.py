@@ -458,8 +458,11 @@ def mlp_chain_fwd(K, x, layers, save=True):
     layers: list of (w_bf16 [N,Kd], bias f32 or None, act in {ACT_NONE, ACT_RELU, ACT_TANH, ACT_GELU}).
     Returns (out f32 [M, N_last], saved)."""
     M = x.shape[0]
-    cur = _e(x, x.shape, BF16)
-    K.cast(x.contiguous(), cur)
+    if x.dtype == BF16:
+        cur = x.contiguous()
+    else:
+        cur = _e(x, x.shape, BF16)
+        K.cast(x.contiguous(), cur)
     saved = []
     out = None
     for i, (wt, b, act) in enumerate(layers):

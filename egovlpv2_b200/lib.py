@@ -312,10 +312,12 @@ class Kernels:
         assert labels.dtype == torch.int64 and labels.is_contiguous() and labels.numel() == logits.shape[0]
         ld_d = 0
         if dlogits is not None:
-            assert dlogits.dtype == torch.bfloat16 and dlogits.stride(1) == 1 and dlogits.shape[0] == logits.shape[0]
+            assert dlogits.dtype in (torch.bfloat16, torch.float32) and dlogits.stride(1) == 1
+            assert dlogits.shape[0] == logits.shape[0]
             ld_d = dlogits.stride(0)
+        is_f32 = int(dlogits is not None and dlogits.dtype == torch.float32)
         self._check(self.lib.egv_softmax_xent(_p(logits), c_int64(logits.stride(0)), _p(labels), c_int64(logits.shape[0]),
-                                              V, ignore_index, _p(loss_sum), _p(count), _p(dlogits), c_int64(ld_d),
+                                              V, ignore_index, _p(loss_sum), _p(count), _p(dlogits), is_f32, c_int64(ld_d),
                                               self._stream()))
 
     def xent_finalize(self, loss_sum, count, loss=None, inv_count=None):

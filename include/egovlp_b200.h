@@ -163,9 +163,10 @@ int egv_text_embed_bwd(const float* d_out, const int64_t* ids, int B, int S, int
 /* Losses ------------------------------------------------------------------------------------------
  * softmax cross-entropy with ignore_index (model.py:414-418, 478): per-row loss and dlogits.
  * logits f32 [rows, ld] (V valid columns); writes loss_sum[0] += sum of valid-row losses,
- * count[0] += valid rows; dlogits (bf16 [rows, ld_d], may be NULL) = softmax - onehot (unscaled). */
+ * count[0] += valid rows; dlogits ([rows, ld_d] bf16, or f32 when dlogits_is_f32; may be NULL) = softmax - onehot
+ * (unscaled; rows with label == ignore_index are zero). */
 int egv_softmax_xent(const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int V, int ignore_index,
-                     float* loss_sum, float* count, void* dlogits_bf16, int64_t ld_d, egv_stream_t stream);
+                     float* loss_sum, float* count, void* dlogits, int dlogits_is_f32, int64_t ld_d, egv_stream_t stream);
 /* loss[0] = loss_sum / max(count, 1); inv_count[0] = 1 / max(count, 1)  (device scalars: no host sync) */
 int egv_xent_finalize(const float* loss_sum, const float* count, float* loss, float* inv_count, egv_stream_t stream);
 /* EgoNCE (model.py:385-394, 576-584 sim_matrix; loss.py:40-61).

@@ -151,9 +151,11 @@ class FakeKernels:
         qf = q.float().detach().clone().requires_grad_(True)
         kf = k.float().detach().clone().requires_grad_(True)
         vf = v.float().detach().clone().requires_grad_(True)
-        og, _, qi, ki = attn_reference(spec, qf, kf, vf, key_bias)
+        with torch.enable_grad():
+            og, _, qi, ki = attn_reference(spec, qf, kf, vf, key_bias)
         dog = d_o.float().reshape(B, d_o.shape[1], H, 64)[:, qi].permute(0, 3, 1, 2, 4)
-        og.backward(dog)
+        with torch.enable_grad():
+            og.backward(dog)
         delta.copy_((dog * og.detach()).sum(-1).reshape(delta.shape))
 
         def scatter_rows(dst, grad, rows, accumulate):
@@ -315,12 +317,13 @@ class FakeKernels:
             bn = b / b.norm(dim=1, keepdim=True).clamp_min(1e-8)
             return an @ bn.t()
 
-        s = sm(tt, vv)
-        m = (sm(verb, verb) * sm(noun, noun) + torch.eye(t.shape[0], device=t.device)) > 0
-        i_sm = torch.softmax(s / temperature, 1)
-        j_sm = torch.softmax(s.t() / temperature, 1)
-        L = -torch.log((i_sm * m).sum(1)).mean() - torch.log((j_sm * m).sum(1)).mean()
-        L.backward()
+        with torch.enable_grad():
+            s = sm(tt, vv)
+            m = (sm(verb, verb) * sm(noun, noun) + torch.eye(t.shape[0], device=t.device)) > 0
+            i_sm = torch.softmax(s / temperature, 1)
+            j_sm = torch.softmax(s.t() / temperature, 1)
+            L = -torch.log((i_sm * m).sum(1)).mean() - torch.log((j_sm * m).sum(1)).mean()
+            L.backward()
         sim.copy_(s.detach())
         mask.copy_(m.to(torch.uint8))
         loss.copy_(L.detach().reshape(loss.shape))

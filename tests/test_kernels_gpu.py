@@ -403,12 +403,17 @@ def test_softmax_xent(K, R):
         ls, cnt = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
         dl = torch.full((rows, ld), 7.0, dtype=torch.bfloat16, device=DEV)
         impl.softmax_xent(logits, labels, V, ls, cnt, dlogits=dl[:, :V])
+        dl32 = torch.full((rows, V), 7.0, device=DEV)
+        ls2, cnt2 = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+        impl.softmax_xent(logits, labels, V, ls2, cnt2, dlogits=dl32)
+        assert torch.equal(ls, ls2) or abs((ls - ls2).item()) < 1e-3
         loss, inv = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
         impl.xent_finalize(ls, cnt, loss, inv)
-        r.append((loss, inv, dl))
+        r.append((loss, inv, dl, dl32))
     check(r[0][0], r[1][0], 1e-5, "xent loss")
     check(r[0][1], r[1][1], 1e-6, "xent inv count")
     check(r[0][2], r[1][2], 4e-3, "xent dlogits")
+    check(r[0][3], r[1][3], 1e-5, "xent dlogits f32")
     ref = torch.nn.functional.cross_entropy(logits, labels, ignore_index=-100)
     check(r[0][0], ref.reshape(1), 1e-5, "xent vs torch")
 
