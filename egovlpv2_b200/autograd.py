@@ -227,6 +227,7 @@ class EgoNceFn(torch.autograd.Function):
         mask = torch.empty(G, G, dtype=torch.uint8, device=dev)
         loss = torch.empty(1, device=dev)
         dt, dv = torch.empty(n, P, device=dev), torch.empty(n, P, device=dev)
+        K.mark("egonce")
         K.egonce(_f32c(t_all), _f32c(v_all), _f32c(noun_all), _f32c(verb_all), temperature, sim, mask, loss, row0, n, dt, dv)
         ctx.dt, ctx.dv = dt, dv
         ctx.mark_non_differentiable(sim, mask)

@@ -106,6 +106,7 @@ def video_block_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=Tr
     M = B * N
     x2 = x.reshape(M, C)
     s = types.SimpleNamespace(fused=y is not None, shape=(B, N, C), x=x2)
+    K.mark("video_block")
     # ---- time attention branch: t = proj(attn_time(qkv(norm3(x))))
     s.ln3, s.mean3, s.rstd3 = _e(x, (M, C), BF16), _e(x, (M,), F32), _e(x, (M,), F32)
     K.layernorm_fwd(x2, p["norm3.weight"], p["norm3.bias"], eps, y_bf16=s.ln3, mean=s.mean3, rstd=s.rstd3)
@@ -130,6 +131,7 @@ def video_block_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=Tr
         xa = _e(x, (M, C), F32)
         K.gemm(GEMM_NT, s.o_s.view(M, C), w["attn.proj.weight"], bias=p["attn.proj.bias"], residual=x2, out_f32=xa,
                out_pre=s.a)
+        K.mark("xattn_i2t_fwd")
         s.lnc, s.meanc, s.rstdc = _e(x, (M, C), BF16), _e(x, (M,), F32), _e(x, (M,), F32)
         K.layernorm_fwd(s.a, p["attn.norm_i2t_i.weight"], p["attn.norm_i2t_i.bias"], eps, y_bf16=s.lnc, mean=s.meanc,
                         rstd=s.rstdc)
@@ -149,6 +151,7 @@ def video_block_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=Tr
         K.gemm(GEMM_NT, s.o_c.view(M, C), w["attn.proj_i2t.weight"], bias=p["attn.proj_i2t.bias"],
                scale_dev=p["attn.alpha_i2t"], residual=xa, out_f32=s.sr, out_pre=s.c)
     # ---- MLP
+    K.mark("video_block")
     s.ln2, s.mean2, s.rstd2 = _e(x, (M, C), BF16), _e(x, (M,), F32), _e(x, (M,), F32)
     K.layernorm_fwd(s.sr, p["norm2.weight"], p["norm2.bias"], eps, y_bf16=s.ln2, mean=s.mean2, rstd=s.rstd2)
     Hd = w["mlp.fc1.weight"].shape[0]
@@ -164,6 +167,7 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True):
     B, N, C = s.shape
     M = B * N
     g = {}
+    K.mark("video_block_bwd")
     d_out = d_out.reshape(M, C)
     d_out_bf = _e(d_out, (M, C), BF16)
     K.cast(d_out.contiguous(), d_out_bf)
@@ -185,6 +189,7 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True):
     if s.fused:
         S, Ct = s.y_bf.shape[0] // B, s.y_bf.shape[1]
         alpha = p["attn.alpha_i2t"]
+        K.mark("xattn_i2t_bwd")
         # sr = x + a + alpha * c,  c = proj_i2t(o_c)
         g["attn.alpha_i2t"] = _e(d_out, (1,), F32)
         K.dot(d_sr, s.c, g["attn.alpha_i2t"])
@@ -209,6 +214,7 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True):
         K.layernorm_bwd(d_lnc, s.a, p["attn.norm_i2t_i.weight"], s.meanc, s.rstdc, add=d_sr, dx=None, dx_bf16=d_a_bf,
                         bf16_total=True, dgamma=g["attn.norm_i2t_i.weight"], dbeta=g["attn.norm_i2t_i.bias"])
         d_s_bf = d_a_bf
+        K.mark("video_block_bwd")
     # ---- space attention: s = proj(attn_space(qkv(ln1)))
     g["attn.proj.weight"], g["attn.proj.bias"] = linear_bwd_params(K, d_s_bf, s.o_s.view(M, C))
     d_os = _e(d_out, (B, N, C), BF16)
@@ -259,6 +265,7 @@ def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True):
     h2 = h.reshape(M, C)
     d = C // H
     s = types.SimpleNamespace(fused=video is not None, shape=(B, S, C), key_bias=key_bias)
+    K.mark("text_layer")
     s.h_bf = _e(h, (M, C), BF16)
     K.cast(h2.contiguous(), s.h_bf)
     s.qkv = _e(h, (M, 3 * C), BF16)
@@ -275,6 +282,7 @@ def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True):
            residual=h2, out_f32=sh, out_pre=s.so_bf)
     if s.fused:
         Bv, N, Cv = video.shape
+        K.mark("xattn_t2i_fwd")
         s.vshape = (Bv, N, Cv)
         s.x_bf = _e(h, (Bv * N, Cv), BF16)
         K.cast(video.reshape(Bv * N, Cv).contiguous(), s.x_bf)
@@ -294,6 +302,7 @@ def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True):
                bias=p["crossattention_t2i.output.dense.bias"], scale_dev=p["alpha_t2i"], residual=sh, out_f32=sh2,
                out_pre=s.c)
         sh = sh2
+        K.mark("text_layer")
     s.sh = sh
     s.a, s.a_bf = _e(h, (M, C), F32), _e(h, (M, C), BF16)
     s.mean_a, s.rstd_a = _e(h, (M,), F32), _e(h, (M,), F32)
@@ -318,6 +327,7 @@ def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True):
     B, S, C = s.shape
     M = B * S
     g = {}
+    K.mark("text_layer_bwd")
     d_out = d_out.reshape(M, C).contiguous()
     # out = LN_o(fa)
     d_fa, d_fa_bf = _e(d_out, (M, C), F32), _e(d_out, (M, C), BF16)
@@ -342,6 +352,7 @@ def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True):
     if s.fused:
         Bv, N, Cv = s.vshape
         alpha = p["alpha_t2i"]
+        K.mark("xattn_t2i_bwd")
         g["alpha_t2i"] = _e(d_out, (1,), F32)
         K.dot(d_sh, s.c, g["alpha_t2i"])
         g["crossattention_t2i.output.dense.weight"], g["crossattention_t2i.output.dense.bias"] = linear_bwd_params(
@@ -361,6 +372,7 @@ def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True):
         # d_so = d_sh + Wq_x'(dqx)
         d_so_bf = _e(d_out, (M, C), BF16)
         K.gemm(GEMM_NN, dqx2, w["crossattention_t2i.self.query.weight"], residual=d_sh, out_bf16=d_so_bf)
+        K.mark("text_layer_bwd")
     g["attention.output.dense.weight"], g["attention.output.dense.bias"] = linear_bwd_params(K, d_so_bf, s.o.view(M, C))
     d_o = _e(d_out, (B, S, C), BF16)
     K.gemm(GEMM_NN, d_so_bf, w["attention.output.dense.weight"], out_bf16=d_o.view(M, C))
@@ -385,6 +397,7 @@ def video_tokens_fwd(K, video, p, w, cls_token, patch, save=True):
     B, T, Cin, Hh, Ww = video.shape
     Nf = (Hh // patch) * (Ww // patch)
     C = w["patch_embed.proj.weight"].shape[0]
+    K.mark("embed")
     cols = _e(video, (B * T * Nf, Cin * patch * patch), BF16)
     K.patchify(video.reshape(B * T, Cin, Hh, Ww).contiguous(), patch, cols)
     pe = _e(video, (B * T * Nf, C), F32)
@@ -399,6 +412,7 @@ def video_tokens_fwd(K, video, p, w, cls_token, patch, save=True):
 def video_tokens_bwd(K, s, d_tokens):
     """-> grads dict: patch_embed.proj.{weight [C, 3*p*p] flattened, bias}, pos_embed, temporal_embed, cls_token."""
     B, T, Nf, C = s.B, s.T, s.Nf, s.C
+    K.mark("embed_bwd")
     d_patch = _e(d_tokens, (B * T * Nf, C), BF16)
     g = {"cls_token": _z(d_tokens, (C,)), "pos_embed": _z(d_tokens, (1 + Nf, C)), "temporal_embed": _z(d_tokens, (s.t_max, C))}
     K.assemble_tokens_bwd(d_tokens.contiguous(), B, T, Nf, d_patch, g["cls_token"], g["pos_embed"], g["temporal_embed"])
@@ -411,6 +425,7 @@ def text_embeddings_fwd(K, ids, p, eps=1e-5, pad_id=1, save=True):
     B, S = ids.shape
     C = p["word_embeddings.weight"].shape[1]
     ids = ids.contiguous()
+    K.mark("embed")
     pre = _e(p["LayerNorm.weight"], (B, S, C), F32)
     K.text_embed(ids, p["word_embeddings.weight"], p["position_embeddings.weight"],
                  p["token_type_embeddings.weight"].reshape(-1)[:C].contiguous(), pre, pad_id)
@@ -423,6 +438,7 @@ def text_embeddings_fwd(K, ids, p, eps=1e-5, pad_id=1, save=True):
 
 def text_embeddings_bwd(K, s, d_out, p):
     C = s.pre.shape[-1]
+    K.mark("embed_bwd")
     g = {"LayerNorm.weight": _z(d_out, (C,)), "LayerNorm.bias": _z(d_out, (C,))}
     d_pre = _e(d_out, s.pre.shape, F32)
     K.layernorm_bwd(d_out.contiguous(), s.pre, p["LayerNorm.weight"], s.mean, s.rstd, dx=d_pre, dgamma=g["LayerNorm.weight"],
@@ -458,6 +474,7 @@ def mlp_chain_fwd(K, x, layers, save=True):
     layers: list of (w_bf16 [N,Kd], bias f32 or None, act in {ACT_NONE, ACT_RELU, ACT_TANH, ACT_GELU}).
     Returns (out f32 [M, N_last], saved)."""
     M = x.shape[0]
+    K.mark("heads")
     if x.dtype == BF16:
         cur = x.contiguous()
     else:
@@ -485,6 +502,7 @@ def mlp_chain_bwd(K, saved, d_out, layers, scale_dev=None, need_dx=True):
     The gradient of every activation is folded into the epilogue of the GEMM that produces it; only a
     trailing activation of the LAST layer needs the stand-alone act_grad kernel."""
     grads = [None] * len(layers)
+    K.mark("heads_bwd")
     last = len(layers) - 1
     act = layers[last][2]
     aux = None if act == ACT_NONE else (saved[last][2] if act == ACT_GELU else saved[last][1])
@@ -519,6 +537,7 @@ def mlm_head_fwd(K, h, labels, p, w, save=True):
     layers = [(w["cross_modal_text_transform.weight"], p["cross_modal_text_transform.bias"], ACT_NONE),
               (w["mlm_score.transform.dense.weight"], p["mlm_score.transform.dense.bias"], ACT_GELU)]
     t, chain = mlp_chain_fwd(K, h.reshape(M, C), layers)
+    K.mark("mlm_head")
     tn = _e(h, (M, C), BF16)
     mean, rstd = _e(h, (M,), F32), _e(h, (M,), F32)
     K.layernorm_fwd(t, p["mlm_score.transform.LayerNorm.weight"], p["mlm_score.transform.LayerNorm.bias"], 1e-12, y_bf16=tn,
@@ -543,6 +562,7 @@ def mlm_head_bwd(K, s, scale_dev, p, w):
     B, S, C = s.shape
     M = B * S
     g = {}
+    K.mark("mlm_head_bwd")
     g["mlm_score.decoder.weight"], g["mlm_score.bias"] = linear_bwd_params(K, s.dlogits, s.tn, scale_dev=scale_dev)
     d_tn = _e(s.t, (M, C), BF16)
     K.gemm(GEMM_NN, s.dlogits, w["mlm_score.decoder.weight"], scale_dev=scale_dev, out_bf16=d_tn)

@@ -92,6 +92,35 @@ class Kernels:
 
     def __init__(self):
         self.lib = _load()
+        self.profile = None      # list of (region, kind, work, start_event, stop_event) when profiling is on
+        self._region = "other"
+
+    # ------------------------------------------------------------------ per-launch timing (bench.py roofline)
+    def mark(self, region):
+        """Label the kernels launched from here on (cheap; only read while profiling)."""
+        self._region = region
+
+    def start_profile(self):
+        self.profile = []
+
+    def stop_profile(self):
+        """-> {(region, kind): (seconds, work, launches)}; call after a stream synchronize."""
+        out = {}
+        for region, kind, work, e0, e1 in self.profile:
+            t, w, n = out.get((region, kind), (0.0, 0.0, 0))
+            out[(region, kind)] = (t + e0.elapsed_time(e1) * 1e-3, w + work, n + 1)
+        self.profile = None
+        return out
+
+    def _timed(self, kind, work, fn):
+        if self.profile is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        self.profile.append((self._region, kind, work, e0, e1))
+        return r
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -152,7 +181,7 @@ class Kernels:
             a.scale_dev = _p(scale_dev)
         a.scale = float(scale)
         a.act, a.accumulate, a.split_k = int(act), int(bool(accumulate)), int(split_k)
-        self._check(self.lib.egv_gemm_bf16(C.byref(a), self._stream()))
+        self._timed("gemm", 2.0 * M * N * K, lambda: self._check(self.lib.egv_gemm_bf16(C.byref(a), self._stream())))
 
     # ------------------------------------------------------------------ LayerNorm
     def layernorm_fwd(self, x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):
@@ -210,7 +239,8 @@ class Kernels:
 
     def attention_fwd(self, spec, q, k, v, o, lse, key_bias=None):
         a = self._attn_args(spec, q, k, v, o, lse, key_bias)
-        self._check(self.lib.egv_attention_fwd(C.byref(a), self._stream()))
+        work = 4.0 * a.B * spec.H * spec.G * spec.Lq * (spec.Lk + int(spec.has_cls_key)) * 64
+        self._timed("attn_fwd", work, lambda: self._check(self.lib.egv_attention_fwd(C.byref(a), self._stream())))
 
     def attention_bwd(self, spec, q, k, v, o, lse, d_o, dq, dk, dv, delta, dkv_cls=None, dkv_accumulate=False,
                       key_bias=None):
@@ -226,7 +256,8 @@ class Kernels:
             assert dkv_cls.dtype == torch.float32 and dkv_cls.numel() == a.B * spec.H * 128
             a.dkv_cls = _p(dkv_cls)
         a.dkv_accumulate = int(bool(dkv_accumulate))
-        self._check(self.lib.egv_attention_bwd(C.byref(a), self._stream()))
+        work = 8.0 * a.B * spec.H * spec.G * spec.Lq * (spec.Lk + int(spec.has_cls_key)) * 64
+        self._timed("attn_bwd", work, lambda: self._check(self.lib.egv_attention_bwd(C.byref(a), self._stream())))
 
     def attention_cls_finalize(self, dkv_cls, dk, dv, H, cls_row=0, accumulate=False):
         ld, bs = self._rows3(dk, "dk")

@@ -1,0 +1,110 @@
+"""One EgoNCE+MLM+ITM pre-training step (trainer_egoclip.py:106-150 + base_trainer.py:324-393) on the B200 kernels:
+H2D of the batch, FrozenInTime.forward (three passes), backward, gradient all-reduce (N > 1), fused AdamW.
+
+This is the host driver used by bench.py and __graft_entry__.smoke(); the reference's own trainer can drive the same
+model unchanged."""
+import types
+
+import torch
+import torch.distributed as dist
+
+from . import lib as _lib
+from .comm import NcclAllGather, P2PAllGather
+from .model.loss import EgoNCE
+from .model.model import DEFAULT_CONFIG, FrozenInTime
+from .optim import FusedAdamW
+
+
+def model_config(C=768, heads=12, depth=12, n_fuse=6, vocab=50265):
+    return dict(DEFAULT_CONFIG, input_image_embed_size=C, input_text_embed_size=C, hidden_size=C, num_heads=heads,
+                num_layers=depth, num_fuse_block=n_fuse, vocab_size=vocab)
+
+
+def build_model(T=16, img=224, C=768, heads=12, depth=12, n_fuse=6, vocab=50265, proj=4096, tasks="EgoNCE_ITM_MLM"):
+    return FrozenInTime(
+        video_params=dict(model="SpaceTimeTransformer", arch_config="base_patch16_224", num_frames=T, pretrained=True,
+                          time_init="zeros", img_size=img, embed_dim=C, depth=depth, num_heads=heads),
+        text_params=dict(model="roberta-base", pretrained=True, input="text",
+                         config=dict(hidden_size=C, num_hidden_layers=depth, num_attention_heads=heads,
+                                     intermediate_size=4 * C, vocab_size=vocab)),
+        projection_dim=proj, config=model_config(C, heads, depth, n_fuse, vocab), task_names=tasks, embed_dim=C)
+
+
+def randomize_gates(model, seed=0):
+    """The reference zero-initialises the fusion gates and the time attention, which would let a
+    benchmark skip real work numerically; give them non-trivial values (same recipe as the parity oracle)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("alpha_i2t") or n.endswith("alpha_t2i"):
+                p.fill_(0.5)
+            elif ".timeattn." in n:
+                p.copy_((0.02 * torch.randn(p.shape, generator=g)).to(p.device))
+
+
+class PretrainStep:
+    def __init__(self, model, device, lr=3e-5, weight_decay=0.01, lr_mult_head=1.0, lr_mult_cross_modal=4.0,
+                 tasks="EgoNCE_MLM_ITM", gather="auto", max_steps=None, warmup_steps=0):
+        self.device = device
+        self.model = model.to(device)
+        self.tasks = tasks
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.opt = FusedAdamW(self.model, lr, weight_decay, lr_mult_head, lr_mult_cross_modal, max_steps=max_steps,
+                              warmup_steps=warmup_steps)
+        self.loss_fn = EgoNCE()
+        self.args = types.SimpleNamespace(world_size=self.world, rank=self.rank)
+        self.gather_kind = "none"
+        if self.world > 1:
+            if gather in ("auto", "p2p"):
+                try:
+                    self.allgather = P2PAllGather(device)
+                    self.gather_kind = "p2p"
+                except Exception:
+                    if gather == "p2p":
+                        raise
+                    self.allgather = NcclAllGather()
+                    self.gather_kind = "nccl"
+            else:
+                self.allgather = NcclAllGather()
+                self.gather_kind = "nccl"
+        else:
+            self.allgather = lambda t, n=None, a=None: t
+        self.cfg = {"loss": {"type": "EgoNCE"}}
+
+    def to_device(self, host_batch):
+        """H2D of one step's inputs from pinned host memory (non-blocking on the current stream)."""
+        return {k: v.to(self.device, non_blocking=True) for k, v in host_batch.items()}
+
+    def step(self, dev_batch):
+        """forward + backward + (all-reduce) + AdamW; returns the detached total loss (device scalar)."""
+        d = dev_batch
+        data = {"video": d["video"], "text": {"input_ids": d["input_ids"], "attention_mask": d["attention_mask"]},
+                "text_mlm_ids": d["text_mlm_ids"], "text_mlm_labels": d["text_mlm_labels"]}
+        self.opt.zero_grad()
+        loss, loss_dict, _ = self.model(data, d["noun_vec"], d["verb_vec"], self.allgather, self.world, self.args, self.cfg,
+                                        self.loss_fn, self.rank, task_names=self.tasks)
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.opt.arena.grad)          # DDP semantics: average over ranks (base_trainer.py:269)
+            self.opt.step(grad_scale=1.0 / self.world)
+        else:
+            self.opt.step()
+        return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}
+
+
+def step_flops(B, T, img=224, patch=16, S=32, C=768, depth=12, n_fuse=6, P=4096, V=50265):
+    """Algorithmic FLOPs of one step (fwd + bwd = 3x fwd, no recompute) -- SURVEY.md section 8(d)."""
+    Nf = (img // patch) ** 2
+    N = T * Nf + 1
+    vblk = 32 * N * C * C + 4 * (N - 1) * C * ((T + 1) + (Nf + 1)) + 8 * N * C
+    xattn = 4 * N * C * C + 4 * S * C * C + 4 * N * S * C
+    tblk = 24 * S * C * C + 4 * S * S * C
+    patch_f = 2 * T * Nf * (3 * patch * patch) * C
+    proj = 2 * (C * P + 2 * P * P)
+    mlm_head = 2 * S * C * C + S * (2 * C * C + 2 * C * V)
+    itm_head = 8 * C * C
+    pass_nce = patch_f + depth * vblk + depth * tblk + 2 * proj
+    pass_fused = patch_f + depth * vblk + n_fuse * xattn + depth * tblk + n_fuse * xattn
+    fwd = pass_nce + (pass_fused + mlm_head) + (pass_fused + itm_head)
+    return 3.0 * B * fwd, dict(vblk=vblk, xattn=xattn, fwd_per_sample=fwd)

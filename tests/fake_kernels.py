@@ -58,6 +58,9 @@ class FakeKernels:
     def force_simt(self, on):
         pass
 
+    def mark(self, region):
+        pass
+
     # ------------------------------------------------------------------ GEMM
     def gemm(self, layout, A, B, *, bias=None, aux=None, act=ACT_NONE, scale=1.0, scale_dev=None, residual=None,
              out_f32=None, out_bf16=None, out_pre=None, accumulate=False, split_k=1):

@@ -1,0 +1,214 @@
+"""-m gpu: the CUDA path behind the drop-in module API against (a) the golden vectors produced by the UNMODIFIED
+reference and (b) the fp32 oracle run on the same device, at toy and at full width (C=768, 12 heads).
+
+Stated tolerances (SURVEY.md section 8d, bf16 operands / fp32 accumulate vs the fp32 reference): block outputs
+rel-L2 <= 1e-2; sim_v2t abs <= 1.5e-2; loss terms rel <= 2e-2; block-level gradients rel-L2 <= 3e-2; end-to-end
+gradients of the 4-clip toy step rel-L2 <= 0.4 (EgoNCE temperature 0.05 amplifies cosine errors 20x; see
+tests/test_model_cpu.py)."""
+import os
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from egovlpv2_b200 import functional as Fn  # noqa: E402
+from egovlpv2_b200 import lib as L  # noqa: E402
+from egovlpv2_b200 import weights  # noqa: E402
+from egovlpv2_b200.model.loss import EgoNCE  # noqa: E402
+from egovlpv2_b200.model.roberta import RobertaConfig, RobertaLayer  # noqa: E402
+from egovlpv2_b200.model import roberta as rb  # noqa: E402
+from egovlpv2_b200.model.video_transformer import SpaceTimeBlock  # noqa: E402
+from oracle import egovlp_oracle as O  # noqa: E402
+from tests.test_model_cpu import _golden, build_tiny  # noqa: E402
+
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def real_kernels():
+    L.set_kernels(None)
+    weights.cache().arena = None
+    weights.cache().clear()
+    assert Fn.BF16 == torch.bfloat16
+    yield L.kernels()
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-9)).item()
+
+
+def test_tiny_pretrain_step_vs_reference_golden(golden_dir):
+    fx, c, shapes, sd, data, plan = _golden(golden_dir)
+    model = build_tiny(c)
+    model.load_state_dict(sd, strict=False)
+    model.eval().to(DEV)
+    model.itm_plan = plan
+    d = {k: v.to(DEV) for k, v in data.items()}
+    batch = {"video": d["video"], "text": {"input_ids": d["input_ids"], "attention_mask": d["attention_mask"]},
+             "text_mlm_ids": d["text_mlm_ids"], "text_mlm_labels": d["text_mlm_labels"]}
+    args = types.SimpleNamespace(world_size=1, rank=0)
+    n0 = L.kernels().launch_count()
+    loss, loss_dict, ret = model(batch, d["noun_vec"], d["verb_vec"], lambda t, n, a: t, 1, args, {"loss": {"type": "EgoNCE"}},
+                                 EgoNCE(), 0, task_names="EgoNCE_MLM_ITM")
+    loss.backward()
+    torch.cuda.synchronize()
+    assert L.kernels().launch_count() - n0 > 500
+    for k, fk in (("EgoNCE", "EgoNCE"), ("loss_mlm", "loss_mlm"), ("loss_itm", "loss_itm"), ("loss_total", "loss_total")):
+        a, b = float(loss_dict[k]), float(fx[fk])
+        assert abs(a - b) <= 2e-2 * max(1.0, abs(b)), (k, a, b)
+    assert (ret["sim_v2t"].cpu() - fx["sim_v2t"]).abs().max().item() <= 1.5e-2
+    assert rel(ret["text_embeds"].cpu(), fx["text_embeds"]) <= 2e-2
+    assert rel(ret["video_embeds"].cpu(), fx["video_embeds"]) <= 2e-2
+    assert (ret["cross_attn_itm_logits"].cpu() - fx["itm_logits"]).abs().max().item() <= 2e-2
+    assert rel(ret["cross_attn_mlm_logits"][:, :, ::997].cpu(), fx["mlm_logits_slice"]) <= 2e-2
+    gfx = torch.load(os.path.join(golden_dir, "tiny_step_grads.pt"))["grads"]
+    params = dict(model.named_parameters())
+    for k, g in gfx.items():
+        mine = params[k].grad.cpu()
+        assert torch.isfinite(mine).all(), k
+        if mine.numel() > 70000:
+            mine = mine.flatten()[::37]
+        assert rel(mine, g) <= 0.4, (k, rel(mine, g))
+
+
+def test_fullwidth_blocks_vs_reference_golden(golden_dir):
+    """SpaceTimeBlock / RobertaLayer at C=768, 12 heads against outputs of the reference's own classes."""
+    fx = torch.load(os.path.join(golden_dir, "blocks_fullwidth.pt"))
+    C, h, T, Nf = fx["C"], fx["heads"], fx["T"], fx["Nf"]
+    shapes = O.key_shapes(C=C, heads=h, depth=7, n_fuse=1, T=T, img=48, patch=16, vocab=64, proj=64)
+    sd = O.seeded_state(shapes, seed=fx["weight_seed"])
+    blk = SpaceTimeBlock(dim=C, num_heads=h, qkv_bias=True, time_init="rand", dim_text=C)
+    blk.load_state_dict({k[len("video_model.blocks.6."):]: v for k, v in sd.items() if k.startswith("video_model.blocks.6.")})
+    blk.to(DEV)
+    x, y = fx["x"].to(DEV), fx["y"].to(DEV)
+    ext = O.extended_mask(fx["attention_mask"]).to(DEV)
+    es = ('b (f n) d', '(b f) n d', 'b (f n) d', '(b n) f d')
+    with torch.no_grad():
+        out = blk(x, *es, time_n=Nf, space_f=T)
+        assert rel(out.cpu(), fx["video_plain"]) <= 1e-2, rel(out.cpu(), fx["video_plain"])
+        out = blk(x, *es, time_n=Nf, space_f=T, y=y, y_mask=ext)
+        assert rel(out.cpu(), fx["video_fused"]) <= 1e-2, rel(out.cpu(), fx["video_fused"])
+    rb.NUM_FUSE_BLOCK, rb.DIM_IMG = 1, C
+    layer = RobertaLayer(RobertaConfig(hidden_size=C, num_hidden_layers=7, num_attention_heads=h, intermediate_size=4 * C),
+                         layer_index=6)
+    layer.load_state_dict({k[len("text_model.encoder.layer.6."):]: v for k, v in sd.items()
+                           if k.startswith("text_model.encoder.layer.6.")})
+    layer.to(DEV)
+    with torch.no_grad():
+        out = layer(y, ext)[0]
+        assert rel(out.cpu(), fx["text_plain"]) <= 1e-2, rel(out.cpu(), fx["text_plain"])
+        out = layer(y, ext, encoder_hidden_states=x, last_norm=True)[0]
+        assert rel(out.cpu(), fx["text_fused"]) <= 1e-2, rel(out.cpu(), fx["text_fused"])
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_fullwidth_block_gradients_vs_oracle(fused):
+    """fwd + bwd of one video block and one text layer at C=768, T=4, 196 patches/frame, B=2 against autograd through
+    the oracle on the same device (fp32)."""
+    C, H, T, Nf, S, B = 768, 12, 4, 196, 32, 2
+    N = 1 + T * Nf
+    shapes = O.key_shapes(C=C, heads=H, depth=7, n_fuse=1, T=T, img=224, patch=16, vocab=64, proj=64)
+    sd = {k: v.to(DEV) for k, v in O.seeded_state(shapes, seed=11).items()}
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, N, C, generator=g).to(DEV)
+    y = torch.randn(B, S, C, generator=g).to(DEV)
+    am = (torch.arange(S)[None] < torch.tensor([S, 20])[:, None]).long().to(DEV)
+    kb = O.extended_mask(am).reshape(B, S).contiguous()
+    d_out = torch.randn(B, N, C, generator=g).to(DEV)
+    K = L.kernels()
+    # ---- video block
+    prefix = "video_model.blocks.6."
+    names = Fn.VIDEO_BLOCK_PARAMS + (Fn.VIDEO_FUSE_PARAMS if fused else [])
+    p = {n: sd[prefix + n] for n in names}
+    w = {}
+    for n in names:
+        if p[n].dim() == 2:
+            w[n] = torch.empty_like(p[n], dtype=torch.bfloat16)
+            K.cast(p[n], w[n])
+    out, saved = Fn.video_block_fwd(K, x, p, w, H, T, Nf, y=y if fused else None, y_bias=kb if fused else None)
+    dx, dy, grads = Fn.video_block_bwd(K, saved, d_out, p, w, H, T, Nf)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    ref = O.space_time_block(xr, sdr, prefix, H, T, Nf, y=yr if fused else None, y_mask=O.extended_mask(am) if fused else None)
+    ref.backward(d_out)
+    assert rel(out, ref) <= 1e-2, rel(out, ref)
+    assert rel(dx, xr.grad) <= 3e-2, rel(dx, xr.grad)
+    if fused:
+        assert rel(dy, yr.grad) <= 3e-2, rel(dy, yr.grad)
+    for n in names:
+        r = rel(grads[n].reshape(-1), sdr[prefix + n].grad.reshape(-1))
+        assert r <= 3e-2, (n, r)
+    # ---- text layer
+    prefix = "text_model.encoder.layer.6."
+    names = Fn.TEXT_LAYER_PARAMS + (Fn.TEXT_FUSE_PARAMS if fused else [])
+    p = {n: sd[prefix + n] for n in names}
+    w = {}
+    for n in names:
+        if p[n].dim() == 2:
+            w[n] = torch.empty_like(p[n], dtype=torch.bfloat16)
+            K.cast(p[n], w[n])
+    sa = ["attention.self.query", "attention.self.key", "attention.self.value"]
+    p["qkv.bias"] = torch.cat([p[n + ".bias"] for n in sa])
+    w["qkv"] = torch.cat([w[n + ".weight"] for n in sa])
+    if fused:
+        ca = ["crossattention_t2i.self.key", "crossattention_t2i.self.value"]
+        p["cross.kv.bias"] = torch.cat([p[n + ".bias"] for n in ca])
+        w["cross.kv"] = torch.cat([w[n + ".weight"] for n in ca])
+    d_h = torch.randn(B, S, C, generator=g).to(DEV)
+    out, saved = Fn.text_layer_fwd(K, y, kb, p, w, H, video=x if fused else None)
+    dh, dvid, grads = Fn.text_layer_bwd(K, saved, d_h, p, w, H)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    hr, vr = y.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ref = O.roberta_layer(hr, O.extended_mask(am), sdr, prefix, H, video=vr if fused else None)
+    ref.backward(d_h)
+    assert rel(out, ref) <= 1e-2, rel(out, ref)
+    assert rel(dh, hr.grad) <= 3e-2, rel(dh, hr.grad)
+    if fused:
+        assert rel(dvid, vr.grad) <= 3e-2, rel(dvid, vr.grad)
+    got = dict(grads)
+    got[sa[0] + ".weight"], got[sa[1] + ".weight"], got[sa[2] + ".weight"] = got["qkv"].chunk(3, 0)
+    got[sa[0] + ".bias"], got[sa[1] + ".bias"], got[sa[2] + ".bias"] = got["qkv.bias"].chunk(3, 0)
+    if fused:
+        got[ca[0] + ".weight"], got[ca[1] + ".weight"] = got["cross.kv"].chunk(2, 0)
+        got[ca[0] + ".bias"], got[ca[1] + ".bias"] = got["cross.kv.bias"].chunk(2, 0)
+    for n in names:
+        gref = sdr[prefix + n].grad.reshape(-1)
+        if gref.norm().item() < 1e-4 * max(1.0, got[n].norm().item()) and "key.bias" in n:
+            continue   # the key bias gradient is analytically zero under softmax
+        r = rel(got[n].reshape(-1), gref)
+        assert r <= 3e-2, (n, r)
+
+
+def test_optimizer_arena_step_matches_torch_adamw_semantics():
+    """FusedAdamW over the flat arena == HF AdamW update rule, and the bf16 operand copies follow the master weights."""
+    from egovlpv2_b200.optim import FusedAdamW, param_groups
+    c = dict(C=128, heads=2, depth=8, n_fuse=2, T=2, img=64, patch=16, S=8, B=4, proj=256, vocab=50265)
+    model = build_tiny(c).to(DEV)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    groups = param_groups(model, 1e-3, 0.01, 1.0, 4.0)
+    assert sum(len(g["params"]) for g in groups) == len(before)
+    by = {g["name"]: g for g in groups}
+    names = {id(p): n for n, p in model.named_parameters()}
+    assert all("i2t" in names[id(p)] or "t2i" in names[id(p)] or "cross_modal" in names[id(p)] for p in by["cross_decay"]["params"])
+    # norm3 / norm_i2t_i weights are NOT matched by the no-decay substrings: they receive weight decay
+    assert any(names[id(p)].endswith("norm3.weight") for p in by["backbone_decay"]["params"])
+    opt = FusedAdamW(model, 1e-3, 0.01, 1.0, 4.0)
+    for n, p in model.named_parameters():
+        assert torch.equal(p.detach(), before[n]), n
+    opt.zero_grad()
+    for p in model.parameters():
+        p.grad.copy_(torch.ones_like(p) * 0.5)
+    opt.step()
+    torch.cuda.synchronize()
+    n, p = next((n, p) for n, p in model.named_parameters() if n.endswith("blocks.0.mlp.fc1.weight"))
+    # step 1 of Adam with constant gradient: update = lr * sign(g) (bias-corrected), then decoupled decay
+    expect = before[n] - 1e-3 * torch.ones_like(p)
+    expect = expect - 1e-3 * 0.01 * expect
+    assert (p.detach() - expect).abs().max().item() < 1e-6
+    sh = weights.cache().bf16(p)
+    assert torch.equal(sh, p.detach().to(torch.bfloat16))
+    weights.cache().arena = None
+    weights.cache().clear()
