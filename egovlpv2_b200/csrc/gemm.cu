@@ -498,15 +498,37 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
 
   int BN = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
   const int num_m_tiles = (int)cdiv(a->M, BM);
+  p.k_blocks_total = (int)cdiv(a->K, BK);
+  // Automatic split-K: a plain fp32 output whose tile grid cannot fill the GPU but whose reduction is long
+  // (weight gradients dW = dy^T x: 768..3072-wide outputs, K = B*N tokens).  The output is zeroed and the
+  // slices are combined with fp32 atomics.
+  bool auto_split = false;
+  if (split_k == 1 && !a->accumulate && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && a->act == EGV_ACT_NONE &&
+      !a->residual) {
+    const long long tiles256 = (long long)num_m_tiles * cdiv(a->N, BN);
+    if (tiles256 * 2 <= sm_count() && p.k_blocks_total >= 16) {
+      long long want = cdiv(sm_count(), tiles256);
+      long long cap = p.k_blocks_total / 8;   // >= 8 k-blocks (512 elements) per slice
+      split_k = (int)std::max<long long>(1, std::min<long long>(want, cap));
+      auto_split = split_k > 1;
+    }
+  }
   // prefer the 128-wide tile when the 256-wide one would leave most SMs idle
   if (BN == 256 && (long long)num_m_tiles * cdiv(a->N, 256) * split_k < sm_count() / 2) BN = 128;
   p.num_n_tiles = (int)cdiv(a->N, BN);
-  p.k_blocks_total = (int)cdiv(a->K, BK);
   if (split_k > p.k_blocks_total) split_k = p.k_blocks_total;
   p.k_blocks_per_split = (int)cdiv(p.k_blocks_total, split_k);
   split_k = (int)cdiv(p.k_blocks_total, p.k_blocks_per_split);
   p.split_k = split_k;
   p.total_items = num_m_tiles * p.num_n_tiles * split_k;
+  if (auto_split) {
+    if (a->ld_out_f32 == a->N) {
+      cudaMemsetAsync(a->out_f32, 0, (size_t)a->M * a->N * sizeof(float), stream);
+    } else {
+      cudaMemset2DAsync(a->out_f32, (size_t)a->ld_out_f32 * sizeof(float), 0, (size_t)a->N * sizeof(float), (size_t)a->M, stream);
+    }
+    p.accumulate = 1;
+  }
 
   CUtensorMap ta, tb;
   int rc;

@@ -49,6 +49,7 @@ def rnd(*shape, dtype=torch.bfloat16, scale=1.0, seed=None):
 
 # ------------------------------------------------------------------------------------------- GEMM
 GEMM_SHAPES = [
+    (768, 768, 6280),     # weight-gradient shape: few output tiles, long K -> automatic split-K (TN layout)
     # M, N, K
     (128, 64, 64),        # one tile, BN=64
     (300, 200, 136),      # tails in every dimension
@@ -441,8 +442,8 @@ def test_egonce_vs_oracle(K, R, G):
     check(sim, osim.detach(), 1e-5, "egonce sim")
     assert torch.equal(mask.bool(), omask)
     check(loss, oloss.detach().reshape(1), 1e-5, "egonce loss", atol=2e-6)
-    check(dt, tt.grad[r0:r0 + nr], 1e-4, "egonce dt")
-    check(dv, vv.grad[r0:r0 + nr], 1e-4, "egonce dv")
+    check(dt, tt.grad[r0:r0 + nr], 1e-4, "egonce dt", atol=1e-7)
+    check(dv, vv.grad[r0:r0 + nr], 1e-4, "egonce dv", atol=1e-7)
 
 
 def test_adamw(K, R):
