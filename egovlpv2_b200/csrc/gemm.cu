@@ -28,7 +28,7 @@ constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
-constexpr int EPI_STAGE_FLOATS = 32 * 33;
+constexpr int EPI_STAGE_FLOATS = 32 * 34;
 
 struct GemmParams {
   int M, N, K;
@@ -48,6 +48,7 @@ struct GemmParams {
   long long ld_out_pre;
   int act;
   int accumulate;
+  int vec_ok;  // N even, every row stride even and every pointer aligned for 2-element vector access
 };
 
 // erf with |abs err| < 1.5e-7 (Abramowitz-Stegun 7.1.26): far below bf16 resolution, ~3x cheaper than erff.
@@ -62,25 +63,29 @@ EGV_DEVINL float fast_erf(float x) {
   return copysignf(r, x);
 }
 
-// Shared epilogue math.  `lead` is false for split-K slices > 0 (they only add their partial sum).
-EGV_DEVINL void epilogue_store(const GemmParams& p, float v, int row, int col, bool lead, float resv, float auxv,
-                               float scale_total) {
+template <int ACT>
+EGV_DEVINL float apply_act(float v, float auxv) {
+  if (ACT == EGV_ACT_GELU) return 0.5f * v * (1.0f + fast_erf(v * 0.70710678118654752f));
+  if (ACT == EGV_ACT_RELU) return fmaxf(v, 0.0f);
+  if (ACT == EGV_ACT_TANH) return tanhf(v);
+  if (ACT == EGV_ACT_GELU_BWD) {
+    const float cdf = 0.5f * (1.0f + fast_erf(auxv * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * auxv * auxv);
+    return v * fmaf(auxv, pdf, cdf);
+  }
+  if (ACT == EGV_ACT_RELU_BWD) return auxv > 0.0f ? v : 0.0f;
+  if (ACT == EGV_ACT_TANH_BWD) return v * (1.0f - auxv * auxv);
+  return v;
+}
+
+// Epilogue math for one element (scalar path: SIMT kernel and odd-shaped tensor-core problems).
+// `lead` is false for split-K slices > 0 (they only add their partial sum).
+template <int ACT>
+EGV_DEVINL void epilogue_store_t(const GemmParams& p, float v, int row, int col, bool lead, float resv, float auxv,
+                                 float scale_total) {
   if (lead && p.bias) v += __ldg(p.bias + col);
   if (p.out_pre) p.out_pre[(long long)row * p.ld_out_pre + col] = __float2bfloat16(v);
-  switch (p.act) {
-    case EGV_ACT_GELU: v = 0.5f * v * (1.0f + fast_erf(v * 0.70710678118654752f)); break;
-    case EGV_ACT_RELU: v = fmaxf(v, 0.0f); break;
-    case EGV_ACT_TANH: v = tanhf(v); break;
-    case EGV_ACT_GELU_BWD: {
-      float cdf = 0.5f * (1.0f + fast_erf(auxv * 0.70710678118654752f));
-      float pdf = 0.3989422804014327f * __expf(-0.5f * auxv * auxv);
-      v *= fmaf(auxv, pdf, cdf);
-    } break;
-    case EGV_ACT_RELU_BWD: v = auxv > 0.0f ? v : 0.0f; break;
-    case EGV_ACT_TANH_BWD: v *= (1.0f - auxv * auxv); break;
-    default: break;
-  }
-  v *= scale_total;
+  v = apply_act<ACT>(v, auxv) * scale_total;
   if (lead) v += resv;
   if (p.out_f32) {
     float* o = p.out_f32 + (long long)row * p.ld_out_f32 + col;
@@ -89,16 +94,94 @@ EGV_DEVINL void epilogue_store(const GemmParams& p, float v, int row, int col, b
   }
   if (p.out_bf16) p.out_bf16[(long long)row * p.ld_out_bf16 + col] = __float2bfloat16(v);
 }
+EGV_DEVINL void epilogue_store(const GemmParams& p, float v, int row, int col, bool lead, float resv, float auxv,
+                               float scale_total) {
+  switch (p.act) {
+    case EGV_ACT_GELU: epilogue_store_t<EGV_ACT_GELU>(p, v, row, col, lead, resv, auxv, scale_total); break;
+    case EGV_ACT_RELU: epilogue_store_t<EGV_ACT_RELU>(p, v, row, col, lead, resv, auxv, scale_total); break;
+    case EGV_ACT_TANH: epilogue_store_t<EGV_ACT_TANH>(p, v, row, col, lead, resv, auxv, scale_total); break;
+    case EGV_ACT_GELU_BWD: epilogue_store_t<EGV_ACT_GELU_BWD>(p, v, row, col, lead, resv, auxv, scale_total); break;
+    case EGV_ACT_RELU_BWD: epilogue_store_t<EGV_ACT_RELU_BWD>(p, v, row, col, lead, resv, auxv, scale_total); break;
+    case EGV_ACT_TANH_BWD: epilogue_store_t<EGV_ACT_TANH_BWD>(p, v, row, col, lead, resv, auxv, scale_total); break;
+    default: epilogue_store_t<EGV_ACT_NONE>(p, v, row, col, lead, resv, auxv, scale_total); break;
+  }
+}
+
+constexpr int EPI_LD = 34;  // staging row stride in floats (even: float2 access; conflict-free per half-warp)
+
+// One 32-row x 32-column chunk of a warp, read back from the staging tile two rows per instruction:
+// lanes 0-15 take row 2i, lanes 16-31 row 2i+1; every lane owns two adjacent columns (vector I/O).
+template <int ACT>
+EGV_DEVINL void epi_rows_vec(const GemmParams& p, const float* stg, int lane, int row_base, int gcol, bool lead,
+                             float scale_total) {
+  const int half = lane >> 4;
+  const bool c_ok = gcol < p.N;   // N is even on this path, so gcol + 1 < N as well
+  float2 b = make_float2(0.f, 0.f);
+  if (lead && p.bias && c_ok) b = __ldg(reinterpret_cast<const float2*>(p.bias + gcol));
+  constexpr bool NEED_AUX = ACT >= EGV_ACT_GELU_BWD && ACT <= EGV_ACT_TANH_BWD;
+  const bool has_res = lead && p.residual != nullptr;
+  // issue the residual / aux loads of all 16 row pairs up front (memory-level parallelism)
+  float2 rs[16];
+  uint32_t ax[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int row = row_base + 2 * i + half;
+    const bool ok = c_ok && row < p.M;
+    rs[i] = (has_res && ok) ? __ldg(reinterpret_cast<const float2*>(p.residual + (long long)row * p.ld_res + gcol))
+                            : make_float2(0.f, 0.f);
+    ax[i] = (NEED_AUX && ok) ? __ldg(reinterpret_cast<const unsigned int*>(p.aux + (long long)row * p.ld_aux + gcol)) : 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int rl = 2 * i + half;
+    const int row = row_base + rl;
+    const float2 a = *reinterpret_cast<const float2*>(stg + rl * EPI_LD + 2 * (lane & 15));
+    if (!(c_ok && row < p.M)) continue;
+    float v0 = a.x + b.x, v1 = a.y + b.y;
+    if (p.out_pre) *reinterpret_cast<uint32_t*>(p.out_pre + (long long)row * p.ld_out_pre + gcol) = pack_bf16(v0, v1);
+    const float2 av = unpack_bf16(ax[i]);
+    v0 = apply_act<ACT>(v0, av.x) * scale_total + rs[i].x;
+    v1 = apply_act<ACT>(v1, av.y) * scale_total + rs[i].y;
+    if (p.out_f32) {
+      float* o = p.out_f32 + (long long)row * p.ld_out_f32 + gcol;
+      if (p.accumulate) {
+        atomicAdd(o, v0);
+        atomicAdd(o + 1, v1);
+      } else {
+        *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
+      }
+    }
+    if (p.out_bf16) *reinterpret_cast<uint32_t*>(p.out_bf16 + (long long)row * p.ld_out_bf16 + gcol) = pack_bf16(v0, v1);
+  }
+}
+
+// Scalar read-back of the same staging tile: lane = column, one row per iteration (odd N / unaligned tensors).
+EGV_DEVINL void epi_rows_scalar(const GemmParams& p, const float* stg, int lane, int row_base, int gcol, bool lead,
+                                float scale_total) {
+  const bool c_ok = gcol < p.N;
+  const bool need_aux = p.act >= EGV_ACT_GELU_BWD && p.act <= EGV_ACT_TANH_BWD;
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    const int row = row_base + r;
+    const float acc = stg[r * EPI_LD + lane];
+    if (!(c_ok && row < p.M)) continue;
+    const float resv = (lead && p.residual) ? p.residual[(long long)row * p.ld_res + gcol] : 0.0f;
+    const float auxv = need_aux ? __bfloat162float(p.aux[(long long)row * p.ld_aux + gcol]) : 0.0f;
+    epilogue_store(p, acc, row, gcol, lead, resv, auxv, scale_total);
+  }
+}
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 5 : 7);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_FLOATS * 4;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  // the 1024-byte alignment slack does not fit next to 4 x 48 KB stages: BN = 256 relies on (and checks) an aligned base
+  static constexpr int SLACK = BN == 256 ? 0 : 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + SLACK;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -108,8 +191,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // keep the shared address space visible to the compiler (pointer + offset, no integer round trip)
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  if (pad > (uint32_t)Cfg::SLACK) {
+    if (threadIdx.x == 0) printf("egv: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint8_t* smem = smem_raw + pad;
   float* epi_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;
@@ -226,7 +315,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int chalf = ew >> 2;       // which half of the BN columns
     float* stg = epi_smem + ew * EPI_STAGE_FLOATS;
     const float scale_total = p.scale * (p.scale_dev ? __ldg(p.scale_dev) : 1.0f);
-    const bool need_aux = p.act >= EGV_ACT_GELU_BWD;
     int it = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++it) {
       const int ks = w % p.split_k;
@@ -242,42 +330,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         const int col0 = chalf * (BN / 2) + c * 32;
-        const int gcol = n0 + col0 + lane;
-        const bool col_ok = gcol < p.N;
-        // prefetch residual / aux for the 32 rows of this chunk while TMEM is being read
-        float resv[32];
-        float auxv[32];
-        if (p.residual && lead) {
-#pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const int row = row_base + r;
-            resv[r] = (col_ok && row < p.M) ? __ldg(p.residual + (long long)row * p.ld_res + gcol) : 0.0f;
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < 32; ++r) resv[r] = 0.0f;
-        }
-        if (need_aux) {
-#pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const int row = row_base + r;
-            auxv[r] = (col_ok && row < p.M) ? __bfloat162float(p.aux[(long long)row * p.ld_aux + gcol]) : 0.0f;
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < 32; ++r) auxv[r] = 0.0f;
-        }
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + col0), v);
         tmem_ld_wait();
+        // thread = row: 32 consecutive columns -> staging tile (float2 stores, conflict-free per half-warp)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j)
+          *reinterpret_cast<float2*>(stg + lane * EPI_LD + 2 * j) =
+              make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
         __syncwarp();
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const int row = row_base + r;
-          const float acc = stg[r * 33 + lane];
-          if (col_ok && row < p.M) epilogue_store(p, acc, row, gcol, lead, resv[r], auxv[r], scale_total);
+        if (p.act == 99) {
+          // debug: mainloop-only timing (tools/gemm_bench.py) -- consume the tile without any global traffic
+          if (stg[lane * EPI_LD] == 1.2345e38f) p.out_f32[0] = 0.f;
+        } else if (p.vec_ok) {
+          const int gcol = n0 + col0 + 2 * (lane & 15);
+          switch (p.act) {
+            case EGV_ACT_GELU: epi_rows_vec<EGV_ACT_GELU>(p, stg, lane, row_base, gcol, lead, scale_total); break;
+            case EGV_ACT_RELU: epi_rows_vec<EGV_ACT_RELU>(p, stg, lane, row_base, gcol, lead, scale_total); break;
+            case EGV_ACT_TANH: epi_rows_vec<EGV_ACT_TANH>(p, stg, lane, row_base, gcol, lead, scale_total); break;
+            case EGV_ACT_GELU_BWD: epi_rows_vec<EGV_ACT_GELU_BWD>(p, stg, lane, row_base, gcol, lead, scale_total); break;
+            case EGV_ACT_RELU_BWD: epi_rows_vec<EGV_ACT_RELU_BWD>(p, stg, lane, row_base, gcol, lead, scale_total); break;
+            case EGV_ACT_TANH_BWD: epi_rows_vec<EGV_ACT_TANH_BWD>(p, stg, lane, row_base, gcol, lead, scale_total); break;
+            default: epi_rows_vec<EGV_ACT_NONE>(p, stg, lane, row_base, gcol, lead, scale_total); break;
+          }
+        } else {
+          epi_rows_scalar(p, stg, lane, row_base, n0 + col0 + lane, lead, scale_total);
         }
         __syncwarp();
       }
@@ -342,7 +419,7 @@ gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, SimtStr
       int row = m0 + ty + 16 * i, col = n0 + tx + 16 * j;
       if (row < p.M && col < p.N) {
         float resv = (p.residual && lead) ? p.residual[(long long)row * p.ld_res + col] : 0.0f;
-        float auxv = (p.act >= EGV_ACT_GELU_BWD) ? __bfloat162float(p.aux[(long long)row * p.ld_aux + col]) : 0.0f;
+        float auxv = (p.act >= EGV_ACT_GELU_BWD && p.act <= EGV_ACT_TANH_BWD) ? __bfloat162float(p.aux[(long long)row * p.ld_aux + col]) : 0.0f;
         epilogue_store(p, acc[i][j], row, col, lead, resv, auxv, scale_total);
       }
     }
@@ -454,7 +531,7 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return fail(EGV_ERR_ARG, "gemm: bad shape %d %d %d", a->M, a->N, a->K);
   if (a->layout < 0 || a->layout > 2) return fail(EGV_ERR_ARG, "gemm: bad layout %d", a->layout);
   if (!a->out_f32 && !a->out_bf16 && !a->out_pre_bf16) return fail(EGV_ERR_ARG, "gemm: no output");
-  if (a->act >= EGV_ACT_GELU_BWD && !a->aux) return fail(EGV_ERR_ARG, "gemm: act %d needs aux", a->act);
+  if (a->act >= EGV_ACT_GELU_BWD && a->act <= EGV_ACT_TANH_BWD && !a->aux) return fail(EGV_ERR_ARG, "gemm: act %d needs aux", a->act);
   int split_k = a->split_k < 1 ? 1 : a->split_k;
   if (split_k > 1 && (!a->accumulate || !a->out_f32 || a->out_bf16 || a->out_pre_bf16 || a->act != EGV_ACT_NONE))
     return fail(EGV_ERR_ARG, "gemm: split_k > 1 needs accumulate=1, f32 output only, no activation");
@@ -469,6 +546,12 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   p.out_bf16 = (bf16*)a->out_bf16; p.ld_out_bf16 = a->ld_out_bf16;
   p.out_pre = (bf16*)a->out_pre_bf16; p.ld_out_pre = a->ld_out_pre;
   p.act = a->act; p.accumulate = a->accumulate;
+  {
+    auto even = [](const void* ptr, long long ld, int bytes) { return !ptr || (((uintptr_t)ptr) % bytes == 0 && ld % 2 == 0); };
+    p.vec_ok = (a->N % 2 == 0) && (!a->bias || ((uintptr_t)a->bias) % 8 == 0) && even(a->aux, a->ld_aux, 4) &&
+               even(a->residual, a->ld_res, 8) && even(a->out_f32, a->ld_out_f32, 8) &&
+               even(a->out_bf16, a->ld_out_bf16, 4) && even(a->out_pre_bf16, a->ld_out_pre, 4);
+  }
 
   const bool a_mn = a->layout == EGV_GEMM_TN;                           // A stored [K, M]
   const bool b_mn = a->layout == EGV_GEMM_NN || a->layout == EGV_GEMM_TN;  // B stored [K, N]
