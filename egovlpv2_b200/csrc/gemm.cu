@@ -28,7 +28,7 @@ constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
-constexpr int EPI_STAGE_FLOATS = 32 * 34;
+constexpr int EPI_STAGE_FLOATS = 32 * 32;
 
 struct GemmParams {
   int M, N, K;
@@ -48,7 +48,8 @@ struct GemmParams {
   long long ld_out_pre;
   int act;
   int accumulate;
-  int vec_ok;  // N even, every row stride even and every pointer aligned for 2-element vector access
+  int vec_ok;  // N % 4 == 0, every row stride % 4 == 0 and every pointer aligned for 4-element vector access
+  float* colsum;  // optional [N]: += column sums of the final value (bias gradients), fp32 atomics
 };
 
 // erf with |abs err| < 1.5e-7 (Abramowitz-Stegun 7.1.26): far below bf16 resolution, ~3x cheaper than erff.
@@ -81,8 +82,8 @@ EGV_DEVINL float apply_act(float v, float auxv) {
 // Epilogue math for one element (scalar path: SIMT kernel and odd-shaped tensor-core problems).
 // `lead` is false for split-K slices > 0 (they only add their partial sum).
 template <int ACT>
-EGV_DEVINL void epilogue_store_t(const GemmParams& p, float v, int row, int col, bool lead, float resv, float auxv,
-                                 float scale_total) {
+EGV_DEVINL float epilogue_store_t(const GemmParams& p, float v, int row, int col, bool lead, float resv, float auxv,
+                                  float scale_total) {
   if (lead && p.bias) v += __ldg(p.bias + col);
   if (p.out_pre) p.out_pre[(long long)row * p.ld_out_pre + col] = __float2bfloat16(v);
   v = apply_act<ACT>(v, auxv) * scale_total;
@@ -93,66 +94,115 @@ EGV_DEVINL void epilogue_store_t(const GemmParams& p, float v, int row, int col,
     else *o = v;
   }
   if (p.out_bf16) p.out_bf16[(long long)row * p.ld_out_bf16 + col] = __float2bfloat16(v);
+  return v;
 }
-EGV_DEVINL void epilogue_store(const GemmParams& p, float v, int row, int col, bool lead, float resv, float auxv,
-                               float scale_total) {
+EGV_DEVINL float epilogue_store(const GemmParams& p, float v, int row, int col, bool lead, float resv, float auxv,
+                                float scale_total) {
   switch (p.act) {
-    case EGV_ACT_GELU: epilogue_store_t<EGV_ACT_GELU>(p, v, row, col, lead, resv, auxv, scale_total); break;
-    case EGV_ACT_RELU: epilogue_store_t<EGV_ACT_RELU>(p, v, row, col, lead, resv, auxv, scale_total); break;
-    case EGV_ACT_TANH: epilogue_store_t<EGV_ACT_TANH>(p, v, row, col, lead, resv, auxv, scale_total); break;
-    case EGV_ACT_GELU_BWD: epilogue_store_t<EGV_ACT_GELU_BWD>(p, v, row, col, lead, resv, auxv, scale_total); break;
-    case EGV_ACT_RELU_BWD: epilogue_store_t<EGV_ACT_RELU_BWD>(p, v, row, col, lead, resv, auxv, scale_total); break;
-    case EGV_ACT_TANH_BWD: epilogue_store_t<EGV_ACT_TANH_BWD>(p, v, row, col, lead, resv, auxv, scale_total); break;
-    default: epilogue_store_t<EGV_ACT_NONE>(p, v, row, col, lead, resv, auxv, scale_total); break;
+    case EGV_ACT_GELU: return epilogue_store_t<EGV_ACT_GELU>(p, v, row, col, lead, resv, auxv, scale_total);
+    case EGV_ACT_RELU: return epilogue_store_t<EGV_ACT_RELU>(p, v, row, col, lead, resv, auxv, scale_total);
+    case EGV_ACT_TANH: return epilogue_store_t<EGV_ACT_TANH>(p, v, row, col, lead, resv, auxv, scale_total);
+    case EGV_ACT_GELU_BWD: return epilogue_store_t<EGV_ACT_GELU_BWD>(p, v, row, col, lead, resv, auxv, scale_total);
+    case EGV_ACT_RELU_BWD: return epilogue_store_t<EGV_ACT_RELU_BWD>(p, v, row, col, lead, resv, auxv, scale_total);
+    case EGV_ACT_TANH_BWD: return epilogue_store_t<EGV_ACT_TANH_BWD>(p, v, row, col, lead, resv, auxv, scale_total);
+    default: return epilogue_store_t<EGV_ACT_NONE>(p, v, row, col, lead, resv, auxv, scale_total);
   }
 }
 
-constexpr int EPI_LD = 34;  // staging row stride in floats (even: float2 access; conflict-free per half-warp)
+// Staging tile of one epilogue warp: 32 rows x 32 fp32, row stride 32 words, 16-byte chunks XOR-swizzled with the
+// row index (chunk' = chunk ^ (row & 7)): both the row-per-thread writes and the 4-rows-per-instruction reads are
+// conflict-free without padding.
+EGV_DEVINL int stg_off(int row, int chunk) { return row * 32 + ((chunk ^ (row & 7)) << 2); }
 
-// One 32-row x 32-column chunk of a warp, read back from the staging tile two rows per instruction:
-// lanes 0-15 take row 2i, lanes 16-31 row 2i+1; every lane owns two adjacent columns (vector I/O).
-template <int ACT>
-EGV_DEVINL void epi_rows_vec(const GemmParams& p, const float* stg, int lane, int row_base, int gcol, bool lead,
-                             float scale_total) {
-  const int half = lane >> 4;
-  const bool c_ok = gcol < p.N;   // N is even on this path, so gcol + 1 < N as well
-  float2 b = make_float2(0.f, 0.f);
-  if (lead && p.bias && c_ok) b = __ldg(reinterpret_cast<const float2*>(p.bias + gcol));
+EGV_DEVINL uint2 pack4_bf16(float a, float b, float c, float d) {
+  uint2 u;
+  u.x = pack_bf16(a, b);
+  u.y = pack_bf16(c, d);
+  return u;
+}
+
+// One 32-row x 32-column chunk, read back 4 rows per instruction: lane l owns columns 4*(l&7)..+3 of rows 4i+(l>>3).
+// FULL: the tile has no row / column tail (no predicates in the loop).
+template <int ACT, bool FULL>
+EGV_DEVINL void epi_rows_vec4(const GemmParams& p, const float* stg, int lane, int row_base, int gcol, bool lead,
+                              float scale_total) {
+  const int sub = lane >> 3, ch = lane & 7;
+  const bool c_ok = FULL || gcol < p.N;   // N % 4 == 0 on this path: the whole 4-column group is in or out
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lead && p.bias && c_ok) b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
   constexpr bool NEED_AUX = ACT >= EGV_ACT_GELU_BWD && ACT <= EGV_ACT_TANH_BWD;
   const bool has_res = lead && p.residual != nullptr;
-  // issue the residual / aux loads of all 16 row pairs up front (memory-level parallelism)
-  float2 rs[16];
-  uint32_t ax[16];
+  const int rows_left = p.M - row_base;   // rows of this chunk that exist (>= 32 when FULL)
+  const float* res_p = p.residual ? p.residual + (long long)row_base * p.ld_res + gcol : nullptr;
+  const bf16* aux_p = p.aux ? p.aux + (long long)row_base * p.ld_aux + gcol : nullptr;
+  float* o32 = p.out_f32 ? p.out_f32 + (long long)row_base * p.ld_out_f32 + gcol : nullptr;
+  bf16* o16 = p.out_bf16 ? p.out_bf16 + (long long)row_base * p.ld_out_bf16 + gcol : nullptr;
+  bf16* opre = p.out_pre ? p.out_pre + (long long)row_base * p.ld_out_pre + gcol : nullptr;
+  const int ld_res = (int)p.ld_res, ld_aux = (int)p.ld_aux, ld32 = (int)p.ld_out_f32, ld16 = (int)p.ld_out_bf16,
+            ldpre = (int)p.ld_out_pre;
+  // all residual / aux loads of the chunk are issued before the first use (memory-level parallelism)
+  float4 rs[8];
+  uint2 ax[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int row = row_base + 2 * i + half;
-    const bool ok = c_ok && row < p.M;
-    rs[i] = (has_res && ok) ? __ldg(reinterpret_cast<const float2*>(p.residual + (long long)row * p.ld_res + gcol))
-                            : make_float2(0.f, 0.f);
-    ax[i] = (NEED_AUX && ok) ? __ldg(reinterpret_cast<const unsigned int*>(p.aux + (long long)row * p.ld_aux + gcol)) : 0u;
+  for (int i = 0; i < 8; ++i) {
+    const int rl = 4 * i + sub;
+    const bool ok = c_ok && (FULL || rl < rows_left);
+    rs[i] = (has_res && ok) ? __ldg(reinterpret_cast<const float4*>(res_p + rl * ld_res)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ax[i] = (NEED_AUX && ok) ? __ldg(reinterpret_cast<const uint2*>(aux_p + rl * ld_aux)) : make_uint2(0u, 0u);
   }
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int rl = 2 * i + half;
-    const int row = row_base + rl;
-    const float2 a = *reinterpret_cast<const float2*>(stg + rl * EPI_LD + 2 * (lane & 15));
-    if (!(c_ok && row < p.M)) continue;
-    float v0 = a.x + b.x, v1 = a.y + b.y;
-    if (p.out_pre) *reinterpret_cast<uint32_t*>(p.out_pre + (long long)row * p.ld_out_pre + gcol) = pack_bf16(v0, v1);
-    const float2 av = unpack_bf16(ax[i]);
-    v0 = apply_act<ACT>(v0, av.x) * scale_total + rs[i].x;
-    v1 = apply_act<ACT>(v1, av.y) * scale_total + rs[i].y;
-    if (p.out_f32) {
-      float* o = p.out_f32 + (long long)row * p.ld_out_f32 + gcol;
+  for (int i = 0; i < 8; ++i) {
+    const int rl = 4 * i + sub;
+    const float4 a = *reinterpret_cast<const float4*>(stg + stg_off(rl, ch));
+    if (!FULL && !(c_ok && rl < rows_left)) continue;
+    float v0 = a.x + b.x, v1 = a.y + b.y, v2 = a.z + b.z, v3 = a.w + b.w;
+    if (opre) *reinterpret_cast<uint2*>(opre + rl * ldpre) = pack4_bf16(v0, v1, v2, v3);
+    const float2 a01 = unpack_bf16(ax[i].x), a23 = unpack_bf16(ax[i].y);
+    v0 = fmaf(apply_act<ACT>(v0, a01.x), scale_total, rs[i].x);
+    v1 = fmaf(apply_act<ACT>(v1, a01.y), scale_total, rs[i].y);
+    v2 = fmaf(apply_act<ACT>(v2, a23.x), scale_total, rs[i].z);
+    v3 = fmaf(apply_act<ACT>(v3, a23.y), scale_total, rs[i].w);
+    if (o32) {
+      float* o = o32 + rl * ld32;
       if (p.accumulate) {
         atomicAdd(o, v0);
         atomicAdd(o + 1, v1);
+        atomicAdd(o + 2, v2);
+        atomicAdd(o + 3, v3);
       } else {
-        *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
+        *reinterpret_cast<float4*>(o) = make_float4(v0, v1, v2, v3);
       }
     }
-    if (p.out_bf16) *reinterpret_cast<uint32_t*>(p.out_bf16 + (long long)row * p.ld_out_bf16 + gcol) = pack_bf16(v0, v1);
+    if (o16) *reinterpret_cast<uint2*>(o16 + rl * ld16) = pack4_bf16(v0, v1, v2, v3);
+    cs.x += v0;
+    cs.y += v1;
+    cs.z += v2;
+    cs.w += v3;
   }
+  if (p.colsum) {
+    // rows 4i+sub for sub = 0..3 live in lanes l, l^8, l^16, l^24
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
+      cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+      cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
+      cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+    }
+    if (sub == 0 && c_ok) {
+      atomicAdd(p.colsum + gcol, cs.x);
+      atomicAdd(p.colsum + gcol + 1, cs.y);
+      atomicAdd(p.colsum + gcol + 2, cs.z);
+      atomicAdd(p.colsum + gcol + 3, cs.w);
+    }
+  }
+}
+
+template <int ACT>
+EGV_DEVINL void epi_rows_vec4_d(const GemmParams& p, const float* stg, int lane, int row_base, int gcol, bool lead,
+                                float scale_total, bool full) {
+  if (full) epi_rows_vec4<ACT, true>(p, stg, lane, row_base, gcol, lead, scale_total);
+  else epi_rows_vec4<ACT, false>(p, stg, lane, row_base, gcol, lead, scale_total);
 }
 
 // Scalar read-back of the same staging tile: lane = column, one row per iteration (odd N / unaligned tensors).
@@ -160,27 +210,28 @@ EGV_DEVINL void epi_rows_scalar(const GemmParams& p, const float* stg, int lane,
                                 float scale_total) {
   const bool c_ok = gcol < p.N;
   const bool need_aux = p.act >= EGV_ACT_GELU_BWD && p.act <= EGV_ACT_TANH_BWD;
+  float cs = 0.f;
 #pragma unroll 4
   for (int r = 0; r < 32; ++r) {
     const int row = row_base + r;
-    const float acc = stg[r * EPI_LD + lane];
+    const float acc = stg[stg_off(r, lane >> 2) + (lane & 3)];
     if (!(c_ok && row < p.M)) continue;
     const float resv = (lead && p.residual) ? p.residual[(long long)row * p.ld_res + gcol] : 0.0f;
     const float auxv = need_aux ? __bfloat162float(p.aux[(long long)row * p.ld_aux + gcol]) : 0.0f;
-    epilogue_store(p, acc, row, gcol, lead, resv, auxv, scale_total);
+    cs += epilogue_store(p, acc, row, gcol, lead, resv, auxv, scale_total);
   }
+  if (p.colsum && c_ok) atomicAdd(p.colsum + gcol, cs);
 }
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 5 : 7);
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_FLOATS * 4;
   static constexpr int BAR_BYTES = 256;
-  // the 1024-byte alignment slack does not fit next to 4 x 48 KB stages: BN = 256 relies on (and checks) an aligned base
-  static constexpr int SLACK = BN == 256 ? 0 : 1024;
+  static constexpr int SLACK = 1024;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + SLACK;
   static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -333,25 +384,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + col0), v);
         tmem_ld_wait();
-        // thread = row: 32 consecutive columns -> staging tile (float2 stores, conflict-free per half-warp)
+        // thread = row: 32 consecutive columns -> swizzled staging tile (8 x 16-byte stores)
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          *reinterpret_cast<float2*>(stg + lane * EPI_LD + 2 * j) =
-              make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + stg_off(lane, j)) =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3]));
         __syncwarp();
         if (p.act == 99) {
           // debug: mainloop-only timing (tools/gemm_bench.py) -- consume the tile without any global traffic
-          if (stg[lane * EPI_LD] == 1.2345e38f) p.out_f32[0] = 0.f;
+          if (stg[lane * 32] == 1.2345e38f) p.out_f32[0] = 0.f;
         } else if (p.vec_ok) {
-          const int gcol = n0 + col0 + 2 * (lane & 15);
+          const int gcol = n0 + col0 + 4 * (lane & 7);
+          const bool full = (row_base + 32 <= p.M) && (n0 + col0 + 32 <= p.N);
           switch (p.act) {
-            case EGV_ACT_GELU: epi_rows_vec<EGV_ACT_GELU>(p, stg, lane, row_base, gcol, lead, scale_total); break;
-            case EGV_ACT_RELU: epi_rows_vec<EGV_ACT_RELU>(p, stg, lane, row_base, gcol, lead, scale_total); break;
-            case EGV_ACT_TANH: epi_rows_vec<EGV_ACT_TANH>(p, stg, lane, row_base, gcol, lead, scale_total); break;
-            case EGV_ACT_GELU_BWD: epi_rows_vec<EGV_ACT_GELU_BWD>(p, stg, lane, row_base, gcol, lead, scale_total); break;
-            case EGV_ACT_RELU_BWD: epi_rows_vec<EGV_ACT_RELU_BWD>(p, stg, lane, row_base, gcol, lead, scale_total); break;
-            case EGV_ACT_TANH_BWD: epi_rows_vec<EGV_ACT_TANH_BWD>(p, stg, lane, row_base, gcol, lead, scale_total); break;
-            default: epi_rows_vec<EGV_ACT_NONE>(p, stg, lane, row_base, gcol, lead, scale_total); break;
+            case EGV_ACT_GELU: epi_rows_vec4_d<EGV_ACT_GELU>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
+            case EGV_ACT_RELU: epi_rows_vec4_d<EGV_ACT_RELU>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
+            case EGV_ACT_TANH: epi_rows_vec4_d<EGV_ACT_TANH>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
+            case EGV_ACT_GELU_BWD: epi_rows_vec4_d<EGV_ACT_GELU_BWD>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
+            case EGV_ACT_RELU_BWD: epi_rows_vec4_d<EGV_ACT_RELU_BWD>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
+            case EGV_ACT_TANH_BWD: epi_rows_vec4_d<EGV_ACT_TANH_BWD>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
+            default: epi_rows_vec4_d<EGV_ACT_NONE>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
           }
         } else {
           epi_rows_scalar(p, stg, lane, row_base, n0 + col0 + lane, lead, scale_total);
@@ -420,7 +473,8 @@ gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, SimtStr
       if (row < p.M && col < p.N) {
         float resv = (p.residual && lead) ? p.residual[(long long)row * p.ld_res + col] : 0.0f;
         float auxv = (p.act >= EGV_ACT_GELU_BWD && p.act <= EGV_ACT_TANH_BWD) ? __bfloat162float(p.aux[(long long)row * p.ld_aux + col]) : 0.0f;
-        epilogue_store(p, acc[i][j], row, col, lead, resv, auxv, scale_total);
+        const float fv = epilogue_store(p, acc[i][j], row, col, lead, resv, auxv, scale_total);
+        if (p.colsum) atomicAdd(p.colsum + col, fv);
       }
     }
 }
@@ -547,11 +601,14 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   p.out_pre = (bf16*)a->out_pre_bf16; p.ld_out_pre = a->ld_out_pre;
   p.act = a->act; p.accumulate = a->accumulate;
   {
-    auto even = [](const void* ptr, long long ld, int bytes) { return !ptr || (((uintptr_t)ptr) % bytes == 0 && ld % 2 == 0); };
-    p.vec_ok = (a->N % 2 == 0) && (!a->bias || ((uintptr_t)a->bias) % 8 == 0) && even(a->aux, a->ld_aux, 4) &&
-               even(a->residual, a->ld_res, 8) && even(a->out_f32, a->ld_out_f32, 8) &&
-               even(a->out_bf16, a->ld_out_bf16, 4) && even(a->out_pre_bf16, a->ld_out_pre, 4);
+    auto al4 = [](const void* ptr, long long ld, int bytes) { return !ptr || (((uintptr_t)ptr) % bytes == 0 && ld % 4 == 0); };
+    p.vec_ok = (a->N % 4 == 0) && (!a->bias || ((uintptr_t)a->bias) % 16 == 0) && al4(a->aux, a->ld_aux, 8) &&
+               al4(a->residual, a->ld_res, 16) && al4(a->out_f32, a->ld_out_f32, 16) &&
+               al4(a->out_bf16, a->ld_out_bf16, 8) && al4(a->out_pre_bf16, a->ld_out_pre, 8) &&
+               (!a->colsum || ((uintptr_t)a->colsum) % 4 == 0);
   }
+  p.colsum = a->colsum;
+  if (a->colsum && split_k > 1) return fail(EGV_ERR_ARG, "gemm: colsum cannot be combined with split_k > 1");
 
   const bool a_mn = a->layout == EGV_GEMM_TN;                           // A stored [K, M]
   const bool b_mn = a->layout == EGV_GEMM_NN || a->layout == EGV_GEMM_TN;  // B stored [K, N]

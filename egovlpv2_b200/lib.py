@@ -28,7 +28,7 @@ class GemmArgs(C.Structure):
                 ("out_f32", c_void_p), ("ld_out_f32", c_int64),
                 ("out_bf16", c_void_p), ("ld_out_bf16", c_int64),
                 ("out_pre_bf16", c_void_p), ("ld_out_pre", c_int64),
-                ("act", c_int), ("accumulate", c_int), ("split_k", c_int)]
+                ("act", c_int), ("accumulate", c_int), ("split_k", c_int), ("colsum", c_void_p)]
 
 
 class AttnArgs(C.Structure):
@@ -141,7 +141,7 @@ class Kernels:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, layout, A, B, *, bias=None, aux=None, act=ACT_NONE, scale=1.0, scale_dev=None,
-             residual=None, out_f32=None, out_bf16=None, out_pre=None, accumulate=False, split_k=1):
+             residual=None, out_f32=None, out_bf16=None, out_pre=None, accumulate=False, split_k=1, colsum=None):
         lda = _chk2d(A, torch.bfloat16, "A")
         ldb = _chk2d(B, torch.bfloat16, "B")
         if layout == GEMM_NT:
@@ -180,6 +180,9 @@ class Kernels:
             assert scale_dev.dtype == torch.float32 and scale_dev.numel() == 1
             a.scale_dev = _p(scale_dev)
         a.scale = float(scale)
+        if colsum is not None:
+            assert colsum.dtype == torch.float32 and colsum.numel() == N and colsum.is_contiguous()
+            a.colsum = _p(colsum)
         a.act, a.accumulate, a.split_k = int(act), int(bool(accumulate)), int(split_k)
         self._timed("gemm", 2.0 * M * N * K, lambda: self._check(self.lib.egv_gemm_bf16(C.byref(a), self._stream())))
 

@@ -45,7 +45,7 @@ int egv_device_sm_count(void);
  * epilogue, in this order (each step optional):
  *   v = acc + bias[n];  out_pre = bf16(v);  v = act(v)  or  v *= act'(aux[m,n]);
  *   v *= scale * (scale_dev ? *scale_dev : 1);  v += residual[m,n];
- *   out_f32[m,n] = v (or atomically += v when accumulate != 0);  out_bf16[m,n] = bf16(v)
+ *   out_f32[m,n] = v (or atomically += v when accumulate != 0);  out_bf16[m,n] = bf16(v);  colsum[n] += v
  */
 enum { EGV_GEMM_NT = 0, EGV_GEMM_NN = 1, EGV_GEMM_TN = 2 };
 enum {
@@ -71,6 +71,7 @@ typedef struct egv_gemm_args {
   int act;
   int accumulate;  /* 1: out_f32 += v with fp32 atomics (required when split_k > 1) */
   int split_k;     /* >= 1; K is cut into split_k slices, one CTA pass each */
+  float* colsum;   /* optional [N] f32: colsum[n] += sum_m of the final value v (bias gradients); zero it first */
 } egv_gemm_args;
 int egv_gemm_bf16(const egv_gemm_args* args, egv_stream_t stream);
 /* test hook: route every GEMM through the SIMT fallback kernel (1) or restore normal dispatch (0) */

@@ -63,7 +63,7 @@ class FakeKernels:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, layout, A, B, *, bias=None, aux=None, act=ACT_NONE, scale=1.0, scale_dev=None, residual=None,
-             out_f32=None, out_bf16=None, out_pre=None, accumulate=False, split_k=1):
+             out_f32=None, out_bf16=None, out_pre=None, accumulate=False, split_k=1, colsum=None):
         self._launches += 1
         a, b = A.float(), B.float()
         if layout == GEMM_NT:
@@ -102,6 +102,8 @@ class FakeKernels:
                 out_f32.copy_(v)
         if out_bf16 is not None:
             out_bf16.copy_(v)
+        if colsum is not None:
+            colsum.add_(v.sum(0))
 
     # ------------------------------------------------------------------ LayerNorm
     def layernorm_fwd(self, x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):

@@ -104,12 +104,21 @@ def test_gemm_epilogue(K, R, act):
         o32 = torch.full((M, N), float("nan"), device=DEV)
         o16 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
         opre = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        cs = torch.ones(N, device=DEV)
         impl.gemm(L.GEMM_NT, A, B, bias=bias, aux=aux, act=act, scale=1.5, scale_dev=sdev, residual=res, out_f32=o32,
-                  out_bf16=o16, out_pre=opre)
-        outs.append((o32, o16, opre))
+                  out_bf16=o16, out_pre=opre, colsum=cs)
+        # same problem through the scalar epilogue (odd N: 519 columns)
+        o32s = torch.full((M, N - 1), float("nan"), device=DEV)
+        css = torch.zeros(N - 1, device=DEV)
+        impl.gemm(L.GEMM_NT, A, B[:N - 1], bias=bias[:N - 1].contiguous(), aux=None if aux is None else aux[:, :N - 1],
+                  act=act, scale=1.5, scale_dev=sdev, residual=res[:, :N - 1], out_f32=o32s, colsum=css)
+        outs.append((o32, o16, opre, cs, o32s, css))
     check(outs[0][0], outs[1][0], 2e-5, "epilogue f32 act %d" % act)
     check(outs[0][1], outs[1][1], 4e-3, "epilogue bf16 act %d" % act)
     check(outs[0][2], outs[1][2], 4e-3, "epilogue pre act %d" % act)
+    check(outs[0][3], outs[1][3], 1e-4, "epilogue colsum act %d" % act)
+    check(outs[0][4], outs[1][4], 2e-5, "scalar epilogue f32 act %d" % act)
+    check(outs[0][5], outs[1][5], 1e-4, "scalar epilogue colsum act %d" % act)
 
 
 def test_gemm_inplace_residual_and_strided_outputs(K, R):

@@ -37,11 +37,15 @@ def operands(layout, M, N, Kd):
 
 
 shapes = [(25096, 2304, 768), (25096, 768, 768), (25096, 3072, 768), (25096, 768, 3072), (25096, 1536, 768)]
+ONLY = os.environ.get("GEMM_ONLY")       # substring of the variant name
+LAYOUTS = os.environ.get("GEMM_LAYOUTS", "NT,NN,TN,REF").split(",")
 if len(sys.argv) > 1:
     shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
 print("%-22s %-4s %-26s %9s %9s" % ("shape MxNxK", "lay", "epilogue", "us", "TFLOP/s"))
 for (M, N, Kd) in shapes:
     for layout, lname in ((L.GEMM_NT, "NT"), (L.GEMM_NN, "NN")):
+        if lname not in LAYOUTS:
+            continue
         A, B = operands(layout, M, N, Kd)
         bias = torch.randn(N, device=dev)
         res = torch.randn(M, N, device=dev)
@@ -57,15 +61,19 @@ for (M, N, Kd) in shapes:
             ("gelu_bwd(aux) + bf16 out", dict(aux=opre, act=L.ACT_GELU_BWD, out_bf16=o16)),
         ]
         for name, kw in variants:
+            if ONLY and ONLY not in name:
+                continue
             t = timeit(lambda: K.gemm(layout, A, B, **kw))
             print("%-22s %-4s %-26s %9.1f %9.1f" % ("%dx%dx%d" % (M, N, Kd), lname, name, t * 1e6, 2.0 * M * N * Kd / t / 1e12))
+    if "TN" not in LAYOUTS:
+        continue
     # weight-gradient shape: out [N, Kd] = dy^T x with reduction over M
     A, B = torch.randn(M, N, device=dev).bfloat16(), torch.randn(M, Kd, device=dev).bfloat16()
     out = torch.empty(N, Kd, device=dev)
     t = timeit(lambda: K.gemm(L.GEMM_TN, A, B, out_f32=out))
     print("%-22s %-4s %-26s %9.1f %9.1f" % ("%dx%dx%d" % (N, Kd, M), "TN", "f32 out (auto split-K)", t * 1e6, 2.0 * M * N * Kd / t / 1e12))
 # reference point: cuBLAS through torch
-for (M, N, Kd) in shapes:
+for (M, N, Kd) in (shapes if "REF" in LAYOUTS else []):
     A, B = torch.randn(M, Kd, device=dev).bfloat16(), torch.randn(N, Kd, device=dev).bfloat16()
     t = timeit(lambda: torch.matmul(A, B.t()))
     print("%-22s %-4s %-26s %9.1f %9.1f" % ("%dx%dx%d" % (M, N, Kd), "NT", "torch.matmul (cuBLAS) ref", t * 1e6, 2.0 * M * N * Kd / t / 1e12))
