@@ -52,12 +52,13 @@ EGV_DEVINL long long k_row(const AttnP& a, int b, int g, int j) {
 }
 
 // which logical tensor a smem tile is filled from
-enum { T_Q = 0, T_K = 1, T_V = 2, T_DO = 3 };
+enum { T_Q = 0, T_K = 1, T_V = 2, T_DO = 3, T_O = 4 };
 
 template <int WHAT>
 EGV_DEVINL const bf16* row_ptr(const AttnP& a, int b, int h, int g, int idx) {
   if (WHAT == T_Q) return a.q + q_row(a, b, g, idx) * a.ldq + h * HD;
   if (WHAT == T_DO) return a.d_o + o_row(a, b, g, idx) * a.ldo + h * HD;
+  if (WHAT == T_O) return a.o + o_row(a, b, g, idx) * a.ldo + h * HD;
   if (WHAT == T_K) return a.k + k_row(a, b, g, idx) * a.ldkv + h * HD;
   return a.v + k_row(a, b, g, idx) * a.ldkv + h * HD;
 }
@@ -178,6 +179,8 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
   } else if (MODE == MODE_DQ) {
     load_tile<T_Q, ROWS, NT>(rowA, a, b, h, g, row0, n_rows, tid);
     load_tile<T_DO, ROWS, NT>(rowB, a, b, h, g, row0, n_rows, tid);
+    static_assert(KC >= 16 * NW || NW > 4, "the O tile is staged in the stream buffer");
+    load_tile<T_O, ROWS, NT>(strA, a, b, h, g, row0, n_rows, tid);   // O rows, only for delta = rowsum(dO * O)
   } else {
     load_tile<T_K, ROWS, NT>(rowA, a, b, h, g, row0, n_rows, tid);
     load_tile<T_V, ROWS, NT>(rowB, a, b, h, g, row0, n_rows, tid);
@@ -195,17 +198,13 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
   const int r_lo = row0 + wq * 16 + gq, r_hi = r_lo + 8;
   float st0_lo = 0.f, st0_hi = 0.f, st1_lo = 0.f, st1_hi = 0.f;
   if (MODE == MODE_DQ) {
-    // delta_i = sum_d dO[i,d] * O[i,d]; one row per iteration, 2 columns per lane
+    // delta_i = sum_d dO[i,d] * O[i,d] from the staged tiles; one row per iteration, 2 columns per lane
+#pragma unroll
     for (int r = 0; r < 16; ++r) {
       const int idx = row0 + wq * 16 + r;
-      float part = 0.f;
-      if (idx < n_rows) {
-        const long long orow = o_row(a, b, g, idx) * a.ldo + h * HD + 2 * lane;
-        float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.d_o + orow));
-        float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.o + orow));
-        part = x.x * y.x + x.y * y.y;
-      }
-      part = warp_sum(part);
+      const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(rowB + (wq * 16 + r) * LDS + 2 * lane));
+      const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(strA + (wq * 16 + r) * LDS + 2 * lane));
+      const float part = warp_sum(x.x * y.x + x.y * y.y);
       if (idx < n_rows && lane == 0) a.delta[stat_base + idx] = part;
       if (r == gq) st1_lo = part;
       if (r == gq + 8) st1_hi = part;
@@ -425,6 +424,403 @@ __global__ void __launch_bounds__(128) attn_warp_kernel(const AttnP a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Single-query attention (the CLS query of VarAttention: one query row per (b, h), every token a key).
+// One CTA per (b, h, g); every warp streams a strided subset of the keys with coalesced 128-byte row reads
+// (2 head-dim elements per lane), keeps an online-softmax partial (m, l, o[2 per lane]) and the CTA merges the
+// partials through shared memory.  Pure HBM/L2 streaming: 2 * Lk * 128 bytes per (b, h).
+constexpr int SQ_WARPS = 16;
+
+__global__ void __launch_bounds__(SQ_WARPS * 32) attn_single_fwd_kernel(const AttnP a) {
+  __shared__ float sm_m[SQ_WARPS], sm_l[SQ_WARPS];
+  __shared__ float sm_o[SQ_WARPS][HD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = blockIdx.x % a.G;
+  const int h = (blockIdx.x / a.G) % a.H;
+  const int b = blockIdx.x / (a.G * a.H);
+  const float scale2 = a.scale * LOG2E;
+  const float2 q = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.q + q_row(a, b, g, 0) * a.ldq + h * HD + 2 * lane));
+  float m = -1e30f, l = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int j0 = warp; j0 < a.LkT; j0 += SQ_WARPS * 4) {
+    // 4 keys in flight per warp iteration
+    float2 kk[4], vv[4];
+    float sc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * SQ_WARPS;
+      if (j < a.LkT) {
+        const long long off = k_row(a, b, g, j) * a.ldkv + h * HD + 2 * lane;
+        kk[u] = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.k + off));
+        vv[u] = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.v + off));
+      } else {
+        kk[u] = vv[u] = make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * SQ_WARPS;
+      float d = warp_sum(q.x * kk[u].x + q.y * kk[u].y);
+      float bj = 0.f;
+      if (a.key_bias && j < a.LkT) bj = fmaxf(a.key_bias[(long long)b * a.LkT + j], -1e30f) * LOG2E;
+      sc[u] = j < a.LkT ? fmaf(d, scale2, bj) : -1e30f;
+    }
+    float mn = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])), m);
+    const float al = exp2f(m - mn);
+    l *= al;
+    o0 *= al;
+    o1 *= al;
+    m = mn;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * SQ_WARPS;
+      const float pj = j < a.LkT ? exp2f(sc[u] - m) : 0.f;
+      l += pj;
+      o0 = fmaf(pj, vv[u].x, o0);
+      o1 = fmaf(pj, vv[u].y, o1);
+    }
+  }
+  if (lane == 0) {
+    sm_m[warp] = m;
+    sm_l[warp] = l;
+  }
+  sm_o[warp][2 * lane] = o0;
+  sm_o[warp][2 * lane + 1] = o1;
+  __syncthreads();
+  if (warp == 0) {
+    float M = -1e30f;
+#pragma unroll
+    for (int w = 0; w < SQ_WARPS; ++w) M = fmaxf(M, sm_m[w]);
+    float L = 0.f, r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < SQ_WARPS; ++w) {
+      const float f = exp2f(sm_m[w] - M);
+      L = fmaf(sm_l[w], f, L);
+      r0 = fmaf(sm_o[w][2 * lane], f, r0);
+      r1 = fmaf(sm_o[w][2 * lane + 1], f, r1);
+    }
+    const float inv = 1.0f / L;
+    *reinterpret_cast<uint32_t*>(a.o + o_row(a, b, g, 0) * a.ldo + h * HD + 2 * lane) = pack_bf16(r0 * inv, r1 * inv);
+    if (lane == 0) a.lse[((long long)b * a.H + h) * a.G + g] = M + log2f(L);
+  }
+}
+
+// Backward of the single-query attention: P_j = exp2(s_j - lse), dP_j = dO . v_j, dS_j = P_j (dP_j - delta);
+// dq = scale * sum_j dS_j k_j;  dk_j (+)= scale * dS_j q;  dv_j (+)= P_j dO.  The shared CLS key goes to dkv_cls.
+__global__ void __launch_bounds__(SQ_WARPS * 32) attn_single_bwd_kernel(const AttnP a) {
+  __shared__ float sm_q[SQ_WARPS][HD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = blockIdx.x % a.G;
+  const int h = (blockIdx.x / a.G) % a.H;
+  const int b = blockIdx.x / (a.G * a.H);
+  const float scale2 = a.scale * LOG2E;
+  const long long stat = ((long long)b * a.H + h) * a.G + g;
+  const long long qoff = q_row(a, b, g, 0) * a.ldq + h * HD + 2 * lane;
+  const long long ooff = o_row(a, b, g, 0) * a.ldo + h * HD + 2 * lane;
+  const float2 q = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.q + qoff));
+  const float2 d_o = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.d_o + ooff));
+  const float2 o = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.o + ooff));
+  const float delta = warp_sum(d_o.x * o.x + d_o.y * o.y);
+  const float lse = a.lse[stat];
+  if (threadIdx.x == 0) a.delta[stat] = delta;
+  float dq0 = 0.f, dq1 = 0.f;
+  for (int j = warp; j < a.LkT; j += SQ_WARPS) {
+    const long long row = k_row(a, b, g, j);
+    const long long off = row * a.ldkv + h * HD + 2 * lane;
+    const float2 kk = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.k + off));
+    const float2 vv = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.v + off));
+    float s = q.x * kk.x + q.y * kk.y;
+    float dp = d_o.x * vv.x + d_o.y * vv.y;
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, sh);
+      dp += __shfl_xor_sync(0xffffffffu, dp, sh);
+    }
+    float bj = 0.f;
+    if (a.key_bias) bj = fmaxf(a.key_bias[(long long)b * a.LkT + j], -1e30f) * LOG2E;
+    const float pj = exp2f(fmaf(s, scale2, bj) - lse);
+    const float ds = pj * (dp - delta);
+    dq0 = fmaf(ds, kk.x, dq0);
+    dq1 = fmaf(ds, kk.y, dq1);
+    const float gk0 = a.scale * ds * q.x, gk1 = a.scale * ds * q.y;
+    const float gv0 = pj * d_o.x, gv1 = pj * d_o.y;
+    if (a.has_cls && j == 0) {
+      float* dst = a.dkv_cls + ((long long)b * a.H + h) * 2 * HD;
+      atomicAdd(dst + 2 * lane, gk0);
+      atomicAdd(dst + 2 * lane + 1, gk1);
+      atomicAdd(dst + HD + 2 * lane, gv0);
+      atomicAdd(dst + HD + 2 * lane + 1, gv1);
+    } else {
+      const long long goff = row * a.lddkv + h * HD + 2 * lane;
+      uint32_t* pk = reinterpret_cast<uint32_t*>(a.dk + goff);
+      uint32_t* pv = reinterpret_cast<uint32_t*>(a.dv + goff);
+      if (a.dkv_accumulate) {
+        const float2 ok = unpack_bf16(*pk), ov = unpack_bf16(*pv);
+        *pk = pack_bf16(ok.x + gk0, ok.y + gk1);
+        *pv = pack_bf16(ov.x + gv0, ov.y + gv1);
+      } else {
+        *pk = pack_bf16(gk0, gk1);
+        *pv = pack_bf16(gv0, gv1);
+      }
+    }
+  }
+  sm_q[warp][2 * lane] = dq0;
+  sm_q[warp][2 * lane + 1] = dq1;
+  __syncthreads();
+  if (warp == 0) {
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < SQ_WARPS; ++w) {
+      r0 += sm_q[w][2 * lane];
+      r1 += sm_q[w][2 * lane + 1];
+    }
+    *reinterpret_cast<uint32_t*>(a.dq + q_row(a, b, g, 0) * a.lddq + h * HD + 2 * lane) = pack_bf16(r0 * a.scale, r1 * a.scale);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Single-query attention, all heads per warp (H % 4 == 0, H <= 16).  A warp reads the full key / value row of one
+// token (H*64 bf16 = 1.5 KB contiguous for H = 12) with 16-byte loads: lane l holds elements [256 i + 8 l, +8) of
+// group i, i.e. head 4 i + l / 8, so a dot product is an 8-lane reduction.  CTA = (batch, key split): B * SQ_SPLITS
+// CTAs fill the GPU; partial (m, l, o) per (b, split, h) are merged by a second tiny kernel.
+constexpr int SQ_SPLITS = 16;
+constexpr int SQH_WARPS = 8;
+
+struct bf16x8 { float v[8]; };
+EGV_DEVINL bf16x8 ld8(const bf16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  bf16x8 r;
+  float2 t = unpack_bf16(u.x); r.v[0] = t.x; r.v[1] = t.y;
+  t = unpack_bf16(u.y); r.v[2] = t.x; r.v[3] = t.y;
+  t = unpack_bf16(u.z); r.v[4] = t.x; r.v[5] = t.y;
+  t = unpack_bf16(u.w); r.v[6] = t.x; r.v[7] = t.y;
+  return r;
+}
+EGV_DEVINL float dot8(const bf16x8& a, const bf16x8& b) {
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s = fmaf(a.v[e], b.v[e], s);
+  return s;
+}
+EGV_DEVINL float red8(float s) {   // sum over the 8 lanes that share a head
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  return s;
+}
+
+// partial layout: part[((b * SQ_SPLITS + split) * H + h) * 66 + {0: m, 1: l, 2..65: o}]
+template <int NG>
+__global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_fwd_heads_kernel(const AttnP a, float* __restrict__ part) {
+  __shared__ float sm_m[SQH_WARPS][NG * 4], sm_l[SQH_WARPS][NG * 4];
+  __shared__ float sm_o[SQH_WARPS][NG * 256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int split = blockIdx.x % SQ_SPLITS, b = blockIdx.x / SQ_SPLITS;
+  const float scale2 = a.scale * LOG2E;
+  const int per = (a.LkT + SQ_SPLITS - 1) / SQ_SPLITS;
+  const int j_lo = split * per, j_hi = min(a.LkT, j_lo + per);
+  bf16x8 q[NG];
+  const bf16* qp = a.q + q_row(a, b, 0, 0) * a.ldq;
+#pragma unroll
+  for (int i = 0; i < NG; ++i) q[i] = ld8(qp + 256 * i + 8 * lane);
+  float m[NG], l[NG], o[NG][8];
+#pragma unroll
+  for (int i = 0; i < NG; ++i) {
+    m[i] = -1e30f;
+    l[i] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[i][e] = 0.f;
+  }
+  for (int j = j_lo + warp; j < j_hi; j += SQH_WARPS) {
+    const long long off = k_row(a, b, 0, j) * a.ldkv;
+    bf16x8 kk[NG], vv[NG];
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      kk[i] = ld8(a.k + off + 256 * i + 8 * lane);
+      vv[i] = ld8(a.v + off + 256 * i + 8 * lane);
+    }
+    float bj = 0.f;
+    if (a.key_bias) bj = fmaxf(a.key_bias[(long long)b * a.LkT + j], -1e30f) * LOG2E;
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      const float sc = fmaf(red8(dot8(q[i], kk[i])), scale2, bj);
+      const float mn = fmaxf(m[i], sc);
+      const float al = exp2f(m[i] - mn), pj = exp2f(sc - mn);
+      m[i] = mn;
+      l[i] = fmaf(l[i], al, pj);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[i][e] = fmaf(o[i][e], al, pj * vv[i].v[e]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NG; ++i) {
+    if ((lane & 7) == 0) {
+      sm_m[warp][4 * i + (lane >> 3)] = m[i];
+      sm_l[warp][4 * i + (lane >> 3)] = l[i];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sm_o[warp][256 * i + 8 * lane + e] = o[i][e];
+  }
+  __syncthreads();
+  // merge the warps: thread t < H*64 owns output element t (head t / 64)
+  for (int t = threadIdx.x; t < a.H * HD; t += SQH_WARPS * 32) {
+    const int h = t >> 6;
+    float M = -1e30f;
+#pragma unroll
+    for (int w = 0; w < SQH_WARPS; ++w) M = fmaxf(M, sm_m[w][h]);
+    float L = 0.f, r = 0.f;
+#pragma unroll
+    for (int w = 0; w < SQH_WARPS; ++w) {
+      const float f = exp2f(sm_m[w][h] - M);
+      L = fmaf(sm_l[w][h], f, L);
+      r = fmaf(sm_o[w][t], f, r);
+    }
+    float* dst = part + (((long long)b * SQ_SPLITS + split) * a.H + h) * 66;
+    dst[2 + (t & 63)] = r;
+    if ((t & 63) == 0) {
+      dst[0] = M;
+      dst[1] = L;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(64) attn_single_combine_kernel(const AttnP a, const float* __restrict__ part) {
+  const int h = blockIdx.x % a.H, b = blockIdx.x / a.H;
+  const int d = threadIdx.x;
+  float M = -1e30f;
+  for (int s = 0; s < SQ_SPLITS; ++s) M = fmaxf(M, part[(((long long)b * SQ_SPLITS + s) * a.H + h) * 66]);
+  float L = 0.f, r = 0.f;
+  for (int s = 0; s < SQ_SPLITS; ++s) {
+    const float* p = part + (((long long)b * SQ_SPLITS + s) * a.H + h) * 66;
+    const float f = exp2f(p[0] - M);
+    L = fmaf(p[1], f, L);
+    r = fmaf(p[2 + d], f, r);
+  }
+  a.o[o_row(a, b, 0, 0) * a.ldo + h * HD + d] = __float2bfloat16(r / L);
+  if (d == 0) a.lse[(long long)b * a.H + h] = M + log2f(L);
+}
+
+// backward, all heads per warp.  dq is accumulated in fp32 (dq_acc [B, H*64], zeroed by the host wrapper) and written
+// out by attn_single_dq_finalize_kernel.
+template <int NG>
+__global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_bwd_heads_kernel(const AttnP a, float* __restrict__ dq_acc) {
+  __shared__ float sm_q[SQH_WARPS][NG * 256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int split = blockIdx.x % SQ_SPLITS, b = blockIdx.x / SQ_SPLITS;
+  const float scale2 = a.scale * LOG2E;
+  const int per = (a.LkT + SQ_SPLITS - 1) / SQ_SPLITS;
+  const int j_lo = split * per, j_hi = min(a.LkT, j_lo + per);
+  bf16x8 q[NG], d_o[NG];
+  float delta[NG], lse[NG], dq[NG][8];
+  const bf16* qp = a.q + q_row(a, b, 0, 0) * a.ldq;
+  const long long orow = o_row(a, b, 0, 0) * a.ldo;
+#pragma unroll
+  for (int i = 0; i < NG; ++i) {
+    q[i] = ld8(qp + 256 * i + 8 * lane);
+    d_o[i] = ld8(a.d_o + orow + 256 * i + 8 * lane);
+    const bf16x8 oo = ld8(a.o + orow + 256 * i + 8 * lane);
+    delta[i] = red8(dot8(d_o[i], oo));
+    const int h = 4 * i + (lane >> 3);
+    lse[i] = a.lse[(long long)b * a.H + h];
+    if (split == 0 && warp == 0 && (lane & 7) == 0) a.delta[(long long)b * a.H + h] = delta[i];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dq[i][e] = 0.f;
+  }
+  for (int j = j_lo + warp; j < j_hi; j += SQH_WARPS) {
+    const long long row = k_row(a, b, 0, j);
+    const long long off = row * a.ldkv, goff = row * a.lddkv;
+    const bool to_cls = a.has_cls && j == 0;
+    bf16x8 kk[NG], vv[NG];
+    uint4 ok[NG], ov[NG];
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      kk[i] = ld8(a.k + off + 256 * i + 8 * lane);
+      vv[i] = ld8(a.v + off + 256 * i + 8 * lane);
+      if (a.dkv_accumulate && !to_cls) {
+        ok[i] = *reinterpret_cast<const uint4*>(a.dk + goff + 256 * i + 8 * lane);
+        ov[i] = *reinterpret_cast<const uint4*>(a.dv + goff + 256 * i + 8 * lane);
+      } else {
+        ok[i] = ov[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    float bj = 0.f;
+    if (a.key_bias) bj = fmaxf(a.key_bias[(long long)b * a.LkT + j], -1e30f) * LOG2E;
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      const float s = red8(dot8(q[i], kk[i]));
+      const float dp = red8(dot8(d_o[i], vv[i]));
+      const float pj = exp2f(fmaf(s, scale2, bj) - lse[i]);
+      const float ds = pj * (dp - delta[i]);
+      float gk[8], gv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dq[i][e] = fmaf(ds, kk[i].v[e], dq[i][e]);
+        gk[e] = a.scale * ds * q[i].v[e];
+        gv[e] = pj * d_o[i].v[e];
+      }
+      if (to_cls) {
+        const int h = 4 * i + (lane >> 3);
+        float* dst = a.dkv_cls + ((long long)b * a.H + h) * 2 * HD + 8 * (lane & 7);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          atomicAdd(dst + e, gk[e]);
+          atomicAdd(dst + HD + e, gv[e]);
+        }
+      } else {
+        const uint32_t* pk = reinterpret_cast<const uint32_t*>(&ok[i]);
+        const uint32_t* pv = reinterpret_cast<const uint32_t*>(&ov[i]);
+        uint4 wk, wv;
+        uint32_t* qk = reinterpret_cast<uint32_t*>(&wk);
+        uint32_t* qv = reinterpret_cast<uint32_t*>(&wv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 x = unpack_bf16(pk[e]), y = unpack_bf16(pv[e]);
+          qk[e] = pack_bf16(x.x + gk[2 * e], x.y + gk[2 * e + 1]);
+          qv[e] = pack_bf16(y.x + gv[2 * e], y.y + gv[2 * e + 1]);
+        }
+        *reinterpret_cast<uint4*>(a.dk + goff + 256 * i + 8 * lane) = wk;
+        *reinterpret_cast<uint4*>(a.dv + goff + 256 * i + 8 * lane) = wv;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NG; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sm_q[warp][256 * i + 8 * lane + e] = dq[i][e];
+  __syncthreads();
+  for (int t = threadIdx.x; t < a.H * HD; t += SQH_WARPS * 32) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < SQH_WARPS; ++w) r += sm_q[w][t];
+    atomicAdd(dq_acc + (long long)b * a.H * HD + t, r * a.scale);
+  }
+}
+
+__global__ void attn_single_dq_finalize_kernel(const AttnP a, const float* __restrict__ dq_acc) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.B * a.H * HD) return;
+  const int b = t / (a.H * HD), c = t % (a.H * HD);
+  a.dq[q_row(a, b, 0, 0) * a.lddq + c] = __float2bfloat16(dq_acc[t]);
+}
+
+// library-owned scratch for the split single-query kernels (grows on demand; one stream at a time)
+static float* sq_workspace(size_t floats) {
+  static float* buf = nullptr;
+  static size_t cap = 0;
+  if (floats > cap) {
+    if (buf) cudaFree(buf);
+    cap = floats * 2;
+    if (cudaMalloc(&buf, cap * sizeof(float)) != cudaSuccess) {
+      buf = nullptr;
+      cap = 0;
+    }
+  }
+  return buf;
+}
+
+static bool single_heads_ok(const AttnP& a) {
+  return a.Lq == 1 && a.G == 1 && a.H % 4 == 0 && a.H <= 16 && a.LkT >= 256;
+}
+
 // fp32 CLS accumulators -> bf16 rows of the dk / dv tensors
 __global__ void attn_cls_finalize_kernel(const float* __restrict__ dkv_cls, bf16* dk, bf16* dv, long long lddkv,
                                          long long kv_bstride, int cls_row, int B, int H, int accumulate) {
@@ -546,6 +942,26 @@ extern "C" int egv_attention_fwd(const egv_attn_args* x, egv_stream_t stream) {
   AttnP a;
   int rc = fill_params(x, a, false);
   if (rc) return rc;
+  if (single_heads_ok(a)) {
+    float* part = sq_workspace((size_t)a.B * SQ_SPLITS * a.H * 66);
+    if (!part) return fail(EGV_ERR_CUDA, "attention: workspace allocation failed");
+    const unsigned grid = (unsigned)(a.B * SQ_SPLITS);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (a.H / 4) {
+      case 1: attn_single_fwd_heads_kernel<1><<<grid, SQH_WARPS * 32, 0, s>>>(a, part); break;
+      case 2: attn_single_fwd_heads_kernel<2><<<grid, SQH_WARPS * 32, 0, s>>>(a, part); break;
+      case 3: attn_single_fwd_heads_kernel<3><<<grid, SQH_WARPS * 32, 0, s>>>(a, part); break;
+      default: attn_single_fwd_heads_kernel<4><<<grid, SQH_WARPS * 32, 0, s>>>(a, part); break;
+    }
+    rc = check_launch("attn_single_fwd_heads_kernel");
+    if (rc) return rc;
+    attn_single_combine_kernel<<<(unsigned)(a.B * a.H), 64, 0, s>>>(a, part);
+    return check_launch("attn_single_combine_kernel");
+  }
+  if (a.Lq == 1) {
+    attn_single_fwd_kernel<<<(unsigned)(a.B * a.H * a.G), SQ_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("attn_single_fwd_kernel");
+  }
   return launch_mode<MODE_FWD>(a, (cudaStream_t)stream);
 }
 
@@ -553,6 +969,28 @@ extern "C" int egv_attention_bwd(const egv_attn_args* x, egv_stream_t stream) {
   AttnP a;
   int rc = fill_params(x, a, true);
   if (rc) return rc;
+  if (single_heads_ok(a)) {
+    const size_t n = (size_t)a.B * a.H * HD;
+    float* acc = sq_workspace(n);
+    if (!acc) return fail(EGV_ERR_CUDA, "attention: workspace allocation failed");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(acc, 0, n * sizeof(float), s);
+    const unsigned grid = (unsigned)(a.B * SQ_SPLITS);
+    switch (a.H / 4) {
+      case 1: attn_single_bwd_heads_kernel<1><<<grid, SQH_WARPS * 32, 0, s>>>(a, acc); break;
+      case 2: attn_single_bwd_heads_kernel<2><<<grid, SQH_WARPS * 32, 0, s>>>(a, acc); break;
+      case 3: attn_single_bwd_heads_kernel<3><<<grid, SQH_WARPS * 32, 0, s>>>(a, acc); break;
+      default: attn_single_bwd_heads_kernel<4><<<grid, SQH_WARPS * 32, 0, s>>>(a, acc); break;
+    }
+    rc = check_launch("attn_single_bwd_heads_kernel");
+    if (rc) return rc;
+    attn_single_dq_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, acc);
+    return check_launch("attn_single_dq_finalize_kernel");
+  }
+  if (a.Lq == 1) {
+    attn_single_bwd_kernel<<<(unsigned)(a.B * a.H * a.G), SQ_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("attn_single_bwd_kernel");
+  }
   rc = launch_mode<MODE_DQ>(a, (cudaStream_t)stream);   // also produces delta
   if (rc) return rc;
   return launch_mode<MODE_DKV>(a, (cudaStream_t)stream);

@@ -78,25 +78,28 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x,
 }
 
 // val = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dx = (add ? add : 0) + val (add may alias dx);
-// dx_bf16 = bf16(bf16_total ? dx : val);  dgamma += sum dy*xhat;  dbeta += sum dy
+// dx_bf16 = bf16(bf16_total ? dx : val);  dgamma += sum dy*xhat;  dbeta += sum dy;  out_colsum += sum of the value
+// written to dx_bf16 (bias gradient of the Linear that produced this LayerNorm's input branch).
+// One warp per row.  The three column accumulators live in per-warp shared memory (lane-private float4 slots, no
+// conflicts, no atomics) so that registers only hold one row: high occupancy for an HBM-bound kernel.
 template <bool DYBF, bool XBF>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, long long rows, int C,
                                                      const float* add, float* dx, int bf16_total, bf16* __restrict__ dx_bf16,
-                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float red[8][32 * 4 + 1];
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                     float* __restrict__ out_colsum) {
+  extern __shared__ __align__(16) float ln_smem[];   // [8 warps][3][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long warp0 = (long long)blockIdx.x * 8 + warp;
   const long long nwarps = (long long)gridDim.x * 8;
   const int nv = C >> 2;
-  float4 dg[LN_MAXV], db[LN_MAXV], g[LN_MAXV];
-#pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int c4 = lane + i * 32;
-    g[i] = c4 < nv ? *reinterpret_cast<const float4*>(gamma + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  float4* acc_g = reinterpret_cast<float4*>(ln_smem + (size_t)warp * 3 * C);
+  float4* acc_b = acc_g + nv;
+  float4* acc_s = acc_b + nv;
+  const bool want_params = dgamma != nullptr || dbeta != nullptr;
+  const bool want_cs = out_colsum != nullptr;
+  for (int c4 = lane; c4 < nv; c4 += 32) acc_g[c4] = acc_b[c4] = acc_s[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long row = warp0; row < rows; row += nwarps) {
     const long long base = row * C;
     const float mu = mean[row], rs = rstd[row];
@@ -108,12 +111,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
       if (c4 < nv) {
         const float4 xv = ld4<XBF>(x, base + 4 * c4);
         const float4 d = ld4<DYBF>(dy, base + 4 * c4);
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c4);
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        gy[i] = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
+        gy[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
         s1 += gy[i].x + gy[i].y + gy[i].z + gy[i].w;
         s2 += gy[i].x * xh[i].x + gy[i].y * xh[i].y + gy[i].z * xh[i].z + gy[i].w * xh[i].w;
-        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
-        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+        if (want_params) {
+          float4 a = acc_g[c4], b = acc_b[c4];
+          a.x += d.x * xh[i].x; a.y += d.y * xh[i].y; a.z += d.z * xh[i].z; a.w += d.w * xh[i].w;
+          b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+          acc_g[c4] = a;
+          acc_b[c4] = b;
+        }
       }
     }
     s1 = warp_sum(s1) / C;
@@ -133,35 +142,30 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
           tot.x += old.x; tot.y += old.y; tot.z += old.z; tot.w += old.w;
         }
         if (dx) *reinterpret_cast<float4*>(dx + base + 4 * c4) = tot;
-        if (dx_bf16) st4_bf16(dx_bf16 + base + 4 * c4, bf16_total ? tot : o);
+        const float4 ob = bf16_total ? tot : o;
+        if (dx_bf16) st4_bf16(dx_bf16 + base + 4 * c4, ob);
+        if (want_cs) {
+          float4 a = acc_s[c4];
+          a.x += ob.x; a.y += ob.y; a.z += ob.z; a.w += ob.w;
+          acc_s[c4] = a;
+        }
       }
     }
   }
-  // block reduction of the column sums, then one atomic per column per block
-  if (dgamma || dbeta) {
+  __syncthreads();
+  // block reduction over the 8 warps, then one atomic per column per block
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float g = 0.f, b = 0.f, sc = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-      const int c4 = lane + i * 32;  // uniform guard across warps
-      if (i * 32 >= nv) break;
-      for (int pass = 0; pass < 2; ++pass) {
-        const float4 val = pass == 0 ? dg[i] : db[i];
-        __syncthreads();
-        red[warp][lane * 4 + 0] = val.x;
-        red[warp][lane * 4 + 1] = val.y;
-        red[warp][lane * 4 + 2] = val.z;
-        red[warp][lane * 4 + 3] = val.w;
-        __syncthreads();
-        if (threadIdx.x < 128) {
-          float s = 0.f;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-          const int col = 4 * (i * 32 + (threadIdx.x >> 2)) + (threadIdx.x & 3);
-          float* dst = pass == 0 ? dgamma : dbeta;
-          if (dst && col < C) atomicAdd(dst + col, s);
-        }
-      }
-      (void)c4;
+    for (int w = 0; w < 8; ++w) {
+      const float* base = ln_smem + (size_t)w * 3 * C;
+      g += base[c];
+      b += base[C + c];
+      sc += base[2 * C + c];
     }
+    if (dgamma) atomicAdd(dgamma + c, g);
+    if (dbeta) atomicAdd(dbeta + c, b);
+    if (out_colsum) atomicAdd(out_colsum + c, sc);
   }
 }
 
@@ -187,17 +191,27 @@ extern "C" int egv_layernorm_fwd(const void* x, int x_is_bf16, const float* gamm
 
 extern "C" int egv_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_bf16, const float* gamma,
                                  const float* mean, const float* rstd, int64_t rows, int C, const float* add, float* dx,
-                                 void* dx_bf16, int bf16_total, float* dgamma, float* dbeta, egv_stream_t stream) {
+                                 void* dx_bf16, int bf16_total, float* dgamma, float* dbeta, float* out_colsum,
+                                 egv_stream_t stream) {
   if (!dy || !x || !gamma || !mean || !rstd) return fail(EGV_ERR_ARG, "layernorm_bwd: null pointer");
   if (C % 4 || C > 128 * LN_MAXV || C <= 0) return fail(EGV_ERR_UNSUPPORTED, "layernorm: C=%d must be a multiple of 4 and <= 1024", C);
   if (rows <= 0) return EGV_OK;
   long long blocks = cdiv(rows, 8 * 8);  // >= 8 rows per warp amortises the column-sum atomics
-  const long long cap = (long long)sm_count() * 4;
+  const long long cap = (long long)sm_count() * 2;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   cudaStream_t s = (cudaStream_t)stream;
-#define EGV_LN_BWD(DYB, XB) \
-  ln_bwd_kernel<DYB, XB><<<(unsigned)blocks, 256, 0, s>>>(dy, x, gamma, mean, rstd, rows, C, add, dx, bf16_total, (bf16*)dx_bf16, dgamma, dbeta)
+  const int smem = 8 * 3 * C * (int)sizeof(float);
+#define EGV_LN_BWD(DYB, XB)                                                                                          \
+  do {                                                                                                               \
+    static bool cfg = false;                                                                                         \
+    if (!cfg) {                                                                                                      \
+      cudaFuncSetAttribute(ln_bwd_kernel<DYB, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4);   \
+      cfg = true;                                                                                                    \
+    }                                                                                                                \
+    ln_bwd_kernel<DYB, XB><<<(unsigned)blocks, 256, smem, s>>>(dy, x, gamma, mean, rstd, rows, C, add, dx,           \
+                                                               bf16_total, (bf16*)dx_bf16, dgamma, dbeta, out_colsum); \
+  } while (0)
   if (dy_is_bf16 && x_is_bf16) EGV_LN_BWD(true, true);
   else if (dy_is_bf16) EGV_LN_BWD(true, false);
   else if (x_is_bf16) EGV_LN_BWD(false, true);

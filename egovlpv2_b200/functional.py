@@ -31,12 +31,18 @@ def _z(like, shape, dtype=F32):
 
 
 # ----------------------------------------------------------------------------------------------- linear
-def linear_bwd_params(K, dy_bf, x_bf, scale_dev=None, scale=1.0, bias=True):
-    """dW [N, Kd] = dy^T x, db [N] = colsum(dy)  (optionally scaled by a device scalar)."""
+def linear_bwd_params(K, dy_bf, x_bf, scale_dev=None, scale=1.0, bias=True, db=None):
+    """dW [N, Kd] = dy^T x, db [N] = colsum(dy)  (optionally scaled by a device scalar).  `db`: column sums already
+    produced by the kernel that wrote dy (GEMM / LayerNorm-backward epilogues) -- skips the colsum launch."""
     N, Kd = dy_bf.shape[1], x_bf.shape[1]
     dW = _e(dy_bf, (N, Kd), F32)
     K.gemm(GEMM_TN, dy_bf, x_bf, out_f32=dW, scale=scale, scale_dev=scale_dev)
-    db = None
+    if db is not None:
+        if scale_dev is not None or scale != 1.0:
+            sdb = _e(dy_bf, (N,), F32)
+            K.axpy(None, db, scale, scale_dev, y=sdb)
+            db = sdb
+        return dW, db
     if bias:
         db = _e(dy_bf, (N,), F32)
         K.colsum(dy_bf, db, scale=scale, scale_dev=scale_dev)
@@ -174,18 +180,21 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True):
     # ---- MLP: out = sr + fc2(gelu(fc1(ln2)))
     g["mlp.fc2.weight"], g["mlp.fc2.bias"] = linear_bwd_params(K, d_out_bf, s.h_act)
     d_hpre = _e(d_out, s.h_pre.shape, BF16)
-    K.gemm(GEMM_NN, d_out_bf, w["mlp.fc2.weight"], aux=s.h_pre, act=ACT_GELU_BWD, out_bf16=d_hpre)
-    g["mlp.fc1.weight"], g["mlp.fc1.bias"] = linear_bwd_params(K, d_hpre, s.ln2)
+    db1 = _z(d_out, (s.h_pre.shape[1],))
+    K.gemm(GEMM_NN, d_out_bf, w["mlp.fc2.weight"], aux=s.h_pre, act=ACT_GELU_BWD, out_bf16=d_hpre, colsum=db1)
+    g["mlp.fc1.weight"], g["mlp.fc1.bias"] = linear_bwd_params(K, d_hpre, s.ln2, db=db1)
     d_ln2 = _e(d_out, (M, C), BF16)
     K.gemm(GEMM_NN, d_hpre, w["mlp.fc1.weight"], out_bf16=d_ln2)
     del d_hpre
     # d_sr = d_out + LN2'(d_ln2)
     d_sr, d_sr_bf = _e(d_out, (M, C), F32), _e(d_out, (M, C), BF16)
     g["norm2.weight"], g["norm2.bias"] = _z(d_out, (C,)), _z(d_out, (C,))
+    cs_sr = _z(d_out, (C,))        # column sums of d_sr: bias gradient of attn.proj (or proj_i2t when fused)
     K.layernorm_bwd(d_ln2, s.sr, p["norm2.weight"], s.mean2, s.rstd2, add=d_out, dx=d_sr, dx_bf16=d_sr_bf,
-                    bf16_total=True, dgamma=g["norm2.weight"], dbeta=g["norm2.bias"])
+                    bf16_total=True, dgamma=g["norm2.weight"], dbeta=g["norm2.bias"], out_colsum=cs_sr)
     dy = None
     d_s_bf = d_sr_bf
+    cs_s = cs_sr
     if s.fused:
         S, Ct = s.y_bf.shape[0] // B, s.y_bf.shape[1]
         alpha = p["attn.alpha_i2t"]
@@ -193,7 +202,8 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True):
         # sr = x + a + alpha * c,  c = proj_i2t(o_c)
         g["attn.alpha_i2t"] = _e(d_out, (1,), F32)
         K.dot(d_sr, s.c, g["attn.alpha_i2t"])
-        g["attn.proj_i2t.weight"], g["attn.proj_i2t.bias"] = linear_bwd_params(K, d_sr_bf, s.o_c.view(M, C), scale_dev=alpha)
+        g["attn.proj_i2t.weight"], g["attn.proj_i2t.bias"] = linear_bwd_params(K, d_sr_bf, s.o_c.view(M, C), scale_dev=alpha,
+                                                                               db=cs_sr)
         d_oc = _e(d_out, (B, N, C), BF16)
         K.gemm(GEMM_NN, d_sr_bf, w["attn.proj_i2t.weight"], scale_dev=alpha, out_bf16=d_oc.view(M, C))
         kv3 = s.kv_t.view(B, S, 2 * C)
@@ -211,12 +221,14 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True):
         # d_a = d_sr + LNc'(d_lnc)
         d_a_bf = _e(d_out, (M, C), BF16)
         g["attn.norm_i2t_i.weight"], g["attn.norm_i2t_i.bias"] = _z(d_out, (C,)), _z(d_out, (C,))
+        cs_s = _z(d_out, (C,))
         K.layernorm_bwd(d_lnc, s.a, p["attn.norm_i2t_i.weight"], s.meanc, s.rstdc, add=d_sr, dx=None, dx_bf16=d_a_bf,
-                        bf16_total=True, dgamma=g["attn.norm_i2t_i.weight"], dbeta=g["attn.norm_i2t_i.bias"])
+                        bf16_total=True, dgamma=g["attn.norm_i2t_i.weight"], dbeta=g["attn.norm_i2t_i.bias"],
+                        out_colsum=cs_s)
         d_s_bf = d_a_bf
         K.mark("video_block_bwd")
     # ---- space attention: s = proj(attn_space(qkv(ln1)))
-    g["attn.proj.weight"], g["attn.proj.bias"] = linear_bwd_params(K, d_s_bf, s.o_s.view(M, C))
+    g["attn.proj.weight"], g["attn.proj.bias"] = linear_bwd_params(K, d_s_bf, s.o_s.view(M, C), db=cs_s)
     d_os = _e(d_out, (B, N, C), BF16)
     K.gemm(GEMM_NN, d_s_bf, w["attn.proj.weight"], out_bf16=d_os.view(M, C))
     d_qkv = divided_attention_bwd(K, s.qkv_s.view(B, N, 3 * C), s.o_s, s.lse_s, d_os, H, T, Nf, "space").view(M, 3 * C)
@@ -226,10 +238,11 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True):
     # d_tr = LN1'(d_ln1);  running d_x = d_sr + d_tr   (x feeds sr directly and tr directly)
     d_x, d_tr_bf = _e(d_out, (M, C), F32), _e(d_out, (M, C), BF16)
     g["norm1.weight"], g["norm1.bias"] = _z(d_out, (C,)), _z(d_out, (C,))
+    cs_tr = _z(d_out, (C,))
     K.layernorm_bwd(d_ln1, s.tr, p["norm1.weight"], s.mean1, s.rstd1, add=d_sr, dx=d_x, dx_bf16=d_tr_bf,
-                    bf16_total=False, dgamma=g["norm1.weight"], dbeta=g["norm1.bias"])
+                    bf16_total=False, dgamma=g["norm1.weight"], dbeta=g["norm1.bias"], out_colsum=cs_tr)
     # ---- time attention: t = proj(attn_time(qkv(ln3)))
-    g["timeattn.proj.weight"], g["timeattn.proj.bias"] = linear_bwd_params(K, d_tr_bf, s.o_t.view(M, C))
+    g["timeattn.proj.weight"], g["timeattn.proj.bias"] = linear_bwd_params(K, d_tr_bf, s.o_t.view(M, C), db=cs_tr)
     d_ot = _e(d_out, (B, N, C), BF16)
     K.gemm(GEMM_NN, d_tr_bf, w["timeattn.proj.weight"], out_bf16=d_ot.view(M, C))
     d_qkv = divided_attention_bwd(K, s.qkv_t.view(B, N, 3 * C), s.o_t, s.lse_t, d_ot, H, T, Nf, "time").view(M, 3 * C)

@@ -198,7 +198,7 @@ class Kernels:
                                                self._stream()))
 
     def layernorm_bwd(self, dy, x, gamma, mean, rstd, add=None, dx=None, dx_bf16=None, bf16_total=True, dgamma=None,
-                      dbeta=None):
+                      dbeta=None, out_colsum=None):
         Cdim = x.shape[-1]
         rows = x.numel() // Cdim
         assert dy.is_contiguous() and x.is_contiguous() and dy.numel() == x.numel()
@@ -208,7 +208,7 @@ class Kernels:
         self._check(self.lib.egv_layernorm_bwd(_p(dy), int(dy.dtype == torch.bfloat16), _p(x),
                                                int(x.dtype == torch.bfloat16), _p(gamma), _p(mean), _p(rstd),
                                                c_int64(rows), Cdim, _p(add), _p(dx), _p(dx_bf16), int(bool(bf16_total)),
-                                               _p(dgamma), _p(dbeta), self._stream()))
+                                               _p(dgamma), _p(dbeta), _p(out_colsum), self._stream()))
 
     # ------------------------------------------------------------------ attention
     @staticmethod

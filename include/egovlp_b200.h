@@ -86,10 +86,12 @@ int egv_layernorm_fwd(const void* x, int x_is_bf16, const float* gamma, const fl
                       egv_stream_t stream);
 /* val = LayerNorm'(dy);  dx (f32, may be NULL) = (add ? add : 0) + val, where add (f32, may be NULL) may alias dx;
  * dx_bf16 (may be NULL) = bf16(bf16_total ? dx : val);  dgamma/dbeta [C] (f32, may be NULL) are always accumulated
- * with atomics: zero them first for a plain result.  dy is f32 or bf16. */
+ * with atomics: zero them first for a plain result; out_colsum [C] (may be NULL) += column sums of the value written
+ * to dx_bf16 (the bias gradient of the Linear feeding this branch).  dy is f32 or bf16. */
 int egv_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_bf16, const float* gamma,
                       const float* mean, const float* rstd, int64_t rows, int C, const float* add, float* dx,
-                      void* dx_bf16, int bf16_total, float* dgamma, float* dbeta, egv_stream_t stream);
+                      void* dx_bf16, int bf16_total, float* dgamma, float* dbeta, float* out_colsum,
+                      egv_stream_t stream);
 
 /* Strided multi-head attention (head_dim 64) ------------------------------------------------------
  * One flash-style kernel family covers every attention on the path:

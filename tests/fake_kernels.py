@@ -123,7 +123,7 @@ class FakeKernels:
             rstd.copy_(rs.reshape(rstd.shape))
 
     def layernorm_bwd(self, dy, x, gamma, mean, rstd, add=None, dx=None, dx_bf16=None, bf16_total=True, dgamma=None,
-                      dbeta=None):
+                      dbeta=None, out_colsum=None):
         self._launches += 1
         Cd = x.shape[-1]
         xf, d = x.float().reshape(-1, Cd), dy.float().reshape(-1, Cd)
@@ -135,6 +135,8 @@ class FakeKernels:
             dx.copy_(tot.reshape(dx.shape))
         if dx_bf16 is not None:
             dx_bf16.copy_((tot if bf16_total else val).reshape(dx_bf16.shape))
+        if out_colsum is not None:
+            out_colsum.add_((tot if bf16_total else val).sum(0))
         if dgamma is not None:
             dgamma.add_((d * xh).sum(0))
         if dbeta is not None:

@@ -212,12 +212,15 @@ def test_layernorm(K, R, rows, C, xbf):
         dx = torch.ones(rows, C, device=DEV)
         dx16 = torch.empty(rows, C, dtype=torch.bfloat16, device=DEV)
         dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
-        impl.layernorm_bwd(dy, x, g, mean, rstd, add=dx, dx=dx, dx_bf16=dx16, bf16_total=True, dgamma=dg, dbeta=db)
+        cs1, cs2 = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+        impl.layernorm_bwd(dy, x, g, mean, rstd, add=dx, dx=dx, dx_bf16=dx16, bf16_total=True, dgamma=dg, dbeta=db,
+                           out_colsum=cs1)
         dx2 = torch.empty(rows, C, device=DEV)
         dx216 = torch.empty(rows, C, dtype=torch.bfloat16, device=DEV)
-        impl.layernorm_bwd(dy.to(torch.bfloat16), x, g, mean, rstd, add=dx, dx=dx2, dx_bf16=dx216, bf16_total=False)
-        res.append((y16, y32, mean, rstd, dx, dx16, dg, db, dx2, dx216))
-    names = "y16 y32 mean rstd dx dx16 dgamma dbeta dx_from_bf16 dx16_partial".split()
+        impl.layernorm_bwd(dy.to(torch.bfloat16), x, g, mean, rstd, add=dx, dx=dx2, dx_bf16=dx216, bf16_total=False,
+                           out_colsum=cs2)
+        res.append((y16, y32, mean, rstd, dx, dx16, dg, db, dx2, dx216, cs1, cs2))
+    names = "y16 y32 mean rstd dx dx16 dgamma dbeta dx_from_bf16 dx16_partial colsum_total colsum_partial".split()
     for n, a, r in zip(names, res[0], res[1]):
         check(a, r, 4e-3 if a.dtype == torch.bfloat16 else 3e-5, "layernorm " + n)
     ref = torch.nn.functional.layer_norm(x.float(), (C,), g, b, 1e-5)
@@ -237,6 +240,9 @@ def _attn_case(name, B=2, H=2):
                                 k_istride=1, has_cls_key=True, cls_row=0, scale=sc), False
     if name == "cls":
         return N, N, L.AttnSpec(H=H, G=1, Lq=1, Lk=N - 1, q_row0=0, k_row0=1, has_cls_key=True, cls_row=0, scale=sc), False
+    if name == "cls_h12":   # 12 heads, 785 tokens: the all-heads-per-warp single-query kernels
+        n = 1 + 4 * 196
+        return n, n, L.AttnSpec(H=H, G=1, Lq=1, Lk=n - 1, q_row0=0, k_row0=1, has_cls_key=True, cls_row=0, scale=sc), False
     if name == "i2t":      # many queries, 11 keys with a pad mask
         return 200, 11, L.AttnSpec(H=H, G=1, Lq=200, Lk=11, scale=sc), True
     if name == "t2i":      # few queries, many keys
@@ -256,9 +262,9 @@ def _attn_case(name, B=2, H=2):
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name", ["time", "space", "cls", "i2t", "t2i", "text", "space196", "time16"])
+@pytest.mark.parametrize("name", ["time", "space", "cls", "cls_h12", "i2t", "t2i", "text", "space196", "time16"])
 def test_attention_fwd_bwd(K, R, name):
-    B, H = (3, 3) if name == "time16" else (2, 2)
+    B, H = (3, 3) if name == "time16" else ((3, 12) if name == "cls_h12" else (2, 2))
     Nq, Nk, spec, masked = _attn_case(name, B, H)
     C = H * 64
     fused = Nq == Nk and spec.has_cls_key
@@ -296,10 +302,11 @@ def test_attention_fwd_bwd(K, R, name):
         check(a, r, tol, "attention %s %s" % (name, n))
 
 
-def test_attention_dkv_accumulate(K, R):
+@pytest.mark.parametrize("case", ["cls", "cls_h12"])
+def test_attention_dkv_accumulate(K, R, case):
     """The CLS-query pass adds its dk/dv onto what the grouped pass wrote (read-modify-write rows)."""
-    B, H = 2, 2
-    Nq, Nk, spec, _ = _attn_case("cls", B, H)
+    B, H = (2, 2) if case == "cls" else (2, 12)
+    Nq, Nk, spec, _ = _attn_case(case, B, H)
     C = H * 64
     qkv = rnd(B, Nq, 3 * C, seed=81)
     q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
