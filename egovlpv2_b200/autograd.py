@@ -22,6 +22,21 @@ def _pdict(names, params):
     return {n: t.detach() for n, t in zip(names, params)}
 
 
+def _sinks(names, params):
+    """name -> slice of the flat gradient arena for every parameter that lives in the arena (weights.ParamArena);
+    the backward kernels then accumulate in place and autograd gets None for those parameters."""
+    from .weights import cache
+    arena = cache().arena
+    if arena is None:
+        return {}
+    return {n: arena.grad_view(p) for n, p in zip(names, params) if id(p) in arena.offsets}
+
+
+def _ret(g, name, shape):
+    t = g.get(name)
+    return None if t is None else t.reshape(shape)
+
+
 def _f32c(t):
     t = t.detach()
     if t.dtype != torch.float32:
@@ -37,6 +52,7 @@ class VideoBlockFn(torch.autograd.Function):
         out, s = F_.video_block_fwd(_K(), _f32c(x), p, w, cfg.H, cfg.T, cfg.Nf, y=None if y is None else _f32c(y),
                                     y_bias=y_bias, eps=cfg.eps, save=True)
         ctx.cfg, ctx.w, ctx.s, ctx.p = cfg, w, s, p
+        ctx.sink = _sinks(cfg.names, params)
         return out
 
     @staticmethod
@@ -44,9 +60,9 @@ class VideoBlockFn(torch.autograd.Function):
     def backward(ctx, d_out):
         cfg = ctx.cfg
         dx, dy, g = F_.video_block_bwd(_K(), ctx.s, _f32c(d_out), ctx.p, ctx.w, cfg.H, cfg.T, cfg.Nf,
-                                       need_dx=ctx.needs_input_grad[2])
+                                       need_dx=ctx.needs_input_grad[2], sink=ctx.sink)
         ctx.s = None
-        grads = tuple(g[n].view(ctx.p[n].shape) for n in cfg.names)
+        grads = tuple(_ret(g, n, ctx.p[n].shape) for n in cfg.names)
         return (None, None, dx, dy, None) + grads
 
 
@@ -61,22 +77,45 @@ class TextLayerFn(torch.autograd.Function):
         out, s = F_.text_layer_fwd(_K(), _f32c(h), key_bias, p, w, cfg.H, video=None if video is None else _f32c(video),
                                    eps=cfg.eps, save=True)
         ctx.cfg, ctx.w, ctx.s, ctx.p = cfg, w, s, p
+        sink = _sinks(cfg.names, params)
+        # concatenated q/k/v (and cross k/v) gradients: only when the arena laid the parts out back to back
+        from .weights import cache
+        arena = cache().arena
+        byname = dict(zip(cfg.names, params))
+        cat = {"qkv": ("attention.self.", ("query", "key", "value")),
+               "cross.kv": ("crossattention_t2i.self.", ("key", "value"))}
+        for key, (pre, parts) in cat.items():
+            for sfx, k2 in ((".weight", key), (".bias", key + ".bias")):
+                names = [pre + q + sfx for q in parts]
+                v = None
+                if arena is not None and all(n in byname for n in names):
+                    v = arena.grad_cat_view([byname[n] for n in names])
+                if v is not None:
+                    sink[k2] = v
+                else:
+                    for n in names:
+                        sink.pop(n, None)   # parts must then come back through autograd
+        ctx.sink = sink
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_out):
         cfg = ctx.cfg
-        dh, dvid, g = F_.text_layer_bwd(_K(), ctx.s, _f32c(d_out), ctx.p, ctx.w, cfg.H, need_dh=ctx.needs_input_grad[3])
+        dh, dvid, g = F_.text_layer_bwd(_K(), ctx.s, _f32c(d_out), ctx.p, ctx.w, cfg.H, need_dh=ctx.needs_input_grad[3],
+                                        sink=ctx.sink)
         ctx.s = None
         sa = "attention.self."
-        g[sa + "query.weight"], g[sa + "key.weight"], g[sa + "value.weight"] = g["qkv"].chunk(3, 0)
-        g[sa + "query.bias"], g[sa + "key.bias"], g[sa + "value.bias"] = g["qkv.bias"].chunk(3, 0)
+        if "qkv" in g:
+            g[sa + "query.weight"], g[sa + "key.weight"], g[sa + "value.weight"] = g["qkv"].chunk(3, 0)
+        if "qkv.bias" in g:
+            g[sa + "query.bias"], g[sa + "key.bias"], g[sa + "value.bias"] = g["qkv.bias"].chunk(3, 0)
+        ca = "crossattention_t2i.self."
         if "cross.kv" in g:
-            ca = "crossattention_t2i.self."
             g[ca + "key.weight"], g[ca + "value.weight"] = g["cross.kv"].chunk(2, 0)
+        if "cross.kv.bias" in g:
             g[ca + "key.bias"], g[ca + "value.bias"] = g["cross.kv.bias"].chunk(2, 0)
-        grads = tuple(g[n].reshape(ctx.p[n].shape) for n in cfg.names)
+        grads = tuple(_ret(g, n, ctx.p[n].shape) for n in cfg.names)
         return (None, None, None, dh, None, dvid) + grads
 
 
@@ -88,16 +127,18 @@ class VideoTokensFn(torch.autograd.Function):
         p = {"patch_embed.proj.bias": pb.detach(), "pos_embed": pos.detach(), "temporal_embed": tem.detach()}
         tokens, s = F_.video_tokens_fwd(_K(), _f32c(video), p, w, cls.detach(), cfg.patch, save=True)
         ctx.s, ctx.shapes = s, (pw.shape, pos.shape, tem.shape, cls.shape)
+        ctx.sink = _sinks(["patch_embed.proj.weight", "patch_embed.proj.bias", "pos_embed", "temporal_embed", "cls_token"],
+                          [pw, pb, pos, tem, cls])
         return tokens
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_tokens):
-        g = F_.video_tokens_bwd(_K(), ctx.s, _f32c(d_tokens))
+        g = F_.video_tokens_bwd(_K(), ctx.s, _f32c(d_tokens), sink=ctx.sink)
         ctx.s = None
         sw, sp, st, sc = ctx.shapes
-        return (None, None, None, g["patch_embed.proj.weight"].view(sw), g["patch_embed.proj.bias"],
-                g["pos_embed"].view(sp), g["temporal_embed"].view(st), g["cls_token"].view(sc))
+        return (None, None, None, _ret(g, "patch_embed.proj.weight", sw), g.get("patch_embed.proj.bias"),
+                _ret(g, "pos_embed", sp), _ret(g, "temporal_embed", st), _ret(g, "cls_token", sc))
 
 
 class TextEmbedFn(torch.autograd.Function):
@@ -109,14 +150,15 @@ class TextEmbedFn(torch.autograd.Function):
         p = _pdict(TextEmbedFn.NAMES, params)
         out, s = F_.text_embeddings_fwd(_K(), ids, p, eps=cfg.eps, pad_id=cfg.pad_id, save=True)
         ctx.s, ctx.p = s, p
+        ctx.sink = _sinks(TextEmbedFn.NAMES, params)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_out):
-        g = F_.text_embeddings_bwd(_K(), ctx.s, _f32c(d_out), ctx.p)
+        g = F_.text_embeddings_bwd(_K(), ctx.s, _f32c(d_out), ctx.p, sink=ctx.sink)
         ctx.s = None
-        return (None, None) + tuple(g[n] for n in TextEmbedFn.NAMES)
+        return (None, None) + tuple(g.get(n) for n in TextEmbedFn.NAMES)
 
 
 class LayerNormRowsFn(torch.autograd.Function):
@@ -124,12 +166,13 @@ class LayerNormRowsFn(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, eps):
         y, s = F_.layernorm_rows_fwd(_K(), _f32c(x), gamma.detach(), beta.detach(), eps)
         ctx.s, ctx.gamma = s, gamma.detach()
+        ctx.sink = _sinks(["weight", "bias"], [gamma, beta])
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        dx, dg, db = F_.layernorm_rows_bwd(_K(), ctx.s, _f32c(dy), ctx.gamma)
+        dx, dg, db = F_.layernorm_rows_bwd(_K(), ctx.s, _f32c(dy), ctx.gamma, sink=ctx.sink)
         ctx.s = None
         return dx, dg, db, None
 
@@ -148,19 +191,30 @@ class MlpChainFn(torch.autograd.Function):
         out, s = F_.mlp_chain_fwd(_K(), x.detach() if x.dtype == torch.bfloat16 else _f32c(x), layers, save=True)
         ctx.cfg, ctx.layers, ctx.s = cfg, layers, s
         ctx.wshapes = [t.shape for t in params]
+        sk = _sinks(list(range(len(params))), params)
+        sinks, j = [], 0
+        for i in range(len(cfg.acts)):
+            sw = sk.get(j)
+            j += 1
+            sb = None
+            if cfg.has_bias[i]:
+                sb = sk.get(j)
+                j += 1
+            sinks.append((sw, sb))
+        ctx.sinks = sinks
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_out):
-        dx, grads = F_.mlp_chain_bwd(_K(), ctx.s, _f32c(d_out), ctx.layers, need_dx=ctx.needs_input_grad[2])
+        dx, grads = F_.mlp_chain_bwd(_K(), ctx.s, _f32c(d_out), ctx.layers, need_dx=ctx.needs_input_grad[2], sinks=ctx.sinks)
         ctx.s = None
         flat = []
         for i, (dW, db) in enumerate(grads):
             flat.append(dW)
             if ctx.cfg.has_bias[i]:
                 flat.append(db)
-        flat = [gr.view(shp) for gr, shp in zip(flat, ctx.wshapes)]
+        flat = [None if gr is None else gr.view(shp) for gr, shp in zip(flat, ctx.wshapes)]
         return (None, None, dx) + tuple(flat)
 
 
@@ -176,6 +230,7 @@ class MlmLossFn(torch.autograd.Function):
         p = _pdict(MlmLossFn.NAMES, params)
         logits, loss_sum, count, s = F_.mlm_head_fwd(_K(), _f32c(h), labels, p, w, save=True)
         ctx.s, ctx.p, ctx.w = s, p, w
+        ctx.sink = _sinks(MlmLossFn.NAMES, params)
         B, S, _ = h.shape
         logits3 = logits.view(B, S, logits.shape[-1]) if logits.is_contiguous() else logits.unflatten(0, (B, S))
         ctx.mark_non_differentiable(count, logits3)
@@ -184,9 +239,9 @@ class MlmLossFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, d_loss_sum, _dc, _dl):
-        dh, g = F_.mlm_head_bwd(_K(), ctx.s, _f32c(d_loss_sum).reshape(1), ctx.p, ctx.w)
+        dh, g = F_.mlm_head_bwd(_K(), ctx.s, _f32c(d_loss_sum).reshape(1), ctx.p, ctx.w, sink=ctx.sink)
         ctx.s = None
-        return (None, dh, None) + tuple(g[n].view(ctx.p[n].shape) for n in MlmLossFn.NAMES)
+        return (None, dh, None) + tuple(_ret(g, n, ctx.p[n].shape) for n in MlmLossFn.NAMES)
 
 
 class XentFn(torch.autograd.Function):

@@ -9,6 +9,8 @@
 //     DQ  : rows = queries, stream = keys      dQ (and delta = rowsum(dO*O))
 //     DKV : rows = keys,    stream = queries   dK, dV
 // Scores never touch HBM.  Small groups (time attention: T queries x T+1 keys) run one group per warp.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_common.h"
 
@@ -179,7 +181,7 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
   } else if (MODE == MODE_DQ) {
     load_tile<T_Q, ROWS, NT>(rowA, a, b, h, g, row0, n_rows, tid);
     load_tile<T_DO, ROWS, NT>(rowB, a, b, h, g, row0, n_rows, tid);
-    static_assert(KC >= 16 * NW || NW > 4, "the O tile is staged in the stream buffer");
+    static_assert(2 * KC >= 16 * NW, "the O tile is staged in the (contiguous) stream buffers");
     load_tile<T_O, ROWS, NT>(strA, a, b, h, g, row0, n_rows, tid);   // O rows, only for delta = rowsum(dO * O)
   } else {
     load_tile<T_K, ROWS, NT>(rowA, a, b, h, g, row0, n_rows, tid);
@@ -917,18 +919,52 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
     long long grid = std::min<long long>(a.items, (long long)sm_count() * 16);
     if (e == cudaSuccess) kern<<<(unsigned)grid, 64, smem, stream>>>(a);
   } else {
-    constexpr int KC = 64;
-    a.row_tiles = (int)cdiv(n_rows, 64);
-    a.items = groups * a.row_tiles;
-    auto kern = attn_cta_kernel<MODE, 4, KC>;
-    const int smem = AttnSmem<MODE, 4, KC>::BYTES;
-    static bool cfg = false;
-    if (!cfg) {
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      cfg = true;
+    // tile shapes: 4 warps x 64-row chunks, or 7 warps x 112-row chunks when that wastes fewer MMA slots
+    // (196-197 rows per space-attention group: 2 x 112 = 224 instead of 4 x 64 = 256); 32-row chunks for short streams.
+    auto util = [](int n, int t) { return (double)n / (double)(cdiv(n, t) * t); };
+    static const int wide_mode = getenv("EGV_ATTN_WIDE") ? atoi(getenv("EGV_ATTN_WIDE")) : 6;   // bit per MODE
+    const bool wide = ((wide_mode >> MODE) & 1) && n_str > 32 &&
+                      util(n_rows, 112) * util(n_str, 112) > 1.1 * util(n_rows, 64) * util(n_str, 64);
+    if (n_str <= 32) {
+      constexpr int KC = 32;
+      a.row_tiles = (int)cdiv(n_rows, 64);
+      a.items = groups * a.row_tiles;
+      auto kern = attn_cta_kernel<MODE, 4, KC>;
+      const int smem = AttnSmem<MODE, 4, KC>::BYTES;
+      static bool cfg = false;
+      if (!cfg) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cfg = true;
+      }
+      long long grid = std::min<long long>(a.items, (long long)sm_count() * 8);
+      if (e == cudaSuccess) kern<<<(unsigned)grid, 128, smem, stream>>>(a);
+    } else if (wide) {
+      constexpr int KC = 112;
+      a.row_tiles = (int)cdiv(n_rows, 112);
+      a.items = groups * a.row_tiles;
+      auto kern = attn_cta_kernel<MODE, 7, KC>;
+      const int smem = AttnSmem<MODE, 7, KC>::BYTES;
+      static bool cfg = false;
+      if (!cfg) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cfg = true;
+      }
+      long long grid = std::min<long long>(a.items, (long long)sm_count() * 4);
+      if (e == cudaSuccess) kern<<<(unsigned)grid, 224, smem, stream>>>(a);
+    } else {
+      constexpr int KC = 64;
+      a.row_tiles = (int)cdiv(n_rows, 64);
+      a.items = groups * a.row_tiles;
+      auto kern = attn_cta_kernel<MODE, 4, KC>;
+      const int smem = AttnSmem<MODE, 4, KC>::BYTES;
+      static bool cfg = false;
+      if (!cfg) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cfg = true;
+      }
+      long long grid = std::min<long long>(a.items, (long long)sm_count() * 8);
+      if (e == cudaSuccess) kern<<<(unsigned)grid, 128, smem, stream>>>(a);
     }
-    long long grid = std::min<long long>(a.items, (long long)sm_count() * 8);
-    if (e == cudaSuccess) kern<<<(unsigned)grid, 128, smem, stream>>>(a);
   }
   if (e != cudaSuccess) return fail(EGV_ERR_CUDA, "attention smem attribute: %s", cudaGetErrorString(e));
   return check_launch("attention kernel");

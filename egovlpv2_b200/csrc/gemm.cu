@@ -643,8 +643,8 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   // (weight gradients dW = dy^T x: 768..3072-wide outputs, K = B*N tokens).  The output is zeroed and the
   // slices are combined with fp32 atomics.
   bool auto_split = false;
-  if (split_k == 1 && !a->accumulate && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && a->act == EGV_ACT_NONE &&
-      !a->residual) {
+  if (split_k == 1 && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && a->act == EGV_ACT_NONE && !a->residual &&
+      !a->colsum) {
     const long long tiles256 = (long long)num_m_tiles * cdiv(a->N, BN);
     if (tiles256 * 2 <= sm_count() && p.k_blocks_total >= 16) {
       long long want = cdiv(sm_count(), tiles256);
@@ -661,14 +661,14 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   split_k = (int)cdiv(p.k_blocks_total, p.k_blocks_per_split);
   p.split_k = split_k;
   p.total_items = num_m_tiles * p.num_n_tiles * split_k;
-  if (auto_split) {
+  if (auto_split && !a->accumulate) {
     if (a->ld_out_f32 == a->N) {
       cudaMemsetAsync(a->out_f32, 0, (size_t)a->M * a->N * sizeof(float), stream);
     } else {
       cudaMemset2DAsync(a->out_f32, (size_t)a->ld_out_f32 * sizeof(float), 0, (size_t)a->N * sizeof(float), (size_t)a->M, stream);
     }
-    p.accumulate = 1;
   }
+  if (auto_split) p.accumulate = 1;
 
   CUtensorMap ta, tb;
   int rc;

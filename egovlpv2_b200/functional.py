@@ -30,23 +30,77 @@ def _z(like, shape, dtype=F32):
     return torch.zeros(shape, dtype=dtype, device=like.device)
 
 
-# ----------------------------------------------------------------------------------------------- linear
-def linear_bwd_params(K, dy_bf, x_bf, scale_dev=None, scale=1.0, bias=True, db=None):
-    """dW [N, Kd] = dy^T x, db [N] = colsum(dy)  (optionally scaled by a device scalar).  `db`: column sums already
-    produced by the kernel that wrote dy (GEMM / LayerNorm-backward epilogues) -- skips the colsum launch."""
-    N, Kd = dy_bf.shape[1], x_bf.shape[1]
-    dW = _e(dy_bf, (N, Kd), F32)
-    K.gemm(GEMM_TN, dy_bf, x_bf, out_f32=dW, scale=scale, scale_dev=scale_dev)
-    if db is not None:
-        if scale_dev is not None or scale != 1.0:
-            sdb = _e(dy_bf, (N,), F32)
-            K.axpy(None, db, scale, scale_dev, y=sdb)
-            db = sdb
-        return dW, db
-    if bias:
-        db = _e(dy_bf, (N,), F32)
-        K.colsum(dy_bf, db, scale=scale, scale_dev=scale_dev)
-    return dW, db
+# ----------------------------------------------------------------------------------------------- parameter gradients
+class Grads:
+    """Collects parameter gradients of one backward call.
+
+    Without a sink every gradient is a fresh tensor returned to autograd (`self.g[name]`).  With `sink`
+    (name -> fp32 tensor, normally views of the flat gradient arena, already holding the running sum of this step)
+    the kernels accumulate straight into it -- weight-gradient GEMMs with atomic split-K, bias / LayerNorm gradients
+    through the atomics they use anyway -- and nothing is returned for that parameter: no temporaries, no zero fills,
+    no `grad += g` launches."""
+
+    def __init__(self, K, like, sink=None):
+        self.K, self.like, self.sink, self.g = K, like, sink or {}, {}
+
+    def weight(self, name, dy_bf, x_bf, scale_dev=None, scale=1.0):
+        """dW [N, Kd] (+)= scale * dy^T x"""
+        N, Kd = dy_bf.shape[1], x_bf.shape[1]
+        if name in self.sink:
+            self.K.gemm(GEMM_TN, dy_bf, x_bf, out_f32=self.sink[name].view(N, Kd), scale=scale, scale_dev=scale_dev,
+                        accumulate=True)
+        else:
+            dW = _e(dy_bf, (N, Kd), F32)
+            self.K.gemm(GEMM_TN, dy_bf, x_bf, out_f32=dW, scale=scale, scale_dev=scale_dev)
+            self.g[name] = dW
+
+    def vec(self, name, n):
+        """fp32 [n] accumulator for kernels that add with atomics (LayerNorm dgamma/dbeta, fused column sums)."""
+        if name in self.sink:
+            return self.sink[name].view(n)
+        t = _z(self.like, (n,))
+        self.g[name] = t
+        return t
+
+    def bias(self, name, dy_bf, scale_dev=None, scale=1.0):
+        """db [N] (+)= scale * colsum(dy)"""
+        N = dy_bf.shape[1]
+        if name in self.sink:
+            self.K.colsum(dy_bf, self.sink[name].view(N), accumulate=True, scale=scale, scale_dev=scale_dev)
+        else:
+            db = _e(dy_bf, (N,), F32)
+            self.K.colsum(dy_bf, db, scale=scale, scale_dev=scale_dev)
+            self.g[name] = db
+
+    def bias_from(self, name, cs, scale_dev=None, scale=1.0):
+        """db (+)= scale * cs, cs = column sums produced by another kernel's epilogue"""
+        N = cs.numel()
+        if name in self.sink:
+            t = self.sink[name].view(N)
+            self.K.axpy(t, cs, scale, scale_dev, y=t)
+        elif scale_dev is None and scale == 1.0:
+            self.g[name] = cs
+        else:
+            db = _e(cs, (N,), F32)
+            self.K.axpy(None, cs, scale, scale_dev, y=db)
+            self.g[name] = db
+
+    def scalar_dot(self, name, a, b):
+        """g (+)= sum(a * b)   (the scalar fusion gates)"""
+        if name in self.sink:
+            self.K.dot(a, b, self.sink[name].view(1), accumulate=True)
+        else:
+            t = _e(self.like, (1,), F32)
+            self.K.dot(a, b, t)
+            self.g[name] = t
+
+    def full(self, name, shape):
+        """zero-initialised (or sink) tensor for kernels that scatter-add (embedding tables)."""
+        if name in self.sink:
+            return self.sink[name].view(shape)
+        t = _z(self.like, shape)
+        self.g[name] = t
+        return t
 
 
 # ----------------------------------------------------------------------------------------------- divided attention
@@ -168,42 +222,41 @@ def video_block_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=Tr
     return out.view(B, N, C), (s if save else None)
 
 
-def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True):
+def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True, sink=None):
     """Backward of video_block_fwd.  Returns (dx [B,N,C] f32 or None, dy [B,S,Ct] f32 or None, grads dict)."""
     B, N, C = s.shape
     M = B * N
-    g = {}
+    G = Grads(K, d_out, sink)
     K.mark("video_block_bwd")
     d_out = d_out.reshape(M, C)
     d_out_bf = _e(d_out, (M, C), BF16)
     K.cast(d_out.contiguous(), d_out_bf)
     # ---- MLP: out = sr + fc2(gelu(fc1(ln2)))
-    g["mlp.fc2.weight"], g["mlp.fc2.bias"] = linear_bwd_params(K, d_out_bf, s.h_act)
+    G.weight("mlp.fc2.weight", d_out_bf, s.h_act)
+    G.bias("mlp.fc2.bias", d_out_bf)
     d_hpre = _e(d_out, s.h_pre.shape, BF16)
-    db1 = _z(d_out, (s.h_pre.shape[1],))
-    K.gemm(GEMM_NN, d_out_bf, w["mlp.fc2.weight"], aux=s.h_pre, act=ACT_GELU_BWD, out_bf16=d_hpre, colsum=db1)
-    g["mlp.fc1.weight"], g["mlp.fc1.bias"] = linear_bwd_params(K, d_hpre, s.ln2, db=db1)
+    K.gemm(GEMM_NN, d_out_bf, w["mlp.fc2.weight"], aux=s.h_pre, act=ACT_GELU_BWD, out_bf16=d_hpre,
+           colsum=G.vec("mlp.fc1.bias", s.h_pre.shape[1]))
+    G.weight("mlp.fc1.weight", d_hpre, s.ln2)
     d_ln2 = _e(d_out, (M, C), BF16)
     K.gemm(GEMM_NN, d_hpre, w["mlp.fc1.weight"], out_bf16=d_ln2)
     del d_hpre
     # d_sr = d_out + LN2'(d_ln2)
     d_sr, d_sr_bf = _e(d_out, (M, C), F32), _e(d_out, (M, C), BF16)
-    g["norm2.weight"], g["norm2.bias"] = _z(d_out, (C,)), _z(d_out, (C,))
-    cs_sr = _z(d_out, (C,))        # column sums of d_sr: bias gradient of attn.proj (or proj_i2t when fused)
+    # column sums of d_sr = bias gradient of attn.proj (plain block) or, times alpha, of proj_i2t (fused block)
+    cs_sr = _z(d_out, (C,)) if s.fused else G.vec("attn.proj.bias", C)
     K.layernorm_bwd(d_ln2, s.sr, p["norm2.weight"], s.mean2, s.rstd2, add=d_out, dx=d_sr, dx_bf16=d_sr_bf,
-                    bf16_total=True, dgamma=g["norm2.weight"], dbeta=g["norm2.bias"], out_colsum=cs_sr)
+                    bf16_total=True, dgamma=G.vec("norm2.weight", C), dbeta=G.vec("norm2.bias", C), out_colsum=cs_sr)
     dy = None
     d_s_bf = d_sr_bf
-    cs_s = cs_sr
     if s.fused:
         S, Ct = s.y_bf.shape[0] // B, s.y_bf.shape[1]
         alpha = p["attn.alpha_i2t"]
         K.mark("xattn_i2t_bwd")
         # sr = x + a + alpha * c,  c = proj_i2t(o_c)
-        g["attn.alpha_i2t"] = _e(d_out, (1,), F32)
-        K.dot(d_sr, s.c, g["attn.alpha_i2t"])
-        g["attn.proj_i2t.weight"], g["attn.proj_i2t.bias"] = linear_bwd_params(K, d_sr_bf, s.o_c.view(M, C), scale_dev=alpha,
-                                                                               db=cs_sr)
+        G.scalar_dot("attn.alpha_i2t", d_sr, s.c)
+        G.weight("attn.proj_i2t.weight", d_sr_bf, s.o_c.view(M, C), scale_dev=alpha)
+        G.bias_from("attn.proj_i2t.bias", cs_sr, scale_dev=alpha)
         d_oc = _e(d_out, (B, N, C), BF16)
         K.gemm(GEMM_NN, d_sr_bf, w["attn.proj_i2t.weight"], scale_dev=alpha, out_bf16=d_oc.view(M, C))
         kv3 = s.kv_t.view(B, S, 2 * C)
@@ -212,47 +265,47 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True):
         K.attention_bwd(s.spec_c, s.q_c.view(B, N, C), kv3[:, :, :C], kv3[:, :, C:], s.o_c, s.lse_c, d_oc, dq_c,
                         dkv[:, :, :C], dkv[:, :, C:], _e(d_out, s.lse_c.shape, F32), key_bias=s.y_bias)
         dq2, dkv2 = dq_c.view(M, C), dkv.view(B * S, 2 * C)
-        g["attn.qkv_i2t.weight"], g["attn.qkv_i2t.bias"] = linear_bwd_params(K, dq2, s.lnc)
+        G.weight("attn.qkv_i2t.weight", dq2, s.lnc)
+        G.bias("attn.qkv_i2t.bias", dq2)
         d_lnc = _e(d_out, (M, C), BF16)
         K.gemm(GEMM_NN, dq2, w["attn.qkv_i2t.weight"], out_bf16=d_lnc)
-        g["attn.qkv_text_i2t.weight"], g["attn.qkv_text_i2t.bias"] = linear_bwd_params(K, dkv2, s.y_bf)
+        G.weight("attn.qkv_text_i2t.weight", dkv2, s.y_bf)
+        G.bias("attn.qkv_text_i2t.bias", dkv2)
         dy = _e(d_out, (B, S, Ct), F32)
         K.gemm(GEMM_NN, dkv2, w["attn.qkv_text_i2t.weight"], out_f32=dy.view(B * S, Ct))
         # d_a = d_sr + LNc'(d_lnc)
         d_a_bf = _e(d_out, (M, C), BF16)
-        g["attn.norm_i2t_i.weight"], g["attn.norm_i2t_i.bias"] = _z(d_out, (C,)), _z(d_out, (C,))
-        cs_s = _z(d_out, (C,))
         K.layernorm_bwd(d_lnc, s.a, p["attn.norm_i2t_i.weight"], s.meanc, s.rstdc, add=d_sr, dx=None, dx_bf16=d_a_bf,
-                        bf16_total=True, dgamma=g["attn.norm_i2t_i.weight"], dbeta=g["attn.norm_i2t_i.bias"],
-                        out_colsum=cs_s)
+                        bf16_total=True, dgamma=G.vec("attn.norm_i2t_i.weight", C), dbeta=G.vec("attn.norm_i2t_i.bias", C),
+                        out_colsum=G.vec("attn.proj.bias", C))
         d_s_bf = d_a_bf
         K.mark("video_block_bwd")
     # ---- space attention: s = proj(attn_space(qkv(ln1)))
-    g["attn.proj.weight"], g["attn.proj.bias"] = linear_bwd_params(K, d_s_bf, s.o_s.view(M, C), db=cs_s)
+    G.weight("attn.proj.weight", d_s_bf, s.o_s.view(M, C))
     d_os = _e(d_out, (B, N, C), BF16)
     K.gemm(GEMM_NN, d_s_bf, w["attn.proj.weight"], out_bf16=d_os.view(M, C))
     d_qkv = divided_attention_bwd(K, s.qkv_s.view(B, N, 3 * C), s.o_s, s.lse_s, d_os, H, T, Nf, "space").view(M, 3 * C)
-    g["attn.qkv.weight"], g["attn.qkv.bias"] = linear_bwd_params(K, d_qkv, s.ln1)
+    G.weight("attn.qkv.weight", d_qkv, s.ln1)
+    G.bias("attn.qkv.bias", d_qkv)
     d_ln1 = _e(d_out, (M, C), BF16)
     K.gemm(GEMM_NN, d_qkv, w["attn.qkv.weight"], out_bf16=d_ln1)
     # d_tr = LN1'(d_ln1);  running d_x = d_sr + d_tr   (x feeds sr directly and tr directly)
     d_x, d_tr_bf = _e(d_out, (M, C), F32), _e(d_out, (M, C), BF16)
-    g["norm1.weight"], g["norm1.bias"] = _z(d_out, (C,)), _z(d_out, (C,))
-    cs_tr = _z(d_out, (C,))
     K.layernorm_bwd(d_ln1, s.tr, p["norm1.weight"], s.mean1, s.rstd1, add=d_sr, dx=d_x, dx_bf16=d_tr_bf,
-                    bf16_total=False, dgamma=g["norm1.weight"], dbeta=g["norm1.bias"], out_colsum=cs_tr)
+                    bf16_total=False, dgamma=G.vec("norm1.weight", C), dbeta=G.vec("norm1.bias", C),
+                    out_colsum=G.vec("timeattn.proj.bias", C))
     # ---- time attention: t = proj(attn_time(qkv(ln3)))
-    g["timeattn.proj.weight"], g["timeattn.proj.bias"] = linear_bwd_params(K, d_tr_bf, s.o_t.view(M, C), db=cs_tr)
+    G.weight("timeattn.proj.weight", d_tr_bf, s.o_t.view(M, C))
     d_ot = _e(d_out, (B, N, C), BF16)
     K.gemm(GEMM_NN, d_tr_bf, w["timeattn.proj.weight"], out_bf16=d_ot.view(M, C))
     d_qkv = divided_attention_bwd(K, s.qkv_t.view(B, N, 3 * C), s.o_t, s.lse_t, d_ot, H, T, Nf, "time").view(M, 3 * C)
-    g["timeattn.qkv.weight"], g["timeattn.qkv.bias"] = linear_bwd_params(K, d_qkv, s.ln3)
+    G.weight("timeattn.qkv.weight", d_qkv, s.ln3)
+    G.bias("timeattn.qkv.bias", d_qkv)
     d_ln3 = _e(d_out, (M, C), BF16)
     K.gemm(GEMM_NN, d_qkv, w["timeattn.qkv.weight"], out_bf16=d_ln3)
-    g["norm3.weight"], g["norm3.bias"] = _z(d_out, (C,)), _z(d_out, (C,))
     K.layernorm_bwd(d_ln3, s.x, p["norm3.weight"], s.mean3, s.rstd3, add=d_x, dx=d_x if need_dx else None,
-                    dgamma=g["norm3.weight"], dbeta=g["norm3.bias"])
-    return (d_x.view(B, N, C) if need_dx else None), dy, g
+                    dgamma=G.vec("norm3.weight", C), dbeta=G.vec("norm3.bias", C))
+    return (d_x.view(B, N, C) if need_dx else None), dy, G.g
 
 
 # ----------------------------------------------------------------------------------------------- RobertaLayer
@@ -334,31 +387,31 @@ def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True):
     return out.view(B, S, C), (s if save else None)
 
 
-def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True):
+def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True, sink=None):
     """Backward of text_layer_fwd -> (dh [B,S,C] f32, dvideo [B,N,Cv] f32 or None, grads dict with the
     concatenated 'qkv' / 'cross.kv' gradients)."""
     B, S, C = s.shape
     M = B * S
-    g = {}
+    G = Grads(K, d_out, sink)
     K.mark("text_layer_bwd")
     d_out = d_out.reshape(M, C).contiguous()
     # out = LN_o(fa)
     d_fa, d_fa_bf = _e(d_out, (M, C), F32), _e(d_out, (M, C), BF16)
-    g["output.LayerNorm.weight"], g["output.LayerNorm.bias"] = _z(d_out, (C,)), _z(d_out, (C,))
     K.layernorm_bwd(d_out, s.fa, p["output.LayerNorm.weight"], s.mean_o, s.rstd_o, dx=d_fa, dx_bf16=d_fa_bf,
-                    dgamma=g["output.LayerNorm.weight"], dbeta=g["output.LayerNorm.bias"])
+                    dgamma=G.vec("output.LayerNorm.weight", C), dbeta=G.vec("output.LayerNorm.bias", C))
     # fa = a + dense2(gelu(dense1(a)))
-    g["output.dense.weight"], g["output.dense.bias"] = linear_bwd_params(K, d_fa_bf, s.f_act)
+    G.weight("output.dense.weight", d_fa_bf, s.f_act)
+    G.bias("output.dense.bias", d_fa_bf)
     d_fpre = _e(d_out, s.f_pre.shape, BF16)
     K.gemm(GEMM_NN, d_fa_bf, w["output.dense.weight"], aux=s.f_pre, act=ACT_GELU_BWD, out_bf16=d_fpre)
-    g["intermediate.dense.weight"], g["intermediate.dense.bias"] = linear_bwd_params(K, d_fpre, s.a_bf)
+    G.weight("intermediate.dense.weight", d_fpre, s.a_bf)
+    G.bias("intermediate.dense.bias", d_fpre)
     d_a = _e(d_out, (M, C), F32)
     K.gemm(GEMM_NN, d_fpre, w["intermediate.dense.weight"], residual=d_fa, out_f32=d_a)   # d_a = d_fa + dense1'(...)
     # a = LN_a(sh)
     d_sh, d_sh_bf = _e(d_out, (M, C), F32), _e(d_out, (M, C), BF16)
-    g["attention.output.LayerNorm.weight"], g["attention.output.LayerNorm.bias"] = _z(d_out, (C,)), _z(d_out, (C,))
     K.layernorm_bwd(d_a, s.sh, p["attention.output.LayerNorm.weight"], s.mean_a, s.rstd_a, dx=d_sh, dx_bf16=d_sh_bf,
-                    dgamma=g["attention.output.LayerNorm.weight"], dbeta=g["attention.output.LayerNorm.bias"])
+                    dgamma=G.vec("attention.output.LayerNorm.weight", C), dbeta=G.vec("attention.output.LayerNorm.bias", C))
     # sh = h + so + alpha * c
     dvideo = None
     d_so_bf = d_sh_bf
@@ -366,10 +419,9 @@ def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True):
         Bv, N, Cv = s.vshape
         alpha = p["alpha_t2i"]
         K.mark("xattn_t2i_bwd")
-        g["alpha_t2i"] = _e(d_out, (1,), F32)
-        K.dot(d_sh, s.c, g["alpha_t2i"])
-        g["crossattention_t2i.output.dense.weight"], g["crossattention_t2i.output.dense.bias"] = linear_bwd_params(
-            K, d_sh_bf, s.ox.view(M, C), scale_dev=alpha)
+        G.scalar_dot("alpha_t2i", d_sh, s.c)
+        G.weight("crossattention_t2i.output.dense.weight", d_sh_bf, s.ox.view(M, C), scale_dev=alpha)
+        G.bias("crossattention_t2i.output.dense.bias", d_sh_bf, scale_dev=alpha)
         d_ox = _e(d_out, (B, S, C), BF16)
         K.gemm(GEMM_NN, d_sh_bf, w["crossattention_t2i.output.dense.weight"], scale_dev=alpha, out_bf16=d_ox.view(M, C))
         kv3 = s.kv.view(Bv, N, 2 * C)
@@ -378,15 +430,18 @@ def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True):
         K.attention_bwd(s.spec_x, s.qx.view(B, S, C), kv3[:, :, :C], kv3[:, :, C:], s.ox, s.lse_x, d_ox, dqx, dkv[:, :, :C],
                         dkv[:, :, C:], _e(d_out, s.lse_x.shape, F32))
         dqx2, dkv2 = dqx.view(M, C), dkv.view(Bv * N, 2 * C)
-        g["crossattention_t2i.self.query.weight"], g["crossattention_t2i.self.query.bias"] = linear_bwd_params(K, dqx2, s.so_bf)
-        g["cross.kv"], g["cross.kv.bias"] = linear_bwd_params(K, dkv2, s.x_bf)
+        G.weight("crossattention_t2i.self.query.weight", dqx2, s.so_bf)
+        G.bias("crossattention_t2i.self.query.bias", dqx2)
+        G.weight("cross.kv", dkv2, s.x_bf)
+        G.bias("cross.kv.bias", dkv2)
         dvideo = _e(d_out, (Bv, N, Cv), F32)
         K.gemm(GEMM_NN, dkv2, w["cross.kv"], out_f32=dvideo.view(Bv * N, Cv))
         # d_so = d_sh + Wq_x'(dqx)
         d_so_bf = _e(d_out, (M, C), BF16)
         K.gemm(GEMM_NN, dqx2, w["crossattention_t2i.self.query.weight"], residual=d_sh, out_bf16=d_so_bf)
         K.mark("text_layer_bwd")
-    g["attention.output.dense.weight"], g["attention.output.dense.bias"] = linear_bwd_params(K, d_so_bf, s.o.view(M, C))
+    G.weight("attention.output.dense.weight", d_so_bf, s.o.view(M, C))
+    G.bias("attention.output.dense.bias", d_so_bf)
     d_o = _e(d_out, (B, S, C), BF16)
     K.gemm(GEMM_NN, d_so_bf, w["attention.output.dense.weight"], out_bf16=d_o.view(M, C))
     qkv3 = s.qkv.view(B, S, 3 * C)
@@ -394,13 +449,14 @@ def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True):
     K.attention_bwd(s.spec, qkv3[:, :, :C], qkv3[:, :, C:2 * C], qkv3[:, :, 2 * C:], s.o, s.lse, d_o, d_qkv[:, :, :C],
                     d_qkv[:, :, C:2 * C], d_qkv[:, :, 2 * C:], _e(d_out, s.lse.shape, F32), key_bias=s.key_bias)
     d_qkv2 = d_qkv.view(M, 3 * C)
-    g["qkv"], g["qkv.bias"] = linear_bwd_params(K, d_qkv2, s.h_bf)
+    G.weight("qkv", d_qkv2, s.h_bf)
+    G.bias("qkv.bias", d_qkv2)
     dh = None
     if need_dh:
         dh = _e(d_out, (M, C), F32)
         K.gemm(GEMM_NN, d_qkv2, w["qkv"], residual=d_sh, out_f32=dh)   # dh = d_sh (residual path) + qkv'(...)
         dh = dh.view(B, S, C)
-    return dh, dvideo, g
+    return dh, dvideo, G.g
 
 
 # ----------------------------------------------------------------------------------------------- embeddings
@@ -422,15 +478,17 @@ def video_tokens_fwd(K, video, p, w, cls_token, patch, save=True):
     return tokens, s
 
 
-def video_tokens_bwd(K, s, d_tokens):
+def video_tokens_bwd(K, s, d_tokens, sink=None):
     """-> grads dict: patch_embed.proj.{weight [C, 3*p*p] flattened, bias}, pos_embed, temporal_embed, cls_token."""
     B, T, Nf, C = s.B, s.T, s.Nf, s.C
     K.mark("embed_bwd")
+    G = Grads(K, d_tokens, sink)
     d_patch = _e(d_tokens, (B * T * Nf, C), BF16)
-    g = {"cls_token": _z(d_tokens, (C,)), "pos_embed": _z(d_tokens, (1 + Nf, C)), "temporal_embed": _z(d_tokens, (s.t_max, C))}
-    K.assemble_tokens_bwd(d_tokens.contiguous(), B, T, Nf, d_patch, g["cls_token"], g["pos_embed"], g["temporal_embed"])
-    g["patch_embed.proj.weight"], g["patch_embed.proj.bias"] = linear_bwd_params(K, d_patch, s.cols)
-    return g
+    K.assemble_tokens_bwd(d_tokens.contiguous(), B, T, Nf, d_patch, G.full("cls_token", (C,)), G.full("pos_embed", (1 + Nf, C)),
+                          G.full("temporal_embed", (s.t_max, C)))
+    G.weight("patch_embed.proj.weight", d_patch, s.cols)
+    G.bias("patch_embed.proj.bias", d_patch)
+    return G.g
 
 
 def text_embeddings_fwd(K, ids, p, eps=1e-5, pad_id=1, save=True):
@@ -449,19 +507,18 @@ def text_embeddings_fwd(K, ids, p, eps=1e-5, pad_id=1, save=True):
     return out, s
 
 
-def text_embeddings_bwd(K, s, d_out, p):
+def text_embeddings_bwd(K, s, d_out, p, sink=None):
     C = s.pre.shape[-1]
     K.mark("embed_bwd")
-    g = {"LayerNorm.weight": _z(d_out, (C,)), "LayerNorm.bias": _z(d_out, (C,))}
+    G = Grads(K, d_out, sink)
     d_pre = _e(d_out, s.pre.shape, F32)
-    K.layernorm_bwd(d_out.contiguous(), s.pre, p["LayerNorm.weight"], s.mean, s.rstd, dx=d_pre, dgamma=g["LayerNorm.weight"],
-                    dbeta=g["LayerNorm.bias"])
-    g["word_embeddings.weight"] = _z(d_out, p["word_embeddings.weight"].shape)
-    g["position_embeddings.weight"] = _z(d_out, p["position_embeddings.weight"].shape)
-    g["token_type_embeddings.weight"] = _z(d_out, p["token_type_embeddings.weight"].shape)
-    K.text_embed_bwd(d_pre, s.ids, g["word_embeddings.weight"], g["position_embeddings.weight"],
-                     g["token_type_embeddings.weight"].view(-1)[:C], s.pad_id)
-    return g
+    K.layernorm_bwd(d_out.contiguous(), s.pre, p["LayerNorm.weight"], s.mean, s.rstd, dx=d_pre,
+                    dgamma=G.vec("LayerNorm.weight", C), dbeta=G.vec("LayerNorm.bias", C))
+    K.text_embed_bwd(d_pre, s.ids, G.full("word_embeddings.weight", tuple(p["word_embeddings.weight"].shape)),
+                     G.full("position_embeddings.weight", tuple(p["position_embeddings.weight"].shape)),
+                     G.full("token_type_embeddings.weight", tuple(p["token_type_embeddings.weight"].shape)).view(-1)[:C],
+                     s.pad_id)
+    return G.g
 
 
 # ----------------------------------------------------------------------------------------------- small heads
@@ -474,11 +531,13 @@ def layernorm_rows_fwd(K, x, gamma, beta, eps, save=True):
     return y, (types.SimpleNamespace(x=x, mean=mean, rstd=rstd) if save else None)
 
 
-def layernorm_rows_bwd(K, s, dy, gamma):
+def layernorm_rows_bwd(K, s, dy, gamma, sink=None):
+    """sink: {'weight': t, 'bias': t} to accumulate into; returns (dx, dgamma or None, dbeta or None)."""
     C = s.x.shape[1]
-    dx, dg, db = _e(dy, s.x.shape, F32), _z(dy, (C,)), _z(dy, (C,))
-    K.layernorm_bwd(dy.contiguous(), s.x, gamma, s.mean, s.rstd, dx=dx, dgamma=dg, dbeta=db)
-    return dx, dg, db
+    G = Grads(K, dy, sink)
+    dx = _e(dy, s.x.shape, F32)
+    K.layernorm_bwd(dy.contiguous(), s.x, gamma, s.mean, s.rstd, dx=dx, dgamma=G.vec("weight", C), dbeta=G.vec("bias", C))
+    return dx, G.g.get("weight"), G.g.get("bias")
 
 
 def mlp_chain_fwd(K, x, layers, save=True):
@@ -510,8 +569,9 @@ def mlp_chain_fwd(K, x, layers, save=True):
 _ACT_BWD = {ACT_NONE: ACT_NONE, ACT_GELU: ACT_GELU_BWD, ACT_RELU: ACT_RELU_BWD, ACT_TANH: ACT_TANH_BWD}
 
 
-def mlp_chain_bwd(K, saved, d_out, layers, scale_dev=None, need_dx=True):
-    """-> (dx f32 [M, Kd] or None, [(dW, db)] per layer).  `scale_dev` scales d_out (device scalar).
+def mlp_chain_bwd(K, saved, d_out, layers, scale_dev=None, need_dx=True, sinks=None):
+    """-> (dx f32 [M, Kd] or None, [(dW, db)] per layer; None where the gradient went to `sinks[i]` = (dW sink, db sink)).
+    `scale_dev` scales d_out (device scalar).
     The gradient of every activation is folded into the epilogue of the GEMM that produces it; only a
     trailing activation of the LAST layer needs the stand-alone act_grad kernel."""
     grads = [None] * len(layers)
@@ -525,7 +585,12 @@ def mlp_chain_bwd(K, saved, d_out, layers, scale_dev=None, need_dx=True):
     for i in range(last, -1, -1):
         wt, b, _ = layers[i]
         x_in = saved[i][0]
-        grads[i] = linear_bwd_params(K, d_cur, x_in, bias=b is not None)
+        sw, sb = sinks[i] if sinks is not None else (None, None)
+        G = Grads(K, d_out, {k: v for k, v in (("w", sw), ("b", sb)) if v is not None})
+        G.weight("w", d_cur, x_in)
+        if b is not None:
+            G.bias("b", d_cur)
+        grads[i] = (G.g.get("w"), G.g.get("b"))
         if i > 0:
             pact = layers[i - 1][2]
             paux = None if pact == ACT_NONE else (saved[i - 1][2] if pact == ACT_GELU else saved[i - 1][1])
@@ -570,22 +635,29 @@ def mlm_head_fwd(K, h, labels, p, w, save=True):
     return logits, loss_sum, count, s
 
 
-def mlm_head_bwd(K, s, scale_dev, p, w):
+def mlm_head_bwd(K, s, scale_dev, p, w, sink=None):
     """scale_dev: device scalar = d(loss)/d(loss_sum) (grad_out / global count).  -> (dh [B,S,C] f32, grads dict)."""
     B, S, C = s.shape
     M = B * S
-    g = {}
+    sink = sink or {}
+    G = Grads(K, s.t, sink)
     K.mark("mlm_head_bwd")
-    g["mlm_score.decoder.weight"], g["mlm_score.bias"] = linear_bwd_params(K, s.dlogits, s.tn, scale_dev=scale_dev)
+    G.weight("mlm_score.decoder.weight", s.dlogits, s.tn, scale_dev=scale_dev)
+    G.bias("mlm_score.bias", s.dlogits, scale_dev=scale_dev)
     d_tn = _e(s.t, (M, C), BF16)
     K.gemm(GEMM_NN, s.dlogits, w["mlm_score.decoder.weight"], scale_dev=scale_dev, out_bf16=d_tn)
     d_t = _e(s.t, (M, C), F32)
-    g["mlm_score.transform.LayerNorm.weight"], g["mlm_score.transform.LayerNorm.bias"] = _z(s.t, (C,)), _z(s.t, (C,))
     K.layernorm_bwd(d_tn, s.t, p["mlm_score.transform.LayerNorm.weight"], s.mean, s.rstd, dx=d_t,
-                    dgamma=g["mlm_score.transform.LayerNorm.weight"], dbeta=g["mlm_score.transform.LayerNorm.bias"])
-    dh, grads = mlp_chain_bwd(K, s.chain, d_t, s.layers)
-    g["cross_modal_text_transform.weight"], g["cross_modal_text_transform.bias"] = grads[0]
-    g["mlm_score.transform.dense.weight"], g["mlm_score.transform.dense.bias"] = grads[1]
+                    dgamma=G.vec("mlm_score.transform.LayerNorm.weight", C), dbeta=G.vec("mlm_score.transform.LayerNorm.bias", C))
+    names = [("cross_modal_text_transform.weight", "cross_modal_text_transform.bias"),
+             ("mlm_score.transform.dense.weight", "mlm_score.transform.dense.bias")]
+    dh, grads = mlp_chain_bwd(K, s.chain, d_t, s.layers, sinks=[(sink.get(a), sink.get(b)) for a, b in names])
+    g = G.g
+    for (a, b), (dW, db) in zip(names, grads):
+        if dW is not None:
+            g[a] = dW
+        if db is not None:
+            g[b] = db
     return dh.view(B, S, C), g
 
 

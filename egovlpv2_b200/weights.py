@@ -151,7 +151,11 @@ class ParamArena:
         for p in self.params:
             p.grad = self.grad_view(p)
 
-    def cat_view(self, params, bf16):
+    def grad_cat_view(self, params):
+        """gradient-buffer view of torch.cat(params, 0) when the arena laid them out adjacently, else None"""
+        return self.cat_view(params, bf16=False, buf=self.grad)
+
+    def cat_view(self, params, bf16, buf=None):
         ents = [self.offsets.get(id(p)) for p in params]
         if any(e is None for e in ents):
             return None
@@ -160,6 +164,7 @@ class ParamArena:
             if o != off:
                 return None
             off += n
-        buf = self.shadow if bf16 else self.master
+        if buf is None:
+            buf = self.shadow if bf16 else self.master
         rows = sum(e[2][0] for e in ents)
         return buf[ents[0][0]:off].view((rows,) + ents[0][2][1:])

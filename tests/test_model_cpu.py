@@ -163,3 +163,48 @@ def test_temporal_embed_inflation(golden_dir, fake_kernels):
     # bilinear with align_corners keeps the end points (model.py:556-559)
     assert torch.allclose(new["video_model.temporal_embed"][0, 0], sd["video_model.temporal_embed"][0, 0], atol=1e-6)
     assert torch.allclose(new["video_model.temporal_embed"][0, -1], sd["video_model.temporal_embed"][0, -1], atol=1e-6)
+
+
+def test_gradient_arena_matches_autograd_path(golden_dir, fake_kernels):
+    """With the flat ParamArena active the backward kernels accumulate parameter gradients in place (no tensors
+    returned to autograd); the result must equal the plain autograd path, also when accumulating over two passes."""
+    from egovlpv2_b200.optim import FusedAdamW
+    old = Fn.BF16
+    Fn.BF16 = torch.float32
+    try:
+        fx, c, shapes, sd, data, plan = _golden(golden_dir)
+        ref_model = build_tiny(c)
+        ref_model.load_state_dict(sd, strict=False)
+        ref_model.eval()
+        loss, _, _ = _step(ref_model, data, plan)
+        loss.backward()
+        want = {n: p.grad.clone() for n, p in ref_model.named_parameters()}
+
+        model = build_tiny(c)
+        model.load_state_dict(sd, strict=False)
+        model.eval()
+        opt = FusedAdamW(model, 1e-3, 0.01, 1.0, 4.0)
+        assert weights.cache().arena is opt.arena
+        # parameters are now views of the flat master buffer, q/k/v weights adjacent
+        l0 = model.text_model.encoder.layer[0].attention.self
+        assert opt.arena.cat_view([l0.query.weight, l0.key.weight, l0.value.weight], bf16=False) is not None
+        opt.zero_grad()
+        for _ in range(2):
+            loss2, _, _ = _step(model, data, plan)
+            loss2.backward()
+        assert abs(loss2.item() - loss.item()) < 1e-5
+        for n, p in model.named_parameters():
+            got = opt.arena.grad_view(p)
+            assert p.grad is not None and p.grad.data_ptr() == got.data_ptr(), n
+            err = (got - 2 * want[n]).abs().max().item()
+            assert err <= 2e-4 * max(1e-3, (2 * want[n]).abs().max().item()) + 1e-7, (n, err)
+        before = {n: p.detach().clone() for n, p in model.named_parameters()}
+        opt.step()
+        changed = sum(int(not torch.equal(before[n], p.detach())) for n, p in model.named_parameters())
+        assert changed >= len(before) - 2          # position_ids-free; every trained tensor moved
+        sh = weights.cache().bf16(model.vid_proj[0].weight)
+        assert torch.equal(sh.float(), model.vid_proj[0].weight.detach())   # exact mode: shadow dtype is fp32
+    finally:
+        Fn.BF16 = old
+        weights.cache().arena = None
+        weights.cache().clear()
