@@ -268,8 +268,13 @@ __global__ void __launch_bounds__(128) text_embed_bwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, bf16* __restrict__ p_bf16, long long n, float lr,
                                                     float beta1, float beta2, float eps, float wd, float bias_c1, float bias_c2,
-                                                    float grad_scale) {
+                                                    float grad_scale, const float* __restrict__ hyper) {
   const long long stride = (long long)gridDim.x * blockDim.x;
+  if (hyper) {  // step-dependent scalars live on the device so that a captured CUDA graph stays valid across steps
+    lr *= hyper[0];
+    bias_c1 = hyper[1];
+    bias_c2 = hyper[2];
+  }
   const float step = lr * sqrtf(bias_c2) / bias_c1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float gi = g[i] * grad_scale;
@@ -417,10 +422,10 @@ extern "C" int egv_text_embed_bwd(const float* d_out, const int64_t* ids, int B,
 
 extern "C" int egv_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
                          float beta2, float eps, float weight_decay, float bias_c1, float bias_c2, float grad_scale,
-                         egv_stream_t stream) {
+                         const float* hyper_dev, egv_stream_t stream) {
   if (n <= 0) return EGV_OK;
   if (!p || !g || !m || !v) return fail(EGV_ERR_ARG, "adamw: null pointer");
   adamw_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)p_bf16, n, lr, beta1, beta2, eps,
-                                                                      weight_decay, bias_c1, bias_c2, grad_scale);
+                                                                      weight_decay, bias_c1, bias_c2, grad_scale, hyper_dev);
   return check_launch("adamw_kernel");
 }

@@ -369,13 +369,13 @@ class Kernels:
                                         _p(dv), _p(scratch), self._stream()))
 
     # ------------------------------------------------------------------ optimiser
-    def adamw(self, p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    def adamw(self, p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, hyper_dev=None):
         for x in (p, g, m, v):
             assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() == p.numel()
         self._check(self.lib.egv_adamw(_p(p), _p(g), _p(m), _p(v), _p(p_bf16), c_int64(p.numel()), c_float(lr),
                                        c_float(beta1), c_float(beta2), c_float(eps), c_float(weight_decay),
                                        c_float(1.0 - beta1 ** step), c_float(1.0 - beta2 ** step), c_float(grad_scale),
-                                       self._stream()))
+                                       _p(hyper_dev), self._stream()))
 
     # ------------------------------------------------------------------ NVSwitch P2P all-gather
     def p2p_alloc(self, nbytes):

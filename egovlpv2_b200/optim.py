@@ -63,6 +63,11 @@ class FusedAdamW:
         self.v = torch.zeros_like(self.arena.master)
         self.betas, self.eps = betas, eps
         self.step_count = 0
+        # {lr multiplier, 1-beta1^t, 1-beta2^t} on the device: lets a captured CUDA graph serve every step
+        self.hyper_dev = torch.ones(3, dtype=torch.float32, device=self.arena.master.device)
+        self.hyper_host = torch.ones(3, dtype=torch.float32)
+        if self.arena.master.is_cuda:
+            self.hyper_host = self.hyper_host.pin_memory()
         self.max_steps, self.warmup_steps = max_steps, warmup_steps
         self.arena.bind_grads()
 
@@ -80,11 +85,24 @@ class FusedAdamW:
         _lib.kernels().zero(self.arena.grad)
         self.arena.bind_grads()
 
-    def step(self, grad_scale=1.0):
-        K = _lib.kernels()
+    def advance(self):
+        """Host part of a step: bump the counter and upload the step-dependent scalars (async H2D, outside any graph)."""
         scale = self.lr_scale()
         self.step_count += 1
+        self.hyper_host[0] = scale
+        self.hyper_host[1] = 1.0 - self.betas[0] ** self.step_count
+        self.hyper_host[2] = 1.0 - self.betas[1] ** self.step_count
+        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
+
+    def launch(self, grad_scale=1.0):
+        """Device part of a step (capturable): one fused AdamW launch per hyper-parameter group."""
+        K = _lib.kernels()
         a = self.arena
         for g, (name, lo, hi) in zip(self.groups, a.ranges):
-            K.adamw(a.master[lo:hi], a.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], a.shadow[lo:hi], g["lr"] * scale,
-                    self.betas[0], self.betas[1], self.eps, g["weight_decay"], self.step_count, grad_scale=grad_scale)
+            K.adamw(a.master[lo:hi], a.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], a.shadow[lo:hi], g["lr"],
+                    self.betas[0], self.betas[1], self.eps, g["weight_decay"], 1, grad_scale=grad_scale,
+                    hyper_dev=self.hyper_dev)
+
+    def step(self, grad_scale=1.0):
+        self.advance()
+        self.launch(grad_scale)

@@ -76,8 +76,44 @@ class PretrainStep:
         """H2D of one step's inputs from pinned host memory (non-blocking on the current stream)."""
         return {k: v.to(self.device, non_blocking=True) for k, v in host_batch.items()}
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def capture(self, example_batch, warmup=3):
+        """Capture forward + backward + all-reduce + AdamW of one step into a CUDA graph with static input buffers.
+        Afterwards `step_graph(batch)` copies the batch into the static buffers and replays the graph: one host call
+        instead of ~3000 kernel launches and the Python autograd bookkeeping."""
+        if getattr(self, "gather_kind", "none") == "p2p":
+            raise RuntimeError("the P2P gather passes its sequence number by value; capture with gather='nccl'")
+        self.static = {k: v.clone() for k, v in example_batch.items()}
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.opt.advance()
+                self._device_step(self.static)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.kernels().launch_count()
+        with torch.cuda.graph(self.graph):
+            self.static_loss, self.static_loss_dict = self._device_step(self.static)
+        self.launches_per_step = _lib.kernels().launch_count() - n0   # kernels of this library inside one replay
+        return self.graph
+
+    def step_graph(self, batch):
+        """`batch`: device or pinned-host tensors (copied into the static input buffers), then one graph replay."""
+        for k, v in batch.items():
+            if v is not self.static[k]:
+                self.static[k].copy_(v, non_blocking=True)
+        self.opt.advance()
+        self.graph.replay()
+        return self.static_loss, self.static_loss_dict
+
     def step(self, dev_batch):
-        """forward + backward + (all-reduce) + AdamW; returns the detached total loss (device scalar)."""
+        """forward + backward + (all-reduce) + AdamW, eager launches; returns the detached total loss (device scalar)."""
+        self.opt.advance()
+        return self._device_step(dev_batch)
+
+    def _device_step(self, dev_batch):
         d = dev_batch
         data = {"video": d["video"], "text": {"input_ids": d["input_ids"], "attention_mask": d["attention_mask"]},
                 "text_mlm_ids": d["text_mlm_ids"], "text_mlm_labels": d["text_mlm_labels"]}
@@ -87,9 +123,9 @@ class PretrainStep:
         loss.backward()
         if self.world > 1:
             dist.all_reduce(self.opt.arena.grad)          # DDP semantics: average over ranks (base_trainer.py:269)
-            self.opt.step(grad_scale=1.0 / self.world)
+            self.opt.launch(grad_scale=1.0 / self.world)
         else:
-            self.opt.step()
+            self.opt.launch()
         return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}
 
 

@@ -195,10 +195,13 @@ int egv_p2p_free(void* ptr);
 int egv_p2p_allgather(const void* src, int64_t bytes, int64_t slot_bytes, void* const* slots, void* const* flags, int rank,
                       int world, uint32_t seq, egv_stream_t stream);
 
-/* Optimiser (next row f-1): fused AdamW on one flat fp32 tensor; also refreshes the bf16 weight copy */
+/* Optimiser (next row f-1): fused AdamW (transformers.AdamW semantics, set_optim_schedule.py:108) on one flat fp32
+ * tensor; also refreshes the bf16 weight copy.  hyper_dev (optional, device float[3]) = {lr multiplier, 1-beta1^t,
+ * 1-beta2^t}: when given it overrides bias_c1 / bias_c2 and scales lr, so a captured CUDA graph can be replayed
+ * across optimiser steps. */
 int egv_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
               float beta2, float eps, float weight_decay, float bias_c1, float bias_c2, float grad_scale,
-              egv_stream_t stream);
+              const float* hyper_dev, egv_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -340,12 +340,17 @@ class FakeKernels:
             dv.copy_(vv.grad[grad_row0:grad_row0 + grad_rows])
 
     # ------------------------------------------------------------------ optimiser
-    def adamw(self, p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    def adamw(self, p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, hyper_dev=None):
         self._launches += 1
+        if hyper_dev is not None:
+            lr = lr * float(hyper_dev[0])
+            c1, c2 = float(hyper_dev[1]), float(hyper_dev[2])
+        else:
+            c1, c2 = 1 - beta1 ** step, 1 - beta2 ** step
         gi = g * grad_scale
         m.mul_(beta1).add_(gi, alpha=1 - beta1)
         v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
-        step_size = lr * math.sqrt(1 - beta2 ** step) / (1 - beta1 ** step)
+        step_size = lr * math.sqrt(c2) / c1
         p.addcdiv_(m, v.sqrt().add_(eps), value=-step_size)
         p.add_(p, alpha=-lr * weight_decay)
         if p_bf16 is not None:
