@@ -11,6 +11,8 @@
 // Scores never touch HBM.  Small groups (time attention: T queries x T+1 keys) run one group per warp.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_common.h"
 
@@ -20,6 +22,13 @@ enum { MODE_FWD = 0, MODE_DQ = 1, MODE_DKV = 2 };
 constexpr int HD = 64;       // head dim
 constexpr int LDS = 72;      // smem row stride in bf16 (144 B: conflict-free ldmatrix)
 constexpr float LOG2E = 1.4426950408889634f;
+
+// 2^x on the XU pipe in one instruction (inputs here are <= 0 or differences of bounded log-sum-exps)
+EGV_DEVINL float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct AttnP {
   int B, H, G, Lq, LkT;  // LkT = keys per group including the optional CLS key
@@ -74,6 +83,33 @@ EGV_DEVINL void load_tile(bf16* s, const AttnP& a, int b, int h, int g, int idx0
     const bool ok = idx < count;
     const bf16* src = ok ? row_ptr<WHAT>(a, b, h, g, idx) + ch * 8 : a.q;
     cp_async_16(s + r * LDS + ch * 8, src, ok);
+  }
+}
+
+// Row addressing of one logical tensor inside a work item, linear in the row index:
+// element offset(idx) = off + idx * step, except the shared CLS key at idx == 0 (has_cls) which lives at `cls`.
+struct RowAddr {
+  const bf16* base;
+  long long off, step, cls;
+  bool has_cls;
+  EGV_DEVINL const bf16* at(int idx) const { return base + ((has_cls && idx == 0) ? cls : off + (long long)idx * step); }
+};
+
+// cp.async rows idx0 .. idx0+rows_cap-1 (zero-filled past `count`) into a [rows_cap x 64] tile; thread t moves the
+// 16-byte chunk t & 7 of rows (t >> 3) + k * NT/8: one pointer increment per copy instead of re-deriving the address.
+template <int NT>
+EGV_DEVINL void load_rows(bf16* dst, const RowAddr& ra, int idx0, int count, int rows_cap, int tid) {
+  constexpr int RSTEP = NT / 8;
+  int r = tid >> 3;
+  const int ch = tid & 7;
+  const bf16* p = ra.base + ra.off + (long long)(idx0 + r) * ra.step + ch * 8;
+  bf16* d = dst + r * LDS + ch * 8;
+  const long long pstep = (long long)RSTEP * ra.step;
+  for (; r < rows_cap; r += RSTEP, p += pstep, d += RSTEP * LDS) {
+    const int idx = idx0 + r;
+    const bool ok = idx < count;
+    const bf16* sp = (ra.has_cls && idx == 0) ? ra.base + ra.cls + ch * 8 : p;
+    cp_async_16(d, ok ? sp : ra.base, ok);
   }
 }
 
@@ -139,24 +175,28 @@ EGV_DEVINL void c_to_smem(bf16* s, const float (&c)[8][4], float mul0, float mul
   }
 }
 
-template <int MODE, int NW, int KC>
+// NCH = chunks of the stream side resident in shared memory.  NCH == 1: chunks are (re)loaded inside the loop;
+// NCH > 1: the whole stream side of the group (<= NCH*KC rows) is loaded once, the loop has no loads and no barriers.
+template <int MODE, int NW, int KC, int NCH = 1>
 struct AttnSmem {
   static constexpr int ROWS = 16 * NW;
   static constexpr int ROW_TILES = (MODE == MODE_FWD) ? 1 : 2;
-  static constexpr int BYTES = (ROW_TILES * ROWS + 2 * KC) * LDS * 2 + 2 * KC * 4;
+  static constexpr int SROWS = KC * NCH;
+  static constexpr int BYTES = (ROW_TILES * ROWS + 2 * SROWS) * LDS * 2 + 2 * SROWS * 4;
 };
 
-template <int MODE, int NW, int KC>
+template <int MODE, int NW, int KC, int NCH = 1>
 EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, int tid) {
   constexpr int NT = NW * 32;
   constexpr int ROWS = 16 * NW;
-  using SM = AttnSmem<MODE, NW, KC>;
+  using SM = AttnSmem<MODE, NW, KC, NCH>;
+  constexpr int SROWS = SM::SROWS;
   bf16* rowA = reinterpret_cast<bf16*>(smem_unit);
   bf16* rowB = rowA + (SM::ROW_TILES - 1) * ROWS * LDS;  // == rowA for FWD (unused)
   bf16* strA = rowA + SM::ROW_TILES * ROWS * LDS;
-  bf16* strB = strA + KC * LDS;
-  float* sf0 = reinterpret_cast<float*>(strB + KC * LDS);  // FWD/DQ: key bias (log2 units); DKV: lse of stream queries
-  float* sf1 = sf0 + KC;                                   // DKV: delta of stream queries
+  bf16* strB = strA + SROWS * LDS;
+  float* sf0 = reinterpret_cast<float*>(strB + SROWS * LDS);  // FWD/DQ: key bias (log2 units); DKV: lse of stream queries
+  float* sf1 = sf0 + SROWS;                                   // DKV: delta of stream queries
 
   const int lane = tid & 31;
   const int wq = tid >> 5;
@@ -175,17 +215,30 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
   const float scale2 = a.scale * LOG2E;
   const long long stat_base = (((long long)b * a.H + h) * a.G + g) * a.Lq;
 
+  // linear row addressing of this item's tensors (element offsets)
+  const long long q_row_first = (long long)b * a.q_bstride + a.q_row0 + (long long)g * a.q_gstride;
+  const long long o_row_first = (long long)b * a.o_bstride + a.q_row0 + (long long)g * a.q_gstride;
+  const long long k_row_first = (long long)b * a.kv_bstride + a.k_row0 + (long long)g * a.k_gstride;
+  const long long k_cls_row = (long long)b * a.kv_bstride + a.cls_row;
+  const int hc = a.has_cls ? 1 : 0;
+  const RowAddr aQ{a.q, q_row_first * a.ldq + h * HD, (long long)a.q_istride * a.ldq, 0, false};
+  const RowAddr aO{a.o, o_row_first * a.ldo + h * HD, (long long)a.q_istride * a.ldo, 0, false};
+  const RowAddr aDO{a.d_o, o_row_first * a.ldo + h * HD, (long long)a.q_istride * a.ldo, 0, false};
+  const RowAddr aK{a.k, (k_row_first - (long long)hc * a.k_istride) * a.ldkv + h * HD, (long long)a.k_istride * a.ldkv,
+                   k_cls_row * a.ldkv + h * HD, a.has_cls != 0};
+  const RowAddr aV{a.v, aK.off, aK.step, aK.cls, aK.has_cls};
+
   // ---------------------------------------------------------------- row-side operands -> registers
   if (MODE == MODE_FWD) {
-    load_tile<T_Q, ROWS, NT>(rowA, a, b, h, g, row0, n_rows, tid);
+    load_rows<NT>(rowA, aQ, row0, n_rows, ROWS, tid);
   } else if (MODE == MODE_DQ) {
-    load_tile<T_Q, ROWS, NT>(rowA, a, b, h, g, row0, n_rows, tid);
-    load_tile<T_DO, ROWS, NT>(rowB, a, b, h, g, row0, n_rows, tid);
-    static_assert(2 * KC >= 16 * NW, "the O tile is staged in the (contiguous) stream buffers");
-    load_tile<T_O, ROWS, NT>(strA, a, b, h, g, row0, n_rows, tid);   // O rows, only for delta = rowsum(dO * O)
+    load_rows<NT>(rowA, aQ, row0, n_rows, ROWS, tid);
+    load_rows<NT>(rowB, aDO, row0, n_rows, ROWS, tid);
+    static_assert(2 * KC * NCH >= 16 * NW, "the O tile is staged in the (contiguous) stream buffers");
+    load_rows<NT>(strA, aO, row0, n_rows, ROWS, tid);   // O rows, only for delta = rowsum(dO * O)
   } else {
-    load_tile<T_K, ROWS, NT>(rowA, a, b, h, g, row0, n_rows, tid);
-    load_tile<T_V, ROWS, NT>(rowB, a, b, h, g, row0, n_rows, tid);
+    load_rows<NT>(rowA, aK, row0, n_rows, ROWS, tid);
+    load_rows<NT>(rowB, aV, row0, n_rows, ROWS, tid);
   }
   cp_async_commit();
   cp_async_wait<0>();
@@ -230,110 +283,154 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
   float m_lo = -1e30f, m_hi = -1e30f, l_lo = 0.f, l_hi = 0.f;  // FWD online softmax state
 
   // ---------------------------------------------------------------- stream loop
-  for (int c0 = 0; c0 < n_str; c0 += KC) {
-    unit_sync<NW>();  // previous chunk fully consumed
+  auto load_stream = [&](int c0, int rows_cap, bf16* dA, bf16* dB, float* d0, float* d1) {
+    // rows c0 .. c0+rows_cap-1 of the stream side -> dA / dB (+ per-row scalars); rows past n_str are zero-filled
     if (MODE == MODE_DKV) {
-      load_tile<T_Q, KC, NT>(strA, a, b, h, g, c0, n_str, tid);
-      load_tile<T_DO, KC, NT>(strB, a, b, h, g, c0, n_str, tid);
-      for (int j = tid; j < KC; j += NT) {
+      load_rows<NT>(dA, aQ, c0, n_str, rows_cap, tid);
+      load_rows<NT>(dB, aDO, c0, n_str, rows_cap, tid);
+      for (int j = tid; j < rows_cap; j += NT) {
         const int idx = c0 + j;
-        sf0[j] = idx < n_str ? a.lse[stat_base + idx] : 0.f;
-        sf1[j] = idx < n_str ? a.delta[stat_base + idx] : 0.f;
+        d0[j] = idx < n_str ? a.lse[stat_base + idx] : 0.f;
+        d1[j] = idx < n_str ? a.delta[stat_base + idx] : 0.f;
       }
     } else {
-      load_tile<T_K, KC, NT>(strA, a, b, h, g, c0, n_str, tid);
-      load_tile<T_V, KC, NT>(strB, a, b, h, g, c0, n_str, tid);
-      for (int j = tid; j < KC; j += NT) {
-        const int idx = c0 + j;
-        float bj = 0.f;
-        if (a.key_bias && idx < n_str) bj = fmaxf(a.key_bias[(long long)b * a.LkT + idx], -1e30f) * LOG2E;
-        sf0[j] = bj;
+      load_rows<NT>(dA, aK, c0, n_str, rows_cap, tid);
+      load_rows<NT>(dB, aV, c0, n_str, rows_cap, tid);
+      if (a.key_bias) {
+        for (int j = tid; j < rows_cap; j += NT) {
+          const int idx = c0 + j;
+          d0[j] = idx < n_str ? fmaxf(a.key_bias[(long long)b * a.LkT + idx], -1e30f) * LOG2E : 0.f;
+        }
       }
     }
+  };
+  if (NCH > 1) {
+    unit_sync<NW>();  // row-side phase (delta from the staged O tile) finished with the stream buffers
+    const int rows_needed = ((n_str + KC - 1) / KC) * KC;   // <= SROWS (checked by the host)
+    load_stream(0, rows_needed, strA, strB, sf0, sf1);
     cp_async_commit();
     cp_async_wait<0>();
     unit_sync<NW>();
+  }
+  for (int c0 = 0; c0 < n_str; c0 += KC) {
+    if (NCH == 1) {
+      unit_sync<NW>();  // previous chunk fully consumed
+      load_stream(c0, KC, strA, strB, sf0, sf1);
+      cp_async_commit();
+      cp_async_wait<0>();
+      unit_sync<NW>();
+    }
+    const int coff = NCH > 1 ? c0 : 0;
+    const bf16* cA = strA + coff * LDS;
+    const bf16* cB = strB + coff * LDS;
+    const float* cf0 = sf0 + coff;
+    const float* cf1 = sf1 + coff;
 
     float s[KC / 8][4];
 #pragma unroll
     for (int i = 0; i < KC / 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
-    mma_a_stile_nt<KC>(s, fa, strA, lane);  // FWD/DQ: Q K^T    DKV: K Q^T
+    mma_a_stile_nt<KC>(s, fa, cA, lane);  // FWD/DQ: Q K^T    DKV: K Q^T
 
-    if (MODE == MODE_FWD) {
-      float cm_lo = -1e30f, cm_hi = -1e30f;
+    // The scalar part below is what bounds these kernels (XU / ALU pipes), so it is specialised at compile time on
+    // FULL (no stream-side tail in this chunk: no bounds predicates) and BIAS (additive key bias present).
+    const int lim = n_str - c0;   // valid stream rows in this chunk (>= KC when full)
+    auto chunk = [&](auto full_t, auto bias_t) {
+      constexpr bool FULL = decltype(full_t)::value;
+      constexpr bool BIAS = decltype(bias_t)::value;
+      if (MODE == MODE_FWD) {
+        float cm_lo = -1e30f, cm_hi = -1e30f;
 #pragma unroll
-      for (int nt = 0; nt < KC / 8; ++nt) {
+        for (int nt = 0; nt < KC / 8; ++nt) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = nt * 8 + 2 * tq + (e & 1);
-          float v = (c0 + col < n_str) ? fmaf(s[nt][e], scale2, sf0[col]) : -1e30f;
-          s[nt][e] = v;
-          if (e < 2) cm_lo = fmaxf(cm_lo, v);
-          else cm_hi = fmaxf(cm_hi, v);
+          for (int e = 0; e < 4; ++e) {
+            const int col = nt * 8 + 2 * tq + (e & 1);
+            float v = BIAS ? fmaf(s[nt][e], scale2, cf0[col]) : s[nt][e] * scale2;
+            if (!FULL) v = col < lim ? v : -1e30f;
+            s[nt][e] = v;
+            if (e < 2) cm_lo = fmaxf(cm_lo, v);
+            else cm_hi = fmaxf(cm_hi, v);
+          }
         }
-      }
-      cm_lo = fmaxf(cm_lo, __shfl_xor_sync(0xffffffffu, cm_lo, 1));
-      cm_lo = fmaxf(cm_lo, __shfl_xor_sync(0xffffffffu, cm_lo, 2));
-      cm_hi = fmaxf(cm_hi, __shfl_xor_sync(0xffffffffu, cm_hi, 1));
-      cm_hi = fmaxf(cm_hi, __shfl_xor_sync(0xffffffffu, cm_hi, 2));
-      const float mn_lo = fmaxf(m_lo, cm_lo), mn_hi = fmaxf(m_hi, cm_hi);
-      const float al_lo = exp2f(m_lo - mn_lo), al_hi = exp2f(m_hi - mn_hi);
-      m_lo = mn_lo;
-      m_hi = mn_hi;
-      l_lo *= al_lo;
-      l_hi *= al_hi;
+        cm_lo = fmaxf(cm_lo, __shfl_xor_sync(0xffffffffu, cm_lo, 1));
+        cm_lo = fmaxf(cm_lo, __shfl_xor_sync(0xffffffffu, cm_lo, 2));
+        cm_hi = fmaxf(cm_hi, __shfl_xor_sync(0xffffffffu, cm_hi, 1));
+        cm_hi = fmaxf(cm_hi, __shfl_xor_sync(0xffffffffu, cm_hi, 2));
+        const float mn_lo = fmaxf(m_lo, cm_lo), mn_hi = fmaxf(m_hi, cm_hi);
+        const float al_lo = ex2(m_lo - mn_lo), al_hi = ex2(m_hi - mn_hi);
+        m_lo = mn_lo;
+        m_hi = mn_hi;
+        l_lo *= al_lo;
+        l_hi *= al_hi;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        acc0[nt][0] *= al_lo;
-        acc0[nt][1] *= al_lo;
-        acc0[nt][2] *= al_hi;
-        acc0[nt][3] *= al_hi;
-      }
-#pragma unroll
-      for (int nt = 0; nt < KC / 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = nt * 8 + 2 * tq + (e & 1);
-          float pv = (c0 + col < n_str) ? exp2f(s[nt][e] - (e < 2 ? m_lo : m_hi)) : 0.f;
-          s[nt][e] = pv;
-          if (e < 2) l_lo += pv;
-          else l_hi += pv;
+        for (int nt = 0; nt < 8; ++nt) {
+          acc0[nt][0] *= al_lo;
+          acc0[nt][1] *= al_lo;
+          acc0[nt][2] *= al_hi;
+          acc0[nt][3] *= al_hi;
         }
+#pragma unroll
+        for (int nt = 0; nt < KC / 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float pv = ex2(s[nt][e] - (e < 2 ? m_lo : m_hi));
+            if (!FULL) {
+              const int col = nt * 8 + 2 * tq + (e & 1);
+              pv = col < lim ? pv : 0.f;
+            }
+            s[nt][e] = pv;
+            if (e < 2) l_lo += pv;
+            else l_hi += pv;
+          }
+        }
+        mma_p_stile<KC>(acc0, s, cB, lane);  // O += P V
+      } else {
+        // P (or P^T) from the saved log-sum-exp
+#pragma unroll
+        for (int nt = 0; nt < KC / 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = nt * 8 + 2 * tq + (e & 1);
+            float pv;
+            if (MODE == MODE_DQ) {
+              const float sc = BIAS ? fmaf(s[nt][e], scale2, cf0[col]) : s[nt][e] * scale2;
+              pv = ex2(sc - (e < 2 ? st0_lo : st0_hi));
+            } else {
+              // DKV: the key bias is a per-row constant (0 when absent), the lse is per stream column
+              pv = ex2(fmaf(s[nt][e], scale2, (e < 2 ? st0_lo : st0_hi)) - cf0[col]);
+            }
+            if (!FULL) pv = col < lim ? pv : 0.f;
+            s[nt][e] = pv;
+          }
+        }
+        if (MODE == MODE_DKV) mma_p_stile<KC>(acc1, s, cB, lane);  // dV += P^T dO
+        float dp[KC / 8][4];
+#pragma unroll
+        for (int i = 0; i < KC / 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dp[i][j] = 0.f;
+        mma_a_stile_nt<KC>(dp, fb, cB, lane);  // DQ: dO V^T    DKV: V dO^T
+#pragma unroll
+        for (int nt = 0; nt < KC / 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = nt * 8 + 2 * tq + (e & 1);
+            const float dl = (MODE == MODE_DQ) ? (e < 2 ? st1_lo : st1_hi) : cf1[col];
+            s[nt][e] = s[nt][e] * (dp[nt][e] - dl);  // dS (or dS^T)
+          }
+        }
+        mma_p_stile<KC>(acc0, s, cA, lane);  // DQ: dQ += dS K    DKV: dK += dS^T Q
       }
-      mma_p_stile<KC>(acc0, s, strB, lane);  // O += P V
+    };
+    const bool full = lim >= KC;
+    const bool has_bias = (MODE != MODE_DKV) && a.key_bias != nullptr;
+    if (full) {
+      if (has_bias) chunk(std::true_type{}, std::true_type{});
+      else chunk(std::true_type{}, std::false_type{});
     } else {
-      // P (or P^T) from the saved log-sum-exp
-#pragma unroll
-      for (int nt = 0; nt < KC / 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = nt * 8 + 2 * tq + (e & 1);
-          const bool ok = c0 + col < n_str;
-          float pv;
-          if (MODE == MODE_DQ) pv = exp2f(fmaf(s[nt][e], scale2, sf0[col]) - (e < 2 ? st0_lo : st0_hi));
-          else pv = exp2f(fmaf(s[nt][e], scale2, (e < 2 ? st0_lo : st0_hi)) - sf0[col]);
-          s[nt][e] = ok ? pv : 0.f;
-        }
-      }
-      if (MODE == MODE_DKV) mma_p_stile<KC>(acc1, s, strB, lane);  // dV += P^T dO
-      float dp[KC / 8][4];
-#pragma unroll
-      for (int i = 0; i < KC / 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dp[i][j] = 0.f;
-      mma_a_stile_nt<KC>(dp, fb, strB, lane);  // DQ: dO V^T    DKV: V dO^T
-#pragma unroll
-      for (int nt = 0; nt < KC / 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = nt * 8 + 2 * tq + (e & 1);
-          const float dl = (MODE == MODE_DQ) ? (e < 2 ? st1_lo : st1_hi) : sf1[col];
-          s[nt][e] = s[nt][e] * (dp[nt][e] - dl);  // dS (or dS^T)
-        }
-      }
-      mma_p_stile<KC>(acc0, s, strA, lane);  // DQ: dQ += dS K    DKV: dK += dS^T Q
+      if (has_bias) chunk(std::false_type{}, std::true_type{});
+      else chunk(std::false_type{}, std::false_type{});
     }
   }
 
@@ -367,49 +464,53 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
     }
   }
   unit_sync<NW>();
-  for (int c = tid; c < ROWS * 8; c += NT) {
-    const int r = c >> 3, ch = c & 7;
-    const int idx = row0 + r;
-    if (idx >= n_rows) continue;
-    if (MODE == MODE_FWD) {
-      bf16* dst = a.o + o_row(a, b, g, idx) * a.ldo + h * HD + ch * 8;
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(rowA + r * LDS + ch * 8);
-    } else if (MODE == MODE_DQ) {
-      bf16* dst = a.dq + q_row(a, b, g, idx) * a.lddq + h * HD + ch * 8;
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(rowA + r * LDS + ch * 8);
-    } else {
-      if (a.has_cls && idx == 0) continue;  // shared CLS key: accumulated in dkv_cls above
-      const long long off = k_row(a, b, g, idx) * a.lddkv + h * HD + ch * 8;
-      uint4 vk = *reinterpret_cast<const uint4*>(rowA + r * LDS + ch * 8);
-      uint4 vv = *reinterpret_cast<const uint4*>(rowB + r * LDS + ch * 8);
-      if (a.dkv_accumulate) {
-        uint4 ok = *reinterpret_cast<const uint4*>(a.dk + off);
-        uint4 ov = *reinterpret_cast<const uint4*>(a.dv + off);
-        uint32_t* pk = reinterpret_cast<uint32_t*>(&vk);
-        uint32_t* pv = reinterpret_cast<uint32_t*>(&vv);
-        const uint32_t* qk = reinterpret_cast<const uint32_t*>(&ok);
-        const uint32_t* qv = reinterpret_cast<const uint32_t*>(&ov);
+  {
+    constexpr int RSTEP = NT / 8;
+    const int ch = tid & 7;
+    const RowAddr gQ{a.dq, q_row_first * a.lddq + h * HD, (long long)a.q_istride * a.lddq, 0, false};
+    const RowAddr gK{a.dk, (k_row_first - (long long)hc * a.k_istride) * a.lddkv + h * HD, (long long)a.k_istride * a.lddkv, 0, false};
+    for (int r = tid >> 3; r < ROWS; r += RSTEP) {
+      const int idx = row0 + r;
+      if (idx >= n_rows) break;
+      const uint4 va = *reinterpret_cast<const uint4*>(rowA + r * LDS + ch * 8);
+      if (MODE == MODE_FWD) {
+        *reinterpret_cast<uint4*>(a.o + aO.off + (long long)idx * aO.step + ch * 8) = va;
+      } else if (MODE == MODE_DQ) {
+        *reinterpret_cast<uint4*>(a.dq + gQ.off + (long long)idx * gQ.step + ch * 8) = va;
+      } else {
+        if (a.has_cls && idx == 0) continue;  // shared CLS key: accumulated in dkv_cls above
+        const long long off = gK.off + (long long)idx * gK.step + ch * 8;
+        uint4 vk = va;
+        uint4 vv = *reinterpret_cast<const uint4*>(rowB + r * LDS + ch * 8);
+        if (a.dkv_accumulate) {
+          uint4 ok = *reinterpret_cast<const uint4*>(a.dk + off);
+          uint4 ov = *reinterpret_cast<const uint4*>(a.dv + off);
+          uint32_t* pk = reinterpret_cast<uint32_t*>(&vk);
+          uint32_t* pv = reinterpret_cast<uint32_t*>(&vv);
+          const uint32_t* qk = reinterpret_cast<const uint32_t*>(&ok);
+          const uint32_t* qv = reinterpret_cast<const uint32_t*>(&ov);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float2 x = unpack_bf16(pk[e]), y = unpack_bf16(qk[e]);
-          pk[e] = pack_bf16(x.x + y.x, x.y + y.y);
-          x = unpack_bf16(pv[e]);
-          y = unpack_bf16(qv[e]);
-          pv[e] = pack_bf16(x.x + y.x, x.y + y.y);
+          for (int e = 0; e < 4; ++e) {
+            float2 x = unpack_bf16(pk[e]), y = unpack_bf16(qk[e]);
+            pk[e] = pack_bf16(x.x + y.x, x.y + y.y);
+            x = unpack_bf16(pv[e]);
+            y = unpack_bf16(qv[e]);
+            pv[e] = pack_bf16(x.x + y.x, x.y + y.y);
+          }
         }
+        *reinterpret_cast<uint4*>(a.dk + off) = vk;
+        *reinterpret_cast<uint4*>(a.dv + off) = vv;
       }
-      *reinterpret_cast<uint4*>(a.dk + off) = vk;
-      *reinterpret_cast<uint4*>(a.dv + off) = vv;
     }
   }
 }
 
 // CTA-per-item variant (large groups): NW warps cooperate on one item.
-template <int MODE, int NW, int KC>
+template <int MODE, int NW, int KC, int NCH = 1>
 __global__ void __launch_bounds__(NW * 32) attn_cta_kernel(const AttnP a) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   for (long long item = blockIdx.x; item < a.items; item += gridDim.x) {
-    attn_unit<MODE, NW, KC>(a, item, smem_attn, threadIdx.x);
+    attn_unit<MODE, NW, KC, NCH>(a, item, smem_attn, threadIdx.x);
     __syncthreads();
   }
 }
@@ -467,7 +568,7 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) attn_single_fwd_kernel(const At
       sc[u] = j < a.LkT ? fmaf(d, scale2, bj) : -1e30f;
     }
     float mn = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])), m);
-    const float al = exp2f(m - mn);
+    const float al = ex2(m - mn);
     l *= al;
     o0 *= al;
     o1 *= al;
@@ -475,7 +576,7 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) attn_single_fwd_kernel(const At
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = j0 + u * SQ_WARPS;
-      const float pj = j < a.LkT ? exp2f(sc[u] - m) : 0.f;
+      const float pj = j < a.LkT ? ex2(sc[u] - m) : 0.f;
       l += pj;
       o0 = fmaf(pj, vv[u].x, o0);
       o1 = fmaf(pj, vv[u].y, o1);
@@ -495,7 +596,7 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) attn_single_fwd_kernel(const At
     float L = 0.f, r0 = 0.f, r1 = 0.f;
 #pragma unroll
     for (int w = 0; w < SQ_WARPS; ++w) {
-      const float f = exp2f(sm_m[w] - M);
+      const float f = ex2(sm_m[w] - M);
       L = fmaf(sm_l[w], f, L);
       r0 = fmaf(sm_o[w][2 * lane], f, r0);
       r1 = fmaf(sm_o[w][2 * lane + 1], f, r1);
@@ -539,7 +640,7 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) attn_single_bwd_kernel(const At
     }
     float bj = 0.f;
     if (a.key_bias) bj = fmaxf(a.key_bias[(long long)b * a.LkT + j], -1e30f) * LOG2E;
-    const float pj = exp2f(fmaf(s, scale2, bj) - lse);
+    const float pj = ex2(fmaf(s, scale2, bj) - lse);
     const float ds = pj * (dp - delta);
     dq0 = fmaf(ds, kk.x, dq0);
     dq1 = fmaf(ds, kk.y, dq1);
@@ -646,7 +747,7 @@ __global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_fwd_heads_kernel(c
     for (int i = 0; i < NG; ++i) {
       const float sc = fmaf(red8(dot8(q[i], kk[i])), scale2, bj);
       const float mn = fmaxf(m[i], sc);
-      const float al = exp2f(m[i] - mn), pj = exp2f(sc - mn);
+      const float al = ex2(m[i] - mn), pj = ex2(sc - mn);
       m[i] = mn;
       l[i] = fmaf(l[i], al, pj);
 #pragma unroll
@@ -672,7 +773,7 @@ __global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_fwd_heads_kernel(c
     float L = 0.f, r = 0.f;
 #pragma unroll
     for (int w = 0; w < SQH_WARPS; ++w) {
-      const float f = exp2f(sm_m[w][h] - M);
+      const float f = ex2(sm_m[w][h] - M);
       L = fmaf(sm_l[w][h], f, L);
       r = fmaf(sm_o[w][t], f, r);
     }
@@ -693,7 +794,7 @@ __global__ void __launch_bounds__(64) attn_single_combine_kernel(const AttnP a, 
   float L = 0.f, r = 0.f;
   for (int s = 0; s < SQ_SPLITS; ++s) {
     const float* p = part + (((long long)b * SQ_SPLITS + s) * a.H + h) * 66;
-    const float f = exp2f(p[0] - M);
+    const float f = ex2(p[0] - M);
     L = fmaf(p[1], f, L);
     r = fmaf(p[2 + d], f, r);
   }
@@ -750,7 +851,7 @@ __global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_bwd_heads_kernel(c
     for (int i = 0; i < NG; ++i) {
       const float s = red8(dot8(q[i], kk[i]));
       const float dp = red8(dot8(d_o[i], vv[i]));
-      const float pj = exp2f(fmaf(s, scale2, bj) - lse[i]);
+      const float pj = ex2(fmaf(s, scale2, bj) - lse[i]);
       const float ds = pj * (dp - delta[i]);
       float gk[8], gv[8];
 #pragma unroll
@@ -925,7 +1026,23 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
     static const int wide_mode = getenv("EGV_ATTN_WIDE") ? atoi(getenv("EGV_ATTN_WIDE")) : 6;   // bit per MODE
     const bool wide = ((wide_mode >> MODE) & 1) && n_str > 32 &&
                       util(n_rows, 112) * util(n_str, 112) > 1.1 * util(n_rows, 64) * util(n_str, 64);
-    if (n_str <= 32) {
+    static const int resident_mode = getenv("EGV_ATTN_RESIDENT") ? atoi(getenv("EGV_ATTN_RESIDENT")) : 6;
+    if (((resident_mode >> MODE) & 1) && n_str > 64 && n_str <= 256 && n_rows > 64) {
+      // the whole stream side of a group stays in shared memory (space attention: 196-197 rows)
+      constexpr int KC = 64, NCH = 4;
+      constexpr int NWR = (MODE == MODE_DKV) ? 4 : 7;
+      a.row_tiles = (int)cdiv(n_rows, 16 * NWR);
+      a.items = groups * a.row_tiles;
+      auto kern = attn_cta_kernel<MODE, NWR, KC, NCH>;
+      const int smem = AttnSmem<MODE, NWR, KC, NCH>::BYTES;
+      static bool cfg = false;
+      if (!cfg) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cfg = true;
+      }
+      long long grid = std::min<long long>(a.items, (long long)sm_count() * 4);
+      if (e == cudaSuccess) kern<<<(unsigned)grid, NWR * 32, smem, stream>>>(a);
+    } else if (n_str <= 32) {
       constexpr int KC = 32;
       a.row_tiles = (int)cdiv(n_rows, 64);
       a.items = groups * a.row_tiles;
