@@ -152,7 +152,7 @@ def run_ours(a, rank, world, local_rank):
     randomize_gates(model)
     model.eval()      # text dropout is not implemented: eval-mode semantics
     use_graph = not a.no_graph
-    step = PretrainStep(model, dev, max_steps=10000, warmup_steps=100, gather="nccl" if use_graph else "auto")
+    step = PretrainStep(model, dev, max_steps=10000, warmup_steps=100, gather=a.gather)
     host = synthetic_batch(a.batch, a.frames, 224, a.seq, seed=1234 + rank, pin=True)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     dev_batch = step.to_device(host)
@@ -189,12 +189,21 @@ def run_ours(a, rank, world, local_rank):
             ms = float(t.item())
         return ms, last
 
-    for _ in range(max(a.warmup, 3)):
+    def note(msg):
+        if os.environ.get("BENCH_VERBOSE"):
+            torch.cuda.synchronize()
+            print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
+
+    note("model built, gather=%s" % step.gather_kind)
+    for i in range(max(a.warmup, 3)):
         step.step(dev_batch)
+        note("eager warm-up step %d done" % i)
     if use_graph:
         step.capture(dev_batch, warmup=1)
+        note("graph captured")
         for _ in range(2):
             step.step_graph(dev_batch)
+        note("graph replays ok")
     launches0 = K.launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms, _ = timed(a.steps, e2e=False)
@@ -203,12 +212,14 @@ def run_ours(a, rank, world, local_rank):
     clocks = sampler.stop() if sampler else None
 
     # instrumented extra step: per-launch CUDA events -> GEMM / attention time and work (not part of the timed region)
+    # (every rank runs it -- a step contains collectives -- but only rank 0 keeps the timings)
     prof = None
+    torch.cuda.synchronize()
     if rank == 0:
-        torch.cuda.synchronize()
         K.start_profile()
-        step.step(dev_batch)
-        torch.cuda.synchronize()
+    step.step(dev_batch)
+    torch.cuda.synchronize()
+    if rank == 0:
         prof = K.stop_profile()
     if world > 1:
         dist.barrier()
@@ -274,6 +285,7 @@ def main():
     ap.add_argument("--seq", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=1, dest="cpu_sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"], help="embedding all-gather implementation")
     ap.add_argument("--no-graph", action="store_true", help="eager kernel launches instead of replaying a captured CUDA graph")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -44,9 +44,6 @@ class P2PAllGather:
             else:
                 self.peer_slots.append(K.p2p_open(hs))
                 self.peer_flags.append(K.p2p_open(hf))
-        self.seq = 0
-        # view of the local receive buffer as a torch tensor (uint8) without copying
-        self._local = _as_tensor(self.slots_ptr, nslots, device)
         dist.barrier()
 
     def __call__(self, tensor, n_gpu=None, args=None):
@@ -54,20 +51,6 @@ class P2PAllGather:
         nbytes = t.numel() * t.element_size()
         if nbytes > self.SLOT_BYTES or nbytes % 16 or t.data_ptr() % 16:
             return self.nccl(t)
-        self.seq += 1
-        parity = self.seq & 1
-        half = self.world * self.SLOT_BYTES
-        slots = [p + parity * half for p in self.peer_slots]
-        self.K.p2p_allgather(t, nbytes, self.SLOT_BYTES, slots, self.peer_flags, self.rank, self.world, self.seq)
-        loc = self._local[parity * half:(parity + 1) * half].view(self.world, self.SLOT_BYTES)[:, :nbytes]
-        out = loc.contiguous().view(t.dtype).view((self.world * t.shape[0],) + tuple(t.shape[1:]))
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self.K.p2p_allgather(t, nbytes, self.SLOT_BYTES, self.peer_slots, self.peer_flags, self.rank, self.world, out)
         return out
-
-
-def _as_tensor(ptr, nbytes, device):
-    """Wrap a raw device allocation as a uint8 torch tensor via the CUDA array interface."""
-    class _Holder:
-        pass
-    h = _Holder()
-    h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
-    return torch.as_tensor(h, device=device)

@@ -52,27 +52,46 @@ struct GemmParams {
   float* colsum;  // optional [N]: += column sums of the final value (bias gradients), fp32 atomics
 };
 
-// erf with |abs err| < 1.5e-7 (Abramowitz-Stegun 7.1.26): far below bf16 resolution, ~3x cheaper than erff.
-EGV_DEVINL float fast_erf(float x) {
-  float ax = fabsf(x);
-  float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  float r = 1.0f - p * t * __expf(-ax * ax);
-  return copysignf(r, x);
+EGV_DEVINL float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+EGV_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Phi(x) = 0.5 (1 + erf(x / sqrt 2)) with ONE transcendental: Abramowitz-Stegun 7.1.28,
+// erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, |err| <= 3e-7 (far below bf16 resolution); the 1/sqrt(2) is folded
+// into the coefficients.  The epilogue of the GELU GEMMs is bound by the XU (MUFU) pipe, hence the form.
+EGV_DEVINL float gelu_cdf(float x) {
+  const float ax = fabsf(x);
+  float d = fmaf(ax, 5.3829750e-6f, 4.8890636e-5f);   // a6/8, a5/(4 sqrt2)
+  d = fmaf(d, ax, 3.8003575e-5f);                     // a4/4
+  d = fmaf(d, ax, 3.2776263e-3f);                     // a3/(2 sqrt2)
+  d = fmaf(d, ax, 2.1141006e-2f);                     // a2/2
+  d = fmaf(d, ax, 4.9867347e-2f);                     // a1/sqrt2
+  d = fmaf(d, ax, 1.0f);
+  float r = rcp_approx(d);
+  r *= r;
+  r *= r;
+  r *= r;
+  r *= r;                       // d^-16 = 1 - erf(|x|/sqrt2)
+  const float half_erfc = 0.5f * r;
+  return x >= 0.f ? 1.0f - half_erfc : half_erfc;
 }
 
 template <int ACT>
 EGV_DEVINL float apply_act(float v, float auxv) {
-  if (ACT == EGV_ACT_GELU) return 0.5f * v * (1.0f + fast_erf(v * 0.70710678118654752f));
+  if (ACT == EGV_ACT_GELU) return v * gelu_cdf(v);
   if (ACT == EGV_ACT_RELU) return fmaxf(v, 0.0f);
   if (ACT == EGV_ACT_TANH) return tanhf(v);
   if (ACT == EGV_ACT_GELU_BWD) {
-    const float cdf = 0.5f * (1.0f + fast_erf(auxv * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * auxv * auxv);
-    return v * fmaf(auxv, pdf, cdf);
+    // gelu'(x) = Phi(x) + x phi(x),  phi(x) = exp(-x^2/2) / sqrt(2 pi)
+    const float pdf = 0.3989422804014327f * ex2_approx(-0.72134752044448170f * auxv * auxv);
+    return v * fmaf(auxv, pdf, gelu_cdf(auxv));
   }
   if (ACT == EGV_ACT_RELU_BWD) return auxv > 0.0f ? v : 0.0f;
   if (ACT == EGV_ACT_TANH_BWD) return v * (1.0f - auxv * auxv);
@@ -166,10 +185,8 @@ EGV_DEVINL void epi_rows_vec4(const GemmParams& p, const float* stg, int lane, i
     if (o32) {
       float* o = o32 + rl * ld32;
       if (p.accumulate) {
-        atomicAdd(o, v0);
-        atomicAdd(o + 1, v1);
-        atomicAdd(o + 2, v2);
-        atomicAdd(o + 3, v3);
+        // one 16-byte reduction instead of four scalar ones (split-K slices / gradient accumulation)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
       } else {
         *reinterpret_cast<float4*>(o) = make_float4(v0, v1, v2, v3);
       }
@@ -645,6 +662,7 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   bool auto_split = false;
   if (split_k == 1 && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && a->act == EGV_ACT_NONE && !a->residual &&
       !a->colsum) {
+    if (BN == 256 && (long long)num_m_tiles * cdiv(a->N, 128) <= sm_count()) BN = 128;
     const long long tiles256 = (long long)num_m_tiles * cdiv(a->N, BN);
     if (tiles256 * 2 <= sm_count() && p.k_blocks_total >= 16) {
       long long want = cdiv(sm_count(), tiles256);

@@ -389,11 +389,11 @@ class Kernels:
         self._check(self.lib.egv_p2p_open(C.c_char_p(handle), C.byref(ptr)))
         return ptr.value
 
-    def p2p_allgather(self, src, nbytes, slot_bytes, slots, flags, rank, world, seq):
+    def p2p_allgather(self, src, nbytes, slot_bytes, slots, flags, rank, world, out):
         arr_s = (C.c_void_p * world)(*slots)
         arr_f = (C.c_void_p * world)(*flags)
         self._check(self.lib.egv_p2p_allgather(_p(src), c_int64(nbytes), c_int64(slot_bytes), arr_s, arr_f, rank, world,
-                                               C.c_uint32(seq), self._stream()))
+                                               _p(out), self._stream()))
 
 
 _KERNELS = None

@@ -81,8 +81,6 @@ class PretrainStep:
         """Capture forward + backward + all-reduce + AdamW of one step into a CUDA graph with static input buffers.
         Afterwards `step_graph(batch)` copies the batch into the static buffers and replays the graph: one host call
         instead of ~3000 kernel launches and the Python autograd bookkeeping."""
-        if getattr(self, "gather_kind", "none") == "p2p":
-            raise RuntimeError("the P2P gather passes its sequence number by value; capture with gather='nccl'")
         self.static = {k: v.clone() for k, v in example_batch.items()}
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())

@@ -183,17 +183,17 @@ int egv_egonce(const float* t, const float* v, int G, int P, const float* noun, 
                float* dv, float* scratch, egv_stream_t stream);
 
 /* NVSwitch peer-to-peer all-gather (trainer_egoclip.py:25-41 AllGather_multi; model.py:385-388) ------------
- * Symmetric buffers: every rank egv_p2p_alloc()s `slots` (W * slot_bytes, x2 for double buffering by the caller)
+ * Symmetric buffers: every rank egv_p2p_alloc()s `slots` (2 * W * slot_bytes: two sets, consecutive gathers alternate)
  * and `flags` (32 uint32), exchanges the 64-byte IPC handles out of band (torch.distributed) and maps the peers'
- * buffers with egv_p2p_open().  egv_p2p_allgather pushes `bytes` from src into slot `rank` of every peer, publishes
- * the monotonically increasing `seq` and waits until all W local flags reached it.  Consecutive gathers must
- * alternate between two slot sets (the caller offsets the `slots` pointers by parity of seq). */
+ * buffers with egv_p2p_open().  egv_p2p_allgather pushes `bytes` from src into slot `rank` of every peer, publishes a
+ * device-resident, monotonically increasing sequence number, waits until all W local flags reached it and copies the
+ * W gathered payloads (rank-major) into `out`.  No host-side state: the call can be captured in a CUDA graph. */
 int egv_p2p_alloc(int64_t bytes, void** ptr, void* ipc_handle_64);
 int egv_p2p_open(const void* ipc_handle_64, void** ptr);
 int egv_p2p_close(void* ptr);
 int egv_p2p_free(void* ptr);
 int egv_p2p_allgather(const void* src, int64_t bytes, int64_t slot_bytes, void* const* slots, void* const* flags, int rank,
-                      int world, uint32_t seq, egv_stream_t stream);
+                      int world, void* out, egv_stream_t stream);
 
 /* Optimiser (next row f-1): fused AdamW (transformers.AdamW semantics, set_optim_schedule.py:108) on one flat fp32
  * tensor; also refreshes the bf16 weight copy.  hyper_dev (optional, device float[3]) = {lr multiplier, 1-beta1^t,

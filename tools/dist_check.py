@@ -1,0 +1,86 @@
+"""Multi-GPU checks (run under torchrun, one rank per GPU):
+  1. the NVSwitch P2P all-gather kernel returns exactly what NCCL all_gather returns (odd number of calls: both slot sets);
+  2. multi-rank parity of the pre-training step: every rank's losses equal the single-process losses on the
+     concatenated batch, and the rank-summed gradients equal the full-batch gradients."""
+import os
+import sys
+import types
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from egovlpv2_b200 import lib as L  # noqa: E402
+from egovlpv2_b200.comm import NcclAllGather, P2PAllGather  # noqa: E402
+from egovlpv2_b200.model.loss import EgoNCE  # noqa: E402
+from egovlpv2_b200.synthetic import synthetic_batch  # noqa: E402
+from egovlpv2_b200.trainer import build_model, randomize_gates  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+K = L.kernels()
+p2p, nccl = P2PAllGather(dev), NcclAllGather()
+g = torch.Generator(device="cpu").manual_seed(100 + rank)
+for i, shape in enumerate([(8, 4096), (4, 582), (4, 118), (8, 4096), (4, 32), (16, 4096), (8, 4096)]):
+    dt = torch.float32 if i != 4 else torch.int64
+    t = (torch.randn(shape, generator=g) * 3).to(dt).to(dev)
+    a, b = p2p(t), nccl(t)
+    torch.cuda.synchronize()
+    assert a.shape == b.shape and torch.equal(a, b), ("p2p gather mismatch", i, rank)
+if rank == 0:
+    print("p2p all-gather == nccl all_gather: ok (%d ranks)" % world)
+
+# ---- step parity
+c = dict(C=128, heads=2, depth=8, n_fuse=2, T=2, img=64, S=8, proj=256, vocab=50265)
+Bl = 4
+torch.manual_seed(0)
+model = build_model(T=c["T"], img=c["img"], C=c["C"], heads=c["heads"], depth=c["depth"], n_fuse=c["n_fuse"], vocab=c["vocab"],
+                    proj=c["proj"])
+randomize_gates(model)
+model.eval().to(dev)
+for p in model.parameters():
+    dist.broadcast(p.data, 0)
+full = synthetic_batch(Bl * world, c["T"], c["img"], c["S"], seed=7)
+full = {k: v.to(dev) for k, v in full.items()}
+gp = torch.Generator().manual_seed(5)
+G = Bl * world
+labels = torch.cat([torch.ones(Bl // 2), torch.zeros(Bl - Bl // 2)]).repeat(world)
+swap = torch.rand(G, generator=gp) > 0.5
+neg = (torch.arange(G) + torch.randint(1, G, (G,), generator=gp)) % G
+
+
+def run(batch, plan, allgather, args):
+    model.zero_grad(set_to_none=True)
+    model.itm_plan = plan
+    data = {"video": batch["video"], "text": {"input_ids": batch["input_ids"], "attention_mask": batch["attention_mask"]},
+            "text_mlm_ids": batch["text_mlm_ids"], "text_mlm_labels": batch["text_mlm_labels"]}
+    loss, ld, _ = model(data, batch["noun_vec"], batch["verb_vec"], allgather, world, args, {"loss": {"type": "EgoNCE"}},
+                        EgoNCE(), local, task_names="EgoNCE_MLM_ITM")
+    loss.backward()
+    return {k: float(v) for k, v in ld.items()}, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+
+sl = slice(rank * Bl, (rank + 1) * Bl)
+loc = {k: v[sl].contiguous() for k, v in full.items()}
+ld_r, g_r = run(loc, dict(labels=labels[sl], swap_video=swap[sl], neg_idx=neg[sl]), p2p,
+                types.SimpleNamespace(world_size=world, rank=rank))
+# single-process reference on the concatenated batch: no cross-rank reduction of the loss sums
+model._global_mean = lambda ls, cnt: ls.reshape(()) / cnt.reshape(()).clamp_min(1.0)
+ld_f, g_f = run(full, dict(labels=labels, swap_video=swap, neg_idx=neg), lambda t, n=None, a=None: t,
+                types.SimpleNamespace(world_size=1, rank=0))
+for k in ld_f:
+    assert abs(ld_r[k] - ld_f[k]) <= 2e-2 * max(1.0, abs(ld_f[k])), (k, ld_r[k], ld_f[k], rank)
+worst = 0.0
+for n in sorted(g_f)[::7]:
+    s = g_r[n].clone()
+    dist.all_reduce(s)
+    ref = g_f[n]
+    err = ((s - ref).norm() / ref.norm().clamp_min(1e-6)).item()
+    worst = max(worst, err)
+    assert err <= 0.2, (n, err)
+if rank == 0:
+    print("multi-rank step parity ok: losses %s ; worst sampled gradient rel-L2 %.3f" % (ld_r, worst))
+dist.barrier()
+dist.destroy_process_group()
