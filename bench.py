@@ -95,46 +95,57 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU port (oracle)
-def cpu_port_clips_per_sec(a, sample_batch, iters=1):
+class CpuPort:
     """The oracle (oracle/egovlp_oracle.py: fp32 functional restatement of the reference's PyTorch path) timed on the
     host cores: forward + backward of one EgoNCE+MLM+ITM step on `sample_batch` clips of the workload."""
-    from oracle import egovlp_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    shapes = O.key_shapes(T=a.frames)
-    sd = {k: v.requires_grad_(True) for k, v in O.seeded_state(shapes, seed=0).items()}
-    data = O.synthetic_batch(sample_batch, a.frames, 224, a.seq, seed=1234)
-    plan = O.synthetic_itm_plan(sample_batch)
-    best = None
-    for _ in range(iters):
+
+    def __init__(self, a, sample_batch):
+        from oracle import egovlp_oracle as O
+        self.O = O
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        shapes = O.key_shapes(T=a.frames)
+        self.sd = {k: v.requires_grad_(True) for k, v in O.seeded_state(shapes, seed=0).items()}
+        self.data = O.synthetic_batch(sample_batch, a.frames, 224, a.seq, seed=1234)
+        self.plan = O.synthetic_itm_plan(sample_batch)
+        self.n = sample_batch
+
+    def step(self):
         t0 = time.perf_counter()
-        out = O.pretrain_step(data, sd, 12, 12, 6, plan)
+        out = self.O.pretrain_step(self.data, self.sd, 12, 12, 6, self.plan)
         out["loss_total"].backward()
         dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-        for v in sd.values():
+        for v in self.sd.values():
             v.grad = None
-    return sample_batch / best, cores, best
+        return dt
+
+
+def cpu_port_clips_per_sec(a, sample_batch):
+    port = CpuPort(a, sample_batch)
+    dt = port.step()
+    return sample_batch / dt, port.cores, dt
 
 
 def run_reference(a, rank):
     if rank != 0:
         return
-    vals = []
     sample = a.cpu_sample
+    port = CpuPort(a, sample)
+    times = []
     for i in range(a.warmup + a.steps):
-        v, cores, dt = cpu_port_clips_per_sec(a, sample)
+        dt = port.step()
         if i >= a.warmup:
-            vals.append(v)
-    val = sum(vals) / len(vals)
+            times.append(dt)
+    mean_dt = sum(times) / len(times)
+    val, cores = sample / mean_dt, port.cores
     desc = "B=%d clips of the workload per step, fwd+bwd (no optimizer), fp32 oracle port, %d torch threads" % (sample, cores)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1e3 * sample / val, "higher_is_better": True, "scaling": "weak",
+            "warmup": a.warmup, "ms_per_step": 1e3 * mean_dt, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "sample": desc},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -271,10 +282,29 @@ def run_ours(a, rank, world, local_rank):
     }
     if cpu_val is not None:
         line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_desc}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout; libraries (NCCL's version banner, ...) also write to fd 1.
+    Point fd 1 at stderr for everybody else and keep a private handle on the real stdout for the result line."""
+    global _RESULT_OUT
+    real = os.dup(1)
+    os.dup2(2, 1)
+    _RESULT_OUT = os.fdopen(real, "w")
+
+
+_RESULT_OUT = None
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
