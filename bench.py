@@ -242,6 +242,10 @@ def run_ours(a, rank, world, local_rank):
     e2e_value = clips / (ms_e2e * 1e-3)
     flops, parts = step_flops(a.batch, a.frames, S=a.seq)
     sustained, burst, hbm, peak_src = peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tp):   # dram__bytes_read+write per GEMM launch from the committed ncu capture of the same step
+        traffic = json.load(open(tp)).get("gemm_dram_bytes_per_launch")
     gemm_t = sum(t for (r, k), (t, w, n) in prof.items() if k == "gemm")
     gemm_w = sum(w for (r, k), (t, w, n) in prof.items() if k == "gemm")
     gemm_n = sum(n for (r, k), (t, w, n) in prof.items() if k == "gemm")
@@ -278,7 +282,8 @@ def run_ours(a, rank, world, local_rank):
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all GEMMs of one step)", "achieved": achieved,
                      "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained, "peak_source": peak_src,
-                     "launches": gemm_n, "avg_launch_us": gemm_t / max(gemm_n, 1) * 1e6, "traffic": None},
+                     "launches": gemm_n, "avg_launch_us": gemm_t / max(gemm_n, 1) * 1e6, "traffic": traffic,
+                     "traffic_note": "avg DRAM bytes per GEMM launch, ncu capture profiles/r01_gemm_traffic.json"},
     }
     if cpu_val is not None:
         line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_desc}

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ a, 
 }
 
 // ------------------------------------------------------------------------------------------- column sum
-// out[c] (+)= scale * sum_r x[r, c].  Block = 64 columns x 8 row lanes; grid.y splits the rows; fp32 atomics.
+// out[c] (+)= scale * sum_r x[r, c].  Generic kernel: block = 64 columns x 8 row lanes; grid.y splits the rows.
 template <bool XBF>
 __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x, long long rows, int C, long long ld,
                                                      float* __restrict__ out, float scale,
@@ -90,6 +90,58 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x,
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
     const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < C) atomicAdd(out + c, s * scale * (scale_dev ? __ldg(scale_dev) : 1.0f));
+  }
+}
+
+// Streaming variant for wide bf16 matrices (C % 8 == 0, 16-byte aligned rows): a lane owns 8 adjacent columns
+// (one 16-byte load), a block 256 columns x 8 row lanes, 4 rows in flight per thread.  HBM-bound.
+__global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16* __restrict__ x, long long rows, int C, long long ld,
+                                                            float* __restrict__ out, float scale,
+                                                            const float* __restrict__ scale_dev) {
+  __shared__ float red[8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + 8 * tx;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (c0 < C) {
+    const long long rstep = (long long)gridDim.y * 8;
+    long long r = (long long)blockIdx.y * 8 + ty;
+    for (; r + 3 * rstep < rows; r += 4 * rstep) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(x + (r + k * rstep) * ld + c0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&u[k]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16(w[e]);
+          acc[2 * e] += f.x;
+          acc[2 * e + 1] += f.y;
+        }
+      }
+    }
+    for (; r < rows; r += rstep) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + r * ld + c0);
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        acc[2 * e] += f.x;
+        acc[2 * e + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[ty][8 * tx + e] = acc[e];
+  __syncthreads();
+  {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    const int c = blockIdx.x * 256 + threadIdx.x;
     if (c < C) atomicAdd(out + c, s * scale * (scale_dev ? __ldg(scale_dev) : 1.0f));
   }
 }
@@ -349,6 +401,15 @@ extern "C" int egv_colsum(const void* x, int x_is_bf16, int64_t rows, int C, int
     if (rc) return rc;
   }
   if (rows <= 0) return EGV_OK;
+  if (x_is_bf16 && C % 8 == 0 && ld % 8 == 0 && (((uintptr_t)x) & 15) == 0 && rows >= 256) {
+    const unsigned gx8 = (unsigned)cdiv(C, 256);
+    long long gy8 = cdiv(rows, 8 * 8);
+    const long long cap8 = cdiv((long long)sm_count() * 6, gx8);
+    if (gy8 > cap8) gy8 = cap8;
+    dim3 grid8(gx8, (unsigned)gy8);
+    colsum_bf16x8_kernel<<<grid8, 256, 0, s>>>((const bf16*)x, rows, C, ld, out, scale, scale_dev);
+    return check_launch("colsum_bf16x8_kernel");
+  }
   const unsigned gx = (unsigned)cdiv(C, 64);
   long long gy = cdiv(rows, 8 * 16);
   const long long cap = cdiv((long long)sm_count() * 8, gx);

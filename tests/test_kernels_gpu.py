@@ -354,6 +354,15 @@ def test_elementwise(K, R):
         K.colsum(mm[:, 1:769], c1)
         R.colsum(mm[:, 1:769], c2)
         check(c1, c2, 2e-5, "colsum odd offset")
+    wide = rnd(3000, 2304, seed=95)        # streaming bf16x8 path (aligned rows, C % 8 == 0)
+    c1, c2 = torch.ones(2304, device=DEV), torch.ones(2304, device=DEV)
+    K.colsum(wide, c1, accumulate=True, scale=2.0)
+    R.colsum(wide, c2, accumulate=True, scale=2.0)
+    check(c1, c2, 2e-5, "colsum bf16x8")
+    c1, c2 = torch.zeros(768, device=DEV), torch.zeros(768, device=DEV)
+    K.colsum(wide[:, 768:1536], c1)
+    R.colsum(wide[:, 768:1536], c2)
+    check(c1, c2, 2e-5, "colsum bf16x8 column slice")
     d1, d2 = torch.ones(1, device=DEV), torch.ones(1, device=DEV)
     K.dot(x, y1, d1, accumulate=True)
     R.dot(x, y1, d2, accumulate=True)
