@@ -340,13 +340,15 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
       constexpr bool FULL = decltype(full_t)::value;
       constexpr bool BIAS = decltype(bias_t)::value;
       if (MODE == MODE_FWD) {
+        // Without a key bias the softmax scale is folded into the exponent: max on the raw scores (scale > 0), then
+        // p = 2^(s*scale2 - m) as one FFMA + EX2 per element.
         float cm_lo = -1e30f, cm_hi = -1e30f;
 #pragma unroll
         for (int nt = 0; nt < KC / 8; ++nt) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int col = nt * 8 + 2 * tq + (e & 1);
-            float v = BIAS ? fmaf(s[nt][e], scale2, cf0[col]) : s[nt][e] * scale2;
+            float v = BIAS ? fmaf(s[nt][e], scale2, cf0[col]) : s[nt][e];
             if (!FULL) v = col < lim ? v : -1e30f;
             s[nt][e] = v;
             if (e < 2) cm_lo = fmaxf(cm_lo, v);
@@ -357,6 +359,10 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
         cm_lo = fmaxf(cm_lo, __shfl_xor_sync(0xffffffffu, cm_lo, 2));
         cm_hi = fmaxf(cm_hi, __shfl_xor_sync(0xffffffffu, cm_hi, 1));
         cm_hi = fmaxf(cm_hi, __shfl_xor_sync(0xffffffffu, cm_hi, 2));
+        if (!BIAS) {   // to the scaled (log2) domain; -1e30 * scale2 stays a huge negative number
+          cm_lo *= scale2;
+          cm_hi *= scale2;
+        }
         const float mn_lo = fmaxf(m_lo, cm_lo), mn_hi = fmaxf(m_hi, cm_hi);
         const float al_lo = ex2(m_lo - mn_lo), al_hi = ex2(m_hi - mn_hi);
         m_lo = mn_lo;
@@ -374,7 +380,8 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
         for (int nt = 0; nt < KC / 8; ++nt) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float pv = ex2(s[nt][e] - (e < 2 ? m_lo : m_hi));
+            const float mm = e < 2 ? m_lo : m_hi;
+            float pv = BIAS ? ex2(s[nt][e] - mm) : ex2(fmaf(s[nt][e], scale2, -mm));
             if (!FULL) {
               const int col = nt * 8 + 2 * tq + (e & 1);
               pv = col < lim ? pv : 0.f;

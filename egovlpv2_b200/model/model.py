@@ -9,7 +9,10 @@ Differences from the reference that do not change results:
   * the MLM pass skips the last video block, whose output the reference computes and discards (SURVEY.md Q6);
   * MLM / ITM cross-entropies are reduced as (local sum, local count) + a scalar all-reduce instead of all-gathering
     the [B*S, 50265] logits; the value and the gradients are identical (SURVEY.md Q9);
-  * ITM hard negatives are drawn on the device (same distribution, no per-row host sync).
+  * ITM hard negatives are drawn on the device (same distribution, no per-row host sync);
+  * the ITM pass reuses the MLM pass's activations of the unfused video blocks for the rows whose clip is unchanged
+    (the label-1 half of the batch) and recomputes them only for the label-0 half: the video side has no dropout or
+    stochastic depth, both passes use the same CLS token and weights, so the values are identical.
 Known gap: text-side dropout (p = 0.1 in the reference's train mode) is not applied (parity is defined in eval mode).
 """
 import os
@@ -172,6 +175,7 @@ class FrozenInTime(nn.Module):
             self.itm_score.apply(init_weights)
 
         self.itm_plan = None   # test hook: dict(labels, swap_video, neg_idx) replacing the random ITM plan
+        self.share_itm_prefix = True   # reuse MLM-pass activations of the unfused video blocks in the ITM pass (Q7-iii)
 
         if load_checkpoint not in ["", None]:
             checkpoint = torch.load(load_checkpoint, map_location='cpu')
@@ -214,10 +218,9 @@ class FrozenInTime(nn.Module):
     def compute_video(self, video_data):
         return self._proj(self.vid_proj, self.video_model(video_data))
 
-    def _fused_stack(self, video_data, input_ids, attention_mask, need_video_out=True):
-        """model.py:211-271 / 295-357: (num_layers - num_fuse_block) plain blocks per tower, then the fused pairs: video
-        block i reads the text entering layer i, text layer i reads the video ENTERING block i."""
-        vm, tm = self.video_model, self.text_model
+    def _video_prefix(self, video_data):
+        """tokens + the unfused video blocks (model.py:211-244): [B,T,3,H,W] -> [B,N,C] entering the first fused block"""
+        vm = self.video_model
         n, f = self.patches_per_frame, video_data.shape[1]
         x = vm.tokens(video_data, cls_token=self.cls_token)
         x = vm.pos_drop(x)
@@ -225,6 +228,17 @@ class FrozenInTime(nn.Module):
         es = (self.einops_from_space, self.einops_to_space, self.einops_from_time, self.einops_to_time)
         for blk in vm.blocks[:unfused]:
             x = blk(x, *es, time_n=n, space_f=f)
+        return x
+
+    def _fused_stack(self, video_data, input_ids, attention_mask, need_video_out=True, video_prefix=None):
+        """model.py:211-271 / 295-357: (num_layers - num_fuse_block) plain blocks per tower, then the fused pairs: video
+        block i reads the text entering layer i, text layer i reads the video ENTERING block i.
+        `video_prefix`: precomputed output of the unfused video blocks (see _video_prefix)."""
+        vm, tm = self.video_model, self.text_model
+        n, f = self.patches_per_frame, video_data.shape[1]
+        x = self._video_prefix(video_data) if video_prefix is None else video_prefix
+        unfused = self.num_text_layer - self.num_fuse_block
+        es = (self.einops_from_space, self.einops_to_space, self.einops_from_time, self.einops_to_time)
         h = tm.embeddings(input_ids=input_ids)
         ext = tm.get_extended_attention_mask(attention_mask, attention_mask.size(), h.device)
         for layer in tm.encoder.layer[:unfused]:
@@ -249,7 +263,8 @@ class FrozenInTime(nn.Module):
             if return_embeds:
                 ret.update({'text_embeds': text_embeddings, 'video_embeds': video_embeddings})
         if 'ITM' in self.task_names:
-            x, h = self._fused_stack(video_data, text_data['input_ids'], text_data['attention_mask'])
+            x, h = self._fused_stack(video_data, text_data['input_ids'], text_data['attention_mask'],
+                                     video_prefix=data.get('_video_prefix'))
             v = A.LayerNormRowsFn.apply(x[:, 0], self.norm.weight, self.norm.bias, self.norm.eps)
             v = self.pre_logits(v)
             # transform -> pooler (tanh) per modality, then fc on the concatenation (model.py:279-290)
@@ -258,7 +273,10 @@ class FrozenInTime(nn.Module):
             cls_feats = torch.cat([t_feats, v_feats], dim=-1)
             ret.update({"cross_attn_itm_logits": self.itm_score(cls_feats)})
         if 'MLM' in self.task_names:
-            _, h = self._fused_stack(video_data, data['text_mlm_ids'], text_data['attention_mask'], need_video_out=False)
+            prefix = self._video_prefix(video_data)
+            ret['_video_prefix_mlm'] = prefix   # consumed (and removed) by forward() for the ITM pass
+            _, h = self._fused_stack(video_data, data['text_mlm_ids'], text_data['attention_mask'], need_video_out=False,
+                                     video_prefix=prefix)
             if 'text_mlm_labels' in data and torch.is_grad_enabled():
                 names = A.MlmLossFn.NAMES
                 params = [self.get_parameter(nm) for nm in names]
@@ -317,8 +335,18 @@ class FrozenInTime(nn.Module):
             loss = loss + loss_mlm
             loss_dict.update({"loss_mlm": loss_mlm})
 
+        prefix_mlm = ret.pop('_video_prefix_mlm', None)
         if 'ITM' in task_names:
             data_itm, itm_labels = self._build_itm_batch(data, sim, mask_bool, temp, rank, allgather, n_gpu, args)
+            if self.share_itm_prefix and prefix_mlm is not None:
+                # label-1 rows keep their own clip: their unfused-block activations equal the MLM pass's.  Recompute
+                # only the label-0 rows (a fixed bsz - bsz//2 of them: static shapes, CUDA-graph safe).
+                n_neg = bsz - bsz // 2
+                order = torch.argsort(itm_labels, stable=True)            # label-0 rows first, then label-1 rows
+                redo_idx, keep_idx = order[:n_neg], order[n_neg:]
+                x_redo = self._video_prefix(data_itm['video'].index_select(0, redo_idx))
+                x_cat = torch.cat([x_redo, prefix_mlm.index_select(0, keep_idx)], 0)
+                data_itm['_video_prefix'] = x_cat.index_select(0, torch.argsort(order))
             ret = self.infer(data_itm, task_names='ITM', ret=ret)
             loss_sum, count = A.XentFn.apply(ret["cross_attn_itm_logits"], itm_labels.long())
             loss_itm = self._global_mean(loss_sum, count)

@@ -208,3 +208,29 @@ def test_gradient_arena_matches_autograd_path(golden_dir, fake_kernels):
         Fn.BF16 = old
         weights.cache().arena = None
         weights.cache().clear()
+
+
+def test_itm_prefix_reuse_is_exact(golden_dir, fake_kernels):
+    """Reusing the MLM pass's unfused video-block activations for the label-1 rows of the ITM pass
+    must not change any loss or gradient."""
+    old = Fn.BF16
+    Fn.BF16 = torch.float32
+    try:
+        fx, c, shapes, sd, data, plan = _golden(golden_dir)
+        res = []
+        for share in (False, True):
+            model = build_tiny(c)
+            model.load_state_dict(sd, strict=False)
+            model.eval()
+            model.share_itm_prefix = share
+            loss, ld, ret = _step(model, data, plan)
+            loss.backward()
+            assert "_video_prefix_mlm" not in ret
+            res.append(({k: v.item() for k, v in ld.items()}, {n: p.grad.clone() for n, p in model.named_parameters()}))
+        for k in res[0][0]:
+            assert abs(res[0][0][k] - res[1][0][k]) <= 1e-5 * max(1.0, abs(res[0][0][k])), k
+        for n in res[0][1]:
+            a, b = res[0][1][n], res[1][1][n]
+            assert (a - b).abs().max().item() <= 2e-5 * max(1e-3, a.abs().max().item()) + 1e-8, n
+    finally:
+        Fn.BF16 = old
