@@ -99,6 +99,31 @@ EGV_DEVINL void tma_load_2d(void* dst, const void* tmap, uint64_t* bar, int c0, 
       : "memory");
 }
 
+// 2-D tiled load multicast to every CTA of the cluster selected by `mask`: the tile lands at the same CTA-relative
+// shared-memory offset in each destination and completes bytes on the mbarrier at the same offset there.
+EGV_DEVINL void tma_load_2d_mc(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------- thread-block clusters
+EGV_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+EGV_DEVINL void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+EGV_DEVINL void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// shared::cluster address of `local_smem_addr` in CTA `rank` of the cluster
+EGV_DEVINL uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 EGV_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 EGV_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -127,6 +152,12 @@ EGV_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint3
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 EGV_DEVINL void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// same, on an mbarrier given by its shared::cluster address (e.g. the peer CTA's barrier obtained with mapa_shared)
+EGV_DEVINL void umma_commit_addr(uint32_t bar_cluster_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_cluster_addr)
                : "memory");
 }
 

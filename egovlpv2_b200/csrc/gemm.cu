@@ -14,6 +14,7 @@
 // Fallback path: a small SIMT kernel with identical semantics for shapes TMA cannot address
 // (row strides that are not multiples of 16 bytes) and for tiny problems.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -253,7 +254,11 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs of a cluster work on vertically adjacent output tiles
+// (same n-tile, m-tiles 2i and 2i+1) and share the B operand: each CTA loads one half of the B tile and multicasts it
+// into both shared memories, so a CTA pulls A (16 KB) + half of B per k-block through L2 instead of A + B.  The GEMMs
+// of this workload are L2->SM bandwidth-bound at 128 x 256 tiles (~1 GB per launch), which is what this relieves.
+template <int BN, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
@@ -277,6 +282,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+  const int first_item = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+  const int item_stride = CL > 1 ? (int)(gridDim.x / CL) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -285,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);   // a stage is free once every CTA of the cluster has consumed it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -296,6 +304,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) {   // barrier inits must be visible to the peer before it multicasts into / arrives on them
+    cluster_arrive();
+    cluster_wait();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -304,10 +316,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+      for (int w = first_item; w < p.total_items; w += item_stride) {
         const int ks = w % p.split_k;
         const int tile = w / p.split_k;
-        const int m0 = (tile / p.num_n_tiles) * BM;
+        const int m0 = ((tile / p.num_n_tiles) * CL + (int)cta_rank) * BM;
         const int n0 = (tile % p.num_n_tiles) * BN;
         const int kb0 = ks * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
@@ -323,7 +335,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           } else {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
           }
-          if (B_MN) {
+          if (CL > 1) {
+            // this CTA fetches half `cta_rank` of the B tile and multicasts it to both CTAs of the cluster
+            if (B_MN) {
+#pragma unroll
+              for (int jj = 0; jj < BN / 128; ++jj) {
+                const int j = (int)cta_rank * (BN / 128) + jj;
+                tma_load_2d_mc(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0, (uint16_t)0x3);
+              }
+            } else {
+              tma_load_2d_mc(sb + cta_rank * (Cfg::B_BYTES / 2), &tmap_b, &full_bar[stage], k0,
+                             n0 + (int)cta_rank * (BN / 2), (uint16_t)0x3);
+            }
+          } else if (B_MN) {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
           } else {
@@ -346,7 +370,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++it) {
+      const uint32_t peer = cta_rank ^ 1u;
+      for (int w = first_item; w < p.total_items; w += item_stride, ++it) {
         const int ks = w % p.split_k;
         const int kb0 = ks * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
@@ -368,6 +393,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                       (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (CL > 1) umma_commit_addr(mapa_shared(smem_u32(&empty_bar[stage]), peer));  // ... in the peer CTA too
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -384,10 +410,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float* stg = epi_smem + ew * EPI_STAGE_FLOATS;
     const float scale_total = p.scale * (p.scale_dev ? __ldg(p.scale_dev) : 1.0f);
     int it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++it) {
+    for (int w = first_item; w < p.total_items; w += item_stride, ++it) {
       const int ks = w % p.split_k;
       const int tile = w / p.split_k;
-      const int m0 = (tile / p.num_n_tiles) * BM;
+      const int m0 = ((tile / p.num_n_tiles) * CL + (int)cta_rank) * BM;
       const int n0 = (tile % p.num_n_tiles) * BN;
       const int as = it & 1;
       const uint32_t use = (uint32_t)(it >> 1) & 1u;
@@ -435,6 +461,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) {   // no CTA may exit while its peer can still multicast into its smem or arrive on its barriers
+    cluster_arrive();
+    cluster_wait();
+  }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -564,37 +594,57 @@ static int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint6
   return EGV_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CL>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return fail(EGV_ERR_CUDA, "gemm smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  int grid = p.total_items < sm_count() ? p.total_items : sm_count();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  const int units = sm_count() / CL;   // persistent: one CTA (or CTA pair) per SM (pair)
+  const int grid = (p.total_items < units ? p.total_items : units) * CL;
+  if (CL == 1) {
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) return fail(EGV_ERR_CUDA, "gemm cluster launch: %s", cudaGetErrorString(e));
+  }
   return check_launch("gemm_tc_kernel");
 }
 
-template <int BN>
+template <int BN, int CL>
 static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                           cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch_tc<BN, false, false>(ta, tb, p, s);
-  if (!a_mn && b_mn) return launch_tc<BN, false, true>(ta, tb, p, s);
-  if (a_mn && b_mn) return launch_tc<BN, true, true>(ta, tb, p, s);
-  return launch_tc<BN, true, false>(ta, tb, p, s);
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false, CL>(ta, tb, p, s);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true, CL>(ta, tb, p, s);
+  if (a_mn && b_mn) return launch_tc<BN, true, true, CL>(ta, tb, p, s);
+  return launch_tc<BN, true, false, CL>(ta, tb, p, s);
 }
 
 static int g_force_simt = 0;
+static int g_cluster_mode = -1;   // -1: env EGV_GEMM_CLUSTER (default 0 = off: measured slower); 0 off; 1 on
 
 }  // namespace egv
 
 using namespace egv;
 
 extern "C" void egv_gemm_force_simt(int on) { g_force_simt = on; }
+extern "C" void egv_gemm_set_cluster(int on) { g_cluster_mode = on; }
 
 extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -678,7 +728,12 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   p.k_blocks_per_split = (int)cdiv(p.k_blocks_total, split_k);
   split_k = (int)cdiv(p.k_blocks_total, p.k_blocks_per_split);
   p.split_k = split_k;
-  p.total_items = num_m_tiles * p.num_n_tiles * split_k;
+  // CTA pairs sharing the B tile (TMA multicast) when there are enough tile rows to pair up and fill the GPU
+  if (g_cluster_mode < 0) g_cluster_mode = getenv("EGV_GEMM_CLUSTER") ? atoi(getenv("EGV_GEMM_CLUSTER")) : 0;
+  const bool pair = g_cluster_mode > 0 && BN >= 128 && num_m_tiles >= 2 &&
+                    (long long)num_m_tiles * p.num_n_tiles * split_k >= sm_count() / 2;
+  const int m_units = pair ? (int)cdiv(num_m_tiles, 2) : num_m_tiles;
+  p.total_items = m_units * p.num_n_tiles * split_k;
   if (auto_split && !a->accumulate) {
     if (a->ld_out_f32 == a->N) {
       cudaMemsetAsync(a->out_f32, 0, (size_t)a->M * a->N * sizeof(float), stream);
@@ -694,12 +749,18 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   else rc = get_tensor_map(a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM, &ta);
   if (rc) return rc;
   if (b_mn) rc = get_tensor_map(a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK, &tb);
-  else rc = get_tensor_map(a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, (uint32_t)BN, &tb);
+  else rc = get_tensor_map(a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, (uint32_t)(pair ? BN / 2 : BN), &tb);
   if (rc) return rc;
 
+  if (pair) {
+    switch (BN) {
+      case 256: return dispatch_major<256, 2>(a_mn, b_mn, ta, tb, p, stream);
+      default: return dispatch_major<128, 2>(a_mn, b_mn, ta, tb, p, stream);
+    }
+  }
   switch (BN) {
-    case 256: return dispatch_major<256>(a_mn, b_mn, ta, tb, p, stream);
-    case 128: return dispatch_major<128>(a_mn, b_mn, ta, tb, p, stream);
-    default: return dispatch_major<64>(a_mn, b_mn, ta, tb, p, stream);
+    case 256: return dispatch_major<256, 1>(a_mn, b_mn, ta, tb, p, stream);
+    case 128: return dispatch_major<128, 1>(a_mn, b_mn, ta, tb, p, stream);
+    default: return dispatch_major<64, 1>(a_mn, b_mn, ta, tb, p, stream);
   }
 }

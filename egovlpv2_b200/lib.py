@@ -139,6 +139,9 @@ class Kernels:
     def force_simt(self, on):
         self.lib.egv_gemm_force_simt(int(bool(on)))
 
+    def set_cluster(self, on):
+        self.lib.egv_gemm_set_cluster(int(bool(on)))
+
     # ------------------------------------------------------------------ GEMM
     def gemm(self, layout, A, B, *, bias=None, aux=None, act=ACT_NONE, scale=1.0, scale_dev=None,
              residual=None, out_f32=None, out_bf16=None, out_pre=None, accumulate=False, split_k=1, colsum=None):

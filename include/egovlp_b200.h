@@ -76,6 +76,9 @@ typedef struct egv_gemm_args {
 int egv_gemm_bf16(const egv_gemm_args* args, egv_stream_t stream);
 /* test hook: route every GEMM through the SIMT fallback kernel (1) or restore normal dispatch (0) */
 void egv_gemm_force_simt(int on);
+/* 1: large problems run as 2-CTA clusters that share the B tile through TMA multicast; 0 (default): single CTAs.
+ * Measured in round 1: the cluster variant is 10-15 % slower at the cfg-3 shapes (lock-step stage recycling). */
+void egv_gemm_set_cluster(int on);
 
 /* LayerNorm ------------------------------------------------------------------------------------
  * nn.LayerNorm over the last dim C (video_transformer.py:196,207,210,115,304; roberta.py:161,336,417;

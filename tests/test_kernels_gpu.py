@@ -186,6 +186,24 @@ def test_gemm_linearity_full_size(K):
     check(out[idx], ref.to(torch.bfloat16), 4e-3, "sampled rows of the full-size GEMM")
 
 
+@pytest.mark.parametrize("layout", [L.GEMM_NT, L.GEMM_NN, L.GEMM_TN])
+def test_gemm_cluster_pairs_match_single_cta(K, layout):
+    """2-CTA clusters with the multicast B tile must give bit-identical tiles to the single-CTA kernel (odd number of
+    m-tiles: the last pair has one out-of-range tile)."""
+    M, N, Kd = 128 * 37 + 5, 1536, 328
+    A, B = _operands(layout, M, N, Kd, seed=61)
+    bias = rnd(N, dtype=torch.float32, seed=62)
+    o1 = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    o2 = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    K.set_cluster(True)
+    try:
+        K.gemm(layout, A, B, bias=bias, act=L.ACT_GELU, out_bf16=o1)
+    finally:
+        K.set_cluster(False)
+    K.gemm(layout, A, B, bias=bias, act=L.ACT_GELU, out_bf16=o2)
+    assert torch.equal(o1, o2)
+
+
 def test_gemm_argument_errors(K):
     A, B = rnd(64, 64), rnd(64, 64)
     with pytest.raises(RuntimeError):
