@@ -66,6 +66,29 @@ class VideoBlockFn(torch.autograd.Function):
         return (None, None, dx, dy, None) + grads
 
 
+class VideoBlockClsFn(torch.autograd.Function):
+    """SpaceTimeBlock whose output is consumed at the CLS row only (functional.video_block_cls_fwd): -> [B, C]."""
+
+    @staticmethod
+    def forward(ctx, cfg, w, x, y, y_bias, *params):
+        p = _pdict(cfg.names, params)
+        out, s = F_.video_block_cls_fwd(_K(), _f32c(x), p, w, cfg.H, cfg.T, cfg.Nf, y=None if y is None else _f32c(y),
+                                        y_bias=y_bias, eps=cfg.eps, save=True)
+        ctx.cfg, ctx.w, ctx.s, ctx.p = cfg, w, s, p
+        ctx.sink = _sinks(cfg.names, params)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        cfg = ctx.cfg
+        dx, dy, g = F_.video_block_cls_bwd(_K(), ctx.s, _f32c(d_out), ctx.p, ctx.w, cfg.H, cfg.T, cfg.Nf,
+                                           need_dx=ctx.needs_input_grad[2], sink=ctx.sink)
+        ctx.s = None
+        grads = tuple(_ret(g, n, ctx.p[n].shape) for n in cfg.names)
+        return (None, None, dx, dy, None) + grads
+
+
 class TextLayerFn(torch.autograd.Function):
     """cfg.names lists the reference parameter names; q/k/v (and cross k/v) are concatenated for the kernels and the
     concatenated gradients are split back here."""

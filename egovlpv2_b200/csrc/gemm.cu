@@ -243,7 +243,7 @@ EGV_DEVINL void epi_rows_scalar(const GemmParams& p, const float* stg, int lane,
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -251,7 +251,7 @@ struct GemmCfg {
   static constexpr int BAR_BYTES = 256;
   static constexpr int SLACK = 1024;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + SLACK;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // allocation: power of two
 };
 
 // CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs of a cluster work on vertically adjacent output tiles
@@ -637,6 +637,7 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
 }
 
 static int g_force_simt = 0;
+static int g_plan_mode = -1;      // -1: env EGV_GEMM_PLAN (default 1); 0: round-1 heuristic; 1: cost-model planner; 2: + 192-wide tiles
 static int g_cluster_mode = -1;   // -1: env EGV_GEMM_CLUSTER (default 0 = off: measured slower); 0 off; 1 on
 
 }  // namespace egv
@@ -645,6 +646,7 @@ using namespace egv;
 
 extern "C" void egv_gemm_force_simt(int on) { g_force_simt = on; }
 extern "C" void egv_gemm_set_cluster(int on) { g_cluster_mode = on; }
+extern "C" void egv_gemm_set_plan(int mode) { g_plan_mode = mode; }
 
 extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -707,11 +709,46 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   const int num_m_tiles = (int)cdiv(a->M, BM);
   p.k_blocks_total = (int)cdiv(a->K, BK);
   // Automatic split-K: a plain fp32 output whose tile grid cannot fill the GPU but whose reduction is long
-  // (weight gradients dW = dy^T x: 768..3072-wide outputs, K = B*N tokens).  The output is zeroed and the
-  // slices are combined with fp32 atomics.
-  bool auto_split = false;
-  if (split_k == 1 && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && a->act == EGV_ACT_NONE && !a->residual &&
-      !a->colsum) {
+  // (weight gradients dW = dy^T x: 768..3072-wide outputs, K = B*N tokens).  The output is zeroed (unless the caller
+  // accumulates anyway) and the slices are combined with fp32 vector reductions.
+  bool auto_split = false, planned = false;
+  const bool splittable = split_k == 1 && a->out_f32 && !a->out_bf16 && !a->out_pre_bf16 && a->act == EGV_ACT_NONE &&
+                          !a->residual && !a->colsum;
+  if (g_plan_mode < 0) g_plan_mode = getenv("EGV_GEMM_PLAN") ? atoi(getenv("EGV_GEMM_PLAN")) : 1;
+  if (splittable && g_plan_mode >= 1) {
+    // Plan (tile width, split) together.  Cost model in units of "one 128x256 k-block": a CTA processes
+    // ceil(items / SMs) items of ceil(kb / split) k-blocks each.  Narrow tiles cost less per k-block but run the
+    // SS-mode MMA against the shared-memory read limit (128x128: 8 KB per 64 cycles = 128 B/clk, the whole budget),
+    // hence the efficiency factors; every item also pays an un-overlapped epilogue (fp32 reductions of its tile).
+    if ((long long)num_m_tiles * cdiv(a->N, 256) < 2 * sm_count() && p.k_blocks_total >= 16) {
+      const int widths[3] = {256, 192, 128};
+      const double kcost[3] = {1.0, 0.75 / 0.92, 0.5 / 0.72};
+      const double ecost[3] = {8.0, 6.0, 4.0};
+      double best = 1e30;
+      int best_bn = BN, best_split = 1;
+      for (int wi = 0; wi < 3; ++wi) {
+        const int bn = widths[wi];
+        if (bn > 128 && a->N <= 128) continue;
+        if (bn == 192 && (a->N % 192 != 0 || g_plan_mode < 2)) continue;
+        const long long tiles = (long long)num_m_tiles * cdiv(a->N, bn);
+        const int max_split = (int)std::max<long long>(1, std::min<long long>(p.k_blocks_total / 8, 64));
+        for (int sp = 1; sp <= max_split; ++sp) {
+          const long long items = tiles * sp;
+          const long long rounds = cdiv(items, sm_count());
+          const double cost = (double)rounds * ((double)cdiv(p.k_blocks_total, sp) * kcost[wi] + ecost[wi]);
+          if (cost < best * 0.999) {
+            best = cost;
+            best_bn = bn;
+            best_split = sp;
+          }
+        }
+      }
+      BN = best_bn;
+      split_k = best_split;
+      auto_split = split_k > 1;
+      planned = true;
+    }
+  } else if (splittable) {
     if (BN == 256 && (long long)num_m_tiles * cdiv(a->N, 128) <= sm_count()) BN = 128;
     const long long tiles256 = (long long)num_m_tiles * cdiv(a->N, BN);
     if (tiles256 * 2 <= sm_count() && p.k_blocks_total >= 16) {
@@ -722,7 +759,7 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
     }
   }
   // prefer the 128-wide tile when the 256-wide one would leave most SMs idle
-  if (BN == 256 && (long long)num_m_tiles * cdiv(a->N, 256) * split_k < sm_count() / 2) BN = 128;
+  if (!planned && BN == 256 && (long long)num_m_tiles * cdiv(a->N, 256) * split_k < sm_count() / 2) BN = 128;
   p.num_n_tiles = (int)cdiv(a->N, BN);
   if (split_k > p.k_blocks_total) split_k = p.k_blocks_total;
   p.k_blocks_per_split = (int)cdiv(p.k_blocks_total, split_k);
@@ -730,7 +767,7 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   p.split_k = split_k;
   // CTA pairs sharing the B tile (TMA multicast) when there are enough tile rows to pair up and fill the GPU
   if (g_cluster_mode < 0) g_cluster_mode = getenv("EGV_GEMM_CLUSTER") ? atoi(getenv("EGV_GEMM_CLUSTER")) : 0;
-  const bool pair = g_cluster_mode > 0 && BN >= 128 && num_m_tiles >= 2 &&
+  const bool pair = g_cluster_mode > 0 && (BN == 128 || BN == 256) && num_m_tiles >= 2 &&
                     (long long)num_m_tiles * p.num_n_tiles * split_k >= sm_count() / 2;
   const int m_units = pair ? (int)cdiv(num_m_tiles, 2) : num_m_tiles;
   p.total_items = m_units * p.num_n_tiles * split_k;
@@ -760,6 +797,7 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   }
   switch (BN) {
     case 256: return dispatch_major<256, 1>(a_mn, b_mn, ta, tb, p, stream);
+    case 192: return dispatch_major<192, 1>(a_mn, b_mn, ta, tb, p, stream);
     case 128: return dispatch_major<128, 1>(a_mn, b_mn, ta, tb, p, stream);
     default: return dispatch_major<64, 1>(a_mn, b_mn, ta, tb, p, stream);
   }

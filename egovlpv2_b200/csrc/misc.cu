@@ -55,6 +55,17 @@ __global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ a, 
   }
 }
 
+// y[r, c] += x[r, c] for r < rows, c < C with independent row strides (the CLS rows of a [B, N, C] tensor).
+__global__ void __launch_bounds__(256) add_rows_kernel(float* __restrict__ y, long long ldy, const float* __restrict__ x,
+                                                       long long ldx, int rows, int C) {
+  const long long n = (long long)rows * C;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long r = i / C, c = i % C;
+    y[r * ldy + c] += x[r * ldx + c];
+  }
+}
+
 // ------------------------------------------------------------------------------------------- column sum
 // out[c] (+)= scale * sum_r x[r, c].  Generic kernel: block = 64 columns x 8 row lanes; grid.y splits the rows.
 template <bool XBF>
@@ -370,6 +381,12 @@ extern "C" int egv_axpy_f32(const float* a, const float* b, float alpha, const f
   if (!b || (!y && !y_bf16)) return fail(EGV_ERR_ARG, "axpy: null pointer");
   axpy_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(a, b, alpha, alpha_dev, y, (bf16*)y_bf16, n);
   return check_launch("axpy_kernel");
+}
+extern "C" int egv_add_rows_f32(float* y, int64_t ldy, const float* x, int64_t ldx, int rows, int C, egv_stream_t stream) {
+  if (rows <= 0 || C <= 0) return EGV_OK;
+  if (!y || !x) return fail(EGV_ERR_ARG, "add_rows: null pointer");
+  add_rows_kernel<<<grid_for((long long)rows * C, 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, x, ldx, rows, C);
+  return check_launch("add_rows_kernel");
 }
 extern "C" int egv_zero_f32(float* p, int64_t n, egv_stream_t stream) {
   if (n <= 0) return EGV_OK;

@@ -308,6 +308,181 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True, sink=None):
     return (d_x.view(B, N, C) if need_dx else None), dy, G.g
 
 
+# ----------------------------------------------------------------------------------------------- SpaceTimeBlock, CLS row only
+def video_block_cls_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=True):
+    """SpaceTimeBlock.forward for a block whose output is consumed at the CLS row only -- the LAST block of the
+    EgoNCE pass (video_transformer.py:391 `norm(x)[:, 0]`) and of the ITM pass (model.py:275-278), SURVEY.md Q6.
+    The time branch and LN1 still run on every token (the CLS query of the space attention attends the keys / values
+    of all tokens); everything after the space attention -- query projection, out-projection, gated video->text
+    cross-attention, MLP -- runs on the B CLS rows.  The CLS row of the result is identical to video_block_fwd's.
+    x [B,N,C] f32 -> (out [B,C] f32, saved)."""
+    B, N, C = x.shape
+    M = B * N
+    x2 = x.reshape(M, C)
+    x3 = x2.view(B, N, C)
+    s = types.SimpleNamespace(fused=y is not None, shape=(B, N, C), x=x2)
+    K.mark("video_block")
+    # ---- time attention branch on every token (identical to video_block_fwd)
+    s.ln3, s.mean3, s.rstd3 = _e(x, (M, C), BF16), _e(x, (M,), F32), _e(x, (M,), F32)
+    K.layernorm_fwd(x2, p["norm3.weight"], p["norm3.bias"], eps, y_bf16=s.ln3, mean=s.mean3, rstd=s.rstd3)
+    s.qkv_t = _e(x, (M, 3 * C), BF16)
+    K.gemm(GEMM_NT, s.ln3, w["timeattn.qkv.weight"], bias=p["timeattn.qkv.bias"], out_bf16=s.qkv_t)
+    s.o_t, s.lse_t = divided_attention_fwd(K, s.qkv_t.view(B, N, 3 * C), H, T, Nf, "time")
+    s.tr = _e(x, (M, C), F32)
+    K.gemm(GEMM_NT, s.o_t.view(M, C), w["timeattn.proj.weight"], bias=p["timeattn.proj.bias"], residual=x2, out_f32=s.tr)
+    # ---- space attention, CLS query only: keys / values of every token, the query of the B CLS rows
+    s.ln1, s.mean1, s.rstd1 = _e(x, (M, C), BF16), _e(x, (M,), F32), _e(x, (M,), F32)
+    K.layernorm_fwd(s.tr, p["norm1.weight"], p["norm1.bias"], eps, y_bf16=s.ln1, mean=s.mean1, rstd=s.rstd1)
+    wqkv, bqkv = w["attn.qkv.weight"], p["attn.qkv.bias"]
+    s.kv_s = _e(x, (M, 2 * C), BF16)
+    K.gemm(GEMM_NT, s.ln1, wqkv[C:], bias=bqkv[C:], out_bf16=s.kv_s)
+    ln1_cls = s.ln1.view(B, N, C)[:, 0]                       # [B, C] strided view (row stride N*C)
+    s.q_cls = _e(x, (B, 1, C), BF16)
+    K.gemm(GEMM_NT, ln1_cls, wqkv[:C], bias=bqkv[:C], out_bf16=s.q_cls.view(B, C))
+    s.spec_cls = AttnSpec(H=H, G=1, Lq=1, Lk=N - 1, q_row0=0, k_row0=1, k_istride=1, has_cls_key=True, cls_row=0,
+                          scale=(C // H) ** -0.5)
+    kv3 = s.kv_s.view(B, N, 2 * C)
+    s.o_cls, s.lse_cls = _e(x, (B, 1, C), BF16), _e(x, (B * H,), F32)
+    K.attention_fwd(s.spec_cls, s.q_cls, kv3[:, :, :C], kv3[:, :, C:], s.o_cls, s.lse_cls)
+    x_cls = x3[:, 0]                                          # [B, C] f32 strided view
+    s.sr = _e(x, (B, C), F32)
+    if y is None:
+        K.gemm(GEMM_NT, s.o_cls.view(B, C), w["attn.proj.weight"], bias=p["attn.proj.bias"], residual=x_cls, out_f32=s.sr)
+    else:
+        S, Ct = y.shape[1], y.shape[2]
+        s.a = _e(x, (B, C), BF16)
+        xa = _e(x, (B, C), F32)
+        K.gemm(GEMM_NT, s.o_cls.view(B, C), w["attn.proj.weight"], bias=p["attn.proj.bias"], residual=x_cls, out_f32=xa,
+               out_pre=s.a)
+        K.mark("xattn_i2t_fwd")
+        s.lnc, s.meanc, s.rstdc = _e(x, (B, C), BF16), _e(x, (B,), F32), _e(x, (B,), F32)
+        K.layernorm_fwd(s.a, p["attn.norm_i2t_i.weight"], p["attn.norm_i2t_i.bias"], eps, y_bf16=s.lnc, mean=s.meanc,
+                        rstd=s.rstdc)
+        s.q_c = _e(x, (B, 1, C), BF16)
+        K.gemm(GEMM_NT, s.lnc, w["attn.qkv_i2t.weight"], bias=p["attn.qkv_i2t.bias"], out_bf16=s.q_c.view(B, C))
+        s.y_bf = _e(x, (B * S, Ct), BF16)
+        K.cast(y.reshape(B * S, Ct), s.y_bf)
+        s.kv_t = _e(x, (B * S, 2 * C), BF16)
+        K.gemm(GEMM_NT, s.y_bf, w["attn.qkv_text_i2t.weight"], bias=p["attn.qkv_text_i2t.bias"], out_bf16=s.kv_t)
+        s.spec_c = AttnSpec(H=H, G=1, Lq=1, Lk=S, scale=(C // H) ** -0.5)
+        s.y_bias = y_bias
+        kvt3 = s.kv_t.view(B, S, 2 * C)
+        s.o_c, s.lse_c = _e(x, (B, 1, C), BF16), _e(x, (B * H,), F32)
+        K.attention_fwd(s.spec_c, s.q_c, kvt3[:, :, :C], kvt3[:, :, C:], s.o_c, s.lse_c, key_bias=y_bias)
+        s.c = _e(x, (B, C), BF16)
+        K.gemm(GEMM_NT, s.o_c.view(B, C), w["attn.proj_i2t.weight"], bias=p["attn.proj_i2t.bias"],
+               scale_dev=p["attn.alpha_i2t"], residual=xa, out_f32=s.sr, out_pre=s.c)
+    # ---- MLP on the CLS rows
+    K.mark("video_block")
+    s.ln2, s.mean2, s.rstd2 = _e(x, (B, C), BF16), _e(x, (B,), F32), _e(x, (B,), F32)
+    K.layernorm_fwd(s.sr, p["norm2.weight"], p["norm2.bias"], eps, y_bf16=s.ln2, mean=s.mean2, rstd=s.rstd2)
+    Hd = w["mlp.fc1.weight"].shape[0]
+    s.h_pre, s.h_act = _e(x, (B, Hd), BF16), _e(x, (B, Hd), BF16)
+    K.gemm(GEMM_NT, s.ln2, w["mlp.fc1.weight"], bias=p["mlp.fc1.bias"], act=ACT_GELU, out_bf16=s.h_act, out_pre=s.h_pre)
+    out = _e(x, (B, C), F32)
+    K.gemm(GEMM_NT, s.h_act, w["mlp.fc2.weight"], bias=p["mlp.fc2.bias"], residual=s.sr, out_f32=out)
+    return out, (s if save else None)
+
+
+def video_block_cls_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True, sink=None):
+    """Backward of video_block_cls_fwd.  d_out [B,C] f32 -> (dx [B,N,C] f32 or None, dy [B,S,Ct] f32 or None, grads)."""
+    B, N, C = s.shape
+    M = B * N
+    G = Grads(K, d_out, sink)
+    K.mark("video_block_bwd")
+    d_out = d_out.reshape(B, C).contiguous()
+    d_out_bf = _e(d_out, (B, C), BF16)
+    K.cast(d_out, d_out_bf)
+    # ---- MLP (B rows)
+    G.weight("mlp.fc2.weight", d_out_bf, s.h_act)
+    G.bias("mlp.fc2.bias", d_out_bf)
+    d_hpre = _e(d_out, s.h_pre.shape, BF16)
+    K.gemm(GEMM_NN, d_out_bf, w["mlp.fc2.weight"], aux=s.h_pre, act=ACT_GELU_BWD, out_bf16=d_hpre,
+           colsum=G.vec("mlp.fc1.bias", s.h_pre.shape[1]))
+    G.weight("mlp.fc1.weight", d_hpre, s.ln2)
+    d_ln2 = _e(d_out, (B, C), BF16)
+    K.gemm(GEMM_NN, d_hpre, w["mlp.fc1.weight"], out_bf16=d_ln2)
+    d_sr, d_sr_bf = _e(d_out, (B, C), F32), _e(d_out, (B, C), BF16)
+    cs_sr = _z(d_out, (C,)) if s.fused else G.vec("attn.proj.bias", C)
+    K.layernorm_bwd(d_ln2, s.sr, p["norm2.weight"], s.mean2, s.rstd2, add=d_out, dx=d_sr, dx_bf16=d_sr_bf,
+                    bf16_total=True, dgamma=G.vec("norm2.weight", C), dbeta=G.vec("norm2.bias", C), out_colsum=cs_sr)
+    dy = None
+    d_s_bf = d_sr_bf
+    if s.fused:
+        S, Ct = s.y_bf.shape[0] // B, s.y_bf.shape[1]
+        alpha = p["attn.alpha_i2t"]
+        K.mark("xattn_i2t_bwd")
+        G.scalar_dot("attn.alpha_i2t", d_sr, s.c)
+        G.weight("attn.proj_i2t.weight", d_sr_bf, s.o_c.view(B, C), scale_dev=alpha)
+        G.bias_from("attn.proj_i2t.bias", cs_sr, scale_dev=alpha)
+        d_oc = _e(d_out, (B, 1, C), BF16)
+        K.gemm(GEMM_NN, d_sr_bf, w["attn.proj_i2t.weight"], scale_dev=alpha, out_bf16=d_oc.view(B, C))
+        kvt3 = s.kv_t.view(B, S, 2 * C)
+        dq_c = _e(d_out, (B, 1, C), BF16)
+        dkv = _e(d_out, (B, S, 2 * C), BF16)
+        K.attention_bwd(s.spec_c, s.q_c, kvt3[:, :, :C], kvt3[:, :, C:], s.o_c, s.lse_c, d_oc, dq_c, dkv[:, :, :C],
+                        dkv[:, :, C:], _e(d_out, s.lse_c.shape, F32), key_bias=s.y_bias)
+        dq2, dkv2 = dq_c.view(B, C), dkv.view(B * S, 2 * C)
+        G.weight("attn.qkv_i2t.weight", dq2, s.lnc)
+        G.bias("attn.qkv_i2t.bias", dq2)
+        d_lnc = _e(d_out, (B, C), BF16)
+        K.gemm(GEMM_NN, dq2, w["attn.qkv_i2t.weight"], out_bf16=d_lnc)
+        G.weight("attn.qkv_text_i2t.weight", dkv2, s.y_bf)
+        G.bias("attn.qkv_text_i2t.bias", dkv2)
+        dy = _e(d_out, (B, S, Ct), F32)
+        K.gemm(GEMM_NN, dkv2, w["attn.qkv_text_i2t.weight"], out_f32=dy.view(B * S, Ct))
+        d_a_bf = _e(d_out, (B, C), BF16)
+        K.layernorm_bwd(d_lnc, s.a, p["attn.norm_i2t_i.weight"], s.meanc, s.rstdc, add=d_sr, dx=None, dx_bf16=d_a_bf,
+                        bf16_total=True, dgamma=G.vec("attn.norm_i2t_i.weight", C), dbeta=G.vec("attn.norm_i2t_i.bias", C),
+                        out_colsum=G.vec("attn.proj.bias", C))
+        d_s_bf = d_a_bf
+        K.mark("video_block_bwd")
+    # ---- space attention of the CLS query
+    G.weight("attn.proj.weight", d_s_bf, s.o_cls.view(B, C))
+    d_ocls = _e(d_out, (B, 1, C), BF16)
+    K.gemm(GEMM_NN, d_s_bf, w["attn.proj.weight"], out_bf16=d_ocls.view(B, C))
+    kv3 = s.kv_s.view(B, N, 2 * C)
+    d_qkv_cls = _e(d_out, (B, 1, 3 * C), BF16)                # [dq | dk | dv] of the CLS rows
+    d_kv = _e(d_out, (B, N, 2 * C), BF16)                     # every row written by the CLS-query backward
+    dkv_cls = _z(d_out, (B * H * 128,))
+    K.attention_bwd(s.spec_cls, s.q_cls, kv3[:, :, :C], kv3[:, :, C:], s.o_cls, s.lse_cls, d_ocls, d_qkv_cls[:, :, :C],
+                    d_kv[:, :, :C], d_kv[:, :, C:], _e(d_out, s.lse_cls.shape, F32), dkv_cls=dkv_cls)
+    K.attention_cls_finalize(dkv_cls, d_kv[:, :, :C], d_kv[:, :, C:], H, cls_row=0, accumulate=False)
+    d_qkv_cls[:, 0, C:].copy_(d_kv[:, 0])                     # data movement only (B rows)
+    wqkv = w["attn.qkv.weight"]
+    ln1_cls = s.ln1.view(B, N, C)[:, 0]
+    dq2, d_kv2 = d_qkv_cls.view(B, 3 * C)[:, :C], d_kv.view(M, 2 * C)
+    gw = G.full("attn.qkv.weight", (3 * C, C))
+    K.gemm(GEMM_TN, dq2, ln1_cls, out_f32=gw[:C], accumulate=True)
+    K.gemm(GEMM_TN, d_kv2, s.ln1, out_f32=gw[C:], accumulate=True)
+    gb = G.full("attn.qkv.bias", (3 * C,))
+    K.colsum(dq2, gb[:C], accumulate=True)
+    K.colsum(d_kv2, gb[C:], accumulate=True)
+    d_ln1 = _e(d_out, (M, C), BF16)
+    K.gemm(GEMM_NN, d_kv2, wqkv[C:], out_bf16=d_ln1)
+    # the CLS rows also carry the query path: d_ln1[cls] = [dq | dk | dv][cls] @ W_qkv (overwrites the kv-only value)
+    K.gemm(GEMM_NN, d_qkv_cls.view(B, 3 * C), wqkv, out_bf16=d_ln1.view(B, N, C)[:, 0])
+    # d_tr = LN1'(d_ln1);  d_x = d_tr (+ d_sr on the CLS rows: x feeds sr there directly)
+    d_x, d_tr_bf = _e(d_out, (M, C), F32), _e(d_out, (M, C), BF16)
+    K.layernorm_bwd(d_ln1, s.tr, p["norm1.weight"], s.mean1, s.rstd1, add=None, dx=d_x, dx_bf16=d_tr_bf,
+                    bf16_total=False, dgamma=G.vec("norm1.weight", C), dbeta=G.vec("norm1.bias", C),
+                    out_colsum=G.vec("timeattn.proj.bias", C))
+    d_x_cls = d_x.view(B, N, C)[:, 0]
+    K.axpy_rows(d_x_cls, d_sr)
+    # ---- time attention (identical to video_block_bwd)
+    G.weight("timeattn.proj.weight", d_tr_bf, s.o_t.view(M, C))
+    d_ot = _e(d_out, (B, N, C), BF16)
+    K.gemm(GEMM_NN, d_tr_bf, w["timeattn.proj.weight"], out_bf16=d_ot.view(M, C))
+    d_qkv = divided_attention_bwd(K, s.qkv_t.view(B, N, 3 * C), s.o_t, s.lse_t, d_ot, H, T, Nf, "time").view(M, 3 * C)
+    G.weight("timeattn.qkv.weight", d_qkv, s.ln3)
+    G.bias("timeattn.qkv.bias", d_qkv)
+    d_ln3 = _e(d_out, (M, C), BF16)
+    K.gemm(GEMM_NN, d_qkv, w["timeattn.qkv.weight"], out_bf16=d_ln3)
+    K.layernorm_bwd(d_ln3, s.x, p["norm3.weight"], s.mean3, s.rstd3, add=d_x, dx=d_x if need_dx else None,
+                    dgamma=G.vec("norm3.weight", C), dbeta=G.vec("norm3.bias", C))
+    return (d_x.view(B, N, C) if need_dx else None), dy, G.g
+
+
 # ----------------------------------------------------------------------------------------------- RobertaLayer
 TEXT_LAYER_PARAMS = ["attention.self.query.weight", "attention.self.query.bias", "attention.self.key.weight",
                      "attention.self.key.bias", "attention.self.value.weight", "attention.self.value.bias",

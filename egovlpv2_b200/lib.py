@@ -142,6 +142,9 @@ class Kernels:
     def set_cluster(self, on):
         self.lib.egv_gemm_set_cluster(int(bool(on)))
 
+    def set_plan(self, mode):
+        self.lib.egv_gemm_set_plan(int(mode))
+
     # ------------------------------------------------------------------ GEMM
     def gemm(self, layout, A, B, *, bias=None, aux=None, act=ACT_NONE, scale=1.0, scale_dev=None,
              residual=None, out_f32=None, out_bf16=None, out_pre=None, accumulate=False, split_k=1, colsum=None):
@@ -288,6 +291,13 @@ class Kernels:
         assert y_bf16 is None or (y_bf16.dtype == torch.bfloat16 and y_bf16.is_contiguous())
         self._check(self.lib.egv_axpy_f32(_p(a), _p(b), c_float(alpha), _p(alpha_dev), _p(y), _p(y_bf16),
                                           c_int64(b.numel()), self._stream()))
+
+    def axpy_rows(self, y, x):
+        """y[r, :] += x[r, :] on 2-D f32 views with unit inner stride (rows may be strided)."""
+        assert y.dim() == 2 and x.dim() == 2 and y.shape == x.shape and y.stride(1) == 1 and x.stride(1) == 1
+        assert y.dtype == torch.float32 and x.dtype == torch.float32
+        self._check(self.lib.egv_add_rows_f32(_p(y), c_int64(y.stride(0)), _p(x), c_int64(x.stride(0)), y.shape[0],
+                                              y.shape[1], self._stream()))
 
     def act_grad(self, dy, aux, act, out_bf16, scale=1.0, scale_dev=None):
         assert dy.is_contiguous() and out_bf16.is_contiguous() and out_bf16.dtype == torch.bfloat16

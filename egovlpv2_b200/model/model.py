@@ -26,7 +26,7 @@ from torch import nn
 from .. import autograd as A
 from ..lib import ACT_NONE, ACT_RELU, ACT_TANH
 from ..weights import cache
-from . import heads, roberta
+from . import heads, roberta, video_transformer
 from .roberta import RobertaConfig, RobertaModel
 from .video_transformer import SpaceTimeTransformer
 
@@ -247,7 +247,9 @@ class FrozenInTime(nn.Module):
         for i in range(unfused, self.num_text_layer):
             fuse_x = None
             if need_video_out or i < last:   # the last video block's output is unused by the MLM head
-                fuse_x = vm.blocks[i](x, *es, y=h, y_mask=ext, time_n=n, space_f=f)
+                # ... and the ITM head reads only its CLS row (model.py:275-278)
+                fuse_x = vm.blocks[i](x, *es, y=h, y_mask=ext, time_n=n, space_f=f,
+                                      cls_only=video_transformer.CLS_ONLY_LAST_BLOCK and i == last)
             h = tm.encoder.layer[i](h, ext, encoder_hidden_states=x, last_norm=True)[0]
             x = fuse_x
         return x, h

@@ -5,6 +5,7 @@ Same module tree and parameter names as the reference; `S
 The nn.Linear / nn.LayerNorm / nn.Conv2d children are parameter containers only: their own forward is never
 called on the hot path.
 """
+import os
 from functools import partial
 
 import torch
@@ -15,6 +16,9 @@ from .. import functional as Fn
 from ..weights import cache
 
 NUM_FUSE_BLOCK = 6
+# the last block of a pass that consumes only `x[:, 0]` computes its post-attention part on the CLS rows only
+# (exactly the same CLS row; set EGV_CLS_ONLY_LAST=0 to run the full block)
+CLS_ONLY_LAST_BLOCK = os.environ.get("EGV_CLS_ONLY_LAST", "1") != "0"
 DIM_TEXT = 768   # video_transformer.py:33
 
 
@@ -125,7 +129,9 @@ class SpaceTimeBlock(nn.Module):
         return names, [self.get_parameter(n) for n in names]
 
     def forward(self, x, einops_from_space, einops_to_space, einops_from_time, einops_to_time, time_n, space_f, y=None,
-                y_mask=None):
+                y_mask=None, cls_only=False):
+        """`cls_only` (extension, default off): return only the CLS row, [B, 1, C] -- for a block whose output is
+        consumed as `x[:, 0]` (the last block of the EgoNCE and ITM passes); the row equals the full forward's."""
         fused = y is not None
         if fused and not self.has_fusion:
             raise AttributeError("this SpaceTimeBlock was built without cross-attention parameters (dim_text=None)")
@@ -135,6 +141,8 @@ class SpaceTimeBlock(nn.Module):
         if fused and y_mask is not None:
             y_bias = y_mask.reshape(y.shape[0], -1).float().contiguous()   # [B,1,1,S] additive mask -> [B,S]
         cfg = A.cfg(names=names, H=self.num_heads, T=space_f, Nf=time_n, eps=self._eps)
+        if cls_only:
+            return A.VideoBlockClsFn.apply(cfg, w, x, y, y_bias, *params).unsqueeze(1)
         return A.VideoBlockFn.apply(cfg, w, x, y, y_bias, *params)
 
 
@@ -215,9 +223,10 @@ class SpaceTimeTransformer(nn.Module):
         b, curr_frames = x.shape[:2]
         x = self.tokens(x)
         n, f = self.patches_per_frame, curr_frames
-        for blk in self.blocks:
+        for i, blk in enumerate(self.blocks):
+            # only the CLS row of the last block is consumed below: its per-token tail is skipped
             x = blk(x, self.einops_from_space, self.einops_to_space, self.einops_from_time, self.einops_to_time,
-                    time_n=n, space_f=f)
+                    time_n=n, space_f=f, cls_only=CLS_ONLY_LAST_BLOCK and i == len(self.blocks) - 1)
         # only the CLS row of the final norm is consumed (video_transformer.py:391)
         x = A.LayerNormRowsFn.apply(x[:, 0], self.norm.weight, self.norm.bias, self.norm.eps)
         return self.pre_logits(x)

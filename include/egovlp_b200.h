@@ -79,6 +79,9 @@ void egv_gemm_force_simt(int on);
 /* 1: large problems run as 2-CTA clusters that share the B tile through TMA multicast; 0 (default): single CTAs.
  * Measured in round 1: the cluster variant is 10-15 % slower at the cfg-3 shapes (lock-step stage recycling). */
 void egv_gemm_set_cluster(int on);
+/* tile-width / split-K planner for plain fp32-output GEMMs (weight gradients): 0 = round-1 heuristic, 1 = cost model
+ * over {256,128}-wide tiles x split (default), 2 = also 192-wide tiles.  Env EGV_GEMM_PLAN sets the default. */
+void egv_gemm_set_plan(int mode);
 
 /* LayerNorm ------------------------------------------------------------------------------------
  * nn.LayerNorm over the last dim C (video_transformer.py:196,207,210,115,304; roberta.py:161,336,417;
@@ -149,6 +152,9 @@ int egv_dot(const void* a, int a_is_bf16, const void* b, int b_is_bf16, int64_t 
  * writes y (f32) and/or y_bf16 */
 int egv_axpy_f32(const float* a, const float* b, float alpha, const float* alpha_dev, float* y, void* y_bf16, int64_t n,
                  egv_stream_t stream);
+/* y[r, 0:C] += x[r, 0:C] for r < rows; ldy / ldx = row strides (the residual add on the CLS rows of a [B, N, C]
+ * stream when only the CLS output of a block is consumed: video_transformer.py:391, model.py:275) */
+int egv_add_rows_f32(float* y, int64_t ldy, const float* x, int64_t ldx, int rows, int C, egv_stream_t stream);
 
 /* Patch embedding (video_transformer.py:78-83, 354-372; model.py:211-232) -------------------------
  * im2col: video f32 [BT, 3, H, W] -> bf16 [BT*gh*gw, 3*p*p] (column order c,i,j = Conv2d weight order) */

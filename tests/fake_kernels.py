@@ -203,6 +203,10 @@ class FakeKernels:
         if y_bf16 is not None:
             y_bf16.copy_(r.reshape(y_bf16.shape))
 
+    def axpy_rows(self, y, x):
+        self._launches += 1
+        y.add_(x)
+
     def act_grad(self, dy, aux, act, out_bf16, scale=1.0, scale_dev=None):
         self._launches += 1
         v = dy.float()

@@ -225,3 +225,37 @@ def test_mlp_chain_and_mlm_head(sd, mode):
     assert rel(dh, hr.grad) <= tol(mode, True)
     for n in names:
         assert rel(grads[n].reshape(-1), sdr[n].grad.reshape(-1)) <= tol(mode, True), n
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_video_block_cls_only(sd, mode, fused):
+    """The CLS-only variant of the block (last block of the EgoNCE / ITM passes) against autograd through
+    the oracle's FULL block with the loss reading only the CLS row."""
+    K = FakeKernels()
+    prefix = "video_model.blocks.6."
+    names = Fn.VIDEO_BLOCK_PARAMS + (Fn.VIDEO_FUSE_PARAMS if fused else [])
+    p = block_params(sd, prefix, names)
+    w = operand_copies(p)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, N, C, generator=g)
+    y = torch.randn(B, S, C, generator=g) if fused else None
+    am, yb = mask_bias([S, 5, 3])
+    d_cls = torch.randn(B, C, generator=g)
+    out, saved = Fn.video_block_cls_fwd(K, x, p, w, HEADS, T, NF, y=y, y_bias=yb if fused else None)
+    dx, dy, grads = Fn.video_block_cls_bwd(K, saved, d_cls, p, w, HEADS, T, NF)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    yr = y.clone().requires_grad_(True) if fused else None
+    ref = O.space_time_block(xr, sdr, prefix, HEADS, T, NF, y=yr, y_mask=O.extended_mask(am) if fused else None)
+    ref[:, 0].backward(d_cls)
+    assert out.shape == (B, C)
+    assert rel(out, ref[:, 0]) <= tol(mode), rel(out, ref[:, 0])
+    assert rel(dx, xr.grad) <= tol(mode, True), rel(dx, xr.grad)
+    if fused:
+        assert rel(dy, yr.grad) <= tol(mode, True), rel(dy, yr.grad)
+    for n in names:
+        r = rel(grads[n].reshape(-1), sdr[prefix + n].grad.reshape(-1))
+        assert r <= tol(mode, True), (n, r)
+    # and the full kernel sequence gives the same CLS row
+    full, _ = Fn.video_block_fwd(K, x, p, w, HEADS, T, NF, y=y, y_bias=yb if fused else None, save=False)
+    assert rel(out, full[:, 0]) <= tol(mode)

@@ -1,0 +1,141 @@
+"""One launch of every hot kernel at the cfg-3 shapes between cudaProfilerStart/Stop -- the target of
+`ncu --set full --profile-from-start off` (tools/run_prof.sh).  PROF_ONLY=<substring list, comma separated> filters."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from egovlpv2_b200 import lib as L  # noqa: E402
+
+K = L.Kernels()
+dev = "cuda"
+B, T, Nf, H, S = 8, 16, 196, 12, 32
+C = H * 64
+N = 1 + T * Nf
+M = B * N
+sc = 64 ** -0.5
+ONLY = [s for s in os.environ.get("PROF_ONLY", "").split(",") if s]
+BF = torch.bfloat16
+
+
+def want(name):
+    return not ONLY or any(s in name for s in ONLY)
+
+
+jobs = []
+qkv = torch.randn(B, N, 3 * C, device=dev).to(BF)
+q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+specs = {
+    "time": L.AttnSpec(H=H, G=Nf, Lq=T, Lk=T, q_row0=1, q_gstride=1, q_istride=Nf, k_row0=1, k_gstride=1, k_istride=Nf,
+                       has_cls_key=True, cls_row=0, scale=sc),
+    "space": L.AttnSpec(H=H, G=T, Lq=Nf, Lk=Nf, q_row0=1, q_gstride=Nf, q_istride=1, k_row0=1, k_gstride=Nf, k_istride=1,
+                        has_cls_key=True, cls_row=0, scale=sc),
+    "cls": L.AttnSpec(H=H, G=1, Lq=1, Lk=N - 1, q_row0=0, k_row0=1, has_cls_key=True, cls_row=0, scale=sc),
+}
+o = torch.zeros(B, N, C, device=dev, dtype=BF)
+d_o = torch.randn(B, N, C, device=dev).to(BF)
+dqkv = torch.zeros_like(qkv)
+cls_acc = torch.zeros(B * H * 128, device=dev)
+for name, spec in specs.items():
+    lse = torch.zeros(B * H * spec.G * spec.Lq, device=dev)
+    jobs.append(("attn_%s_fwd" % name, lambda spec=spec, lse=lse: K.attention_fwd(spec, q, k, v, o, lse)))
+    jobs.append(("attn_%s_bwd" % name, lambda spec=spec, lse=lse, name=name: K.attention_bwd(
+        spec, q, k, v, o, lse, d_o, dqkv[:, :, :C], dqkv[:, :, C:2 * C], dqkv[:, :, 2 * C:], torch.empty_like(lse),
+        dkv_cls=cls_acc, dkv_accumulate=(name == "cls"))))
+xq = torch.randn(B, N, C, device=dev).to(BF)
+tkv = torch.randn(B, S, 2 * C, device=dev).to(BF)
+kb = torch.zeros(B, S, device=dev)
+i2t = L.AttnSpec(H=H, G=1, Lq=N, Lk=S, scale=sc)
+lse_c = torch.zeros(B * H * N, device=dev)
+dq_c = torch.zeros_like(xq)
+dkv_c = torch.zeros(B, S, 2 * C, device=dev, dtype=BF)
+jobs.append(("attn_i2t_fwd", lambda: K.attention_fwd(i2t, xq, tkv[:, :, :C], tkv[:, :, C:], o, lse_c, key_bias=kb)))
+jobs.append(("attn_i2t_bwd", lambda: K.attention_bwd(i2t, xq, tkv[:, :, :C], tkv[:, :, C:], o, lse_c, d_o, dq_c,
+                                                     dkv_c[:, :, :C], dkv_c[:, :, C:], torch.empty_like(lse_c), key_bias=kb)))
+t2i = L.AttnSpec(H=H, G=1, Lq=S, Lk=N, scale=sc)
+tq = torch.randn(B, S, C, device=dev).to(BF)
+to = torch.zeros(B, S, C, device=dev, dtype=BF)
+lse_x = torch.zeros(B * H * S, device=dev)
+dtq = torch.zeros_like(tq)
+jobs.append(("attn_t2i_fwd", lambda: K.attention_fwd(t2i, tq, k, v, to, lse_x)))
+jobs.append(("attn_t2i_bwd", lambda: K.attention_bwd(t2i, tq, k, v, to, lse_x, torch.randn(B, S, C, device=dev).to(BF), dtq,
+                                                     dqkv[:, :, C:2 * C], dqkv[:, :, 2 * C:], torch.empty_like(lse_x))))
+
+# LayerNorm
+x32 = torch.randn(M, C, device=dev)
+dy16 = torch.randn(M, C, device=dev).to(BF)
+add32 = torch.randn(M, C, device=dev)
+g = torch.randn(C, device=dev)
+mean, rstd = torch.zeros(M, device=dev), torch.ones(M, device=dev)
+dx32, dx16 = torch.empty(M, C, device=dev), torch.empty(M, C, device=dev, dtype=BF)
+dg, db, cs = torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+y16 = torch.empty(M, C, device=dev, dtype=BF)
+jobs.append(("ln_fwd", lambda: K.layernorm_fwd(x32, g, g, 1e-5, y_bf16=y16, mean=mean, rstd=rstd)))
+jobs.append(("ln_bwd", lambda: K.layernorm_bwd(dy16, x32, g, mean, rstd, add=add32, dx=dx32, dx_bf16=dx16, bf16_total=True,
+                                               dgamma=dg, dbeta=db, out_colsum=cs)))
+
+# GEMMs
+def gemm_job(name, layout, Mm, Nn, Kk, **kw):
+    if layout == L.GEMM_NT:
+        A, Bm = torch.randn(Mm, Kk, device=dev).to(BF), torch.randn(Nn, Kk, device=dev).to(BF)
+    elif layout == L.GEMM_NN:
+        A, Bm = torch.randn(Mm, Kk, device=dev).to(BF), torch.randn(Kk, Nn, device=dev).to(BF)
+    else:
+        A, Bm = torch.randn(Kk, Mm, device=dev).to(BF), torch.randn(Kk, Nn, device=dev).to(BF)
+    args = {}
+    if kw.get("bias"):
+        args["bias"] = torch.randn(Nn, device=dev)
+    if kw.get("res"):
+        args["residual"] = torch.randn(Mm, Nn, device=dev)
+    if kw.get("f32"):
+        args["out_f32"] = torch.zeros(Mm, Nn, device=dev)
+    if kw.get("bf16"):
+        args["out_bf16"] = torch.empty(Mm, Nn, device=dev, dtype=BF)
+    if kw.get("pre"):
+        args["out_pre"] = torch.empty(Mm, Nn, device=dev, dtype=BF)
+    if kw.get("aux"):
+        args["aux"] = torch.randn(Mm, Nn, device=dev).to(BF)
+    if kw.get("colsum"):
+        args["colsum"] = torch.zeros(Nn, device=dev)
+    args["act"] = kw.get("act", L.ACT_NONE)
+    args["accumulate"] = kw.get("acc", False)
+    jobs.append((name, lambda: K.gemm(layout, A, Bm, **args)))
+
+
+gemm_job("gemm_qkv_fwd", L.GEMM_NT, M, 3 * C, C, bias=1, bf16=1)
+gemm_job("gemm_proj_fwd_res", L.GEMM_NT, M, C, C, bias=1, res=1, f32=1)
+gemm_job("gemm_fc1_gelu", L.GEMM_NT, M, 4 * C, C, bias=1, bf16=1, pre=1, act=L.ACT_GELU)
+gemm_job("gemm_fc2_res", L.GEMM_NT, M, C, 4 * C, bias=1, res=1, f32=1)
+gemm_job("gemm_dgrad_fc2_gelubwd", L.GEMM_NN, M, 4 * C, C, aux=1, bf16=1, act=L.ACT_GELU_BWD, colsum=1)
+gemm_job("gemm_dgrad_fc1", L.GEMM_NN, M, C, 4 * C, bf16=1)
+gemm_job("gemm_dgrad_qkv", L.GEMM_NN, M, C, 3 * C, bf16=1)
+gemm_job("gemm_wgrad_qkv", L.GEMM_TN, 3 * C, C, M, f32=1, acc=1)
+gemm_job("gemm_wgrad_proj", L.GEMM_TN, C, C, M, f32=1, acc=1)
+gemm_job("gemm_wgrad_fc1", L.GEMM_TN, 4 * C, C, M, f32=1, acc=1)
+gemm_job("gemm_wgrad_fc2", L.GEMM_TN, C, 4 * C, M, f32=1, acc=1)
+
+jobs = [(n, f) for n, f in jobs if want(n)]
+for n, f in jobs:      # warm-up (module load, smem attributes, tensor-map cache)
+    f()
+torch.cuda.synchronize()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+torch.cuda.profiler.start()
+for n, f in jobs:
+    f()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+# plain timing (CUDA events, L2 flushed) for the same list -- meaningless under ncu, useful without it
+if not os.environ.get("PROF_NO_TIMING"):
+    for n, f in jobs:
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            f()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        ts.sort()
+        print("%-28s %9.1f us" % (n, ts[2]))
