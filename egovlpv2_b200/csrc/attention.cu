@@ -13,41 +13,9 @@
 
 #include <type_traits>
 
-#include "common.cuh"
-#include "host_common.h"
+#include "attention.cuh"
 
 namespace egv {
-
-enum { MODE_FWD = 0, MODE_DQ = 1, MODE_DKV = 2 };
-constexpr int HD = 64;       // head dim
-constexpr int LDS = 72;      // smem row stride in bf16 (144 B: conflict-free ldmatrix)
-constexpr float LOG2E = 1.4426950408889634f;
-
-// 2^x on the XU pipe in one instruction (inputs here are <= 0 or differences of bounded log-sum-exps)
-EGV_DEVINL float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-struct AttnP {
-  int B, H, G, Lq, LkT;  // LkT = keys per group including the optional CLS key
-  const bf16* q; long long ldq, q_bstride; int q_row0, q_gstride, q_istride;
-  const bf16* k; const bf16* v; long long ldkv, kv_bstride; int k_row0, k_gstride, k_istride;
-  int has_cls, cls_row;
-  const float* key_bias;
-  float scale;
-  bf16* o; long long ldo, o_bstride;
-  float* lse;
-  const bf16* d_o;
-  bf16* dq; long long lddq;
-  bf16* dk; bf16* dv; long long lddkv;
-  float* delta;
-  float* dkv_cls;
-  int dkv_accumulate;
-  int row_tiles;       // tiles of the row side per group
-  long long items;     // B*G*H*row_tiles
-};
 
 EGV_DEVINL long long q_row(const AttnP& a, int b, int g, int i) {
   return (long long)b * a.q_bstride + a.q_row0 + (long long)g * a.q_gstride + (long long)i * a.q_istride;
@@ -984,6 +952,11 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
   const long long groups = (long long)a.B * a.H * a.G;
   const bool small = n_rows <= 32 && n_str <= 64 && groups >= 1024;
   cudaError_t e = cudaSuccess;
+  {
+    // large contiguous groups (space attention): group-resident TMA-fed kernels (attention_group.cu)
+    const int r = launch_group_attention(MODE, a, stream);
+    if (r != 0) return r < 0 ? r : EGV_OK;
+  }
   if (small) {
     constexpr int KC = 32;
     a.row_tiles = (int)cdiv(n_rows, 16);

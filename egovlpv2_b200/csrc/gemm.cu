@@ -563,8 +563,8 @@ struct MapKeyHash {
 };
 
 // bf16 2-D tensor map: `inner` contiguous elements, `outer` rows `ld` elements apart, 128B swizzle.
-static int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                          uint32_t box_outer, CUtensorMap* out) {
+int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                   uint32_t box_outer, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key{ptr, inner, outer, ld, box_inner, box_outer};

@@ -1,5 +1,7 @@
 // egv_layernorm_fwd / egv_layernorm_bwd: nn.LayerNorm over the last dimension, one warp per row, fp32 statistics.
 // HBM-bound: each row is read once (kept in registers for C <= 1024) and written once.
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_common.h"
 
@@ -82,8 +84,14 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x,
 // written to dx_bf16 (bias gradient of the Linear that produced this LayerNorm's input branch).
 // One warp per row.  The three column accumulators live in per-warp shared memory (lane-private float4 slots, no
 // conflicts, no atomics) so that registers only hold one row: high occupancy for an HBM-bound kernel.
+EGV_DEVINL float4 unpack_dy(const float4& v) { return v; }
+EGV_DEVINL float4 unpack_dy(const uint2& u) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
 template <bool DYBF, bool XBF>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, long long rows, int C,
                                                      const float* add, float* dx, int bf16_total, bf16* __restrict__ dx_bf16,
@@ -102,23 +110,39 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
   for (int c4 = lane; c4 < nv; c4 += 32) acc_g[c4] = acc_b[c4] = acc_s[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long row = warp0; row < rows; row += nwarps) {
     const long long base = row * C;
-    const float mu = mean[row], rs = rstd[row];
-    float4 xh[LN_MAXV], gy[LN_MAXV];
+    // Every global load of the row (x, dy and the residual gradient `add`) is issued before the first use: one memory
+    // round trip per row instead of two -- the kernel is bound by bytes in flight per SM, not by issue slots.
+    // dy stays in its storage format (bf16 pairs when DYBF) and x stays raw: xhat and g * dy are recomputed in the
+    // second pass, which keeps the kernel at 128 registers = two resident 256-thread blocks per SM.
+    typedef typename std::conditional<DYBF, uint2, float4>::type dy_t;
+    float4 xv[LN_MAXV], av[LN_MAXV];
+    dy_t dv[LN_MAXV];
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c4 = lane + i * 32;
+      if (c4 < nv) {
+        xv[i] = ld4<XBF>(x, base + 4 * c4);
+        if (DYBF) dv[i] = *reinterpret_cast<const dy_t*>(reinterpret_cast<const bf16*>(dy) + base + 4 * c4);
+        else dv[i] = *reinterpret_cast<const dy_t*>(reinterpret_cast<const float*>(dy) + base + 4 * c4);
+        if (add) av[i] = *reinterpret_cast<const float4*>(add + base + 4 * c4);
+      }
+    }
+    const float rs = rstd[row];
+    const float nmu = -mean[row] * rs;   // xhat = x * rs + nmu
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAXV; ++i) {
       const int c4 = lane + i * 32;
       if (c4 < nv) {
-        const float4 xv = ld4<XBF>(x, base + 4 * c4);
-        const float4 d = ld4<DYBF>(dy, base + 4 * c4);
+        const float4 d = unpack_dy(dv[i]);
         const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c4);
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        gy[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-        s1 += gy[i].x + gy[i].y + gy[i].z + gy[i].w;
-        s2 += gy[i].x * xh[i].x + gy[i].y * xh[i].y + gy[i].z * xh[i].z + gy[i].w * xh[i].w;
+        const float4 xh = make_float4(fmaf(xv[i].x, rs, nmu), fmaf(xv[i].y, rs, nmu), fmaf(xv[i].z, rs, nmu), fmaf(xv[i].w, rs, nmu));
+        const float4 gy = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+        s1 += gy.x + gy.y + gy.z + gy.w;
+        s2 += gy.x * xh.x + gy.y * xh.y + gy.z * xh.z + gy.w * xh.w;
         if (want_params) {
           float4 a = acc_g[c4], b = acc_b[c4];
-          a.x += d.x * xh[i].x; a.y += d.y * xh[i].y; a.z += d.z * xh[i].z; a.w += d.w * xh[i].w;
+          a.x += d.x * xh.x; a.y += d.y * xh.y; a.z += d.z * xh.z; a.w += d.w * xh.w;
           b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
           acc_g[c4] = a;
           acc_b[c4] = b;
@@ -131,15 +155,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
     for (int i = 0; i < LN_MAXV; ++i) {
       const int c4 = lane + i * 32;
       if (c4 < nv) {
+        const float4 d = unpack_dy(dv[i]);
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c4);
         float4 o;
-        o.x = rs * (gy[i].x - s1 - xh[i].x * s2);
-        o.y = rs * (gy[i].y - s1 - xh[i].y * s2);
-        o.z = rs * (gy[i].z - s1 - xh[i].z * s2);
-        o.w = rs * (gy[i].w - s1 - xh[i].w * s2);
+        o.x = rs * (d.x * g.x - s1 - fmaf(xv[i].x, rs, nmu) * s2);
+        o.y = rs * (d.y * g.y - s1 - fmaf(xv[i].y, rs, nmu) * s2);
+        o.z = rs * (d.z * g.z - s1 - fmaf(xv[i].z, rs, nmu) * s2);
+        o.w = rs * (d.w * g.w - s1 - fmaf(xv[i].w, rs, nmu) * s2);
         float4 tot = o;
         if (add) {
-          const float4 old = *reinterpret_cast<const float4*>(add + base + 4 * c4);
-          tot.x += old.x; tot.y += old.y; tot.z += old.z; tot.w += old.w;
+          tot.x += av[i].x; tot.y += av[i].y; tot.z += av[i].z; tot.w += av[i].w;
         }
         if (dx) *reinterpret_cast<float4*>(dx + base + 4 * c4) = tot;
         const float4 ob = bf16_total ? tot : o;

@@ -272,6 +272,12 @@ def _attn_case(name, B=2, H=2):
         n = 1 + T2 * Nf2
         return n, n, L.AttnSpec(H=H, G=T2, Lq=Nf2, Lk=Nf2, q_row0=1, q_gstride=Nf2, q_istride=1, k_row0=1,
                                 k_gstride=Nf2, k_istride=1, has_cls_key=True, cls_row=0, scale=sc), False
+    if name.startswith("grp"):   # group-resident kernels (attention_group.cu): contiguous groups of 64..224 rows
+        Lq, Lk, cls, G = {"grp_nocls": (100, 150, False, 3), "grp112": (112, 112, True, 2), "grp64": (64, 70, True, 3),
+                          "grp224": (224, 207, True, 2), "grp_q196_k40": (196, 40, False, 2)}[name]
+        nq, nk = 1 + G * Lq, 1 + G * Lk
+        return nq, nk, L.AttnSpec(H=H, G=G, Lq=Lq, Lk=Lk, q_row0=1, q_gstride=Lq, q_istride=1, k_row0=1, k_gstride=Lk,
+                                  k_istride=1, has_cls_key=cls, cls_row=0, scale=sc), False
     if name == "time16":    # 16 frames: 16 queries x 17 keys per group, many groups -> warp-per-group kernel
         Nf2, T2 = 196, 16
         n = 1 + T2 * Nf2
@@ -280,7 +286,8 @@ def _attn_case(name, B=2, H=2):
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name", ["time", "space", "cls", "cls_h12", "i2t", "t2i", "text", "space196", "time16"])
+@pytest.mark.parametrize("name", ["time", "space", "cls", "cls_h12", "i2t", "t2i", "text", "space196", "time16", "grp_nocls",
+                                  "grp112", "grp64", "grp224", "grp_q196_k40"])
 def test_attention_fwd_bwd(K, R, name):
     B, H = (3, 3) if name == "time16" else ((3, 12) if name == "cls_h12" else (2, 2))
     Nq, Nk, spec, masked = _attn_case(name, B, H)

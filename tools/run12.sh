@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q --tb=short -p no:cacheprovider -k attention > gpurun_out/attn_tests.log 2>&1
+echo "== attention tests: exit $? : $(tail -n 1 gpurun_out/attn_tests.log)"; grep -E "^E|FAILED|egv:" gpurun_out/attn_tests.log | head -30
+PROF_ONLY=attn_space timeout 300 python tools/prof_kernels.py 2>&1 | tail -4
+EGV_ATTN_GROUP=0 PROF_ONLY=attn_space timeout 300 python tools/prof_kernels.py 2>&1 | tail -4
