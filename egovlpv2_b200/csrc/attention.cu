@@ -90,10 +90,11 @@ EGV_DEVINL void unit_sync() {
 // acc[nt] (16 x 8 fp32 tiles, nt < KC/8) = A(16 x 64, fragments af) * S^T, S = smem tile [KC rows][64] (row = n index)
 template <int KC>
 EGV_DEVINL void mma_a_stile_nt(float (&acc)[KC / 8][4], const uint32_t (&af)[4][4], const bf16* s, int lane) {
+  // k-step outermost: consecutive HMMAs hit KC/8 different accumulators (no back-to-back dependent pairs)
 #pragma unroll
-  for (int n2 = 0; n2 < KC / 16; ++n2) {
+  for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int n2 = 0; n2 < KC / 16; ++n2) {
       uint32_t b0, b1, b2, b3;
       const bf16* p = s + (n2 * 16 + (lane & 7) + ((lane >> 4) << 3)) * LDS + kk * 16 + ((lane >> 3) & 1) * 8;
       ldmatrix_x4(b0, b1, b2, b3, smem_u32(p));
@@ -1071,6 +1072,8 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
 
 using namespace egv;
 
+extern "C" void egv_attention_set_tiny(int mode) { set_tiny_mode(mode); }
+
 extern "C" int egv_attention_fwd(const egv_attn_args* x, egv_stream_t stream) {
   AttnP a;
   int rc = fill_params(x, a, false);
@@ -1094,6 +1097,10 @@ extern "C" int egv_attention_fwd(const egv_attn_args* x, egv_stream_t stream) {
   if (a.Lq == 1) {
     attn_single_fwd_kernel<<<(unsigned)(a.B * a.H * a.G), SQ_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch("attn_single_fwd_kernel");
+  }
+  {
+    const int r = launch_tiny_attention(0, a, (cudaStream_t)stream);   // many tiny groups (time attention)
+    if (r != 0) return r < 0 ? r : EGV_OK;
   }
   return launch_mode<MODE_FWD>(a, (cudaStream_t)stream);
 }
@@ -1123,6 +1130,10 @@ extern "C" int egv_attention_bwd(const egv_attn_args* x, egv_stream_t stream) {
   if (a.Lq == 1) {
     attn_single_bwd_kernel<<<(unsigned)(a.B * a.H * a.G), SQ_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch("attn_single_bwd_kernel");
+  }
+  {
+    const int r = launch_tiny_attention(1, a, (cudaStream_t)stream);   // fused single-launch backward for tiny groups
+    if (r != 0) return r < 0 ? r : EGV_OK;
   }
   rc = launch_mode<MODE_DQ>(a, (cudaStream_t)stream);   // also produces delta
   if (rc) return rc;

@@ -40,6 +40,42 @@ struct AttnP {
 };
 
 
+// ---- device helpers shared by the TMA-fed kernels (attention_group.cu, attention_tiny.cu)
+EGV_DEVINL void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// per-lane constants of the two ldmatrix address patterns over a 128B-swizzled [rows][64] bf16 tile
+// (16-byte chunk c of row r lives at r * 128 + ((c ^ (r & 7)) << 4))
+struct LaneAddr {
+  uint32_t nt_row, nt_x[4];   // B operand of A * tile^T : rows = n index
+  uint32_t p_row, p_x[4];     // B operand of P * tile (transposed load) and A fragments of a row tile
+};
+EGV_DEVINL LaneAddr lane_addr(int lane) {
+  LaneAddr la;
+  const uint32_t l7 = lane & 7;
+  la.nt_row = ((lane & 7) + ((lane >> 4) << 3)) * 128;
+  la.p_row = ((lane & 7) + ((lane >> 3) & 1) * 8) * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    la.nt_x[i] = (((uint32_t)(i * 2 + ((lane >> 3) & 1))) ^ l7) << 4;
+    la.p_x[i] = (((uint32_t)(i * 2 + (lane >> 4))) ^ l7) << 4;
+  }
+  return la;
+}
+
+// a warp's 16 x 64 fp32 C-layout tile -> its swizzled bf16 staging tile
+EGV_DEVINL void g_stage(uint8_t* stg, const float (&c)[8][4], float mul0, float mul1, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<uint32_t*>(stg + g * 128 + ((nt ^ (g & 7)) << 4) + 4 * t) = pack_bf16(c[nt][0] * mul0, c[nt][1] * mul0);
+    *reinterpret_cast<uint32_t*>(stg + (g + 8) * 128 + ((nt ^ (g & 7)) << 4) + 4 * t) = pack_bf16(c[nt][2] * mul1, c[nt][3] * mul1);
+  }
+}
+
 // attention_group.cu: returns 1 when it launched the group-resident kernel for this problem, 0 when the problem is not
 // eligible (the caller falls back to the generic kernels), < 0 on error.
 int launch_group_attention(int mode, const AttnP& a, cudaStream_t stream);
@@ -47,5 +83,14 @@ int launch_group_attention(int mode, const AttnP& a, cudaStream_t stream);
 // gemm.cu: cached bf16 2-D tensor map (`inner` contiguous elements, `outer` rows `ld` elements apart, 128B swizzle)
 int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
                    CUtensorMap* out);
+
+int get_tensor_map_nd(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      CUtensorMap* out);
+
+// attention_tiny.cu: fused kernels for many tiny groups (time attention: <= 16 queries x <= 16 keys + the CLS key per
+// group, adjacent groups on adjacent rows).  Same return convention as launch_group_attention; `bwd` = 0 forward,
+// 1 = the whole backward (dQ, dK, dV, delta) in one launch.
+int launch_tiny_attention(int bwd, const AttnP& a, cudaStream_t stream);
+void set_tiny_mode(int mode);
 
 }  // namespace egv

@@ -18,12 +18,8 @@
 
 namespace egv {
 
-constexpr int GW = 7;                          // compute warps
-constexpr int GROWS = 16 * GW;                 // rows of the row side per pass
 constexpr int GSCAP = 208;                     // stream-side capacity: 13 x 16 rows
-constexpr int G_THREADS = (GW + 1) * 32;
-constexpr int ROW_TILE_BYTES = GROWS * 128;    // 64 bf16 = 128 B per row
-constexpr int STR_TILE_BYTES = GSCAP * 128;
+constexpr int STR_TILE_BYTES = GSCAP * 128;    // 64 bf16 = 128 B per row
 constexpr int STAT_BYTES = 1024;               // GSCAP floats, padded
 constexpr int OUT_STAGE_BYTES = 16 * 128;
 
@@ -41,50 +37,34 @@ struct GroupP {
   long long total;           // problems = B * G * H
 };
 
-template <int MODE>
+// GW compute warps (16 rows each) + 1 producer warp; KC = stream rows per chunk; RS = row-side stages.
+// 13 warps cover a whole 196/197-row group in ONE pass; the register file (64 K) then allows ~146 registers per thread,
+// which the backward modes reach with 32-row chunks.  The row side needs a single stage in that case: its tiles are
+// dead as soon as every warp holds its fragments, i.e. the next problem's rows load during this problem's math.
+template <int MODE, int GW_, int KC_, int RS_>
 struct GCfg {
+  static constexpr int GW = GW_, KC = KC_, RS = RS_;
+  static constexpr int GROWS = 16 * GW;
+  static constexpr int THREADS = (GW + 1) * 32;
+  static constexpr int ROW_TILE_BYTES = ((GROWS * 128 + 1023) / 1024) * 1024;
   static constexpr int NR = MODE == MODE_FWD ? 1 : (MODE == MODE_DQ ? 3 : 2);
   static constexpr int NOUT = MODE == MODE_DKV ? 2 : 1;
   static constexpr int ROW_OFF = 0;
-  static constexpr int STR_OFF = ROW_OFF + 2 * NR * ROW_TILE_BYTES;
+  static constexpr int STR_OFF = ROW_OFF + RS * NR * ROW_TILE_BYTES;
   static constexpr int STAT_OFF = STR_OFF + 4 * STR_TILE_BYTES;
   static constexpr int OUT_OFF = STAT_OFF + 4 * STAT_BYTES;
   static constexpr int BAR_OFF = OUT_OFF + GW * NOUT * OUT_STAGE_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 128 + 1024;   // barriers + alignment slack
 };
 
-EGV_DEVINL void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// per-lane constants of the two ldmatrix address patterns over a 128B-swizzled [rows][64] bf16 tile
-// (16-byte chunk c of row r lives at r * 128 + ((c ^ (r & 7)) << 4))
-struct LaneAddr {
-  uint32_t nt_row, nt_x[4];   // B operand of A * tile^T : rows = n index
-  uint32_t p_row, p_x[4];     // B operand of P * tile (transposed load) and A fragments of a row tile
-};
-EGV_DEVINL LaneAddr lane_addr(int lane) {
-  LaneAddr la;
-  const uint32_t l7 = lane & 7;
-  la.nt_row = ((lane & 7) + ((lane >> 4) << 3)) * 128;
-  la.p_row = ((lane & 7) + ((lane >> 3) & 1) * 8) * 128;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    la.nt_x[i] = (((uint32_t)(i * 2 + ((lane >> 3) & 1))) ^ l7) << 4;
-    la.p_x[i] = (((uint32_t)(i * 2 + (lane >> 4))) ^ l7) << 4;
-  }
-  return la;
-}
-
 // acc[nt] (16 x 8 tiles, nt < KC/8) = A (16 x 64 fragments) * T^T, T = KC rows of a swizzled tile starting at `tile`
 template <int KC>
 EGV_DEVINL void g_mma_nt(float (&acc)[KC / 8][4], const uint32_t (&af)[4][4], uint32_t tile, const LaneAddr& la) {
+  // k-step outermost: consecutive HMMAs hit KC/8 different accumulators, so none waits for its predecessor's result
 #pragma unroll
-  for (int n2 = 0; n2 < KC / 16; ++n2) {
+  for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int n2 = 0; n2 < KC / 16; ++n2) {
       uint32_t b0, b1, b2, b3;
       ldmatrix_x4(b0, b1, b2, b3, tile + n2 * 2048 + la.nt_row + la.nt_x[kk]);
       mma_16816(acc[2 * n2], af[kk], b0, b1);
@@ -115,15 +95,6 @@ EGV_DEVINL void g_load_a(uint32_t (&af)[4][4], uint32_t tile_rows, const LaneAdd
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk)
     ldmatrix_x4(af[kk][0], af[kk][1], af[kk][2], af[kk][3], tile_rows + la.p_row + la.p_x[kk]);
-}
-// a warp's 16 x 64 fp32 C-layout tile -> its swizzled bf16 staging tile
-EGV_DEVINL void g_stage(uint8_t* stg, const float (&c)[8][4], float mul0, float mul1, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    *reinterpret_cast<uint32_t*>(stg + g * 128 + ((nt ^ (g & 7)) << 4) + 4 * t) = pack_bf16(c[nt][0] * mul0, c[nt][1] * mul0);
-    *reinterpret_cast<uint32_t*>(stg + (g + 8) * 128 + ((nt ^ (g & 7)) << 4) + 4 * t) = pack_bf16(c[nt][2] * mul1, c[nt][3] * mul1);
-  }
 }
 // staging tile -> global rows (16-byte stores); row r of the tile is row idx0 + r of the tensor, valid below `limit`
 EGV_DEVINL void g_store_rows(const uint8_t* stg, bf16* base, long long row_first, long long ld, int col0, int idx0, int limit,
@@ -239,11 +210,14 @@ EGV_DEVINL void g_chunk(int c0, int n_str, float scale2, const uint32_t (&fa)[4]
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(G_THREADS, 1)
+template <int MODE, int GW, int KC, int RS>
+// (the register file is 4 x 16 K registers, one slice per SM sub-partition: with 14 warps some sub-partition holds 4 of
+// them, so the per-thread budget is 16384 / (4 * 32) = 128 registers, which is what __launch_bounds__(448) yields)
+__global__ void __launch_bounds__((GW + 1) * 32, 1)
 attn_group_kernel(const __grid_constant__ GroupMaps maps, const AttnP a, const GroupP gp) {
-  using Cfg = GCfg<MODE>;
+  using Cfg = GCfg<MODE, GW, KC, RS>;
   constexpr int NR = Cfg::NR;
+  constexpr int G_THREADS = Cfg::THREADS, GROWS = Cfg::GROWS, ROW_TILE_BYTES = Cfg::ROW_TILE_BYTES;
   extern __shared__ __align__(1024) uint8_t gsm_raw[];
   const uint32_t pad = (1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u;
   uint8_t* smem = gsm_raw + pad;
@@ -252,8 +226,8 @@ attn_group_kernel(const __grid_constant__ GroupMaps maps, const AttnP a, const G
   uint8_t* statbuf = smem + Cfg::STAT_OFF;
   uint8_t* outbuf = smem + Cfg::OUT_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
-  uint64_t* row_full = bars;        // [2]
-  uint64_t* row_empty = bars + 2;   // [2]
+  uint64_t* row_full = bars;        // [RS]
+  uint64_t* row_empty = bars + 2;   // [RS]
   uint64_t* str_full = bars + 4;    // [2]
   uint64_t* str_empty = bars + 6;   // [2]
 
@@ -269,9 +243,11 @@ attn_group_kernel(const __grid_constant__ GroupMaps maps, const AttnP a, const G
     fence_proxy_async();   // generic-proxy zero fill before async-proxy (TMA) writes to the same tiles
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < RS; ++s) {
       mbar_init(&row_full[s], row_manual ? 2 : 1);
       mbar_init(&row_empty[s], GW);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&str_full[s], str_manual ? 2 : 1);
       mbar_init(&str_empty[s], GW);
     }
@@ -359,7 +335,7 @@ attn_group_kernel(const __grid_constant__ GroupMaps maps, const AttnP a, const G
           __syncwarp();
           if (lane == 0) mbar_arrive(&row_full[rs]);
         }
-        if (++rs == 2) {
+        if (++rs == RS) {
           rs = 0;
           rph ^= 1;
         }
@@ -417,7 +393,7 @@ attn_group_kernel(const __grid_constant__ GroupMaps maps, const AttnP a, const G
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&row_empty[rs]);   // fragments are in registers: the producer may refill this stage
-      if (++rs == 2) {
+      if (++rs == RS) {
         rs = 0;
         rph ^= 1;
       }
@@ -430,21 +406,18 @@ attn_group_kernel(const __grid_constant__ GroupMaps maps, const AttnP a, const G
         for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = 0.f;
       float m_lo = -1e30f, m_hi = -1e30f, l_lo = 0.f, l_hi = 0.f;
       if (idx0 < n_rows) {   // warp-uniform: tiles entirely past the last row have nothing to do
+        int c0 = 0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 192 && c0 < n_str; c0 += 64) {
-          if (n_str - c0 >= 64)
-            g_chunk<MODE, 64, true>(c0, n_str, scale2, fa, fb, strA, strB, st0, st1, acc0, acc1, m_lo, m_hi, l_lo, l_hi,
+        for (; c0 + KC <= n_str; c0 += KC)
+          g_chunk<MODE, KC, true>(c0, n_str, scale2, fa, fb, strA, strB, st0, st1, acc0, acc1, m_lo, m_hi, l_lo, l_hi, r0_lo,
+                                  r0_hi, r1_lo, r1_hi, la, tq);
+#pragma unroll 1
+        for (; c0 < n_str; c0 += 16) {   // tail in 16-row pieces (197 keys = 3 x 64 + 5 or 6 x 32 + 5)
+          if (n_str - c0 >= 16)
+            g_chunk<MODE, 16, true>(c0, n_str, scale2, fa, fb, strA, strB, st0, st1, acc0, acc1, m_lo, m_hi, l_lo, l_hi,
                                     r0_lo, r0_hi, r1_lo, r1_hi, la, tq);
           else
-            g_chunk<MODE, 64, false>(c0, n_str, scale2, fa, fb, strA, strB, st0, st1, acc0, acc1, m_lo, m_hi, l_lo, l_hi,
-                                     r0_lo, r0_hi, r1_lo, r1_hi, la, tq);
-        }
-        if (n_str > 192) {
-          if (n_str - 192 >= 16)
-            g_chunk<MODE, 16, true>(192, n_str, scale2, fa, fb, strA, strB, st0, st1, acc0, acc1, m_lo, m_hi, l_lo, l_hi,
-                                    r0_lo, r0_hi, r1_lo, r1_hi, la, tq);
-          else
-            g_chunk<MODE, 16, false>(192, n_str, scale2, fa, fb, strA, strB, st0, st1, acc0, acc1, m_lo, m_hi, l_lo, l_hi,
+            g_chunk<MODE, 16, false>(c0, n_str, scale2, fa, fb, strA, strB, st0, st1, acc0, acc1, m_lo, m_hi, l_lo, l_hi,
                                      r0_lo, r0_hi, r1_lo, r1_hi, la, tq);
         }
       }
@@ -503,10 +476,11 @@ attn_group_kernel(const __grid_constant__ GroupMaps maps, const AttnP a, const G
 
 static int g_group_mode = -1;   // env EGV_ATTN_GROUP: bit per MODE (default 7 = all)
 
-template <int MODE>
+template <int MODE, int GW, int KC, int RS>
 static int launch_group(const GroupMaps& maps, const AttnP& a, const GroupP& gp, cudaStream_t stream) {
-  using Cfg = GCfg<MODE>;
-  auto kern = attn_group_kernel<MODE>;
+  using Cfg = GCfg<MODE, GW, KC, RS>;
+  static_assert(Cfg::SMEM_BYTES <= 232448, "group attention tile set exceeds the 227 KB shared memory of an SM");
+  auto kern = attn_group_kernel<MODE, GW, KC, RS>;
   static bool cfg = false;
   if (!cfg) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -514,10 +488,13 @@ static int launch_group(const GroupMaps& maps, const AttnP& a, const GroupP& gp,
     cfg = true;
   }
   const long long grid = gp.total < sm_count() ? gp.total : sm_count();
-  kern<<<(unsigned)grid, G_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, a, gp);
+  kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(maps, a, gp);
   int rc = check_launch("attn_group_kernel");
   return rc ? rc : 1;
 }
+
+static int g_group_wide = -1;   // env EGV_ATTN_GROUP_WIDE, bit per MODE: 1 = 13 compute warps / one pass per group, 0 = 7 warps / two passes
+                                // (default 1: forward only -- measured: the 128-register budget of 14 warps costs the backward 20 %)
 
 int launch_group_attention(int mode, const AttnP& a, cudaStream_t stream) {
   if (g_group_mode < 0) g_group_mode = getenv("EGV_ATTN_GROUP") ? atoi(getenv("EGV_ATTN_GROUP")) : 7;
@@ -536,6 +513,9 @@ int launch_group_attention(int mode, const AttnP& a, cudaStream_t stream) {
     gp.str_reg = lk_reg; gp.str_cls = a.has_cls ? 1 : 0;
   }
   const int n_rows = gp.rows_reg + gp.row_cls, n_str = gp.str_reg + gp.str_cls;
+  if (g_group_wide < 0) g_group_wide = getenv("EGV_ATTN_GROUP_WIDE") ? atoi(getenv("EGV_ATTN_GROUP_WIDE")) : 1;
+  const bool wide = (g_group_wide >> mode) & 1;
+  const int GROWS = 16 * (wide ? 13 : 7);
   if (gp.rows_reg < 64 || n_rows > 2 * GROWS || gp.str_reg < 16 || n_str > GSCAP) return 0;
   gp.npass = (int)cdiv(n_rows, GROWS);
   gp.r0 = gp.rows_reg < GROWS ? gp.rows_reg : GROWS;
@@ -570,9 +550,10 @@ int launch_group_attention(int mode, const AttnP& a, cudaStream_t stream) {
   for (int t = 0; t < 2; ++t)
     if ((rc = get_tensor_map(strt[t].p, width, strt[t].rows, strt[t].ld, 64, (uint32_t)gp.str_reg, &maps.str[t]))) return rc;
   switch (mode) {
-    case MODE_FWD: return launch_group<MODE_FWD>(maps, a, gp, stream);
-    case MODE_DQ: return launch_group<MODE_DQ>(maps, a, gp, stream);
-    default: return launch_group<MODE_DKV>(maps, a, gp, stream);
+    // <mode, compute warps, chunk rows, row-side stages>
+    case MODE_FWD: return wide ? launch_group<MODE_FWD, 13, 64, 2>(maps, a, gp, stream) : launch_group<MODE_FWD, 7, 64, 2>(maps, a, gp, stream);
+    case MODE_DQ: return wide ? launch_group<MODE_DQ, 13, 32, 1>(maps, a, gp, stream) : launch_group<MODE_DQ, 7, 64, 2>(maps, a, gp, stream);
+    default: return wide ? launch_group<MODE_DKV, 13, 32, 1>(maps, a, gp, stream) : launch_group<MODE_DKV, 7, 64, 2>(maps, a, gp, stream);
   }
 }
 

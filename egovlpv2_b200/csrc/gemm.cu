@@ -15,6 +15,7 @@
 // (row strides that are not multiples of 16 bytes) and for tiny problems.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -588,6 +589,65 @@ int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
   if (r != CUDA_SUCCESS)
     return fail(EGV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%llu outer=%llu ld=%llu", (int)r, ptr,
                 (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache[key] = *out;
+  return EGV_OK;
+}
+
+// bf16 tensor map of rank 2..4 with 128B swizzle: dims[0] = contiguous elements, byte strides of dims 1.. in
+// strides[0..rank-2], box extents per dimension (box[0] must be 64 elements = one swizzle row).
+int get_tensor_map_nd(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      CUtensorMap* out) {
+  struct Key {
+    const void* ptr;
+    int rank;
+    uint64_t d[4], s[3];
+    uint32_t b[4];
+    bool operator==(const Key& o) const { return memcmp(this, &o, sizeof(Key)) == 0; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key& k) const {
+      const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+      size_t h = 1469598103934665603ull;
+      for (size_t i = 0; i < sizeof(Key) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+      return h;
+    }
+  };
+  static std::mutex mu;
+  static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  if (rank < 2 || rank > 4) return fail(EGV_ERR_ARG, "tensor map rank %d", rank);
+  Key key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr;
+  key.rank = rank;
+  for (int i = 0; i < rank; ++i) {
+    key.d[i] = dims[i];
+    key.b[i] = box[i];
+    if (i + 1 < rank) key.s[i] = strides_bytes[i];
+  }
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return EGV_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(EGV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t d[4], st[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) st[i] = strides_bytes[i];
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EGV_ERR_CUDA, "cuTensorMapEncodeTiled (rank %d) failed (%d) ptr=%p", rank, (int)r, ptr);
   std::lock_guard<std::mutex> lock(mu);
   if (cache.size() > 8192) cache.clear();
   cache[key] = *out;

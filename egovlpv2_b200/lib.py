@@ -142,6 +142,9 @@ class Kernels:
     def set_cluster(self, on):
         self.lib.egv_gemm_set_cluster(int(bool(on)))
 
+    def set_attention_tiny(self, mode):
+        self.lib.egv_attention_set_tiny(int(mode))
+
     def set_plan(self, mode):
         self.lib.egv_gemm_set_plan(int(mode))
 

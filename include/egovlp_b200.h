@@ -129,6 +129,9 @@ typedef struct egv_attn_args {
 } egv_attn_args;
 int egv_attention_fwd(const egv_attn_args* a, egv_stream_t stream);
 int egv_attention_bwd(const egv_attn_args* a, egv_stream_t stream);
+/* fused tiny-group kernels (time attention; csrc/attention_tiny.cu): bit 0 = forward, bit 1 = backward.  Default 0
+ * (env EGV_ATTN_TINY): validated but not yet faster than the generic kernels -- see DESIGN.md. */
+void egv_attention_set_tiny(int mode);
 /* dk/dv row `cls_row` of every batch (+)= the fp32 accumulators dkv_cls [B,H,2,64] filled by egv_attention_bwd */
 int egv_attention_cls_finalize(const float* dkv_cls, void* dk, void* dv, int64_t lddkv, int64_t kv_bstride, int cls_row,
                                int B, int H, int accumulate, egv_stream_t stream);

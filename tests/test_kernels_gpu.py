@@ -278,6 +278,12 @@ def _attn_case(name, B=2, H=2):
         nq, nk = 1 + G * Lq, 1 + G * Lk
         return nq, nk, L.AttnSpec(H=H, G=G, Lq=Lq, Lk=Lk, q_row0=1, q_gstride=Lq, q_istride=1, k_row0=1, k_gstride=Lk,
                                   k_istride=1, has_cls_key=cls, cls_row=0, scale=sc), False
+    if name.startswith("tiny"):   # fused tiny-group kernels (attention_tiny.cu): frames Nf rows apart, adjacent groups
+        T2, Nf2, cls = {"tiny12_nocls": (12, 100, False), "tiny8_cls": (8, 150, True), "tiny16_g8": (16, 8, True),
+                        "tiny_time16": (16, 196, True)}[name]
+        n = 1 + T2 * Nf2
+        return n, n, L.AttnSpec(H=H, G=Nf2, Lq=T2, Lk=T2, q_row0=1, q_gstride=1, q_istride=Nf2, k_row0=1, k_gstride=1,
+                                k_istride=Nf2, has_cls_key=cls, cls_row=0, scale=sc), False
     if name == "time16":    # 16 frames: 16 queries x 17 keys per group, many groups -> warp-per-group kernel
         Nf2, T2 = 196, 16
         n = 1 + T2 * Nf2
@@ -287,9 +293,11 @@ def _attn_case(name, B=2, H=2):
 
 
 @pytest.mark.parametrize("name", ["time", "space", "cls", "cls_h12", "i2t", "t2i", "text", "space196", "time16", "grp_nocls",
-                                  "grp112", "grp64", "grp224", "grp_q196_k40"])
+                                  "grp112", "grp64", "grp224", "grp_q196_k40", "tiny12_nocls", "tiny8_cls", "tiny16_g8", "tiny_time16"])
 def test_attention_fwd_bwd(K, R, name):
     B, H = (3, 3) if name == "time16" else ((3, 12) if name == "cls_h12" else (2, 2))
+    if name.startswith("tiny"):
+        B, H = (12, 12) if name == "tiny16_g8" else (3, 4)
     Nq, Nk, spec, masked = _attn_case(name, B, H)
     C = H * 64
     fused = Nq == Nk and spec.has_cls_key
@@ -305,6 +313,7 @@ def test_attention_fwd_bwd(K, R, name):
         kb = kb.float().contiguous()
     d_o = rnd(B, Nq, C, seed=75)
     outs = []
+    K.set_attention_tiny(3 if name.startswith("tiny") else 0)
     for impl in (K, R):
         o = torch.zeros(B, Nq, C, dtype=torch.bfloat16, device=DEV)
         lse = torch.zeros(B * H * spec.G * spec.Lq, device=DEV)
@@ -322,6 +331,7 @@ def test_attention_fwd_bwd(K, R, name):
         if spec.has_cls_key:
             impl.attention_cls_finalize(cls, dk, dv, H, cls_row=0, accumulate=False)
         outs.append((o, lse, dq, dk, dv, delta))
+    K.set_attention_tiny(0)
     for n, a, r in zip("o lse dq dk dv delta".split(), outs[0], outs[1]):
         tol = {"dq": 1.2e-2, "dk": 1.2e-2, "dv": 1.2e-2, "o": 8e-3, "delta": 2e-2, "lse": 1e-4}[n]
         check(a, r, tol, "attention %s %s" % (name, n))
