@@ -226,12 +226,16 @@ def run_ours(a, rank, world, local_rank):
     # (every rank runs it -- a step contains collectives -- but only rank 0 keeps the timings)
     prof = None
     torch.cuda.synchronize()
+    from egovlpv2_b200 import streams
+    two_streams = streams.enabled()
+    streams.enable(False)    # per-launch events must not time kernels that share the GPU with the other stream
     if rank == 0:
         K.start_profile()
     step.step(dev_batch)
     torch.cuda.synchronize()
     if rank == 0:
         prof = K.stop_profile()
+    streams.enable(two_streams)
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -270,7 +274,7 @@ def run_ours(a, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": a.batch * world, "parallelism": "dp%d" % world,
                    "l2_policy": "per-step working set (>30 GB of activations) exceeds the 126 MB L2; no flush needed",
-                   "embedding_gather": step.gather_kind, "cuda_graph": use_graph, "step_tflop_algorithmic": round(flops / 1e12, 2),
+                   "embedding_gather": step.gather_kind, "cuda_graph": use_graph, "text_tower_side_stream": two_streams, "step_tflop_algorithmic": round(flops / 1e12, 2),
                    "step_frac_of_sustained_peak": round(flops / (ms / a.steps * 1e-3) / 1e12 / sustained, 4),
                    "xattn_i2t_fwd": region("xattn_i2t_fwd"), "xattn_t2i_fwd": region("xattn_t2i_fwd"),
                    "xattn_i2t_bwd": region("xattn_i2t_bwd"), "xattn_t2i_bwd": region("xattn_t2i_bwd"),

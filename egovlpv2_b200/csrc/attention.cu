@@ -171,8 +171,10 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
   const int wq = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
 
-  const int tile = (int)(item % a.row_tiles);
-  long long rest = item / a.row_tiles;
+  const int split = (int)(item % a.n_split);
+  const long long item_ns = item / a.n_split;   // item index without the split
+  const int tile = (int)(item_ns % a.row_tiles);
+  long long rest = item_ns / a.row_tiles;
   const int h = (int)(rest % a.H);
   rest /= a.H;
   const int g = (int)(rest % a.G);
@@ -281,7 +283,15 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
     cp_async_wait<0>();
     unit_sync<NW>();
   }
-  for (int c0 = 0; c0 < n_str; c0 += KC) {
+  // stream range of this split (whole chunks)
+  int c_begin = 0, c_end = n_str;
+  if (a.n_split > 1) {
+    const int chunks = (n_str + KC - 1) / KC;
+    const int per = (chunks + a.n_split - 1) / a.n_split;
+    c_begin = split * per * KC;
+    c_end = min(n_str, c_begin + per * KC);
+  }
+  for (int c0 = c_begin; c0 < c_end; c0 += KC) {
     if (NCH == 1) {
       unit_sync<NW>();  // previous chunk fully consumed
       load_stream(c0, KC, strA, strB, sf0, sf1);
@@ -410,6 +420,39 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
     }
   }
 
+  // ---------------------------------------------------------------- split: fp32 partials, merged by attn_split_finalize_kernel
+  if (a.n_split > 1) {
+    // ws[((item_ns * n_split + split) * ROWS + row) * W + ...],  W = 66 (FWD: m, l, o[64]), 64 (DQ) or 128 (DKV: dk, dv)
+    constexpr int W = MODE == MODE_FWD ? 66 : (MODE == MODE_DQ ? 64 : 128);
+    float* base = a.ws + ((item_ns * a.n_split + split) * ROWS + wq * 16) * W;
+    float* p_lo = base + (long long)gq * W, *p_hi = base + (long long)(gq + 8) * W;
+    if (MODE == MODE_FWD) {
+      l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+      l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+      l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+      l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+      if (tq == 0) {
+        p_lo[0] = m_lo; p_lo[1] = l_lo;
+        p_hi[0] = m_hi; p_hi[1] = l_hi;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<float2*>(p_lo + 2 + nt * 8 + 2 * tq) = make_float2(acc0[nt][0], acc0[nt][1]);
+        *reinterpret_cast<float2*>(p_hi + 2 + nt * 8 + 2 * tq) = make_float2(acc0[nt][2], acc0[nt][3]);
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<float2*>(p_lo + nt * 8 + 2 * tq) = make_float2(acc0[nt][0] * a.scale, acc0[nt][1] * a.scale);
+        *reinterpret_cast<float2*>(p_hi + nt * 8 + 2 * tq) = make_float2(acc0[nt][2] * a.scale, acc0[nt][3] * a.scale);
+        if (MODE == MODE_DKV) {
+          *reinterpret_cast<float2*>(p_lo + 64 + nt * 8 + 2 * tq) = make_float2(acc1[nt][0], acc1[nt][1]);
+          *reinterpret_cast<float2*>(p_hi + 64 + nt * 8 + 2 * tq) = make_float2(acc1[nt][2], acc1[nt][3]);
+        }
+      }
+    }
+    return;
+  }
   // ---------------------------------------------------------------- write-out (through smem for 16-byte stores)
   unit_sync<NW>();
   bf16* outA = rowA + wq * 16 * LDS;
@@ -917,6 +960,71 @@ __global__ void attn_cls_finalize_kernel(const float* __restrict__ dkv_cls, bf16
   dv[off] = __float2bfloat16(vv);
 }
 
+// Merge the per-split partials of attn_unit (n_split > 1): one 64-thread block per (item, row).
+template <int MODE>
+__global__ void __launch_bounds__(64) attn_split_finalize_kernel(const AttnP a, int rows_cap) {
+  constexpr int W = MODE == MODE_FWD ? 66 : (MODE == MODE_DQ ? 64 : 128);
+  const int n_rows = (MODE == MODE_DKV) ? a.LkT : a.Lq;
+  const long long item_ns = blockIdx.x / rows_cap;
+  const int r = blockIdx.x % rows_cap;
+  const int tile = (int)(item_ns % a.row_tiles);
+  long long rest = item_ns / a.row_tiles;
+  const int h = (int)(rest % a.H);
+  rest /= a.H;
+  const int g = (int)(rest % a.G);
+  const int b = (int)(rest / a.G);
+  const int idx = tile * rows_cap + r;
+  if (idx >= n_rows) return;
+  const int d = threadIdx.x;
+  const float* p = a.ws + ((item_ns * a.n_split) * rows_cap + r) * W;
+  const long long sstride = (long long)rows_cap * W;
+  if (MODE == MODE_FWD) {
+    float M = -1e30f;
+    for (int s = 0; s < a.n_split; ++s) M = fmaxf(M, p[s * sstride]);
+    float L = 0.f, o = 0.f;
+    for (int s = 0; s < a.n_split; ++s) {
+      const float f = ex2(p[s * sstride] - M);
+      L = fmaf(p[s * sstride + 1], f, L);
+      o = fmaf(p[s * sstride + 2 + d], f, o);
+    }
+    a.o[o_row(a, b, g, idx) * a.ldo + h * HD + d] = __float2bfloat16(o / L);
+    if (d == 0) a.lse[(((long long)b * a.H + h) * a.G + g) * a.Lq + idx] = M + log2f(L);
+  } else if (MODE == MODE_DQ) {
+    float v = 0.f;
+    for (int s = 0; s < a.n_split; ++s) v += p[s * sstride + d];
+    a.dq[q_row(a, b, g, idx) * a.lddq + h * HD + d] = __float2bfloat16(v);
+  } else {
+    if (a.has_cls && idx == 0) return;   // the shared CLS key was accumulated into dkv_cls by the splits
+    float vk = 0.f, vv = 0.f;
+    for (int s = 0; s < a.n_split; ++s) {
+      vk += p[s * sstride + d];
+      vv += p[s * sstride + 64 + d];
+    }
+    const long long off = k_row(a, b, g, idx) * a.lddkv + h * HD + d;
+    if (a.dkv_accumulate) {
+      vk += __bfloat162float(a.dk[off]);
+      vv += __bfloat162float(a.dv[off]);
+    }
+    a.dk[off] = __float2bfloat16(vk);
+    a.dv[off] = __float2bfloat16(vv);
+  }
+}
+
+// Stream splits for a (few rows, long stream) problem: enough CTAs to fill the GPU, >= 4 chunks of 64 rows per split.
+static int pick_split(long long items, int n_str) {
+  const int chunks = (n_str + 63) / 64;
+  if (items >= 2 * sm_count() || chunks < 8) return 1;
+  long long want = cdiv(4LL * sm_count(), items);
+  long long cap = chunks / 4;
+  long long n = want < cap ? want : cap;
+  return (int)(n < 1 ? 1 : (n > 32 ? 32 : n));
+}
+template <int MODE>
+static long long split_ws_floats(long long items_ns, int n_split, int rows_cap) {
+  constexpr int W = MODE == MODE_FWD ? 66 : (MODE == MODE_DQ ? 64 : 128);
+  return items_ns * n_split * rows_cap * W;
+}
+
 static int fill_params(const egv_attn_args* x, AttnP& a, bool bwd) {
   if (!x || !x->q || !x->k || !x->v) return fail(EGV_ERR_ARG, "attention: null q/k/v");
   if (x->B <= 0 || x->H <= 0 || x->G <= 0 || x->Lq <= 0 || x->Lk < 0) return fail(EGV_ERR_ARG, "attention: bad sizes");
@@ -937,6 +1045,7 @@ static int fill_params(const egv_attn_args* x, AttnP& a, bool bwd) {
   a.d_o = (const bf16*)x->d_o; a.dq = (bf16*)x->dq; a.lddq = x->lddq;
   a.dk = (bf16*)x->dk; a.dv = (bf16*)x->dv; a.lddkv = x->lddkv;
   a.delta = x->delta; a.dkv_cls = x->dkv_cls; a.dkv_accumulate = x->dkv_accumulate;
+  a.n_split = 1; a.ws = (float*)x->workspace; a.ws_floats = x->workspace_bytes / 4;
   if (bwd) {
     if (!x->d_o || !x->dq || !x->dk || !x->dv || !x->delta) return fail(EGV_ERR_ARG, "attention bwd: null gradient buffer");
     if ((x->lddq % 8) || (x->lddkv % 8)) return fail(EGV_ERR_ARG, "attention bwd: gradient strides must be multiples of 8");
@@ -978,6 +1087,13 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
     constexpr int KC = 64;
     a.row_tiles = (int)cdiv(n_rows, 16);
     a.items = groups * a.row_tiles;
+    {
+      const int ns = pick_split(a.items, n_str);
+      if (ns > 1 && a.ws && split_ws_floats<MODE>(a.items, ns, 16) <= a.ws_floats) {
+        a.n_split = ns;
+        a.items *= ns;
+      }
+    }
     auto kern = attn_cta_kernel<MODE, 1, KC>;
     const int smem = AttnSmem<MODE, 1, KC>::BYTES;
     static bool cfg = false;
@@ -987,10 +1103,22 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
     }
     long long grid = std::min<long long>(a.items, (long long)sm_count() * 32);
     if (e == cudaSuccess) kern<<<(unsigned)grid, 32, smem, stream>>>(a);
+    if (e == cudaSuccess && a.n_split > 1) {
+      int rc = check_launch("attention kernel");
+      if (rc) return rc;
+      attn_split_finalize_kernel<MODE><<<(unsigned)(a.items / a.n_split * 16), 64, 0, stream>>>(a, 16);
+    }
   } else if (n_rows <= 32) {
     constexpr int KC = 64;
     a.row_tiles = (int)cdiv(n_rows, 32);
     a.items = groups * a.row_tiles;
+    {
+      const int ns = pick_split(a.items, n_str);
+      if (ns > 1 && a.ws && split_ws_floats<MODE>(a.items, ns, 32) <= a.ws_floats) {
+        a.n_split = ns;
+        a.items *= ns;
+      }
+    }
     auto kern = attn_cta_kernel<MODE, 2, KC>;
     const int smem = AttnSmem<MODE, 2, KC>::BYTES;
     static bool cfg = false;
@@ -1000,6 +1128,11 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
     }
     long long grid = std::min<long long>(a.items, (long long)sm_count() * 16);
     if (e == cudaSuccess) kern<<<(unsigned)grid, 64, smem, stream>>>(a);
+    if (e == cudaSuccess && a.n_split > 1) {
+      int rc = check_launch("attention kernel");
+      if (rc) return rc;
+      attn_split_finalize_kernel<MODE><<<(unsigned)(a.items / a.n_split * 32), 64, 0, stream>>>(a, 32);
+    }
   } else {
     // tile shapes: 4 warps x 64-row chunks, or 7 warps x 112-row chunks when that wastes fewer MMA slots
     // (196-197 rows per space-attention group: 2 x 112 = 224 instead of 4 x 64 = 256); 32-row chunks for short streams.
@@ -1073,6 +1206,23 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
 using namespace egv;
 
 extern "C" void egv_attention_set_tiny(int mode) { set_tiny_mode(mode); }
+
+extern "C" int64_t egv_attention_workspace_bytes(const egv_attn_args* x) {
+  // upper bound over the forward and both backward modes of the split-stream path (0 when it cannot apply)
+  if (!x || x->Lq <= 0) return 0;
+  const int lkt = x->Lk + (x->has_cls_key ? 1 : 0);
+  const long long groups = (long long)x->B * x->H * x->G;
+  long long need = 0;
+  auto consider = [&](int n_rows, int n_str, int w) {
+    if (n_rows > 32 || (n_rows <= 32 && n_str <= 64 && groups >= 1024)) return;
+    const int cap = n_rows <= 16 ? 16 : 32;
+    const int ns = pick_split(groups, n_str);
+    if (ns > 1) need = std::max<long long>(need, groups * ns * cap * w * 4);
+  };
+  consider(x->Lq, lkt, 66);    // FWD / DQ: rows = queries
+  consider(lkt, x->Lq, 128);   // DKV: rows = keys
+  return need;
+}
 
 extern "C" int egv_attention_fwd(const egv_attn_args* x, egv_stream_t stream) {
   AttnP a;

@@ -36,7 +36,12 @@ struct AttnP {
   float* dkv_cls;
   int dkv_accumulate;
   int row_tiles;       // tiles of the row side per group
-  long long items;     // B*G*H*row_tiles
+  long long items;     // B*G*H*row_tiles*n_split
+  // stream-side split (few rows, long stream: text->video attention and the key side of video->text attention):
+  // item = (group, tile, split); every split walks 1/n_split of the stream and leaves an fp32 partial in `ws`
+  int n_split;
+  float* ws;
+  long long ws_floats;
 };
 
 

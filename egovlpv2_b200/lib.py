@@ -43,7 +43,8 @@ class AttnArgs(C.Structure):
                 ("lse", c_void_p),
                 ("d_o", c_void_p), ("dq", c_void_p), ("lddq", c_int64),
                 ("dk", c_void_p), ("dv", c_void_p), ("lddkv", c_int64),
-                ("delta", c_void_p), ("dkv_cls", c_void_p), ("dkv_accumulate", c_int)]
+                ("delta", c_void_p), ("dkv_cls", c_void_p), ("dkv_accumulate", c_int),
+                ("workspace", c_void_p), ("workspace_bytes", c_int64)]
 
 
 @dataclasses.dataclass(frozen=True)
@@ -73,6 +74,7 @@ def _load():
     lib.egv_last_error.restype = C.c_char_p
     lib.egv_launch_count.restype = C.c_longlong
     lib.egv_egonce_scratch_floats.restype = c_int64
+    lib.egv_attention_workspace_bytes.restype = c_int64
     return lib
 
 
@@ -247,6 +249,10 @@ class Kernels:
             assert key_bias.dtype == torch.float32 and key_bias.is_contiguous()
             assert key_bias.numel() == a.B * (spec.Lk + int(spec.has_cls_key))
             a.key_bias = _p(key_bias)
+        nbytes = int(self.lib.egv_attention_workspace_bytes(C.byref(a)))
+        if nbytes > 0:   # split-stream scratch (kept alive by the caller's frame until the launches are enqueued)
+            a._ws = torch.empty(nbytes // 4, dtype=torch.float32, device=q.device)
+            a.workspace, a.workspace_bytes = _p(a._ws), nbytes
         return a
 
     def attention_fwd(self, spec, q, k, v, o, lse, key_bias=None):

@@ -24,6 +24,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import autograd as A
+from .. import streams
 from ..lib import ACT_NONE, ACT_RELU, ACT_TANH
 from ..weights import cache
 from . import heads, roberta, video_transformer
@@ -233,26 +234,39 @@ class FrozenInTime(nn.Module):
     def _fused_stack(self, video_data, input_ids, attention_mask, need_video_out=True, video_prefix=None):
         """model.py:211-271 / 295-357: (num_layers - num_fuse_block) plain blocks per tower, then the fused pairs: video
         block i reads the text entering layer i, text layer i reads the video ENTERING block i.
-        `video_prefix`: precomputed output of the unfused video blocks (see _video_prefix)."""
+        `video_prefix`: precomputed output of the unfused video blocks (see _video_prefix), or a callable producing it
+        (evaluated after the text prefix has been enqueued, so the two can overlap on two streams).
+        Returns (video out, text out, video prefix)."""
         vm, tm = self.video_model, self.text_model
         n, f = self.patches_per_frame, video_data.shape[1]
-        x = self._video_prefix(video_data) if video_prefix is None else video_prefix
         unfused = self.num_text_layer - self.num_fuse_block
         es = (self.einops_from_space, self.einops_to_space, self.einops_from_time, self.einops_to_time)
-        h = tm.embeddings(input_ids=input_ids)
-        ext = tm.get_extended_attention_mask(attention_mask, attention_mask.size(), h.device)
-        for layer in tm.encoder.layer[:unfused]:
-            h = layer(h, ext)[0]
+        ext = tm.get_extended_attention_mask(attention_mask, attention_mask.size(), input_ids.device)
+        streams.to_side(ext, input_ids)
+        with streams.side():   # text prefix next to the video prefix
+            h = tm.embeddings(input_ids=input_ids)
+            for layer in tm.encoder.layer[:unfused]:
+                h = layer(h, ext)[0]
+        if video_prefix is None:
+            video_prefix = self._video_prefix(video_data)
+        elif callable(video_prefix):
+            video_prefix = video_prefix()
+        x = video_prefix
         last = self.num_text_layer - 1
         for i in range(unfused, self.num_text_layer):
+            streams.exchange()        # level i reads both outputs of level i - 1
+            streams.to_main(h)
+            streams.to_side(x)
             fuse_x = None
             if need_video_out or i < last:   # the last video block's output is unused by the MLM head (SURVEY.md Q6)
                 # ... and the ITM head reads only its CLS row (model.py:275-278)
                 fuse_x = vm.blocks[i](x, *es, y=h, y_mask=ext, time_n=n, space_f=f,
                                       cls_only=video_transformer.CLS_ONLY_LAST_BLOCK and i == last)
-            h = tm.encoder.layer[i](h, ext, encoder_hidden_states=x, last_norm=True)[0]
+            with streams.side():
+                h = tm.encoder.layer[i](h, ext, encoder_hidden_states=x, last_norm=True)[0]
             x = fuse_x
-        return x, h
+        streams.join(h)
+        return x, h, video_prefix
 
     def infer(self, data, video_only=False, return_embeds=True, task_names=None, ret=None):
         ret = {} if ret is None else ret    # (the reference's mutable default leaks state across calls: SURVEY.md Q10)
@@ -260,13 +274,16 @@ class FrozenInTime(nn.Module):
         if task_names is not None:
             self.task_names = task_names
         if 'EgoNCE' in self.task_names:
-            text_embeddings = self.compute_text(text_data)
+            streams.to_side(*[v for v in text_data.values() if torch.is_tensor(v)])
+            with streams.side():     # the text tower runs next to the video tower
+                text_embeddings = self.compute_text(text_data)
             video_embeddings = self.compute_video(video_data)
+            streams.join(text_embeddings)
             if return_embeds:
                 ret.update({'text_embeds': text_embeddings, 'video_embeds': video_embeddings})
         if 'ITM' in self.task_names:
-            x, h = self._fused_stack(video_data, text_data['input_ids'], text_data['attention_mask'],
-                                     video_prefix=data.get('_video_prefix'))
+            x, h, _ = self._fused_stack(video_data, text_data['input_ids'], text_data['attention_mask'],
+                                        video_prefix=data.get('_video_prefix'))
             v = A.LayerNormRowsFn.apply(x[:, 0], self.norm.weight, self.norm.bias, self.norm.eps)
             v = self.pre_logits(v)
             # transform -> pooler (tanh) per modality, then fc on the concatenation (model.py:279-290)
@@ -275,10 +292,9 @@ class FrozenInTime(nn.Module):
             cls_feats = torch.cat([t_feats, v_feats], dim=-1)
             ret.update({"cross_attn_itm_logits": self.itm_score(cls_feats)})
         if 'MLM' in self.task_names:
-            prefix = self._video_prefix(video_data)
+            _, h, prefix = self._fused_stack(video_data, data['text_mlm_ids'], text_data['attention_mask'],
+                                             need_video_out=False)
             ret['_video_prefix_mlm'] = prefix   # consumed (and removed) by forward() for the ITM pass
-            _, h = self._fused_stack(video_data, data['text_mlm_ids'], text_data['attention_mask'], need_video_out=False,
-                                     video_prefix=prefix)
             if 'text_mlm_labels' in data and torch.is_grad_enabled():
                 names = A.MlmLossFn.NAMES
                 params = [self.get_parameter(nm) for nm in names]
@@ -346,9 +362,13 @@ class FrozenInTime(nn.Module):
                 n_neg = bsz - bsz // 2
                 order = torch.argsort(itm_labels, stable=True)            # label-0 rows first, then label-1 rows
                 redo_idx, keep_idx = order[:n_neg], order[n_neg:]
-                x_redo = self._video_prefix(data_itm['video'].index_select(0, redo_idx))
-                x_cat = torch.cat([x_redo, prefix_mlm.index_select(0, keep_idx)], 0)
-                data_itm['_video_prefix'] = x_cat.index_select(0, torch.argsort(order))
+
+                def itm_prefix(video=data_itm['video']):
+                    x_redo = self._video_prefix(video.index_select(0, redo_idx))
+                    x_cat = torch.cat([x_redo, prefix_mlm.index_select(0, keep_idx)], 0)
+                    return x_cat.index_select(0, torch.argsort(order))
+
+                data_itm['_video_prefix'] = itm_prefix   # evaluated inside _fused_stack, after the text prefix is enqueued
             ret = self.infer(data_itm, task_names='ITM', ret=ret)
             loss_sum, count = A.XentFn.apply(ret["cross_attn_itm_logits"], itm_labels.long())
             loss_itm = self._global_mean(loss_sum, count)

@@ -9,6 +9,7 @@ import torch
 import torch.distributed as dist
 
 from . import lib as _lib
+from . import streams
 from .comm import NcclAllGather, P2PAllGather
 from .model.loss import EgoNCE
 from .model.model import DEFAULT_CONFIG, FrozenInTime
@@ -71,6 +72,7 @@ class PretrainStep:
         else:
             self.allgather = lambda t, n=None, a=None: t
         self.cfg = {"loss": {"type": "EgoNCE"}}
+        self.two_streams = streams.enable(True)   # text tower on a side stream (env EGV_TEXT_STREAM=0 turns it off)
 
     def to_device(self, host_batch):
         """H2D of one step's inputs from pinned host memory (non-blocking on the current stream)."""
@@ -119,6 +121,8 @@ class PretrainStep:
         loss, loss_dict, _ = self.model(data, d["noun_vec"], d["verb_vec"], self.allgather, self.world, self.args, self.cfg,
                                         self.loss_fn, self.rank, task_names=self.tasks)
         loss.backward()
+        # the backward of the text tower ran on the side stream and wrote into the gradient arena directly
+        streams.join()
         if self.world > 1:
             dist.all_reduce(self.opt.arena.grad)          # DDP semantics: average over ranks (base_trainer.py:269)
             self.opt.launch(grad_scale=1.0 / self.world)

@@ -126,7 +126,11 @@ typedef struct egv_attn_args {
   float* delta;                         /* scratch [B,H,G,Lq] f32 */
   float* dkv_cls;                       /* f32 [B, H, 2, 64] accumulator for the shared CLS key/value (or NULL) */
   int dkv_accumulate;                   /* 1: dk/dv rows are read-modify-written (+=) */
+  /* optional scratch for the split-stream path (few rows x long stream, e.g. 32 text queries x 3137 video keys):
+   * egv_attention_workspace_bytes() bytes of device memory, contents undefined; NULL = never split */
+  void* workspace; int64_t workspace_bytes;
 } egv_attn_args;
+int64_t egv_attention_workspace_bytes(const egv_attn_args* a);
 int egv_attention_fwd(const egv_attn_args* a, egv_stream_t stream);
 int egv_attention_bwd(const egv_attn_args* a, egv_stream_t stream);
 /* fused tiny-group kernels (time attention; csrc/attention_tiny.cu): bit 0 = forward, bit 1 = backward.  Default 0

@@ -265,6 +265,12 @@ def _attn_case(name, B=2, H=2):
         return 200, 11, L.AttnSpec(H=H, G=1, Lq=200, Lk=11, scale=sc), True
     if name == "t2i":      # few queries, many keys
         return 11, 333, L.AttnSpec(H=H, G=1, Lq=11, Lk=333, scale=sc), False
+    if name == "t2i_long":   # 32 text queries x 3137 video keys: split-stream forward / dQ
+        return 32, 3137, L.AttnSpec(H=H, G=1, Lq=32, Lk=3137, scale=sc), False
+    if name == "t2i_11":     # <= 16 rows, long stream
+        return 11, 1000, L.AttnSpec(H=H, G=1, Lq=11, Lk=1000, scale=sc), False
+    if name == "i2t_long":   # 3137 video queries x 32 text keys with a pad mask: split-stream dK / dV
+        return 3137, 32, L.AttnSpec(H=H, G=1, Lq=3137, Lk=32, scale=sc), True
     if name == "text":
         return 32, 32, L.AttnSpec(H=H, G=1, Lq=32, Lk=32, scale=sc), True
     if name == "space196":  # real per-frame size, 2 frames
@@ -293,7 +299,7 @@ def _attn_case(name, B=2, H=2):
 
 
 @pytest.mark.parametrize("name", ["time", "space", "cls", "cls_h12", "i2t", "t2i", "text", "space196", "time16", "grp_nocls",
-                                  "grp112", "grp64", "grp224", "grp_q196_k40", "tiny12_nocls", "tiny8_cls", "tiny16_g8", "tiny_time16"])
+                                  "grp112", "grp64", "grp224", "grp_q196_k40", "tiny12_nocls", "tiny8_cls", "tiny16_g8", "tiny_time16", "t2i_long", "t2i_11", "i2t_long"])
 def test_attention_fwd_bwd(K, R, name):
     B, H = (3, 3) if name == "time16" else ((3, 12) if name == "cls_h12" else (2, 2))
     if name.startswith("tiny"):
