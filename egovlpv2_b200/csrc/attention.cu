@@ -704,10 +704,18 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) attn_single_bwd_kernel(const At
 // token (H*64 bf16 = 1.5 KB contiguous for H = 12) with 16-byte loads: lane l holds elements [256 i + 8 l, +8) of
 // group i, i.e. head 4 i + l / 8, so a dot product is an 8-lane reduction.  CTA = (batch, key split): B * SQ_SPLITS
 // CTAs fill the GPU; partial (m, l, o) per (b, split, h) are merged by a second tiny kernel.
-constexpr int SQ_SPLITS = 16;
+constexpr int SQ_SPLITS_MAX = 64;   // key splits per batch element (runtime: a.n_split, ~2 CTAs per SM)
 constexpr int SQH_WARPS = 8;
 
 struct bf16x8 { float v[8]; };
+EGV_DEVINL bf16x8 unpack8(const uint4& u) {
+  bf16x8 r;
+  float2 t = unpack_bf16(u.x); r.v[0] = t.x; r.v[1] = t.y;
+  t = unpack_bf16(u.y); r.v[2] = t.x; r.v[3] = t.y;
+  t = unpack_bf16(u.z); r.v[4] = t.x; r.v[5] = t.y;
+  t = unpack_bf16(u.w); r.v[6] = t.x; r.v[7] = t.y;
+  return r;
+}
 EGV_DEVINL bf16x8 ld8(const bf16* p) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   bf16x8 r;
@@ -730,15 +738,15 @@ EGV_DEVINL float red8(float s) {   // sum over the 8 lanes that share a head
   return s;
 }
 
-// partial layout: part[((b * SQ_SPLITS + split) * H + h) * 66 + {0: m, 1: l, 2..65: o}]
+// partial layout: part[((b * n_split + split) * H + h) * 66 + {0: m, 1: l, 2..65: o}]
 template <int NG>
 __global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_fwd_heads_kernel(const AttnP a, float* __restrict__ part) {
   __shared__ float sm_m[SQH_WARPS][NG * 4], sm_l[SQH_WARPS][NG * 4];
   __shared__ float sm_o[SQH_WARPS][NG * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int split = blockIdx.x % SQ_SPLITS, b = blockIdx.x / SQ_SPLITS;
+  const int split = blockIdx.x % a.n_split, b = blockIdx.x / a.n_split;
   const float scale2 = a.scale * LOG2E;
-  const int per = (a.LkT + SQ_SPLITS - 1) / SQ_SPLITS;
+  const int per = (a.LkT + a.n_split - 1) / a.n_split;
   const int j_lo = split * per, j_hi = min(a.LkT, j_lo + per);
   bf16x8 q[NG];
   const bf16* qp = a.q + q_row(a, b, 0, 0) * a.ldq;
@@ -752,25 +760,37 @@ __global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_fwd_heads_kernel(c
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[i][e] = 0.f;
   }
-  for (int j = j_lo + warp; j < j_hi; j += SQH_WARPS) {
+  // two keys per iteration: both rows' loads (2 x 3 KB per warp) are in flight before the first dot product
+  for (int j = j_lo + warp; j < j_hi; j += 2 * SQH_WARPS) {
+    const int j2 = j + SQH_WARPS;
+    const bool has2 = j2 < j_hi;
     const long long off = k_row(a, b, 0, j) * a.ldkv;
-    bf16x8 kk[NG], vv[NG];
+    const long long off2 = k_row(a, b, 0, has2 ? j2 : j) * a.ldkv;
+    uint4 rk[2][NG], rv[2][NG];
 #pragma unroll
     for (int i = 0; i < NG; ++i) {
-      kk[i] = ld8(a.k + off + 256 * i + 8 * lane);
-      vv[i] = ld8(a.v + off + 256 * i + 8 * lane);
+      rk[0][i] = *reinterpret_cast<const uint4*>(a.k + off + 256 * i + 8 * lane);
+      rv[0][i] = *reinterpret_cast<const uint4*>(a.v + off + 256 * i + 8 * lane);
+      rk[1][i] = *reinterpret_cast<const uint4*>(a.k + off2 + 256 * i + 8 * lane);
+      rv[1][i] = *reinterpret_cast<const uint4*>(a.v + off2 + 256 * i + 8 * lane);
     }
-    float bj = 0.f;
-    if (a.key_bias) bj = fmaxf(a.key_bias[(long long)b * a.LkT + j], -1e30f) * LOG2E;
 #pragma unroll
-    for (int i = 0; i < NG; ++i) {
-      const float sc = fmaf(red8(dot8(q[i], kk[i])), scale2, bj);
-      const float mn = fmaxf(m[i], sc);
-      const float al = ex2(m[i] - mn), pj = ex2(sc - mn);
-      m[i] = mn;
-      l[i] = fmaf(l[i], al, pj);
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !has2) break;
+      const int ju = u ? j2 : j;
+      float bj = 0.f;
+      if (a.key_bias) bj = fmaxf(a.key_bias[(long long)b * a.LkT + ju], -1e30f) * LOG2E;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[i][e] = fmaf(o[i][e], al, pj * vv[i].v[e]);
+      for (int i = 0; i < NG; ++i) {
+        const bf16x8 kk = unpack8(rk[u][i]), vv = unpack8(rv[u][i]);
+        const float sc = fmaf(red8(dot8(q[i], kk)), scale2, bj);
+        const float mn = fmaxf(m[i], sc);
+        const float al = ex2(m[i] - mn), pj = ex2(sc - mn);
+        m[i] = mn;
+        l[i] = fmaf(l[i], al, pj);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[i][e] = fmaf(o[i][e], al, pj * vv.v[e]);
+      }
     }
   }
 #pragma unroll
@@ -796,7 +816,7 @@ __global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_fwd_heads_kernel(c
       L = fmaf(sm_l[w][h], f, L);
       r = fmaf(sm_o[w][t], f, r);
     }
-    float* dst = part + (((long long)b * SQ_SPLITS + split) * a.H + h) * 66;
+    float* dst = part + (((long long)b * a.n_split + split) * a.H + h) * 66;
     dst[2 + (t & 63)] = r;
     if ((t & 63) == 0) {
       dst[0] = M;
@@ -806,17 +826,34 @@ __global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_fwd_heads_kernel(c
 }
 
 __global__ void __launch_bounds__(64) attn_single_combine_kernel(const AttnP a, const float* __restrict__ part) {
+  __shared__ float sm_f[SQ_SPLITS_MAX];   // 2^(m_s - M) per split
+  __shared__ float sm_ml[2];
   const int h = blockIdx.x % a.H, b = blockIdx.x / a.H;
   const int d = threadIdx.x;
-  float M = -1e30f;
-  for (int s = 0; s < SQ_SPLITS; ++s) M = fmaxf(M, part[(((long long)b * SQ_SPLITS + s) * a.H + h) * 66]);
-  float L = 0.f, r = 0.f;
-  for (int s = 0; s < SQ_SPLITS; ++s) {
-    const float* p = part + (((long long)b * SQ_SPLITS + s) * a.H + h) * 66;
-    const float f = ex2(p[0] - M);
-    L = fmaf(p[1], f, L);
-    r = fmaf(p[2 + d], f, r);
+  const float* base = part + ((long long)b * a.n_split * a.H + h) * 66;
+  const long long sstride = (long long)a.H * 66;
+  // every split's (m, l) is fetched by its own thread: one memory round trip instead of n_split dependent ones
+  float ms = -1e30f, ls = 0.f;
+  if (d < a.n_split) {
+    ms = base[d * sstride];
+    ls = base[d * sstride + 1];
   }
+  float M = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, 16));
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+  if ((d & 31) == 0) sm_ml[d >> 5] = M;
+  __syncthreads();
+  M = fmaxf(sm_ml[0], sm_ml[1]);
+  __syncthreads();
+  const float f = d < a.n_split ? ex2(ms - M) : 0.f;
+  if (d < a.n_split) sm_f[d] = f;
+  float L = warp_sum(ls * f);
+  if ((d & 31) == 0) sm_ml[d >> 5] = L;
+  __syncthreads();
+  L = sm_ml[0] + sm_ml[1];
+  float r = 0.f;
+#pragma unroll 8
+  for (int s = 0; s < a.n_split; ++s) r = fmaf(base[s * sstride + 2 + d], sm_f[s], r);
   a.o[o_row(a, b, 0, 0) * a.ldo + h * HD + d] = __float2bfloat16(r / L);
   if (d == 0) a.lse[(long long)b * a.H + h] = M + log2f(L);
 }
@@ -827,9 +864,9 @@ template <int NG>
 __global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_bwd_heads_kernel(const AttnP a, float* __restrict__ dq_acc) {
   __shared__ float sm_q[SQH_WARPS][NG * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int split = blockIdx.x % SQ_SPLITS, b = blockIdx.x / SQ_SPLITS;
+  const int split = blockIdx.x % a.n_split, b = blockIdx.x / a.n_split;
   const float scale2 = a.scale * LOG2E;
-  const int per = (a.LkT + SQ_SPLITS - 1) / SQ_SPLITS;
+  const int per = (a.LkT + a.n_split - 1) / a.n_split;
   const int j_lo = split * per, j_hi = min(a.LkT, j_lo + per);
   bf16x8 q[NG], d_o[NG];
   float delta[NG], lse[NG], dq[NG][8];
@@ -937,6 +974,15 @@ static float* sq_workspace(size_t floats) {
     }
   }
   return buf;
+}
+
+// key splits of the all-heads single-query kernels: ~2 resident CTAs per SM, >= 32 keys per split
+static int single_query_splits(const AttnP& a) {
+  int n = (2 * sm_count() + a.B - 1) / a.B;
+  const int cap = a.LkT / 32;
+  if (n > cap) n = cap;
+  if (n > SQ_SPLITS_MAX) n = SQ_SPLITS_MAX;
+  return n < 1 ? 1 : n;
 }
 
 static bool single_heads_ok(const AttnP& a) {
@@ -1229,9 +1275,10 @@ extern "C" int egv_attention_fwd(const egv_attn_args* x, egv_stream_t stream) {
   int rc = fill_params(x, a, false);
   if (rc) return rc;
   if (single_heads_ok(a)) {
-    float* part = sq_workspace((size_t)a.B * SQ_SPLITS * a.H * 66);
+    a.n_split = single_query_splits(a);
+    float* part = sq_workspace((size_t)a.B * SQ_SPLITS_MAX * a.H * 66);
     if (!part) return fail(EGV_ERR_CUDA, "attention: workspace allocation failed");
-    const unsigned grid = (unsigned)(a.B * SQ_SPLITS);
+    const unsigned grid = (unsigned)(a.B * a.n_split);
     cudaStream_t s = (cudaStream_t)stream;
     switch (a.H / 4) {
       case 1: attn_single_fwd_heads_kernel<1><<<grid, SQH_WARPS * 32, 0, s>>>(a, part); break;
@@ -1265,7 +1312,8 @@ extern "C" int egv_attention_bwd(const egv_attn_args* x, egv_stream_t stream) {
     if (!acc) return fail(EGV_ERR_CUDA, "attention: workspace allocation failed");
     cudaStream_t s = (cudaStream_t)stream;
     cudaMemsetAsync(acc, 0, n * sizeof(float), s);
-    const unsigned grid = (unsigned)(a.B * SQ_SPLITS);
+    a.n_split = single_query_splits(a);
+    const unsigned grid = (unsigned)(a.B * a.n_split);
     switch (a.H / 4) {
       case 1: attn_single_bwd_heads_kernel<1><<<grid, SQH_WARPS * 32, 0, s>>>(a, acc); break;
       case 2: attn_single_bwd_heads_kernel<2><<<grid, SQH_WARPS * 32, 0, s>>>(a, acc); break;

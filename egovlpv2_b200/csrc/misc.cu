@@ -339,12 +339,38 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     bias_c2 = hyper[2];
   }
   const float step = lr * sqrtf(bias_c2) / bias_c1;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float gi = g[i] * grad_scale;
-    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-    float pi = p[i] - step * mi / (sqrtf(vi) + eps);
-    pi -= lr * wd * pi;
+  const float ob1 = 1.0f - beta1, ob2 = 1.0f - beta2, decay = 1.0f - lr * wd;
+  auto upd = [&](float gi, float& mi, float& vi, float& pi) {
+    gi *= grad_scale;
+    mi = beta1 * mi + ob1 * gi;
+    vi = beta2 * vi + ob2 * gi * gi;
+    pi = (pi - step * mi / (sqrtf(vi) + eps)) * decay;
+  };
+  // 16-byte path (every arena slot is 64-element aligned): 4 parameters per thread per iteration
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0;
+  const long long n4 = vec ? (n >> 2) : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 g4 = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 m4 = reinterpret_cast<const float4*>(m)[i], v4 = reinterpret_cast<const float4*>(v)[i];
+    float4 p4 = reinterpret_cast<const float4*>(p)[i];
+    upd(g4.x, m4.x, v4.x, p4.x);
+    upd(g4.y, m4.y, v4.y, p4.y);
+    upd(g4.z, m4.z, v4.z, p4.z);
+    upd(g4.w, m4.w, v4.w, p4.w);
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    reinterpret_cast<float4*>(p)[i] = p4;
+    if (p_bf16) {
+      uint2 u;
+      u.x = pack_bf16(p4.x, p4.y);
+      u.y = pack_bf16(p4.z, p4.w);
+      reinterpret_cast<uint2*>(p_bf16)[i] = u;
+    }
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float mi = m[i], vi = v[i], pi = p[i];
+    upd(g[i], mi, vi, pi);
     m[i] = mi;
     v[i] = vi;
     p[i] = pi;
@@ -503,7 +529,7 @@ extern "C" int egv_adamw(float* p, const float* g, float* m, float* v, void* p_b
                          const float* hyper_dev, egv_stream_t stream) {
   if (n <= 0) return EGV_OK;
   if (!p || !g || !m || !v) return fail(EGV_ERR_ARG, "adamw: null pointer");
-  adamw_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)p_bf16, n, lr, beta1, beta2, eps,
+  adamw_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)p_bf16, n, lr, beta1, beta2, eps,
                                                                       weight_decay, bias_c1, bias_c2, grad_scale, hyper_dev);
   return check_launch("adamw_kernel");
 }
