@@ -90,11 +90,10 @@ EGV_DEVINL void unit_sync() {
 // acc[nt] (16 x 8 fp32 tiles, nt < KC/8) = A(16 x 64, fragments af) * S^T, S = smem tile [KC rows][64] (row = n index)
 template <int KC>
 EGV_DEVINL void mma_a_stile_nt(float (&acc)[KC / 8][4], const uint32_t (&af)[4][4], const bf16* s, int lane) {
-  // k-step outermost: consecutive HMMAs hit KC/8 different accumulators (no back-to-back dependent pairs)
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
+  for (int n2 = 0; n2 < KC / 16; ++n2) {
 #pragma unroll
-    for (int n2 = 0; n2 < KC / 16; ++n2) {
+    for (int kk = 0; kk < 4; ++kk) {
       uint32_t b0, b1, b2, b3;
       const bf16* p = s + (n2 * 16 + (lane & 7) + ((lane >> 4) << 3)) * LDS + kk * 16 + ((lane >> 3) & 1) * 8;
       ldmatrix_x4(b0, b1, b2, b3, smem_u32(p));
@@ -154,7 +153,9 @@ struct AttnSmem {
   static constexpr int BYTES = (ROW_TILES * ROWS + 2 * SROWS) * LDS * 2 + 2 * SROWS * 4;
 };
 
-template <int MODE, int NW, int KC, int NCH = 1>
+// SPLIT: the kernel may be launched with a.n_split > 1 (stream-side split, fp32 partials); compiled out elsewhere so the
+// warp-per-group kernels keep their register budget.
+template <int MODE, int NW, int KC, int NCH = 1, bool SPLIT = false>
 EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, int tid) {
   constexpr int NT = NW * 32;
   constexpr int ROWS = 16 * NW;
@@ -171,8 +172,12 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
   const int wq = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
 
-  const int split = (int)(item % a.n_split);
-  const long long item_ns = item / a.n_split;   // item index without the split
+  int split = 0;
+  long long item_ns = item;   // item index without the split
+  if (SPLIT && a.n_split > 1) {   // (64-bit division: keep it off the common path)
+    split = (int)(item % a.n_split);
+    item_ns = item / a.n_split;
+  }
   const int tile = (int)(item_ns % a.row_tiles);
   long long rest = item_ns / a.row_tiles;
   const int h = (int)(rest % a.H);
@@ -285,7 +290,7 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
   }
   // stream range of this split (whole chunks)
   int c_begin = 0, c_end = n_str;
-  if (a.n_split > 1) {
+  if (SPLIT && a.n_split > 1) {
     const int chunks = (n_str + KC - 1) / KC;
     const int per = (chunks + a.n_split - 1) / a.n_split;
     c_begin = split * per * KC;
@@ -421,7 +426,7 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
   }
 
   // ---------------------------------------------------------------- split: fp32 partials, merged by attn_split_finalize_kernel
-  if (a.n_split > 1) {
+  if (SPLIT && a.n_split > 1) {
     // ws[((item_ns * n_split + split) * ROWS + row) * W + ...],  W = 66 (FWD: m, l, o[64]), 64 (DQ) or 128 (DKV: dk, dv)
     constexpr int W = MODE == MODE_FWD ? 66 : (MODE == MODE_DQ ? 64 : 128);
     float* base = a.ws + ((item_ns * a.n_split + split) * ROWS + wq * 16) * W;
@@ -525,11 +530,11 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
 }
 
 // CTA-per-item variant (large groups): NW warps cooperate on one item.
-template <int MODE, int NW, int KC, int NCH = 1>
+template <int MODE, int NW, int KC, int NCH = 1, bool SPLIT = false>
 __global__ void __launch_bounds__(NW * 32) attn_cta_kernel(const AttnP a) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   for (long long item = blockIdx.x; item < a.items; item += gridDim.x) {
-    attn_unit<MODE, NW, KC, NCH>(a, item, smem_attn, threadIdx.x);
+    attn_unit<MODE, NW, KC, NCH, SPLIT>(a, item, smem_attn, threadIdx.x);
     __syncthreads();
   }
 }
@@ -1140,7 +1145,7 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
         a.items *= ns;
       }
     }
-    auto kern = attn_cta_kernel<MODE, 1, KC>;
+    auto kern = attn_cta_kernel<MODE, 1, KC, 1, true>;
     const int smem = AttnSmem<MODE, 1, KC>::BYTES;
     static bool cfg = false;
     if (!cfg) {
@@ -1165,7 +1170,7 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
         a.items *= ns;
       }
     }
-    auto kern = attn_cta_kernel<MODE, 2, KC>;
+    auto kern = attn_cta_kernel<MODE, 2, KC, 1, true>;
     const int smem = AttnSmem<MODE, 2, KC>::BYTES;
     static bool cfg = false;
     if (!cfg) {

@@ -274,7 +274,7 @@ attn_group_kernel(const __grid_constant__ GroupMaps maps, const AttnP a, const G
       const long long cls_off = ((long long)b * a.kv_bstride + a.cls_row) * a.ldkv + h * HD + (lane & 7) * 8;
       const long long stat_base = (((long long)b * a.H + h) * a.G + g) * a.Lq;
       // ---- stream side of this problem
-      mbar_wait(&str_empty[ks], kph ^ 1);
+      mbar_wait_sleep(&str_empty[ks], kph ^ 1, 100);
       uint8_t* sA = strbuf + (ks * 2 + 0) * STR_TILE_BYTES;
       uint8_t* sB = strbuf + (ks * 2 + 1) * STR_TILE_BYTES;
       if (lane == 0) {
@@ -305,7 +305,7 @@ attn_group_kernel(const __grid_constant__ GroupMaps maps, const AttnP a, const G
       }
       // ---- row side, pass by pass
       for (int pass = 0; pass < gp.npass; ++pass) {
-        mbar_wait(&row_empty[rs], rph ^ 1);
+        mbar_wait_sleep(&row_empty[rs], rph ^ 1, 100);
         const int rows = pass == 0 ? gp.r0 : gp.r1;
         uint8_t* rb = rowbuf + rs * NR * ROW_TILE_BYTES;
         if (lane == 0) {

@@ -173,7 +173,7 @@ attn_tiny_kernel(const __grid_constant__ TinyMaps maps, const AttnP a, const Tin
       const int gt = (int)(it % tp.n_gt);
       const int h = (int)((it / tp.n_gt) % a.H), b = (int)(it / ((long long)tp.n_gt * a.H));
       const int g0 = gt * TG;
-      mbar_wait(&empty[st], ph ^ 1);
+      mbar_wait_sleep(&empty[st], ph ^ 1, 100);
       uint8_t* sb = smem + st * Cfg::STAGE_BYTES;
       if (lane == 0) {
         uint32_t bytes = (uint32_t)NT * T_TILE_BYTES;

@@ -87,6 +87,29 @@ EGV_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, for single-thread "service" warps (TMA producers, MMA issuers): back off with nanosleep between polls.  A
+// tight try_wait loop is always eligible and takes every other issue slot of its SM sub-partition from the compute /
+// epilogue warps that share it (measured: ~20 % of all issued instructions of the GEMM were such polls).
+EGV_DEVINL void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(ns);
+    if (spins > (1u << 24)) {
+      printf("egv: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- TMA
 EGV_DEVINL void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
@@ -193,6 +216,51 @@ EGV_DEVINL uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------- CTA pairs (tcgen05 cta_group::2)
+// Two CTAs of a cluster (ranks 0 = leader, 1 = peer) run ONE 256-row MMA: each CTA stages its own 128 rows of A and
+// its own half of B's N rows in its own shared memory at the same offsets, the leader issues the instruction, each
+// CTA's tensor core accumulates its 128 rows x N columns into its own TMEM.  Per SM the operand traffic through shared
+// memory drops from A + B to A + B/2 per k-block (SS-mode 128 x 256 tiles otherwise run against the 128 B/clk port).
+template <int NCOLS>
+EGV_DEVINL void tmem_alloc_cg2(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+EGV_DEVINL void tmem_dealloc_cg2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+EGV_DEVINL void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all previously issued MMAs of this thread completed) on the mbarrier at this offset in BOTH CTAs
+EGV_DEVINL void umma_commit_cg2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)0x3)
+               : "memory");
+}
+// TMA load into THIS CTA's shared memory that signals the mbarrier at shared::cluster address `bar_cluster_addr`
+// (the leader's barrier, also when issued by the peer)
+EGV_DEVINL void tma_load_2d_cg2(void* dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+EGV_DEVINL void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes)
+               : "memory");
+}
+EGV_DEVINL void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
 // ----------------------------------------------------------------------------- legacy tensor path helpers (mma.sync, attention)

@@ -85,9 +85,26 @@ EGV_DEVINL float gelu_cdf(float x) {
   return x >= 0.f ? 1.0f - half_erfc : half_erfc;
 }
 
+// x Phi(x) = relu(x) - |x| * erfc(|x| / sqrt 2) / 2: same polynomial, no select / complement (3 instructions fewer)
+EGV_DEVINL float gelu_fwd(float x) {
+  const float ax = fabsf(x);
+  float d = fmaf(ax, 5.3829750e-6f, 4.8890636e-5f);
+  d = fmaf(d, ax, 3.8003575e-5f);
+  d = fmaf(d, ax, 3.2776263e-3f);
+  d = fmaf(d, ax, 2.1141006e-2f);
+  d = fmaf(d, ax, 4.9867347e-2f);
+  d = fmaf(d, ax, 1.0f);
+  float r = rcp_approx(d);
+  r *= r;
+  r *= r;
+  r *= r;
+  r *= r;
+  return fmaf(-0.5f * ax, r, fmaxf(x, 0.0f));
+}
+
 template <int ACT>
 EGV_DEVINL float apply_act(float v, float auxv) {
-  if (ACT == EGV_ACT_GELU) return v * gelu_cdf(v);
+  if (ACT == EGV_ACT_GELU) return gelu_fwd(v);
   if (ACT == EGV_ACT_RELU) return fmaxf(v, 0.0f);
   if (ACT == EGV_ACT_TANH) return tanhf(v);
   if (ACT == EGV_ACT_GELU_BWD) {
@@ -242,12 +259,12 @@ EGV_DEVINL void epi_rows_scalar(const GemmParams& p, const float* stg, int lane,
   if (p.colsum && c_ok) atomicAdd(p.colsum + gcol, cs);
 }
 
-template <int BN>
+template <int BN, int CL = 1>
 struct GemmCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CL) * BK * 2;   // a CTA pair splits B's N rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = CL == 2 ? (BN == 256 ? 6 : 8) : (BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8)));
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_FLOATS * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SLACK = 1024;
@@ -255,15 +272,19 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // allocation: power of two
 };
 
-// CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs of a cluster work on vertically adjacent output tiles
-// (same n-tile, m-tiles 2i and 2i+1) and share the B operand: each CTA loads one half of the B tile and multicasts it
-// into both shared memories, so a CTA pulls A (16 KB) + half of B per k-block through L2 instead of A + B.  The GEMMs
-// of this workload are L2->SM bandwidth-bound at 128 x 256 tiles (~1 GB per launch), which is what this relieves.
+// CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs of a cluster form a tcgen05 CTA pair (cta_group::2) on a
+// 256 x BN output tile (m-tiles 2i and 2i+1 of the same n-tile): each CTA stages its own 128 rows of A and its own half
+// of B's N rows, the leader (rank 0) issues M = 256 MMAs for both, each CTA's epilogue drains its own TMEM.  Motivation
+// (tools/gemm_bench.py): single-CTA 128 x 256 SS-mode mainloops stop at ~1470 TF/s because A + B per k-block needs
+// ~190 B/clk through a 128 B/clk shared-memory port; the pair needs ~126 B/clk.  STATUS: bit-identical results
+// (tests/test_kernels_gpu.py::test_gemm_cluster_pairs_match_single_cta) but 2x SLOWER than the single-CTA kernel in
+// round 1 (657 vs 1355 TF/s, K = 768): the leader's MMA thread spends most of each tile waiting for the accumulator
+// release (16 arrivals, 8 of them remote with cluster-scope release fences) -- off by default (EGV_GEMM_CLUSTER=1).
 template <int BN, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // keep the shared address space visible to the compiler (pointer + offset, no integer round trip)
@@ -293,16 +314,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);   // a stage is free once every CTA of the cluster has consumed it
+      mbar_init(&full_bar[s], CL);    // pair: one arrive.expect_tx per CTA, both on the LEADER's barrier
+      mbar_init(&empty_bar[s], 1);    // pair: the leader's commit is multicast to both CTAs' barriers
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], EPI_WARPS);
+      mbar_init(&tmem_empty[s], EPI_WARPS * CL);   // pair: both CTAs' epilogue warps release the leader's accumulator
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if (CL == 2) tmem_alloc_cg2<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) {   // barrier inits must be visible to the peer before it multicasts into / arrives on them
@@ -325,34 +349,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int kb0 = ks * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 64);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int k0 = kb * BK;
-          if (A_MN) {
+          if (CL == 2) {
+            // CTA pair: this CTA's 128 rows of A and its half of B's N rows land in ITS shared memory; every byte is
+            // accounted on the LEADER's full barrier, which gates the leader's M = 256 MMAs.
+            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0u);
+            mbar_arrive_expect_tx_cluster(fb, Cfg::STAGE_BYTES);
+            if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, k0);
-          } else {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
-          }
-          if (CL > 1) {
-            // this CTA fetches half `cta_rank` of the B tile and multicasts it to both CTAs of the cluster
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg2(sa + j * 8192, &tmap_a, fb, m0 + 64 * j, k0);
+            } else {
+              tma_load_2d_cg2(sa, &tmap_a, fb, k0, m0);
+            }
+            const int nh = n0 + (int)cta_rank * (BN / 2);
             if (B_MN) {
 #pragma unroll
-              for (int jj = 0; jj < BN / 128; ++jj) {
-                const int j = (int)cta_rank * (BN / 128) + jj;
-                tma_load_2d_mc(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0, (uint16_t)0x3);
-              }
+              for (int j = 0; j < BN / 128; ++j) tma_load_2d_cg2(sb + j * 8192, &tmap_b, fb, nh + 64 * j, k0);
             } else {
-              tma_load_2d_mc(sb + cta_rank * (Cfg::B_BYTES / 2), &tmap_b, &full_bar[stage], k0,
-                             n0 + (int)cta_rank * (BN / 2), (uint16_t)0x3);
+              tma_load_2d_cg2(sb, &tmap_b, fb, k0, nh);
             }
-          } else if (B_MN) {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
           } else {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if (A_MN) {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, k0);
+            } else {
+              tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
+            } else {
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -363,26 +395,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (lane == 0 && cta_rank == 0) {   // pair: the leader issues for both CTAs
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CL, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // encoded (>>4) start-address advance per UMMA_K step
       constexpr uint32_t a_adv = A_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
       constexpr uint32_t b_adv = B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      const uint32_t peer = cta_rank ^ 1u;
       for (int w = first_item; w < p.total_items; w += item_stride, ++it) {
         const int ks = w % p.split_k;
         const int kb0 = ks * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
         const int as = it & 1;
         const uint32_t use = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(&tmem_empty[as], use ^ 1);
+        mbar_wait_sleep(&tmem_empty[as], use ^ 1, 32);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_sleep(&full_bar[stage], phase, 20);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -390,17 +421,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t bdesc = B_MN ? umma_desc_sw128(sb, 8192, 1024) : umma_desc_sw128(sb, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
-                      (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CL == 2)
+              umma_bf16_cg2(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
+                            (kb > kb0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
+                        (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (CL > 1) umma_commit_addr(mapa_shared(smem_u32(&empty_bar[stage]), peer));  // ... in the peer CTA too
+          // smem slot reusable once these MMAs retire (pair: in both CTAs)
+          if (CL == 2) umma_commit_cg2(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (pair: of both CTAs)
+        if (CL == 2) umma_commit_cg2(&tmem_full[as]);
+        else umma_commit(&tmem_full[as]);
       }
     }
   } else if (warp >= 4) {
@@ -457,7 +495,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if (CL == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0u));   // the leader's barrier
+        else mbar_arrive(&tmem_empty[as]);
+      }
     }
   }
   tc_fence_before();
@@ -468,7 +509,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (CL == 2) tmem_dealloc_cg2<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -656,7 +698,7 @@ int get_tensor_map_nd(const void* ptr, int rank, const uint64_t* dims, const uin
 
 template <int BN, bool A_MN, bool B_MN, int CL>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL>;
   if (!configured) {
@@ -698,7 +740,7 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
 
 static int g_force_simt = 0;
 static int g_plan_mode = -1;      // -1: env EGV_GEMM_PLAN (default 1); 0: round-1 heuristic; 1: cost-model planner; 2: + 192-wide tiles
-static int g_cluster_mode = -1;   // -1: env EGV_GEMM_CLUSTER (default 0 = off: measured slower); 0 off; 1 on
+static int g_cluster_mode = -1;   // -1: env EGV_GEMM_CLUSTER (default 0 = off: the cta_group::2 pairs are correct but slower, see above); 0 off; 1 on
 
 }  // namespace egv
 

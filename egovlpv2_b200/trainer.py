@@ -108,6 +108,35 @@ class PretrainStep:
         self.graph.replay()
         return self.static_loss, self.static_loss_dict
 
+    # ------------------------------------------------------------------ input prefetch for the captured step
+    def prefetch(self, host_batch):
+        """Start the H2D copy of a (pinned) host batch into a staging buffer on a copy stream; it overlaps whatever the
+        compute stream is doing.  `step_graph_prefetched()` then moves it into the graph's static inputs (a device-side
+        copy) and replays.  The reference gets the same overlap from its DataLoader workers + non_blocking .cuda()."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staging = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._h2d_done = torch.cuda.Event()
+            self._staging_free = torch.cuda.Event()
+            self._staging_free.record()
+        cs = self._copy_stream
+        cs.wait_event(self._staging_free)          # the previous step's device-side copy has drained the staging buffer
+        with torch.cuda.stream(cs):
+            for k, v in host_batch.items():
+                self._staging[k].copy_(v, non_blocking=True)
+            self._h2d_done.record(cs)
+
+    def step_graph_prefetched(self):
+        """Consume the batch started with `prefetch()`: staging -> static inputs, then one graph replay."""
+        main = torch.cuda.current_stream()
+        main.wait_event(self._h2d_done)
+        for k, v in self._staging.items():
+            self.static[k].copy_(v, non_blocking=True)
+        self._staging_free.record(main)
+        self.opt.advance()
+        self.graph.replay()
+        return self.static_loss, self.static_loss_dict
+
     def step(self, dev_batch):
         """forward + backward + (all-reduce) + AdamW, eager launches; returns the detached total loss (device scalar)."""
         self.opt.advance()

@@ -76,8 +76,8 @@ typedef struct egv_gemm_args {
 int egv_gemm_bf16(const egv_gemm_args* args, egv_stream_t stream);
 /* test hook: route every GEMM through the SIMT fallback kernel (1) or restore normal dispatch (0) */
 void egv_gemm_force_simt(int on);
-/* 1: large problems run as 2-CTA clusters that share the B tile through TMA multicast; 0 (default): single CTAs.
- * Measured in round 1: the cluster variant is 10-15 % slower at the cfg-3 shapes (lock-step stage recycling). */
+/* 1: large problems run as tcgen05 CTA pairs (cta_group::2: 256 x BN tiles, each CTA stages half of B); 0 (default):
+ * single CTAs.  Round 1: the pair kernel is bit-identical but ~2x slower (accumulator hand-back latency), see gemm.cu. */
 void egv_gemm_set_cluster(int on);
 /* tile-width / split-K planner for plain fp32-output GEMMs (weight gradients): 0 = round-1 heuristic, 1 = cost model
  * over {256,128}-wide tiles x split (default), 2 = also 192-wide tiles.  Env EGV_GEMM_PLAN sets the default. */

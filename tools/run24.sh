@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 180 python -m pytest tests/test_kernels_gpu.py -m gpu -q --tb=short -p no:cacheprovider -k "cluster_pairs" -x > gpurun_out/pair_tests.log 2>&1
+echo "== pair tests: exit $? : $(tail -n 1 gpurun_out/pair_tests.log)"; grep -E "^E|FAILED|egv:" gpurun_out/pair_tests.log | head -12
+for c in 1 0; do echo CLUSTER=$c; EGV_GEMM_CLUSTER=$c GEMM_LAYOUTS=NT,NN,TN timeout 240 python tools/gemm_bench.py 25096x2304x768 25096x3072x768 25096x768x3072 25096x768x768 2>&1 | grep -E "TN|bf16 out|mainloop|residual|gelu" | grep -v "bias + bf16"; done | tee gpurun_out/pair_bench.txt
