@@ -254,8 +254,10 @@ def run_ours(a, rank, world, local_rank):
     flops, parts = step_flops(a.batch, a.frames, S=a.seq)
     sustained, burst, hbm, peak_src = peaks()
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(tp):   # dram__bytes_read+write per GEMM launch from the committed ncu capture of the same step
+    import glob
+    tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))
+    tp = tps[-1] if tps else None
+    if tp:   # dram__bytes_read+write per GEMM launch from the latest committed ncu capture of the same step
         traffic = json.load(open(tp)).get("gemm_dram_bytes_per_launch")
     gemm_t = sum(t for (r, k), (t, w, n) in prof.items() if k == "gemm")
     gemm_w = sum(w for (r, k), (t, w, n) in prof.items() if k == "gemm")
@@ -295,7 +297,7 @@ def run_ours(a, rank, world, local_rank):
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all GEMMs of one step)", "achieved": achieved,
                      "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained, "peak_source": peak_src,
                      "launches": gemm_n, "avg_launch_us": gemm_t / max(gemm_n, 1) * 1e6, "traffic": traffic,
-                     "traffic_note": "avg DRAM bytes per GEMM launch, ncu capture profiles/r01_gemm_traffic.json"},
+                     "traffic_note": "avg DRAM bytes per GEMM launch, ncu capture %s" % (os.path.relpath(tp, ROOT) if tp else None)},
     }
     if cpu_val is not None:
         line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_desc}
@@ -330,7 +332,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--seq", type=int, default=32)
-    ap.add_argument("--cpu-sample", type=int, default=1, dest="cpu_sample")
+    ap.add_argument("--cpu-sample", type=int, default=3, dest="cpu_sample",
+                    help="clips per step of the CPU port (one step of 3 clips is ~15 s on 16 host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"], help="embedding all-gather implementation")
     ap.add_argument("--no-graph", action="store_true", help="eager kernel launches instead of replaying a captured CUDA graph")

@@ -255,12 +255,15 @@ EGV_DEVINL void tma_load_2d_cg2(void* dst, const void* tmap, uint32_t bar_cluste
       ::"r"(smem_u32(dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// Remote arrivals are RELAXED: they only move barrier counters (transaction bytes; "my tcgen05.ld of this accumulator
+// has completed", which tcgen05.wait::ld + fence::before_thread_sync already ordered).  The default .release at cluster
+// scope compiles to MEMBAR + ERRBAR, i.e. it waits for every outstanding global store of the warp.
 EGV_DEVINL void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes)
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes)
                : "memory");
 }
 EGV_DEVINL void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
 // ----------------------------------------------------------------------------- legacy tensor path helpers (mma.sync, attention)

@@ -357,7 +357,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // CTA pair: this CTA's 128 rows of A and its half of B's N rows land in ITS shared memory; every byte is
             // accounted on the LEADER's full barrier, which gates the leader's M = 256 MMAs.
             const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0u);
-            mbar_arrive_expect_tx_cluster(fb, Cfg::STAGE_BYTES);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            else mbar_arrive_expect_tx_cluster(fb, Cfg::STAGE_BYTES);
             if (A_MN) {
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg2(sa + j * 8192, &tmap_a, fb, m0 + 64 * j, k0);
@@ -496,7 +497,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CL == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0u));   // the leader's barrier
+        if (CL == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0u));   // the leader's barrier
         else mbar_arrive(&tmem_empty[as]);
       }
     }

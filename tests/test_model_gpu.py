@@ -212,3 +212,41 @@ def test_optimizer_arena_step_matches_torch_adamw_semantics():
     assert torch.equal(sh, p.detach().to(torch.bfloat16))
     weights.cache().arena = None
     weights.cache().clear()
+
+
+def test_two_streams_match_single_stream(golden_dir):
+    """The text tower on a side CUDA stream (egovlpv2_b200/streams.py) must not change the step: same losses, logits and
+    gradients as the single-stream run (up to the order of fp32 atomics)."""
+    from egovlpv2_b200 import streams
+    fx, c, shapes, sd, data, plan = _golden(golden_dir)
+    d = {k: v.to(DEV) for k, v in data.items()}
+    batch = {"video": d["video"], "text": {"input_ids": d["input_ids"], "attention_mask": d["attention_mask"]},
+             "text_mlm_ids": d["text_mlm_ids"], "text_mlm_labels": d["text_mlm_labels"]}
+    args = types.SimpleNamespace(world_size=1, rank=0)
+    results = []
+    try:
+        for on in (False, True):
+            streams.enable(on)
+            assert streams.enabled() == on
+            model = build_tiny(c)
+            model.load_state_dict(sd, strict=False)
+            model.eval().to(DEV)
+            model.itm_plan = plan
+            for _ in range(2):   # twice: the second pass runs against a warm allocator with blocks owned by both streams
+                model.zero_grad(set_to_none=True)
+                loss, loss_dict, ret = model(batch, d["noun_vec"], d["verb_vec"], lambda t, n, a: t, 1, args,
+                                             {"loss": {"type": "EgoNCE"}}, EgoNCE(), 0, task_names="EgoNCE_MLM_ITM")
+                loss.backward()
+                streams.join()
+            torch.cuda.synchronize()
+            results.append(({k: float(v) for k, v in loss_dict.items()}, ret["cross_attn_itm_logits"].float().cpu(),
+                            {k: p.grad.float().cpu() for k, p in model.named_parameters() if p.grad is not None}))
+    finally:
+        streams.enable(False)
+    (l0, i0, g0), (l1, i1, g1) = results
+    for k in l0:
+        assert abs(l0[k] - l1[k]) <= 1e-4 * max(1.0, abs(l0[k])), (k, l0[k], l1[k])
+    assert (i0 - i1).abs().max().item() <= 1e-4
+    assert g0.keys() == g1.keys()
+    for k in g0:
+        assert rel(g1[k], g0[k]) <= 2e-3 or (g0[k].norm().item() < 1e-6 and g1[k].norm().item() < 1e-6), (k, rel(g1[k], g0[k]))
