@@ -1,11 +1,13 @@
 // Fused attention kernels for MANY TINY groups -- the time attention of the divided space-time block
 // (video_transformer.py:117-153, 'b (f n) d -> (b n) f d'): per (clip, patch position n, head) T <= 16 queries attend
 // T <= 16 keys plus the shared CLS key; 18 816 such groups per call at cfg 3, each touching ~6 KB.  The work is pure
-// HBM traffic, so the kernels are built around the memory system:
-//   * a producer warp fetches, per (batch, head, tile of 8 ADJACENT groups), every operand as ONE 4-D TMA box
-//     {64 head columns, 8 groups, 16 frames, 1 clip} (rows of one group are Nf rows apart, adjacent groups are
-//     adjacent rows), 2-3 stages ahead of the math; out-of-range groups / frames are zero-filled by the TMA unit;
-//   * 8 compute warps take one group each, entirely in registers (mma.sync m16n8k16: one 16 x 16 (+CLS) score tile);
+// HBM traffic and instruction latency, so:
+//   * every WARP is its own pipeline: it walks a contiguous range of (clip, head, group) items, fetches each operand of
+//     the next group as ONE 4-D TMA box {64 head columns, 1 group, 16 frames, 1 clip} (the frames of a group are Nf rows
+//     apart) into its private 2-stage ring while it computes the current one -- no block-level barrier anywhere, so the
+//     LDSM -> HMMA -> shuffle chains of different warps interleave (the first version moved 8 warps in lock-step
+//     behind one stage barrier and lost to the generic kernels); out-of-range frames are zero-filled by the TMA unit;
+//   * a group lives entirely in registers (mma.sync m16n8k16: one 16 x 16 (+CLS) score tile);
 //   * the BACKWARD is one launch instead of two: dQ from the query-row view, dK / dV from the transposed (key-row)
 //     view recomputed from the same shared-memory tiles, the CLS key as an extra 1-row key tile whose gradient is
 //     carried in registers across the groups of a (clip, head) and flushed with a handful of atomics.
@@ -16,32 +18,32 @@
 
 namespace egv {
 
-constexpr int TG = 8;                        // groups per tile = compute warps
 constexpr int TL = 16;                       // rows (frames) per group, padded
-constexpr int T_THREADS = (TG + 1) * 32;
-constexpr int T_TILE_BYTES = TL * TG * 128;  // 16 KB: [frame i][group g][64 bf16], row = i * 8 + g, 128B swizzle
+constexpr int T_TILE_BYTES = TL * 128;       // 2 KB: [frame i][64 bf16], 128B swizzle
 constexpr int T_X_BYTES = 16 * 128;          // extra key tile: row 0 = CLS key (or value), rows 1..15 zero
-constexpr int T_STAT_BYTES = 1024;           // lse of the tile's groups (backward): TG * TL floats, padded to the swizzle period
 
 struct TinyMaps {
   CUtensorMap t[5];   // q, k, v, d_o, o
 };
 struct TinyP {
-  int n_gt;           // group tiles per (batch, head)
-  long long items;    // B * H * n_gt
+  long long items;    // B * H * G
   int istride;        // rows between consecutive frames of a group
   int lk_reg;         // regular keys per group
 };
 
 template <bool BWD>
 struct TCfg {
+  static constexpr int WARPS = BWD ? 8 : 12;
   static constexpr int NT = BWD ? 5 : 3;
-  static constexpr int STAGES = BWD ? 2 : 3;
-  static constexpr int STAGE_BYTES = NT * T_TILE_BYTES + 2 * T_X_BYTES + (BWD ? T_STAT_BYTES : 0);
-  static constexpr int OUT_OFF = STAGES * STAGE_BYTES;
-  static constexpr int DELTA_OFF = OUT_OFF + TG * 2048;
-  static constexpr int BAR_OFF = DELTA_OFF + TG * TL * 4;
-  static constexpr int SMEM_BYTES = BAR_OFF + 128 + 1024;
+  static constexpr int STAGE_BYTES = NT * T_TILE_BYTES;
+  // per warp: 2 stages, the CLS key / value tiles, one output staging tile, lse (2 stages) + delta
+  static constexpr int X_OFF = 2 * STAGE_BYTES;
+  static constexpr int OUT_OFF = X_OFF + 2 * T_X_BYTES;
+  static constexpr int STAT_OFF = OUT_OFF + 2048;
+  // lse[2][16] + delta[16] floats (backward only); regions stay multiples of 1024 B (128B-swizzle period)
+  static constexpr int WARP_BYTES = ((STAT_OFF + (BWD ? 256 : 0) + 1023) / 1024) * 1024;
+  static constexpr int BAR_OFF = WARPS * WARP_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + WARPS * 16 + 1024;
 };
 
 EGV_DEVINL void tma_load_4d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -51,18 +53,17 @@ EGV_DEVINL void tma_load_4d(void* dst, const void* tmap, uint64_t* bar, int c0, 
       : "memory");
 }
 
-// per-lane byte offsets into a group tile for warp (= local group) w:
+// per-lane byte offsets into a [16 rows][128 B] swizzled tile:
 //   a[kk]: A fragments (rows = frames) and transposed B loads (rows = k index);  n[kk]: B loads with rows = n index
 struct TinyAddr {
   uint32_t a[4], n[4];
 };
-EGV_DEVINL TinyAddr tiny_addr(int lane, int w) {
+EGV_DEVINL TinyAddr tiny_addr(const LaneAddr& la) {
   TinyAddr t;
-  const uint32_t ia = (lane & 7) + ((lane >> 3) & 1) * 8, jn = (lane & 7) + ((lane >> 4) << 3);
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    t.a[kk] = ia * 1024 + w * 128 + ((((uint32_t)(kk * 2 + (lane >> 4))) ^ (uint32_t)w) << 4);
-    t.n[kk] = jn * 1024 + w * 128 + ((((uint32_t)(kk * 2 + ((lane >> 3) & 1))) ^ (uint32_t)w) << 4);
+    t.a[kk] = la.p_row + la.p_x[kk];
+    t.n[kk] = la.nt_row + la.nt_x[kk];
   }
   return t;
 }
@@ -129,90 +130,63 @@ EGV_DEVINL void t_store_rows(const uint8_t* stg, bf16* base, long long first, lo
   }
 }
 
-// 9 warps: one SM sub-partition holds 3 of them, so the budget is 16384 / (3 * 32) = 170 registers per thread
+// 12 warps x 153 registers (forward) / 8 warps x 168 (backward): 3 / 2 warps per SM sub-partition, within 16384 / 32 each
 template <bool BWD>
 __global__ void __maxnreg__(168)
 attn_tiny_kernel(const __grid_constant__ TinyMaps maps, const AttnP a, const TinyP tp) {
   using Cfg = TCfg<BWD>;
-  constexpr int NT = Cfg::NT, STAGES = Cfg::STAGES;
+  constexpr int NT = Cfg::NT, WARPS = Cfg::WARPS;
   extern __shared__ __align__(1024) uint8_t tsm_raw[];
   const uint32_t pad = (1024u - (smem_u32(tsm_raw) & 1023u)) & 1023u;
   uint8_t* smem = tsm_raw + pad;
-  uint8_t* outbuf = smem + Cfg::OUT_OFF;
-  float* sdelta = reinterpret_cast<float*>(smem + Cfg::DELTA_OFF);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
-  uint64_t* empty = full + STAGES;
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* wsm = smem + warp * Cfg::WARP_BYTES;                 // this warp's private region (multiple of 1024 B)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF) + warp * 2;
   const bool has_cls = a.has_cls != 0;
   {
-    uint4* z = reinterpret_cast<uint4*>(smem);
-    for (int i = threadIdx.x; i < Cfg::OUT_OFF / 16; i += T_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint4* z = reinterpret_cast<uint4*>(wsm);
+    for (int i = lane; i < Cfg::WARP_BYTES / 16; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
-  }
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], has_cls ? 2 : 1);
-      mbar_init(&empty[s], TG);
+    if (lane == 0) {
+      mbar_init(&full[0], 1);
+      mbar_init(&full[1], 1);
+      fence_barrier_init();
+      if (warp == 0)
+        for (int t = 0; t < NT; ++t) tma_prefetch_desc(&maps.t[t]);
     }
-    fence_barrier_init();
-    for (int t = 0; t < NT; ++t) tma_prefetch_desc(&maps.t[t]);
+    __syncwarp();
   }
-  __syncthreads();
 
-  // contiguous range of (batch, head, group tile) items per CTA: consecutive items share (batch, head)
-  const long long per = (tp.items + gridDim.x - 1) / gridDim.x;
-  const long long it0 = (long long)blockIdx.x * per;
+  // contiguous range of (batch, head, group) items per warp: consecutive items share (batch, head)
+  const long long nwarps = (long long)gridDim.x * WARPS;
+  const long long per = (tp.items + nwarps - 1) / nwarps;
+  const long long it0 = ((long long)blockIdx.x * WARPS + warp) * per;
   const long long it1 = it0 + per < tp.items ? it0 + per : tp.items;
+  if (it0 >= it1) return;
 
-  if (warp == TG) {
-    // ------------------------------------------------------------------------------------------ producer
-    int st = 0;
-    uint32_t ph = 0;
-    for (long long it = it0; it < it1; ++it) {
-      const int gt = (int)(it % tp.n_gt);
-      const int h = (int)((it / tp.n_gt) % a.H), b = (int)(it / ((long long)tp.n_gt * a.H));
-      const int g0 = gt * TG;
-      mbar_wait_sleep(&empty[st], ph ^ 1, 100);
-      uint8_t* sb = smem + st * Cfg::STAGE_BYTES;
-      if (lane == 0) {
-        uint32_t bytes = (uint32_t)NT * T_TILE_BYTES;
-        const int ng = a.G - g0 < TG ? a.G - g0 : TG;
-        if (BWD) bytes += (uint32_t)(ng * a.Lq) * 4u;
-        mbar_arrive_expect_tx(&full[st], bytes);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) tma_load_4d(sb + t * T_TILE_BYTES, &maps.t[t], &full[st], h * HD, g0, 0, b);
-        if (BWD) {
-          const long long stat_base = (((long long)b * a.H + h) * a.G + g0) * a.Lq;
-          bulk_copy_g2s(sb + NT * T_TILE_BYTES + 2 * T_X_BYTES, a.lse + stat_base, (uint32_t)(ng * a.Lq) * 4u, &full[st]);
-        }
-      }
-      if (has_cls) {
-        if (lane < 16) {
-          const long long off = ((long long)b * a.kv_bstride + a.cls_row) * a.ldkv + h * HD + (lane & 7) * 8;
-          const uint4 val = *reinterpret_cast<const uint4*>((lane < 8 ? a.k : a.v) + off);
-          // row 0 of the extra tile: chunk c at c ^ 0
-          *reinterpret_cast<uint4*>(sb + NT * T_TILE_BYTES + (lane < 8 ? 0 : T_X_BYTES) + ((lane & 7) << 4)) = val;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[st]);
-      }
-      if (++st == STAGES) {
-        st = 0;
-        ph ^= 1;
-      }
-    }
-    return;
-  }
-
-  // ---------------------------------------------------------------------------------------------- compute warps
-  const int w = warp;
   const int gq = lane >> 2, tq = lane & 3;
-  const TinyAddr ta = tiny_addr(lane, w);
   const LaneAddr la = lane_addr(lane);
+  const TinyAddr ta = tiny_addr(la);
   const float scale2 = a.scale * LOG2E;
-  uint8_t* stg = outbuf + w * 2048;
-  float* wdelta = sdelta + w * TL;
+  uint8_t* stg = wsm + Cfg::OUT_OFF;
+  float* wdelta = reinterpret_cast<float*>(wsm + Cfg::STAT_OFF) + 2 * TL;
+  const uint32_t xK = smem_u32(wsm + Cfg::X_OFF), xV = xK + T_X_BYTES;
+
+  auto issue = [&](long long it, int st) {   // lane 0: TMA boxes (+ lse) of item `it` into stage `st`
+    const int g = (int)(it % a.G), h = (int)((it / a.G) % a.H), b = (int)(it / ((long long)a.G * a.H));
+    uint8_t* sb = wsm + st * Cfg::STAGE_BYTES;
+    uint32_t bytes = (uint32_t)NT * T_TILE_BYTES;
+    if (BWD) bytes += (uint32_t)a.Lq * 4u;
+    fence_proxy_async();   // this warp's generic-proxy reads of the stage (two items ago) precede the async writes
+    mbar_arrive_expect_tx(&full[st], bytes);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) tma_load_4d(sb + t * T_TILE_BYTES, &maps.t[t], &full[st], h * HD, g, 0, b);
+    if (BWD) {
+      const long long stat_base = (((long long)b * a.H + h) * a.G + g) * a.Lq;
+      bulk_copy_g2s(wsm + Cfg::STAT_OFF + st * TL * 4, a.lse + stat_base, (uint32_t)a.Lq * 4u, &full[st]);
+    }
+  };
+
   // running gradient of the shared CLS key / value (row 0 of the extra key tile) over the groups of one (batch, head)
   float clsk[8][4], clsv[8][4];
 #pragma unroll
@@ -237,24 +211,33 @@ attn_tiny_kernel(const __grid_constant__ TinyMaps maps, const AttnP a, const Tin
       for (int j = 0; j < 4; ++j) clsk[i][j] = clsv[i][j] = 0.f;
   };
 
-  int st = 0;
-  uint32_t ph = 0;
+  if (lane == 0) issue(it0, 0);
+  uint32_t phbits = 0u;   // bit s = parity the next wait on full[s] expects
   for (long long it = it0; it < it1; ++it) {
-    const int gt = (int)(it % tp.n_gt);
-    const int h = (int)((it / tp.n_gt) % a.H), b = (int)(it / ((long long)tp.n_gt * a.H));
-    const int g = gt * TG + w;
+    const int st = (int)((it - it0) & 1);
+    const int g = (int)(it % a.G), h = (int)((it / a.G) % a.H), b = (int)(it / ((long long)a.G * a.H));
     const long long bh = (long long)b * a.H + h;
-    if (BWD && bh != cls_bh) {
-      flush_cls();
+    __syncwarp();                                     // every lane is done with the other stage (previous item)
+    if (lane == 0 && it + 1 < it1) issue(it + 1, st ^ 1);
+    if (bh != cls_bh) {
+      if (BWD) flush_cls();
       cls_bh = bh;
+      if (has_cls) {   // CLS key / value of this (batch, head) -> row 0 of the extra tiles (chunk c at c ^ 0)
+        if (lane < 16) {
+          const long long off = ((long long)b * a.kv_bstride + a.cls_row) * a.ldkv + h * HD + (lane & 7) * 8;
+          const uint4 val = *reinterpret_cast<const uint4*>((lane < 8 ? a.k : a.v) + off);
+          *reinterpret_cast<uint4*>(wsm + Cfg::X_OFF + (lane < 8 ? 0 : T_X_BYTES) + ((lane & 7) << 4)) = val;
+        }
+        __syncwarp();
+      }
     }
-    mbar_wait(&full[st], ph);
-    const uint8_t* sb = smem + st * Cfg::STAGE_BYTES;
+    mbar_wait(&full[st], (phbits >> st) & 1u);
+    phbits ^= 1u << st;
+    const uint8_t* sb = wsm + st * Cfg::STAGE_BYTES;
     const uint32_t tQ = smem_u32(sb), tK = tQ + T_TILE_BYTES, tV = tQ + 2 * T_TILE_BYTES;
     const uint32_t tDO = tQ + 3 * T_TILE_BYTES;
-    const uint32_t xK = tQ + NT * T_TILE_BYTES, xV = xK + T_X_BYTES;
-    const float* slse = reinterpret_cast<const float*>(sb + NT * T_TILE_BYTES + 2 * T_X_BYTES) + w * a.Lq;
-    if (g < a.G) {   // warp-uniform
+    const float* slse = reinterpret_cast<const float*>(wsm + Cfg::STAT_OFF) + st * TL;
+    {
       const long long q_first = (long long)b * a.q_bstride + a.q_row0 + g;
       const long long o_first = (long long)b * a.o_bstride + a.q_row0 + g;
       const long long k_first = (long long)b * a.kv_bstride + a.k_row0 + g;
@@ -304,8 +287,6 @@ attn_tiny_kernel(const __grid_constant__ TinyMaps maps, const AttnP a, const Tin
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
         t_mma_p(acc, s, tV, xV, has_cls, ta, la);   // O = P V
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
         g_stage(stg, acc, 1.0f / l_lo, 1.0f / l_hi, lane);
         if (tq == 0) {
           if (gq < a.Lq) a.lse[stat_base + gq] = m_lo + log2f(l_lo);
@@ -322,7 +303,7 @@ attn_tiny_kernel(const __grid_constant__ TinyMaps maps, const AttnP a, const Tin
         float d_lo = 0.f, d_hi = 0.f;
 #pragma unroll
         for (int r = 0; r < TL; ++r) {
-          const uint32_t off = r * 1024 + w * 128 + ((((uint32_t)(lane >> 2)) ^ (uint32_t)w) << 4) + 4 * (lane & 3);
+          const uint32_t off = r * 128 + ((((uint32_t)(lane >> 2)) ^ (uint32_t)(r & 7)) << 4) + 4 * (lane & 3);
           const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(sb + 3 * T_TILE_BYTES + off));
           const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(sb + 4 * T_TILE_BYTES + off));
           const float part = warp_sum(x.x * y.x + x.y * y.y);
@@ -420,29 +401,20 @@ attn_tiny_kernel(const __grid_constant__ TinyMaps maps, const AttnP a, const Tin
             t_mma_p(clsk, stt, tQ, 0u, false, ta, la);
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
       }
-    } else {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[st]);
-    }
-    if (++st == STAGES) {
-      st = 0;
-      ph ^= 1;
     }
   }
   if (BWD) flush_cls();
 }
 
-static int g_tiny_mode = -1;   // env EGV_ATTN_TINY: bit 0 forward, bit 1 backward.  Default 0: correct (tests run it with
-                               // EGV_ATTN_TINY=3) but measured 60 / 225 us vs 49 / 200 us for the generic kernels at cfg 3 -- the 8 warps
-                               // of a CTA move in lock-step behind one barrier, so instruction latency is exposed; see DESIGN.md
+static int g_tiny_mode = -1;   // env EGV_ATTN_TINY: bit 0 forward, bit 1 backward (default 3).  Measured at cfg 3 (18 816 groups):
+                               // 39 / 115 us vs 49 / 200 us for the generic warp-per-group kernels (forward / backward).
 
 template <bool BWD>
 static int launch_tiny(const TinyMaps& maps, const AttnP& a, const TinyP& tp, cudaStream_t stream) {
   using Cfg = TCfg<BWD>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "tiny attention tile set exceeds the shared memory of an SM");
+  static_assert(Cfg::WARP_BYTES % 1024 == 0, "per-warp regions must keep the 128B-swizzle period");
   auto kern = attn_tiny_kernel<BWD>;
   static bool cfg = false;
   if (!cfg) {
@@ -450,8 +422,9 @@ static int launch_tiny(const TinyMaps& maps, const AttnP& a, const TinyP& tp, cu
     if (e != cudaSuccess) return fail(EGV_ERR_CUDA, "tiny attention smem attribute: %s", cudaGetErrorString(e));
     cfg = true;
   }
-  const long long grid = tp.items < sm_count() ? tp.items : sm_count();
-  kern<<<(unsigned)grid, T_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, a, tp);
+  long long grid = cdiv(tp.items, (long long)Cfg::WARPS * 4);   // >= 4 items per warp
+  if (grid > sm_count()) grid = sm_count();
+  kern<<<(unsigned)grid, Cfg::WARPS * 32, Cfg::SMEM_BYTES, stream>>>(maps, a, tp);
   int rc = check_launch("attn_tiny_kernel");
   return rc ? rc : 1;
 }
@@ -459,20 +432,19 @@ static int launch_tiny(const TinyMaps& maps, const AttnP& a, const TinyP& tp, cu
 void set_tiny_mode(int mode) { g_tiny_mode = mode; }
 
 int launch_tiny_attention(int bwd, const AttnP& a, cudaStream_t stream) {
-  if (g_tiny_mode < 0) g_tiny_mode = getenv("EGV_ATTN_TINY") ? atoi(getenv("EGV_ATTN_TINY")) : 0;
+  if (g_tiny_mode < 0) g_tiny_mode = getenv("EGV_ATTN_TINY") ? atoi(getenv("EGV_ATTN_TINY")) : 3;
   if (!((g_tiny_mode >> bwd) & 1)) return 0;
   const int lk_reg = a.LkT - (a.has_cls ? 1 : 0);
   if (a.key_bias || a.Lq > TL || lk_reg > TL || lk_reg < 1 || a.Lq < 1) return 0;
   if (a.q_gstride != 1 || a.k_gstride != 1 || a.q_istride != a.k_istride || a.q_istride < a.G) return 0;
-  if (a.G < TG || (long long)a.B * a.H * a.G < 1024) return 0;
+  if ((long long)a.B * a.H * a.G < 1024) return 0;
   if (bwd && (a.dkv_accumulate || (a.Lq % 4) || (a.has_cls && !a.dkv_cls))) return 0;
   TinyP tp;
-  tp.n_gt = (int)cdiv(a.G, TG);
-  tp.items = (long long)a.B * a.H * tp.n_gt;
+  tp.items = (long long)a.B * a.H * a.G;
   tp.istride = a.q_istride;
   tp.lk_reg = lk_reg;
   TinyMaps maps;
-  const uint32_t box[4] = {64, TG, TL, 1};
+  const uint32_t box[4] = {64, 1, TL, 1};
   struct T { const bf16* p; long long ld, bstride; int row0, L; };
   const T ts[5] = {{a.q, a.ldq, a.q_bstride, a.q_row0, a.Lq}, {a.k, a.ldkv, a.kv_bstride, a.k_row0, lk_reg},
                    {a.v, a.ldkv, a.kv_bstride, a.k_row0, lk_reg}, {a.d_o, a.ldo, a.o_bstride, a.q_row0, a.Lq},

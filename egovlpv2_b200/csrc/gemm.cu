@@ -274,12 +274,13 @@ struct GemmCfg {
 
 // CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs of a cluster form a tcgen05 CTA pair (cta_group::2) on a
 // 256 x BN output tile (m-tiles 2i and 2i+1 of the same n-tile): each CTA stages its own 128 rows of A and its own half
-// of B's N rows, the leader (rank 0) issues M = 256 MMAs for both, each CTA's epilogue drains its own TMEM.  Motivation
-// (tools/gemm_bench.py): single-CTA 128 x 256 SS-mode mainloops stop at ~1470 TF/s because A + B per k-block needs
-// ~190 B/clk through a 128 B/clk shared-memory port; the pair needs ~126 B/clk.  STATUS: bit-identical results
-// (tests/test_kernels_gpu.py::test_gemm_cluster_pairs_match_single_cta) but 2x SLOWER than the single-CTA kernel in
-// round 1 (657 vs 1355 TF/s, K = 768): the leader's MMA thread spends most of each tile waiting for the accumulator
-// release (16 arrivals, 8 of them remote with cluster-scope release fences) -- off by default (EGV_GEMM_CLUSTER=1).
+// of B's N rows, the leader (rank 0) issues M = 256 MMAs for both, each CTA's epilogue drains its own TMEM; per SM the
+// operand traffic through shared memory and from L2 drops from A + B to A + B/2 per k-block.  Bit-identical to the
+// single-CTA kernel (tests/test_kernels_gpu.py::test_gemm_cluster_pairs_match_single_cta).  Measured (round 1,
+// tools/gemm_bench.py, M or K = 25096): weight gradients (TN) 79 / 87 / 85 us vs 85 / 95 / 95 us single-CTA (+7-11 %);
+// NT / NN with K = 768 equal, with K = 3072 5 % slower -> default: pairs for the TN layout only (EGV_GEMM_CLUSTER=2).
+// (First version: 2x slower -- remote mbarrier arrivals with the default .release.cluster semantics compile to
+// MEMBAR + ERRBAR and wait for the epilogue's outstanding global stores; they are .relaxed now.)
 template <int BN, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -741,14 +742,14 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
 
 static int g_force_simt = 0;
 static int g_plan_mode = -1;      // -1: env EGV_GEMM_PLAN (default 1); 0: round-1 heuristic; 1: cost-model planner; 2: + 192-wide tiles
-static int g_cluster_mode = -1;   // -1: env EGV_GEMM_CLUSTER (default 0 = off: the cta_group::2 pairs are correct but slower, see above); 0 off; 1 on
+static int g_cluster_mode = -1;   // -1: env EGV_GEMM_CLUSTER (default 2); 0 = single CTAs, 1 = CTA pairs wherever possible, 2 = pairs for TN (weight gradients)
 
 }  // namespace egv
 
 using namespace egv;
 
 extern "C" void egv_gemm_force_simt(int on) { g_force_simt = on; }
-extern "C" void egv_gemm_set_cluster(int on) { g_cluster_mode = on; }
+extern "C" void egv_gemm_set_cluster(int mode) { g_cluster_mode = mode; }
 extern "C" void egv_gemm_set_plan(int mode) { g_plan_mode = mode; }
 
 extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
@@ -869,8 +870,9 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   split_k = (int)cdiv(p.k_blocks_total, p.k_blocks_per_split);
   p.split_k = split_k;
   // CTA pairs sharing the B tile (TMA multicast) when there are enough tile rows to pair up and fill the GPU
-  if (g_cluster_mode < 0) g_cluster_mode = getenv("EGV_GEMM_CLUSTER") ? atoi(getenv("EGV_GEMM_CLUSTER")) : 0;
-  const bool pair = g_cluster_mode > 0 && (BN == 128 || BN == 256) && num_m_tiles >= 2 &&
+  if (g_cluster_mode < 0) g_cluster_mode = getenv("EGV_GEMM_CLUSTER") ? atoi(getenv("EGV_GEMM_CLUSTER")) : 2;
+  const bool pair_wanted = g_cluster_mode == 1 || (g_cluster_mode == 2 && a_mn && b_mn);
+  const bool pair = pair_wanted && (BN == 128 || BN == 256) && num_m_tiles >= 2 &&
                     (long long)num_m_tiles * p.num_n_tiles * split_k >= sm_count() / 2;
   const int m_units = pair ? (int)cdiv(num_m_tiles, 2) : num_m_tiles;
   p.total_items = m_units * p.num_n_tiles * split_k;

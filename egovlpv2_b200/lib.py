@@ -141,8 +141,9 @@ class Kernels:
     def force_simt(self, on):
         self.lib.egv_gemm_force_simt(int(bool(on)))
 
-    def set_cluster(self, on):
-        self.lib.egv_gemm_set_cluster(int(bool(on)))
+    def set_cluster(self, mode):
+        """0 / False: single CTAs; 1 / True: CTA pairs wherever possible; 2: pairs for the TN layout only (default)."""
+        self.lib.egv_gemm_set_cluster(int(mode))
 
     def set_attention_tiny(self, mode):
         self.lib.egv_attention_set_tiny(int(mode))

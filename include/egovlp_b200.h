@@ -76,9 +76,9 @@ typedef struct egv_gemm_args {
 int egv_gemm_bf16(const egv_gemm_args* args, egv_stream_t stream);
 /* test hook: route every GEMM through the SIMT fallback kernel (1) or restore normal dispatch (0) */
 void egv_gemm_force_simt(int on);
-/* 1: large problems run as tcgen05 CTA pairs (cta_group::2: 256 x BN tiles, each CTA stages half of B); 0 (default):
- * single CTAs.  Round 1: the pair kernel is bit-identical but ~2x slower (accumulator hand-back latency), see gemm.cu. */
-void egv_gemm_set_cluster(int on);
+/* tcgen05 CTA pairs (cta_group::2: 256 x BN tiles, each CTA stages its 128 rows of A and half of B): 0 = never,
+ * 1 = wherever the tile grid allows, 2 (default) = for the TN layout (weight gradients: +7-11 %); bit-identical results. */
+void egv_gemm_set_cluster(int mode);
 /* tile-width / split-K planner for plain fp32-output GEMMs (weight gradients): 0 = round-1 heuristic, 1 = cost model
  * over {256,128}-wide tiles x split (default), 2 = also 192-wide tiles.  Env EGV_GEMM_PLAN sets the default. */
 void egv_gemm_set_plan(int mode);
@@ -133,8 +133,8 @@ typedef struct egv_attn_args {
 int64_t egv_attention_workspace_bytes(const egv_attn_args* a);
 int egv_attention_fwd(const egv_attn_args* a, egv_stream_t stream);
 int egv_attention_bwd(const egv_attn_args* a, egv_stream_t stream);
-/* fused tiny-group kernels (time attention; csrc/attention_tiny.cu): bit 0 = forward, bit 1 = backward.  Default 0
- * (env EGV_ATTN_TINY): validated but not yet faster than the generic kernels -- see DESIGN.md. */
+/* fused tiny-group kernels (time attention; csrc/attention_tiny.cu): bit 0 = forward, bit 1 = backward.  Default 3
+ * (env EGV_ATTN_TINY); 0 routes those shapes through the generic warp-per-group kernels. */
 void egv_attention_set_tiny(int mode);
 /* dk/dv row `cls_row` of every batch (+)= the fp32 accumulators dkv_cls [B,H,2,64] filled by egv_attention_bwd */
 int egv_attention_cls_finalize(const float* dkv_cls, void* dk, void* dv, int64_t lddkv, int64_t kv_bstride, int cls_row,

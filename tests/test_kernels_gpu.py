@@ -188,20 +188,36 @@ def test_gemm_linearity_full_size(K):
 
 @pytest.mark.parametrize("layout", [L.GEMM_NT, L.GEMM_NN, L.GEMM_TN])
 def test_gemm_cluster_pairs_match_single_cta(K, layout):
-    """2-CTA clusters with the multicast B tile must give bit-identical tiles to the single-CTA kernel (odd number of
-    m-tiles: the last pair has one out-of-range tile)."""
+    """tcgen05 CTA pairs (cta_group::2) must give bit-identical tiles to the single-CTA kernel (odd number of m-tiles:
+    the last pair has one out-of-range tile)."""
     M, N, Kd = 128 * 37 + 5, 1536, 328
     A, B = _operands(layout, M, N, Kd, seed=61)
     bias = rnd(N, dtype=torch.float32, seed=62)
     o1 = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
     o2 = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
-    K.set_cluster(True)
+    K.set_cluster(1)
     try:
         K.gemm(layout, A, B, bias=bias, act=L.ACT_GELU, out_bf16=o1)
+        K.set_cluster(0)
+        K.gemm(layout, A, B, bias=bias, act=L.ACT_GELU, out_bf16=o2)
     finally:
-        K.set_cluster(False)
-    K.gemm(layout, A, B, bias=bias, act=L.ACT_GELU, out_bf16=o2)
+        K.set_cluster(2)
     assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("shape", [(768, 768, 6277), (2304, 768, 3137), (768, 3072, 4100)])
+def test_gemm_pair_weight_gradient(K, R, shape):
+    """dW (+)= dy^T x through the default path: tile/split planner + CTA pairs + fp32 vector reductions into a gradient
+    sink that already holds a value."""
+    N, Kd, M = shape            # dW [N, Kd], reduction over M tokens
+    dy, x = rnd(M, N, seed=91), rnd(M, Kd, seed=92)
+    base = rnd(N, Kd, dtype=torch.float32, seed=93)
+    outs = []
+    for impl in (K, R):
+        o = base.clone()
+        impl.gemm(L.GEMM_TN, dy, x, out_f32=o, accumulate=True, scale=0.5)
+        outs.append(o)
+    check(outs[0], outs[1], 2e-3, "pair weight gradient")
 
 
 def test_gemm_argument_errors(K):
@@ -319,7 +335,7 @@ def test_attention_fwd_bwd(K, R, name):
         kb = kb.float().contiguous()
     d_o = rnd(B, Nq, C, seed=75)
     outs = []
-    K.set_attention_tiny(3 if name.startswith("tiny") else 0)
+    K.set_attention_tiny(3 if name.startswith("tiny") else 0)   # "time*" cases keep the generic kernels covered
     for impl in (K, R):
         o = torch.zeros(B, Nq, C, dtype=torch.bfloat16, device=DEV)
         lse = torch.zeros(B * H * spec.G * spec.Lq, device=DEV)
@@ -337,7 +353,7 @@ def test_attention_fwd_bwd(K, R, name):
         if spec.has_cls_key:
             impl.attention_cls_finalize(cls, dk, dv, H, cls_row=0, accumulate=False)
         outs.append((o, lse, dq, dk, dv, delta))
-    K.set_attention_tiny(0)
+    K.set_attention_tiny(3)
     for n, a, r in zip("o lse dq dk dv delta".split(), outs[0], outs[1]):
         tol = {"dq": 1.2e-2, "dk": 1.2e-2, "dv": 1.2e-2, "o": 8e-3, "delta": 2e-2, "lse": 1e-4}[n]
         check(a, r, tol, "attention %s %s" % (name, n))

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q --tb=short -p no:cacheprovider -k "attention or gemm" > gpurun_out/tests.log 2>&1
+echo "== tests: exit $? : $(tail -n 1 gpurun_out/tests.log)"; grep -E "^E|FAILED|egv:" gpurun_out/tests.log | head -20
+echo "tiny on"; EGV_ATTN_TINY=3 PROF_ONLY=attn_time timeout 300 python tools/prof_kernels.py 2>&1 | tail -2
+echo "tiny off"; PROF_ONLY=attn_time,gemm_wgrad timeout 300 python tools/prof_kernels.py 2>&1 | tail -6
