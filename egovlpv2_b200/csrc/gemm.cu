@@ -52,6 +52,7 @@ struct GemmParams {
   int accumulate;
   int vec_ok;  // N % 4 == 0, every row stride % 4 == 0 and every pointer aligned for 4-element vector access
   float* colsum;  // optional [N]: += column sums of the final value (bias gradients), fp32 atomics
+  int fast;       // 1: MLP fc1 forward (bias, pre + GELU bf16 outputs only); 2: its backward (GELU' of aux, bf16 output [+ colsum])
 };
 
 EGV_DEVINL float rcp_approx(float x) {
@@ -231,6 +232,107 @@ EGV_DEVINL void epi_rows_vec4(const GemmParams& p, const float* stg, int lane, i
       atomicAdd(p.colsum + gcol + 2, cs.z);
       atomicAdd(p.colsum + gcol + 3, cs.w);
     }
+  }
+}
+
+// Lean epilogues of the two activation GEMMs of the MLP (fc1 forward: 118 GF with K = 768, i.e. the epilogue has to
+// keep up with a 5 us mainloop per 128 x 256 tile): full tiles only, no optional outputs, pointers advanced instead of
+// re-derived, no per-row uniform branches.  p.fast == 1: out_pre = bf16(acc + bias), out_bf16 = bf16(gelu(acc + bias)).
+EGV_DEVINL void epi_rows_gelu_fwd_fast(const GemmParams& p, const float* stg, int lane, int row_base, int gcol) {
+  const int sub = lane >> 3, ch = lane & 7;
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+  bf16* opre = p.out_pre + (long long)(row_base + sub) * p.ld_out_pre + gcol;
+  bf16* oact = p.out_bf16 + (long long)(row_base + sub) * p.ld_out_bf16 + gcol;
+  const long long spre = 4 * p.ld_out_pre, sact = 4 * p.ld_out_bf16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 a = *reinterpret_cast<const float4*>(stg + stg_off(4 * i + sub, ch));
+    const float v0 = a.x + b.x, v1 = a.y + b.y, v2 = a.z + b.z, v3 = a.w + b.w;
+    *reinterpret_cast<uint2*>(opre) = pack4_bf16(v0, v1, v2, v3);
+    *reinterpret_cast<uint2*>(oact) = pack4_bf16(gelu_fwd(v0), gelu_fwd(v1), gelu_fwd(v2), gelu_fwd(v3));
+    opre += spre;
+    oact += sact;
+  }
+}
+// p.fast == 2: out_bf16 = bf16(acc * gelu'(aux)), colsum (optional) += column sums
+EGV_DEVINL void epi_rows_gelu_bwd_fast(const GemmParams& p, const float* stg, int lane, int row_base, int gcol) {
+  const int sub = lane >> 3, ch = lane & 7;
+  const bf16* aux = p.aux + (long long)(row_base + sub) * p.ld_aux + gcol;
+  bf16* o16 = p.out_bf16 + (long long)(row_base + sub) * p.ld_out_bf16 + gcol;
+  const long long saux = 4 * p.ld_aux, s16 = 4 * p.ld_out_bf16;
+  uint2 ax[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ax[i] = __ldg(reinterpret_cast<const uint2*>(aux + i * saux));
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 a = *reinterpret_cast<const float4*>(stg + stg_off(4 * i + sub, ch));
+    const float2 a01 = unpack_bf16(ax[i].x), a23 = unpack_bf16(ax[i].y);
+    const float v0 = apply_act<EGV_ACT_GELU_BWD>(a.x, a01.x), v1 = apply_act<EGV_ACT_GELU_BWD>(a.y, a01.y);
+    const float v2 = apply_act<EGV_ACT_GELU_BWD>(a.z, a23.x), v3 = apply_act<EGV_ACT_GELU_BWD>(a.w, a23.y);
+    *reinterpret_cast<uint2*>(o16) = pack4_bf16(v0, v1, v2, v3);
+    o16 += s16;
+    cs.x += v0;
+    cs.y += v1;
+    cs.z += v2;
+    cs.w += v3;
+  }
+  if (p.colsum) {
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
+      cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+      cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
+      cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+    }
+    if (sub == 0) {
+      atomicAdd(p.colsum + gcol, cs.x);
+      atomicAdd(p.colsum + gcol + 1, cs.y);
+      atomicAdd(p.colsum + gcol + 2, cs.z);
+      atomicAdd(p.colsum + gcol + 3, cs.w);
+    }
+  }
+}
+
+// p.fast == 3: out_bf16 = bf16((acc [+ bias]) * scale)   (qkv projections, input gradients)
+EGV_DEVINL void epi_rows_bf16_fast(const GemmParams& p, const float* stg, int lane, int row_base, int gcol, float sc) {
+  const int sub = lane >> 3, ch = lane & 7;
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+  bf16* o16 = p.out_bf16 + (long long)(row_base + sub) * p.ld_out_bf16 + gcol;
+  const long long s16 = 4 * p.ld_out_bf16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 a = *reinterpret_cast<const float4*>(stg + stg_off(4 * i + sub, ch));
+    *reinterpret_cast<uint2*>(o16) = pack4_bf16((a.x + b.x) * sc, (a.y + b.y) * sc, (a.z + b.z) * sc, (a.w + b.w) * sc);
+    o16 += s16;
+  }
+}
+// p.fast == 4: v = acc [+ bias]; out_pre (optional) = bf16(v); out_f32 = v * scale + residual   (out-projections)
+EGV_DEVINL void epi_rows_residual_fast(const GemmParams& p, const float* stg, int lane, int row_base, int gcol,
+                                       float scale_total) {
+  const int sub = lane >> 3, ch = lane & 7;
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+  const float* res = p.residual + (long long)(row_base + sub) * p.ld_res + gcol;
+  float* o32 = p.out_f32 + (long long)(row_base + sub) * p.ld_out_f32 + gcol;
+  const long long sres = 4 * p.ld_res, s32 = 4 * p.ld_out_f32;
+  float4 rs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rs[i] = __ldg(reinterpret_cast<const float4*>(res + i * sres));
+  bf16* opre = p.out_pre ? p.out_pre + (long long)(row_base + sub) * p.ld_out_pre + gcol : nullptr;
+  const long long spre = 4 * p.ld_out_pre;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 a = *reinterpret_cast<const float4*>(stg + stg_off(4 * i + sub, ch));
+    const float v0 = a.x + b.x, v1 = a.y + b.y, v2 = a.z + b.z, v3 = a.w + b.w;
+    if (opre) {
+      *reinterpret_cast<uint2*>(opre) = pack4_bf16(v0, v1, v2, v3);
+      opre += spre;
+    }
+    *reinterpret_cast<float4*>(o32) = make_float4(fmaf(v0, scale_total, rs[i].x), fmaf(v1, scale_total, rs[i].y),
+                                                  fmaf(v2, scale_total, rs[i].z), fmaf(v3, scale_total, rs[i].w));
+    o32 += s32;
   }
 }
 
@@ -481,6 +583,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         } else if (p.vec_ok) {
           const int gcol = n0 + col0 + 4 * (lane & 7);
           const bool full = (row_base + 32 <= p.M) && (n0 + col0 + 32 <= p.N);
+          if (full && p.fast == 1) {
+            epi_rows_gelu_fwd_fast(p, stg, lane, row_base, gcol);
+          } else if (full && p.fast == 2) {
+            epi_rows_gelu_bwd_fast(p, stg, lane, row_base, gcol);
+          } else if (full && p.fast == 3) {
+            epi_rows_bf16_fast(p, stg, lane, row_base, gcol, scale_total);
+          } else if (full && p.fast == 4 && lead) {
+            epi_rows_residual_fast(p, stg, lane, row_base, gcol, scale_total);
+          } else
           switch (p.act) {
             case EGV_ACT_GELU: epi_rows_vec4_d<EGV_ACT_GELU>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
             case EGV_ACT_RELU: epi_rows_vec4_d<EGV_ACT_RELU>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
@@ -781,6 +892,17 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
                (!a->colsum || ((uintptr_t)a->colsum) % 4 == 0);
   }
   p.colsum = a->colsum;
+  p.fast = 0;
+  static const bool no_fast = getenv("EGV_GEMM_NO_FAST") != nullptr;
+  if (!no_fast && p.vec_ok && split_k == 1 && !a->accumulate) {
+    const bool unit = !a->scale_dev && a->scale == 1.0f;
+    if (!a->residual && !a->out_f32 && a->out_bf16) {
+      if (unit && a->act == EGV_ACT_GELU && a->bias && a->out_pre_bf16 && !a->colsum) p.fast = 1;
+      if (unit && a->act == EGV_ACT_GELU_BWD && !a->bias && !a->out_pre_bf16 && a->aux) p.fast = 2;
+      if (a->act == EGV_ACT_NONE && !a->out_pre_bf16 && !a->colsum) p.fast = 3;
+    }
+    if (a->act == EGV_ACT_NONE && a->residual && a->out_f32 && !a->out_bf16 && !a->colsum) p.fast = 4;
+  }
   if (a->colsum && split_k > 1) return fail(EGV_ERR_ARG, "gemm: colsum cannot be combined with split_k > 1");
 
   const bool a_mn = a->layout == EGV_GEMM_TN;                           // A stored [K, M]

@@ -121,6 +121,37 @@ def test_gemm_epilogue(K, R, act):
     check(outs[0][5], outs[1][5], 1e-4, "scalar epilogue colsum act %d" % act)
 
 
+@pytest.mark.parametrize("layout", [L.GEMM_NT, L.GEMM_NN])
+def test_gemm_mlp_fast_epilogues(K, R, layout):
+    """The lean epilogues of the MLP's activation GEMMs (fc1 forward: bias + pre + GELU outputs; its backward: GELU' of
+    the saved pre-activation + column sums), full and partial tiles, strided outputs."""
+    M, N, Kd = 128 * 3 + 45, 512 + 64, 200
+    A, B = _operands(layout, M, N, Kd, seed=15)
+    A, B = A * 0.25, B * 0.25
+    bias = rnd(N, dtype=torch.float32, seed=16)
+    aux = rnd(M, N, seed=17)
+    outs = []
+    for impl in (K, R):
+        wide = torch.zeros(M, 2 * N, dtype=torch.bfloat16, device=DEV)
+        o16, opre = wide[:, :N], wide[:, N:]                      # row stride 2N
+        impl.gemm(layout, A, B, bias=bias, act=L.ACT_GELU, out_bf16=o16, out_pre=opre)
+        g16 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        cs = torch.ones(N, device=DEV)
+        impl.gemm(layout, A, B, aux=aux, act=L.ACT_GELU_BWD, out_bf16=g16, colsum=cs)
+        g16b = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        impl.gemm(layout, A, B, aux=aux, act=L.ACT_GELU_BWD, out_bf16=g16b)
+        p16 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        impl.gemm(layout, A, B, bias=bias, out_bf16=p16, scale=0.5, scale_dev=torch.tensor([1.7], device=DEV))  # lean bias, scale -> bf16
+        res = rnd(M, N, dtype=torch.float32, seed=18)
+        r32 = res.clone()
+        rpre = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        impl.gemm(layout, A, B, bias=bias, scale_dev=torch.tensor([0.37], device=DEV), residual=r32, out_f32=r32,
+                  out_pre=rpre)                                                            # lean gated residual, in place
+        outs.append((o16.clone(), opre.clone(), g16, cs, g16b, p16, r32, rpre))
+    for n, a, r in zip("gelu pre gelu_bwd colsum gelu_bwd_nocs plain_bf16 residual_f32 residual_pre".split(), outs[0], outs[1]):
+        check(a, r, 1e-4 if n == "colsum" else (2e-5 if n == "residual_f32" else 4e-3), "fast epilogue " + n)
+
+
 def test_gemm_inplace_residual_and_strided_outputs(K, R):
     M, N, Kd = 390, 256, 128
     A, B = _operands(L.GEMM_NT, M, N, Kd, seed=21)
