@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x,
 }
 
 // Streaming variant for wide bf16 matrices (C % 8 == 0, 16-byte aligned rows): a lane owns 8 adjacent columns
-// (one 16-byte load), a block 256 columns x 8 row lanes, 4 rows in flight per thread.  HBM-bound.
+// (one 16-byte load), a block 256 columns x 8 row lanes, 8 rows in flight per thread.  HBM-bound.
 __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16* __restrict__ x, long long rows, int C, long long ld,
                                                             float* __restrict__ out, float scale,
                                                             const float* __restrict__ scale_dev) {
@@ -119,12 +119,12 @@ __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16* __restri
   if (c0 < C) {
     const long long rstep = (long long)gridDim.y * 8;
     long long r = (long long)blockIdx.y * 8 + ty;
-    for (; r + 3 * rstep < rows; r += 4 * rstep) {
-      uint4 u[4];
+    for (; r + 7 * rstep < rows; r += 8 * rstep) {   // 8 independent 16-byte loads in flight per thread
+      uint4 u[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(x + (r + k * rstep) * ld + c0);
+      for (int k = 0; k < 8; ++k) u[k] = *reinterpret_cast<const uint4*>(x + (r + k * rstep) * ld + c0);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         const uint32_t* w = reinterpret_cast<const uint32_t*>(&u[k]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
