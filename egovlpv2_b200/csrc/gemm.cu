@@ -52,7 +52,7 @@ struct GemmParams {
   int accumulate;
   int vec_ok;  // N % 4 == 0, every row stride % 4 == 0 and every pointer aligned for 4-element vector access
   float* colsum;  // optional [N]: += column sums of the final value (bias gradients), fp32 atomics
-  int fast;       // 1: MLP fc1 forward (bias, pre + GELU bf16 outputs only); 2: its backward (GELU' of aux, bf16 output [+ colsum])
+  int fast;       // lean full-tile epilogues: 1 / 5 fc1 forward (GELU, pre or derivative saved), 2 / 6 its backward, 3 bf16, 4 residual
 };
 
 EGV_DEVINL float rcp_approx(float x) {
@@ -103,9 +103,17 @@ EGV_DEVINL float gelu_fwd(float x) {
   return fmaf(-0.5f * ax, r, fmaxf(x, 0.0f));
 }
 
+// gelu'(x) = Phi(x) + x phi(x)
+EGV_DEVINL float gelu_grad(float x) {
+  const float pdf = 0.3989422804014327f * ex2_approx(-0.72134752044448170f * x * x);
+  return fmaf(x, pdf, gelu_cdf(x));
+}
+EGV_DEVINL bool act_needs_aux(int act) { return (act >= EGV_ACT_GELU_BWD && act <= EGV_ACT_TANH_BWD) || act == EGV_ACT_MUL_AUX; }
+
 template <int ACT>
 EGV_DEVINL float apply_act(float v, float auxv) {
-  if (ACT == EGV_ACT_GELU) return gelu_fwd(v);
+  if (ACT == EGV_ACT_GELU || ACT == EGV_ACT_GELU_DG) return gelu_fwd(v);
+  if (ACT == EGV_ACT_MUL_AUX) return v * auxv;
   if (ACT == EGV_ACT_RELU) return fmaxf(v, 0.0f);
   if (ACT == EGV_ACT_TANH) return tanhf(v);
   if (ACT == EGV_ACT_GELU_BWD) {
@@ -124,7 +132,7 @@ template <int ACT>
 EGV_DEVINL float epilogue_store_t(const GemmParams& p, float v, int row, int col, bool lead, float resv, float auxv,
                                   float scale_total) {
   if (lead && p.bias) v += __ldg(p.bias + col);
-  if (p.out_pre) p.out_pre[(long long)row * p.ld_out_pre + col] = __float2bfloat16(v);
+  if (p.out_pre) p.out_pre[(long long)row * p.ld_out_pre + col] = __float2bfloat16(ACT == EGV_ACT_GELU_DG ? gelu_grad(v) : v);
   v = apply_act<ACT>(v, auxv) * scale_total;
   if (lead) v += resv;
   if (p.out_f32) {
@@ -144,6 +152,8 @@ EGV_DEVINL float epilogue_store(const GemmParams& p, float v, int row, int col, 
     case EGV_ACT_GELU_BWD: return epilogue_store_t<EGV_ACT_GELU_BWD>(p, v, row, col, lead, resv, auxv, scale_total);
     case EGV_ACT_RELU_BWD: return epilogue_store_t<EGV_ACT_RELU_BWD>(p, v, row, col, lead, resv, auxv, scale_total);
     case EGV_ACT_TANH_BWD: return epilogue_store_t<EGV_ACT_TANH_BWD>(p, v, row, col, lead, resv, auxv, scale_total);
+    case EGV_ACT_GELU_DG: return epilogue_store_t<EGV_ACT_GELU_DG>(p, v, row, col, lead, resv, auxv, scale_total);
+    case EGV_ACT_MUL_AUX: return epilogue_store_t<EGV_ACT_MUL_AUX>(p, v, row, col, lead, resv, auxv, scale_total);
     default: return epilogue_store_t<EGV_ACT_NONE>(p, v, row, col, lead, resv, auxv, scale_total);
   }
 }
@@ -169,7 +179,7 @@ EGV_DEVINL void epi_rows_vec4(const GemmParams& p, const float* stg, int lane, i
   const bool c_ok = FULL || gcol < p.N;   // N % 4 == 0 on this path: the whole 4-column group is in or out
   float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
   if (lead && p.bias && c_ok) b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
-  constexpr bool NEED_AUX = ACT >= EGV_ACT_GELU_BWD && ACT <= EGV_ACT_TANH_BWD;
+  constexpr bool NEED_AUX = (ACT >= EGV_ACT_GELU_BWD && ACT <= EGV_ACT_TANH_BWD) || ACT == EGV_ACT_MUL_AUX;
   const bool has_res = lead && p.residual != nullptr;
   const int rows_left = p.M - row_base;   // rows of this chunk that exist (>= 32 when FULL)
   const float* res_p = p.residual ? p.residual + (long long)row_base * p.ld_res + gcol : nullptr;
@@ -196,7 +206,10 @@ EGV_DEVINL void epi_rows_vec4(const GemmParams& p, const float* stg, int lane, i
     const float4 a = *reinterpret_cast<const float4*>(stg + stg_off(rl, ch));
     if (!FULL && !(c_ok && rl < rows_left)) continue;
     float v0 = a.x + b.x, v1 = a.y + b.y, v2 = a.z + b.z, v3 = a.w + b.w;
-    if (opre) *reinterpret_cast<uint2*>(opre + rl * ldpre) = pack4_bf16(v0, v1, v2, v3);
+    if (opre) {
+      if (ACT == EGV_ACT_GELU_DG) *reinterpret_cast<uint2*>(opre + rl * ldpre) = pack4_bf16(gelu_grad(v0), gelu_grad(v1), gelu_grad(v2), gelu_grad(v3));
+      else *reinterpret_cast<uint2*>(opre + rl * ldpre) = pack4_bf16(v0, v1, v2, v3);
+    }
     const float2 a01 = unpack_bf16(ax[i].x), a23 = unpack_bf16(ax[i].y);
     v0 = fmaf(apply_act<ACT>(v0, a01.x), scale_total, rs[i].x);
     v1 = fmaf(apply_act<ACT>(v1, a01.y), scale_total, rs[i].y);
@@ -238,6 +251,8 @@ EGV_DEVINL void epi_rows_vec4(const GemmParams& p, const float* stg, int lane, i
 // Lean epilogues of the two activation GEMMs of the MLP (fc1 forward: 118 GF with K = 768, i.e. the epilogue has to
 // keep up with a 5 us mainloop per 128 x 256 tile): full tiles only, no optional outputs, pointers advanced instead of
 // re-derived, no per-row uniform branches.  p.fast == 1: out_pre = bf16(acc + bias), out_bf16 = bf16(gelu(acc + bias)).
+// DG: out_pre = bf16(gelu'(acc + bias)) instead (EGV_ACT_GELU_DG): Phi is shared between the value and the derivative.
+template <bool DG>
 EGV_DEVINL void epi_rows_gelu_fwd_fast(const GemmParams& p, const float* stg, int lane, int row_base, int gcol) {
   const int sub = lane >> 3, ch = lane & 7;
   const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
@@ -248,13 +263,22 @@ EGV_DEVINL void epi_rows_gelu_fwd_fast(const GemmParams& p, const float* stg, in
   for (int i = 0; i < 8; ++i) {
     const float4 a = *reinterpret_cast<const float4*>(stg + stg_off(4 * i + sub, ch));
     const float v0 = a.x + b.x, v1 = a.y + b.y, v2 = a.z + b.z, v3 = a.w + b.w;
-    *reinterpret_cast<uint2*>(opre) = pack4_bf16(v0, v1, v2, v3);
-    *reinterpret_cast<uint2*>(oact) = pack4_bf16(gelu_fwd(v0), gelu_fwd(v1), gelu_fwd(v2), gelu_fwd(v3));
+    if (DG) {
+      const float c0 = gelu_cdf(v0), c1 = gelu_cdf(v1), c2 = gelu_cdf(v2), c3 = gelu_cdf(v3);
+      const float k = -0.72134752044448170f, n = 0.3989422804014327f;
+      *reinterpret_cast<uint2*>(opre) = pack4_bf16(fmaf(v0 * n, ex2_approx(k * v0 * v0), c0), fmaf(v1 * n, ex2_approx(k * v1 * v1), c1),
+                                                   fmaf(v2 * n, ex2_approx(k * v2 * v2), c2), fmaf(v3 * n, ex2_approx(k * v3 * v3), c3));
+      *reinterpret_cast<uint2*>(oact) = pack4_bf16(v0 * c0, v1 * c1, v2 * c2, v3 * c3);
+    } else {
+      *reinterpret_cast<uint2*>(opre) = pack4_bf16(v0, v1, v2, v3);
+      *reinterpret_cast<uint2*>(oact) = pack4_bf16(gelu_fwd(v0), gelu_fwd(v1), gelu_fwd(v2), gelu_fwd(v3));
+    }
     opre += spre;
     oact += sact;
   }
 }
-// p.fast == 2: out_bf16 = bf16(acc * gelu'(aux)), colsum (optional) += column sums
+// p.fast == 2: out_bf16 = bf16(acc * gelu'(aux)), colsum (optional) += column sums;  MUL (p.fast == 6): acc * aux
+template <bool MUL>
 EGV_DEVINL void epi_rows_gelu_bwd_fast(const GemmParams& p, const float* stg, int lane, int row_base, int gcol) {
   const int sub = lane >> 3, ch = lane & 7;
   const bf16* aux = p.aux + (long long)(row_base + sub) * p.ld_aux + gcol;
@@ -268,8 +292,9 @@ EGV_DEVINL void epi_rows_gelu_bwd_fast(const GemmParams& p, const float* stg, in
   for (int i = 0; i < 8; ++i) {
     const float4 a = *reinterpret_cast<const float4*>(stg + stg_off(4 * i + sub, ch));
     const float2 a01 = unpack_bf16(ax[i].x), a23 = unpack_bf16(ax[i].y);
-    const float v0 = apply_act<EGV_ACT_GELU_BWD>(a.x, a01.x), v1 = apply_act<EGV_ACT_GELU_BWD>(a.y, a01.y);
-    const float v2 = apply_act<EGV_ACT_GELU_BWD>(a.z, a23.x), v3 = apply_act<EGV_ACT_GELU_BWD>(a.w, a23.y);
+    constexpr int A = MUL ? EGV_ACT_MUL_AUX : EGV_ACT_GELU_BWD;
+    const float v0 = apply_act<A>(a.x, a01.x), v1 = apply_act<A>(a.y, a01.y);
+    const float v2 = apply_act<A>(a.z, a23.x), v3 = apply_act<A>(a.w, a23.y);
     *reinterpret_cast<uint2*>(o16) = pack4_bf16(v0, v1, v2, v3);
     o16 += s16;
     cs.x += v0;
@@ -347,7 +372,7 @@ EGV_DEVINL void epi_rows_vec4_d(const GemmParams& p, const float* stg, int lane,
 EGV_DEVINL void epi_rows_scalar(const GemmParams& p, const float* stg, int lane, int row_base, int gcol, bool lead,
                                 float scale_total) {
   const bool c_ok = gcol < p.N;
-  const bool need_aux = p.act >= EGV_ACT_GELU_BWD && p.act <= EGV_ACT_TANH_BWD;
+  const bool need_aux = act_needs_aux(p.act);
   float cs = 0.f;
 #pragma unroll 4
   for (int r = 0; r < 32; ++r) {
@@ -584,9 +609,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int gcol = n0 + col0 + 4 * (lane & 7);
           const bool full = (row_base + 32 <= p.M) && (n0 + col0 + 32 <= p.N);
           if (full && p.fast == 1) {
-            epi_rows_gelu_fwd_fast(p, stg, lane, row_base, gcol);
+            epi_rows_gelu_fwd_fast<false>(p, stg, lane, row_base, gcol);
+          } else if (full && p.fast == 5) {
+            epi_rows_gelu_fwd_fast<true>(p, stg, lane, row_base, gcol);
           } else if (full && p.fast == 2) {
-            epi_rows_gelu_bwd_fast(p, stg, lane, row_base, gcol);
+            epi_rows_gelu_bwd_fast<false>(p, stg, lane, row_base, gcol);
+          } else if (full && p.fast == 6) {
+            epi_rows_gelu_bwd_fast<true>(p, stg, lane, row_base, gcol);
           } else if (full && p.fast == 3) {
             epi_rows_bf16_fast(p, stg, lane, row_base, gcol, scale_total);
           } else if (full && p.fast == 4 && lead) {
@@ -599,6 +628,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             case EGV_ACT_GELU_BWD: epi_rows_vec4_d<EGV_ACT_GELU_BWD>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
             case EGV_ACT_RELU_BWD: epi_rows_vec4_d<EGV_ACT_RELU_BWD>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
             case EGV_ACT_TANH_BWD: epi_rows_vec4_d<EGV_ACT_TANH_BWD>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
+            case EGV_ACT_GELU_DG: epi_rows_vec4_d<EGV_ACT_GELU_DG>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
+            case EGV_ACT_MUL_AUX: epi_rows_vec4_d<EGV_ACT_MUL_AUX>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
             default: epi_rows_vec4_d<EGV_ACT_NONE>(p, stg, lane, row_base, gcol, lead, scale_total, full); break;
           }
         } else {
@@ -675,7 +706,7 @@ gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, SimtStr
       int row = m0 + ty + 16 * i, col = n0 + tx + 16 * j;
       if (row < p.M && col < p.N) {
         float resv = (p.residual && lead) ? p.residual[(long long)row * p.ld_res + col] : 0.0f;
-        float auxv = (p.act >= EGV_ACT_GELU_BWD && p.act <= EGV_ACT_TANH_BWD) ? __bfloat162float(p.aux[(long long)row * p.ld_aux + col]) : 0.0f;
+        float auxv = act_needs_aux(p.act) ? __bfloat162float(p.aux[(long long)row * p.ld_aux + col]) : 0.0f;
         const float fv = epilogue_store(p, acc[i][j], row, col, lead, resv, auxv, scale_total);
         if (p.colsum) atomicAdd(p.colsum + col, fv);
       }
@@ -869,7 +900,8 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return fail(EGV_ERR_ARG, "gemm: bad shape %d %d %d", a->M, a->N, a->K);
   if (a->layout < 0 || a->layout > 2) return fail(EGV_ERR_ARG, "gemm: bad layout %d", a->layout);
   if (!a->out_f32 && !a->out_bf16 && !a->out_pre_bf16) return fail(EGV_ERR_ARG, "gemm: no output");
-  if (a->act >= EGV_ACT_GELU_BWD && a->act <= EGV_ACT_TANH_BWD && !a->aux) return fail(EGV_ERR_ARG, "gemm: act %d needs aux", a->act);
+  if (((a->act >= EGV_ACT_GELU_BWD && a->act <= EGV_ACT_TANH_BWD) || a->act == EGV_ACT_MUL_AUX) && !a->aux)
+    return fail(EGV_ERR_ARG, "gemm: act %d needs aux", a->act);
   int split_k = a->split_k < 1 ? 1 : a->split_k;
   if (split_k > 1 && (!a->accumulate || !a->out_f32 || a->out_bf16 || a->out_pre_bf16 || a->act != EGV_ACT_NONE))
     return fail(EGV_ERR_ARG, "gemm: split_k > 1 needs accumulate=1, f32 output only, no activation");
@@ -899,6 +931,8 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
     if (!a->residual && !a->out_f32 && a->out_bf16) {
       if (unit && a->act == EGV_ACT_GELU && a->bias && a->out_pre_bf16 && !a->colsum) p.fast = 1;
       if (unit && a->act == EGV_ACT_GELU_BWD && !a->bias && !a->out_pre_bf16 && a->aux) p.fast = 2;
+      if (unit && a->act == EGV_ACT_GELU_DG && a->bias && a->out_pre_bf16 && !a->colsum) p.fast = 5;
+      if (unit && a->act == EGV_ACT_MUL_AUX && !a->bias && !a->out_pre_bf16 && a->aux) p.fast = 6;
       if (a->act == EGV_ACT_NONE && !a->out_pre_bf16 && !a->colsum) p.fast = 3;
     }
     if (a->act == EGV_ACT_NONE && a->residual && a->out_f32 && !a->out_bf16 && !a->colsum) p.fast = 4;

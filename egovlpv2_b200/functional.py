@@ -16,8 +16,8 @@ import types
 
 import torch
 
-from .lib import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_RELU, ACT_RELU_BWD, ACT_TANH, ACT_TANH_BWD, GEMM_NN, GEMM_NT,
-                  GEMM_TN, AttnSpec)
+from .lib import (ACT_GELU, ACT_GELU_BWD, ACT_GELU_DG, ACT_MUL_AUX, ACT_NONE, ACT_RELU, ACT_RELU_BWD, ACT_TANH, ACT_TANH_BWD,
+                  GEMM_NN, GEMM_NT, GEMM_TN, AttnSpec)
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -216,7 +216,8 @@ def video_block_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=Tr
     K.layernorm_fwd(s.sr, p["norm2.weight"], p["norm2.bias"], eps, y_bf16=s.ln2, mean=s.mean2, rstd=s.rstd2)
     Hd = w["mlp.fc1.weight"].shape[0]
     s.h_pre, s.h_act = _e(x, (M, Hd), BF16), _e(x, (M, Hd), BF16)
-    K.gemm(GEMM_NT, s.ln2, w["mlp.fc1.weight"], bias=p["mlp.fc1.bias"], act=ACT_GELU, out_bf16=s.h_act, out_pre=s.h_pre)
+    # h_pre holds gelu'(fc1 output): the backward then multiplies instead of re-deriving Phi and phi (ACT_GELU_DG)
+    K.gemm(GEMM_NT, s.ln2, w["mlp.fc1.weight"], bias=p["mlp.fc1.bias"], act=ACT_GELU_DG, out_bf16=s.h_act, out_pre=s.h_pre)
     out = _e(x, (M, C), F32)
     K.gemm(GEMM_NT, s.h_act, w["mlp.fc2.weight"], bias=p["mlp.fc2.bias"], residual=s.sr, out_f32=out)
     return out.view(B, N, C), (s if save else None)
@@ -235,7 +236,7 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True, sink=None):
     G.weight("mlp.fc2.weight", d_out_bf, s.h_act)
     G.bias("mlp.fc2.bias", d_out_bf)
     d_hpre = _e(d_out, s.h_pre.shape, BF16)
-    K.gemm(GEMM_NN, d_out_bf, w["mlp.fc2.weight"], aux=s.h_pre, act=ACT_GELU_BWD, out_bf16=d_hpre,
+    K.gemm(GEMM_NN, d_out_bf, w["mlp.fc2.weight"], aux=s.h_pre, act=ACT_MUL_AUX, out_bf16=d_hpre,
            colsum=G.vec("mlp.fc1.bias", s.h_pre.shape[1]))
     G.weight("mlp.fc1.weight", d_hpre, s.ln2)
     d_ln2 = _e(d_out, (M, C), BF16)
@@ -378,7 +379,8 @@ def video_block_cls_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, sav
     K.layernorm_fwd(s.sr, p["norm2.weight"], p["norm2.bias"], eps, y_bf16=s.ln2, mean=s.mean2, rstd=s.rstd2)
     Hd = w["mlp.fc1.weight"].shape[0]
     s.h_pre, s.h_act = _e(x, (B, Hd), BF16), _e(x, (B, Hd), BF16)
-    K.gemm(GEMM_NT, s.ln2, w["mlp.fc1.weight"], bias=p["mlp.fc1.bias"], act=ACT_GELU, out_bf16=s.h_act, out_pre=s.h_pre)
+    # h_pre holds gelu'(fc1 output): the backward then multiplies instead of re-deriving Phi and phi (ACT_GELU_DG)
+    K.gemm(GEMM_NT, s.ln2, w["mlp.fc1.weight"], bias=p["mlp.fc1.bias"], act=ACT_GELU_DG, out_bf16=s.h_act, out_pre=s.h_pre)
     out = _e(x, (B, C), F32)
     K.gemm(GEMM_NT, s.h_act, w["mlp.fc2.weight"], bias=p["mlp.fc2.bias"], residual=s.sr, out_f32=out)
     return out, (s if save else None)
@@ -397,7 +399,7 @@ def video_block_cls_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True, sink=None):
     G.weight("mlp.fc2.weight", d_out_bf, s.h_act)
     G.bias("mlp.fc2.bias", d_out_bf)
     d_hpre = _e(d_out, s.h_pre.shape, BF16)
-    K.gemm(GEMM_NN, d_out_bf, w["mlp.fc2.weight"], aux=s.h_pre, act=ACT_GELU_BWD, out_bf16=d_hpre,
+    K.gemm(GEMM_NN, d_out_bf, w["mlp.fc2.weight"], aux=s.h_pre, act=ACT_MUL_AUX, out_bf16=d_hpre,
            colsum=G.vec("mlp.fc1.bias", s.h_pre.shape[1]))
     G.weight("mlp.fc1.weight", d_hpre, s.ln2)
     d_ln2 = _e(d_out, (B, C), BF16)

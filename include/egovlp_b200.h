@@ -55,7 +55,10 @@ enum {
   EGV_ACT_TANH = 3,
   EGV_ACT_GELU_BWD = 4, /* v *= gelu'(aux), aux = pre-activation   */
   EGV_ACT_RELU_BWD = 5, /* v *= (aux > 0),  aux = post-activation  */
-  EGV_ACT_TANH_BWD = 6  /* v *= 1 - aux^2,  aux = tanh output      */
+  EGV_ACT_TANH_BWD = 6, /* v *= 1 - aux^2,  aux = tanh output      */
+  EGV_ACT_GELU_DG = 7,  /* forward like EGV_ACT_GELU, but out_pre receives bf16(gelu'(v)) instead of bf16(v): the
+                           backward of the MLP then is a plain multiply (the GELU' epilogue was its slowest GEMM) */
+  EGV_ACT_MUL_AUX = 8   /* v *= aux,  aux = the derivative saved by EGV_ACT_GELU_DG */
 };
 typedef struct egv_gemm_args {
   int layout, M, N, K;

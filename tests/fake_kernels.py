@@ -12,8 +12,8 @@ import math
 import torch
 import torch.nn.functional as F
 
-from egovlpv2_b200.lib import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_RELU, ACT_RELU_BWD, ACT_TANH, ACT_TANH_BWD, GEMM_NN,
-                               GEMM_NT, GEMM_TN)
+from egovlpv2_b200.lib import (ACT_GELU, ACT_GELU_BWD, ACT_GELU_DG, ACT_MUL_AUX, ACT_NONE, ACT_RELU, ACT_RELU_BWD, ACT_TANH,
+                               ACT_TANH_BWD, GEMM_NN, GEMM_NT, GEMM_TN)
 
 
 def attn_indices(spec, B, device):
@@ -75,9 +75,15 @@ class FakeKernels:
         if bias is not None:
             v = v + bias
         if out_pre is not None:
-            out_pre.copy_(v)
-        if act == ACT_GELU:
+            if act == ACT_GELU_DG:   # the derivative is saved instead of the pre-activation
+                cdf = 0.5 * (1 + torch.erf(v / math.sqrt(2)))
+                out_pre.copy_(cdf + v * torch.exp(-0.5 * v * v) / math.sqrt(2 * math.pi))
+            else:
+                out_pre.copy_(v)
+        if act in (ACT_GELU, ACT_GELU_DG):
             v = F.gelu(v)
+        elif act == ACT_MUL_AUX:
+            v = v * aux.float()
         elif act == ACT_RELU:
             v = F.relu(v)
         elif act == ACT_TANH:

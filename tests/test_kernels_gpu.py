@@ -88,7 +88,7 @@ def test_gemm_plain(K, R, layout, shape):
 
 
 @pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_GELU, L.ACT_RELU, L.ACT_TANH, L.ACT_GELU_BWD, L.ACT_RELU_BWD,
-                                 L.ACT_TANH_BWD])
+                                 L.ACT_TANH_BWD, L.ACT_GELU_DG, L.ACT_MUL_AUX])
 def test_gemm_epilogue(K, R, act):
     M, N, Kd = 700, 520, 264
     A, B = _operands(L.GEMM_NT, M, N, Kd, seed=5)
@@ -147,9 +147,15 @@ def test_gemm_mlp_fast_epilogues(K, R, layout):
         rpre = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
         impl.gemm(layout, A, B, bias=bias, scale_dev=torch.tensor([0.37], device=DEV), residual=r32, out_f32=r32,
                   out_pre=rpre)                                                            # lean gated residual, in place
-        outs.append((o16.clone(), opre.clone(), g16, cs, g16b, p16, r32, rpre))
-    for n, a, r in zip("gelu pre gelu_bwd colsum gelu_bwd_nocs plain_bf16 residual_f32 residual_pre".split(), outs[0], outs[1]):
-        check(a, r, 1e-4 if n == "colsum" else (2e-5 if n == "residual_f32" else 4e-3), "fast epilogue " + n)
+        wide2 = torch.zeros(M, 2 * N, dtype=torch.bfloat16, device=DEV)
+        impl.gemm(layout, A, B, bias=bias, act=L.ACT_GELU_DG, out_bf16=wide2[:, :N], out_pre=wide2[:, N:])   # value + derivative
+        m16 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        cs2 = torch.zeros(N, device=DEV)
+        impl.gemm(layout, A, B, aux=wide2[:, N:], act=L.ACT_MUL_AUX, out_bf16=m16, colsum=cs2)
+        outs.append((o16.clone(), opre.clone(), g16, cs, g16b, p16, r32, rpre, wide2[:, :N].clone(), wide2[:, N:].clone(), m16, cs2))
+    names = "gelu pre gelu_bwd colsum gelu_bwd_nocs plain_bf16 residual_f32 residual_pre dg_value dg_deriv mul_aux colsum2"
+    for n, a, r in zip(names.split(), outs[0], outs[1]):
+        check(a, r, 2e-3 if n.startswith("colsum") else (2e-5 if n == "residual_f32" else 5e-3), "fast epilogue " + n)
 
 
 def test_gemm_inplace_residual_and_strided_outputs(K, R):

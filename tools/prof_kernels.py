@@ -106,8 +106,10 @@ def gemm_job(name, layout, Mm, Nn, Kk, **kw):
 gemm_job("gemm_qkv_fwd", L.GEMM_NT, M, 3 * C, C, bias=1, bf16=1)
 gemm_job("gemm_proj_fwd_res", L.GEMM_NT, M, C, C, bias=1, res=1, f32=1)
 gemm_job("gemm_fc1_gelu", L.GEMM_NT, M, 4 * C, C, bias=1, bf16=1, pre=1, act=L.ACT_GELU)
+gemm_job("gemm_fc1_gelu_dg", L.GEMM_NT, M, 4 * C, C, bias=1, bf16=1, pre=1, act=L.ACT_GELU_DG)
 gemm_job("gemm_fc2_res", L.GEMM_NT, M, C, 4 * C, bias=1, res=1, f32=1)
 gemm_job("gemm_dgrad_fc2_gelubwd", L.GEMM_NN, M, 4 * C, C, aux=1, bf16=1, act=L.ACT_GELU_BWD, colsum=1)
+gemm_job("gemm_dgrad_fc2_mulaux", L.GEMM_NN, M, 4 * C, C, aux=1, bf16=1, act=L.ACT_MUL_AUX, colsum=1)
 gemm_job("gemm_dgrad_fc1", L.GEMM_NN, M, C, 4 * C, bf16=1)
 gemm_job("gemm_dgrad_qkv", L.GEMM_NN, M, C, 3 * C, bf16=1)
 gemm_job("gemm_wgrad_qkv", L.GEMM_TN, 3 * C, C, M, f32=1, acc=1)
