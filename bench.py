@@ -165,6 +165,11 @@ def run_ours(a, rank, world, local_rank):
     use_graph = not a.no_graph
     step = PretrainStep(model, dev, max_steps=10000, warmup_steps=100, gather=a.gather)
     host = synthetic_batch(a.batch, a.frames, 224, a.seq, seed=1234 + rank, pin=True)
+    if a.input_dtype == "u8":
+        # decoder-format frames: the loader's / 255 + NormalizeVideo run inside the im2col kernel,
+        # the H2D copy carries 1 byte per sample instead of 4
+        gen = torch.Generator().manual_seed(99 + rank)
+        host["video"] = torch.randint(0, 256, tuple(host["video"].shape), generator=gen, dtype=torch.uint8).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     dev_batch = step.to_device(host)
     torch.cuda.synchronize()
@@ -283,7 +288,7 @@ def run_ours(a, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": a.batch * world, "parallelism": "dp%d" % world,
                    "l2_policy": "per-step working set (>30 GB of activations) exceeds the 126 MB L2; no flush needed",
-                   "embedding_gather": step.gather_kind, "cuda_graph": use_graph, "text_tower_side_stream": two_streams, "step_tflop_algorithmic": round(flops / 1e12, 2),
+                   "embedding_gather": step.gather_kind, "cuda_graph": use_graph, "input_dtype": a.input_dtype, "text_tower_side_stream": two_streams, "step_tflop_algorithmic": round(flops / 1e12, 2),
                    "step_frac_of_sustained_peak": round(flops / (ms / a.steps * 1e-3) / 1e12 / sustained, 4),
                    "xattn_i2t_fwd": region("xattn_i2t_fwd"), "xattn_t2i_fwd": region("xattn_t2i_fwd"),
                    "xattn_i2t_bwd": region("xattn_i2t_bwd"), "xattn_t2i_bwd": region("xattn_t2i_bwd"),
@@ -337,6 +342,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"], help="embedding all-gather implementation")
     ap.add_argument("--no-graph", action="store_true", help="eager kernel launches instead of replaying a captured CUDA graph")
+    ap.add_argument("--input-dtype", default="f32", choices=["f32", "u8"], dest="input_dtype",
+                    help="video frames as the reference's loader ships them (f32, normalised) or as decoded (uint8)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

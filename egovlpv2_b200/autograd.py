@@ -148,7 +148,8 @@ class VideoTokensFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, w, video, pw, pb, pos, tem, cls):
         p = {"patch_embed.proj.bias": pb.detach(), "pos_embed": pos.detach(), "temporal_embed": tem.detach()}
-        tokens, s = F_.video_tokens_fwd(_K(), _f32c(video), p, w, cls.detach(), cfg.patch, save=True)
+        video = video.detach().contiguous() if video.dtype == torch.uint8 else _f32c(video)
+        tokens, s = F_.video_tokens_fwd(_K(), video, p, w, cls.detach(), cfg.patch, save=True, norm=getattr(cfg, "norm", None))
         ctx.s, ctx.shapes = s, (pw.shape, pos.shape, tem.shape, cls.shape)
         ctx.sink = _sinks(["patch_embed.proj.weight", "patch_embed.proj.bias", "pos_embed", "temporal_embed", "cls_token"],
                           [pw, pb, pos, tem, cls])
@@ -320,6 +321,56 @@ class EgoNceFn(torch.autograd.Function):
         K.axpy(None, ctx.dt, 1.0, g, y=dt)
         K.axpy(None, ctx.dv, 1.0, g, y=dv)
         return dt, dv, None, None, None, None, None, None
+
+
+class ReluRowsFn(torch.autograd.Function):
+    """x f32 [M, C] -> bf16 relu(x) (model_epic_charades.py:118: txt_proj = Sequential(ReLU(), Linear))"""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = F_.relu_rows_fwd(_K(), _f32c(x))
+        ctx.y = y
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        dx = F_.relu_rows_bwd(_K(), ctx.y, dy.detach().contiguous())
+        ctx.y = None
+        return dx
+
+
+class DualLossFn(torch.autograd.Function):
+    """sim_matrix + NormSoftmax / MaxMarginRanking / AdaptiveMaxMarginRanking loss on gathered embeddings
+    (model_epic_charades.py:414-431; loss.py:13-31, 65-143); gradients for this rank's rows only (the all-gather's
+    backward is the local slice: trainer_epic.py AllGather_multi)."""
+
+    @staticmethod
+    def forward(ctx, t_local, v_local, t_all, v_all, weight_all, kind, param, fix_norm, row0):
+        K = _K()
+        G, P = t_all.shape
+        n = t_local.shape[0]
+        dev = t_all.device
+        sim = torch.empty(G, G, device=dev)
+        loss = torch.empty(1, device=dev)
+        dt, dv = torch.empty(n, P, device=dev), torch.empty(n, P, device=dev)
+        K.mark("dual_loss")
+        K.dual_loss(_f32c(t_all), _f32c(v_all), kind, param, sim, loss,
+                    weight=None if weight_all is None else _f32c(weight_all).reshape(-1), fix_norm=fix_norm,
+                    grad_row0=row0, grad_rows=n, dt=dt, dv=dv)
+        ctx.dt, ctx.dv = dt, dv
+        ctx.mark_non_differentiable(sim)
+        return loss.reshape(()), sim
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_loss, _ds):
+        K = _K()
+        g = _f32c(d_loss).reshape(1)
+        dt, dv = torch.empty_like(ctx.dt), torch.empty_like(ctx.dv)
+        K.axpy(None, ctx.dt, 1.0, g, y=dt)
+        K.axpy(None, ctx.dv, 1.0, g, y=dv)
+        return dt, dv, None, None, None, None, None, None, None
 
 
 def cfg(**kw):

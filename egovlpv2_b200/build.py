@@ -47,12 +47,20 @@ def build(force=False, verbose=True):
         return LIB
     nvcc = _nvcc()
 
+    headers = [d for d in deps if d not in srcs]
+
     def compile_one(src):
+        # per-object digest (its source + every header): an edit to one .cu recompiles that file only
         obj = os.path.join(OBJ, os.path.basename(src) + ".o")
+        mark, want = obj + ".sha", _digest([src] + headers)
+        if not force and os.path.exists(obj) and os.path.exists(mark) and open(mark).read() == want:
+            return obj
         cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        with open(mark, "w") as f:
+            f.write(want)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:

@@ -161,6 +161,67 @@ __global__ void __launch_bounds__(256) egonce_loss_kernel(const float* __restric
   if (threadIdx.x == 0) loss[0] = part / G;
 }
 
+// Fine-tuning losses on the text x video cosine matrix (model_epic_charades.py:419-431), single block like the above.
+//   kind 0  NormSoftmaxLoss (loss.py:13-31):  -mean_i log softmax(sim_i. / tau)_i - mean_i log softmax(sim_.i / tau)_i
+//   kind 1  MaxMarginRankingLoss (loss.py:65-100):          mean relu(m       - (sim_ii - sim_ij)), relu(m       - (sim_ii - sim_ji))
+//   kind 2  AdaptiveMaxMarginRankingLoss (loss.py:102-143): mean relu(w_i * m - (sim_ii - sim_ij)), relu(w_i * m - (sim_ii - sim_ji))
+// (fix_norm: the mean runs over the 2G(G-1) off-diagonal terms; otherwise over all 2G^2, the diagonal adding w_i * m each).
+__global__ void __launch_bounds__(256) dual_loss_kernel(const float* __restrict__ sim, int G, int kind, float param,
+                                                        const float* __restrict__ weight, int fix_norm,
+                                                        float* __restrict__ loss, float* __restrict__ dsim) {
+  __shared__ float red[8];
+  for (int e = threadIdx.x; e < G * G; e += 256) dsim[e] = 0.f;
+  __syncthreads();
+  float part = 0.f;
+  if (kind == 0) {
+    const float it = 1.0f / param;
+    for (int dir = 0; dir < 2; ++dir) {   // dir 0: thread i owns row i; dir 1: column i
+      for (int i = threadIdx.x; i < G; i += 256) {
+        const int si = dir == 0 ? G : 1, sj = dir == 0 ? 1 : G;
+        float mx = -INFINITY;
+        for (int j = 0; j < G; ++j) mx = fmaxf(mx, sim[i * si + j * sj] * it);
+        float z = 0.f;
+        for (int j = 0; j < G; ++j) z += __expf(sim[i * si + j * sj] * it - mx);
+        part -= sim[i * G + i] * it - mx - logf(z);
+        for (int j = 0; j < G; ++j) {
+          const float pj = __expf(sim[i * si + j * sj] * it - mx) / z;
+          dsim[i * si + j * sj] += (pj - (i == j ? 1.f : 0.f)) * it / G;
+        }
+      }
+      __syncthreads();
+    }
+    part = block_sum<256>(part, red);
+    if (threadIdx.x == 0) loss[0] = part / G;
+    return;
+  }
+  const float cnt = fix_norm ? 2.f * G * (G - 1) : 2.f * G * G;
+  const float gq = 1.0f / cnt;
+  for (int dir = 0; dir < 2; ++dir) {
+    for (int i = threadIdx.x; i < G; i += 256) {
+      const int si = dir == 0 ? G : 1, sj = dir == 0 ? 1 : G;
+      const float m = (kind == 2 ? weight[i] : 1.0f) * param;
+      const float xii = sim[i * G + i];
+      float dii = 0.f;
+      for (int j = 0; j < G; ++j) {
+        if (j == i) {
+          if (!fix_norm) part += fmaxf(m, 0.f);
+          continue;
+        }
+        const float a = m - (xii - sim[i * si + j * sj]);
+        if (a > 0.f) {
+          part += a;
+          dii -= gq;
+          dsim[i * si + j * sj] += gq;
+        }
+      }
+      dsim[i * G + i] += dii;
+    }
+    __syncthreads();
+  }
+  part = block_sum<256>(part, red);
+  if (threadIdx.x == 0) loss[0] = part / cnt;
+}
+
 // block (r, which): which=0 -> d t[row0+r] ; which=1 -> d v[row0+r].  Back-propagates through the L2 normalisation.
 __global__ void __launch_bounds__(256) egonce_grad_kernel(const float* __restrict__ dsim, const float* __restrict__ tn,
                                                           const float* __restrict__ vn, const float* __restrict__ inv_t,
@@ -253,6 +314,40 @@ extern "C" int egv_egonce(const float* t, const float* v, int G, int P, const fl
   if ((rc = check_launch("rowdot_kernel"))) return rc;
   egonce_loss_kernel<<<1, 256, 0, s>>>(sim, simv, simn, G, temperature, mask, loss, dsim);
   if ((rc = check_launch("egonce_loss_kernel"))) return rc;
+  if (grad_rows > 0 && (dt || dv)) {
+    dim3 grid((unsigned)grad_rows, 2);
+    egonce_grad_kernel<<<grid, 256, G * sizeof(float), s>>>(dsim, tn, vn, inv_t, inv_v, G, P, grad_row0, dt, dv);
+    if ((rc = check_launch("egonce_grad_kernel"))) return rc;
+  }
+  return EGV_OK;
+}
+
+extern "C" int64_t egv_dual_loss_scratch_floats(int G, int P) { return 2ll * G * P + 2ll * G + (long long)G * G; }
+
+extern "C" int egv_dual_loss(const float* t, const float* v, int G, int P, int kind, float param, const float* weight,
+                             int fix_norm, float* sim, float* loss, int grad_row0, int grad_rows, float* dt, float* dv,
+                             float* scratch, egv_stream_t stream) {
+  if (!t || !v || !sim || !loss || !scratch) return fail(EGV_ERR_ARG, "dual_loss: null pointer");
+  if (G <= 0 || P <= 0 || G > 4096) return fail(EGV_ERR_ARG, "dual_loss: bad sizes");
+  if (kind < EGV_DUAL_NORM_SOFTMAX || kind > EGV_DUAL_ADAPTIVE_MAX_MARGIN) return fail(EGV_ERR_ARG, "dual_loss: unknown kind");
+  if (kind == EGV_DUAL_ADAPTIVE_MAX_MARGIN && !weight) return fail(EGV_ERR_ARG, "dual_loss: the adaptive margin needs weights");
+  if (kind == EGV_DUAL_NORM_SOFTMAX && !(param > 0.f)) return fail(EGV_ERR_ARG, "dual_loss: temperature must be positive");
+  if (grad_rows < 0 || grad_row0 < 0 || grad_row0 + grad_rows > G) return fail(EGV_ERR_ARG, "dual_loss: bad gradient row range");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* tn = scratch;
+  float* vn = tn + (long long)G * P;
+  float* inv_t = vn + (long long)G * P;
+  float* inv_v = inv_t + G;
+  float* dsim = inv_v + G;
+  int rc;
+  rownorm_kernel<<<G, 256, 0, s>>>(t, P, 1e-8f, tn, inv_t);
+  if ((rc = check_launch("rownorm_kernel"))) return rc;
+  rownorm_kernel<<<G, 256, 0, s>>>(v, P, 1e-8f, vn, inv_v);
+  if ((rc = check_launch("rownorm_kernel"))) return rc;
+  rowdot_kernel<<<(unsigned)cdiv((long long)G * G, 8), 256, 0, s>>>(tn, vn, G, G, P, sim);
+  if ((rc = check_launch("rowdot_kernel"))) return rc;
+  dual_loss_kernel<<<1, 256, 0, s>>>(sim, G, kind, param, weight, fix_norm, loss, dsim);
+  if ((rc = check_launch("dual_loss_kernel"))) return rc;
   if (grad_rows > 0 && (dt || dv)) {
     dim3 grid((unsigned)grad_rows, 2);
     egonce_grad_kernel<<<grid, 256, G * sizeof(float), s>>>(dsim, tn, vn, inv_t, inv_v, G, P, grad_row0, dt, dv);

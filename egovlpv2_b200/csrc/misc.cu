@@ -235,6 +235,49 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
   }
 }
 
+// Same im2col straight from the decoder's uint8 frames: the reference's loader computes
+// frames.float() / 255 (base_dataset.py:248,300) and NormalizeVideo's (x - mean[c]) / std[c] (transforms.py:49) on the host
+// and ships fp32; here the H2D copy stays uint8 (4x fewer bytes) and the per-channel 256-entry table of
+// bf16((u / 255 - mean) / std) -- the exact fp32 operation order of the reference, then the bf16 operand rounding of
+// patchify_kernel -- is built in shared memory.  One thread moves 8 pixels (8 B read, 16 B write).
+struct U8Norm {
+  float mean[4], stdv[4];
+};
+__global__ void __launch_bounds__(256) patchify_u8_kernel(const uint8_t* __restrict__ video, int BT, int Cin, int H, int W,
+                                                          int p, U8Norm nrm, bf16* __restrict__ out) {
+  __shared__ unsigned short lut[4 * 256];
+  for (int t = threadIdx.x; t < Cin * 256; t += blockDim.x) {
+    const int c = t >> 8;
+    const float v = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(t & 255), 255.f), nrm.mean[c]), nrm.stdv[c]);
+    lut[t] = __bfloat16_as_ushort(__float2bfloat16(v));
+  }
+  __syncthreads();
+  const int gw = W / p, gh = H / p;
+  const int w8 = W >> 3;
+  const long long total = (long long)BT * Cin * H * w8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int Kc = Cin * p * p;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int xc = (int)(i % w8);
+    long long r = i / w8;
+    const int y = (int)(r % H);
+    r /= H;
+    const int c = (int)(r % Cin);
+    const int bt = (int)(r / Cin);
+    const int x = xc << 3;
+    const uint2 px = __ldg(reinterpret_cast<const uint2*>(video + (((long long)bt * Cin + c) * H + y) * W + x));
+    const unsigned short* l = lut + (c << 8);
+    const int gy = y / p, iy = y % p, gx = x / p, jx = x % p;
+    uint4 u;
+    u.x = (unsigned)l[px.x & 255u] | ((unsigned)l[(px.x >> 8) & 255u] << 16);
+    u.y = (unsigned)l[(px.x >> 16) & 255u] | ((unsigned)l[px.x >> 24] << 16);
+    u.z = (unsigned)l[px.y & 255u] | ((unsigned)l[(px.y >> 8) & 255u] << 16);
+    u.w = (unsigned)l[(px.y >> 16) & 255u] | ((unsigned)l[px.y >> 24] << 16);
+    bf16* dst = out + (((long long)bt * gh + gy) * gw + gx) * Kc + (c * p + iy) * p + jx;
+    *reinterpret_cast<uint4*>(dst) = u;
+  }
+}
+
 // tokens[b,0] = cls + pos[0]; tokens[b,1+f*Nf+n] = patch[(b*T+f)*Nf+n] + pos[1+n] + temporal[f]
 __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
                                                               const float* __restrict__ pos, const float* __restrict__ temporal,
@@ -489,6 +532,24 @@ extern "C" int egv_patchify(const float* video, int BT, int Cin, int H, int W, i
   const long long total = (long long)BT * Cin * H * (W / 8);
   patchify_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(video, BT, Cin, H, W, p, (bf16*)out_bf16);
   return check_launch("patchify_kernel");
+}
+
+extern "C" int egv_patchify_u8(const uint8_t* video, int BT, int Cin, int H, int W, int p, const float* mean, const float* stdv,
+                               void* out_bf16, egv_stream_t stream) {
+  if (!video || !out_bf16 || !mean || !stdv) return fail(EGV_ERR_ARG, "patchify_u8: null pointer");
+  if (Cin < 1 || Cin > 4) return fail(EGV_ERR_UNSUPPORTED, "patchify_u8: 1..4 input channels");
+  if (p % 8 || H % p || W % p || W % 8) return fail(EGV_ERR_UNSUPPORTED, "patchify_u8: patch size must be a multiple of 8 and divide H, W");
+  if ((((uintptr_t)video) & 7) || (((uintptr_t)out_bf16) & 15)) return fail(EGV_ERR_ARG, "patchify_u8: unaligned pointer");
+  U8Norm nrm;
+  for (int c = 0; c < 4; ++c) {
+    nrm.mean[c] = c < Cin ? mean[c] : 0.f;
+    nrm.stdv[c] = c < Cin ? stdv[c] : 1.f;
+    if (!(nrm.stdv[c] > 0.f)) return fail(EGV_ERR_ARG, "patchify_u8: std must be positive");
+  }
+  const long long total = (long long)BT * Cin * H * (W / 8);
+  if (total == 0) return EGV_OK;
+  patchify_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(video, BT, Cin, H, W, p, nrm, (bf16*)out_bf16);
+  return check_launch("patchify_u8_kernel");
 }
 
 extern "C" int egv_assemble_tokens(const float* patch, const float* cls, const float* pos, const float* temporal, int B,

@@ -637,15 +637,24 @@ def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True, sink=None):
 
 
 # ----------------------------------------------------------------------------------------------- embeddings
-def video_tokens_fwd(K, video, p, w, cls_token, patch, save=True):
+# NormalizeVideo defaults of the reference's transforms (data_loader/transforms.py:39-49), used when frames arrive as uint8
+VIDEO_NORM_MEAN, VIDEO_NORM_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def video_tokens_fwd(K, video, p, w, cls_token, patch, save=True, norm=None):
     """VideoPatchEmbed + token assembly (video_transformer.py:78-83, 354-372; model.py:211-232).
-    video [B,T,3,H,W] f32 -> tokens [B, 1+T*Nf, C] f32."""
+    video [B,T,3,H,W] f32 -> tokens [B, 1+T*Nf, C] f32.  uint8 video: the loader's `/ 255` and
+    NormalizeVideo (base_dataset.py:248, transforms.py:49; norm = (mean, std)) run inside the im2col kernel."""
     B, T, Cin, Hh, Ww = video.shape
     Nf = (Hh // patch) * (Ww // patch)
     C = w["patch_embed.proj.weight"].shape[0]
     K.mark("embed")
     cols = _e(video, (B * T * Nf, Cin * patch * patch), BF16)
-    K.patchify(video.reshape(B * T, Cin, Hh, Ww).contiguous(), patch, cols)
+    if video.dtype == torch.uint8:
+        mean, std = norm if norm is not None else (VIDEO_NORM_MEAN, VIDEO_NORM_STD)
+        K.patchify_u8(video.reshape(B * T, Cin, Hh, Ww).contiguous(), patch, cols, mean, std)
+    else:
+        K.patchify(video.reshape(B * T, Cin, Hh, Ww).contiguous(), patch, cols)
     pe = _e(video, (B * T * Nf, C), F32)
     K.gemm(GEMM_NT, cols, w["patch_embed.proj.weight"], bias=p["patch_embed.proj.bias"], out_f32=pe)
     tokens = _e(video, (B, 1 + T * Nf, C), F32)
@@ -715,6 +724,25 @@ def layernorm_rows_bwd(K, s, dy, gamma, sink=None):
     dx = _e(dy, s.x.shape, F32)
     K.layernorm_bwd(dy.contiguous(), s.x, gamma, s.mean, s.rstd, dx=dx, dgamma=G.vec("weight", C), dbeta=G.vec("bias", C))
     return dx, G.g.get("weight"), G.g.get("bias")
+
+
+def relu_rows_fwd(K, x):
+    """Leading nn.ReLU of the fine-tuning text projection (model_epic_charades.py:118): f32 [M, C] -> bf16 relu(x), the
+    operand format of the Linear that follows.  relu(x) = x * relu'(x): one pass of the activation-gradient kernel."""
+    xb = _e(x, x.shape, BF16)
+    K.cast(x.contiguous(), xb)
+    y = _e(x, x.shape, BF16)
+    K.act_grad(x.contiguous(), xb, ACT_RELU_BWD, y)
+    return y
+
+
+def relu_rows_bwd(K, y, dy):
+    """dx (f32) = dy * [y > 0]"""
+    db = _e(dy, dy.shape, BF16)
+    K.act_grad(dy.contiguous(), y, ACT_RELU_BWD, db)
+    dx = _e(dy, dy.shape, F32)
+    K.cast(db, dx)
+    return dx
 
 
 def mlp_chain_fwd(K, x, layers, save=True):

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libegovlp_b200.so")
 
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH, ACT_GELU_BWD, ACT_RELU_BWD, ACT_TANH_BWD, ACT_GELU_DG, ACT_MUL_AUX = range(9)
+DUAL_NORM_SOFTMAX, DUAL_MAX_MARGIN, DUAL_ADAPTIVE_MAX_MARGIN = range(3)
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -74,6 +75,7 @@ def _load():
     lib.egv_last_error.restype = C.c_char_p
     lib.egv_launch_count.restype = C.c_longlong
     lib.egv_egonce_scratch_floats.restype = c_int64
+    lib.egv_dual_loss_scratch_floats.restype = c_int64
     lib.egv_attention_workspace_bytes.restype = c_int64
     return lib
 
@@ -337,6 +339,15 @@ class Kernels:
         assert out.is_contiguous() and out.numel() == video.numel()
         self._check(self.lib.egv_patchify(_p(video), BT, Cin, H, W, p, _p(out), self._stream()))
 
+    def patchify_u8(self, video, p, out, mean, std):
+        """uint8 frames -> normalised bf16 patches; mean / std: per-channel sequences (transforms.py:49)."""
+        BT, Cin, H, W = video.shape
+        assert video.dtype == torch.uint8 and video.is_contiguous() and out.dtype == torch.bfloat16
+        assert out.is_contiguous() and out.numel() == video.numel() and len(mean) == Cin and len(std) == Cin
+        fa = C.c_float * Cin
+        self._check(self.lib.egv_patchify_u8(_p(video), BT, Cin, H, W, p, fa(*[float(m) for m in mean]),
+                                             fa(*[float(v) for v in std]), _p(out), self._stream()))
+
     def assemble_tokens(self, patch, cls, pos, temporal, B, T, Nf, tokens):
         Cd = tokens.shape[-1]
         for t in (patch, cls, pos, temporal, tokens):
@@ -390,6 +401,17 @@ class Kernels:
         self._check(self.lib.egv_egonce(_p(t), _p(v), G, P, _p(noun), noun.shape[1], _p(verb), verb.shape[1],
                                         c_float(temperature), _p(sim), _p(mask), _p(loss), grad_row0, grad_rows, _p(dt),
                                         _p(dv), _p(scratch), self._stream()))
+
+    def dual_loss(self, t, v, kind, param, sim, loss, weight=None, fix_norm=True, grad_row0=0, grad_rows=0, dt=None, dv=None):
+        """sim_matrix + NormSoftmax / (Adaptive)MaxMarginRanking loss on gathered embeddings (model_epic_charades.py:408-445)."""
+        G, P = t.shape
+        for x in (t, v, sim) + (() if weight is None else (weight,)):
+            assert x.dtype == torch.float32 and x.is_contiguous()
+        assert weight is None or weight.numel() == G
+        scratch = torch.empty(int(self.lib.egv_dual_loss_scratch_floats(G, P)), dtype=torch.float32, device=t.device)
+        self._check(self.lib.egv_dual_loss(_p(t), _p(v), G, P, int(kind), c_float(param), _p(weight), int(bool(fix_norm)),
+                                           _p(sim), _p(loss), grad_row0, grad_rows, _p(dt), _p(dv), _p(scratch),
+                                           self._stream()))
 
     # ------------------------------------------------------------------ optimiser
     def adamw(self, p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, hyper_dev=None):

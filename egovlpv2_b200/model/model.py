@@ -82,6 +82,8 @@ def state_dict_data_parallel_fix(load_state_dict, curr_state_dict):
 
 
 class FrozenInTime(nn.Module):
+    DUAL_TASK = 'EgoNCE'     # task name of the dual-encoder branch of infer() (model.py:198; 'Dual' in model_epic_charades.py:218)
+
     def __init__(self, video_params, text_params, projection_dim=4096, load_checkpoint=None, projection='minimal',
                  load_temporal_fix='bilinear', config=config, task_names='EgoNCE_ITM_MLM', norm_layer=None, embed_dim=768):
         super().__init__()
@@ -126,17 +128,7 @@ class FrozenInTime(nn.Module):
             raise NotImplementedError(f"{video_params['model']} not implemented")
         self.video_model.fc = nn.Identity()
 
-        if projection == 'minimal':
-            txt_proj = nn.Sequential(nn.Linear(self.text_model.config.hidden_size, projection_dim, bias=False),
-                                     nn.ReLU(inplace=True), nn.Linear(projection_dim, projection_dim, bias=True),
-                                     nn.ReLU(inplace=True), nn.Linear(projection_dim, projection_dim, bias=True))
-            vid_proj = nn.Sequential(nn.Linear(ftr_dim, projection_dim, bias=False),
-                                     nn.ReLU(inplace=True), nn.Linear(projection_dim, projection_dim, bias=True),
-                                     nn.ReLU(inplace=True), nn.Linear(projection_dim, projection_dim, bias=True))
-        elif projection == '':
-            txt_proj, vid_proj = nn.Identity(), nn.Identity()
-        else:
-            raise NotImplementedError
+        txt_proj, vid_proj = self._build_projections(projection, self.text_model.config.hidden_size, ftr_dim, projection_dim)
         self.txt_proj, self.vid_proj = txt_proj, vid_proj
 
         if fused_heads:
@@ -185,6 +177,21 @@ class FrozenInTime(nn.Module):
             new_state_dict = self._inflate_positional_embeds(new_state_dict)
             self.load_state_dict(new_state_dict, strict=False)
 
+    def _build_projections(self, projection, txt_dim, ftr_dim, projection_dim):
+        """model.py:104-121"""
+        if projection == 'minimal':
+            txt_proj = nn.Sequential(nn.Linear(txt_dim, projection_dim, bias=False),
+                                     nn.ReLU(inplace=True), nn.Linear(projection_dim, projection_dim, bias=True),
+                                     nn.ReLU(inplace=True), nn.Linear(projection_dim, projection_dim, bias=True))
+            vid_proj = nn.Sequential(nn.Linear(ftr_dim, projection_dim, bias=False),
+                                     nn.ReLU(inplace=True), nn.Linear(projection_dim, projection_dim, bias=True),
+                                     nn.ReLU(inplace=True), nn.Linear(projection_dim, projection_dim, bias=True))
+        elif projection == '':
+            txt_proj, vid_proj = nn.Identity(), nn.Identity()
+        else:
+            raise NotImplementedError
+        return txt_proj, vid_proj
+
     def set_device(self, device):
         self.device = device
 
@@ -194,6 +201,8 @@ class FrozenInTime(nn.Module):
             return x
         lins = [m for m in seq if isinstance(m, nn.Linear)]
         acts = [ACT_RELU] * (len(lins) - 1) + [ACT_NONE]
+        if isinstance(seq[0], nn.ReLU):    # model_epic_charades.py:118: Sequential(ReLU(), Linear)
+            x = A.ReluRowsFn.apply(x.reshape(-1, x.shape[-1])).view(x.shape)
         params = []
         for lin in lins:
             params.append(lin.weight)
@@ -273,7 +282,7 @@ class FrozenInTime(nn.Module):
         text_data, video_data = data['text'], data['video']
         if task_names is not None:
             self.task_names = task_names
-        if 'EgoNCE' in self.task_names:
+        if self.DUAL_TASK in self.task_names:
             streams.to_side(*[v for v in text_data.values() if torch.is_tensor(v)])
             with streams.side():     # the text tower runs next to the video tower
                 text_embeddings = self.compute_text(text_data)

@@ -161,6 +161,8 @@ class SpaceTimeTransformer(nn.Module):
         self.num_classes = num_classes
         self.num_features = self.embed_dim = embed_dim
         self.num_frames = num_frames
+        # statistics applied to uint8 frames on the device (the reference's loader applies them on the host)
+        self.norm_mean, self.norm_std = Fn.VIDEO_NORM_MEAN, Fn.VIDEO_NORM_STD
         norm_layer = norm_layer or partial(nn.LayerNorm, eps=1e-6)
         self.patch_embed = VideoPatchEmbed(img_size=img_size, patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim,
                                            num_frames=num_frames)
@@ -216,7 +218,8 @@ class SpaceTimeTransformer(nn.Module):
         pw = self.patch_embed.proj.weight
         w = {"patch_embed.proj.weight": cache().bf16(pw, (pw.shape[0], pw[0].numel()))}
         cls = self.cls_token if cls_token is None else cls_token
-        cfg = A.cfg(patch=self.patch_embed.patch_size[0])
+        # uint8 frames are normalised inside the im2col kernel with the loader's statistics (transforms.py:39-49)
+        cfg = A.cfg(patch=self.patch_embed.patch_size[0], norm=(self.norm_mean, self.norm_std))
         return A.VideoTokensFn.apply(cfg, w, x, pw, self.patch_embed.proj.bias, self.pos_embed, self.temporal_embed, cls)
 
     def forward_features(self, x):

@@ -169,6 +169,11 @@ int egv_add_rows_f32(float* y, int64_t ldy, const float* x, int64_t ldx, int row
 /* Patch embedding (video_transformer.py:78-83, 354-372; model.py:211-232) -------------------------
  * im2col: video f32 [BT, 3, H, W] -> bf16 [BT*gh*gw, 3*p*p] (column order c,i,j = Conv2d weight order) */
 int egv_patchify(const float* video, int BT, int Cin, int H, int W, int p, void* out_bf16, egv_stream_t stream);
+/* the same im2col from uint8 frames, fused with the loader's frames.float() / 255 (base/base_dataset.py:248,300) and
+ * NormalizeVideo's (x - mean[c]) / std[c] (data_loader/transforms.py:49): video u8 [BT, Cin, H, W]; mean / std = HOST
+ * arrays of Cin floats (Cin <= 4).  Output bit-identical to egv_patchify on the host-normalised fp32 frames. */
+int egv_patchify_u8(const uint8_t* video, int BT, int Cin, int H, int W, int p, const float* mean, const float* stdv,
+                    void* out_bf16, egv_stream_t stream);
 /* tokens[b,0] = cls + pos[0]; tokens[b,1+f*Nf+n] = patch[b,f,n] + pos[1+n] + temporal[f]   (all f32) */
 int egv_assemble_tokens(const float* patch, const float* cls, const float* pos, const float* temporal, int B,
                         int T, int Nf, int C, float* tokens, egv_stream_t stream);
@@ -200,6 +205,18 @@ int64_t egv_egonce_scratch_floats(int G, int P, int Dn, int Dv);
 int egv_egonce(const float* t, const float* v, int G, int P, const float* noun, int Dn, const float* verb, int Dv,
                float temperature, float* sim, uint8_t* mask, float* loss, int grad_row0, int grad_rows, float* dt,
                float* dv, float* scratch, egv_stream_t stream);
+
+/* Fine-tuning losses of the dual-encoder ('Dual') path (model_epic_charades.py:408-445): sim_matrix (:542-550) of the
+ * gathered embeddings + NormSoftmaxLoss (loss.py:13-31; param = temperature), MaxMarginRankingLoss (loss.py:65-100;
+ * param = margin) or AdaptiveMaxMarginRankingLoss (loss.py:102-143; param = margin, weight f32 [G] = data['relation']).
+ * Same layout and gradient-slice contract as egv_egonce.  scratch: egv_dual_loss_scratch_floats(G, P) floats. */
+#define EGV_DUAL_NORM_SOFTMAX 0
+#define EGV_DUAL_MAX_MARGIN 1
+#define EGV_DUAL_ADAPTIVE_MAX_MARGIN 2
+int64_t egv_dual_loss_scratch_floats(int G, int P);
+int egv_dual_loss(const float* t, const float* v, int G, int P, int kind, float param, const float* weight, int fix_norm,
+                  float* sim, float* loss, int grad_row0, int grad_rows, float* dt, float* dv, float* scratch,
+                  egv_stream_t stream);
 
 /* NVSwitch peer-to-peer all-gather (trainer_egoclip.py:25-41 AllGather_multi; model.py:385-388) ------------
  * Symmetric buffers: every rank egv_p2p_alloc()s `slots` (2 * W * slot_bytes: two sets, consecutive gathers alternate)

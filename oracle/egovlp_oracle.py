@@ -230,6 +230,45 @@ def egonce(x, sim_v, sim_n, temperature=0.05):
     return -li - lj, mask
 
 
+def norm_softmax_loss(x, temperature=0.05):
+    """loss.NormSoftmaxLoss.forward (loss.py:19-31)."""
+    i = torch.log_softmax(x / temperature, dim=1)
+    j = torch.log_softmax(x.t() / temperature, dim=1)
+    return -torch.diag(i).sum() / x.shape[0] - torch.diag(j).sum() / x.shape[0]
+
+
+def max_margin_ranking_loss(x, margin, weight=None, fix_norm=True):
+    """loss.MaxMarginRankingLoss.forward (loss.py:73-100) and, with `weight` [n], AdaptiveMaxMarginRankingLoss.forward
+    (loss.py:110-143): pairs (x_ii, x_ij) then (x_ii, x_ji) for all i, j; fix_norm removes i == j."""
+    n = x.shape[0]
+    terms = []
+    for i in range(n):
+        m = margin * (float(weight[i]) if weight is not None else 1.0)
+        for j in range(n):
+            if fix_norm and i == j:
+                continue
+            terms.append(torch.relu(m - (x[i, i] - x[i, j])))
+            terms.append(torch.relu(m - (x[i, i] - x[j, i])))
+    return torch.stack(terms).mean()
+
+
+def dual_step(data, sd, heads, depth, dataset_name="charades", temperature=0.05, margin=0.2):
+    """model_epic_charades.FrozenInTime.forward(task_names='Dual') for world size 1 (model_epic_charades.py:408-445):
+    txt_proj = Linear(ReLU(cls)) and vid_proj = Linear(cls), 256 wide (:118-119); NormSoftmaxLoss for 'charades',
+    AdaptiveMaxMarginRankingLoss weighted by data['relation'] for 'epic' (:425-430)."""
+    t = text_features(data["input_ids"], data["attention_mask"], sd, heads, depth)[:, 0]
+    t = _lin(F.relu(t), sd, "txt_proj.1")
+    v = _lin(video_features(data["video"], sd, heads, depth), sd, "vid_proj.0")
+    sim = sim_matrix(t, v)
+    if dataset_name == "epic":
+        loss = max_margin_ranking_loss(sim, margin, data["relation"])
+    elif dataset_name == "charades":
+        loss = norm_softmax_loss(sim, temperature)
+    else:
+        raise NameError()
+    return dict(text_embeds=t, video_embeds=v, sim_v2t=sim, Dual=loss)
+
+
 def mlm_head(x, sd, name="mlm_score", eps=1e-12):
     """heads.MLMHead (heads.py:38-50): BertPredictionHeadTransform (dense, erf-GELU, LN) -> decoder + bias."""
     t = _ln(F.gelu(_lin(x, sd, name + ".transform.dense")), sd, name + ".transform.LayerNorm", eps)
@@ -405,6 +444,16 @@ def key_shapes(C=768, heads=12, depth=12, n_fuse=6, T=16, img=224, patch=16, S_m
     ks["mlm_score.decoder.weight"] = (vocab, C)
     lin("itm_score.fc", 2, 2 * C)
     return ks
+
+
+def dual_key_shapes(**kw):
+    """state_dict schema of model_epic_charades.FrozenInTime: the pre-training schema with the 256-wide projections
+    txt_proj = Sequential(ReLU, Linear), vid_proj = Sequential(Linear) (model_epic_charades.py:118-119)."""
+    shapes = {k: v for k, v in key_shapes(**kw).items() if not k.startswith(("txt_proj.", "vid_proj."))}
+    C = kw.get("C", 768)
+    shapes.update({"txt_proj.1.weight": (256, C), "txt_proj.1.bias": (256,),
+                   "vid_proj.0.weight": (256, C), "vid_proj.0.bias": (256,)})
+    return shapes
 
 
 def seeded_state(shapes, seed=0, device="cpu"):

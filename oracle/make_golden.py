@@ -239,12 +239,98 @@ def golden_egonce(ref):
                os.path.join(OUT, "egonce.pt"))
 
 
+def _load_ref_epic_charades(ref):
+    """import the reference's model/model_epic_charades.py next to the already-shimmed model.* modules"""
+    import importlib
+    cwd = os.getcwd()
+    os.chdir(ref_shim.REF_ROOT)
+    try:
+        mec = importlib.import_module("model.model_epic_charades")
+    finally:
+        os.chdir(cwd)
+    mec.config["use_checkpoint"] = False
+    return mec
+
+
+def dual_key_shapes(c):
+    return O.dual_key_shapes(C=c["C"], heads=c["heads"], depth=c["depth"], n_fuse=c["n_fuse"], T=c["T"], img=c["img"],
+                             patch=c["patch"], vocab=c["vocab"], proj=c["proj"])
+
+
+def golden_dual(ref):
+    """Fine-tuning dual-encoder step: model_epic_charades.FrozenInTime.forward with
+    NormSoftmaxLoss (charades) and AdaptiveMaxMarginRankingLoss (epic), losses + similarities + gradients;
+    plus the three loss classes on a fixed similarity matrix."""
+    mec = _load_ref_epic_charades(ref)
+    c = dict(TINY, T=4)
+    text_cfg = dict(hidden_size=c["C"], num_hidden_layers=c["depth"], num_attention_heads=c["heads"],
+                    intermediate_size=4 * c["C"])
+    saved = mec.SpaceTimeTransformer
+    import functools
+    with ref_shim.tiny_wrapper(ref, img_size=c["img"], embed_dim=c["C"], depth=c["depth"], num_heads=c["heads"],
+                               text_cfg=text_cfg, dim_cross=c["C"]):
+        ref.rb.NUM_FUSE_BLOCK = 12 - (c["depth"] - c["n_fuse"])
+        mec.SpaceTimeTransformer = functools.partial(ref.vt.SpaceTimeTransformer, img_size=c["img"], embed_dim=c["C"],
+                                                     depth=c["depth"], num_heads=c["heads"])
+        try:
+            model = mec.FrozenInTime(
+                video_params=dict(model="SpaceTimeTransformer", arch_config="base_patch16_224", num_frames=c["T"],
+                                  pretrained=True, time_init="zeros", drop_path_rate=0.0),
+                text_params=dict(model="roberta-base", pretrained=True, input="text"),
+                projection="minimal", config=_yaml_cfg(c), task_names="EgoNCE_ITM_MLM", embed_dim=c["C"])
+        finally:
+            mec.SpaceTimeTransformer = saved
+    shapes = dual_key_shapes(c)
+    ref_sd = model.state_dict()
+    theirs = {k for k in ref_sd if not k.endswith("position_ids")}
+    assert set(shapes) == theirs, (sorted(set(shapes) - theirs)[:5], sorted(theirs - set(shapes))[:5])
+    for k in shapes:
+        assert tuple(ref_sd[k].shape) == tuple(shapes[k]), (k, ref_sd[k].shape, shapes[k])
+    sd = O.seeded_state(shapes, 7)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    data = O.synthetic_batch(c["B"], c["T"], c["img"], c["S"], seed=77)
+    g = torch.Generator().manual_seed(78)
+    relation = torch.rand(c["B"], generator=g)
+    out = dict(cfg=c, weight_seed=7, data_seed=77, relation=relation)
+    for ds, loss_mod in (("charades", ref.loss.NormSoftmaxLoss()), ("epic", ref.loss.AdaptiveMaxMarginRankingLoss(margin=0.2))):
+        model.zero_grad()
+        d = dict(video=data["video"].clone(), relation=relation.clone(),
+                 text=dict(input_ids=data["input_ids"].clone(), attention_mask=data["attention_mask"].clone()))
+        loss, ld, ret = model(d, _allgather, 1, _Args(), {}, loss_mod, 0, task_names="Dual", dataset_name=ds)
+        loss.backward()
+        grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None and p.grad.abs().max() > 0}
+        pick = ["txt_proj.1.weight", "txt_proj.1.bias", "vid_proj.0.weight", "vid_proj.0.bias", "video_model.cls_token",
+                "video_model.blocks.0.attn.qkv.weight", "video_model.blocks.7.mlp.fc2.weight",
+                "text_model.encoder.layer.0.attention.self.query.weight", "text_model.encoder.layer.7.output.dense.weight",
+                "video_model.norm.weight"]
+        out[ds] = dict(loss=loss.detach(), sim_v2t=ret["sim_v2t"].detach(), text_embeds=ret["text_embeds"].detach(),
+                       video_embeds=ret["video_embeds"].detach(), grads={k: grads[k] for k in pick},
+                       n_grads=len(grads))
+        print(f"dual[{ds}]: loss {float(loss):.6f}, {len(grads)} tensors with gradient")
+    # the loss classes on a fixed matrix (incl. fix_norm=False)
+    x = torch.tanh(torch.randn(6, 6, generator=g))
+    w = torch.rand(6, generator=g)
+    out["loss_cases"] = dict(
+        x=x, w=w,
+        norm_softmax=ref.loss.NormSoftmaxLoss(0.07)(x)[0],
+        max_margin=ref.loss.MaxMarginRankingLoss(0.2)(x),
+        max_margin_nofix=ref.loss.MaxMarginRankingLoss(0.2, fix_norm=False)(x),
+        adaptive=ref.loss.AdaptiveMaxMarginRankingLoss(0.4)(x, w),
+        adaptive_nofix=ref.loss.AdaptiveMaxMarginRankingLoss(0.4, fix_norm=False)(x, w))
+    torch.save(out, os.path.join(OUT, "dual_step.pt"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load(use_checkpoint=False)
+    if "--dual-only" in sys.argv:
+        golden_dual(ref)
+        return
     golden_egonce(ref)
     golden_blocks_fullwidth(ref)
     golden_tiny_step(ref)
+    golden_dual(ref)
     print("wrote", sorted(os.listdir(OUT)))
 
 

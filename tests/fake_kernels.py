@@ -256,6 +256,15 @@ class FakeKernels:
         x = video.reshape(BT, Cin, gh, p, gw, p).permute(0, 2, 4, 1, 3, 5).reshape(BT * gh * gw, Cin * p * p)
         out.copy_(x.reshape(out.shape))
 
+    def patchify_u8(self, video, p, out, mean, std):
+        # the reference's host pipeline: frames.float() / 255 (base_dataset.py:248), NormalizeVideo (transforms.py:49)
+        # evaluated on the CPU as a 256-entry table per channel (torch's CUDA `x / 255` multiplies by a rounded reciprocal)
+        m = torch.tensor(mean, dtype=torch.float32).view(-1, 1)
+        s = torch.tensor(std, dtype=torch.float32).view(-1, 1)
+        lut = ((torch.arange(256, dtype=torch.float32).view(1, -1) / 255 - m) / s).to(video.device)     # [Cin, 256]
+        ch = torch.arange(video.shape[1], device=video.device).view(1, -1, 1, 1).expand_as(video)
+        self.patchify(lut[ch, video.long()], p, out)
+
     def assemble_tokens(self, patch, cls, pos, temporal, B, T, Nf, tokens):
         self._launches += 1
         Cd = tokens.shape[-1]
@@ -343,6 +352,35 @@ class FakeKernels:
             L.backward()
         sim.copy_(s.detach())
         mask.copy_(m.to(torch.uint8))
+        loss.copy_(L.detach().reshape(loss.shape))
+        if dt is not None:
+            dt.copy_(tt.grad[grad_row0:grad_row0 + grad_rows])
+        if dv is not None:
+            dv.copy_(vv.grad[grad_row0:grad_row0 + grad_rows])
+
+    def dual_loss(self, t, v, kind, param, sim, loss, weight=None, fix_norm=True, grad_row0=0, grad_rows=0, dt=None, dv=None):
+        # restatement of model_epic_charades.py:542-550 (sim_matrix) + loss.py:13-31 / 65-100 / 102-143
+        self._launches += 5
+        tt = t.detach().clone().requires_grad_(True)
+        vv = v.detach().clone().requires_grad_(True)
+        G = t.shape[0]
+        with torch.enable_grad():
+            an = tt / tt.norm(dim=1, keepdim=True).clamp_min(1e-8)
+            bn = vv / vv.norm(dim=1, keepdim=True).clamp_min(1e-8)
+            x = an @ bn.t()
+            if kind == 0:
+                L = -torch.log_softmax(x / param, 1).diag().mean() - torch.log_softmax(x.t() / param, 1).diag().mean()
+            else:
+                w = weight.reshape(G, 1) if kind == 2 else torch.ones(G, 1, device=t.device)
+                d = x.diag().reshape(G, 1)
+                terms = torch.stack([torch.relu(w * param - (d - x)), torch.relu(w * param - (d - x.t()))])
+                if fix_norm:
+                    off = ~torch.eye(G, dtype=torch.bool, device=t.device)
+                    L = terms[:, off].mean()
+                else:
+                    L = terms.mean()
+            L.backward()
+        sim.copy_(x.detach())
         loss.copy_(L.detach().reshape(loss.shape))
         if dt is not None:
             dt.copy_(tt.grad[grad_row0:grad_row0 + grad_rows])

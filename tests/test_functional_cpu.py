@@ -259,3 +259,25 @@ def test_video_block_cls_only(sd, mode, fused):
     # and the full kernel sequence gives the same CLS row
     full, _ = Fn.video_block_fwd(K, x, p, w, HEADS, T, NF, y=y, y_bias=yb if fused else None, save=False)
     assert rel(out, full[:, 0]) <= tol(mode)
+
+
+def test_video_tokens_from_uint8_frames(sd):
+    """uint8 frames through the fused normalise + im2col == the reference's host pipeline
+    (frames.float() / 255, base_dataset.py:248; NormalizeVideo, transforms.py:49) followed by the fp32 path."""
+    K = FakeKernels()
+    g = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (B, T, 3, IMG, IMG), generator=g, dtype=torch.uint8)
+    mean, std = Fn.VIDEO_NORM_MEAN, Fn.VIDEO_NORM_STD
+    host = (frames.float() / 255 - torch.tensor(mean).view(1, 1, 3, 1, 1)) / torch.tensor(std).view(1, 1, 3, 1, 1)
+    vp = "video_model."
+    p = {k: sd[vp + k] for k in ("patch_embed.proj.bias", "pos_embed", "temporal_embed")}
+    w = {"patch_embed.proj.weight": sd[vp + "patch_embed.proj.weight"].reshape(C, -1).to(Fn.BF16)}
+    t_u8, _ = Fn.video_tokens_fwd(K, frames, p, w, sd["cls_token"], PATCH)
+    t_f32, _ = Fn.video_tokens_fwd(K, host, p, w, sd["cls_token"], PATCH)
+    assert torch.equal(t_u8, t_f32)
+    assert rel(t_u8, O.video_tokens(host, sd, sd["cls_token"])) <= 1e-2
+    # caller-provided statistics
+    t2, _ = Fn.video_tokens_fwd(K, frames, p, w, sd["cls_token"], PATCH, norm=((0.5, 0.5, 0.5), (0.25, 0.5, 1.0)))
+    host2 = (frames.float() / 255 - 0.5) / torch.tensor((0.25, 0.5, 1.0)).view(1, 1, 3, 1, 1)
+    t3, _ = Fn.video_tokens_fwd(K, host2, p, w, sd["cls_token"], PATCH)
+    assert torch.equal(t2, t3)

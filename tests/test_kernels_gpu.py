@@ -480,6 +480,23 @@ def test_patch_embed_and_text_embed(K, R):
     K.patchify(video, p, o1)
     R.patchify(video, p, o2)
     assert torch.equal(o1, o2)
+    # uint8 frames: fused / 255 + NormalizeVideo + im2col is bit-identical to the host pipeline + fp32 im2col
+    g = torch.Generator().manual_seed(107)
+    for shape, pp in (((B * T, 3, 2 * p, 2 * p), p), ((5, 3, 48, 24), 8), ((8 * 16, 3, 224, 224), 16), ((3, 1, 32, 32), 16)):
+        u8_host = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8)
+        mean, std = ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)) if shape[1] == 3 else ((0.45,), (0.225,))
+        # the reference's loader runs on the CPU (true fp32 divisions)
+        host = (((u8_host.float() / 255) - torch.tensor(mean).view(1, -1, 1, 1)) / torch.tensor(std).view(1, -1, 1, 1)).to(DEV)
+        u8 = u8_host.to(DEV)
+        a = torch.empty(u8.numel() // (shape[1] * pp * pp), shape[1] * pp * pp, dtype=torch.bfloat16, device=DEV)
+        b = torch.empty_like(a)
+        K.patchify_u8(u8, pp, a, mean, std)
+        K.patchify(host.contiguous(), pp, b)
+        assert torch.equal(a, b), shape
+        R.patchify_u8(u8, pp, b, mean, std)
+        assert torch.equal(a, b), shape
+    with pytest.raises(RuntimeError):
+        K.patchify_u8(u8, 16, a, (0.45,), (0.0,))
     patch = rnd(B * T * Nf, C, dtype=torch.float32, seed=102)
     cls, pos, tem = rnd(C, dtype=torch.float32, seed=103), rnd(1 + Nf, C, dtype=torch.float32, seed=104), rnd(T, C, dtype=torch.float32, seed=105)
     t1, t2 = torch.empty(B, 1 + T * Nf, C, device=DEV), torch.empty(B, 1 + T * Nf, C, device=DEV)
@@ -563,6 +580,43 @@ def test_egonce_vs_oracle(K, R, G):
     check(loss, oloss.detach().reshape(1), 1e-5, "egonce loss", atol=2e-6)
     check(dt, tt.grad[r0:r0 + nr], 1e-4, "egonce dt", atol=1e-7)
     check(dv, vv.grad[r0:r0 + nr], 1e-4, "egonce dv", atol=1e-7)
+
+
+@pytest.mark.parametrize("kind,param,fix_norm", [(0, 0.05, True), (0, 0.07, True), (1, 0.2, True), (1, 0.2, False),
+                                                 (2, 0.4, True), (2, 0.2, False)])
+def test_dual_loss_vs_oracle(K, kind, param, fix_norm):
+    """egv_dual_loss (sim_matrix + NormSoftmax / MaxMarginRanking / AdaptiveMaxMarginRanking + local-slice gradients)
+    vs autograd through the oracle's restatement of loss.py:13-31, 65-143 (pinned to the reference's classes in
+    tests/test_oracle_golden.py)."""
+    from oracle import egovlp_oracle as O
+    for G, P in ((1, 64), (6, 256), (32, 256), (257, 64)):
+        if G == 1 and kind != 0 and fix_norm:
+            continue    # mean over zero off-diagonal terms: NaN in the reference too
+        if G == 257 and kind != 0:
+            continue    # the pure-Python oracle loops over pairs
+        t, v = rnd(G, P, dtype=torch.float32, seed=151), rnd(G, P, dtype=torch.float32, seed=152)
+        v = v + 0.7 * t
+        w = torch.rand(G, generator=torch.Generator().manual_seed(4)).to(DEV)
+        sim, loss = torch.empty(G, G, device=DEV), torch.empty(1, device=DEV)
+        r0, nr = G // 4, max(G // 2, 1)
+        dt, dv = torch.empty(nr, P, device=DEV), torch.empty(nr, P, device=DEV)
+        K.dual_loss(t, v, kind, param, sim, loss, weight=w if kind == 2 else None, fix_norm=fix_norm, grad_row0=r0,
+                    grad_rows=nr, dt=dt, dv=dv)
+        tt, vv = t.clone().requires_grad_(True), v.clone().requires_grad_(True)
+        osim = O.sim_matrix(tt, vv)
+        if kind == 0:
+            oloss = O.norm_softmax_loss(osim, param)
+        else:
+            oloss = O.max_margin_ranking_loss(osim, param, w.cpu() if kind == 2 else None, fix_norm)
+        oloss.backward()
+        check(sim, osim.detach(), 1e-5, "dual sim")
+        check(loss, oloss.detach().reshape(1), 2e-5, "dual loss", atol=2e-6)
+        check(dt, tt.grad[r0:r0 + nr], 2e-4, "dual dt", atol=1e-7)
+        check(dv, vv.grad[r0:r0 + nr], 2e-4, "dual dv", atol=1e-7)
+    with pytest.raises(RuntimeError):
+        K.dual_loss(t, v, 2, 0.2, sim, loss)          # adaptive margin without weights
+    with pytest.raises(RuntimeError):
+        K.dual_loss(t, v, 7, 0.2, sim, loss)
 
 
 def test_adamw(K, R):

@@ -250,3 +250,34 @@ def test_two_streams_match_single_stream(golden_dir):
     assert g0.keys() == g1.keys()
     for k in g0:
         assert rel(g1[k], g0[k]) <= 2e-3 or (g0[k].norm().item() < 1e-6 and g1[k].norm().item() < 1e-6), (k, rel(g1[k], g0[k]))
+
+
+@pytest.mark.parametrize("dataset", ["charades", "epic"])
+def test_dual_step_vs_reference_golden(golden_dir, dataset):
+    """Fine-tuning dual-encoder step (model_epic_charades.py:408-445) on the CUDA path vs the UNMODIFIED reference."""
+    from egovlpv2_b200.model import loss as Lm
+    from tests.test_model_cpu import _dual_golden, build_tiny_dual
+    fx, c, shapes, sd, data = _dual_golden(golden_dir)
+    model = build_tiny_dual(c)
+    model.load_state_dict(sd, strict=False)
+    model.eval().to(DEV)
+    g = fx[dataset]
+    loss_mod = Lm.NormSoftmaxLoss() if dataset == "charades" else Lm.AdaptiveMaxMarginRankingLoss(margin=0.2)
+    d = {"video": data["video"].to(DEV), "relation": fx["relation"].to(DEV),
+         "text": {"input_ids": data["input_ids"].to(DEV), "attention_mask": data["attention_mask"].to(DEV)}}
+    args = types.SimpleNamespace(world_size=1, rank=0)
+    n0 = L.kernels().launch_count()
+    loss, loss_dict, ret = model(d, lambda t, n=None, a=None: t, 1, args, {}, loss_mod, 0, task_names="Dual",
+                                 dataset_name=dataset)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert L.kernels().launch_count() - n0 > 200
+    assert abs(float(loss) - float(g["loss"])) <= 2e-2 * max(1.0, abs(float(g["loss"])))
+    assert (ret["sim_v2t"].cpu() - g["sim_v2t"]).abs().max().item() <= 1.5e-2
+    assert rel(ret["text_embeds"].cpu(), g["text_embeds"]) <= 1e-2
+    assert rel(ret["video_embeds"].cpu(), g["video_embeds"]) <= 1e-2
+    params = dict(model.named_parameters())
+    gmax = max(r.norm().item() for r in g["grads"].values())
+    for k, ref in g["grads"].items():
+        den = max(ref.norm().item(), 0.05 * gmax)     # see tests/test_model_cpu.py for the floor
+        assert (params[k].grad.cpu() - ref).norm().item() / den <= 0.4, k

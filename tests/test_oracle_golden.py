@@ -90,3 +90,33 @@ def test_synthetic_batch_properties():
     assert (d["noun_vec"].sum(1) >= 1).all() and (d["verb_vec"].sum(1) >= 1).all()
     pos = O.roberta_embeddings  # position ids: cumsum over non-pad + pad_id (roberta.py:881-892)
     assert callable(pos)
+
+
+def test_dual_losses_golden(golden_dir):
+    """loss.py:13-31, 65-143 on a fixed matrix (values from the reference's own classes)"""
+    fx = torch.load(os.path.join(golden_dir, "dual_step.pt"))["loss_cases"]
+    x, w = fx["x"], fx["w"]
+    _close(O.norm_softmax_loss(x, 0.07), fx["norm_softmax"])
+    _close(O.max_margin_ranking_loss(x, 0.2), fx["max_margin"])
+    _close(O.max_margin_ranking_loss(x, 0.2, fix_norm=False), fx["max_margin_nofix"])
+    _close(O.max_margin_ranking_loss(x, 0.4, w), fx["adaptive"])
+    _close(O.max_margin_ranking_loss(x, 0.4, w, fix_norm=False), fx["adaptive_nofix"])
+
+
+@pytest.mark.parametrize("dataset", ["charades", "epic"])
+def test_dual_step_golden(golden_dir, dataset):
+    """model_epic_charades.FrozenInTime.forward(task_names='Dual') + backward"""
+    fx = torch.load(os.path.join(golden_dir, "dual_step.pt"))
+    c, g = fx["cfg"], fx[dataset]
+    shapes = O.dual_key_shapes(C=c["C"], heads=c["heads"], depth=c["depth"], n_fuse=c["n_fuse"], T=c["T"], img=c["img"],
+                               patch=c["patch"], vocab=c["vocab"], proj=c["proj"])
+    sd = {k: v.requires_grad_(True) for k, v in O.seeded_state(shapes, fx["weight_seed"]).items()}
+    data = dict(O.synthetic_batch(c["B"], c["T"], c["img"], c["S"], seed=fx["data_seed"]), relation=fx["relation"])
+    out = O.dual_step(data, sd, c["heads"], c["depth"], dataset_name=dataset)
+    for k in ("sim_v2t", "text_embeds", "video_embeds"):
+        _close(out[k], g[k])
+    _close(out["Dual"], g["loss"])
+    out["Dual"].backward()
+    for k, ref in g["grads"].items():
+        got = sd[k].grad
+        assert ((got - ref).norm() / ref.norm()).item() <= 1e-3, k
