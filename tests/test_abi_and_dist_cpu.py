@@ -95,6 +95,34 @@ def _worker(rank, world, port, q):
         assert v[1] == 100 * 1 + 1                       # global row 5 = rank 1, local row 1
         t_ids = d_itm["text"]["input_ids"].reshape(B)
         assert t_ids[2] == 100 * 1 + 2 and t_ids[1] == ids[1, 0]
+        # 4. fine-tuning Dual loss: every rank evaluates the loss on the gathered embeddings and keeps the gradient
+        #    slice of its own rows (model_epic_charades.py:416-431; trainer_epic.py:21-41 AllGather_multi backward)
+        from egovlpv2_b200 import autograd as A
+        gen = torch.Generator().manual_seed(5)
+        full_t, full_v = torch.randn(2 * world, 16, generator=gen), torch.randn(2 * world, 16, generator=gen)
+        rel_w = torch.rand(2 * world, generator=gen)
+        for kind, param in ((0, 0.05), (2, 0.3)):
+            lt = full_t[2 * rank:2 * rank + 2].clone().requires_grad_(True)
+            lv = full_v[2 * rank:2 * rank + 2].clone().requires_grad_(True)
+            w_all = g(rel_w[2 * rank:2 * rank + 2], world, None) if kind == 2 else None
+            loss, sim = A.DualLossFn.apply(lt, lv, g(lt.detach(), world, None), g(lv.detach(), world, None), w_all,
+                                           kind, param, True, 2 * rank)
+            loss.backward()
+            ft, fv = full_t.clone().requires_grad_(True), full_v.clone().requires_grad_(True)
+            tn, vn = ft / ft.norm(dim=1, keepdim=True), fv / fv.norm(dim=1, keepdim=True)
+            x = tn @ vn.t()
+            if kind == 0:
+                ref = -torch.log_softmax(x / param, 1).diag().mean() - torch.log_softmax(x.t() / param, 1).diag().mean()
+            else:
+                n = x.shape[0]
+                d, m = x.diag().reshape(n, 1), rel_w.reshape(n, 1) * param
+                off = ~torch.eye(n, dtype=torch.bool)
+                ref = torch.stack([torch.relu(m - (d - x)), torch.relu(m - (d - x.t()))])[:, off].mean()
+            ref.backward()
+            assert abs(loss.item() - ref.item()) < 1e-5
+            assert torch.allclose(sim, x.detach(), atol=1e-6)
+            assert torch.allclose(lt.grad, ft.grad[2 * rank:2 * rank + 2], atol=1e-6)
+            assert torch.allclose(lv.grad, fv.grad[2 * rank:2 * rank + 2], atol=1e-6)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback

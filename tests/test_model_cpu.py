@@ -335,3 +335,99 @@ def test_dual_losses_and_errors(golden_dir, fake_kernels):
     with pytest.raises(KeyError):       # model_epic_charades.py:83 indexes video_params["drop_path_rate"]
         ME.FrozenInTime(video_params=dict(model="SpaceTimeTransformer", num_frames=2, pretrained=True),
                         text_params=dict(model="roberta-base", pretrained=True, input="text"))
+
+
+# ------------------------------------------------------------ evaluation / downstream surfaces
+def downstream_style_forward(model, video, input_ids, attention_mask):
+    """Drives the SUB-MODULE surface the way the downstream projects do (EgoTaskQA/model/video_qa_model_linear_end2end.py:
+    202-279, QFVS/model/model_fused.py:172-198): own token assembly around video_model.patch_embed, positional block
+    calls, positional / keyword text-layer calls, all-token `norm(x)[:, :]` output."""
+    vm, tm = model.video_model, model.text_model
+    b, f = video.shape[:2]
+    x = vm.patch_embed(video)
+    x = x.flatten(2).transpose(2, 1).reshape(b, -1, vm.patch_embed.embed_dim)
+    x = torch.cat((model.cls_token.expand(b, -1, -1), x), dim=1)
+    cls_embed = vm.pos_embed[:, 0, :].unsqueeze(1)
+    tile_pos = vm.pos_embed[:, 1:, :].repeat(1, model.num_frames, 1)
+    tile_tem = vm.temporal_embed.repeat_interleave(model.patches_per_frame, 1)
+    total = torch.cat([cls_embed, tile_pos + tile_tem], dim=1)
+    x = vm.pos_drop(x + total[:, :x.shape[1]])
+    n = model.patches_per_frame
+    unf = model.num_text_layer - model.num_fuse_block
+    es = (model.einops_from_space, model.einops_to_space, model.einops_from_time, model.einops_to_time)
+    for blk in vm.blocks[:unf]:
+        x = blk(x, *es, n, f)                                   # positional form (under torch.utils.checkpoint upstream)
+    h = tm.embeddings(input_ids=input_ids)
+    ext = tm.get_extended_attention_mask(attention_mask, attention_mask.size(), h.device)
+    for layer in tm.encoder.layer[:unf]:
+        h = layer(h, ext)[0]
+    for i, blk in enumerate(vm.blocks[unf:model.num_text_layer]):
+        if i % 2 == 0:
+            nxt = blk(x, *es, y=h, y_mask=ext, time_n=n, space_f=f)
+            h = tm.encoder.layer[i + unf](h, ext, encoder_hidden_states=x, last_norm=True)[0]
+        else:
+            nxt = blk(x, *es, n, f, h, ext)
+            h = tm.encoder.layer[i + unf](h, ext, None, x, None, None, False, True)[0]
+        x = nxt
+    return model.pre_logits(model.norm(x)[:, :]), h
+
+
+def test_downstream_style_submodule_surface(golden_dir, fake_kernels):
+    fx, c, shapes, sd, data, plan = _golden(golden_dir)
+    model = build_tiny(c)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    with torch.no_grad():
+        x, h = downstream_style_forward(model, data["video"], data["input_ids"], data["attention_mask"])
+        ox, oh = O.fused_stack(data["video"], data["input_ids"], data["attention_mask"], sd, c["heads"], c["depth"], c["n_fuse"])
+        ox = O._ln(ox, sd, "norm", 1e-6)
+    assert x.shape == ox.shape and h.shape == oh.shape
+    assert ((x - ox).norm() / ox.norm()).item() <= 1e-2
+    assert ((h - oh).norm() / oh.norm()).item() <= 1e-2
+
+
+def egomcq_style_validation(model, video5, text, n_choices):
+    """trainer_egoclip.py:219-249: one caption against `n_choices` clips -- infer('EgoNCE') on mismatched text / video
+    batch sizes, then infer('ITM') with the caption repeated per clip; returns (vtc scores, vtm scores) [b1, n_choices]."""
+    b1 = text["input_ids"].shape[0]
+    data = {"video": video5, "text": dict(text)}
+    ret = model.infer(data, return_embeds=True, task_names="EgoNCE", ret={})
+    data["text"]["input_ids"] = torch.repeat_interleave(data["text"]["input_ids"], n_choices, dim=0)
+    data["text"]["attention_mask"] = torch.repeat_interleave(data["text"]["attention_mask"], n_choices, dim=0)
+    ret = model.infer(data, return_embeds=True, task_names="ITM", ret=ret)
+    te = ret["text_embeds"].reshape(b1, 1, -1)
+    ve = ret["video_embeds"].reshape(b1, n_choices, -1)
+    vtc = M.sim_matrix_batch_val(te, ve).squeeze(1)
+    vtm = torch.softmax(ret["cross_attn_itm_logits"], dim=1)[:, 1:].t().reshape(1, b1, n_choices)[0].contiguous()
+    return vtc, vtm
+
+
+def egomcq_oracle(sd, c, video5, text, n_choices):
+    b1 = text["input_ids"].shape[0]
+    t = O.projection(O.text_features(text["input_ids"], text["attention_mask"], sd, c["heads"], c["depth"])[:, 0], sd, "txt_proj")
+    v = O.projection(O.video_features(video5, sd, c["heads"], c["depth"]), sd, "vid_proj")
+    tn = t / t.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+    vn = (v / v.norm(dim=-1, keepdim=True).clamp_min(1e-8)).reshape(b1, n_choices, -1)
+    vtc = torch.einsum("bd,bkd->bk", tn, vn)
+    ids = torch.repeat_interleave(text["input_ids"], n_choices, dim=0)
+    am = torch.repeat_interleave(text["attention_mask"], n_choices, dim=0)
+    x, h = O.fused_stack(video5, ids, am, sd, c["heads"], c["depth"], c["n_fuse"])
+    vtm = torch.softmax(O.itm_logits(x, h, sd), dim=1)[:, 1].reshape(b1, n_choices)
+    return vtc, vtm
+
+
+def test_egomcq_style_validation(golden_dir, fake_kernels):
+    fx, c, shapes, sd, data, plan = _golden(golden_dir)
+    model = build_tiny(c)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    b1, k = 2, 3
+    g = torch.Generator().manual_seed(21)
+    video = torch.randn(b1 * k, c["T"], 3, c["img"], c["img"], generator=g)
+    text = {"input_ids": data["input_ids"][:b1], "attention_mask": data["attention_mask"][:b1]}
+    with torch.no_grad():
+        vtc, vtm = egomcq_style_validation(model, video, text, k)
+        ovtc, ovtm = egomcq_oracle(sd, c, video, text, k)
+    assert vtc.shape == (b1, k) and vtm.shape == (b1, k)
+    assert (vtc - ovtc).abs().max().item() <= 1.5e-2
+    assert (vtm - ovtm).abs().max().item() <= 1.5e-2

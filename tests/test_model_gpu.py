@@ -281,3 +281,36 @@ def test_dual_step_vs_reference_golden(golden_dir, dataset):
     for k, ref in g["grads"].items():
         den = max(ref.norm().item(), 0.05 * gmax)     # see tests/test_model_cpu.py for the floor
         assert (params[k].grad.cpu() - ref).norm().item() / den <= 0.4, k
+
+
+def test_downstream_style_submodule_surface_gpu(golden_dir):
+    """the sub-module surface driven the way EgoTaskQA / QFVS do (all-token fused forward)."""
+    from tests.test_model_cpu import downstream_style_forward
+    fx, c, shapes, sd, data, plan = _golden(golden_dir)
+    model = build_tiny(c)
+    model.load_state_dict(sd, strict=False)
+    model.eval().to(DEV)
+    with torch.no_grad():
+        x, h = downstream_style_forward(model, data["video"].to(DEV), data["input_ids"].to(DEV), data["attention_mask"].to(DEV))
+        ox, oh = O.fused_stack(data["video"], data["input_ids"], data["attention_mask"], sd, c["heads"], c["depth"], c["n_fuse"])
+        ox = O._ln(ox, sd, "norm", 1e-6)
+    assert rel(x.cpu(), ox) <= 1e-2 and rel(h.cpu(), oh) <= 1e-2
+
+
+def test_egomcq_style_validation_gpu(golden_dir):
+    """trainer_egoclip.py:219-249 (5-way infer('EgoNCE') + infer('ITM')) on the CUDA path."""
+    from tests.test_model_cpu import egomcq_oracle, egomcq_style_validation
+    fx, c, shapes, sd, data, plan = _golden(golden_dir)
+    model = build_tiny(c)
+    model.load_state_dict(sd, strict=False)
+    model.eval().to(DEV)
+    b1, k = 2, 5
+    g = torch.Generator().manual_seed(21)
+    video = torch.randn(b1 * k, c["T"], 3, c["img"], c["img"], generator=g)
+    text = {"input_ids": data["input_ids"][:b1], "attention_mask": data["attention_mask"][:b1]}
+    with torch.no_grad():
+        vtc, vtm = egomcq_style_validation(model, video.to(DEV), {kk: v.to(DEV) for kk, v in text.items()}, k)
+        ovtc, ovtm = egomcq_oracle(sd, c, video, text, k)
+    assert (vtc.cpu() - ovtc).abs().max().item() <= 1.5e-2
+    assert (vtm.cpu() - ovtm).abs().max().item() <= 1.5e-2
+    assert torch.equal(vtc.argmax(1).cpu(), ovtc.argmax(1)) or (ovtc.topk(2, 1).values.diff(dim=1).abs().min() < 3e-2)
