@@ -7,13 +7,13 @@ timeout 900 python -m pytest tests/ -m gpu -q --tb=short -p no:cacheprovider > g
 echo "== gpu tests: exit $? : $(tail -n 1 gpurun_out/gpu_tests.log)"; grep -E "^E|FAILED" gpurun_out/gpu_tests.log | head -12
 timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1
 echo "== smoke: exit $? : $(tail -n 1 gpurun_out/smoke.log)"
-timeout 1200 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+timeout 300 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "== bench: exit $?"; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
-EGV_TEXT_STREAM=0 timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu.log 2>&1
+EGV_TEXT_STREAM=0 timeout 330 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu.log 2>&1
 echo "== ncu launch list: exit $?"; python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launches_summary.md; head -12 gpurun_out/launches_summary.md; tail -1 gpurun_out/launches_summary.md
 python tools/gemm_traffic.py gpurun_out/launches.csv gpurun_out/gemm_traffic.json
 gzip -f gpurun_out/launches.csv
-PROF_NO_TIMING=1 PROF_ONLY=gemm_qkv_fwd,gemm_fc1_gelu,gemm_wgrad_fc2,gemm_dgrad_fc1,attn_space,attn_time,attn_cls,ln_bwd timeout 900 ncu --set full --clock-control none --profile-from-start off -o /tmp/kern python tools/prof_kernels.py > gpurun_out/ncu_kern.log 2>&1
+PROF_NO_TIMING=1 PROF_ONLY=gemm_qkv_fwd,gemm_fc1_gelu,gemm_wgrad_fc2,gemm_dgrad_fc1,attn_space,attn_time,attn_cls,ln_bwd timeout 240 ncu --set full --clock-control none --profile-from-start off -o /tmp/kern python tools/prof_kernels.py > gpurun_out/ncu_kern.log 2>&1
 echo "== ncu full: exit $?"
 ncu -i /tmp/kern.ncu-rep --page details --csv > gpurun_out/final_details.csv 2>/dev/null
 ncu -i /tmp/kern.ncu-rep --page raw --csv > gpurun_out/final_raw.csv 2>/dev/null
