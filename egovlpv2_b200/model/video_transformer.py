@@ -214,7 +214,7 @@ class SpaceTimeTransformer(nn.Module):
         """patch embedding + CLS + tiled spatial / repeated temporal position terms (video_transformer.py:354-372;
         model.py:211-232 passes FrozenInTime.cls_token).  x [B,T,3,H,W] -> [B, 1+T*Nf, C] f32."""
         B, T = x.shape[:2]
-        assert T <= self.num_frames, (T, self.num_frames)
+        assert T == self.patch_embed.num_frames, (T, self.patch_embed.num_frames)   # video_transformer.py:80
         pw = self.patch_embed.proj.weight
         w = {"patch_embed.proj.weight": cache().bf16(pw, (pw.shape[0], pw[0].numel()))}
         cls = self.cls_token if cls_token is None else cls_token

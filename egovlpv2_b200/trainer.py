@@ -160,6 +160,45 @@ class PretrainStep:
         return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}
 
 
+def build_dual_model(T=16, img=224, C=768, heads=12, depth=12, n_fuse=6, vocab=50265):
+    """model_epic_charades.FrozenInTime as configs/ft/epic.json / charades.json build it (projection 'minimal')."""
+    from .model.model_epic_charades import FrozenInTime as DualFrozenInTime
+    return DualFrozenInTime(
+        video_params=dict(model="SpaceTimeTransformer", arch_config="base_patch16_224", num_frames=T, pretrained=True,
+                          time_init="zeros", drop_path_rate=0.0, img_size=img, embed_dim=C, depth=depth, num_heads=heads),
+        text_params=dict(model="roberta-base", pretrained=True, input="text",
+                         config=dict(hidden_size=C, num_hidden_layers=depth, num_attention_heads=heads,
+                                     intermediate_size=4 * C, vocab_size=vocab)),
+        projection="minimal", config=model_config(C, heads, depth, n_fuse, vocab), task_names="EgoNCE_ITM_MLM", embed_dim=C)
+
+
+class FinetuneStep(PretrainStep):
+    """One fine-tuning step of the dual-encoder mains (trainer_epic.py:128-150 / trainer_charades.py): H2D, forward
+    (task_names='Dual'), backward, gradient all-reduce, fused AdamW.  Same graph capture / prefetch machinery as the
+    pre-training step; the batch additionally carries `relation` [B] for dataset_name='epic'."""
+
+    def __init__(self, model, device, loss_fn, dataset_name="epic", **kw):
+        super().__init__(model, device, tasks="Dual", **kw)
+        self.loss_fn, self.dataset_name = loss_fn, dataset_name
+
+    def _device_step(self, dev_batch):
+        d = dev_batch
+        data = {"video": d["video"], "text": {"input_ids": d["input_ids"], "attention_mask": d["attention_mask"]}}
+        if self.dataset_name == "epic":
+            data["relation"] = d["relation"]
+        self.opt.zero_grad()
+        loss, loss_dict, _ = self.model(data, self.allgather, self.world, self.args, self.cfg, self.loss_fn, self.rank,
+                                        task_names="Dual", dataset_name=self.dataset_name)
+        loss.backward()
+        streams.join()
+        if self.world > 1:
+            dist.all_reduce(self.opt.arena.grad)
+            self.opt.launch(grad_scale=1.0 / self.world)
+        else:
+            self.opt.launch()
+        return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}
+
+
 def step_flops(B, T, img=224, patch=16, S=32, C=768, depth=12, n_fuse=6, P=4096, V=50265):
     """Algorithmic FLOPs of one step (fwd + bwd = 3x fwd, no recompute) -- SURVEY.md section 8(d)."""
     Nf = (img // patch) ** 2

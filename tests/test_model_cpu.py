@@ -161,6 +161,20 @@ def test_errors_mirror_reference(fake_kernels):
                        config=dict(M.DEFAULT_CONFIG, num_layers=2, num_fuse_block=1))
 
 
+def test_frame_count_must_match_like_reference(golden_dir, fake_kernels):
+    """video_transformer.py:80: `assert F == self.num_frames` in the patch embedding, on every path that embeds frames"""
+    fx, c, shapes, sd, data, plan = _golden(golden_dir)
+    model = build_tiny(c)
+    short = data["video"][:, :c["T"] - 1]
+    with pytest.raises(AssertionError):
+        model.compute_video(short)
+    with pytest.raises(AssertionError):
+        model.video_model.patch_embed(short)
+    with pytest.raises(AssertionError):
+        model.infer({"video": short, "text": {"input_ids": data["input_ids"], "attention_mask": data["attention_mask"]}},
+                    task_names="ITM", ret={})
+
+
 def test_temporal_embed_inflation(golden_dir, fake_kernels):
     fx, c, shapes, sd, _, _ = _golden(golden_dir)
     c4 = dict(c, T=4)
@@ -431,3 +445,30 @@ def test_egomcq_style_validation(golden_dir, fake_kernels):
     assert vtc.shape == (b1, k) and vtm.shape == (b1, k)
     assert (vtc - ovtc).abs().max().item() <= 1.5e-2
     assert (vtm - ovtm).abs().max().item() <= 1.5e-2
+
+
+def test_finetune_step_driver(golden_dir, fake_kernels):
+    """trainer.FinetuneStep (forward 'Dual' + backward + fused AdamW on the flat arena): the loss equals the reference
+    golden, ReLU-gated projection / tower gradients reach the arena, and a step changes the parameters."""
+    from egovlpv2_b200.model import loss as Lm
+    from egovlpv2_b200.trainer import FinetuneStep
+    old = Fn.BF16
+    Fn.BF16 = torch.float32
+    try:
+        fx, c, shapes, sd, data = _dual_golden(golden_dir)
+        model = build_tiny_dual(c)
+        model.load_state_dict(sd, strict=False)
+        model.eval()
+        step = FinetuneStep(model, torch.device("cpu"), Lm.AdaptiveMaxMarginRankingLoss(margin=0.2), dataset_name="epic", lr=1e-3)
+        batch = {"video": data["video"], "input_ids": data["input_ids"], "attention_mask": data["attention_mask"],
+                 "relation": fx["relation"]}
+        w0 = model.txt_proj[1].weight.detach().clone()
+        loss, ld = step.step(batch)
+        assert abs(float(loss) - float(fx["epic"]["loss"])) <= 3e-4 and set(ld) == {"Dual"}
+        g = model.txt_proj[1].weight.grad
+        ref = fx["epic"]["grads"]["txt_proj.1.weight"]
+        assert ((g - ref).norm() / ref.norm()).item() <= 5e-3
+        assert not torch.equal(model.txt_proj[1].weight.detach(), w0)
+    finally:
+        Fn.BF16 = old
+        weights.cache().arena = None
