@@ -73,13 +73,18 @@ ld_f, g_f = run(full, dict(labels=labels, swap_video=swap, neg_idx=neg), lambda 
 for k in ld_f:
     assert abs(ld_r[k] - ld_f[k]) <= 2e-2 * max(1.0, abs(ld_f[k])), (k, ld_r[k], ld_f[k], rank)
 worst = 0.0
-for n in sorted(g_f)[::7]:
+names = sorted(g_f)[::7]
+gmax = max(g_f[n].norm().item() for n in names)
+for n in names:
     s = g_r[n].clone()
     dist.all_reduce(s)
     ref = g_f[n]
-    err = ((s - ref).norm() / ref.norm().clamp_min(1e-6)).item()
+    # attention key biases have an analytically ZERO gradient (softmax is invariant to a per-query constant): what both
+    # runs hold there is rounding noise ~1e-4 of the other gradients, so errors are measured against a floor
+    den = max(ref.norm().item(), 1e-3 * gmax)
+    err = (s - ref).norm().item() / den
     worst = max(worst, err)
-    assert err <= 0.2, (n, err)
+    assert err <= 0.2, (n, err, ref.norm().item(), gmax)
 if rank == 0:
     print("multi-rank step parity ok: losses %s ; worst sampled gradient rel-L2 %.3f" % (ld_r, worst))
 dist.barrier()
