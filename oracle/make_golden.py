@@ -321,16 +321,50 @@ def golden_dual(ref):
     torch.save(out, os.path.join(OUT, "dual_step.pt"))
 
 
+def golden_optim(ref):
+    """The reference's optimiser grouping and LR schedule (set_optim_schedule.py:16-129) applied to the reference's own
+    tiny model: parameter name -> (weight_decay, lr) and the cosine-with-warm-up multipliers of the first steps."""
+    import importlib
+    import transformers.optimization as topt
+    if not hasattr(topt, "AdamW"):          # removed from transformers 5.x; same constructor signature for what is read here
+        topt.AdamW = lambda groups, lr, eps, betas: torch.optim.AdamW(groups, lr=lr, eps=eps, betas=betas)
+    sys.path.insert(0, ref_shim.REF_ROOT)
+    sos = importlib.import_module("set_optim_schedule")
+    model, shapes, sd = build_tiny_reference(ref, TINY, seed=0)
+    cfg = {"optimizer": {"type": "AdamW", "args": {"lr": 3e-5, "weight_decay": 0.01, "lr_mult_head": 2.0,
+                                                   "lr_mult_cross_modal": 4.0}}}
+    opt, sched = sos.set_schedule(model, cfg, {"end_lr": 1e-7, "decay_power": "cosine"}, max_steps=50, warmup_steps=5)
+    by_id = {}
+    for gi, g in enumerate(opt.param_groups):
+        for p in g["params"]:
+            assert id(p) not in by_id
+            by_id[id(p)] = (gi, g["weight_decay"], g["initial_lr"] if "initial_lr" in g else g["lr"])
+    groups = {n: by_id.get(id(p)) for n, p in model.named_parameters()}
+    assert all(v is not None for v in groups.values())
+    scales = []
+    for _ in range(50):
+        scales.append(sched.get_last_lr()[0] / 3e-5)
+        opt.step()
+        sched.step()
+    torch.save(dict(groups=groups, lr_scales=scales, lr=3e-5, weight_decay=0.01, lr_mult_head=2.0, lr_mult_cross_modal=4.0,
+                    max_steps=50, warmup_steps=5), os.path.join(OUT, "optim_groups.pt"))
+    print("optimiser groups: %d parameters in %d groups" % (len(groups), len(opt.param_groups)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load(use_checkpoint=False)
     if "--dual-only" in sys.argv:
         golden_dual(ref)
         return
+    if "--optim-only" in sys.argv:
+        golden_optim(ref)
+        return
     golden_egonce(ref)
     golden_blocks_fullwidth(ref)
     golden_tiny_step(ref)
     golden_dual(ref)
+    golden_optim(ref)
     print("wrote", sorted(os.listdir(OUT)))
 
 

@@ -472,3 +472,33 @@ def test_finetune_step_driver(golden_dir, fake_kernels):
     finally:
         Fn.BF16 = old
         weights.cache().arena = None
+
+
+def test_optimizer_groups_and_schedule_match_reference(golden_dir, fake_kernels):
+    """set_optim_schedule.py:16-129 run by the UNMODIFIED reference on its own tiny model (oracle/make_golden.py
+    golden_optim): every parameter lands in the same (weight_decay, lr) group here -- including the substring quirks
+    (norm3 / norm_i2t_i decay, alpha_* in the cross-modal group) -- and the cosine warm-up multipliers agree."""
+    from egovlpv2_b200.optim import FusedAdamW, param_groups
+    fx = torch.load(os.path.join(golden_dir, "optim_groups.pt"))
+    c = _golden(golden_dir)[1]
+    model = build_tiny(c)
+    groups = param_groups(model, fx["lr"], fx["weight_decay"], fx["lr_mult_head"], fx["lr_mult_cross_modal"])
+    mine = {}
+    names = {id(p): n for n, p in model.named_parameters()}
+    for g in groups:
+        for p in g["params"]:
+            assert names[id(p)] not in mine
+            mine[names[id(p)]] = (g["weight_decay"], g["lr"])
+    assert set(mine) == set(fx["groups"])
+    for n, (gi, wd, lr) in fx["groups"].items():
+        assert mine[n][0] == wd and abs(mine[n][1] - lr) <= 1e-12, (n, mine[n], wd, lr)
+    assert mine["video_model.blocks.6.norm3.weight"][0] == fx["weight_decay"]          # 'norm3.' matches no no-decay entry
+    assert mine["video_model.blocks.6.attn.alpha_i2t"] == (fx["weight_decay"], fx["lr"] * fx["lr_mult_cross_modal"])
+    opt = FusedAdamW(model, fx["lr"], fx["weight_decay"], fx["lr_mult_head"], fx["lr_mult_cross_modal"],
+                     max_steps=fx["max_steps"], warmup_steps=fx["warmup_steps"])
+    try:
+        for want in fx["lr_scales"]:
+            assert abs(opt.lr_scale() - want) <= 1e-6
+            opt.step_count += 1
+    finally:
+        weights.cache().arena = None
