@@ -66,7 +66,7 @@ def _allgather(t, n_gpu, args):
     return t
 
 
-def reference_step(ref, model, data, plan):
+def reference_step(ref, model, data, plan, grad=False):
     """Drive FrozenInTime.forward (model.py:370-487) with the host RNG of the ITM pass
     (:438 randperm, :459 np.random.rand, :460/465 multinomial) replaced by `plan`."""
     labels = plan["labels"]
@@ -86,7 +86,7 @@ def reference_step(ref, model, data, plan):
         d = dict(video=data["video"].clone(),
                  text=dict(input_ids=data["input_ids"].clone(), attention_mask=data["attention_mask"].clone()),
                  text_mlm_ids=data["text_mlm_ids"].clone(), text_mlm_labels=data["text_mlm_labels"].clone())
-        with torch.no_grad():
+        with torch.set_grad_enabled(grad):
             loss, loss_dict, ret = model(d, data["noun_vec"], data["verb_vec"], _allgather, 1, _Args(),
                                          {"loss": {"type": "EgoNCE"}}, ref.loss.EgoNCE(), 0,
                                          task_names="EgoNCE_MLM_ITM")
