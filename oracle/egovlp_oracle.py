@@ -127,6 +127,51 @@ def cross_attention_i2t(a, y, y_mask, sd, prefix, heads):
     return a + sd[prefix + "alpha_i2t"] * c
 
 
+def cross_attention_i2t_reassociated(a, y, y_mask, sd, prefix, heads):
+    """The same function as cross_attention_i2t with the products re-associated around the S (<= 64) text keys
+    (DESIGN.md section 7): per clip and head h,
+        scores_h = LN(a) . M_h + c_h      M_h = d^-1/2 Wq_h^T k_h^T  [C, S],  c_h = d^-1/2 bq_h k_h^T  [S]
+        out      = sum_h P_h . U_h + bp   U_h = v_h Wp[:, h]^T       [S, C]
+    i.e. two [N, C] x [C, h*S] / [N, h*S] x [h*S, C] products (h*S = 384 at the BASELINE shapes) instead of the
+    [N, C] x [C, C] query and output projections: half the FLOPs, no separate attention launch."""
+    B, N, C = a.shape
+    d = C // heads
+    kv = _lin(y, sd, prefix + "qkv_text_i2t")
+    k_t, v_t = (_heads(t, heads) for t in kv.split(C, dim=-1))                       # [B,h,S,d]
+    wq = sd[prefix + "qkv_i2t.weight"].view(heads, d, C)                              # rows of head h
+    bq = sd[prefix + "qkv_i2t.bias"].view(heads, d)
+    wp = sd[prefix + "proj_i2t.weight"].view(C, heads, d)                             # columns of head h
+    M = torch.einsum("hdc,bhsd->bhcs", wq, k_t) * d ** -0.5                           # [B,h,C,S]
+    c0 = torch.einsum("hd,bhsd->bhs", bq, k_t) * d ** -0.5                            # [B,h,S]
+    U = torch.einsum("bhsd,chd->bhsc", v_t, wp)                                       # [B,h,S,C]
+    ln = _ln(a, sd, prefix + "norm_i2t_i", 1e-5)
+    s = torch.einsum("bnc,bhcs->bhns", ln, M) + c0[:, :, None, :]
+    if y_mask is not None:
+        s = s + y_mask.reshape(B, 1, 1, -1)
+    out = torch.einsum("bhns,bhsc->bnc", torch.softmax(s, dim=-1), U) + sd[prefix + "proj_i2t.bias"]
+    return a + sd[prefix + "alpha_i2t"] * out
+
+
+def cross_attention_t2i_reassociated(hq, video, sd, prefix, heads):
+    """_bert_attention(hq, video, None, ...) (the text->video cross-attention, roberta.py:470-486) re-associated
+    around the S text queries: per clip and head h,
+        scores_h = Q'_h . x^T          Q'_h = d^-1/2 q_h Wk_h  [S, C]   (q_h . bk_h is constant over keys: softmax drops it)
+        ctx_h    = (P_h . x) Wv_h^T + bv_h                              (rows of P_h sum to 1)
+    i.e. [h*S, C] x [C, N] and [h*S, N] x [N, C] products instead of the [N, C] x [C, 2C] key / value projection of
+    every video token: half the FLOPs and no K / V tensors in HBM."""
+    B, S, C = hq.shape
+    d = C // heads
+    q = _heads(_lin(hq, sd, prefix + "self.query"), heads)                            # [B,h,S,d]
+    wk = sd[prefix + "self.key.weight"].view(heads, d, -1)                            # [h,d,Cv]
+    wv = sd[prefix + "self.value.weight"].view(heads, d, -1)
+    bv = sd[prefix + "self.value.bias"].view(heads, d)
+    qp = torch.einsum("bhsd,hdc->bhsc", q, wk) / math.sqrt(d)                         # [B,h,S,Cv]
+    p = torch.softmax(torch.einsum("bhsc,bnc->bhsn", qp, video), dim=-1)
+    z = torch.einsum("bhsn,bnc->bhsc", p, video)                                      # [B,h,S,Cv]
+    ctx = torch.einsum("bhsc,hdc->bhsd", z, wv) + bv[None, :, None, :]
+    return _lin(_merge(ctx), sd, prefix + "output.dense")
+
+
 def space_time_block(x, sd, prefix, heads, T, Nf, y=None, y_mask=None, eps=1e-5):
     """SpaceTimeBlock.forward (video_transformer.py:214-228).  Note the space
     residual is added to the block *input* x, not to x+time (:218-222)."""

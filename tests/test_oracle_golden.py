@@ -134,3 +134,35 @@ def test_live_differential_vs_reference():
     r = subprocess.run([sys.executable, "-m", "oracle.live_diff"], cwd=root, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "live differential vs reference ok" in r.stdout
+
+
+def test_reassociated_cross_attention_is_exact():
+    """both gated cross-attentions evaluated around the S text tokens (no [N, C] x [C, C] query /
+    key / value / output projections) equal the reference formulation -- values and gradients -- in fp32."""
+    C, h, T, Nf, S, B = 128, 2, 2, 4, 8, 3
+    shapes = O.key_shapes(C=C, heads=h, depth=7, n_fuse=1, T=T, img=32, patch=16, vocab=64, proj=64)
+    base = O.seeded_state(shapes, seed=4)
+    g = torch.Generator().manual_seed(8)
+    a0 = torch.randn(B, 1 + T * Nf, C, generator=g)
+    y0 = torch.randn(B, S, C, generator=g)
+    am = torch.ones(B, S, dtype=torch.int64)
+    am[1, 5:] = 0
+    am[2, 3:] = 0
+    m = O.extended_mask(am)
+    vp, tp = "video_model.blocks.6.attn.", "text_model.encoder.layer.6.crossattention_t2i."
+    outs = []
+    for f_i2t, f_t2i in ((O.cross_attention_i2t, lambda hq, v, sd: O._bert_attention(hq, v, None, sd, tp, h)),
+                         (O.cross_attention_i2t_reassociated, lambda hq, v, sd: O.cross_attention_t2i_reassociated(hq, v, sd, tp, h))):
+        sd = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+        a, y = a0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+        o1 = f_i2t(a, y, m, sd, vp, h)
+        o2 = f_t2i(y, a, sd)
+        (o1.square().sum() + o2.square().sum()).backward()
+        keys = [k for k in sd if (k.startswith(vp) or k.startswith(tp)) and sd[k].grad is not None]
+        outs.append((o1.detach(), o2.detach(), a.grad, y.grad, {k: sd[k].grad for k in keys}))
+    (r1, r2, ra, ry, rg), (n1, n2, na, ny, ng) = outs
+    _close(n1, r1, 1e-5), _close(n2, r2, 1e-5), _close(na, ra, 1e-4), _close(ny, ry, 1e-4)
+    # the key bias of the text->video attention has an analytically zero gradient: the re-associated form never reads it
+    assert set(rg) - set(ng) <= {tp + "self.key.bias"} and len(ng) >= 12
+    for k in ng:
+        _close(ng[k], rg[k], 1e-4)
