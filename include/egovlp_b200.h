@@ -134,6 +134,11 @@ typedef struct egv_attn_args {
   void* workspace; int64_t workspace_bytes;
 } egv_attn_args;
 int64_t egv_attention_workspace_bytes(const egv_attn_args* a);
+/* Threading: the entry points are stream-ordered and may be issued on several streams concurrently, with ONE exception:
+ * single-query problems (Lq == 1 over all heads: the CLS query of the divided attention, video_transformer.py:134-150)
+ * use library-owned scratch (key-split partials; a self-zeroing fp32 dq accumulator and per-clip tickets that the last
+ * CTA of each clip resets) -- issue those from one stream at a time.  The scratch grows on first use: run every shape once
+ * before capturing a CUDA graph (trainer.PretrainStep.capture does). */
 int egv_attention_fwd(const egv_attn_args* a, egv_stream_t stream);
 int egv_attention_bwd(const egv_attn_args* a, egv_stream_t stream);
 /* fused tiny-group kernels (time attention; csrc/attention_tiny.cu): bit 0 = forward, bit 1 = backward.  Default 3
