@@ -502,3 +502,28 @@ def test_optimizer_groups_and_schedule_match_reference(golden_dir, fake_kernels)
             opt.step_count += 1
     finally:
         weights.cache().arena = None
+
+
+def test_dual_encoder_only_forward_egonce_task(golden_dir, fake_kernels):
+    """BASELINE cfg 2 shape of the API: forward(task_names='EgoNCE') = the EgoNCE dual-encoder pass alone (fusion unused);
+    loss / similarities equal the reference golden's EgoNCE term, gradients reach both towers and no fusion parameter."""
+    fx, c, shapes, sd, data, plan = _golden(golden_dir)
+    model = build_tiny(c)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    args = types.SimpleNamespace(world_size=1, rank=0)
+    batch = {"video": data["video"], "text": {"input_ids": data["input_ids"], "attention_mask": data["attention_mask"]}}
+    loss, ld, ret = model(batch, data["noun_vec"], data["verb_vec"], lambda t, n, a: t, 1, args, {"loss": {"type": "EgoNCE"}},
+                          EgoNCE(), 0, task_names="EgoNCE")
+    assert set(ld) == {"EgoNCE", "loss_total"} and abs(float(loss) - float(fx["EgoNCE"])) <= 2e-2 * abs(float(fx["EgoNCE"]))
+    assert (ret["sim_v2t"] - fx["sim_v2t"]).abs().max().item() <= 1.5e-2
+    loss.backward()
+    named = dict(model.named_parameters())
+    assert named["video_model.blocks.0.attn.qkv.weight"].grad is not None
+    assert named["text_model.encoder.layer.0.attention.self.query.weight"].grad is not None
+    for n, p in named.items():
+        if "i2t" in n or "t2i" in n or n.startswith(("mlm_score", "itm_score", "cross_modal")):
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+    with pytest.raises(NotImplementedError):       # MLM / ITM need the EgoNCE branch's similarities (model.py:420,443)
+        model(batch, data["noun_vec"], data["verb_vec"], lambda t, n, a: t, 1, args, {"loss": {"type": "EgoNCE"}},
+              EgoNCE(), 0, task_names="MLM_ITM")
