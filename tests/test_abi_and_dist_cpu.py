@@ -142,3 +142,82 @@ def test_two_rank_host_logic_gloo():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _ddp_worker(rank, world, port, q, golden_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from egovlpv2_b200 import functional as Fn
+        from egovlpv2_b200 import lib as L
+        from egovlpv2_b200.comm import NcclAllGather
+        from egovlpv2_b200.model.loss import EgoNCE
+        from oracle import egovlp_oracle as O
+        from tests.fake_kernels import FakeKernels
+        from tests.test_model_cpu import _golden, build_tiny
+        L.set_kernels(FakeKernels())
+        Fn.BF16 = torch.float32
+        torch.set_num_threads(2)
+        fx, c, shapes, sd, _, _ = _golden(golden_dir)
+        Bl = 2
+        G = Bl * world
+        full = O.synthetic_batch(G, c["T"], c["img"], c["S"], seed=31)
+        plan = dict(labels=torch.tensor([1., 0.] * world), swap_video=torch.tensor([False, True, False, False][:G]),
+                    neg_idx=torch.tensor([0, 2, 0, 1][:G]))
+
+        def run(model, batch, pl, gather, args, n):
+            inner = model.module if hasattr(model, "module") else model
+            inner.itm_plan = pl
+            data = {"video": batch["video"], "text": {"input_ids": batch["input_ids"], "attention_mask": batch["attention_mask"]},
+                    "text_mlm_ids": batch["text_mlm_ids"], "text_mlm_labels": batch["text_mlm_labels"]}
+            # the call of trainer_egoclip.py:145, through the DDP wrapper
+            loss, ld, _ = model(data, batch["noun_vec"], batch["verb_vec"], gather, n, args, {"loss": {"type": "EgoNCE"}},
+                                EgoNCE(), 0, task_names="EgoNCE_MLM_ITM")
+            loss.backward()
+            return float(loss.detach()), {k: p.grad.clone() for k, p in inner.named_parameters() if p.grad is not None}
+
+        model = build_tiny(c)
+        model.load_state_dict(sd, strict=False)
+        model.eval()
+        ddp = torch.nn.parallel.DistributedDataParallel(model, static_graph=True)      # base_trainer.py:268-269
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        loc = {k: v[sl].contiguous() for k, v in full.items()}
+        loss_r, g_r = run(ddp, loc, {k: v[sl] for k, v in plan.items()}, NcclAllGather(),
+                          types.SimpleNamespace(world_size=world, rank=rank), world)
+        # single-process run of the concatenated batch on a fresh copy (no cross-rank reduction of the loss sums)
+        ref = build_tiny(c)
+        ref.load_state_dict(sd, strict=False)
+        ref.eval()
+        ref._global_mean = lambda ls, cnt: ls.reshape(()) / cnt.reshape(()).clamp_min(1.0)
+        loss_f, g_f = run(ref, full, plan, lambda t, n=None, a=None: t, types.SimpleNamespace(world_size=1, rank=0), 1)
+        assert abs(loss_r - loss_f) <= 1e-4 * max(1.0, abs(loss_f)), (loss_r, loss_f)
+        gmax = max(g.norm().item() for g in g_f.values())
+        worst = 0.0
+        for k, gf in g_f.items():
+            # DDP averages over ranks: mean_r(local gradient) == full-batch gradient / world
+            err = (g_r[k] * world - gf).norm().item() / max(gf.norm().item(), 1e-3 * gmax)
+            worst = max(worst, err)
+            assert err <= 2e-3, (k, err)
+        q.put((rank, "ok %.1e" % worst))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_ddp_static_graph_training_call(golden_dir):
+    """The reference's training configuration on CPU: DistributedDataParallel(static_graph=True) (base_trainer.py:268-269)
+    around the drop-in FrozenInTime, the trainer's call signature (trainer_egoclip.py:145), an all_gather callable, two
+    gloo ranks: DDP-averaged gradients x world == gradients of the concatenated batch in one process."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q, golden_dir)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1].startswith("ok") for r in res), res
