@@ -527,3 +527,44 @@ def test_dual_encoder_only_forward_egonce_task(golden_dir, fake_kernels):
     with pytest.raises(NotImplementedError):       # MLM / ITM need the EgoNCE branch's similarities (model.py:420,443)
         model(batch, data["noun_vec"], data["verb_vec"], lambda t, n, a: t, 1, args, {"loss": {"type": "EgoNCE"}},
               EgoNCE(), 0, task_names="MLM_ITM")
+
+
+def test_itm_hard_negative_sampling_rules():
+    """model.py:426-468 with the random plan (the path the bench and a real run take): half the rows keep their pair;
+    a label-0 row swaps EITHER its clip or its caption for a row drawn from softmax(sim / temp) with the EgoNCE positives
+    (mask_bool) zeroed -- never a positive, never itself, and with a peaked similarity always the hard negative."""
+    torch.manual_seed(0)
+    B = 8
+    video = torch.arange(B).float().reshape(B, 1, 1, 1, 1)
+    ids = torch.arange(B).reshape(B, 1).long() + 100
+    data = {"video": video, "text": {"input_ids": ids, "attention_mask": torch.ones_like(ids)}}
+    mask = torch.eye(B, dtype=torch.bool)
+    mask[0, 1] = mask[1, 0] = True                                  # clips 0 and 1 share noun+verb: EgoNCE positives
+    sim = torch.full((B, B), -1.0)
+    hard = (torch.arange(B) + 3) % B
+    sim[torch.arange(B), hard] = 0.9     # row i peaks at column i+3; column i therefore peaks at row i-3 (model.py:443-444:
+    easy = (torch.arange(B) - 3) % B     # the caption swap draws from sim[i, :], the clip swap from sim.t()[i, :] = sim[:, i])
+    sim.fill_diagonal_(1.0)
+    sim[0, 1] = sim[1, 0] = 0.99                                    # the positive pair looks most similar of all
+    dummy = types.SimpleNamespace(itm_plan=None)
+    args = types.SimpleNamespace(world_size=1, rank=0)
+    seen_video_swap = seen_text_swap = 0
+    for _ in range(20):
+        d_itm, labels = M.FrozenInTime._build_itm_batch(dummy, data, sim, mask, 0.05, 0, lambda t, n, a: t, 1, args)
+        assert labels.sum().item() == B // 2 and labels.numel() == B
+        v = d_itm["video"].reshape(B).long()
+        t = d_itm["text"]["input_ids"].reshape(B) - 100
+        own = torch.arange(B)
+        pos = labels == 1
+        assert torch.equal(v[pos], own[pos]) and torch.equal(t[pos], own[pos])
+        neg_rows = own[~pos]
+        for i in neg_rows.tolist():
+            swapped_v, swapped_t = v[i].item() != i, t[i].item() != i
+            assert swapped_v != swapped_t                       # exactly one side is replaced
+            j = v[i].item() if swapped_v else t[i].item()
+            assert not mask[i, j] and j == (easy[i].item() if swapped_v else hard[i].item())
+            seen_video_swap += swapped_v
+            seen_text_swap += swapped_t
+    assert seen_video_swap > 10 and seen_text_swap > 10            # both branches of the coin flip (model.py:459)
+    # inputs are not mutated (the reference deep-copies the batch, model.py:449)
+    assert torch.equal(data["video"].reshape(B), torch.arange(B).float())
