@@ -281,3 +281,21 @@ def test_video_tokens_from_uint8_frames(sd):
     host2 = (frames.float() / 255 - 0.5) / torch.tensor((0.25, 0.5, 1.0)).view(1, 1, 3, 1, 1)
     t3, _ = Fn.video_tokens_fwd(K, host2, p, w, sd["cls_token"], PATCH)
     assert torch.equal(t2, t3)
+
+
+def test_fused_blocks_at_large_width(monkeypatch):
+    """BASELINE cfg 5 widths (C = 1024, 16 heads of 64; SURVEY.md Q12: parity pinned at block level): the hand-derived
+    forward / backward of the fused video block and the fused text layer are width-agnostic."""
+    import tests.test_functional_cpu as me
+    monkeypatch.setattr(me, "C", 1024)
+    monkeypatch.setattr(me, "HEADS", 16)
+    shapes = O.key_shapes(C=1024, heads=16, depth=7, n_fuse=1, T=T, img=IMG, patch=PATCH, vocab=97, proj=256)
+    keep = {k: v for k, v in shapes.items() if "blocks.6." in k or "layer.6." in k}
+    sd_l = O.seeded_state(keep, seed=5)
+    old = Fn.BF16
+    Fn.BF16 = torch.float32
+    try:
+        test_video_block(sd_l, "exact", True)
+        test_text_layer(sd_l, "exact", True)
+    finally:
+        Fn.BF16 = old
