@@ -221,3 +221,23 @@ def test_two_rank_ddp_static_graph_training_call(golden_dir):
     for p in procs:
         p.join(timeout=60)
     assert all(r[1].startswith("ok") for r in res), res
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU port of the path on the host cores) prints ONE JSON line with the contract's
+    keys: impl, metric / unit of our arm, cpu_baseline{kind, cores, sample, value == the line's}, e2e with zero copy bytes."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "1",
+                        "--frames", "4"], cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "pretrain_clips_per_sec" and d["unit"] == "clips/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
