@@ -568,3 +568,40 @@ def test_itm_hard_negative_sampling_rules():
     assert seen_video_swap > 10 and seen_text_swap > 10            # both branches of the coin flip (model.py:459)
     # inputs are not mutated (the reference deep-copies the batch, model.py:449)
     assert torch.equal(data["video"].reshape(B), torch.arange(B).float())
+
+
+def test_load_checkpoint_constructor_path(golden_dir, fake_kernels, tmp_path):
+    """model.py:179-184: `load_checkpoint=` reads {'state_dict': ...} saved from a DDP-wrapped reference model ('module.'
+    prefix, utils/util.py:31-57), inflates a 2-frame temporal embedding to the current frame count (model.py:532-563)
+    and loads with strict=False; a checkpoint saved by the drop-in loads back bit for bit."""
+    fx, c, shapes, sd, data, plan = _golden(golden_dir)
+    ck = tmp_path / "ref_style.pth"
+    torch.save({"state_dict": {"module." + k: v for k, v in sd.items()}, "epoch": 3}, ck)
+    c4 = dict(c, T=4)
+    cfg = dict(M.DEFAULT_CONFIG, input_image_embed_size=c["C"], input_text_embed_size=c["C"], hidden_size=c["C"],
+               num_heads=c["heads"], num_layers=c["depth"], num_fuse_block=c["n_fuse"], vocab_size=c["vocab"])
+
+    def build(T, load):
+        return M.FrozenInTime(
+            video_params=dict(model="SpaceTimeTransformer", arch_config="base_patch16_224", num_frames=T, pretrained=True,
+                              time_init="zeros", img_size=c["img"], embed_dim=c["C"], depth=c["depth"], num_heads=c["heads"]),
+            text_params=dict(model="roberta-base", pretrained=True, input="text",
+                             config=dict(hidden_size=c["C"], num_hidden_layers=c["depth"], num_attention_heads=c["heads"],
+                                         intermediate_size=4 * c["C"])),
+            projection_dim=c["proj"], config=cfg, load_checkpoint=str(load), embed_dim=c["C"])
+
+    same = build(c["T"], ck)
+    got = same.state_dict()
+    for k, v in sd.items():
+        assert torch.equal(got[k], v), k
+    more = build(c4["T"], ck)                                   # 2-frame checkpoint into a 4-frame model
+    te = more.state_dict()["video_model.temporal_embed"]
+    assert te.shape == (1, 4, c["C"])
+    assert torch.allclose(te[0, 0], sd["video_model.temporal_embed"][0, 0], atol=1e-6)
+    assert torch.allclose(te[0, -1], sd["video_model.temporal_embed"][0, -1], atol=1e-6)
+    assert torch.equal(more.state_dict()["video_model.blocks.3.mlp.fc1.weight"], sd["video_model.blocks.3.mlp.fc1.weight"])
+    ck2 = tmp_path / "dropin.pth"
+    torch.save({"state_dict": same.state_dict()}, ck2)
+    again = build(c["T"], ck2)
+    for k, v in same.state_dict().items():
+        assert torch.equal(again.state_dict()[k], v), k
