@@ -605,3 +605,51 @@ def test_load_checkpoint_constructor_path(golden_dir, fake_kernels, tmp_path):
     again = build(c["T"], ck2)
     for k, v in same.state_dict().items():
         assert torch.equal(again.state_dict()[k], v), k
+
+
+def test_training_call_under_autocast_and_checkpoint_wrapper(golden_dir, fake_kernels):
+    """SURVEY.md 8(b) 'Ownership / dtype': the reference drives the model under torch.cuda.amp.autocast() and downstream
+    callers wrap blocks in torch.utils.checkpoint themselves.  The drop-in's precision policy lives inside its kernels, so
+    an enclosing autocast context must not change results, and a block survives being checkpointed by the caller."""
+    import torch.utils.checkpoint as cp
+
+    class DeviceLikeKernels(FakeKernels):
+        """device kernels do not see the caller's autocast state; the torch restatement must not either"""
+
+        def __getattribute__(self, name):
+            attr = super().__getattribute__(name)
+            if name.startswith("_") or not callable(attr):
+                return attr
+
+            def call(*a, **kw):
+                with torch.autocast("cpu", enabled=False):
+                    return attr(*a, **kw)
+            return call
+
+    L.set_kernels(DeviceLikeKernels())
+    fx, c, shapes, sd, data, plan = _golden(golden_dir)
+    model = build_tiny(c)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    loss0, ld0, _ = _step(model, data, plan)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        loss1, ld1, ret1 = _step(model, data, plan)
+    assert loss1.dtype == torch.float32 and ret1["cross_attn_mlm_logits"].dtype == torch.float32
+    for k in ld0:
+        assert abs(float(ld0[k].detach()) - float(ld1[k].detach())) <= 1e-5 * max(1.0, abs(float(ld0[k].detach()))), k
+    loss1.backward()
+    assert model.video_model.blocks[0].attn.qkv.weight.grad is not None
+    # caller-side activation checkpointing of one block (positional form, as the reference's use_checkpoint branch does)
+    blk = model.video_model.blocks[1]
+    x = torch.randn(2, 1 + c["T"] * model.patches_per_frame, c["C"], requires_grad=True)
+    es = (model.einops_from_space, model.einops_to_space, model.einops_from_time, model.einops_to_time)
+    model.zero_grad()
+    y_plain = blk(x, *es, model.patches_per_frame, c["T"])
+    y_plain.square().sum().backward()
+    g_plain, gx_plain = blk.mlp.fc1.weight.grad.clone(), x.grad.clone()
+    model.zero_grad()
+    x.grad = None
+    y_ck = cp.checkpoint(blk, x, *es, model.patches_per_frame, c["T"], use_reentrant=False)
+    y_ck.square().sum().backward()
+    assert torch.allclose(y_ck, y_plain) and torch.allclose(x.grad, gx_plain, atol=1e-6)
+    assert torch.allclose(blk.mlp.fc1.weight.grad, g_plain, atol=1e-6)
