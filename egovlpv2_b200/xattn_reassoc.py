@@ -1,0 +1,102 @@
+"""ROUND-2 PATH, NOT WIRED INTO THE MODEL YET: the core of the gated video->text cross-attention
+(video_transformer.py:155-185: q = qkv_i2t(LN(x)), softmax(q k^T + mask) v, proj_i2t) re-associated around the S text keys
+(oracle/egovlp_oracle.py::cross_attention_i2t_reassociated):
+
+    scores[b,n,h,s] = LN(x)[b,n,:] . Mt[h,b,s,:] + c0[b,s,h] + mask[b,s]     Mt = d^-1/2 k_h Wq_h        [H, B*S, C]
+    c[b,n,:]        = sum_{h,s} P[b,n,h,s] U[h,b,s,:]                        U  = v_h Wp[:,h]^T + bp/H   [H, B*S, C]
+
+i.e. the [M, C] x [C, C] query and output projections (M = B*N = 25 096 rows at the BASELINE shapes) and the 32-key
+attention launch become two [M, C] x [C, H*S] products with a 32-wide group softmax between them: half the FLOPs.
+What is on the M rows runs in FOUR fused device kernels that do not exist in libegovlp_b200.so yet (batched-per-clip
+variants of gemm_tc_kernel with softmax / softmax-backward epilogues):
+
+    K.xattn_scores_softmax(ln, Mt, c0, mask, P)     K.xattn_weighted_sum(P_or_dS, U_or_Mt, out)
+    K.xattn_dscores(dc, U, P, dS, dbias)            K.xattn_tn(P_or_dS, dc_or_ln, out)
+
+Everything on the B*S = 256 text rows uses the existing GEMM entry point on strided head views.  The sequencing and the
+hand-derived backward below are pinned against autograd through the oracle on CPU (tests/test_functional_cpu.py::
+test_reassociated_i2t_core) with the torch restatement of those four kernels (tests/fake_kernels.py); calling this module
+with the real library raises AttributeError -- there is no fallback."""
+import types
+
+import torch
+
+from . import functional as Fn
+from .lib import GEMM_NN, GEMM_NT, GEMM_TN
+
+_e = Fn._e
+
+
+def _blockdiag_rows(vec, H):
+    """[C] -> [H, C] with vec's head-h slice in row h (the query bias as a block-diagonal operand)."""
+    C = vec.numel()
+    d = C // H
+    out = vec.new_zeros(H, C)
+    for h in range(H):
+        out[h, h * d:(h + 1) * d] = vec[h * d:(h + 1) * d]
+    return out
+
+
+def i2t_core_fwd(K, ln, kv, mask, wq, bq, wp, bp, H):
+    """ln [B,N,C] operand dtype; kv [B,S,2C] operand dtype (k | v); mask [B,S] f32 additive; wq / wp [C,C] operand
+    dtype; bq / bp [C] f32.  Returns (c [B,N,C] operand dtype = proj_i2t(attention) incl. its bias, saved)."""
+    BF16, F32 = Fn.BF16, torch.float32
+    B, N, C = ln.shape
+    S = kv.shape[1]
+    d = C // H
+    sc = d ** -0.5
+    kv2 = kv.view(B * S, 2 * C)
+    Mt, U = _e(ln, (H, B * S, C), BF16), _e(ln, (H, B * S, C), BF16)
+    bp_h = (bp / H).contiguous()
+    for h in range(H):
+        kh, vh = kv2[:, h * d:(h + 1) * d], kv2[:, C + h * d:C + (h + 1) * d]
+        K.gemm(GEMM_NN, kh, wq[h * d:(h + 1) * d, :], scale=sc, out_bf16=Mt[h])
+        K.gemm(GEMM_NT, vh, wp[:, h * d:(h + 1) * d], bias=bp_h, out_bf16=U[h])
+    bq_bd = _blockdiag_rows(bq, H).to(BF16)
+    c0 = _e(ln, (B * S, H), F32)
+    K.gemm(GEMM_NT, kv2[:, :C], bq_bd, scale=sc, out_f32=c0)
+    P = _e(ln, (B, N, H, S), BF16)
+    K.xattn_scores_softmax(ln, Mt.view(H, B, S, C), c0.view(B, S, H), mask, P)
+    c = _e(ln, (B, N, C), BF16)
+    K.xattn_weighted_sum(P, U.view(H, B, S, C), c)
+    return c, types.SimpleNamespace(ln=ln, kv=kv, Mt=Mt, U=U, P=P, bq_bd=bq_bd, H=H)
+
+
+def i2t_core_bwd(K, s, dc, wq, wp):
+    """dc [B,N,C] operand dtype -> (dln [B,N,C], dkv [B,S,2C] f32, dwq [C,C], dbq [C], dwp [C,C], dbp [C])  (f32 grads)."""
+    BF16, F32 = Fn.BF16, torch.float32
+    B, N, C = dc.shape
+    H, S = s.H, s.kv.shape[1]
+    d = C // H
+    sc = d ** -0.5
+    kv2 = s.kv.view(B * S, 2 * C)
+    dS = _e(dc, (B, N, H, S), BF16)
+    dc0 = _e(dc, (B, S, H), F32)
+    K.xattn_dscores(dc, s.U.view(H, B, S, C), s.P, dS, dc0)
+    dU, dM = _e(dc, (H, B * S, C), F32), _e(dc, (H, B * S, C), F32)
+    K.xattn_tn(s.P, dc, dU.view(H, B, S, C))
+    K.xattn_tn(dS, s.ln, dM.view(H, B, S, C))
+    dln = _e(dc, (B, N, C), BF16)
+    K.xattn_weighted_sum(dS, s.Mt.view(H, B, S, C), dln)
+    dU_b, dM_b = _e(dc, dU.shape, BF16), _e(dc, dM.shape, BF16)
+    K.cast(dU, dU_b)
+    K.cast(dM, dM_b)
+    dkv = _e(dc, (B * S, 2 * C), F32)
+    dwq, dwp = _e(dc, (C, C), F32), _e(dc, (C, C), F32)
+    for h in range(H):
+        hs = slice(h * d, (h + 1) * d)
+        kh, vh = kv2[:, hs], kv2[:, C + h * d:C + (h + 1) * d]
+        K.gemm(GEMM_NT, dM_b[h], wq[hs, :], scale=sc, out_f32=dkv[:, hs])                     # dk_h  = d^-1/2 dM_h Wq_h^T
+        K.gemm(GEMM_TN, kh, dM_b[h], scale=sc, out_f32=dwq[hs, :])                             # dWq_h = d^-1/2 k_h^T dM_h
+        K.gemm(GEMM_NN, dU_b[h], wp[:, hs], out_f32=dkv[:, C + h * d:C + (h + 1) * d])         # dv_h  = dU_h Wp[:,h]
+        K.gemm(GEMM_TN, dU_b[h], vh, out_f32=dwp[:, hs])                                       # dWp[:,h] = dU_h^T v_h
+    # the query bias: scores += d^-1/2 (bq_h . k_h)  ->  dk += d^-1/2 dc0 (x) bq ; dbq_h = d^-1/2 k_h^T dc0[:, h]
+    dc0_b = _e(dc, (B * S, H), BF16)
+    K.cast(dc0.view(B * S, H), dc0_b)
+    K.gemm(GEMM_NN, dc0_b, s.bq_bd, scale=sc, out_f32=dkv[:, :C], accumulate=True)
+    dbq_all = _e(dc, (C, H), F32)
+    K.gemm(GEMM_TN, kv2[:, :C], dc0_b, scale=sc, out_f32=dbq_all)
+    dbq = torch.cat([dbq_all[h * d:(h + 1) * d, h] for h in range(H)])
+    dbp = _e(dc, (C,), F32)
+    K.colsum(dU_b.view(H * B * S, C), dbp, scale=1.0 / H)
+    return dln, dkv.view(B, S, 2 * C), dwq, dbq, dwp, dbp

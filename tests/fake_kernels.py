@@ -387,6 +387,32 @@ class FakeKernels:
         if dv is not None:
             dv.copy_(vv.grad[grad_row0:grad_row0 + grad_rows])
 
+    # ------------------------------------------------------------------ re-associated cross-attention (round-2 kernels)
+    def xattn_scores_softmax(self, ln, Mt, c0, mask, P):
+        """P[b,n,h,:] = softmax_s(ln[b,n,:] . Mt[h,b,s,:] + c0[b,s,h] + mask[b,s])"""
+        self._launches += 1
+        s = torch.einsum("bnc,hbsc->bnhs", ln.float(), Mt.float()) + c0.float().permute(0, 2, 1)[:, None] + mask.float()[:, None, None, :]
+        P.copy_(torch.softmax(s, dim=-1))
+
+    def xattn_weighted_sum(self, P, U, out):
+        """out[b,n,:] = sum_{h,s} P[b,n,h,s] U[h,b,s,:]"""
+        self._launches += 1
+        out.copy_(torch.einsum("bnhs,hbsc->bnc", P.float(), U.float()))
+
+    def xattn_dscores(self, dc, U, P, dS, dbias):
+        """dP = dc . U^T; dS = P * (dP - sum_s dP * P); dbias[b,s,h] = sum_n dS[b,n,h,s]"""
+        self._launches += 1
+        p = P.float()
+        dP = torch.einsum("bnc,hbsc->bnhs", dc.float(), U.float())
+        ds = p * (dP - (dP * p).sum(-1, keepdim=True))
+        dS.copy_(ds)
+        dbias.copy_(ds.sum(1).permute(0, 2, 1))
+
+    def xattn_tn(self, X, Y, out):
+        """out[h,b,s,:] = sum_n X[b,n,h,s] Y[b,n,:]"""
+        self._launches += 1
+        out.copy_(torch.einsum("bnhs,bnc->hbsc", X.float(), Y.float()))
+
     # ------------------------------------------------------------------ optimiser
     def adamw(self, p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, hyper_dev=None):
         self._launches += 1

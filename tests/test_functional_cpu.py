@@ -299,3 +299,37 @@ def test_fused_blocks_at_large_width(monkeypatch):
         test_text_layer(sd_l, "exact", True)
     finally:
         Fn.BF16 = old
+
+
+def test_reassociated_i2t_core(sd, mode):
+    """egovlpv2_b200/xattn_reassoc.py (round-2 path): the hand-derived forward / backward of the re-associated
+    video->text cross-attention core == autograd through the reference formulation (q projection, 32-key masked softmax
+    attention, output projection: video_transformer.py:165-183), for every input and parameter gradient."""
+    from egovlpv2_b200 import xattn_reassoc as XR
+    K = FakeKernels()
+    prefix = "video_model.blocks.6.attn."
+    d = C // HEADS
+    g = torch.Generator().manual_seed(17)
+    ln = torch.randn(B, N, C, generator=g)
+    kv = torch.randn(B, S, 2 * C, generator=g)
+    am, mask = mask_bias([S, 5, 3])
+    dc = torch.randn(B, N, C, generator=g)
+    wq, bq = sd[prefix + "qkv_i2t.weight"], sd[prefix + "qkv_i2t.bias"]
+    wp, bp = sd[prefix + "proj_i2t.weight"], sd[prefix + "proj_i2t.bias"]
+    cast = lambda t: t.to(Fn.BF16)  # noqa: E731
+    c, saved = XR.i2t_core_fwd(K, cast(ln), cast(kv), mask, cast(wq), bq, cast(wp), bp, HEADS)
+    dln, dkv, dwq, dbq, dwp, dbp = XR.i2t_core_bwd(K, saved, cast(dc), cast(wq), cast(wp))
+    # reference formulation under autograd
+    r = {k: v.clone().requires_grad_(True) for k, v in dict(ln=ln, kv=kv, wq=wq, bq=bq, wp=wp, bp=bp).items()}
+    q = O._heads(torch.nn.functional.linear(r["ln"], r["wq"], r["bq"]), HEADS) * d ** -0.5
+    k_t, v_t = (O._heads(t, HEADS) for t in r["kv"].split(C, dim=-1))
+    sc = q @ k_t.transpose(-1, -2) + mask.reshape(B, 1, 1, S)
+    ref = torch.nn.functional.linear(O._merge(torch.softmax(sc, dim=-1) @ v_t), r["wp"], r["bp"])
+    ref.backward(dc)
+    assert rel(c, ref) <= tol(mode), rel(c, ref)
+    for name, got in (("ln", dln), ("kv", dkv), ("wq", dwq), ("bq", dbq), ("wp", dwp), ("bp", dbp)):
+        e = rel(got.reshape(-1), r[name].grad.reshape(-1))
+        assert e <= tol(mode, True), (name, e)
+    # the real library does not have the four fused kernels yet: the module must fail loudly, not fall back
+    from egovlpv2_b200 import lib as L
+    assert not hasattr(L.Kernels, "xattn_scores_softmax")
