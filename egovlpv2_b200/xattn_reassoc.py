@@ -7,6 +7,7 @@
 
 i.e. the [M, C] x [C, C] query and output projections (M = B*N = 25 096 rows at the BASELINE shapes) and the 32-key
 attention launch become two [M, C] x [C, H*S] products with a 32-wide group softmax between them: half the FLOPs.
+(The text->video direction, re-associated the same way, follows below.)
 What is on the M rows runs in FOUR fused device kernels that do not exist in libegovlp_b200.so yet (batched-per-clip
 variants of gemm_tc_kernel with softmax / softmax-backward epilogues):
 
@@ -100,3 +101,63 @@ def i2t_core_bwd(K, s, dc, wq, wp):
     dbp = _e(dc, (C,), F32)
     K.colsum(dU_b.view(H * B * S, C), dbp, scale=1.0 / H)
     return dln, dkv.view(B, S, 2 * C), dwq, dbq, dwp, dbp
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# text -> video direction (roberta.py:470-486: q from the text, k / v = Linear(x) of all N video tokens, no mask)
+#
+#     scores[b,h,s,n] = Qp[h,b,s,:] . x[b,n,:]            Qp = d^-1/2 q_h Wk_h   [H, B*S, Cv]   (q_h . bk_h drops out of softmax)
+#     ctx_h           = (P_h x) Wv_h^T + bv_h             Z  = P x               [H, B*S, Cv]
+#
+# The key / value projection of the video tokens (2 * M * Cv * 2C FLOPs, two [M, C] tensors written) disappears; what is
+# left on the M = B*N video rows is ONE flash-style kernel per direction with K = V = x and "head dim" Cv, still to be written:
+#     K.xattn_t2i_flash(Qp, x, Z, lse)          K.xattn_t2i_flash_bwd(dZ, Qp, x, Z, lse, dQp, dx)
+def t2i_core_fwd(K, q, x, wk, wv, bv, H):
+    """q [B,S,C] operand dtype (query projection of the text, bias included); x [B,N,Cv] operand dtype (video stream);
+    wk / wv [C,Cv] operand dtype; bv [C] f32.  Returns (ctx [B,S,C] f32 = merged heads before output.dense, saved)."""
+    BF16, F32 = Fn.BF16, torch.float32
+    B, S, C = q.shape
+    Cv = x.shape[2]
+    d = C // H
+    sc = d ** -0.5
+    q2 = q.view(B * S, C)
+    Qp = _e(q, (H, B * S, Cv), BF16)
+    for h in range(H):
+        K.gemm(GEMM_NN, q2[:, h * d:(h + 1) * d], wk[h * d:(h + 1) * d, :], scale=sc, out_bf16=Qp[h])
+    Z, lse = _e(q, (H, B * S, Cv), BF16), _e(q, (H, B * S), F32)
+    K.xattn_t2i_flash(Qp.view(H, B, S, Cv), x, Z.view(H, B, S, Cv), lse.view(H, B, S))
+    ctx = _e(q, (B * S, C), F32)
+    for h in range(H):
+        hs = slice(h * d, (h + 1) * d)
+        K.gemm(GEMM_NT, Z[h], wv[hs, :], bias=bv[hs], out_f32=ctx[:, hs])
+    return ctx.view(B, S, C), types.SimpleNamespace(q=q, x=x, Qp=Qp, Z=Z, lse=lse, H=H)
+
+
+def t2i_core_bwd(K, s, dctx, wk, wv):
+    """dctx [B,S,C] operand dtype -> (dq [B,S,C] f32, dx [B,N,Cv] f32, dwk [C,Cv], dwv [C,Cv], dbv [C]); the key bias has
+    an analytically zero gradient."""
+    BF16, F32 = Fn.BF16, torch.float32
+    B, S, C = dctx.shape
+    H, Cv = s.H, s.x.shape[2]
+    d = C // H
+    sc = d ** -0.5
+    g2, q2 = dctx.view(B * S, C), s.q.view(B * S, C)
+    dZ = _e(dctx, (H, B * S, Cv), BF16)
+    dwk, dwv = _e(dctx, (C, Cv), F32), _e(dctx, (C, Cv), F32)
+    for h in range(H):
+        hs = slice(h * d, (h + 1) * d)
+        K.gemm(GEMM_NN, g2[:, hs], wv[hs, :], out_bf16=dZ[h])                                   # dZ_h  = dctx_h Wv_h
+        K.gemm(GEMM_TN, g2[:, hs], s.Z[h], out_f32=dwv[hs, :])                                   # dWv_h = dctx_h^T Z_h
+    dbv = _e(dctx, (C,), F32)
+    K.colsum(g2, dbv)
+    dQp, dx = _e(dctx, (H, B * S, Cv), F32), _e(dctx, s.x.shape, F32)
+    K.xattn_t2i_flash_bwd(dZ.view(H, B, S, Cv), s.Qp.view(H, B, S, Cv), s.x, s.Z.view(H, B, S, Cv), s.lse.view(H, B, S),
+                          dQp.view(H, B, S, Cv), dx)
+    dQp_b = _e(dctx, dQp.shape, BF16)
+    K.cast(dQp, dQp_b)
+    dq = _e(dctx, (B * S, C), F32)
+    for h in range(H):
+        hs = slice(h * d, (h + 1) * d)
+        K.gemm(GEMM_NT, dQp_b[h], wk[hs, :], scale=sc, out_f32=dq[:, hs])                        # dq_h  = d^-1/2 dQp_h Wk_h^T
+        K.gemm(GEMM_TN, q2[:, hs], dQp_b[h], scale=sc, out_f32=dwk[hs, :])                       # dWk_h = d^-1/2 q_h^T dQp_h
+    return dq.view(B, S, C), dx, dwk, dwv, dbv

@@ -413,6 +413,23 @@ class FakeKernels:
         self._launches += 1
         out.copy_(torch.einsum("bnhs,bnc->hbsc", X.float(), Y.float()))
 
+    def xattn_t2i_flash(self, Qp, x, Z, lse):
+        """P[h,b,s,:] = softmax_n(Qp[h,b,s,:] . x[b,n,:]); Z = P x; lse = logsumexp of the scores"""
+        self._launches += 1
+        sc = torch.einsum("hbsc,bnc->hbsn", Qp.float(), x.float())
+        lse.copy_(torch.logsumexp(sc, dim=-1))
+        Z.copy_(torch.einsum("hbsn,bnc->hbsc", torch.softmax(sc, dim=-1), x.float()))
+
+    def xattn_t2i_flash_bwd(self, dZ, Qp, x, Z, lse, dQp, dx):
+        """dP = dZ x^T; dS = P * (dP - rowsum(dZ * Z)); dQp = dS x; dx = P^T dZ + dS^T Qp"""
+        self._launches += 1
+        xf, qf, dz = x.float(), Qp.float(), dZ.float()
+        p = torch.exp(torch.einsum("hbsc,bnc->hbsn", qf, xf) - lse.float()[..., None])
+        dP = torch.einsum("hbsc,bnc->hbsn", dz, xf)
+        dS = p * (dP - (dz * Z.float()).sum(-1, keepdim=True))
+        dQp.copy_(torch.einsum("hbsn,bnc->hbsc", dS, xf))
+        dx.copy_(torch.einsum("hbsn,hbsc->bnc", p, dz) + torch.einsum("hbsn,hbsc->bnc", dS, qf))
+
     # ------------------------------------------------------------------ optimiser
     def adamw(self, p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, hyper_dev=None):
         self._launches += 1

@@ -333,3 +333,32 @@ def test_reassociated_i2t_core(sd, mode):
     # the real library does not have the four fused kernels yet: the module must fail loudly, not fall back
     from egovlpv2_b200 import lib as L
     assert not hasattr(L.Kernels, "xattn_scores_softmax")
+
+
+def test_reassociated_t2i_core(sd, mode):
+    """xattn_reassoc.t2i_core_*: text queries over all N video tokens without projecting the tokens to keys / values
+    == autograd through the reference formulation (roberta.py:257-327 with encoder_hidden_states = video, no mask)."""
+    from egovlpv2_b200 import xattn_reassoc as XR
+    K = FakeKernels()
+    prefix = "text_model.encoder.layer.6.crossattention_t2i.self."
+    d = C // HEADS
+    g = torch.Generator().manual_seed(23)
+    q = torch.randn(B, S, C, generator=g)
+    x = torch.randn(B, N, C, generator=g)
+    dctx = torch.randn(B, S, C, generator=g)
+    wk, bk = sd[prefix + "key.weight"], sd[prefix + "key.bias"]
+    wv, bv = sd[prefix + "value.weight"], sd[prefix + "value.bias"]
+    cast = lambda t: t.to(Fn.BF16)  # noqa: E731
+    ctx, saved = XR.t2i_core_fwd(K, cast(q), cast(x), cast(wk), cast(wv), bv, HEADS)
+    dq, dx, dwk, dwv, dbv = XR.t2i_core_bwd(K, saved, cast(dctx), cast(wk), cast(wv))
+    r = {k: v.clone().requires_grad_(True) for k, v in dict(q=q, x=x, wk=wk, bk=bk, wv=wv, bv=bv).items()}
+    lin = torch.nn.functional.linear
+    qh = O._heads(r["q"], HEADS)
+    kh, vh = O._heads(lin(r["x"], r["wk"], r["bk"]), HEADS), O._heads(lin(r["x"], r["wv"], r["bv"]), HEADS)
+    ref = O._merge(torch.softmax(qh @ kh.transpose(-1, -2) / d ** 0.5, dim=-1) @ vh)
+    ref.backward(dctx)
+    assert rel(ctx, ref) <= tol(mode), rel(ctx, ref)
+    for name, got in (("q", dq), ("x", dx), ("wk", dwk), ("wv", dwv), ("bv", dbv)):
+        e = rel(got.reshape(-1), r[name].grad.reshape(-1))
+        assert e <= tol(mode, True), (name, e)
+    assert r["bk"].grad.abs().max().item() <= 1e-5          # the key bias is softmax-invariant: nothing to back-propagate
