@@ -130,8 +130,15 @@ def test_live_differential_vs_reference():
     Runs in a subprocess: the reference shim patches process-wide state."""
     import subprocess
     import sys
+    import socket
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "oracle.live_diff"], cwd=root, capture_output=True, text=True, timeout=900)
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))          # a free rendezvous port for the shim's 1-rank gloo group
+    port = sock.getsockname()[1]
+    sock.close()
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    r = subprocess.run([sys.executable, "-m", "oracle.live_diff"], cwd=root, capture_output=True, text=True, timeout=900,
+                       env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "live differential vs reference ok" in r.stdout
 
