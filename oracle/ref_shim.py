@@ -40,11 +40,16 @@ def available():
     return os.path.isdir(REF_ROOT)
 
 
-def load(use_checkpoint=False):
-    """Import the reference model modules; returns a namespace with mm/vt/rb/heads/loss."""
+def load(use_checkpoint=False, root=None):
+    """Import the reference model modules; returns a namespace with mm/vt/rb/heads/loss.
+    `root`: another directory holding the same unmodified files (tools/install_ref.py stages baseline/_ref/EgoVLPv2 for
+    the GPU-eager baseline of tools/bench_ref_gpu.py, the only caller that passes it)."""
+    global REF_ROOT
     if _loaded:
         return types.SimpleNamespace(**_loaded)
-    if not available():
+    if root is not None:
+        REF_ROOT = root
+    if not os.path.isdir(REF_ROOT):
         raise RuntimeError("reference tree not present (expected on the build container only)")
 
     import transformers  # noqa: F401  (must precede the timm stub)
