@@ -1,0 +1,258 @@
+// Row-wise pieces of the re-associated gated cross-attention that are not GEMM-shaped (the GEMMs are xgemm.cu):
+//   text -> video (roberta.py:470-486, 281-321): softmax over the N video tokens of every (clip, head, text query) row of
+//     the score matrix Qp x^T, its backward, and (train mode) the Philox dropout of the probabilities (roberta.py:313);
+//   video -> text (video_transformer.py:155-185): the query-bias term of the scores, c0[b,s,h] = d^-1/2 bq_h . k_h[b,s],
+//     plus the additive key mask, and its backward.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace egv {
+namespace xa {
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int ROW_THREADS = 256;
+constexpr int MAX_PER_THREAD = 16;   // rows of up to 4096 columns live in registers
+
+EGV_DEVINL float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool IS_MAX>
+EGV_DEVINL float block_reduce(float v, float* red) {
+  v = IS_MAX ? warp_max(v) : warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();   // red may still be read from the previous reduction
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < ROW_THREADS / 32; ++i) r = IS_MAX ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+// Philox4x32-10 (Salmon et al. 2011), the counter-based generator torch's CUDA dropout uses: the stream is a pure
+// function of (seed, offset + element index / 4), so the backward regenerates the mask instead of storing it.
+EGV_DEVINL uint4 philox4(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+  uint32_t c2 = 0u, c3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// keep-decision of element `idx` of a stream: uniform 24-bit fraction >= p
+EGV_DEVINL bool philox_keep(unsigned long long seed, unsigned long long idx, float p_drop) {
+  const unsigned long long ctr = idx >> 2;
+  const uint4 r = philox4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t w = (idx & 3) == 0 ? r.x : ((idx & 3) == 1 ? r.y : ((idx & 3) == 2 ? r.z : r.w));
+  return (float)(w >> 8) * (1.0f / 16777216.0f) >= p_drop;
+}
+
+// One CTA per row r of scores [rows, ld_s] (row r = batch r / rows_per_batch, local row r % rows_per_batch; output
+// rows of batch b start at b * p_bstride elements).  P = softmax(scores) in bf16, lse = log sum exp (natural log).
+// Dropout (p_drop > 0): P_out = keep ? P / (1 - p) : 0, with `rsum` = the row sum of the dropped probabilities.
+__global__ void __launch_bounds__(ROW_THREADS)
+row_softmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_per_batch, long long s_bstride, int n,
+                   bf16* __restrict__ P, long long ld_p, long long p_bstride, float* __restrict__ lse, float p_drop,
+                   unsigned long long seed, float* __restrict__ rsum) {
+  __shared__ float red[ROW_THREADS / 32];
+  const long long r = blockIdx.x;
+  const long long b = r / rows_per_batch, lr = r % rows_per_batch;
+  const float* src = scores + b * s_bstride + lr * ld_s;
+  bf16* dst = P + b * p_bstride + lr * ld_p;
+  float x[MAX_PER_THREAD];
+  float mx = -3.0e38f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_THREAD; ++i) {
+    const int c = threadIdx.x + i * ROW_THREADS;
+    x[i] = c < n ? __ldg(src + c) : -3.0e38f;
+    mx = fmaxf(mx, x[i]);
+  }
+  mx = block_reduce<true>(mx, red);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_THREAD; ++i) {
+    const int c = threadIdx.x + i * ROW_THREADS;
+    x[i] = c < n ? ex2((x[i] - mx) * LOG2E) : 0.f;
+    sum += x[i];
+  }
+  sum = block_reduce<false>(sum, red);
+  const float inv = 1.0f / sum;
+  const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  float dsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_THREAD; ++i) {
+    const int c = threadIdx.x + i * ROW_THREADS;
+    if (c < n) {
+      float pv = x[i] * inv;
+      if (p_drop > 0.f) {
+        pv = philox_keep(seed, (unsigned long long)r * (unsigned long long)n + c, p_drop) ? pv * keep_scale : 0.f;
+        dsum += pv;
+      }
+      dst[c] = __float2bfloat16(pv);
+    }
+  }
+  if (threadIdx.x == 0 && lse) lse[r] = mx + logf(sum);
+  if (rsum) {
+    dsum = block_reduce<false>(dsum, red);
+    if (threadIdx.x == 0) rsum[r] = p_drop > 0.f ? dsum : 1.0f;
+  }
+}
+
+// Backward of row_softmax_kernel: dS = P * (dP~ - sum_c P dP~), where P = exp(scores - lse) is recomputed from the saved
+// scores and dP~ = dP * keep / (1 - p) undoes the dropout (the mask is regenerated from the Philox stream).
+__global__ void __launch_bounds__(ROW_THREADS)
+row_dsoftmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_per_batch, long long s_bstride, int n,
+                    const float* __restrict__ lse, const float* __restrict__ dP, long long ld_dp, long long dp_bstride,
+                    bf16* __restrict__ dS, long long ld_ds, long long ds_bstride, float p_drop, unsigned long long seed,
+                    const float* __restrict__ row_const) {
+  __shared__ float red[ROW_THREADS / 32];
+  const long long r = blockIdx.x;
+  const long long b = r / rows_per_batch, lr = r % rows_per_batch;
+  const float* src = scores + b * s_bstride + lr * ld_s;
+  const float* dp = dP + b * dp_bstride + lr * ld_dp;
+  bf16* dst = dS + b * ds_bstride + lr * ld_ds;
+  const float l2 = lse[r] * LOG2E;
+  const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const float rc = row_const ? row_const[r] : 0.f;   // value-bias term d_ox_h . bv_h (cancels unless dropout is on)
+  float pr[MAX_PER_THREAD], g[MAX_PER_THREAD];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_THREAD; ++i) {
+    const int c = threadIdx.x + i * ROW_THREADS;
+    pr[i] = 0.f;
+    g[i] = 0.f;
+    if (c < n) {
+      pr[i] = ex2(fmaf(__ldg(src + c), LOG2E, -l2));
+      float gv = __ldg(dp + c) + rc;
+      if (p_drop > 0.f) gv = philox_keep(seed, (unsigned long long)r * (unsigned long long)n + c, p_drop) ? gv * keep_scale : 0.f;
+      g[i] = gv;
+      dot = fmaf(pr[i], gv, dot);
+    }
+  }
+  dot = block_reduce<false>(dot, red);
+#pragma unroll
+  for (int i = 0; i < MAX_PER_THREAD; ++i) {
+    const int c = threadIdx.x + i * ROW_THREADS;
+    if (c < n) dst[c] = __float2bfloat16(pr[i] * (g[i] - dot));
+  }
+}
+
+// bias1[b, h*S + s] = scale * sum_j k[b*S+s, h*64+j] * bq[h*64+j] + mask[b, s]      one warp per (b, s, h)
+__global__ void qbias_fwd_kernel(const bf16* __restrict__ k, long long ldk, const float* __restrict__ bq,
+                                 const float* __restrict__ mask, float scale, int B, int S, int H, float* __restrict__ out) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B * S * H) return;
+  const int h = gw % H, bs = gw / H;
+  const int b = bs / S, s = bs % S;
+  const bf16* kr = k + (long long)bs * ldk + h * 64;
+  const float2 kv = unpack_bf16(*reinterpret_cast<const uint32_t*>(kr + 2 * lane));
+  const float2 q = *reinterpret_cast<const float2*>(bq + h * 64 + 2 * lane);
+  float v = warp_sum(kv.x * q.x + kv.y * q.y);
+  if (lane == 0) out[(long long)b * H * S + h * S + s] = scale * v + (mask ? mask[bs] : 0.f);
+}
+
+// dk[b*S+s, h*64+j] += scale * dbias[b, h*S+s] * bq[h*64+j];   dbq[h*64+j] += scale * sum_{b,s} k[..] * dbias[..]
+// one CTA per head, 64 threads (j); the B*S rows are walked serially (B*S = 256)
+__global__ void qbias_bwd_kernel(const bf16* __restrict__ k, long long ldk, const float* __restrict__ bq,
+                                 const float* __restrict__ dbias, float scale, int B, int S, int H, float* __restrict__ dk,
+                                 long long lddk, float* __restrict__ dbq) {
+  const int h = blockIdx.x, j = threadIdx.x;
+  const float q = bq[h * 64 + j];
+  float acc = 0.f;
+  for (int bs = 0; bs < B * S; ++bs) {
+    const int b = bs / S, s = bs % S;
+    const float g = scale * dbias[(long long)b * H * S + h * S + s];
+    acc = fmaf(g, __bfloat162float(k[(long long)bs * ldk + h * 64 + j]), acc);
+    if (dk) dk[(long long)bs * lddk + h * 64 + j] += g * q;
+  }
+  if (dbq) atomicAdd(dbq + h * 64 + j, acc);
+}
+
+// ox[b*S+s, h*64+j] += rsum[b, h*S+s] * bv[h*64+j]   (value bias under dropout: the dropped probabilities do not sum to 1)
+__global__ void rowscale_bias_kernel(bf16* __restrict__ ox, long long ld, const float* __restrict__ rsum,
+                                     const float* __restrict__ bv, int B, int S, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Cw = H * 64;
+  if (i >= B * S * Cw) return;
+  const int col = i % Cw, bs = i / Cw, h = col / 64, b = bs / S, s = bs % S;
+  bf16* o = ox + (long long)bs * ld + col;
+  *o = __float2bfloat16(__bfloat162float(*o) + rsum[(long long)b * H * S + h * S + s] * bv[col]);
+}
+// dbv[h*64+j] += sum_{b,s} rsum[b, h*S+s] * d_ox[b*S+s, h*64+j]
+__global__ void rowscale_bias_bwd_kernel(const bf16* __restrict__ d_ox, long long ld, const float* __restrict__ rsum,
+                                         float* __restrict__ dbv, int B, int S, int H) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= H * 64) return;
+  const int h = col / 64;
+  float acc = 0.f;
+  for (int bs = 0; bs < B * S; ++bs)
+    acc = fmaf(rsum[(long long)(bs / S) * H * S + h * S + (bs % S)], __bfloat162float(d_ox[(long long)bs * ld + col]), acc);
+  dbv[col] += acc;
+}
+
+}  // namespace xa
+}  // namespace egv
+
+using namespace egv;
+
+extern "C" int egv_xattn_row_softmax(const float* scores, int64_t ld_s, int64_t rows, int rows_per_batch, int64_t s_bstride,
+                                     int n, void* P, int64_t ld_p, int64_t p_bstride, float* lse, float p_drop, uint64_t seed,
+                                     float* rsum, egv_stream_t stream) {
+  if (!scores || !P || rows <= 0 || n <= 0 || rows_per_batch <= 0) return fail(EGV_ERR_ARG, "row_softmax: bad arguments");
+  if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD) return fail(EGV_ERR_UNSUPPORTED, "row_softmax: %d columns > %d", n, xa::ROW_THREADS * xa::MAX_PER_THREAD);
+  if (p_drop < 0.f || p_drop >= 1.f) return fail(EGV_ERR_ARG, "row_softmax: dropout probability %f", p_drop);
+  xa::row_softmax_kernel<<<(unsigned)rows, xa::ROW_THREADS, 0, (cudaStream_t)stream>>>(
+      scores, ld_s, rows_per_batch, s_bstride, n, (bf16*)P, ld_p, p_bstride, lse, p_drop, seed, rsum);
+  return check_launch("row_softmax_kernel");
+}
+
+extern "C" int egv_xattn_row_dsoftmax(const float* scores, int64_t ld_s, int64_t rows, int rows_per_batch, int64_t s_bstride,
+                                      int n, const float* lse, const float* dP, int64_t ld_dp, int64_t dp_bstride, void* dS,
+                                      int64_t ld_ds, int64_t ds_bstride, float p_drop, uint64_t seed, const float* row_const,
+                                      egv_stream_t stream) {
+  if (!scores || !lse || !dP || !dS || rows <= 0 || n <= 0 || rows_per_batch <= 0) return fail(EGV_ERR_ARG, "row_dsoftmax: bad arguments");
+  if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD) return fail(EGV_ERR_UNSUPPORTED, "row_dsoftmax: %d columns > %d", n, xa::ROW_THREADS * xa::MAX_PER_THREAD);
+  xa::row_dsoftmax_kernel<<<(unsigned)rows, xa::ROW_THREADS, 0, (cudaStream_t)stream>>>(
+      scores, ld_s, rows_per_batch, s_bstride, n, lse, dP, ld_dp, dp_bstride, (bf16*)dS, ld_ds, ds_bstride, p_drop, seed, row_const);
+  return check_launch("row_dsoftmax_kernel");
+}
+
+extern "C" int egv_xattn_qbias_fwd(const void* k, int64_t ldk, const float* bq, const float* mask, float scale, int B, int S,
+                                   int H, float* out, egv_stream_t stream) {
+  if (!k || !bq || !out || B <= 0 || S <= 0 || H <= 0) return fail(EGV_ERR_ARG, "qbias_fwd: bad arguments");
+  const long long warps = (long long)B * S * H;
+  xa::qbias_fwd_kernel<<<(unsigned)cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)k, ldk, bq, mask, scale, B, S, H, out);
+  return check_launch("qbias_fwd_kernel");
+}
+
+extern "C" int egv_xattn_qbias_bwd(const void* k, int64_t ldk, const float* bq, const float* dbias, float scale, int B, int S,
+                                   int H, float* dk, int64_t lddk, float* dbq, egv_stream_t stream) {
+  if (!k || !bq || !dbias || B <= 0 || S <= 0 || H <= 0) return fail(EGV_ERR_ARG, "qbias_bwd: bad arguments");
+  xa::qbias_bwd_kernel<<<(unsigned)H, 64, 0, (cudaStream_t)stream>>>((const bf16*)k, ldk, bq, dbias, scale, B, S, H, dk, lddk, dbq);
+  return check_launch("qbias_bwd_kernel");
+}
+
+extern "C" int egv_xattn_rowscale_bias(void* ox, int64_t ld, const float* rsum, const float* bv, int B, int S, int H,
+                                       egv_stream_t stream) {
+  if (!ox || !rsum || !bv || B <= 0 || S <= 0 || H <= 0) return fail(EGV_ERR_ARG, "rowscale_bias: bad arguments");
+  const long long n = (long long)B * S * H * 64;
+  xa::rowscale_bias_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((bf16*)ox, ld, rsum, bv, B, S, H);
+  return check_launch("rowscale_bias_kernel");
+}
+
+extern "C" int egv_xattn_rowscale_bias_bwd(const void* d_ox, int64_t ld, const float* rsum, float* dbv, int B, int S, int H,
+                                           egv_stream_t stream) {
+  if (!d_ox || !rsum || !dbv || B <= 0 || S <= 0 || H <= 0) return fail(EGV_ERR_ARG, "rowscale_bias_bwd: bad arguments");
+  xa::rowscale_bias_bwd_kernel<<<(unsigned)cdiv(H * 64, 64), 64, 0, (cudaStream_t)stream>>>((const bf16*)d_ox, ld, rsum, dbv, B, S, H);
+  return check_launch("rowscale_bias_bwd_kernel");
+}

@@ -16,6 +16,7 @@ import types
 
 import torch
 
+from . import xattn_reassoc as XR
 from .lib import (ACT_GELU, ACT_GELU_BWD, ACT_GELU_DG, ACT_MUL_AUX, ACT_NONE, ACT_RELU, ACT_RELU_BWD, ACT_TANH, ACT_TANH_BWD,
                   GEMM_NN, GEMM_NT, GEMM_TN, AttnSpec)
 
@@ -28,6 +29,25 @@ def _e(like, shape, dtype):
 
 def _z(like, shape, dtype=F32):
     return torch.zeros(shape, dtype=dtype, device=like.device)
+
+
+_REASSOC = None
+
+
+def reassoc_enabled():
+    """The re-associated cross-attention (xattn_reassoc.py) is the default; EGV_XATTN_REASSOC=0 selects the round-1
+    formulation (separate query / key / value projections + the strided attention kernels), kept for shapes the
+    re-associated kernels do not cover (text length != 32, more than 4096 video tokens per clip)."""
+    global _REASSOC
+    if _REASSOC is None:
+        import os
+        _REASSOC = os.environ.get("EGV_XATTN_REASSOC", "1") != "0"
+    return _REASSOC
+
+
+def set_reassoc(on):
+    global _REASSOC
+    _REASSOC = bool(on)
 
 
 # ----------------------------------------------------------------------------------------------- parameter gradients
@@ -195,21 +215,27 @@ def video_block_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=Tr
         s.lnc, s.meanc, s.rstdc = _e(x, (M, C), BF16), _e(x, (M,), F32), _e(x, (M,), F32)
         K.layernorm_fwd(s.a, p["attn.norm_i2t_i.weight"], p["attn.norm_i2t_i.bias"], eps, y_bf16=s.lnc, mean=s.meanc,
                         rstd=s.rstdc)
-        s.q_c = _e(x, (M, C), BF16)
-        K.gemm(GEMM_NT, s.lnc, w["attn.qkv_i2t.weight"], bias=p["attn.qkv_i2t.bias"], out_bf16=s.q_c)
         s.y_bf = _e(x, (B * S, Ct), BF16)
         K.cast(y.reshape(B * S, Ct), s.y_bf)
         s.kv_t = _e(x, (B * S, 2 * C), BF16)
         K.gemm(GEMM_NT, s.y_bf, w["attn.qkv_text_i2t.weight"], bias=p["attn.qkv_text_i2t.bias"], out_bf16=s.kv_t)
-        s.spec_c = AttnSpec(H=H, G=1, Lq=N, Lk=S, scale=(C // H) ** -0.5)
         s.y_bias = y_bias
-        kv3 = s.kv_t.view(B, S, 2 * C)
-        s.o_c, s.lse_c = _e(x, (B, N, C), BF16), _e(x, (B * H * N,), F32)
-        K.attention_fwd(s.spec_c, s.q_c.view(B, N, C), kv3[:, :, :C], kv3[:, :, C:], s.o_c, s.lse_c, key_bias=y_bias)
-        # sr = xa + alpha * (proj_i2t(o_c));  c (pre-gate) kept in bf16 for d_alpha
-        s.c = _e(x, (M, C), BF16)
-        K.gemm(GEMM_NT, s.o_c.view(M, C), w["attn.proj_i2t.weight"], bias=p["attn.proj_i2t.bias"],
-               scale_dev=p["attn.alpha_i2t"], residual=xa, out_f32=s.sr, out_pre=s.c)
+        s.reassoc = reassoc_enabled() and XR.i2t_supported(S, C, H)
+        if s.reassoc:
+            # re-associated around the S text keys (xattn_reassoc.py): no [M, C] query / output projections
+            s.xr = XR.i2t_fwd(K, s.lnc, s.kv_t, y_bias, w["attn.qkv_i2t.weight"], p["attn.qkv_i2t.bias"],
+                              w["attn.proj_i2t.weight"], p["attn.proj_i2t.bias"], p["attn.alpha_i2t"], xa, s.sr, B, N, H)
+        else:
+            s.q_c = _e(x, (M, C), BF16)
+            K.gemm(GEMM_NT, s.lnc, w["attn.qkv_i2t.weight"], bias=p["attn.qkv_i2t.bias"], out_bf16=s.q_c)
+            s.spec_c = AttnSpec(H=H, G=1, Lq=N, Lk=S, scale=(C // H) ** -0.5)
+            kv3 = s.kv_t.view(B, S, 2 * C)
+            s.o_c, s.lse_c = _e(x, (B, N, C), BF16), _e(x, (B * H * N,), F32)
+            K.attention_fwd(s.spec_c, s.q_c.view(B, N, C), kv3[:, :, :C], kv3[:, :, C:], s.o_c, s.lse_c, key_bias=y_bias)
+            # sr = xa + alpha * (proj_i2t(o_c));  c (pre-gate) kept in bf16 for d_alpha
+            s.c = _e(x, (M, C), BF16)
+            K.gemm(GEMM_NT, s.o_c.view(M, C), w["attn.proj_i2t.weight"], bias=p["attn.proj_i2t.bias"],
+                   scale_dev=p["attn.alpha_i2t"], residual=xa, out_f32=s.sr, out_pre=s.c)
     # ---- MLP
     K.mark("video_block")
     s.ln2, s.mean2, s.rstd2 = _e(x, (M, C), BF16), _e(x, (M,), F32), _e(x, (M,), F32)
@@ -254,22 +280,30 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True, sink=None):
         S, Ct = s.y_bf.shape[0] // B, s.y_bf.shape[1]
         alpha = p["attn.alpha_i2t"]
         K.mark("xattn_i2t_bwd")
-        # sr = x + a + alpha * c,  c = proj_i2t(o_c)
-        G.scalar_dot("attn.alpha_i2t", d_sr, s.c)
-        G.weight("attn.proj_i2t.weight", d_sr_bf, s.o_c.view(M, C), scale_dev=alpha)
+        # sr = x + a + alpha * c,  c = proj_i2t(attention)
         G.bias_from("attn.proj_i2t.bias", cs_sr, scale_dev=alpha)
-        d_oc = _e(d_out, (B, N, C), BF16)
-        K.gemm(GEMM_NN, d_sr_bf, w["attn.proj_i2t.weight"], scale_dev=alpha, out_bf16=d_oc.view(M, C))
-        kv3 = s.kv_t.view(B, S, 2 * C)
-        dq_c = _e(d_out, (B, N, C), BF16)
-        dkv = _e(d_out, (B, S, 2 * C), BF16)
-        K.attention_bwd(s.spec_c, s.q_c.view(B, N, C), kv3[:, :, :C], kv3[:, :, C:], s.o_c, s.lse_c, d_oc, dq_c,
-                        dkv[:, :, :C], dkv[:, :, C:], _e(d_out, s.lse_c.shape, F32), key_bias=s.y_bias)
-        dq2, dkv2 = dq_c.view(M, C), dkv.view(B * S, 2 * C)
-        G.weight("attn.qkv_i2t.weight", dq2, s.lnc)
-        G.bias("attn.qkv_i2t.bias", dq2)
-        d_lnc = _e(d_out, (M, C), BF16)
-        K.gemm(GEMM_NN, dq2, w["attn.qkv_i2t.weight"], out_bf16=d_lnc)
+        if s.reassoc:
+            d_lnc, dkv_f = XR.i2t_bwd(K, s.xr, d_sr_bf, cs_sr, w["attn.qkv_i2t.weight"], p["attn.qkv_i2t.bias"],
+                                      w["attn.proj_i2t.weight"], p["attn.proj_i2t.bias"], alpha, G.full("attn.alpha_i2t", (1,)),
+                                      G.full("attn.qkv_i2t.weight", (C, C)), G.full("attn.qkv_i2t.bias", (C,)),
+                                      G.full("attn.proj_i2t.weight", (C, C)))
+            dkv2 = _e(d_out, (B * S, 2 * C), BF16)
+            K.cast(dkv_f, dkv2)
+        else:
+            G.scalar_dot("attn.alpha_i2t", d_sr, s.c)
+            G.weight("attn.proj_i2t.weight", d_sr_bf, s.o_c.view(M, C), scale_dev=alpha)
+            d_oc = _e(d_out, (B, N, C), BF16)
+            K.gemm(GEMM_NN, d_sr_bf, w["attn.proj_i2t.weight"], scale_dev=alpha, out_bf16=d_oc.view(M, C))
+            kv3 = s.kv_t.view(B, S, 2 * C)
+            dq_c = _e(d_out, (B, N, C), BF16)
+            dkv = _e(d_out, (B, S, 2 * C), BF16)
+            K.attention_bwd(s.spec_c, s.q_c.view(B, N, C), kv3[:, :, :C], kv3[:, :, C:], s.o_c, s.lse_c, d_oc, dq_c,
+                            dkv[:, :, :C], dkv[:, :, C:], _e(d_out, s.lse_c.shape, F32), key_bias=s.y_bias)
+            dq2, dkv2 = dq_c.view(M, C), dkv.view(B * S, 2 * C)
+            G.weight("attn.qkv_i2t.weight", dq2, s.lnc)
+            G.bias("attn.qkv_i2t.bias", dq2)
+            d_lnc = _e(d_out, (M, C), BF16)
+            K.gemm(GEMM_NN, dq2, w["attn.qkv_i2t.weight"], out_bf16=d_lnc)
         G.weight("attn.qkv_text_i2t.weight", dkv2, s.y_bf)
         G.bias("attn.qkv_text_i2t.bias", dkv2)
         dy = _e(d_out, (B, S, Ct), F32)
@@ -529,15 +563,22 @@ def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True):
         s.vshape = (Bv, N, Cv)
         s.x_bf = _e(h, (Bv * N, Cv), BF16)
         K.cast(video.reshape(Bv * N, Cv).contiguous(), s.x_bf)
-        s.kv = _e(h, (Bv * N, 2 * C), BF16)
-        K.gemm(GEMM_NT, s.x_bf, w["cross.kv"], bias=p["cross.kv.bias"], out_bf16=s.kv)
         s.qx = _e(h, (M, C), BF16)
         K.gemm(GEMM_NT, s.so_bf, w["crossattention_t2i.self.query.weight"], bias=p["crossattention_t2i.self.query.bias"],
                out_bf16=s.qx)
-        s.spec_x = AttnSpec(H=H, G=1, Lq=S, Lk=N, scale=1.0 / math.sqrt(d))
-        kv3 = s.kv.view(Bv, N, 2 * C)
-        s.ox, s.lse_x = _e(h, (B, S, C), BF16), _e(h, (B * H * S,), F32)
-        K.attention_fwd(s.spec_x, s.qx.view(B, S, C), kv3[:, :, :C], kv3[:, :, C:], s.ox, s.lse_x)
+        s.ox = _e(h, (B, S, C), BF16)
+        s.reassoc = reassoc_enabled() and Bv == B and XR.t2i_supported(S, N, C, H)
+        if s.reassoc:
+            # re-associated around the S text queries (xattn_reassoc.py): K = V = the video stream itself, no K/V projection
+            s.xr = XR.t2i_fwd(K, s.qx, s.x_bf, w["cross.kv"][:C], w["cross.kv"][C:], p["cross.kv.bias"][C:], s.ox.view(M, C),
+                              B, N, H)
+        else:
+            s.kv = _e(h, (Bv * N, 2 * C), BF16)
+            K.gemm(GEMM_NT, s.x_bf, w["cross.kv"], bias=p["cross.kv.bias"], out_bf16=s.kv)
+            s.spec_x = AttnSpec(H=H, G=1, Lq=S, Lk=N, scale=1.0 / math.sqrt(d))
+            kv3 = s.kv.view(Bv, N, 2 * C)
+            s.lse_x = _e(h, (B * H * S,), F32)
+            K.attention_fwd(s.spec_x, s.qx.view(B, S, C), kv3[:, :, :C], kv3[:, :, C:], s.ox, s.lse_x)
         # attn_out + h = alpha * c + so + h
         s.c = _e(h, (M, C), BF16)
         sh2 = _e(h, (M, C), F32)
@@ -601,18 +642,23 @@ def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True, sink=None):
         G.bias("crossattention_t2i.output.dense.bias", d_sh_bf, scale_dev=alpha)
         d_ox = _e(d_out, (B, S, C), BF16)
         K.gemm(GEMM_NN, d_sh_bf, w["crossattention_t2i.output.dense.weight"], scale_dev=alpha, out_bf16=d_ox.view(M, C))
-        kv3 = s.kv.view(Bv, N, 2 * C)
-        dqx = _e(d_out, (B, S, C), BF16)
-        dkv = _e(d_out, (Bv, N, 2 * C), BF16)
-        K.attention_bwd(s.spec_x, s.qx.view(B, S, C), kv3[:, :, :C], kv3[:, :, C:], s.ox, s.lse_x, d_ox, dqx, dkv[:, :, :C],
-                        dkv[:, :, C:], _e(d_out, s.lse_x.shape, F32))
-        dqx2, dkv2 = dqx.view(M, C), dkv.view(Bv * N, 2 * C)
+        dvideo = _e(d_out, (Bv, N, Cv), F32)
+        if s.reassoc:
+            gw, gb = G.full("cross.kv", (2 * C, Cv)), G.full("cross.kv.bias", (2 * C,))
+            dqx2 = XR.t2i_bwd(K, s.xr, d_ox.view(M, C), w["cross.kv"][:C], w["cross.kv"][C:], p["cross.kv.bias"][C:], gw[:C],
+                              gw[C:], gb[C:], dvideo.view(Bv * N, Cv))
+        else:
+            kv3 = s.kv.view(Bv, N, 2 * C)
+            dqx = _e(d_out, (B, S, C), BF16)
+            dkv = _e(d_out, (Bv, N, 2 * C), BF16)
+            K.attention_bwd(s.spec_x, s.qx.view(B, S, C), kv3[:, :, :C], kv3[:, :, C:], s.ox, s.lse_x, d_ox, dqx, dkv[:, :, :C],
+                            dkv[:, :, C:], _e(d_out, s.lse_x.shape, F32))
+            dqx2, dkv2 = dqx.view(M, C), dkv.view(Bv * N, 2 * C)
+            G.weight("cross.kv", dkv2, s.x_bf)
+            G.bias("cross.kv.bias", dkv2)
+            K.gemm(GEMM_NN, dkv2, w["cross.kv"], out_f32=dvideo.view(Bv * N, Cv))
         G.weight("crossattention_t2i.self.query.weight", dqx2, s.so_bf)
         G.bias("crossattention_t2i.self.query.bias", dqx2)
-        G.weight("cross.kv", dkv2, s.x_bf)
-        G.bias("cross.kv.bias", dkv2)
-        dvideo = _e(d_out, (Bv, N, Cv), F32)
-        K.gemm(GEMM_NN, dkv2, w["cross.kv"], out_f32=dvideo.view(Bv * N, Cv))
         # d_so = d_sh + Wq_x'(dqx)
         d_so_bf = _e(d_out, (M, C), BF16)
         K.gemm(GEMM_NN, dqx2, w["crossattention_t2i.self.query.weight"], residual=d_sh, out_bf16=d_so_bf)

@@ -32,6 +32,33 @@ class GemmArgs(C.Structure):
                 ("act", c_int), ("accumulate", c_int), ("split_k", c_int), ("colsum", c_void_p)]
 
 
+class BGemmArgs(C.Structure):
+    _fields_ = [("layout", c_int), ("M", c_int), ("N", c_int), ("K", c_int), ("nb0", c_int), ("nb1", c_int),
+                ("A", c_void_p), ("lda", c_int64), ("sa0", c_int64), ("sa1", c_int64),
+                ("B", c_void_p), ("ldb", c_int64), ("sb0", c_int64), ("sb1", c_int64),
+                ("bias", c_void_p), ("sbias0", c_int64), ("sbias1", c_int64),
+                ("scale", c_float), ("scale_dev", c_void_p),
+                ("residual", c_void_p), ("ld_res", c_int64), ("sres0", c_int64), ("sres1", c_int64),
+                ("out_f32", c_void_p), ("ld_out_f32", c_int64), ("so32_0", c_int64), ("so32_1", c_int64),
+                ("out_bf16", c_void_p), ("ld_out_bf16", c_int64), ("so16_0", c_int64), ("so16_1", c_int64),
+                ("aux", c_void_p), ("ld_aux", c_int64), ("saux0", c_int64), ("saux1", c_int64),
+                ("colsum", c_void_p), ("scol0", c_int64), ("scol1", c_int64),
+                ("dot_out", c_void_p),
+                ("accumulate", c_int), ("split_k", c_int), ("epilogue", c_int)]
+
+
+class BV:
+    """Batched view of a tensor for `Kernels.bgemm`: base tensor `t` (its data_ptr is element (z0=0, z1=0, row 0, col 0)),
+    row stride `ld` and the two batch strides `s0`, `s1` in elements (0 = shared by that batch level)."""
+    __slots__ = ("t", "ld", "s0", "s1")
+
+    def __init__(self, t, ld=None, s0=0, s1=0):
+        self.t, self.ld, self.s0, self.s1 = t, (t.stride(-2) if ld is None else ld), s0, s1
+
+
+EPI_NONE, EPI_SOFTMAX32, EPI_DSOFTMAX32 = 0, 1, 2
+
+
 class AttnArgs(C.Structure):
     _fields_ = [("B", c_int), ("H", c_int), ("G", c_int), ("Lq", c_int), ("Lk", c_int),
                 ("q", c_void_p), ("ldq", c_int64), ("q_bstride", c_int64),
@@ -199,6 +226,76 @@ class Kernels:
             a.colsum = _p(colsum)
         a.act, a.accumulate, a.split_k = int(act), int(bool(accumulate)), int(split_k)
         self._timed("gemm", 2.0 * M * N * K, lambda: self._check(self.lib.egv_gemm_bf16(C.byref(a), self._stream())))
+
+    # ------------------------------------------------------------------ batched GEMM / re-associated cross-attention
+    def bgemm(self, layout, M, N, K, A, B, nb=(1, 1), bias=None, scale=1.0, scale_dev=None, residual=None, out_f32=None,
+              out_bf16=None, aux=None, colsum=None, dot_out=None, accumulate=False, split_k=1, epilogue=EPI_NONE):
+        """D[z] = epilogue(A[z] x B[z]) over the batch grid nb = (nb0, nb1); every tensor argument is a `BV`
+        (bias / colsum: BV whose `ld` is ignored).  See egv_bgemm_bf16 in include/egovlp_b200.h."""
+        a = BGemmArgs()
+        a.layout, a.M, a.N, a.K, a.nb0, a.nb1 = layout, M, N, K, nb[0], nb[1]
+        for v, dt in ((A, torch.bfloat16), (B, torch.bfloat16), (bias, torch.float32), (residual, torch.float32),
+                      (out_f32, torch.float32), (out_bf16, torch.bfloat16), (aux, torch.bfloat16), (colsum, torch.float32)):
+            if v is not None and (v.t.dtype != dt or not v.t.is_cuda):
+                raise ValueError("bgemm: expected a CUDA %s tensor, got %s" % (dt, v.t.dtype))
+        a.A, a.lda, a.sa0, a.sa1 = _p(A.t), A.ld, A.s0, A.s1
+        a.B, a.ldb, a.sb0, a.sb1 = _p(B.t), B.ld, B.s0, B.s1
+        if bias is not None:
+            a.bias, a.sbias0, a.sbias1 = _p(bias.t), bias.s0, bias.s1
+        a.scale = float(scale)
+        if scale_dev is not None:
+            assert scale_dev.dtype == torch.float32 and scale_dev.numel() == 1
+            a.scale_dev = _p(scale_dev)
+        if residual is not None:
+            a.residual, a.ld_res, a.sres0, a.sres1 = _p(residual.t), residual.ld, residual.s0, residual.s1
+        if out_f32 is not None:
+            a.out_f32, a.ld_out_f32, a.so32_0, a.so32_1 = _p(out_f32.t), out_f32.ld, out_f32.s0, out_f32.s1
+        if out_bf16 is not None:
+            a.out_bf16, a.ld_out_bf16, a.so16_0, a.so16_1 = _p(out_bf16.t), out_bf16.ld, out_bf16.s0, out_bf16.s1
+        if aux is not None:
+            a.aux, a.ld_aux, a.saux0, a.saux1 = _p(aux.t), aux.ld, aux.s0, aux.s1
+        if colsum is not None:
+            a.colsum, a.scol0, a.scol1 = _p(colsum.t), colsum.s0, colsum.s1
+        if dot_out is not None:
+            assert dot_out.dtype == torch.float32 and dot_out.numel() == 1
+            a.dot_out = _p(dot_out)
+        a.accumulate, a.split_k, a.epilogue = int(bool(accumulate)), int(split_k), int(epilogue)
+        self._timed("gemm", 2.0 * M * N * K * nb[0] * nb[1], lambda: self._check(self.lib.egv_bgemm_bf16(C.byref(a), self._stream())))
+
+    def xattn_row_softmax(self, scores, ld_s, rows, rows_per_batch, s_bstride, n, P, ld_p, p_bstride, lse, p_drop=0.0, seed=0,
+                          rsum=None):
+        assert scores.dtype == torch.float32 and P.dtype == torch.bfloat16 and lse.dtype == torch.float32
+        self._timed("softmax", 0.0, lambda: self._check(self.lib.egv_xattn_row_softmax(
+            _p(scores), c_int64(ld_s), c_int64(rows), rows_per_batch, c_int64(s_bstride), n, _p(P), c_int64(ld_p),
+            c_int64(p_bstride), _p(lse), c_float(p_drop), C.c_uint64(seed), _p(rsum), self._stream())))
+
+    def xattn_row_dsoftmax(self, scores, ld_s, rows, rows_per_batch, s_bstride, n, lse, dP, ld_dp, dp_bstride, dS, ld_ds,
+                           ds_bstride, p_drop=0.0, seed=0, row_const=None):
+        assert scores.dtype == torch.float32 and dP.dtype == torch.float32 and dS.dtype == torch.bfloat16
+        self._timed("softmax", 0.0, lambda: self._check(self.lib.egv_xattn_row_dsoftmax(
+            _p(scores), c_int64(ld_s), c_int64(rows), rows_per_batch, c_int64(s_bstride), n, _p(lse), _p(dP), c_int64(ld_dp),
+            c_int64(dp_bstride), _p(dS), c_int64(ld_ds), c_int64(ds_bstride), c_float(p_drop), C.c_uint64(seed),
+            _p(row_const), self._stream())))
+
+    def xattn_rowscale_bias(self, ox, rsum, bv, B, S, H):
+        assert ox.dtype == torch.bfloat16 and ox.stride(1) == 1 and rsum.dtype == torch.float32 and bv.dtype == torch.float32
+        self._check(self.lib.egv_xattn_rowscale_bias(_p(ox), c_int64(ox.stride(0)), _p(rsum), _p(bv), B, S, H, self._stream()))
+
+    def xattn_rowscale_bias_bwd(self, d_ox, rsum, dbv, B, S, H):
+        assert d_ox.dtype == torch.bfloat16 and d_ox.stride(1) == 1 and dbv.dtype == torch.float32
+        self._check(self.lib.egv_xattn_rowscale_bias_bwd(_p(d_ox), c_int64(d_ox.stride(0)), _p(rsum), _p(dbv), B, S, H,
+                                                         self._stream()))
+
+    def xattn_qbias_fwd(self, k, ldk, bq, mask, scale, B, S, H, out):
+        assert k.dtype == torch.bfloat16 and bq.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous()
+        assert mask is None or (mask.dtype == torch.float32 and mask.is_contiguous() and mask.numel() == B * S)
+        self._check(self.lib.egv_xattn_qbias_fwd(_p(k), c_int64(ldk), _p(bq), _p(mask), c_float(scale), B, S, H, _p(out),
+                                                 self._stream()))
+
+    def xattn_qbias_bwd(self, k, ldk, bq, dbias, scale, B, S, H, dk=None, lddk=0, dbq=None):
+        assert k.dtype == torch.bfloat16 and dbias.dtype == torch.float32 and dbias.is_contiguous()
+        self._check(self.lib.egv_xattn_qbias_bwd(_p(k), c_int64(ldk), _p(bq), _p(dbias), c_float(scale), B, S, H, _p(dk),
+                                                 c_int64(lddk), _p(dbq), self._stream()))
 
     # ------------------------------------------------------------------ LayerNorm
     def layernorm_fwd(self, x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):

@@ -1,163 +1,202 @@
-"""ROUND-2 PATH, NOT WIRED INTO THE MODEL YET: the core of the gated video->text cross-attention
-(video_transformer.py:155-185: q = qkv_i2t(LN(x)), softmax(q k^T + mask) v, proj_i2t) re-associated around the S text keys
-(oracle/egovlp_oracle.py::cross_attention_i2t_reassociated):
+"""The two gated cross-attentions of the fusion layers, re-associated around the S text tokens
+(oracle/egovlp_oracle.py::cross_attention_{i2t,t2i}_reassociated prove the algebra exact).
 
-    scores[b,n,h,s] = LN(x)[b,n,:] . Mt[h,b,s,:] + c0[b,s,h] + mask[b,s]     Mt = d^-1/2 k_h Wq_h        [H, B*S, C]
-    c[b,n,:]        = sum_{h,s} P[b,n,h,s] U[h,b,s,:]                        U  = v_h Wp[:,h]^T + bp/H   [H, B*S, C]
+video -> text (video_transformer.py:155-185: q = qkv_i2t(LN(a)), softmax(q k^T + mask) v, proj_i2t, gate):
 
-i.e. the [M, C] x [C, C] query and output projections (M = B*N = 25 096 rows at the BASELINE shapes) and the 32-key
-attention launch become two [M, C] x [C, H*S] products with a 32-wide group softmax between them: half the FLOPs.
-(The text->video direction, re-associated the same way, follows below.)
-What is on the M rows runs in FOUR fused device kernels that do not exist in libegovlp_b200.so yet (batched-per-clip
-variants of gemm_tc_kernel with softmax / softmax-backward epilogues):
+    P[b,n,h,:] = softmax_s( LN(a)[b,n,:] . Mt[b,h,s,:] + c0[b,h,s] + mask[b,s] )      Mt = d^-1/2 k_h Wq_h       [B, H, S, C]
+    out[b,n,:] = xa[b,n,:] + alpha * ( sum_{h,s} P[b,n,h,s] U[b,h,s,:] + bp )          U  = v_h Wp[:,h]^T         [B, H, S, C]
 
-    K.xattn_scores_softmax(ln, Mt, c0, mask, P)     K.xattn_weighted_sum(P_or_dS, U_or_Mt, out)
-    K.xattn_dscores(dc, U, P, dS, dbias)            K.xattn_tn(P_or_dS, dc_or_ln, out)
+    -- the [M, C] x [C, C] query and output projections (M = B*N = 25 096 rows at the BASELINE shapes) and the 32-key attention
+    launch become two [N, C] x [C, H*S] products per clip with a 32-wide group softmax in the first one's epilogue.
 
-Everything on the B*S = 256 text rows uses the existing GEMM entry point on strided head views.  The sequencing and the
-hand-derived backward below are pinned against autograd through the oracle on CPU (tests/test_functional_cpu.py::
-test_reassociated_i2t_core) with the torch restatement of those four kernels (tests/fake_kernels.py); calling this module
-with the real library raises AttributeError -- there is no fallback."""
+text -> video (roberta.py:470-486: q from the text, k / v = Linear(x) of all N video tokens, no mask):
+
+    scores[b,h,s,n] = Qp[b,h,s,:] . x[b,n,:]        Qp = d^-1/2 q_h Wk_h   (q_h . bk_h is constant over keys: drops out)
+    ctx_h           = (P_h x) Wv_h^T + bv_h         Z  = P x               [B, H, S, Cv]
+
+    -- the key / value projection of the video tokens (2 * M * Cv * 2C FLOPs, two [M, C] tensors written, and the same again
+    twice in the backward) disappears; the video stream x itself is the key and the value.
+
+Everything runs on `K.bgemm` (csrc/xgemm.cu: batched tcgen05 GEMM over rank-4 TMA maps, batches = clips or (clip, head)
+pairs) plus four small row kernels (csrc/xattn.cu).  The hand-derived backward is pinned against autograd through the
+reference formulation (tests/test_functional_cpu.py::test_reassociated_*), on the GPU against the oracle at C = 768."""
 import types
 
 import torch
 
-from . import functional as Fn
-from .lib import GEMM_NN, GEMM_NT, GEMM_TN
+from .lib import BV, EPI_DSOFTMAX32, EPI_SOFTMAX32, GEMM_NN, GEMM_NT, GEMM_TN
 
-_e = Fn._e
-
-
-def _blockdiag_rows(vec, H):
-    """[C] -> [H, C] with vec's head-h slice in row h (the query bias as a block-diagonal operand)."""
-    C = vec.numel()
-    d = C // H
-    out = vec.new_zeros(H, C)
-    for h in range(H):
-        out[h, h * d:(h + 1) * d] = vec[h * d:(h + 1) * d]
-    return out
+F32 = torch.float32
+HD = 64          # head dim of every attention on this path
+GROUP = 32       # softmax group width of the bgemm epilogues = text tokens per clip
 
 
-def i2t_core_fwd(K, ln, kv, mask, wq, bq, wp, bp, H):
-    """ln [B,N,C] operand dtype; kv [B,S,2C] operand dtype (k | v); mask [B,S] f32 additive; wq / wp [C,C] operand
-    dtype; bq / bp [C] f32.  Returns (c [B,N,C] operand dtype = proj_i2t(attention) incl. its bias, saved)."""
-    BF16, F32 = Fn.BF16, torch.float32
-    B, N, C = ln.shape
-    S = kv.shape[1]
-    d = C // H
-    sc = d ** -0.5
-    kv2 = kv.view(B * S, 2 * C)
-    Mt, U = _e(ln, (H, B * S, C), BF16), _e(ln, (H, B * S, C), BF16)
-    bp_h = (bp / H).contiguous()
-    for h in range(H):
-        kh, vh = kv2[:, h * d:(h + 1) * d], kv2[:, C + h * d:C + (h + 1) * d]
-        K.gemm(GEMM_NN, kh, wq[h * d:(h + 1) * d, :], scale=sc, out_bf16=Mt[h])
-        K.gemm(GEMM_NT, vh, wp[:, h * d:(h + 1) * d], bias=bp_h, out_bf16=U[h])
-    bq_bd = _blockdiag_rows(bq, H).to(BF16)
-    c0 = _e(ln, (B * S, H), F32)
-    K.gemm(GEMM_NT, kv2[:, :C], bq_bd, scale=sc, out_f32=c0)
-    P = _e(ln, (B, N, H, S), BF16)
-    K.xattn_scores_softmax(ln, Mt.view(H, B, S, C), c0.view(B, S, H), mask, P)
-    c = _e(ln, (B, N, C), BF16)
-    K.xattn_weighted_sum(P, U.view(H, B, S, C), c)
-    return c, types.SimpleNamespace(ln=ln, kv=kv, Mt=Mt, U=U, P=P, bq_bd=bq_bd, H=H)
+def _e(like, shape, dtype):
+    return torch.empty(shape, dtype=dtype, device=like.device)
 
 
-def i2t_core_bwd(K, s, dc, wq, wp):
-    """dc [B,N,C] operand dtype -> (dln [B,N,C], dkv [B,S,2C] f32, dwq [C,C], dbq [C], dwp [C,C], dbp [C])  (f32 grads)."""
-    BF16, F32 = Fn.BF16, torch.float32
-    B, N, C = dc.shape
-    H, S = s.H, s.kv.shape[1]
-    d = C // H
-    sc = d ** -0.5
-    kv2 = s.kv.view(B * S, 2 * C)
-    dS = _e(dc, (B, N, H, S), BF16)
-    dc0 = _e(dc, (B, S, H), F32)
-    K.xattn_dscores(dc, s.U.view(H, B, S, C), s.P, dS, dc0)
-    dU, dM = _e(dc, (H, B * S, C), F32), _e(dc, (H, B * S, C), F32)
-    K.xattn_tn(s.P, dc, dU.view(H, B, S, C))
-    K.xattn_tn(dS, s.ln, dM.view(H, B, S, C))
-    dln = _e(dc, (B, N, C), BF16)
-    K.xattn_weighted_sum(dS, s.Mt.view(H, B, S, C), dln)
-    dU_b, dM_b = _e(dc, dU.shape, BF16), _e(dc, dM.shape, BF16)
-    K.cast(dU, dU_b)
-    K.cast(dM, dM_b)
-    dkv = _e(dc, (B * S, 2 * C), F32)
-    dwq, dwp = _e(dc, (C, C), F32), _e(dc, (C, C), F32)
-    for h in range(H):
-        hs = slice(h * d, (h + 1) * d)
-        kh, vh = kv2[:, hs], kv2[:, C + h * d:C + (h + 1) * d]
-        K.gemm(GEMM_NT, dM_b[h], wq[hs, :], scale=sc, out_f32=dkv[:, hs])                     # dk_h  = d^-1/2 dM_h Wq_h^T
-        K.gemm(GEMM_TN, kh, dM_b[h], scale=sc, out_f32=dwq[hs, :])                             # dWq_h = d^-1/2 k_h^T dM_h
-        K.gemm(GEMM_NN, dU_b[h], wp[:, hs], out_f32=dkv[:, C + h * d:C + (h + 1) * d])         # dv_h  = dU_h Wp[:,h]
-        K.gemm(GEMM_TN, dU_b[h], vh, out_f32=dwp[:, hs])                                       # dWp[:,h] = dU_h^T v_h
-    # the query bias: scores += d^-1/2 (bq_h . k_h)  ->  dk += d^-1/2 dc0 (x) bq ; dbq_h = d^-1/2 k_h^T dc0[:, h]
-    dc0_b = _e(dc, (B * S, H), BF16)
-    K.cast(dc0.view(B * S, H), dc0_b)
-    K.gemm(GEMM_NN, dc0_b, s.bq_bd, scale=sc, out_f32=dkv[:, :C], accumulate=True)
-    dbq_all = _e(dc, (C, H), F32)
-    K.gemm(GEMM_TN, kv2[:, :C], dc0_b, scale=sc, out_f32=dbq_all)
-    dbq = torch.cat([dbq_all[h * d:(h + 1) * d, h] for h in range(H)])
-    dbp = _e(dc, (C,), F32)
-    K.colsum(dU_b.view(H * B * S, C), dbp, scale=1.0 / H)
-    return dln, dkv.view(B, S, 2 * C), dwq, dbq, dwp, dbp
+def _z(like, shape, dtype=F32):
+    return torch.zeros(shape, dtype=dtype, device=like.device)
+
+
+def i2t_supported(S, C, H):
+    return S == GROUP and C == H * HD
+
+
+def t2i_supported(S, N, C, H):
+    return C == H * HD and N <= 4096 and S <= 128
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# text -> video direction (roberta.py:470-486: q from the text, k / v = Linear(x) of all N video tokens, no mask)
-#
-#     scores[b,h,s,n] = Qp[h,b,s,:] . x[b,n,:]            Qp = d^-1/2 q_h Wk_h   [H, B*S, Cv]   (q_h . bk_h drops out of softmax)
-#     ctx_h           = (P_h x) Wv_h^T + bv_h             Z  = P x               [H, B*S, Cv]
-#
-# The key / value projection of the video tokens (2 * M * Cv * 2C FLOPs, two [M, C] tensors written) disappears; what is
-# left on the M = B*N video rows is ONE flash-style kernel per direction with K = V = x and "head dim" Cv, still to be written:
-#     K.xattn_t2i_flash(Qp, x, Z, lse)          K.xattn_t2i_flash_bwd(dZ, Qp, x, Z, lse, dQp, dx)
-def t2i_core_fwd(K, q, x, wk, wv, bv, H):
-    """q [B,S,C] operand dtype (query projection of the text, bias included); x [B,N,Cv] operand dtype (video stream);
-    wk / wv [C,Cv] operand dtype; bv [C] f32.  Returns (ctx [B,S,C] f32 = merged heads before output.dense, saved)."""
-    BF16, F32 = Fn.BF16, torch.float32
-    B, S, C = q.shape
-    Cv = x.shape[2]
-    d = C // H
-    sc = d ** -0.5
-    q2 = q.view(B * S, C)
-    Qp = _e(q, (H, B * S, Cv), BF16)
-    for h in range(H):
-        K.gemm(GEMM_NN, q2[:, h * d:(h + 1) * d], wk[h * d:(h + 1) * d, :], scale=sc, out_bf16=Qp[h])
-    Z, lse = _e(q, (H, B * S, Cv), BF16), _e(q, (H, B * S), F32)
-    K.xattn_t2i_flash(Qp.view(H, B, S, Cv), x, Z.view(H, B, S, Cv), lse.view(H, B, S))
-    ctx = _e(q, (B * S, C), F32)
-    for h in range(H):
-        hs = slice(h * d, (h + 1) * d)
-        K.gemm(GEMM_NT, Z[h], wv[hs, :], bias=bv[hs], out_f32=ctx[:, hs])
-    return ctx.view(B, S, C), types.SimpleNamespace(q=q, x=x, Qp=Qp, Z=Z, lse=lse, H=H)
+def i2t_fwd(K, lnc, kv, mask, wq, bq, wp, bp, alpha, xa, out, B, N, H):
+    """lnc [B*N, C] bf16 = LN(a); kv [B*S, 2C] bf16 (k | v of the text); mask [B, S] f32 additive or None; wq / wp [C, C]
+    bf16; bq / bp [C] f32; alpha device scalar; xa [B*N, C] f32 (residual: x + a); out [B*N, C] f32 is written with
+    xa + alpha * proj_i2t(attention).  Returns the saved tensors."""
+    C = lnc.shape[1]
+    S = kv.shape[0] // B
+    HS = H * S
+    sc = HD ** -0.5
+    BF16 = lnc.dtype      # operand dtype (bf16; fp32 in the exact-mode host-logic tests)
+    Mt, U = _e(lnc, (B, H, S, C), BF16), _e(lnc, (B, H, S, C), BF16)
+    ldkv = kv.stride(0)
+    # text side, one batch per (clip, head): Mt = d^-1/2 k_h Wq_h ;  U = v_h Wp[:, h]^T
+    K.bgemm(GEMM_NN, S, C, HD, BV(kv, ldkv, HD, S * ldkv), BV(wq, wq.stride(0), HD * wq.stride(0), 0), nb=(H, B), scale=sc,
+            out_bf16=BV(Mt, C, S * C, HS * C))
+    K.bgemm(GEMM_NT, S, C, HD, BV(kv[:, C:], ldkv, HD, S * ldkv), BV(wp, wp.stride(0), HD, 0), nb=(H, B),
+            out_bf16=BV(U, C, S * C, HS * C))
+    bias1 = _e(lnc, (B, HS), F32)
+    K.xattn_qbias_fwd(kv, ldkv, bq, mask, sc, B, S, H, bias1)
+    # video side, one batch per clip: P = group-softmax(LN(a) Mt^T + bias1) ;  out = xa + alpha (P U + bp)
+    P = _e(lnc, (B, N, HS), BF16)
+    K.bgemm(GEMM_NT, N, HS, C, BV(lnc, C, N * C), BV(Mt, C, HS * C), nb=(B, 1), bias=BV(bias1, 0, HS), out_bf16=BV(P, HS, N * HS),
+            epilogue=EPI_SOFTMAX32)
+    K.bgemm(GEMM_NN, N, C, HS, BV(P, HS, N * HS), BV(U, C, HS * C), nb=(B, 1), bias=BV(bp, 0, 0), scale_dev=alpha,
+            residual=BV(xa, C, N * C), out_f32=BV(out, C, N * C))
+    return types.SimpleNamespace(lnc=lnc, kv=kv, Mt=Mt, U=U, P=P, B=B, N=N, H=H, S=S)
 
 
-def t2i_core_bwd(K, s, dctx, wk, wv):
-    """dctx [B,S,C] operand dtype -> (dq [B,S,C] f32, dx [B,N,Cv] f32, dwk [C,Cv], dwv [C,Cv], dbv [C]); the key bias has
-    an analytically zero gradient."""
-    BF16, F32 = Fn.BF16, torch.float32
-    B, S, C = dctx.shape
-    H, Cv = s.H, s.x.shape[2]
-    d = C // H
-    sc = d ** -0.5
-    g2, q2 = dctx.view(B * S, C), s.q.view(B * S, C)
-    dZ = _e(dctx, (H, B * S, Cv), BF16)
-    dwk, dwv = _e(dctx, (C, Cv), F32), _e(dctx, (C, Cv), F32)
-    for h in range(H):
-        hs = slice(h * d, (h + 1) * d)
-        K.gemm(GEMM_NN, g2[:, hs], wv[hs, :], out_bf16=dZ[h])                                   # dZ_h  = dctx_h Wv_h
-        K.gemm(GEMM_TN, g2[:, hs], s.Z[h], out_f32=dwv[hs, :])                                   # dWv_h = dctx_h^T Z_h
-    dbv = _e(dctx, (C,), F32)
-    K.colsum(g2, dbv)
-    dQp, dx = _e(dctx, (H, B * S, Cv), F32), _e(dctx, s.x.shape, F32)
-    K.xattn_t2i_flash_bwd(dZ.view(H, B, S, Cv), s.Qp.view(H, B, S, Cv), s.x, s.Z.view(H, B, S, Cv), s.lse.view(H, B, S),
-                          dQp.view(H, B, S, Cv), dx)
-    dQp_b = _e(dctx, dQp.shape, BF16)
-    K.cast(dQp, dQp_b)
-    dq = _e(dctx, (B * S, C), F32)
-    for h in range(H):
-        hs = slice(h * d, (h + 1) * d)
-        K.gemm(GEMM_NT, dQp_b[h], wk[hs, :], scale=sc, out_f32=dq[:, hs])                        # dq_h  = d^-1/2 dQp_h Wk_h^T
-        K.gemm(GEMM_TN, q2[:, hs], dQp_b[h], scale=sc, out_f32=dwk[hs, :])                       # dWk_h = d^-1/2 q_h^T dQp_h
-    return dq.view(B, S, C), dx, dwk, dwv, dbv
+def i2t_bwd(K, s, d_out_bf, cs_out, wq, bq, wp, bp, alpha, dalpha, dwq, dbq, dwp):
+    """d_out_bf [B*N, C] bf16 = gradient of `out`.  ACCUMULATES the parameter gradients into dalpha [1], dwq [C, C], dbq [C],
+    dwp [C, C] (f32: zero-filled tensors or slices of the gradient arena) and returns (d_lnc [B*N, C] bf16, dkv [B*S, 2C] f32).
+    cs_out [C] f32 = column sums of the gradient of `out` (the caller has them: they are also alpha^-1 times the gradient
+    of bp, which stays with the caller, like the gradient through xa)."""
+    B, N, H, S = s.B, s.N, s.H, s.S
+    C = s.lnc.shape[1]
+    HS = H * S
+    sc = HD ** -0.5
+    kv = s.kv
+    ldkv = kv.stride(0)
+    BF16 = d_out_bf.dtype
+    # dS = alpha * P * (dP - rowdot(P, dP)),  dP = d_out U^T ;  d alpha = sum rowdot ;  dbias1 = column sums of dS
+    dS = _e(d_out_bf, (B, N, HS), BF16)
+    dbias1 = _z(d_out_bf, (B, HS))
+    K.bgemm(GEMM_NT, N, HS, C, BV(d_out_bf, C, N * C), BV(s.U, C, HS * C), nb=(B, 1), scale_dev=alpha, aux=BV(s.P, HS, N * HS),
+            out_bf16=BV(dS, HS, N * HS), colsum=BV(dbias1, 0, HS), dot_out=dalpha, epilogue=EPI_DSOFTMAX32)
+    K.dot(cs_out, bp, dalpha, accumulate=True)        # the bias part of c = P U + bp:  d alpha += sum_n d_out[n] . bp
+    d_lnc = _e(d_out_bf, (B * N, C), BF16)
+    K.bgemm(GEMM_NN, N, C, HS, BV(dS, HS, N * HS), BV(s.Mt, C, HS * C), nb=(B, 1), out_bf16=BV(d_lnc, C, N * C))
+    # dU[b] = alpha * P[b]^T d_out[b] ;  dM[b] = dS[b]^T LN(a)[b]      (K = N tokens per clip, split-K + fp32 atomics)
+    dU, dM = _z(d_out_bf, (B, H, S, C)), _z(d_out_bf, (B, H, S, C))
+    K.bgemm(GEMM_TN, HS, C, N, BV(s.P, HS, N * HS), BV(d_out_bf, C, N * C), nb=(B, 1), scale_dev=alpha,
+            out_f32=BV(dU, C, HS * C), accumulate=True)
+    K.bgemm(GEMM_TN, HS, C, N, BV(dS, HS, N * HS), BV(s.lnc, C, N * C), nb=(B, 1), out_f32=BV(dM, C, HS * C), accumulate=True)
+    dU_b, dM_b = _e(dU, dU.shape, BF16), _e(dM, dM.shape, BF16)
+    K.cast(dU, dU_b)
+    K.cast(dM, dM_b)
+    # text side, one batch per (clip, head)
+    dkv = _e(d_out_bf, (B * S, 2 * C), F32)
+    bh = dict(nb=(H, B))
+    K.bgemm(GEMM_NT, S, HD, C, BV(dM_b, C, S * C, HS * C), BV(wq, wq.stride(0), HD * wq.stride(0), 0), scale=sc,
+            out_f32=BV(dkv, 2 * C, HD, S * 2 * C), **bh)                                   # dk_h  = d^-1/2 dM_h Wq_h^T
+    K.bgemm(GEMM_NN, S, HD, C, BV(dU_b, C, S * C, HS * C), BV(wp, wp.stride(0), HD, 0),
+            out_f32=BV(dkv[:, C:], 2 * C, HD, S * 2 * C), **bh)                            # dv_h  = dU_h Wp[:, h]
+    K.bgemm(GEMM_TN, HD, C, S, BV(kv, ldkv, HD, S * ldkv), BV(dM_b, C, S * C, HS * C), scale=sc,
+            out_f32=BV(dwq, C, HD * C, 0), accumulate=True, **bh)                          # dWq_h += d^-1/2 k_h^T dM_h
+    K.bgemm(GEMM_TN, C, HD, S, BV(dU_b, C, S * C, HS * C), BV(kv[:, C:], ldkv, HD, S * ldkv),
+            out_f32=BV(dwp, C, HD, 0), accumulate=True, **bh)                              # dWp[:, h] += dU_h^T v_h
+    # the query bias: scores += d^-1/2 bq_h . k_h  ->  dk_h += d^-1/2 dbias1 (x) bq_h ;  dbq_h += d^-1/2 k_h^T dbias1
+    K.xattn_qbias_bwd(kv, ldkv, bq, dbias1, sc, B, S, H, dk=dkv, lddk=2 * C, dbq=dbq)
+    return d_lnc, dkv
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def t2i_fwd(K, q, x_bf, wk, wv, bv, ox, B, N, H, p_drop=0.0, seed=0):
+    """q [B*S, C] bf16 (text query projection, bias included); x_bf [B*N, Cv] bf16 (un-normalised video stream entering
+    the video block); wk / wv [C, Cv] bf16; bv [C] f32; ox [B*S, C] bf16 is written with the merged heads' context
+    (the input of crossattention_t2i.output.dense).  p_drop > 0: dropout on the probabilities (roberta.py:313)."""
+    C = q.shape[1]
+    Cv = x_bf.shape[1]
+    S = q.shape[0] // B
+    HS = H * S
+    sc = HD ** -0.5
+    Np = (N + 7) // 8 * 8
+    BF16 = q.dtype
+    # ZQ[b, 0] = dZ (backward), ZQ[b, 1] = Qp: stacked so that dx = [P; dS]^T [dZ; Qp] is ONE product
+    ZQ = _e(q, (B, 2, HS, Cv), BF16)
+    Qp = ZQ[:, 1]
+    K.bgemm(GEMM_NN, S, Cv, HD, BV(q, C, HD, S * C), BV(wk, wk.stride(0), HD * wk.stride(0), 0), nb=(H, B), scale=sc,
+            out_bf16=BV(Qp, Cv, S * Cv, 2 * HS * Cv))
+    Sc = _e(q, (B, HS, Np), F32)
+    K.bgemm(GEMM_NT, HS, N, Cv, BV(Qp, Cv, 2 * HS * Cv), BV(x_bf, Cv, N * Cv), nb=(B, 1), out_f32=BV(Sc, Np, HS * Np))
+    PdS = _e(q, (B, 2, HS, Np), BF16)              # [b, 0] = P (after dropout), [b, 1] = dS (backward)
+    lse, rsum = _e(q, (B * HS,), F32), _e(q, (B * HS,), F32)
+    K.xattn_row_softmax(Sc, Np, B * HS, HS, HS * Np, N, PdS, Np, 2 * HS * Np, lse, p_drop, seed, rsum)
+    Zf = _z(q, (B, H, S, Cv))
+    K.bgemm(GEMM_NN, HS, Cv, N, BV(PdS, Np, 2 * HS * Np), BV(x_bf, Cv, N * Cv), nb=(B, 1), out_f32=BV(Zf, Cv, HS * Cv),
+            accumulate=True)
+    Z = _e(q, (B, H, S, Cv), BF16)
+    K.cast(Zf, Z)
+    # ctx[b*S+s, h] = Z[b,h,s,:] Wv_h^T + rowsum(P)[b,h,s] * bv_h   (row sum = 1 without dropout)
+    if p_drop > 0.0:
+        K.bgemm(GEMM_NT, S, HD, Cv, BV(Z, Cv, S * Cv, HS * Cv), BV(wv, wv.stride(0), HD * wv.stride(0), 0), nb=(H, B),
+                out_bf16=BV(ox, C, HD, S * C))
+        K.xattn_rowscale_bias(ox, rsum, bv, B, S, H)
+    else:
+        K.bgemm(GEMM_NT, S, HD, Cv, BV(Z, Cv, S * Cv, HS * Cv), BV(wv, wv.stride(0), HD * wv.stride(0), 0), nb=(H, B),
+                bias=BV(bv, 0, HD, 0), out_bf16=BV(ox, C, HD, S * C))
+    return types.SimpleNamespace(q=q, x=x_bf, ZQ=ZQ, Sc=Sc, PdS=PdS, lse=lse, rsum=rsum, Z=Z, B=B, N=N, H=H, S=S, Np=Np,
+                                 p_drop=p_drop, seed=seed)
+
+
+def t2i_bwd(K, s, d_ox, wk, wv, bv, dwk, dwv, dbv, dvideo):
+    """d_ox [B*S, C] bf16.  ACCUMULATES into dwk / dwv [C, Cv] and dbv [C] (f32; the key bias has an analytically zero
+    gradient), writes dvideo [B*N, Cv] f32 and returns dq [B*S, C] bf16."""
+    B, N, H, S, Np = s.B, s.N, s.H, s.S, s.Np
+    C = d_ox.shape[1]
+    Cv = s.x.shape[1]
+    HS = H * S
+    sc = HD ** -0.5
+    bh = dict(nb=(H, B))
+    BF16 = d_ox.dtype
+    dZ, Qp = s.ZQ[:, 0], s.ZQ[:, 1]
+    K.bgemm(GEMM_NN, S, Cv, HD, BV(d_ox, C, HD, S * C), BV(wv, wv.stride(0), HD * wv.stride(0), 0),
+            out_bf16=BV(dZ, Cv, S * Cv, 2 * HS * Cv), **bh)                                 # dZ_h  = d_ox_h Wv_h
+    K.bgemm(GEMM_TN, HD, Cv, S, BV(d_ox, C, HD, S * C), BV(s.Z, Cv, S * Cv, HS * Cv), out_f32=BV(dwv, Cv, HD * Cv, 0),
+            accumulate=True, **bh)                                                         # dWv_h += d_ox_h^T Z_h
+    if s.p_drop > 0.0:
+        K.xattn_rowscale_bias_bwd(d_ox, s.rsum, dbv, B, S, H)
+    else:
+        K.colsum(d_ox, dbv, accumulate=True)
+    dPf = _e(d_ox, (B, HS, Np), F32)
+    K.bgemm(GEMM_NT, HS, N, Cv, BV(dZ, Cv, 2 * HS * Cv), BV(s.x, Cv, N * Cv), nb=(B, 1), out_f32=BV(dPf, Np, HS * Np))
+    dS = s.PdS[:, 1]
+    crow = None
+    if s.p_drop > 0.0:
+        # with dropout the value bias no longer cancels in the softmax backward: dP += d_ox_h . bv_h (a row constant)
+        crow = _e(d_ox, (B, HS), F32)
+        K.xattn_qbias_fwd(d_ox, C, bv, None, 1.0, B, S, H, crow)
+    K.xattn_row_dsoftmax(s.Sc, Np, B * HS, HS, HS * Np, N, s.lse, dPf, Np, HS * Np, dS, Np, 2 * HS * Np, s.p_drop, s.seed,
+                         row_const=crow)
+    dQpf = _z(d_ox, (B, H, S, Cv))
+    K.bgemm(GEMM_NN, HS, Cv, N, BV(dS, Np, 2 * HS * Np), BV(s.x, Cv, N * Cv), nb=(B, 1), out_f32=BV(dQpf, Cv, HS * Cv),
+            accumulate=True)
+    dQp = _e(d_ox, (B, H, S, Cv), BF16)
+    K.cast(dQpf, dQp)
+    # dx[b] = P[b]^T dZ[b] + dS[b]^T Qp[b] = [P; dS][b]^T [dZ; Qp][b]
+    K.bgemm(GEMM_TN, N, Cv, 2 * HS, BV(s.PdS, Np, 2 * HS * Np), BV(s.ZQ, Cv, 2 * HS * Cv), nb=(B, 1), out_f32=BV(dvideo, Cv, N * Cv))
+    dq = _e(d_ox, (B * S, C), BF16)
+    K.bgemm(GEMM_NT, S, HD, Cv, BV(dQp, Cv, S * Cv, HS * Cv), BV(wk, wk.stride(0), HD * wk.stride(0), 0), scale=sc,
+            out_bf16=BV(dq, C, HD, S * C), **bh)                                            # dq_h  = d^-1/2 dQp_h Wk_h^T
+    K.bgemm(GEMM_TN, HD, Cv, S, BV(s.q, C, HD, S * C), BV(dQp, Cv, S * Cv, HS * Cv), scale=sc, out_f32=BV(dwk, Cv, HD * Cv, 0),
+            accumulate=True, **bh)                                                         # dWk_h += d^-1/2 q_h^T dQp_h
+    return dq

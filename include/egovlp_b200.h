@@ -86,6 +86,68 @@ void egv_gemm_set_cluster(int mode);
  * over {256,128}-wide tiles x split (default), 2 = also 192-wide tiles.  Env EGV_GEMM_PLAN sets the default. */
 void egv_gemm_set_plan(int mode);
 
+/* Batched GEMM with the softmax epilogues of the re-associated gated cross-attention -----------------------
+ * (video_transformer.py:155-185 video->text, roberta.py:470-486 text->video).
+ * D[z] = epilogue(A[z] x B[z]) for a two-level batch grid z = (z1, z0), z0 < nb0, z1 < nb1; operand / tensor X of batch z
+ * starts at X + z0 * sX0 + z1 * sX1 elements (a stride of 0 = shared by that level).  Layouts as in egv_gemm_bf16.
+ * Rows / reduction elements beyond a batch's own M, N, K read as zero (rank-4 TMA maps), so per-clip operands with
+ * N = 3137 tokens need no padding.  Epilogues:
+ *   EGV_BGEMM_EPI_NONE        v = acc + bias[n];  v = v * scale * (*scale_dev) + residual;  out_f32 (= or atomically +=),
+ *                             out_bf16
+ *   EGV_BGEMM_EPI_SOFTMAX32   every aligned group of 32 columns of a row (the 32 text keys of one head):
+ *                             v = softmax(acc + bias) -- the attention probabilities P (video_transformer.py:176-181)
+ *   EGV_BGEMM_EPI_DSOFTMAX32  backward of that softmax, aux = P (bf16): t = sum_group(P * acc);
+ *                             v = scale * (*scale_dev) * P * (acc - t);  colsum[n] += sum_m v;  dot_out[0] += sum t
+ * Row strides of every epilogue tensor must be multiples of 4 covering round_up(N, 4) (N itself may be odd: the tail
+ * group of 4 columns is written into the row padding).  split_k > 1 (or 1 with accumulate: chosen automatically) adds
+ * K slices with fp32 atomics. */
+enum { EGV_BGEMM_EPI_NONE = 0, EGV_BGEMM_EPI_SOFTMAX32 = 1, EGV_BGEMM_EPI_DSOFTMAX32 = 2 };
+typedef struct egv_bgemm_args {
+  int layout, M, N, K;               /* per batch */
+  int nb0, nb1;
+  const void* A; int64_t lda, sa0, sa1;     /* bf16 */
+  const void* B; int64_t ldb, sb0, sb1;     /* bf16 */
+  const float* bias; int64_t sbias0, sbias1;
+  float scale; const float* scale_dev;
+  const float* residual; int64_t ld_res, sres0, sres1;
+  float* out_f32; int64_t ld_out_f32, so32_0, so32_1;
+  void* out_bf16; int64_t ld_out_bf16, so16_0, so16_1;
+  const void* aux; int64_t ld_aux, saux0, saux1;   /* bf16 [M, N] per batch */
+  float* colsum; int64_t scol0, scol1;             /* f32 [N] per batch, += */
+  float* dot_out;                                  /* f32 [1], += */
+  int accumulate, split_k, epilogue;
+} egv_bgemm_args;
+int egv_bgemm_bf16(const egv_bgemm_args* args, egv_stream_t stream);
+
+/* Row-wise pieces of the re-associated cross-attention (csrc/xattn.cu) ------------------------------------------
+ * text -> video (roberta.py:470-486 with 281-321): scores f32 [rows, ld_s] hold, per (clip, head, text query) row, the
+ * n = N video-token scores; row r belongs to batch r / rows_per_batch (batch strides in elements).
+ * P = softmax(scores) (bf16), lse = log-sum-exp.  p_drop > 0 applies roberta.py:313's dropout to P with a Philox4x32-10
+ * stream keyed by (seed, r * n + column): P = keep ? P / (1 - p) : 0, rsum[r] = row sum of the result (1 without dropout). */
+int egv_xattn_row_softmax(const float* scores, int64_t ld_s, int64_t rows, int rows_per_batch, int64_t s_bstride, int n,
+                          void* P_bf16, int64_t ld_p, int64_t p_bstride, float* lse, float p_drop, uint64_t seed,
+                          float* rsum, egv_stream_t stream);
+/* dS = P * (dP~ - sum(P * dP~)), P recomputed from (scores, lse), dP~ = (dP + row_const[r]) * keep / (1 - p) (same Philox
+ * stream; row_const, may be NULL, carries the value-bias term d_ctx_h . bv_h, which cancels unless dropout is on) */
+int egv_xattn_row_dsoftmax(const float* scores, int64_t ld_s, int64_t rows, int rows_per_batch, int64_t s_bstride, int n,
+                           const float* lse, const float* dP, int64_t ld_dp, int64_t dp_bstride, void* dS_bf16,
+                           int64_t ld_ds, int64_t ds_bstride, float p_drop, uint64_t seed, const float* row_const,
+                           egv_stream_t stream);
+/* value bias under dropout: ox[b*S+s, h*64+j] (bf16, row stride ld) += rsum[b, h*S+s] * bv[h*64+j];  its backward:
+ * dbv[h*64+j] += sum_{b,s} rsum[b, h*S+s] * d_ox[b*S+s, h*64+j] */
+int egv_xattn_rowscale_bias(void* ox_bf16, int64_t ld, const float* rsum, const float* bv, int B, int S, int H,
+                            egv_stream_t stream);
+int egv_xattn_rowscale_bias_bwd(const void* d_ox_bf16, int64_t ld, const float* rsum, float* dbv, int B, int S, int H,
+                                egv_stream_t stream);
+/* video -> text (video_transformer.py:166-178): the query-bias term of the re-associated scores plus the key mask:
+ * out[b, h*S+s] = scale * sum_j k[b*S+s, h*64+j] * bq[h*64+j] + mask[b*S+s]   (k bf16, row stride ldk; head dim 64) */
+int egv_xattn_qbias_fwd(const void* k_bf16, int64_t ldk, const float* bq, const float* mask, float scale, int B, int S,
+                        int H, float* out, egv_stream_t stream);
+/* its backward: dk[b*S+s, h*64+j] += scale * dbias[b, h*S+s] * bq[h*64+j] (f32, row stride lddk; may be NULL);
+ * dbq[h*64+j] += scale * sum_{b,s} k[b*S+s, h*64+j] * dbias[b, h*S+s] (may be NULL) */
+int egv_xattn_qbias_bwd(const void* k_bf16, int64_t ldk, const float* bq, const float* dbias, float scale, int B, int S,
+                        int H, float* dk, int64_t lddk, float* dbq, egv_stream_t stream);
+
 /* LayerNorm ------------------------------------------------------------------------------------
  * nn.LayerNorm over the last dim C (video_transformer.py:196,207,210,115,304; roberta.py:161,336,417;
  * model.py:155; heads.py:41).  x is f32 or bf16 (x_is_bf16), y is written as bf16 and/or f32.

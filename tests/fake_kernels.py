@@ -387,48 +387,132 @@ class FakeKernels:
         if dv is not None:
             dv.copy_(vv.grad[grad_row0:grad_row0 + grad_rows])
 
-    # ------------------------------------------------------------------ re-associated cross-attention (round-2 kernels)
-    def xattn_scores_softmax(self, ln, Mt, c0, mask, P):
-        """P[b,n,h,:] = softmax_s(ln[b,n,:] . Mt[h,b,s,:] + c0[b,s,h] + mask[b,s])"""
-        self._launches += 1
-        s = torch.einsum("bnc,hbsc->bnhs", ln.float(), Mt.float()) + c0.float().permute(0, 2, 1)[:, None] + mask.float()[:, None, None, :]
-        P.copy_(torch.softmax(s, dim=-1))
+    # ------------------------------------------------------------------ batched GEMM / re-associated cross-attention
+    @staticmethod
+    def _bview(v, rows, cols, z0, z1):
+        t = v.t
+        return t.as_strided((rows, cols), (v.ld, 1), t.storage_offset() + z0 * v.s0 + z1 * v.s1)
 
-    def xattn_weighted_sum(self, P, U, out):
-        """out[b,n,:] = sum_{h,s} P[b,n,h,s] U[h,b,s,:]"""
+    def bgemm(self, layout, M, N, K, A, B, nb=(1, 1), bias=None, scale=1.0, scale_dev=None, residual=None, out_f32=None,
+              out_bf16=None, aux=None, colsum=None, dot_out=None, accumulate=False, split_k=1, epilogue=0):
+        """restatement of egv_bgemm_bf16 (include/egovlp_b200.h): one small matmul per batch"""
         self._launches += 1
-        out.copy_(torch.einsum("bnhs,hbsc->bnc", P.float(), U.float()))
+        sc = scale * (float(scale_dev.item()) if scale_dev is not None else 1.0)
+        for z1 in range(nb[1]):
+            for z0 in range(nb[0]):
+                if layout == GEMM_NT:
+                    v = self._bview(A, M, K, z0, z1).float() @ self._bview(B, N, K, z0, z1).float().t()
+                elif layout == GEMM_NN:
+                    v = self._bview(A, M, K, z0, z1).float() @ self._bview(B, K, N, z0, z1).float()
+                else:
+                    v = self._bview(A, K, M, z0, z1).float().t() @ self._bview(B, K, N, z0, z1).float()
+                if bias is not None:
+                    bt = bias.t
+                    v = v + bt.as_strided((N,), (1,), bt.storage_offset() + z0 * bias.s0 + z1 * bias.s1)
+                if epilogue == 1:
+                    v = torch.softmax(v.reshape(M, N // 32, 32), -1).reshape(M, N)
+                elif epilogue == 2:
+                    pr = self._bview(aux, M, N, z0, z1).float().reshape(M, N // 32, 32)
+                    dp = v.reshape(M, N // 32, 32)
+                    t = (pr * dp).sum(-1, keepdim=True)
+                    if dot_out is not None:
+                        dot_out.add_(t.sum())
+                    v = (pr * (dp - t)).reshape(M, N)
+                v = v * sc
+                if residual is not None:
+                    v = v + self._bview(residual, M, N, z0, z1)
+                if out_f32 is not None:
+                    o = self._bview(out_f32, M, N, z0, z1)
+                    if accumulate:
+                        o.add_(v)
+                    else:
+                        o.copy_(v)
+                if out_bf16 is not None:
+                    self._bview(out_bf16, M, N, z0, z1).copy_(v)
+                if colsum is not None:
+                    ct = colsum.t
+                    ct.as_strided((N,), (1,), ct.storage_offset() + z0 * colsum.s0 + z1 * colsum.s1).add_(v.sum(0))
 
-    def xattn_dscores(self, dc, U, P, dS, dbias):
-        """dP = dc . U^T; dS = P * (dP - sum_s dP * P); dbias[b,s,h] = sum_n dS[b,n,h,s]"""
-        self._launches += 1
-        p = P.float()
-        dP = torch.einsum("bnc,hbsc->bnhs", dc.float(), U.float())
-        ds = p * (dP - (dP * p).sum(-1, keepdim=True))
-        dS.copy_(ds)
-        dbias.copy_(ds.sum(1).permute(0, 2, 1))
+    @staticmethod
+    def philox_keep(seed, idx, p_drop):
+        """Philox4x32-10 keep decisions for the int64 element indices `idx` (any shape): the stream of csrc/xattn.cu"""
+        import numpy as np
+        i = idx.cpu().numpy().astype(np.uint64)
+        ctr = i >> np.uint64(2)
+        m32 = np.uint64(0xFFFFFFFF)
+        c0, c1 = ctr & m32, ctr >> np.uint64(32)
+        c2, c3 = np.zeros_like(c0), np.zeros_like(c0)
+        k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+        for _ in range(10):
+            p0, p1 = np.uint64(0xD2511F53) * c0, np.uint64(0xCD9E8D57) * c2
+            hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
+            c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+            k0, k1 = (k0 + np.uint64(0x9E3779B9)) & m32, (k1 + np.uint64(0xBB67AE85)) & m32
+        lane = i & np.uint64(3)
+        w = np.where(lane == 0, c0, np.where(lane == 1, c1, np.where(lane == 2, c2, c3)))
+        u = (w >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+        return torch.from_numpy(u >= np.float32(p_drop)).to(idx.device)
 
-    def xattn_tn(self, X, Y, out):
-        """out[h,b,s,:] = sum_n X[b,n,h,s] Y[b,n,:]"""
-        self._launches += 1
-        out.copy_(torch.einsum("bnhs,bnc->hbsc", X.float(), Y.float()))
+    def _keep_rows(self, rows, n, p_drop, seed, device):
+        idx = torch.arange(rows, dtype=torch.int64, device=device)[:, None] * n + torch.arange(n, dtype=torch.int64, device=device)[None]
+        return self.philox_keep(seed, idx, p_drop)
 
-    def xattn_t2i_flash(self, Qp, x, Z, lse):
-        """P[h,b,s,:] = softmax_n(Qp[h,b,s,:] . x[b,n,:]); Z = P x; lse = logsumexp of the scores"""
+    def xattn_row_softmax(self, scores, ld_s, rows, rows_per_batch, s_bstride, n, P, ld_p, p_bstride, lse, p_drop=0.0, seed=0,
+                          rsum=None):
         self._launches += 1
-        sc = torch.einsum("hbsc,bnc->hbsn", Qp.float(), x.float())
-        lse.copy_(torch.logsumexp(sc, dim=-1))
-        Z.copy_(torch.einsum("hbsn,bnc->hbsc", torch.softmax(sc, dim=-1), x.float()))
+        nb = rows // rows_per_batch
+        sv = scores.as_strided((nb, rows_per_batch, n), (s_bstride, ld_s, 1), scores.storage_offset()).float()
+        lse.reshape(-1)[:rows].copy_(torch.logsumexp(sv, -1).reshape(-1))
+        pr = torch.softmax(sv, -1)
+        if p_drop > 0:
+            keep = self._keep_rows(rows, n, p_drop, seed, scores.device).reshape(nb, rows_per_batch, n)
+            pr = pr * keep / (1.0 - p_drop)
+        P.as_strided((nb, rows_per_batch, n), (p_bstride, ld_p, 1), P.storage_offset()).copy_(pr)
+        if rsum is not None:
+            rsum.reshape(-1)[:rows].copy_((pr.sum(-1) if p_drop > 0 else torch.ones_like(pr[..., 0])).reshape(-1))
 
-    def xattn_t2i_flash_bwd(self, dZ, Qp, x, Z, lse, dQp, dx):
-        """dP = dZ x^T; dS = P * (dP - rowsum(dZ * Z)); dQp = dS x; dx = P^T dZ + dS^T Qp"""
+    def xattn_row_dsoftmax(self, scores, ld_s, rows, rows_per_batch, s_bstride, n, lse, dP, ld_dp, dp_bstride, dS, ld_ds,
+                           ds_bstride, p_drop=0.0, seed=0, row_const=None):
         self._launches += 1
-        xf, qf, dz = x.float(), Qp.float(), dZ.float()
-        p = torch.exp(torch.einsum("hbsc,bnc->hbsn", qf, xf) - lse.float()[..., None])
-        dP = torch.einsum("hbsc,bnc->hbsn", dz, xf)
-        dS = p * (dP - (dz * Z.float()).sum(-1, keepdim=True))
-        dQp.copy_(torch.einsum("hbsn,bnc->hbsc", dS, xf))
-        dx.copy_(torch.einsum("hbsn,hbsc->bnc", p, dz) + torch.einsum("hbsn,hbsc->bnc", dS, qf))
+        nb = rows // rows_per_batch
+        sv = scores.as_strided((nb, rows_per_batch, n), (s_bstride, ld_s, 1), scores.storage_offset()).float()
+        pr = torch.exp(sv - lse.reshape(-1)[:rows].reshape(nb, rows_per_batch, 1))
+        g = dP.as_strided((nb, rows_per_batch, n), (dp_bstride, ld_dp, 1), dP.storage_offset()).float()
+        if row_const is not None:
+            g = g + row_const.reshape(nb, rows_per_batch, 1)
+        if p_drop > 0:
+            keep = self._keep_rows(rows, n, p_drop, seed, scores.device).reshape(nb, rows_per_batch, n)
+            g = g * keep / (1.0 - p_drop)
+        ds = pr * (g - (pr * g).sum(-1, keepdim=True))
+        dS.as_strided((nb, rows_per_batch, n), (ds_bstride, ld_ds, 1), dS.storage_offset()).copy_(ds)
+
+    def xattn_rowscale_bias(self, ox, rsum, bv, B, S, H):
+        self._launches += 1
+        r = rsum.reshape(B, H, S).permute(0, 2, 1).reshape(B * S, H, 1)
+        ox.copy_((ox.float().reshape(B * S, H, 64) + r * bv.reshape(1, H, 64)).reshape(ox.shape))
+
+    def xattn_rowscale_bias_bwd(self, d_ox, rsum, dbv, B, S, H):
+        self._launches += 1
+        r = rsum.reshape(B, H, S).permute(0, 2, 1).reshape(B * S, H, 1)
+        dbv.add_((r * d_ox.float().reshape(B * S, H, 64)).sum(0).reshape(-1))
+
+    def xattn_qbias_fwd(self, k, ldk, bq, mask, scale, B, S, H, out):
+        self._launches += 1
+        kk = k.as_strided((B * S, H, 64), (ldk, 64, 1), k.storage_offset()).float()
+        v = scale * (kk * bq.reshape(1, H, 64)).sum(-1)            # [B*S, H]
+        v = v.reshape(B, S, H).permute(0, 2, 1)
+        if mask is not None:
+            v = v + mask.reshape(B, 1, S)
+        out.reshape(B, H, S).copy_(v)
+
+    def xattn_qbias_bwd(self, k, ldk, bq, dbias, scale, B, S, H, dk=None, lddk=0, dbq=None):
+        self._launches += 1
+        g = scale * dbias.reshape(B, H, S).permute(0, 2, 1).reshape(B * S, H, 1)      # [B*S, H, 1]
+        if dk is not None:
+            dk.as_strided((B * S, H, 64), (lddk, 64, 1), dk.storage_offset()).add_(g * bq.reshape(1, H, 64))
+        if dbq is not None:
+            kk = k.as_strided((B * S, H, 64), (ldk, 64, 1), k.storage_offset()).float()
+            dbq.reshape(H, 64).add_((g * kk).sum(0))
 
     # ------------------------------------------------------------------ optimiser
     def adamw(self, p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, hyper_dev=None):

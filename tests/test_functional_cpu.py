@@ -62,19 +62,26 @@ def mask_bias(lens):
     return am, O.extended_mask(am).reshape(len(lens), S).contiguous()
 
 
-@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("fused", [False, True, "reassoc", "legacy32"])
 def test_video_block(sd, mode, fused):
+    """fused = True: text length 8 (round-1 formulation of the gated cross-attention); 'reassoc': the BASELINE text length
+    32, which takes the re-associated batched-GEMM path (xattn_reassoc.py); 'legacy32': the same with that path off."""
     K = FakeKernels()
     prefix = "video_model.blocks.6."
+    S = 32 if fused in ("reassoc", "legacy32") else globals()["S"]
+    Fn.set_reassoc(fused != "legacy32")
     names = Fn.VIDEO_BLOCK_PARAMS + (Fn.VIDEO_FUSE_PARAMS if fused else [])
     p = block_params(sd, prefix, names)
     w = operand_copies(p)
     g = torch.Generator().manual_seed(0)
     x = torch.randn(B, N, C, generator=g)
     y = torch.randn(B, S, C, generator=g) if fused else None
-    am, yb = mask_bias([S, 5, 3])
+    am = (torch.arange(S)[None] < torch.tensor([S, 5, 3])[:, None]).long()
+    yb = O.extended_mask(am).reshape(B, S).contiguous()
     d_out = torch.randn(B, N, C, generator=g)
     out, saved = Fn.video_block_fwd(K, x, p, w, HEADS, T, NF, y=y, y_bias=yb if fused else None)
+    assert (not fused) or saved.reassoc == (fused == "reassoc")
+    Fn.set_reassoc(True)
     dx, dy, grads = Fn.video_block_bwd(K, saved, d_out, p, w, HEADS, T, NF)
     # oracle
     sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
@@ -301,43 +308,52 @@ def test_fused_blocks_at_large_width(monkeypatch):
         Fn.BF16 = old
 
 
-def test_reassociated_i2t_core(sd, mode):
-    """egovlpv2_b200/xattn_reassoc.py (round-2 path): the hand-derived forward / backward of the re-associated
-    video->text cross-attention core == autograd through the reference formulation (q projection, 32-key masked softmax
-    attention, output projection: video_transformer.py:165-183), for every input and parameter gradient."""
+def test_reassociated_i2t(sd, mode):
+    """egovlpv2_b200/xattn_reassoc.py: the hand-derived forward / backward of the re-associated gated video->text
+    cross-attention (batched GEMMs + group-softmax epilogues) == autograd through the reference formulation (q projection,
+    32-key masked softmax attention, output projection, gate: video_transformer.py:165-185), for every input and
+    parameter gradient.  The re-associated kernels need the BASELINE text length S = 32."""
     from egovlpv2_b200 import xattn_reassoc as XR
     K = FakeKernels()
     prefix = "video_model.blocks.6.attn."
     d = C // HEADS
+    S32 = 32
     g = torch.Generator().manual_seed(17)
     ln = torch.randn(B, N, C, generator=g)
-    kv = torch.randn(B, S, 2 * C, generator=g)
-    am, mask = mask_bias([S, 5, 3])
-    dc = torch.randn(B, N, C, generator=g)
+    kv = torch.randn(B, S32, 2 * C, generator=g)
+    xa = torch.randn(B, N, C, generator=g)
+    am = (torch.arange(S32)[None] < torch.tensor([S32, 5, 19])[:, None]).long()
+    mask = O.extended_mask(am).reshape(B, S32).contiguous()
+    dout = torch.randn(B, N, C, generator=g)
     wq, bq = sd[prefix + "qkv_i2t.weight"], sd[prefix + "qkv_i2t.bias"]
     wp, bp = sd[prefix + "proj_i2t.weight"], sd[prefix + "proj_i2t.bias"]
+    alpha = torch.tensor([0.7])
     cast = lambda t: t.to(Fn.BF16)  # noqa: E731
-    c, saved = XR.i2t_core_fwd(K, cast(ln), cast(kv), mask, cast(wq), bq, cast(wp), bp, HEADS)
-    dln, dkv, dwq, dbq, dwp, dbp = XR.i2t_core_bwd(K, saved, cast(dc), cast(wq), cast(wp))
+    out = torch.empty(B * N, C)
+    saved = XR.i2t_fwd(K, cast(ln).reshape(B * N, C), cast(kv).reshape(B * S32, 2 * C), mask, cast(wq), bq, cast(wp), bp, alpha,
+                       xa.reshape(B * N, C), out, B, N, HEADS)
+    dalpha, dwq, dbq, dwp = torch.zeros(1), torch.zeros(C, C), torch.zeros(C), torch.zeros(C, C)
+    dln, dkv = XR.i2t_bwd(K, saved, cast(dout).reshape(B * N, C), dout.reshape(B * N, C).sum(0), cast(wq), bq, cast(wp), bp, alpha,
+                          dalpha, dwq, dbq, dwp)
     # reference formulation under autograd
-    r = {k: v.clone().requires_grad_(True) for k, v in dict(ln=ln, kv=kv, wq=wq, bq=bq, wp=wp, bp=bp).items()}
+    r = {k: v.clone().requires_grad_(True) for k, v in dict(ln=ln, kv=kv, wq=wq, bq=bq, wp=wp, bp=bp, alpha=alpha).items()}
     q = O._heads(torch.nn.functional.linear(r["ln"], r["wq"], r["bq"]), HEADS) * d ** -0.5
     k_t, v_t = (O._heads(t, HEADS) for t in r["kv"].split(C, dim=-1))
-    sc = q @ k_t.transpose(-1, -2) + mask.reshape(B, 1, 1, S)
-    ref = torch.nn.functional.linear(O._merge(torch.softmax(sc, dim=-1) @ v_t), r["wp"], r["bp"])
-    ref.backward(dc)
-    assert rel(c, ref) <= tol(mode), rel(c, ref)
-    for name, got in (("ln", dln), ("kv", dkv), ("wq", dwq), ("bq", dbq), ("wp", dwp), ("bp", dbp)):
+    sc = q @ k_t.transpose(-1, -2) + mask.reshape(B, 1, 1, S32)
+    ref = xa + r["alpha"] * torch.nn.functional.linear(O._merge(torch.softmax(sc, dim=-1) @ v_t), r["wp"], r["bp"])
+    ref.backward(dout)
+    assert rel(out.reshape(B, N, C), ref) <= tol(mode), rel(out.reshape(B, N, C), ref)
+    for name, got in (("ln", dln), ("kv", dkv), ("wq", dwq), ("bq", dbq), ("wp", dwp), ("alpha", dalpha)):
         e = rel(got.reshape(-1), r[name].grad.reshape(-1))
         assert e <= tol(mode, True), (name, e)
-    # the real library does not have the four fused kernels yet: the module must fail loudly, not fall back
-    from egovlpv2_b200 import lib as L
-    assert not hasattr(L.Kernels, "xattn_scores_softmax")
 
 
-def test_reassociated_t2i_core(sd, mode):
-    """xattn_reassoc.t2i_core_*: text queries over all N video tokens without projecting the tokens to keys / values
-    == autograd through the reference formulation (roberta.py:257-327 with encoder_hidden_states = video, no mask)."""
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_reassociated_t2i(sd, mode, p_drop):
+    """xattn_reassoc.t2i_*: text queries over all N video tokens without projecting the tokens to keys / values
+    == autograd through the reference formulation (roberta.py:257-327 with encoder_hidden_states = video, no mask),
+    with and without the dropout on the attention probabilities (roberta.py:313; the reference formulation replays the
+    Philox mask of the kernels)."""
     from egovlpv2_b200 import xattn_reassoc as XR
     K = FakeKernels()
     prefix = "text_model.encoder.layer.6.crossattention_t2i.self."
@@ -349,16 +365,24 @@ def test_reassociated_t2i_core(sd, mode):
     wk, bk = sd[prefix + "key.weight"], sd[prefix + "key.bias"]
     wv, bv = sd[prefix + "value.weight"], sd[prefix + "value.bias"]
     cast = lambda t: t.to(Fn.BF16)  # noqa: E731
-    ctx, saved = XR.t2i_core_fwd(K, cast(q), cast(x), cast(wk), cast(wv), bv, HEADS)
-    dq, dx, dwk, dwv, dbv = XR.t2i_core_bwd(K, saved, cast(dctx), cast(wk), cast(wv))
+    ox = torch.empty(B * S, C, dtype=Fn.BF16)
+    saved = XR.t2i_fwd(K, cast(q).reshape(B * S, C), cast(x).reshape(B * N, C), cast(wk), cast(wv), bv, ox, B, N, HEADS,
+                       p_drop=p_drop, seed=77)
+    dwk, dwv, dbv, dx = torch.zeros(C, C), torch.zeros(C, C), torch.zeros(C), torch.empty(B * N, C)
+    dq = XR.t2i_bwd(K, saved, cast(dctx).reshape(B * S, C), cast(wk), cast(wv), bv, dwk, dwv, dbv, dx)
     r = {k: v.clone().requires_grad_(True) for k, v in dict(q=q, x=x, wk=wk, bk=bk, wv=wv, bv=bv).items()}
     lin = torch.nn.functional.linear
     qh = O._heads(r["q"], HEADS)
     kh, vh = O._heads(lin(r["x"], r["wk"], r["bk"]), HEADS), O._heads(lin(r["x"], r["wv"], r["bv"]), HEADS)
-    ref = O._merge(torch.softmax(qh @ kh.transpose(-1, -2) / d ** 0.5, dim=-1) @ vh)
+    pr = torch.softmax(qh @ kh.transpose(-1, -2) / d ** 0.5, dim=-1)          # [B, H, S, N]
+    if p_drop > 0:
+        rows = torch.arange(B * HEADS * S).reshape(B, HEADS, S, 1)                 # kernel row order: (clip, head, query)
+        keep = FakeKernels.philox_keep(77, rows * N + torch.arange(N), p_drop)
+        pr = pr * keep / (1 - p_drop)
+    ref = O._merge(pr @ vh)
     ref.backward(dctx)
-    assert rel(ctx, ref) <= tol(mode), rel(ctx, ref)
+    assert rel(ox.reshape(B, S, C), ref) <= tol(mode), rel(ox.reshape(B, S, C), ref)
     for name, got in (("q", dq), ("x", dx), ("wk", dwk), ("wv", dwv), ("bv", dbv)):
         e = rel(got.reshape(-1), r[name].grad.reshape(-1))
         assert e <= tol(mode, True), (name, e)
-    assert r["bk"].grad.abs().max().item() <= 1e-5          # the key bias is softmax-invariant: nothing to back-propagate
+    assert r["bk"].grad.abs().max().item() <= 1e-5 or p_drop > 0    # the key bias is softmax-invariant without dropout

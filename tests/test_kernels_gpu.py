@@ -631,3 +631,197 @@ def test_adamw(K, R):
         st.append((p, m, v, p16))
     for a, r in zip(*st):
         check(a, r, 4e-3 if a.dtype == torch.bfloat16 else 1e-5, "adamw")
+
+
+# ------------------------------------------------------------------------------------------- batched GEMM (csrc/xgemm.cu)
+from egovlpv2_b200.lib import BV, EPI_DSOFTMAX32, EPI_NONE, EPI_SOFTMAX32, GEMM_NN, GEMM_NT, GEMM_TN  # noqa: E402
+
+
+def _both(K, R, fn):
+    """run `fn(kernels)` (which returns the output tensors it allocated) on the CUDA library and on the restatement"""
+    return fn(K), fn(R)
+
+
+def test_bgemm_group_softmax_epilogue_per_clip(K, R):
+    """P[b] = softmax32(A[b] Mt[b]^T + bias[b]): per-clip operands, 300 rows per clip (row tail inside every batch:
+    rows past a clip's own M must come back as TMA zero fill, not as the next clip's rows), H*S = 384 columns."""
+    B, N, HS, C = 3, 300, 384, 768
+    A, Mt = rnd(B * N, C, seed=1), rnd(B, HS, C, scale=0.05, seed=2)
+    bias = rnd(B, HS, dtype=torch.float32, seed=3)
+    bias[1, 40:64] = torch.finfo(torch.float32).min        # masked keys of one clip (Q13)
+
+    def run(k):
+        P = torch.full((B, N + 5, HS), 7.0, dtype=torch.bfloat16, device=DEV)   # 5 guard rows per clip must stay untouched
+        k.bgemm(GEMM_NT, N, HS, C, BV(A, C, N * C), BV(Mt, C, HS * C), nb=(B, 1), bias=BV(bias, 0, HS),
+                out_bf16=BV(P, HS, (N + 5) * HS), epilogue=EPI_SOFTMAX32)
+        return P
+    got, ref = _both(K, R, run)
+    check(got[:, :N], ref[:, :N], 6e-3, "softmax32")
+    assert (got[:, N:] == 7.0).all(), "rows past a batch's M were written"
+    s = got[:, :N].float().reshape(B, N, HS // 32, 32).sum(-1)
+    assert (s - 1).abs().max().item() < 2e-2
+    assert got[1, :N, 40:64].abs().max().item() == 0.0
+
+
+def test_bgemm_softmax_backward_epilogue(K, R):
+    B, N, HS, C = 2, 261, 384, 768
+    dO, U = rnd(B * N, C, seed=4), rnd(B, HS, C, scale=0.05, seed=5)
+    P = torch.softmax(rnd(B, N, HS // 32, 32, dtype=torch.float32, seed=6), -1).reshape(B, N, HS).to(torch.bfloat16)
+    alpha = torch.tensor([0.37], device=DEV)
+
+    def run(k):
+        dS = torch.zeros(B, N, HS, dtype=torch.bfloat16, device=DEV)
+        dbias, dalpha = torch.zeros(B, HS, device=DEV), torch.zeros(1, device=DEV)
+        k.bgemm(GEMM_NT, N, HS, C, BV(dO, C, N * C), BV(U, C, HS * C), nb=(B, 1), scale_dev=alpha, aux=BV(P, HS, N * HS),
+                out_bf16=BV(dS, HS, N * HS), colsum=BV(dbias, 0, HS), dot_out=dalpha, epilogue=EPI_DSOFTMAX32)
+        return dS, dbias, dalpha
+    (dS, db, da), (dS_r, db_r, da_r) = _both(K, R, run)
+    check(dS, dS_r, 8e-3, "dsoftmax32 dS")
+    check(db, db_r, 2e-2, "dsoftmax32 colsum", atol=2e-2)
+    check(da, da_r, 1e-3, "dsoftmax32 dot")
+
+
+def test_bgemm_head_batches_and_residual(K, R):
+    """batches = (clip, head) pairs addressed as column slices of a [B*S, 2C] tensor (batch stride 64 elements along a
+    row), shared weights (batch stride 0 in the clip level), K = 64 / K = 32 reductions, strided column-slice outputs,
+    accumulation over the clip level into a shared output."""
+    B, S, H, C = 2, 32, 12, 768
+    kv, wq = rnd(B * S, 2 * C, seed=7), rnd(C, C, scale=0.05, seed=8)
+    dM = rnd(B, H, S, C, seed=9)
+    bv = rnd(C, dtype=torch.float32, seed=10)
+
+    def run(k):
+        Mt = torch.zeros(B, H, S, C, dtype=torch.bfloat16, device=DEV)
+        k.bgemm(GEMM_NN, S, C, 64, BV(kv, 2 * C, 64, S * 2 * C), BV(wq, C, 64 * C, 0), nb=(H, B), scale=0.125,
+                out_bf16=BV(Mt, C, S * C, H * S * C))
+        U = torch.zeros(B, H, S, C, dtype=torch.bfloat16, device=DEV)
+        k.bgemm(GEMM_NT, S, C, 64, BV(kv[:, C:], 2 * C, 64, S * 2 * C), BV(wq, C, 64, 0), nb=(H, B), out_bf16=BV(U, C, S * C, H * S * C))
+        dk = torch.zeros(B * S, 2 * C, device=DEV)
+        k.bgemm(GEMM_NT, S, 64, C, BV(dM, C, S * C, H * S * C), BV(wq, C, 64 * C, 0), nb=(H, B), scale=0.125,
+                bias=BV(bv, 0, 64, 0), out_f32=BV(dk, 2 * C, 64, S * 2 * C))
+        k.bgemm(GEMM_NN, S, 64, C, BV(dM, C, S * C, H * S * C), BV(wq, C, 64, 0), nb=(H, B), out_f32=BV(dk[:, C:], 2 * C, 64, S * 2 * C))
+        dwq = torch.zeros(C, C, device=DEV)
+        k.bgemm(GEMM_TN, 64, C, S, BV(kv, 2 * C, 64, S * 2 * C), BV(dM, C, S * C, H * S * C), nb=(H, B), scale=0.125,
+                out_f32=BV(dwq, C, 64 * C, 0), accumulate=True)
+        dwp = torch.zeros(C, C, device=DEV)
+        k.bgemm(GEMM_TN, C, 64, S, BV(dM, C, S * C, H * S * C), BV(kv[:, C:], 2 * C, 64, S * 2 * C), nb=(H, B),
+                out_f32=BV(dwp, C, 64, 0), accumulate=True)
+        return Mt, U, dk, dwq, dwp
+    for name, a, b in zip(("Mt", "U", "dk|dv", "dwq", "dwp"), *_both(K, R, run)):
+        check(a, b, 6e-3, "head batches " + name)
+
+
+def test_bgemm_per_clip_reductions_over_tokens(K, R):
+    """K = tokens of one clip (3137 is odd: the reduction tail of clip b must not read clip b+1), odd N with a padded
+    row stride, split-K accumulation, residual + gate epilogue."""
+    B, N, HS, C = 2, 1201, 384, 768
+    Np = (N + 7) // 8 * 8
+    P = torch.softmax(rnd(B, N, HS // 32, 32, dtype=torch.float32, seed=11), -1).reshape(B, N, HS).to(torch.bfloat16)
+    dO, x = rnd(B * N, C, seed=12), rnd(B * N, C, seed=13)
+    Qp = rnd(B, HS, C, scale=0.05, seed=14)
+    xa = rnd(B * N, C, dtype=torch.float32, seed=15)
+    bp = rnd(C, dtype=torch.float32, seed=16)
+    alpha = torch.tensor([0.5], device=DEV)
+
+    def run(k):
+        dU = torch.zeros(B, HS, C, device=DEV)
+        k.bgemm(GEMM_TN, HS, C, N, BV(P, HS, N * HS), BV(dO, C, N * C), nb=(B, 1), scale_dev=alpha, out_f32=BV(dU, C, HS * C),
+                accumulate=True)
+        Sc = torch.full((B, HS, Np), -5.0, device=DEV)
+        k.bgemm(GEMM_NT, HS, N, C, BV(Qp, C, HS * C), BV(x, C, N * C), nb=(B, 1), out_f32=BV(Sc, Np, HS * Np))
+        Pt = torch.zeros(B, HS, Np, dtype=torch.bfloat16, device=DEV)
+        Pt[:, :, :N] = torch.softmax(Sc[:, :, :N], -1)
+        Z = torch.zeros(B, HS, C, device=DEV)
+        k.bgemm(GEMM_NN, HS, C, N, BV(Pt, Np, HS * Np), BV(x, C, N * C), nb=(B, 1), out_f32=BV(Z, C, HS * C), accumulate=True)
+        dx = torch.zeros(B * N, C, device=DEV)
+        k.bgemm(GEMM_TN, N, C, HS, BV(Pt, Np, HS * Np), BV(Qp, C, HS * C), nb=(B, 1), out_f32=BV(dx, C, N * C))
+        out = torch.zeros(B * N, C, device=DEV)
+        k.bgemm(GEMM_NN, N, C, HS, BV(P, HS, N * HS), BV(Qp, C, HS * C), nb=(B, 1), bias=BV(bp, 0, 0), scale_dev=alpha,
+                residual=BV(xa, C, N * C), out_f32=BV(out, C, N * C))
+        return dU, Sc[:, :, :N].contiguous(), Z, dx, out
+    for name, a, b in zip(("dU", "scores", "Z", "dx", "gated residual"), *_both(K, R, run)):
+        check(a, b, 6e-3, "per-clip " + name)
+
+
+def test_xattn_row_kernels(K, R):
+    B, HS, N = 2, 384, 3137
+    Np = (N + 7) // 8 * 8
+    Sc = rnd(B, HS, Np, dtype=torch.float32, scale=3.0, seed=21)
+    dP = rnd(B, HS, Np, dtype=torch.float32, seed=22)
+    rc = rnd(B, HS, dtype=torch.float32, seed=23)
+    for p_drop in (0.0, 0.1):
+        def run(k):
+            PdS = torch.zeros(B, 2, HS, Np, dtype=torch.bfloat16, device=DEV)
+            lse, rsum = torch.zeros(B * HS, device=DEV), torch.zeros(B * HS, device=DEV)
+            k.xattn_row_softmax(Sc, Np, B * HS, HS, HS * Np, N, PdS, Np, 2 * HS * Np, lse, p_drop, 1234, rsum)
+            k.xattn_row_dsoftmax(Sc, Np, B * HS, HS, HS * Np, N, lse, dP, Np, HS * Np, PdS[:, 1], Np, 2 * HS * Np, p_drop, 1234,
+                                 row_const=rc if p_drop > 0 else None)
+            return PdS[:, 0, :, :N].contiguous(), PdS[:, 1, :, :N].contiguous(), lse, rsum
+        (P, dS, lse, rs), (P_r, dS_r, lse_r, rs_r) = _both(K, R, run)
+        # the dropout masks must be IDENTICAL (same Philox stream): compare the zero patterns exactly
+        assert ((P == 0) == (P_r == 0)).all(), "dropout mask differs from the Philox restatement"
+        if p_drop > 0:
+            frac = (P == 0).float().mean().item()
+            assert abs(frac - p_drop) < 0.01, frac
+        check(P, P_r, 6e-3, "row softmax p=%g" % p_drop)
+        check(dS, dS_r, 8e-3, "row dsoftmax p=%g" % p_drop)
+        check(lse, lse_r, 1e-5, "lse")
+        check(rs, rs_r, 5e-3, "rsum")
+    # query-bias kernels and the value bias under dropout
+    Bc, S, H, C = 3, 32, 12, 768
+    kv = rnd(Bc * S, 2 * C, seed=24)
+    bq = rnd(C, dtype=torch.float32, seed=25)
+    mask = torch.zeros(Bc, S, device=DEV)
+    mask[1, 20:] = torch.finfo(torch.float32).min
+    dbias = rnd(Bc, H * S, dtype=torch.float32, seed=26)
+    rsum = rnd(Bc, H * S, dtype=torch.float32, seed=27)
+    ox0 = rnd(Bc * S, C, seed=28)
+
+    def run2(k):
+        out = torch.zeros(Bc, H * S, device=DEV)
+        k.xattn_qbias_fwd(kv, 2 * C, bq, mask, 0.125, Bc, S, H, out)
+        dk, dbq = torch.ones(Bc * S, 2 * C, device=DEV), torch.zeros(C, device=DEV)
+        k.xattn_qbias_bwd(kv, 2 * C, bq, dbias, 0.125, Bc, S, H, dk=dk, lddk=2 * C, dbq=dbq)
+        ox, dbv = ox0.clone(), torch.zeros(C, device=DEV)
+        k.xattn_rowscale_bias(ox, rsum, bq, Bc, S, H)
+        k.xattn_rowscale_bias_bwd(ox0, rsum, dbv, Bc, S, H)
+        return out, dk, dbq, ox, dbv
+    for name, a, b in zip(("qbias", "dk", "dbq", "rowscale", "dbv"), *_both(K, R, run2)):
+        check(a, b, 6e-3 if name == "rowscale" else 2e-4, name)
+
+
+def test_reassociated_cross_attention_full_size(K, R):
+    """xattn_reassoc at the BASELINE shapes (N = 3137 tokens per clip, C = 768, 12 heads, S = 32; 2 clips): the CUDA
+    kernels against the restatement running the very same sequencing, forward and every gradient, both directions."""
+    from egovlpv2_b200 import xattn_reassoc as XR
+    B, N, C, H, S = 2, 3137, 768, 12, 32
+    lnc, kv = rnd(B * N, C, seed=31), rnd(B * S, 2 * C, seed=32)
+    wq, wp = rnd(C, C, scale=0.03, seed=33), rnd(C, C, scale=0.03, seed=34)
+    bq, bp = rnd(C, dtype=torch.float32, scale=0.1, seed=35), rnd(C, dtype=torch.float32, scale=0.1, seed=36)
+    xa, dout = rnd(B * N, C, dtype=torch.float32, seed=37), rnd(B * N, C, seed=38)
+    mask = torch.zeros(B, S, device=DEV)
+    mask[1, 11:] = torch.finfo(torch.float32).min
+    alpha = torch.tensor([0.5], device=DEV)
+
+    def run_i2t(k):
+        out = torch.empty(B * N, C, device=DEV)
+        s = XR.i2t_fwd(k, lnc, kv, mask, wq, bq, wp, bp, alpha, xa, out, B, N, H)
+        da, dwq, dbq, dwp = (torch.zeros(n, device=DEV) for n in ((1,), (C, C), (C,), (C, C)))
+        dln, dkv = XR.i2t_bwd(k, s, dout, dout.float().sum(0), wq, bq, wp, bp, alpha, da, dwq, dbq, dwp)
+        return out, s.P, dln, dkv, da, dwq, dbq, dwp
+    for name, a, b in zip(("out", "P", "dln", "dkv", "dalpha", "dwq", "dbq", "dwp"), *_both(K, R, run_i2t)):
+        check(a, b, 1.5e-2, "i2t " + name)
+    q, x = rnd(B * S, C, seed=41), rnd(B * N, C, seed=42)
+    wk, wv = rnd(C, C, scale=0.03, seed=43), rnd(C, C, scale=0.03, seed=44)
+    bv = rnd(C, dtype=torch.float32, scale=0.1, seed=45)
+    dox = rnd(B * S, C, seed=46)
+    for p_drop in (0.0, 0.1):
+        def run_t2i(k):
+            ox = torch.empty(B * S, C, dtype=torch.bfloat16, device=DEV)
+            s = XR.t2i_fwd(k, q, x, wk, wv, bv, ox, B, N, H, p_drop=p_drop, seed=99)
+            dwk, dwv, dbv = (torch.zeros(n, device=DEV) for n in ((C, C), (C, C), (C,)))
+            dx = torch.empty(B * N, C, device=DEV)
+            dq = XR.t2i_bwd(k, s, dox, wk, wv, bv, dwk, dwv, dbv, dx)
+            return ox, dq, dx, dwk, dwv, dbv
+        for name, a, b in zip(("ox", "dq", "dx", "dwk", "dwv", "dbv"), *_both(K, R, run_t2i)):
+            check(a, b, 1.5e-2, "t2i p=%g %s" % (p_drop, name))

@@ -40,15 +40,21 @@ def rel(a, b):
 
 
 def _oracle(O, data, sd, plan, tasks, autocast):
-    sdg = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
-    with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
-        out = O.pretrain_step(data, sdg, 12, 12, 6, plan, tasks=tasks)
-    # loss scaling as GradScaler does it (2^16 start value): fp16 backward without underflow; unscaled afterwards
+    # fp16 backward needs loss scaling; GradScaler starts at 2^16 and halves on every overflow -- same rule here
     scale = 65536.0 if autocast else 1.0
-    (out["loss_total"].float() * scale).backward()
-    grads = {k: (sdg[k].grad / scale) for k in GRAD_KEYS if k in sdg and sdg[k].grad is not None}
+    while True:
+        sdg = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+        with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+            out = O.pretrain_step(data, sdg, 12, 12, 6, plan, tasks=tasks)
+        (out["loss_total"].float() * scale).backward()
+        grads = {k: (sdg[k].grad / scale) for k in GRAD_KEYS if k in sdg and sdg[k].grad is not None}
+        if all(bool(torch.isfinite(g).all()) for g in grads.values()) or scale <= 1.0:
+            break
+        scale /= 2.0
+        del sdg, out, grads
     keep = {k: out[k].detach().float() for k in ("EgoNCE", "loss_mlm", "loss_itm", "loss_total", "sim_v2t", "text_embeds",
                                                   "video_embeds", "cross_attn_itm_logits") if k in out}
+    keep["_loss_scale"] = scale
     if "cross_attn_mlm_logits" in out:
         keep["mlm_logits_slice"] = out["cross_attn_mlm_logits"].detach().float()[:, :, ::97].contiguous()
     return keep, grads
@@ -85,7 +91,8 @@ def report(cfg_id=3, B=2, S=32, seed=0):
         mine["cross_attn_itm_logits"] = ret["cross_attn_itm_logits"].float()
         mine["mlm_logits_slice"] = ret["cross_attn_mlm_logits"].float()[:, :, ::97]
     params = dict(model.named_parameters())
-    out = {"cfg": cfg_id, "B": B, "T": c["T"], "tasks": c["tasks"], "loss": {}, "tensors": {}, "grads": {}}
+    out = {"cfg": cfg_id, "B": B, "T": c["T"], "tasks": c["tasks"], "fp16_loss_scale": h16["_loss_scale"], "loss": {}, "tensors": {},
+           "grads": {}}
     for k in ("EgoNCE", "loss_mlm", "loss_itm", "loss_total"):
         if k in ref:
             r = float(ref[k])
