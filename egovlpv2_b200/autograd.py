@@ -45,12 +45,15 @@ def _f32c(t):
 
 
 class VideoBlockFn(torch.autograd.Function):
+    """`Mt, U, bias1`: None, or the text-side preparation of the re-associated gated cross-attention (I2TPrepFn); their
+    gradients are returned to that node."""
+
     @staticmethod
-    def forward(ctx, cfg, w, x, y, y_bias, *params):
+    def forward(ctx, cfg, w, x, y, y_bias, Mt, U, bias1, *params):
         p = _pdict(cfg.names, params)
-        save = torch.is_grad_enabled() or any(ctx.needs_input_grad)
-        out, s = F_.video_block_fwd(_K(), _f32c(x), p, w, cfg.H, cfg.T, cfg.Nf, y=None if y is None else _f32c(y),
-                                    y_bias=y_bias, eps=cfg.eps, save=True)
+        prep = None if Mt is None else (Mt.detach(), U.detach(), bias1.detach())
+        out, s = F_.video_block_fwd(_K(), _f32c(x), p, w, cfg.H, cfg.T, cfg.Nf, y=None if (y is None or prep is not None) else _f32c(y),
+                                    y_bias=y_bias, eps=cfg.eps, save=True, prep=prep)
         ctx.cfg, ctx.w, ctx.s, ctx.p = cfg, w, s, p
         ctx.sink = _sinks(cfg.names, params)
         return out
@@ -62,8 +65,32 @@ class VideoBlockFn(torch.autograd.Function):
         dx, dy, g = F_.video_block_bwd(_K(), ctx.s, _f32c(d_out), ctx.p, ctx.w, cfg.H, cfg.T, cfg.Nf,
                                        need_dx=ctx.needs_input_grad[2], sink=ctx.sink)
         ctx.s = None
+        dprep = g.pop("_prep", (None, None, None))
         grads = tuple(_ret(g, n, ctx.p[n].shape) for n in cfg.names)
-        return (None, None, dx, dy, None) + grads
+        return (None, None, dx, dy, None) + tuple(dprep) + grads
+
+
+class I2TPrepFn(torch.autograd.Function):
+    """Text side of the re-associated gated video->text cross-attention (functional.i2t_prep_fwd): text states -> (Mt, U,
+    bias1).  A node of its own so that the model can run it -- forward and backward -- on the text tower's stream."""
+
+    @staticmethod
+    def forward(ctx, cfg, w, y, y_bias, *params):
+        p = _pdict(F_.I2T_PREP_PARAMS, params)
+        (Mt, U, bias1), s = F_.i2t_prep_fwd(_K(), _f32c(y), y_bias, p, w, cfg.H)
+        ctx.cfg, ctx.w, ctx.s, ctx.p = cfg, w, s, p
+        ctx.sink = _sinks(F_.I2T_PREP_PARAMS, params)
+        return Mt, U, bias1
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dMt, dU, dbias1):
+        K = _K()
+        G = F_.Grads(K, dbias1, ctx.sink)
+        dy = F_.i2t_prep_bwd(K, ctx.s, dMt.contiguous(), dU.contiguous(), dbias1.contiguous(), ctx.p, ctx.w, ctx.cfg.H, G)
+        ctx.s = None
+        grads = tuple(_ret(G.g, n, ctx.p[n].shape) for n in F_.I2T_PREP_PARAMS)
+        return (None, None, dy if ctx.needs_input_grad[2] else None, None) + grads
 
 
 class VideoBlockClsFn(torch.autograd.Function):

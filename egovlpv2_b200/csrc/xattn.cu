@@ -162,16 +162,18 @@ __global__ void qbias_fwd_kernel(const bf16* __restrict__ k, long long ldk, cons
 }
 
 // dk[b*S+s, h*64+j] += scale * dbias[b, h*S+s] * bq[h*64+j];   dbq[h*64+j] += scale * sum_{b,s} k[..] * dbias[..]
-// one CTA per head, 64 threads (j); the B*S rows are walked serially (B*S = 256)
+// grid (H, ceil(B*S / 32)), 64 threads (j): a CTA owns 32 rows of one head and adds its partial dbq with one atomic per j
 __global__ void qbias_bwd_kernel(const bf16* __restrict__ k, long long ldk, const float* __restrict__ bq,
                                  const float* __restrict__ dbias, float scale, int B, int S, int H, float* __restrict__ dk,
                                  long long lddk, float* __restrict__ dbq) {
   const int h = blockIdx.x, j = threadIdx.x;
   const float q = bq[h * 64 + j];
   float acc = 0.f;
-  for (int bs = 0; bs < B * S; ++bs) {
+  const int r0 = blockIdx.y * 32, r1 = min(r0 + 32, B * S);
+#pragma unroll 4
+  for (int bs = r0; bs < r1; ++bs) {
     const int b = bs / S, s = bs % S;
-    const float g = scale * dbias[(long long)b * H * S + h * S + s];
+    const float g = scale * __ldg(dbias + (long long)b * H * S + h * S + s);
     acc = fmaf(g, __bfloat162float(k[(long long)bs * ldk + h * 64 + j]), acc);
     if (dk) dk[(long long)bs * lddk + h * 64 + j] += g * q;
   }
@@ -238,7 +240,7 @@ extern "C" int egv_xattn_qbias_fwd(const void* k, int64_t ldk, const float* bq, 
 extern "C" int egv_xattn_qbias_bwd(const void* k, int64_t ldk, const float* bq, const float* dbias, float scale, int B, int S,
                                    int H, float* dk, int64_t lddk, float* dbq, egv_stream_t stream) {
   if (!k || !bq || !dbias || B <= 0 || S <= 0 || H <= 0) return fail(EGV_ERR_ARG, "qbias_bwd: bad arguments");
-  xa::qbias_bwd_kernel<<<(unsigned)H, 64, 0, (cudaStream_t)stream>>>((const bf16*)k, ldk, bq, dbias, scale, B, S, H, dk, lddk, dbq);
+  xa::qbias_bwd_kernel<<<dim3((unsigned)H, (unsigned)cdiv((long long)B * S, 32)), 64, 0, (cudaStream_t)stream>>>((const bf16*)k, ldk, bq, dbias, scale, B, S, H, dk, lddk, dbq);
   return check_launch("qbias_bwd_kernel");
 }
 

@@ -178,14 +178,53 @@ VIDEO_FUSE_PARAMS = ["attn.alpha_i2t", "attn.qkv_text_i2t.weight", "attn.qkv_tex
                      "attn.norm_i2t_i.bias"]
 
 
-def video_block_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=True):
+I2T_PREP_PARAMS = ["attn.qkv_text_i2t.weight", "attn.qkv_text_i2t.bias", "attn.qkv_i2t.weight", "attn.qkv_i2t.bias",
+                   "attn.proj_i2t.weight"]
+
+
+def i2t_prep_fwd(K, y, y_bias, p, w, H):
+    """Text side of the re-associated gated video->text cross-attention (xattn_reassoc.i2t_prep_fwd): a function of the
+    text states and weights only, so the model runs it on the text tower's stream.  y [B,S,Ct] f32; y_bias [B,S] f32.
+    -> ((Mt, U, bias1), saved)."""
+    B, S, Ct = y.shape
+    C = w["attn.qkv_i2t.weight"].shape[0]
+    K.mark("xattn_i2t_prep")
+    s = types.SimpleNamespace(B=B, S=S, Ct=Ct)
+    s.y_bf = _e(y, (B * S, Ct), BF16)
+    K.cast(y.reshape(B * S, Ct).contiguous(), s.y_bf)
+    s.kv_t = _e(y, (B * S, 2 * C), BF16)
+    K.gemm(GEMM_NT, s.y_bf, w["attn.qkv_text_i2t.weight"], bias=p["attn.qkv_text_i2t.bias"], out_bf16=s.kv_t)
+    prep = XR.i2t_prep_fwd(K, s.kv_t, y_bias, w["attn.qkv_i2t.weight"], p["attn.qkv_i2t.bias"], w["attn.proj_i2t.weight"], B, H)
+    return prep, s
+
+
+def i2t_prep_bwd(K, s, dM_b, dU_b, dbias1, p, w, H, G):
+    """Backward of i2t_prep_fwd; parameter gradients go into the Grads collector G.  -> dy [B,S,Ct] f32."""
+    B, S, Ct = s.B, s.S, s.Ct
+    C = w["attn.qkv_i2t.weight"].shape[0]
+    K.mark("xattn_i2t_prep_bwd")
+    dkv_f = XR.i2t_prep_bwd(K, s.kv_t, w["attn.qkv_i2t.weight"], p["attn.qkv_i2t.bias"], w["attn.proj_i2t.weight"], dM_b, dU_b,
+                            dbias1, G.full("attn.qkv_i2t.weight", (C, C)), G.full("attn.qkv_i2t.bias", (C,)),
+                            G.full("attn.proj_i2t.weight", (C, C)), B, H)
+    dkv2 = _e(dkv_f, (B * S, 2 * C), BF16)
+    K.cast(dkv_f, dkv2)
+    G.weight("attn.qkv_text_i2t.weight", dkv2, s.y_bf)
+    G.bias("attn.qkv_text_i2t.bias", dkv2)
+    dy = _e(dkv_f, (B, S, Ct), F32)
+    K.gemm(GEMM_NN, dkv2, w["attn.qkv_text_i2t.weight"], out_f32=dy.view(B * S, Ct))
+    return dy
+
+
+def video_block_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=True, prep=None):
     """SpaceTimeBlock.forward (video_transformer.py:214-228), optionally with the gated video->text
     cross-attention of VarAttention (video_transformer.py:155-185).
-    x [B,N,C] f32; y [B,S,Ct] f32 text states; y_bias [B,S] f32 additive key mask.  Returns (out f32, saved)."""
+    x [B,N,C] f32; y [B,S,Ct] f32 text states; y_bias [B,S] f32 additive key mask.  `prep`: (Mt, U, bias1) from
+    i2t_prep_fwd when the caller prepared the text side itself (the model does, on the text stream); their gradients
+    then come back from video_block_bwd instead of dy.  Returns (out f32, saved)."""
     B, N, C = x.shape
     M = B * N
     x2 = x.reshape(M, C)
-    s = types.SimpleNamespace(fused=y is not None, shape=(B, N, C), x=x2)
+    s = types.SimpleNamespace(fused=y is not None or prep is not None, shape=(B, N, C), x=x2)
     K.mark("video_block")
     # ---- time attention branch: t = proj(attn_time(qkv(norm3(x))))
     s.ln3, s.mean3, s.rstd3 = _e(x, (M, C), BF16), _e(x, (M,), F32), _e(x, (M,), F32)
@@ -202,10 +241,9 @@ def video_block_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=Tr
     K.gemm(GEMM_NT, s.ln1, w["attn.qkv.weight"], bias=p["attn.qkv.bias"], out_bf16=s.qkv_s)
     s.o_s, s.lse_s = divided_attention_fwd(K, s.qkv_s.view(B, N, 3 * C), H, T, Nf, "space")
     s.sr = _e(x, (M, C), F32)
-    if y is None:
+    if not s.fused:
         K.gemm(GEMM_NT, s.o_s.view(M, C), w["attn.proj.weight"], bias=p["attn.proj.bias"], residual=x2, out_f32=s.sr)
     else:
-        S, Ct = y.shape[1], y.shape[2]
         # a = proj(o_s) (bf16 copy feeds the cross-attention LN);  xa = x + a (fp32)
         s.a = _e(x, (M, C), BF16)
         xa = _e(x, (M, C), F32)
@@ -215,17 +253,22 @@ def video_block_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=Tr
         s.lnc, s.meanc, s.rstdc = _e(x, (M, C), BF16), _e(x, (M,), F32), _e(x, (M,), F32)
         K.layernorm_fwd(s.a, p["attn.norm_i2t_i.weight"], p["attn.norm_i2t_i.bias"], eps, y_bf16=s.lnc, mean=s.meanc,
                         rstd=s.rstdc)
-        s.y_bf = _e(x, (B * S, Ct), BF16)
-        K.cast(y.reshape(B * S, Ct), s.y_bf)
-        s.kv_t = _e(x, (B * S, 2 * C), BF16)
-        K.gemm(GEMM_NT, s.y_bf, w["attn.qkv_text_i2t.weight"], bias=p["attn.qkv_text_i2t.bias"], out_bf16=s.kv_t)
         s.y_bias = y_bias
-        s.reassoc = reassoc_enabled() and XR.i2t_supported(S, C, H)
+        s.reassoc = prep is not None or (reassoc_enabled() and XR.i2t_supported(y.shape[1], C, H))
+        s.prep_saved = None
         if s.reassoc:
             # re-associated around the S text keys (xattn_reassoc.py): no [M, C] query / output projections
-            s.xr = XR.i2t_fwd(K, s.lnc, s.kv_t, y_bias, w["attn.qkv_i2t.weight"], p["attn.qkv_i2t.bias"],
-                              w["attn.proj_i2t.weight"], p["attn.proj_i2t.bias"], p["attn.alpha_i2t"], xa, s.sr, B, N, H)
+            if prep is None:
+                prep, s.prep_saved = i2t_prep_fwd(K, y, y_bias, p, w, H)
+                K.mark("xattn_i2t_fwd")
+            s.Mt, s.U, bias1 = prep
+            s.P = XR.i2t_apply_fwd(K, s.lnc, s.Mt, s.U, bias1, p["attn.proj_i2t.bias"], p["attn.alpha_i2t"], xa, s.sr, B, N, H)
         else:
+            S, Ct = y.shape[1], y.shape[2]
+            s.y_bf = _e(x, (B * S, Ct), BF16)
+            K.cast(y.reshape(B * S, Ct), s.y_bf)
+            s.kv_t = _e(x, (B * S, 2 * C), BF16)
+            K.gemm(GEMM_NT, s.y_bf, w["attn.qkv_text_i2t.weight"], bias=p["attn.qkv_text_i2t.bias"], out_bf16=s.kv_t)
             s.q_c = _e(x, (M, C), BF16)
             K.gemm(GEMM_NT, s.lnc, w["attn.qkv_i2t.weight"], bias=p["attn.qkv_i2t.bias"], out_bf16=s.q_c)
             s.spec_c = AttnSpec(H=H, G=1, Lq=N, Lk=S, scale=(C // H) ** -0.5)
@@ -250,7 +293,8 @@ def video_block_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=Tr
 
 
 def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True, sink=None):
-    """Backward of video_block_fwd.  Returns (dx [B,N,C] f32 or None, dy [B,S,Ct] f32 or None, grads dict)."""
+    """Backward of video_block_fwd.  Returns (dx [B,N,C] f32 or None, dy [B,S,Ct] f32 or None, grads dict); when the
+    forward was given `prep`, grads["_prep"] = (dMt, dU, dbias1), the gradients of those three tensors (and dy is None)."""
     B, N, C = s.shape
     M = B * N
     G = Grads(K, d_out, sink)
@@ -277,19 +321,20 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True, sink=None):
     dy = None
     d_s_bf = d_sr_bf
     if s.fused:
-        S, Ct = s.y_bf.shape[0] // B, s.y_bf.shape[1]
         alpha = p["attn.alpha_i2t"]
         K.mark("xattn_i2t_bwd")
         # sr = x + a + alpha * c,  c = proj_i2t(attention)
         G.bias_from("attn.proj_i2t.bias", cs_sr, scale_dev=alpha)
         if s.reassoc:
-            d_lnc, dkv_f = XR.i2t_bwd(K, s.xr, d_sr_bf, cs_sr, w["attn.qkv_i2t.weight"], p["attn.qkv_i2t.bias"],
-                                      w["attn.proj_i2t.weight"], p["attn.proj_i2t.bias"], alpha, G.full("attn.alpha_i2t", (1,)),
-                                      G.full("attn.qkv_i2t.weight", (C, C)), G.full("attn.qkv_i2t.bias", (C,)),
-                                      G.full("attn.proj_i2t.weight", (C, C)))
-            dkv2 = _e(d_out, (B * S, 2 * C), BF16)
-            K.cast(dkv_f, dkv2)
+            d_lnc, dM_b, dU_b, dbias1 = XR.i2t_apply_bwd(K, s.lnc, s.Mt, s.U, s.P, d_sr_bf, cs_sr, p["attn.proj_i2t.bias"], alpha,
+                                                         G.full("attn.alpha_i2t", (1,)), B, N, H)
+            if s.prep_saved is not None:
+                dy = i2t_prep_bwd(K, s.prep_saved, dM_b, dU_b, dbias1, p, w, H, G)
+                K.mark("xattn_i2t_bwd")
+            else:
+                G.g["_prep"] = (dM_b, dU_b, dbias1)
         else:
+            S, Ct = s.y_bf.shape[0] // B, s.y_bf.shape[1]
             G.scalar_dot("attn.alpha_i2t", d_sr, s.c)
             G.weight("attn.proj_i2t.weight", d_sr_bf, s.o_c.view(M, C), scale_dev=alpha)
             d_oc = _e(d_out, (B, N, C), BF16)
@@ -304,10 +349,10 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True, sink=None):
             G.bias("attn.qkv_i2t.bias", dq2)
             d_lnc = _e(d_out, (M, C), BF16)
             K.gemm(GEMM_NN, dq2, w["attn.qkv_i2t.weight"], out_bf16=d_lnc)
-        G.weight("attn.qkv_text_i2t.weight", dkv2, s.y_bf)
-        G.bias("attn.qkv_text_i2t.bias", dkv2)
-        dy = _e(d_out, (B, S, Ct), F32)
-        K.gemm(GEMM_NN, dkv2, w["attn.qkv_text_i2t.weight"], out_f32=dy.view(B * S, Ct))
+            G.weight("attn.qkv_text_i2t.weight", dkv2, s.y_bf)
+            G.bias("attn.qkv_text_i2t.bias", dkv2)
+            dy = _e(d_out, (B, S, Ct), F32)
+            K.gemm(GEMM_NN, dkv2, w["attn.qkv_text_i2t.weight"], out_f32=dy.view(B * S, Ct))
         # d_a = d_sr + LNc'(d_lnc)
         d_a_bf = _e(d_out, (M, C), BF16)
         K.layernorm_bwd(d_lnc, s.a, p["attn.norm_i2t_i.weight"], s.meanc, s.rstdc, add=d_sr, dx=None, dx_bf16=d_a_bf,

@@ -263,14 +263,20 @@ class FrozenInTime(nn.Module):
         x = video_prefix
         last = self.num_text_layer - 1
         for i in range(unfused, self.num_text_layer):
+            run_video = need_video_out or i < last   # the last video block's output is unused by the MLM head
+            cls_only = video_transformer.CLS_ONLY_LAST_BLOCK and i == last   # the ITM head reads only its CLS row (model.py:275-278)
+            prep = None
+            if run_video and not cls_only:
+                with streams.side():   # text side of video block i's cross-attention: on the text stream, behind text layer i - 1
+                    prep = vm.blocks[i].i2t_prep(h, ext)
             streams.exchange()        # level i reads both outputs of level i - 1
             streams.to_main(h)
+            if prep is not None:
+                streams.to_main(*prep)
             streams.to_side(x)
             fuse_x = None
-            if need_video_out or i < last:   # the last video block's output is unused by the MLM head
-                # ... and the ITM head reads only its CLS row (model.py:275-278)
-                fuse_x = vm.blocks[i](x, *es, y=h, y_mask=ext, time_n=n, space_f=f,
-                                      cls_only=video_transformer.CLS_ONLY_LAST_BLOCK and i == last)
+            if run_video:
+                fuse_x = vm.blocks[i](x, *es, y=h, y_mask=ext, time_n=n, space_f=f, cls_only=cls_only, i2t_prep=prep)
             with streams.side():
                 h = tm.encoder.layer[i](h, ext, encoder_hidden_states=x, last_norm=True)[0]
             x = fuse_x

@@ -128,10 +128,25 @@ class SpaceTimeBlock(nn.Module):
         names = Fn.VIDEO_BLOCK_PARAMS + (Fn.VIDEO_FUSE_PARAMS if fused else [])
         return names, [self.get_parameter(n) for n in names]
 
+    def i2t_prep(self, y, y_mask=None):
+        """(extension) The text side of this block's gated video->text cross-attention, re-associated around the text
+        tokens (xattn_reassoc.py): (Mt, U, bias1), functions of the text states and weights only.  FrozenInTime calls it
+        on the text tower's stream and hands the result to forward(..., i2t_prep=...); None when the re-associated
+        kernels do not cover the shape (forward then takes y and does everything itself)."""
+        from .. import xattn_reassoc as XR
+        dim = self.norm1.normalized_shape[0]
+        if not (self.has_fusion and Fn.reassoc_enabled() and XR.i2t_supported(y.shape[1], dim, self.num_heads)):
+            return None
+        params = [self.get_parameter(n) for n in Fn.I2T_PREP_PARAMS]
+        w = {n: cache().bf16(p) for n, p in zip(Fn.I2T_PREP_PARAMS, params) if p.dim() == 2}
+        y_bias = None if y_mask is None else y_mask.reshape(y.shape[0], -1).float().contiguous()
+        return A.I2TPrepFn.apply(A.cfg(H=self.num_heads), w, y, y_bias, *params)
+
     def forward(self, x, einops_from_space, einops_to_space, einops_from_time, einops_to_time, time_n, space_f, y=None,
-                y_mask=None, cls_only=False):
+                y_mask=None, cls_only=False, i2t_prep=None):
         """`cls_only` (extension, default off): return only the CLS row, [B, 1, C] -- for a block whose output is
-        consumed as `x[:, 0]` (the last block of the EgoNCE and ITM passes); the row equals the full forward's."""
+        consumed as `x[:, 0]` (the last block of the EgoNCE and ITM passes); the row equals the full forward's.
+        `i2t_prep` (extension): the result of self.i2t_prep(y, y_mask)."""
         fused = y is not None
         if fused and not self.has_fusion:
             raise AttributeError("this SpaceTimeBlock was built without cross-attention parameters (dim_text=None)")
@@ -143,7 +158,8 @@ class SpaceTimeBlock(nn.Module):
         cfg = A.cfg(names=names, H=self.num_heads, T=space_f, Nf=time_n, eps=self._eps)
         if cls_only:
             return A.VideoBlockClsFn.apply(cfg, w, x, y, y_bias, *params).unsqueeze(1)
-        return A.VideoBlockFn.apply(cfg, w, x, y, y_bias, *params)
+        Mt, U, bias1 = i2t_prep if i2t_prep is not None else (None, None, None)
+        return A.VideoBlockFn.apply(cfg, w, x, y, y_bias, Mt, U, bias1, *params)
 
 
 class SpaceTimeTransformer(nn.Module):

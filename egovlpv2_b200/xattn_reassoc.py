@@ -48,63 +48,75 @@ def t2i_supported(S, N, C, H):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def i2t_fwd(K, lnc, kv, mask, wq, bq, wp, bp, alpha, xa, out, B, N, H):
-    """lnc [B*N, C] bf16 = LN(a); kv [B*S, 2C] bf16 (k | v of the text); mask [B, S] f32 additive or None; wq / wp [C, C]
-    bf16; bq / bp [C] f32; alpha device scalar; xa [B*N, C] f32 (residual: x + a); out [B*N, C] f32 is written with
-    xa + alpha * proj_i2t(attention).  Returns the saved tensors."""
-    C = lnc.shape[1]
+# video -> text.  Two halves: the TEXT-side preparation (functions of the text states and weights only: [B*S] = 256 rows;
+# small, launch-latency-bound products that the model runs on the text tower's stream, next to the video tower) and the
+# VIDEO-side application (two per-clip GEMMs over the M = B*N token rows in each direction).
+def i2t_prep_fwd(K, kv, mask, wq, bq, wp, B, H):
+    """kv [B*S, 2C] (k | v of the text, operand dtype); mask [B, S] f32 additive or None; wq / wp [C, C]; bq [C] f32.
+    -> Mt [B, H, S, C] = d^-1/2 k_h Wq_h,  U [B, H, S, C] = v_h Wp[:, h]^T,  bias1 [B, H*S] f32 = d^-1/2 bq_h . k_h + mask."""
+    C = kv.shape[1] // 2
     S = kv.shape[0] // B
     HS = H * S
     sc = HD ** -0.5
-    BF16 = lnc.dtype      # operand dtype (bf16; fp32 in the exact-mode host-logic tests)
-    Mt, U = _e(lnc, (B, H, S, C), BF16), _e(lnc, (B, H, S, C), BF16)
+    dt = kv.dtype
+    Mt, U = _e(kv, (B, H, S, C), dt), _e(kv, (B, H, S, C), dt)
     ldkv = kv.stride(0)
-    # text side, one batch per (clip, head): Mt = d^-1/2 k_h Wq_h ;  U = v_h Wp[:, h]^T
     K.bgemm(GEMM_NN, S, C, HD, BV(kv, ldkv, HD, S * ldkv), BV(wq, wq.stride(0), HD * wq.stride(0), 0), nb=(H, B), scale=sc,
             out_bf16=BV(Mt, C, S * C, HS * C))
     K.bgemm(GEMM_NT, S, C, HD, BV(kv[:, C:], ldkv, HD, S * ldkv), BV(wp, wp.stride(0), HD, 0), nb=(H, B),
             out_bf16=BV(U, C, S * C, HS * C))
-    bias1 = _e(lnc, (B, HS), F32)
+    bias1 = _e(kv, (B, HS), F32)
     K.xattn_qbias_fwd(kv, ldkv, bq, mask, sc, B, S, H, bias1)
-    # video side, one batch per clip: P = group-softmax(LN(a) Mt^T + bias1) ;  out = xa + alpha (P U + bp)
-    P = _e(lnc, (B, N, HS), BF16)
+    return Mt, U, bias1
+
+
+def i2t_apply_fwd(K, lnc, Mt, U, bias1, bp, alpha, xa, out, B, N, H):
+    """lnc [B*N, C] = LN(a); xa [B*N, C] f32 (residual x + a); out [B*N, C] f32 <- xa + alpha * (P U + bp) with
+    P [B, N, H*S] = group-softmax(lnc Mt^T + bias1), which is returned (saved for the backward)."""
+    C = lnc.shape[1]
+    HS = Mt.shape[1] * Mt.shape[2]
+    P = _e(lnc, (B, N, HS), lnc.dtype)
     K.bgemm(GEMM_NT, N, HS, C, BV(lnc, C, N * C), BV(Mt, C, HS * C), nb=(B, 1), bias=BV(bias1, 0, HS), out_bf16=BV(P, HS, N * HS),
             epilogue=EPI_SOFTMAX32)
     K.bgemm(GEMM_NN, N, C, HS, BV(P, HS, N * HS), BV(U, C, HS * C), nb=(B, 1), bias=BV(bp, 0, 0), scale_dev=alpha,
             residual=BV(xa, C, N * C), out_f32=BV(out, C, N * C))
-    return types.SimpleNamespace(lnc=lnc, kv=kv, Mt=Mt, U=U, P=P, B=B, N=N, H=H, S=S)
+    return P
 
 
-def i2t_bwd(K, s, d_out_bf, cs_out, wq, bq, wp, bp, alpha, dalpha, dwq, dbq, dwp):
-    """d_out_bf [B*N, C] bf16 = gradient of `out`.  ACCUMULATES the parameter gradients into dalpha [1], dwq [C, C], dbq [C],
-    dwp [C, C] (f32: zero-filled tensors or slices of the gradient arena) and returns (d_lnc [B*N, C] bf16, dkv [B*S, 2C] f32).
-    cs_out [C] f32 = column sums of the gradient of `out` (the caller has them: they are also alpha^-1 times the gradient
-    of bp, which stays with the caller, like the gradient through xa)."""
-    B, N, H, S = s.B, s.N, s.H, s.S
-    C = s.lnc.shape[1]
+def i2t_apply_bwd(K, lnc, Mt, U, P, d_out_bf, cs_out, bp, alpha, dalpha, B, N, H):
+    """d_out_bf [B*N, C] = gradient of `out`; cs_out [C] f32 = its column sums.  ACCUMULATES d alpha into dalpha [1];
+    returns (d_lnc [B*N, C], dM [B, H, S, C], dU [B, H, S, C] (operand dtype), dbias1 [B, H*S] f32)."""
+    C = lnc.shape[1]
+    S = Mt.shape[2]
     HS = H * S
-    sc = HD ** -0.5
-    kv = s.kv
-    ldkv = kv.stride(0)
-    BF16 = d_out_bf.dtype
+    dt = d_out_bf.dtype
     # dS = alpha * P * (dP - rowdot(P, dP)),  dP = d_out U^T ;  d alpha = sum rowdot ;  dbias1 = column sums of dS
-    dS = _e(d_out_bf, (B, N, HS), BF16)
+    dS = _e(d_out_bf, (B, N, HS), dt)
     dbias1 = _z(d_out_bf, (B, HS))
-    K.bgemm(GEMM_NT, N, HS, C, BV(d_out_bf, C, N * C), BV(s.U, C, HS * C), nb=(B, 1), scale_dev=alpha, aux=BV(s.P, HS, N * HS),
+    K.bgemm(GEMM_NT, N, HS, C, BV(d_out_bf, C, N * C), BV(U, C, HS * C), nb=(B, 1), scale_dev=alpha, aux=BV(P, HS, N * HS),
             out_bf16=BV(dS, HS, N * HS), colsum=BV(dbias1, 0, HS), dot_out=dalpha, epilogue=EPI_DSOFTMAX32)
     K.dot(cs_out, bp, dalpha, accumulate=True)        # the bias part of c = P U + bp:  d alpha += sum_n d_out[n] . bp
-    d_lnc = _e(d_out_bf, (B * N, C), BF16)
-    K.bgemm(GEMM_NN, N, C, HS, BV(dS, HS, N * HS), BV(s.Mt, C, HS * C), nb=(B, 1), out_bf16=BV(d_lnc, C, N * C))
+    d_lnc = _e(d_out_bf, (B * N, C), dt)
+    K.bgemm(GEMM_NN, N, C, HS, BV(dS, HS, N * HS), BV(Mt, C, HS * C), nb=(B, 1), out_bf16=BV(d_lnc, C, N * C))
     # dU[b] = alpha * P[b]^T d_out[b] ;  dM[b] = dS[b]^T LN(a)[b]      (K = N tokens per clip, split-K + fp32 atomics)
     dU, dM = _z(d_out_bf, (B, H, S, C)), _z(d_out_bf, (B, H, S, C))
-    K.bgemm(GEMM_TN, HS, C, N, BV(s.P, HS, N * HS), BV(d_out_bf, C, N * C), nb=(B, 1), scale_dev=alpha,
+    K.bgemm(GEMM_TN, HS, C, N, BV(P, HS, N * HS), BV(d_out_bf, C, N * C), nb=(B, 1), scale_dev=alpha,
             out_f32=BV(dU, C, HS * C), accumulate=True)
-    K.bgemm(GEMM_TN, HS, C, N, BV(dS, HS, N * HS), BV(s.lnc, C, N * C), nb=(B, 1), out_f32=BV(dM, C, HS * C), accumulate=True)
-    dU_b, dM_b = _e(dU, dU.shape, BF16), _e(dM, dM.shape, BF16)
+    K.bgemm(GEMM_TN, HS, C, N, BV(dS, HS, N * HS), BV(lnc, C, N * C), nb=(B, 1), out_f32=BV(dM, C, HS * C), accumulate=True)
+    dU_b, dM_b = _e(dU, dU.shape, dt), _e(dM, dM.shape, dt)
     K.cast(dU, dU_b)
     K.cast(dM, dM_b)
-    # text side, one batch per (clip, head)
-    dkv = _e(d_out_bf, (B * S, 2 * C), F32)
+    return d_lnc, dM_b, dU_b, dbias1
+
+
+def i2t_prep_bwd(K, kv, wq, bq, wp, dM_b, dU_b, dbias1, dwq, dbq, dwp, B, H):
+    """Backward of i2t_prep_fwd: ACCUMULATES into dwq [C, C], dbq [C], dwp [C, C] (f32) and returns dkv [B*S, 2C] f32."""
+    C = kv.shape[1] // 2
+    S = kv.shape[0] // B
+    HS = H * S
+    sc = HD ** -0.5
+    ldkv = kv.stride(0)
+    dkv = _e(kv, (B * S, 2 * C), F32)
     bh = dict(nb=(H, B))
     K.bgemm(GEMM_NT, S, HD, C, BV(dM_b, C, S * C, HS * C), BV(wq, wq.stride(0), HD * wq.stride(0), 0), scale=sc,
             out_f32=BV(dkv, 2 * C, HD, S * 2 * C), **bh)                                   # dk_h  = d^-1/2 dM_h Wq_h^T
@@ -116,6 +128,20 @@ def i2t_bwd(K, s, d_out_bf, cs_out, wq, bq, wp, bp, alpha, dalpha, dwq, dbq, dwp
             out_f32=BV(dwp, C, HD, 0), accumulate=True, **bh)                              # dWp[:, h] += dU_h^T v_h
     # the query bias: scores += d^-1/2 bq_h . k_h  ->  dk_h += d^-1/2 dbias1 (x) bq_h ;  dbq_h += d^-1/2 k_h^T dbias1
     K.xattn_qbias_bwd(kv, ldkv, bq, dbias1, sc, B, S, H, dk=dkv, lddk=2 * C, dbq=dbq)
+    return dkv
+
+
+def i2t_fwd(K, lnc, kv, mask, wq, bq, wp, bp, alpha, xa, out, B, N, H):
+    """both halves in sequence (see i2t_prep_fwd / i2t_apply_fwd); returns the saved tensors"""
+    Mt, U, bias1 = i2t_prep_fwd(K, kv, mask, wq, bq, wp, B, H)
+    P = i2t_apply_fwd(K, lnc, Mt, U, bias1, bp, alpha, xa, out, B, N, H)
+    return types.SimpleNamespace(lnc=lnc, kv=kv, Mt=Mt, U=U, P=P, B=B, N=N, H=H, S=kv.shape[0] // B)
+
+
+def i2t_bwd(K, s, d_out_bf, cs_out, wq, bq, wp, bp, alpha, dalpha, dwq, dbq, dwp):
+    """-> (d_lnc [B*N, C], dkv [B*S, 2C] f32); ACCUMULATES into dalpha [1], dwq [C, C], dbq [C], dwp [C, C]."""
+    d_lnc, dM_b, dU_b, dbias1 = i2t_apply_bwd(K, s.lnc, s.Mt, s.U, s.P, d_out_bf, cs_out, bp, alpha, dalpha, s.B, s.N, s.H)
+    dkv = i2t_prep_bwd(K, s.kv, wq, bq, wp, dM_b, dU_b, dbias1, dwq, dbq, dwp, s.B, s.H)
     return d_lnc, dkv
 
 
