@@ -161,7 +161,7 @@ def run_ours(a, rank, world, local_rank):
     torch.manual_seed(0)
     model = build_model(T=a.frames)
     randomize_gates(model)
-    model.eval()      # text dropout is not implemented: eval-mode semantics
+    model.train()     # the reference's step runs in train mode: text-tower dropout (p = 0.1) is part of the timed work
     use_graph = not a.no_graph
     step = PretrainStep(model, dev, max_steps=10000, warmup_steps=100, gather=a.gather)
     host = synthetic_batch(a.batch, a.frames, 224, a.seq, seed=1234 + rank, pin=True)

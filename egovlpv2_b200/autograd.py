@@ -125,7 +125,7 @@ class TextLayerFn(torch.autograd.Function):
         p = _pdict(cfg.names, params)
         p.update(pcat)
         out, s = F_.text_layer_fwd(_K(), _f32c(h), key_bias, p, w, cfg.H, video=None if video is None else _f32c(video),
-                                   eps=cfg.eps, save=True)
+                                   eps=cfg.eps, save=True, drop=getattr(cfg, "drop", None), layer=getattr(cfg, "layer", 0))
         ctx.cfg, ctx.w, ctx.s, ctx.p = cfg, w, s, p
         sink = _sinks(cfg.names, params)
         # concatenated q/k/v (and cross k/v) gradients: only when the arena laid the parts out back to back
@@ -199,7 +199,7 @@ class TextEmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, ids, *params):
         p = _pdict(TextEmbedFn.NAMES, params)
-        out, s = F_.text_embeddings_fwd(_K(), ids, p, eps=cfg.eps, pad_id=cfg.pad_id, save=True)
+        out, s = F_.text_embeddings_fwd(_K(), ids, p, eps=cfg.eps, pad_id=cfg.pad_id, save=True, drop=getattr(cfg, "drop", None))
         ctx.s, ctx.p = s, p
         ctx.sink = _sinks(TextEmbedFn.NAMES, params)
         return out

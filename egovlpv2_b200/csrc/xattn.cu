@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "host_common.h"
+#include "philox.cuh"
 
 namespace egv {
 namespace xa {
@@ -34,36 +35,13 @@ EGV_DEVINL float block_reduce(float v, float* red) {
   return r;
 }
 
-// Philox4x32-10 (Salmon et al. 2011), the counter-based generator torch's CUDA dropout uses: the stream is a pure
-// function of (seed, offset + element index / 4), so the backward regenerates the mask instead of storing it.
-EGV_DEVINL uint4 philox4(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
-  uint32_t c2 = 0u, c3 = 0u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  return make_uint4(c0, c1, c2, c3);
-}
-// keep-decision of element `idx` of a stream: uniform 24-bit fraction >= p
-EGV_DEVINL bool philox_keep(unsigned long long seed, unsigned long long idx, float p_drop) {
-  const unsigned long long ctr = idx >> 2;
-  const uint4 r = philox4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
-  const uint32_t w = (idx & 3) == 0 ? r.x : ((idx & 3) == 1 ? r.y : ((idx & 3) == 2 ? r.z : r.w));
-  return (float)(w >> 8) * (1.0f / 16777216.0f) >= p_drop;
-}
-
 // One CTA per row r of scores [rows, ld_s] (row r = batch r / rows_per_batch, local row r % rows_per_batch; output
 // rows of batch b start at b * p_bstride elements).  P = softmax(scores) in bf16, lse = log sum exp (natural log).
 // Dropout (p_drop > 0): P_out = keep ? P / (1 - p) : 0, with `rsum` = the row sum of the dropped probabilities.
 __global__ void __launch_bounds__(ROW_THREADS)
 row_softmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_per_batch, long long s_bstride, int n,
                    bf16* __restrict__ P, long long ld_p, long long p_bstride, float* __restrict__ lse, float p_drop,
-                   unsigned long long seed, float* __restrict__ rsum) {
+                   const unsigned long long* __restrict__ seed_dev, unsigned long long site, float* __restrict__ rsum) {
   __shared__ float red[ROW_THREADS / 32];
   const long long r = blockIdx.x;
   const long long b = r / rows_per_batch, lr = r % rows_per_batch;
@@ -88,6 +66,7 @@ row_softmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_pe
   sum = block_reduce<false>(sum, red);
   const float inv = 1.0f / sum;
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const unsigned long long seed = p_drop > 0.f ? philox_key(seed_dev, site) : 0ull;
   float dsum = 0.f;
 #pragma unroll
   for (int i = 0; i < MAX_PER_THREAD; ++i) {
@@ -113,8 +92,8 @@ row_softmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_pe
 __global__ void __launch_bounds__(ROW_THREADS)
 row_dsoftmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_per_batch, long long s_bstride, int n,
                     const float* __restrict__ lse, const float* __restrict__ dP, long long ld_dp, long long dp_bstride,
-                    bf16* __restrict__ dS, long long ld_ds, long long ds_bstride, float p_drop, unsigned long long seed,
-                    const float* __restrict__ row_const) {
+                    bf16* __restrict__ dS, long long ld_ds, long long ds_bstride, float p_drop,
+                    const unsigned long long* __restrict__ seed_dev, unsigned long long site, const float* __restrict__ row_const) {
   __shared__ float red[ROW_THREADS / 32];
   const long long r = blockIdx.x;
   const long long b = r / rows_per_batch, lr = r % rows_per_batch;
@@ -124,6 +103,7 @@ row_dsoftmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_p
   const float l2 = lse[r] * LOG2E;
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   const float rc = row_const ? row_const[r] : 0.f;   // value-bias term d_ox_h . bv_h (cancels unless dropout is on)
+  const unsigned long long seed = p_drop > 0.f ? philox_key(seed_dev, site) : 0ull;
   float pr[MAX_PER_THREAD], g[MAX_PER_THREAD];
   float dot = 0.f;
 #pragma unroll
@@ -208,24 +188,24 @@ __global__ void rowscale_bias_bwd_kernel(const bf16* __restrict__ d_ox, long lon
 using namespace egv;
 
 extern "C" int egv_xattn_row_softmax(const float* scores, int64_t ld_s, int64_t rows, int rows_per_batch, int64_t s_bstride,
-                                     int n, void* P, int64_t ld_p, int64_t p_bstride, float* lse, float p_drop, uint64_t seed,
-                                     float* rsum, egv_stream_t stream) {
+                                     int n, void* P, int64_t ld_p, int64_t p_bstride, float* lse, float p_drop,
+                                     const uint64_t* seed_dev, uint64_t site, float* rsum, egv_stream_t stream) {
   if (!scores || !P || rows <= 0 || n <= 0 || rows_per_batch <= 0) return fail(EGV_ERR_ARG, "row_softmax: bad arguments");
   if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD) return fail(EGV_ERR_UNSUPPORTED, "row_softmax: %d columns > %d", n, xa::ROW_THREADS * xa::MAX_PER_THREAD);
   if (p_drop < 0.f || p_drop >= 1.f) return fail(EGV_ERR_ARG, "row_softmax: dropout probability %f", p_drop);
   xa::row_softmax_kernel<<<(unsigned)rows, xa::ROW_THREADS, 0, (cudaStream_t)stream>>>(
-      scores, ld_s, rows_per_batch, s_bstride, n, (bf16*)P, ld_p, p_bstride, lse, p_drop, seed, rsum);
+      scores, ld_s, rows_per_batch, s_bstride, n, (bf16*)P, ld_p, p_bstride, lse, p_drop, (const unsigned long long*)seed_dev, site, rsum);
   return check_launch("row_softmax_kernel");
 }
 
 extern "C" int egv_xattn_row_dsoftmax(const float* scores, int64_t ld_s, int64_t rows, int rows_per_batch, int64_t s_bstride,
                                       int n, const float* lse, const float* dP, int64_t ld_dp, int64_t dp_bstride, void* dS,
-                                      int64_t ld_ds, int64_t ds_bstride, float p_drop, uint64_t seed, const float* row_const,
-                                      egv_stream_t stream) {
+                                      int64_t ld_ds, int64_t ds_bstride, float p_drop, const uint64_t* seed_dev, uint64_t site,
+                                      const float* row_const, egv_stream_t stream) {
   if (!scores || !lse || !dP || !dS || rows <= 0 || n <= 0 || rows_per_batch <= 0) return fail(EGV_ERR_ARG, "row_dsoftmax: bad arguments");
   if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD) return fail(EGV_ERR_UNSUPPORTED, "row_dsoftmax: %d columns > %d", n, xa::ROW_THREADS * xa::MAX_PER_THREAD);
   xa::row_dsoftmax_kernel<<<(unsigned)rows, xa::ROW_THREADS, 0, (cudaStream_t)stream>>>(
-      scores, ld_s, rows_per_batch, s_bstride, n, lse, dP, ld_dp, dp_bstride, (bf16*)dS, ld_ds, ds_bstride, p_drop, seed, row_const);
+      scores, ld_s, rows_per_batch, s_bstride, n, lse, dP, ld_dp, dp_bstride, (bf16*)dS, ld_ds, ds_bstride, p_drop, (const unsigned long long*)seed_dev, site, row_const);
   return check_launch("row_dsoftmax_kernel");
 }
 

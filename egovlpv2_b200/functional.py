@@ -576,8 +576,10 @@ TEXT_FUSE_PARAMS = ["alpha_t2i", "crossattention_t2i.self.query.weight", "crossa
                     "crossattention_t2i.output.dense.weight", "crossattention_t2i.output.dense.bias"]
 
 
-def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True):
-    """RobertaLayer.forward (roberta.py:444-505) in eval mode (dropout = identity), `last_norm=True`.
+def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True, drop=None, layer=0):
+    """RobertaLayer.forward (roberta.py:444-505), `last_norm=True`.  `drop` (train mode, see drop_site; `layer` = encoder
+    layer index): dropout on the attention probabilities (:313) and after the three dense outputs (:342, :422), the
+    cross-attention included; None = eval mode.
     h [B,S,C] f32; key_bias [B,S] f32 additive mask; video [B,N,Cv] f32 = un-normalised video stream entering
     video block i (roberta.py:470-486: K,V = Linear(video), no mask).  `w['qkv']` = cat(query,key,value) weights,
     `p['qkv.bias']` the concatenated bias; likewise `w['cross.kv']`, `p['cross.kv.bias']`.
@@ -586,7 +588,8 @@ def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True):
     M = B * S
     h2 = h.reshape(M, C)
     d = C // H
-    s = types.SimpleNamespace(fused=video is not None, shape=(B, S, C), key_bias=key_bias)
+    s = types.SimpleNamespace(fused=video is not None, shape=(B, S, C), key_bias=key_bias, drop=drop, layer=layer)
+    site = (lambda kind: drop_site(drop, layer + 1, kind)) if drop is not None else None
     K.mark("text_layer")
     s.h_bf = _e(h, (M, C), BF16)
     K.cast(h2.contiguous(), s.h_bf)
@@ -595,13 +598,22 @@ def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True):
     s.spec = AttnSpec(H=H, G=1, Lq=S, Lk=S, scale=1.0 / math.sqrt(d))
     qkv3 = s.qkv.view(B, S, 3 * C)
     s.o, s.lse = _e(h, (B, S, C), BF16), _e(h, (B * H * S,), F32)
-    K.attention_fwd(s.spec, qkv3[:, :, :C], qkv3[:, :, C:2 * C], qkv3[:, :, 2 * C:], s.o, s.lse, key_bias=key_bias)
+    if drop is None:
+        K.attention_fwd(s.spec, qkv3[:, :, :C], qkv3[:, :, C:2 * C], qkv3[:, :, 2 * C:], s.o, s.lse, key_bias=key_bias)
+    else:
+        K.text_attention_fwd(qkv3[:, :, :C], qkv3[:, :, C:2 * C], qkv3[:, :, 2 * C:], key_bias, s.spec.scale, drop.p_attn, drop.seed,
+                             site(DROP_SELF_PROBS), H, s.o, s.lse)
     # so = attention.output.dense(o) (no residual / LN inside RobertaSelfOutput: roberta.py:331-343)
     # sh = so + h  (fp32), so_bf = bf16(so) feeds the cross-attention query
     sh = _e(h, (M, C), F32)
     s.so_bf = _e(h, (M, C), BF16) if s.fused else None
-    K.gemm(GEMM_NT, s.o.view(M, C), w["attention.output.dense.weight"], bias=p["attention.output.dense.bias"],
-           residual=h2, out_f32=sh, out_pre=s.so_bf)
+    if drop is None:
+        K.gemm(GEMM_NT, s.o.view(M, C), w["attention.output.dense.weight"], bias=p["attention.output.dense.bias"],
+               residual=h2, out_f32=sh, out_pre=s.so_bf)
+    else:
+        so_f = _e(h, (M, C), F32)
+        K.gemm(GEMM_NT, s.o.view(M, C), w["attention.output.dense.weight"], bias=p["attention.output.dense.bias"], out_f32=so_f)
+        K.dropout_add(so_f, h2.contiguous(), drop.p, drop.seed, site(DROP_SELF_OUT), out_f32=sh, out_bf16=s.so_bf)
     if s.fused:
         Bv, N, Cv = video.shape
         K.mark("xattn_t2i_fwd")
@@ -616,7 +628,11 @@ def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True):
         if s.reassoc:
             # re-associated around the S text queries (xattn_reassoc.py): K = V = the video stream itself, no K/V projection
             s.xr = XR.t2i_fwd(K, s.qx, s.x_bf, w["cross.kv"][:C], w["cross.kv"][C:], p["cross.kv.bias"][C:], s.ox.view(M, C),
-                              B, N, H)
+                              B, N, H, p_drop=0.0 if drop is None else drop.p_attn, seed_dev=None if drop is None else drop.seed,
+                              site=0 if drop is None else site(DROP_CROSS_PROBS))
+        elif drop is not None:
+            raise NotImplementedError("train-mode dropout of the text->video cross-attention needs the re-associated path "
+                                      "(text length <= 128, <= 4096 video tokens per clip)")
         else:
             s.kv = _e(h, (Bv * N, 2 * C), BF16)
             K.gemm(GEMM_NT, s.x_bf, w["cross.kv"], bias=p["cross.kv.bias"], out_bf16=s.kv)
@@ -627,9 +643,15 @@ def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True):
         # attn_out + h = alpha * c + so + h
         s.c = _e(h, (M, C), BF16)
         sh2 = _e(h, (M, C), F32)
-        K.gemm(GEMM_NT, s.ox.view(M, C), w["crossattention_t2i.output.dense.weight"],
-               bias=p["crossattention_t2i.output.dense.bias"], scale_dev=p["alpha_t2i"], residual=sh, out_f32=sh2,
-               out_pre=s.c)
+        if drop is None:
+            K.gemm(GEMM_NT, s.ox.view(M, C), w["crossattention_t2i.output.dense.weight"],
+                   bias=p["crossattention_t2i.output.dense.bias"], scale_dev=p["alpha_t2i"], residual=sh, out_f32=sh2,
+                   out_pre=s.c)
+        else:   # c = dropout(dense(ox));  sh2 = sh + alpha * c
+            c_f = _e(h, (M, C), F32)
+            K.gemm(GEMM_NT, s.ox.view(M, C), w["crossattention_t2i.output.dense.weight"],
+                   bias=p["crossattention_t2i.output.dense.bias"], out_f32=c_f)
+            K.dropout_add(c_f, sh, drop.p, drop.seed, site(DROP_CROSS_OUT), out_f32=sh2, out_bf16=s.c, scale_dev=p["alpha_t2i"])
         sh = sh2
         K.mark("text_layer")
     s.sh = sh
@@ -642,7 +664,12 @@ def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True):
     K.gemm(GEMM_NT, s.a_bf, w["intermediate.dense.weight"], bias=p["intermediate.dense.bias"], act=ACT_GELU,
            out_bf16=s.f_act, out_pre=s.f_pre)
     s.fa = _e(h, (M, C), F32)
-    K.gemm(GEMM_NT, s.f_act, w["output.dense.weight"], bias=p["output.dense.bias"], residual=s.a, out_f32=s.fa)
+    if drop is None:
+        K.gemm(GEMM_NT, s.f_act, w["output.dense.weight"], bias=p["output.dense.bias"], residual=s.a, out_f32=s.fa)
+    else:
+        fo_f = _e(h, (M, C), F32)
+        K.gemm(GEMM_NT, s.f_act, w["output.dense.weight"], bias=p["output.dense.bias"], out_f32=fo_f)
+        K.dropout_add(fo_f, s.a, drop.p, drop.seed, site(DROP_FFN_OUT), out_f32=s.fa)
     out = _e(h, (M, C), F32)
     s.mean_o, s.rstd_o = _e(h, (M,), F32), _e(h, (M,), F32)
     K.layernorm_fwd(s.fa, p["output.LayerNorm.weight"], p["output.LayerNorm.bias"], eps, y_f32=out, mean=s.mean_o,
@@ -656,12 +683,16 @@ def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True, sink=None):
     B, S, C = s.shape
     M = B * S
     G = Grads(K, d_out, sink)
+    drop = s.drop
+    site = (lambda kind: drop_site(drop, s.layer + 1, kind)) if drop is not None else None
     K.mark("text_layer_bwd")
     d_out = d_out.reshape(M, C).contiguous()
     # out = LN_o(fa)
     d_fa, d_fa_bf = _e(d_out, (M, C), F32), _e(d_out, (M, C), BF16)
     K.layernorm_bwd(d_out, s.fa, p["output.LayerNorm.weight"], s.mean_o, s.rstd_o, dx=d_fa, dx_bf16=d_fa_bf,
                     dgamma=G.vec("output.LayerNorm.weight", C), dbeta=G.vec("output.LayerNorm.bias", C))
+    if drop is not None:   # the dense branch sees the masked gradient, the residual branch (d_fa) the plain one
+        K.dropout_bwd(d_fa, drop.p, drop.seed, site(DROP_FFN_OUT), out_bf16=d_fa_bf)
     # fa = a + dense2(gelu(dense1(a)))
     G.weight("output.dense.weight", d_fa_bf, s.f_act)
     G.bias("output.dense.bias", d_fa_bf)
@@ -683,10 +714,14 @@ def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True, sink=None):
         alpha = p["alpha_t2i"]
         K.mark("xattn_t2i_bwd")
         G.scalar_dot("alpha_t2i", d_sh, s.c)
-        G.weight("crossattention_t2i.output.dense.weight", d_sh_bf, s.ox.view(M, C), scale_dev=alpha)
-        G.bias("crossattention_t2i.output.dense.bias", d_sh_bf, scale_dev=alpha)
+        d_c_bf = d_sh_bf
+        if drop is not None:
+            d_c_bf = _e(d_out, (M, C), BF16)
+            K.dropout_bwd(d_sh, drop.p, drop.seed, site(DROP_CROSS_OUT), out_bf16=d_c_bf)
+        G.weight("crossattention_t2i.output.dense.weight", d_c_bf, s.ox.view(M, C), scale_dev=alpha)
+        G.bias("crossattention_t2i.output.dense.bias", d_c_bf, scale_dev=alpha)
         d_ox = _e(d_out, (B, S, C), BF16)
-        K.gemm(GEMM_NN, d_sh_bf, w["crossattention_t2i.output.dense.weight"], scale_dev=alpha, out_bf16=d_ox.view(M, C))
+        K.gemm(GEMM_NN, d_c_bf, w["crossattention_t2i.output.dense.weight"], scale_dev=alpha, out_bf16=d_ox.view(M, C))
         dvideo = _e(d_out, (Bv, N, Cv), F32)
         if s.reassoc:
             gw, gb = G.full("cross.kv", (2 * C, Cv)), G.full("cross.kv.bias", (2 * C,))
@@ -708,14 +743,22 @@ def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True, sink=None):
         d_so_bf = _e(d_out, (M, C), BF16)
         K.gemm(GEMM_NN, dqx2, w["crossattention_t2i.self.query.weight"], residual=d_sh, out_bf16=d_so_bf)
         K.mark("text_layer_bwd")
+    if drop is not None:   # so entered sh (and the cross-attention query) through the dropout of roberta.py:342
+        d_so_m = _e(d_out, (M, C), BF16)
+        K.dropout_bwd(d_so_bf, drop.p, drop.seed, site(DROP_SELF_OUT), out_bf16=d_so_m)
+        d_so_bf = d_so_m
     G.weight("attention.output.dense.weight", d_so_bf, s.o.view(M, C))
     G.bias("attention.output.dense.bias", d_so_bf)
     d_o = _e(d_out, (B, S, C), BF16)
     K.gemm(GEMM_NN, d_so_bf, w["attention.output.dense.weight"], out_bf16=d_o.view(M, C))
     qkv3 = s.qkv.view(B, S, 3 * C)
     d_qkv = _e(d_out, (B, S, 3 * C), BF16)
-    K.attention_bwd(s.spec, qkv3[:, :, :C], qkv3[:, :, C:2 * C], qkv3[:, :, 2 * C:], s.o, s.lse, d_o, d_qkv[:, :, :C],
-                    d_qkv[:, :, C:2 * C], d_qkv[:, :, 2 * C:], _e(d_out, s.lse.shape, F32), key_bias=s.key_bias)
+    if drop is None:
+        K.attention_bwd(s.spec, qkv3[:, :, :C], qkv3[:, :, C:2 * C], qkv3[:, :, 2 * C:], s.o, s.lse, d_o, d_qkv[:, :, :C],
+                        d_qkv[:, :, C:2 * C], d_qkv[:, :, 2 * C:], _e(d_out, s.lse.shape, F32), key_bias=s.key_bias)
+    else:
+        K.text_attention_bwd(qkv3[:, :, :C], qkv3[:, :, C:2 * C], qkv3[:, :, 2 * C:], s.key_bias, s.spec.scale, drop.p_attn, drop.seed,
+                             site(DROP_SELF_PROBS), H, s.lse, d_o, d_qkv[:, :, :C], d_qkv[:, :, C:2 * C], d_qkv[:, :, 2 * C:])
     d_qkv2 = d_qkv.view(M, 3 * C)
     G.weight("qkv", d_qkv2, s.h_bf)
     G.bias("qkv.bias", d_qkv2)
@@ -768,8 +811,18 @@ def video_tokens_bwd(K, s, d_tokens, sink=None):
     return G.g
 
 
-def text_embeddings_fwd(K, ids, p, eps=1e-5, pad_id=1, save=True):
-    """RobertaEmbeddings.forward (roberta.py:174-204), eval mode."""
+# dropout sites of one text-tower invocation (roberta.py:203,313,342,422): site id = drop.base + layer slot * 16 + kind
+DROP_EMB, DROP_SELF_PROBS, DROP_SELF_OUT, DROP_CROSS_PROBS, DROP_CROSS_OUT, DROP_FFN_OUT = range(6)
+
+
+def drop_site(drop, layer_slot, kind):
+    """drop: namespace(p (dense outputs / embeddings), p_attn (attention probabilities), seed (device int64 [1]), base (int:
+    unique per text-tower invocation)) -- rng.drop_cfg; layer_slot 0 = embeddings, i + 1 = encoder layer i"""
+    return drop.base + layer_slot * 16 + kind
+
+
+def text_embeddings_fwd(K, ids, p, eps=1e-5, pad_id=1, save=True, drop=None):
+    """RobertaEmbeddings.forward (roberta.py:174-204); `drop` (train mode): the dropout after the LayerNorm (:203)."""
     B, S = ids.shape
     C = p["word_embeddings.weight"].shape[1]
     ids = ids.contiguous()
@@ -780,7 +833,11 @@ def text_embeddings_fwd(K, ids, p, eps=1e-5, pad_id=1, save=True):
     out = _e(pre, (B, S, C), F32)
     mean, rstd = _e(pre, (B * S,), F32), _e(pre, (B * S,), F32)
     K.layernorm_fwd(pre, p["LayerNorm.weight"], p["LayerNorm.bias"], eps, y_f32=out, mean=mean, rstd=rstd)
-    s = types.SimpleNamespace(ids=ids, pre=pre, mean=mean, rstd=rstd, pad_id=pad_id) if save else None
+    if drop is not None:
+        dropped = _e(pre, (B, S, C), F32)
+        K.dropout_add(out, None, drop.p, drop.seed, drop_site(drop, 0, DROP_EMB), out_f32=dropped)
+        out = dropped
+    s = types.SimpleNamespace(ids=ids, pre=pre, mean=mean, rstd=rstd, pad_id=pad_id, drop=drop) if save else None
     return out, s
 
 
@@ -789,7 +846,12 @@ def text_embeddings_bwd(K, s, d_out, p, sink=None):
     K.mark("embed_bwd")
     G = Grads(K, d_out, sink)
     d_pre = _e(d_out, s.pre.shape, F32)
-    K.layernorm_bwd(d_out.contiguous(), s.pre, p["LayerNorm.weight"], s.mean, s.rstd, dx=d_pre,
+    d_out = d_out.contiguous()
+    if s.drop is not None:
+        d_ln = _e(d_out, d_out.shape, F32)
+        K.dropout_bwd(d_out, s.drop.p, s.drop.seed, drop_site(s.drop, 0, DROP_EMB), out_f32=d_ln)
+        d_out = d_ln
+    K.layernorm_bwd(d_out, s.pre, p["LayerNorm.weight"], s.mean, s.rstd, dx=d_pre,
                     dgamma=G.vec("LayerNorm.weight", C), dbeta=G.vec("LayerNorm.bias", C))
     K.text_embed_bwd(d_pre, s.ids, G.full("word_embeddings.weight", tuple(p["word_embeddings.weight"].shape)),
                      G.full("position_embeddings.weight", tuple(p["position_embeddings.weight"].shape)),

@@ -47,6 +47,13 @@ class BGemmArgs(C.Structure):
                 ("accumulate", c_int), ("split_k", c_int), ("epilogue", c_int)]
 
 
+class TextAttnArgs(C.Structure):
+    _fields_ = [("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("ld", c_int64), ("key_bias", c_void_p),
+                ("scale", c_float), ("p_drop", c_float), ("seed_dev", c_void_p), ("site", C.c_uint64),
+                ("B", c_int), ("H", c_int), ("S", c_int), ("o", c_void_p), ("ldo", c_int64), ("lse", c_void_p),
+                ("d_o", c_void_p), ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p), ("ldd", c_int64)]
+
+
 class BV:
     """Batched view of a tensor for `Kernels.bgemm`: base tensor `t` (its data_ptr is element (z0=0, z1=0, row 0, col 0)),
     row stride `ld` and the two batch strides `s0`, `s1` in elements (0 = shared by that batch level)."""
@@ -262,20 +269,25 @@ class Kernels:
         a.accumulate, a.split_k, a.epilogue = int(bool(accumulate)), int(split_k), int(epilogue)
         self._timed("gemm", 2.0 * M * N * K * nb[0] * nb[1], lambda: self._check(self.lib.egv_bgemm_bf16(C.byref(a), self._stream())))
 
-    def xattn_row_softmax(self, scores, ld_s, rows, rows_per_batch, s_bstride, n, P, ld_p, p_bstride, lse, p_drop=0.0, seed=0,
-                          rsum=None):
+    @staticmethod
+    def _seed(seed_dev):
+        assert seed_dev is None or (seed_dev.dtype == torch.int64 and seed_dev.numel() == 1 and seed_dev.is_cuda)
+        return _p(seed_dev)
+
+    def xattn_row_softmax(self, scores, ld_s, rows, rows_per_batch, s_bstride, n, P, ld_p, p_bstride, lse, p_drop=0.0,
+                          seed_dev=None, site=0, rsum=None):
         assert scores.dtype == torch.float32 and P.dtype == torch.bfloat16 and lse.dtype == torch.float32
         self._timed("softmax", 0.0, lambda: self._check(self.lib.egv_xattn_row_softmax(
             _p(scores), c_int64(ld_s), c_int64(rows), rows_per_batch, c_int64(s_bstride), n, _p(P), c_int64(ld_p),
-            c_int64(p_bstride), _p(lse), c_float(p_drop), C.c_uint64(seed), _p(rsum), self._stream())))
+            c_int64(p_bstride), _p(lse), c_float(p_drop), self._seed(seed_dev), C.c_uint64(site), _p(rsum), self._stream())))
 
     def xattn_row_dsoftmax(self, scores, ld_s, rows, rows_per_batch, s_bstride, n, lse, dP, ld_dp, dp_bstride, dS, ld_ds,
-                           ds_bstride, p_drop=0.0, seed=0, row_const=None):
+                           ds_bstride, p_drop=0.0, seed_dev=None, site=0, row_const=None):
         assert scores.dtype == torch.float32 and dP.dtype == torch.float32 and dS.dtype == torch.bfloat16
         self._timed("softmax", 0.0, lambda: self._check(self.lib.egv_xattn_row_dsoftmax(
             _p(scores), c_int64(ld_s), c_int64(rows), rows_per_batch, c_int64(s_bstride), n, _p(lse), _p(dP), c_int64(ld_dp),
-            c_int64(dp_bstride), _p(dS), c_int64(ld_ds), c_int64(ds_bstride), c_float(p_drop), C.c_uint64(seed),
-            _p(row_const), self._stream())))
+            c_int64(dp_bstride), _p(dS), c_int64(ld_ds), c_int64(ds_bstride), c_float(p_drop), self._seed(seed_dev),
+            C.c_uint64(site), _p(row_const), self._stream())))
 
     def xattn_rowscale_bias(self, ox, rsum, bv, B, S, H):
         assert ox.dtype == torch.bfloat16 and ox.stride(1) == 1 and rsum.dtype == torch.float32 and bv.dtype == torch.float32
@@ -296,6 +308,59 @@ class Kernels:
         assert k.dtype == torch.bfloat16 and dbias.dtype == torch.float32 and dbias.is_contiguous()
         self._check(self.lib.egv_xattn_qbias_bwd(_p(k), c_int64(ldk), _p(bq), _p(dbias), c_float(scale), B, S, H, _p(dk),
                                                  c_int64(lddk), _p(dbq), self._stream()))
+
+    # ------------------------------------------------------------------ train-mode dropout of the text tower
+    def rng_advance(self, state):
+        """bump the device-resident step seed (int64 [1]); part of the captured step, so every replay draws new masks"""
+        assert state.dtype == torch.int64 and state.numel() == 1 and state.is_cuda
+        self._check(self.lib.egv_rng_advance(_p(state), self._stream()))
+
+    def dropout_add(self, x, res, p_drop, seed_dev, site, out_f32=None, out_bf16=None, scale=1.0, scale_dev=None):
+        """y = dropout(x); out_f32 = res + scale * (*scale_dev) * y; out_bf16 = bf16(y)"""
+        assert x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
+        for t, dt in ((res, torch.float32), (out_f32, torch.float32), (out_bf16, torch.bfloat16)):
+            assert t is None or (t.dtype == dt and t.is_contiguous() and t.numel() == x.numel())
+        self._check(self.lib.egv_dropout_add(_p(x), int(x.dtype == torch.bfloat16), _p(res), c_float(scale), _p(scale_dev),
+                                             c_float(p_drop), self._seed(seed_dev), C.c_uint64(site), _p(out_f32), _p(out_bf16),
+                                             c_int64(x.numel()), self._stream()))
+
+    def dropout_bwd(self, dy, p_drop, seed_dev, site, out_f32=None, out_bf16=None):
+        assert dy.is_contiguous() and dy.dtype in (torch.float32, torch.bfloat16)
+        for t, dt in ((out_f32, torch.float32), (out_bf16, torch.bfloat16)):
+            assert t is None or (t.dtype == dt and t.is_contiguous() and t.numel() == dy.numel())
+        self._check(self.lib.egv_dropout_bwd(_p(dy), int(dy.dtype == torch.bfloat16), c_float(p_drop), self._seed(seed_dev),
+                                             C.c_uint64(site), _p(out_f32), _p(out_bf16), c_int64(dy.numel()), self._stream()))
+
+    def _text_attn_args(self, q, k, v, key_bias, scale, p_drop, seed_dev, site, H, lse):
+        a = TextAttnArgs()
+        B, S, _ = q.shape
+        ld, bs = self._rows3(q, "q")
+        assert bs == S and self._rows3(k, "k") == (ld, bs) and self._rows3(v, "v") == (ld, bs)
+        a.q, a.k, a.v, a.ld = _p(q), _p(k), _p(v), ld
+        if key_bias is not None:
+            assert key_bias.dtype == torch.float32 and key_bias.is_contiguous() and key_bias.numel() == B * S
+            a.key_bias = _p(key_bias)
+        a.scale, a.p_drop, a.seed_dev, a.site = float(scale), float(p_drop), self._seed(seed_dev), int(site)
+        a.B, a.H, a.S = B, H, S
+        assert lse.dtype == torch.float32 and lse.numel() == B * H * S
+        a.lse = _p(lse)
+        return a
+
+    def text_attention_fwd(self, q, k, v, key_bias, scale, p_drop, seed_dev, site, H, o, lse):
+        """RobertaSelfAttention core with dropout on the probabilities; q / k / v / o: [B, S, H*64] bf16 views"""
+        a = self._text_attn_args(q, k, v, key_bias, scale, p_drop, seed_dev, site, H, lse)
+        a.ldo, bs = self._rows3(o, "o")
+        assert bs == q.shape[1]
+        a.o = _p(o)
+        self._check(self.lib.egv_text_attention_fwd(C.byref(a), self._stream()))
+
+    def text_attention_bwd(self, q, k, v, key_bias, scale, p_drop, seed_dev, site, H, lse, d_o, dq, dk, dv):
+        a = self._text_attn_args(q, k, v, key_bias, scale, p_drop, seed_dev, site, H, lse)
+        a.ldo, bs = self._rows3(d_o, "d_o")
+        a.ldd, bs2 = self._rows3(dq, "dq")
+        assert bs == q.shape[1] and bs2 == bs and self._rows3(dk, "dk") == (a.ldd, bs) and self._rows3(dv, "dv") == (a.ldd, bs)
+        a.d_o, a.dq, a.dk, a.dv = _p(d_o), _p(dq), _p(dk), _p(dv)
+        self._check(self.lib.egv_text_attention_bwd(C.byref(a), self._stream()))
 
     # ------------------------------------------------------------------ LayerNorm
     def layernorm_fwd(self, x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):

@@ -24,6 +24,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import autograd as A
+from .. import rng
 from .. import streams
 from ..lib import ACT_NONE, ACT_RELU, ACT_TANH
 from ..weights import cache
@@ -343,6 +344,8 @@ class FrozenInTime(nn.Module):
         ret, loss_dict = {}, {}
         if 'Feature_Extraction' in task_names:
             return self.compute_video(data['video'])
+        if self.training and torch.is_grad_enabled():
+            rng.advance(data['video'].device)    # new dropout masks for this step (a kernel: captured with the step)
         if 'EgoNCE' not in task_names:
             raise NotImplementedError("MLM / ITM need the EgoNCE branch's similarities (model.py:420,443; SURVEY.md Q11)")
 

@@ -2,8 +2,9 @@
 
 Same module tree / parameter names as the reference.  It does not depend on the
 `transformers` package: the configuration is a plain namespace with the RobertaConfig field names the callers read.
-`RobertaLayer.forward` is one autograd node running the sm_100a kernels; dropout (p=0.1 in the reference's train
-mode, roberta.py:162,244,337,418) is not applied: results equal the reference in eval mode.
+`RobertaLayer.forward` is one autograd node running the sm_100a kernels.  In train mode the reference's dropouts
+(p=0.1: roberta.py:162,203 embeddings; :244,313 attention probabilities; :337,342 and :418,422 dense outputs; the
+text->video cross-attention included) are applied inside those kernels from a Philox stream (egovlpv2_b200/rng.py).
 """
 import types
 
@@ -12,6 +13,7 @@ from torch import nn
 
 from .. import autograd as A
 from .. import functional as Fn
+from .. import rng
 from ..weights import cache
 
 NUM_FUSE_BLOCK = 6   # assigned by FrozenInTime (model.py:141)
@@ -51,13 +53,17 @@ class RobertaEmbeddings(nn.Module):
         self.register_buffer("position_ids", torch.arange(config.max_position_embeddings).expand((1, -1)))
         self.padding_idx = config.pad_token_id
         self._eps = config.layer_norm_eps
+        self._p_attn = config.attention_probs_dropout_prob
 
     def forward(self, input_ids=None, token_type_ids=None, position_ids=None, inputs_embeds=None, past_key_values_length=0):
         if input_ids is None or token_type_ids is not None or position_ids is not None or inputs_embeds is not None:
             raise NotImplementedError("only input_ids with default token types / positions is on the EgoVLPv2 path")
         params = [self.word_embeddings.weight, self.position_embeddings.weight, self.token_type_embeddings.weight,
                   self.LayerNorm.weight, self.LayerNorm.bias]
-        return A.TextEmbedFn.apply(A.cfg(eps=self._eps, pad_id=self.padding_idx), input_ids, *params)
+        drop = None
+        if self.training and torch.is_grad_enabled() and self.dropout.p > 0:
+            drop = rng.drop_cfg(self.dropout.p, self._p_attn, input_ids.device, base=rng.begin_pass())
+        return A.TextEmbedFn.apply(A.cfg(eps=self._eps, pad_id=self.padding_idx, drop=drop), input_ids, *params)
 
 
 class RobertaSelfAttention(nn.Module):
@@ -119,6 +125,7 @@ class RobertaLayer(nn.Module):
         self.output = RobertaOutput(config)
         self.num_heads = config.num_attention_heads
         self._eps = config.layer_norm_eps
+        self.layer_index = 0 if layer_index is None else layer_index
 
     def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None,
                 encoder_attention_mask=None, past_key_value=None, output_attentions=False, last_norm=True):
@@ -150,7 +157,13 @@ class RobertaLayer(nn.Module):
             key_bias = None
         else:   # extended additive mask [B,1,1,S] (0 / finfo.min)
             key_bias = attention_mask.reshape(B, S).float().contiguous()
-        cfg = A.cfg(names=names, H=self.num_heads, eps=self._eps)
+        drop = None
+        p_hidden, p_attn = self.output.dropout.p, self.attention.self.dropout.p
+        if self.training and torch.is_grad_enabled() and (p_hidden > 0 or p_attn > 0):
+            if S > 64:
+                raise NotImplementedError("train-mode dropout of the text tower is implemented for <= 64 tokens (got %d)" % S)
+            drop = rng.drop_cfg(p_hidden, p_attn, hidden_states.device)
+        cfg = A.cfg(names=names, H=self.num_heads, eps=self._eps, drop=drop, layer=self.layer_index)
         out = A.TextLayerFn.apply(cfg, w, pcat, hidden_states, key_bias, encoder_hidden_states, *params)
         return (out,)
 

@@ -146,7 +146,7 @@ def i2t_bwd(K, s, d_out_bf, cs_out, wq, bq, wp, bp, alpha, dalpha, dwq, dbq, dwp
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def t2i_fwd(K, q, x_bf, wk, wv, bv, ox, B, N, H, p_drop=0.0, seed=0):
+def t2i_fwd(K, q, x_bf, wk, wv, bv, ox, B, N, H, p_drop=0.0, seed_dev=None, site=0):
     """q [B*S, C] bf16 (text query projection, bias included); x_bf [B*N, Cv] bf16 (un-normalised video stream entering
     the video block); wk / wv [C, Cv] bf16; bv [C] f32; ox [B*S, C] bf16 is written with the merged heads' context
     (the input of crossattention_t2i.output.dense).  p_drop > 0: dropout on the probabilities (roberta.py:313)."""
@@ -166,7 +166,7 @@ def t2i_fwd(K, q, x_bf, wk, wv, bv, ox, B, N, H, p_drop=0.0, seed=0):
     K.bgemm(GEMM_NT, HS, N, Cv, BV(Qp, Cv, 2 * HS * Cv), BV(x_bf, Cv, N * Cv), nb=(B, 1), out_f32=BV(Sc, Np, HS * Np))
     PdS = _e(q, (B, 2, HS, Np), BF16)              # [b, 0] = P (after dropout), [b, 1] = dS (backward)
     lse, rsum = _e(q, (B * HS,), F32), _e(q, (B * HS,), F32)
-    K.xattn_row_softmax(Sc, Np, B * HS, HS, HS * Np, N, PdS, Np, 2 * HS * Np, lse, p_drop, seed, rsum)
+    K.xattn_row_softmax(Sc, Np, B * HS, HS, HS * Np, N, PdS, Np, 2 * HS * Np, lse, p_drop, seed_dev, site, rsum)
     Zf = _z(q, (B, H, S, Cv))
     K.bgemm(GEMM_NN, HS, Cv, N, BV(PdS, Np, 2 * HS * Np), BV(x_bf, Cv, N * Cv), nb=(B, 1), out_f32=BV(Zf, Cv, HS * Cv),
             accumulate=True)
@@ -181,7 +181,7 @@ def t2i_fwd(K, q, x_bf, wk, wv, bv, ox, B, N, H, p_drop=0.0, seed=0):
         K.bgemm(GEMM_NT, S, HD, Cv, BV(Z, Cv, S * Cv, HS * Cv), BV(wv, wv.stride(0), HD * wv.stride(0), 0), nb=(H, B),
                 bias=BV(bv, 0, HD, 0), out_bf16=BV(ox, C, HD, S * C))
     return types.SimpleNamespace(q=q, x=x_bf, ZQ=ZQ, Sc=Sc, PdS=PdS, lse=lse, rsum=rsum, Z=Z, B=B, N=N, H=H, S=S, Np=Np,
-                                 p_drop=p_drop, seed=seed)
+                                 p_drop=p_drop, seed_dev=seed_dev, site=site)
 
 
 def t2i_bwd(K, s, d_ox, wk, wv, bv, dwk, dwv, dbv, dvideo):
@@ -211,8 +211,8 @@ def t2i_bwd(K, s, d_ox, wk, wv, bv, dwk, dwv, dbv, dvideo):
         # with dropout the value bias no longer cancels in the softmax backward: dP += d_ox_h . bv_h (a row constant)
         crow = _e(d_ox, (B, HS), F32)
         K.xattn_qbias_fwd(d_ox, C, bv, None, 1.0, B, S, H, crow)
-    K.xattn_row_dsoftmax(s.Sc, Np, B * HS, HS, HS * Np, N, s.lse, dPf, Np, HS * Np, dS, Np, 2 * HS * Np, s.p_drop, s.seed,
-                         row_const=crow)
+    K.xattn_row_dsoftmax(s.Sc, Np, B * HS, HS, HS * Np, N, s.lse, dPf, Np, HS * Np, dS, Np, 2 * HS * Np, s.p_drop, s.seed_dev,
+                         s.site, row_const=crow)
     dQpf = _z(d_ox, (B, H, S, Cv))
     K.bgemm(GEMM_NN, HS, Cv, N, BV(dS, Np, 2 * HS * Np), BV(s.x, Cv, N * Cv), nb=(B, 1), out_f32=BV(dQpf, Cv, HS * Cv),
             accumulate=True)

@@ -123,16 +123,17 @@ int egv_bgemm_bf16(const egv_bgemm_args* args, egv_stream_t stream);
  * text -> video (roberta.py:470-486 with 281-321): scores f32 [rows, ld_s] hold, per (clip, head, text query) row, the
  * n = N video-token scores; row r belongs to batch r / rows_per_batch (batch strides in elements).
  * P = softmax(scores) (bf16), lse = log-sum-exp.  p_drop > 0 applies roberta.py:313's dropout to P with a Philox4x32-10
- * stream keyed by (seed, r * n + column): P = keep ? P / (1 - p) : 0, rsum[r] = row sum of the result (1 without dropout). */
+ * stream keyed by (*seed_dev + site constant, r * n + column) -- see "Dropout" below: P = keep ? P / (1 - p) : 0,
+ * rsum[r] = row sum of the result (1 without dropout). */
 int egv_xattn_row_softmax(const float* scores, int64_t ld_s, int64_t rows, int rows_per_batch, int64_t s_bstride, int n,
-                          void* P_bf16, int64_t ld_p, int64_t p_bstride, float* lse, float p_drop, uint64_t seed,
-                          float* rsum, egv_stream_t stream);
+                          void* P_bf16, int64_t ld_p, int64_t p_bstride, float* lse, float p_drop, const uint64_t* seed_dev,
+                          uint64_t site, float* rsum, egv_stream_t stream);
 /* dS = P * (dP~ - sum(P * dP~)), P recomputed from (scores, lse), dP~ = (dP + row_const[r]) * keep / (1 - p) (same Philox
  * stream; row_const, may be NULL, carries the value-bias term d_ctx_h . bv_h, which cancels unless dropout is on) */
 int egv_xattn_row_dsoftmax(const float* scores, int64_t ld_s, int64_t rows, int rows_per_batch, int64_t s_bstride, int n,
                            const float* lse, const float* dP, int64_t ld_dp, int64_t dp_bstride, void* dS_bf16,
-                           int64_t ld_ds, int64_t ds_bstride, float p_drop, uint64_t seed, const float* row_const,
-                           egv_stream_t stream);
+                           int64_t ld_ds, int64_t ds_bstride, float p_drop, const uint64_t* seed_dev, uint64_t site,
+                           const float* row_const, egv_stream_t stream);
 /* value bias under dropout: ox[b*S+s, h*64+j] (bf16, row stride ld) += rsum[b, h*S+s] * bv[h*64+j];  its backward:
  * dbv[h*64+j] += sum_{b,s} rsum[b, h*S+s] * d_ox[b*S+s, h*64+j] */
 int egv_xattn_rowscale_bias(void* ox_bf16, int64_t ld, const float* rsum, const float* bv, int B, int S, int H,
@@ -147,6 +148,38 @@ int egv_xattn_qbias_fwd(const void* k_bf16, int64_t ldk, const float* bq, const 
  * dbq[h*64+j] += scale * sum_{b,s} k[b*S+s, h*64+j] * dbias[b, h*S+s] (may be NULL) */
 int egv_xattn_qbias_bwd(const void* k_bf16, int64_t ldk, const float* bq, const float* dbias, float scale, int B, int S,
                         int H, float* dk, int64_t lddk, float* dbq, egv_stream_t stream);
+
+/* Dropout of the RoBERTa tower in train mode (csrc/dropout.cu, csrc/philox.cuh) --------------------------------------
+ * roberta.py:162,203 (embeddings), :244,313 (attention probabilities), :337,342 (attention output dense), :418,422
+ * (feed-forward output dense); p = 0.1.  Masks come from Philox4x32-10: keep(element i of site s) is a pure function of
+ * (key, i) with key = *seed_dev + s * 0x9E3779B97F4A7C15 (seed_dev NULL = 0).  `seed_dev` is a device-resident uint64
+ * that egv_rng_advance bumps once per training step (inside the captured CUDA graph), `site` an immediate that names
+ * the call site (pass, layer, kind); the backward regenerates the forward's mask from the same pair. */
+int egv_rng_advance(uint64_t* state, egv_stream_t stream);
+/* y = keep ? x / (1 - p) : 0 (x f32 or bf16, n elements); out_f32 (may be NULL) = (res ? res : 0) + scale * (*scale_dev) * y;
+ * out_bf16 (may be NULL) = bf16(y)          -- dense -> dropout -> + residual (roberta.py:341-343, 421-425) */
+int egv_dropout_add(const void* x, int x_is_bf16, const float* res, float scale, const float* scale_dev, float p_drop,
+                    const uint64_t* seed_dev, uint64_t site, float* out_f32, void* out_bf16, int64_t n, egv_stream_t stream);
+/* out = keep ? dy / (1 - p) : 0  (dy f32 or bf16; f32 and / or bf16 outputs) */
+int egv_dropout_bwd(const void* dy, int dy_is_bf16, float p_drop, const uint64_t* seed_dev, uint64_t site, float* out_f32,
+                    void* out_bf16, int64_t n, egv_stream_t stream);
+/* RobertaSelfAttention core with dropout on the probabilities (roberta.py:281-321), S <= 64 tokens, head dim 64:
+ * P = softmax(scale * q k^T + key_bias[b, :]);  o = dropout(P) v.  q / k / v / d* rows are b*S + s with row stride ld
+ * (ldd for gradients), head h at columns h*64; lse [B, H, S] is written by fwd and read by bwd.  Dropout element index =
+ * ((b*H + h)*S + query)*S + key. */
+typedef struct egv_text_attn_args {
+  const void* q; const void* k; const void* v; int64_t ld;     /* bf16 */
+  const float* key_bias;                                      /* [B, S] additive or NULL */
+  float scale, p_drop;
+  const uint64_t* seed_dev; uint64_t site;
+  int B, H, S;
+  void* o; int64_t ldo;                                       /* bf16 */
+  float* lse;
+  const void* d_o;                                            /* bwd: bf16, addressed like o */
+  void* dq; void* dk; void* dv; int64_t ldd;                  /* bwd: bf16 */
+} egv_text_attn_args;
+int egv_text_attention_fwd(const egv_text_attn_args* a, egv_stream_t stream);
+int egv_text_attention_bwd(const egv_text_attn_args* a, egv_stream_t stream);
 
 /* LayerNorm ------------------------------------------------------------------------------------
  * nn.LayerNorm over the last dim C (video_transformer.py:196,207,210,115,304; roberta.py:161,336,417;

@@ -204,18 +204,36 @@ def extended_mask(attention_mask):
     return (1.0 - m) * torch.finfo(torch.float32).min
 
 
+# Train-mode dropout of the text tower (roberta.py:203 embeddings, :313 attention probabilities, :342 / :422 dense outputs).
+# None = eval mode.  Tests install a callable (kind, layer_slot, tensor) -> tensor that replays a given keep mask at the
+# reference's dropout sites (kinds: 0 embeddings, 1 self-attention probabilities, 2 self-attention output dense,
+# 3 cross-attention probabilities, 4 cross-attention output dense, 5 feed-forward output dense; layer_slot 0 = embeddings,
+# i + 1 = encoder layer i), in the reference's call order.
+DROPOUT = None
+
+
+def _drop(kind, slot, x):
+    return x if DROPOUT is None else DROPOUT(kind, slot, x)
+
+
+def _layer_slot(prefix):
+    import re
+    m = re.search(r"layer\.(\d+)\.", prefix)
+    return int(m.group(1)) + 1 if m else 1
+
+
 def roberta_embeddings(input_ids, sd, tprefix="text_model.", pad_id=1, eps=1e-5):
-    """RobertaEmbeddings.forward (roberta.py:174-204) + create_position_ids_from_input_ids (:881-892).
-    Dropout (p=.1) is train-mode only and omitted: parity is defined in eval mode."""
+    """RobertaEmbeddings.forward (roberta.py:174-204) + create_position_ids_from_input_ids (:881-892); dropout (:203)
+    through the DROPOUT hook."""
     nonpad = input_ids.ne(pad_id).to(torch.int64)
     pos_ids = torch.cumsum(nonpad, dim=1) * nonpad + pad_id
     e = tprefix + "embeddings."
     x = sd[e + "word_embeddings.weight"][input_ids] + sd[e + "token_type_embeddings.weight"][0] \
         + sd[e + "position_embeddings.weight"][pos_ids]
-    return _ln(x, sd, e + "LayerNorm", eps)
+    return _drop(0, 0, _ln(x, sd, e + "LayerNorm", eps))
 
 
-def _bert_attention(hq, hkv, mask, sd, prefix, heads):
+def _bert_attention(hq, hkv, mask, sd, prefix, heads, kinds=(1, 2)):
     """RobertaSelfAttention + RobertaSelfOutput.dense (roberta.py:257-343); scores are
     scaled by 1/sqrt(d) *after* QK^T (:303)."""
     q = _heads(_lin(hq, sd, prefix + "self.query"), heads)
@@ -224,7 +242,9 @@ def _bert_attention(hq, hkv, mask, sd, prefix, heads):
     s = (q @ k.transpose(-1, -2)) / math.sqrt(q.shape[-1])
     if mask is not None:
         s = s + mask
-    return _lin(_merge(torch.softmax(s, dim=-1) @ v), sd, prefix + "output.dense")
+    slot = _layer_slot(prefix)
+    p = _drop(kinds[0], slot, torch.softmax(s, dim=-1))                                   # roberta.py:313
+    return _drop(kinds[1], slot, _lin(_merge(p @ v), sd, prefix + "output.dense"))        # roberta.py:341-342
 
 
 def roberta_layer(h, ext_mask, sd, prefix, heads, video=None, eps=1e-5):
@@ -232,10 +252,10 @@ def roberta_layer(h, ext_mask, sd, prefix, heads, video=None, eps=1e-5):
     cross-attention (:470-486; K,V from the *un-normalised* video stream, no mask)."""
     s = _bert_attention(h, h, ext_mask, sd, prefix + "attention.", heads)
     if video is not None:
-        c = _bert_attention(s, video, None, sd, prefix + "crossattention_t2i.", heads)
+        c = _bert_attention(s, video, None, sd, prefix + "crossattention_t2i.", heads, kinds=(3, 4))
         s = sd[prefix + "alpha_t2i"] * c + s
     a = _ln(s + h, sd, prefix + "attention.output.LayerNorm", eps)
-    f = _lin(F.gelu(_lin(a, sd, prefix + "intermediate.dense")), sd, prefix + "output.dense")
+    f = _drop(5, _layer_slot(prefix), _lin(F.gelu(_lin(a, sd, prefix + "intermediate.dense")), sd, prefix + "output.dense"))   # :421-422
     return _ln(f + a, sd, prefix + "output.LayerNorm", eps)
 
 

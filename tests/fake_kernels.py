@@ -453,26 +453,95 @@ class FakeKernels:
         u = (w >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
         return torch.from_numpy(u >= np.float32(p_drop)).to(idx.device)
 
-    def _keep_rows(self, rows, n, p_drop, seed, device):
-        idx = torch.arange(rows, dtype=torch.int64, device=device)[:, None] * n + torch.arange(n, dtype=torch.int64, device=device)[None]
-        return self.philox_keep(seed, idx, p_drop)
+    @staticmethod
+    def philox_key(seed_dev, site):
+        """key of a dropout site (csrc/philox.cuh::philox_key)"""
+        base = 0 if seed_dev is None else int(seed_dev.item()) & 0xFFFFFFFFFFFFFFFF
+        return (base + int(site) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
 
-    def xattn_row_softmax(self, scores, ld_s, rows, rows_per_batch, s_bstride, n, P, ld_p, p_bstride, lse, p_drop=0.0, seed=0,
-                          rsum=None):
+    def _keep_rows(self, rows, n, p_drop, seed_dev, site, device):
+        idx = torch.arange(rows, dtype=torch.int64, device=device)[:, None] * n + torch.arange(n, dtype=torch.int64, device=device)[None]
+        return self.philox_keep(self.philox_key(seed_dev, site), idx, p_drop)
+
+    def keep_mask(self, shape, p_drop, seed_dev, site, device):
+        """keep decisions of a dropout site over a tensor of `shape` (row-major element index)"""
+        n = 1
+        for d in shape:
+            n *= d
+        return self.philox_keep(self.philox_key(seed_dev, site), torch.arange(n, dtype=torch.int64, device=device), p_drop).reshape(shape)
+
+    def rng_advance(self, state):
+        self._launches += 1
+        v = (int(state.item()) + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        state.fill_(v - (1 << 64) if v >= (1 << 63) else v)
+
+    def dropout_add(self, x, res, p_drop, seed_dev, site, out_f32=None, out_bf16=None, scale=1.0, scale_dev=None):
+        self._launches += 1
+        y = x.float() * self.keep_mask(x.shape, p_drop, seed_dev, site, x.device) / (1.0 - p_drop)
+        sc = scale * (float(scale_dev.item()) if scale_dev is not None else 1.0)
+        if out_f32 is not None:
+            out_f32.copy_((0 if res is None else res) + sc * y)
+        if out_bf16 is not None:
+            out_bf16.copy_(y)
+
+    def dropout_bwd(self, dy, p_drop, seed_dev, site, out_f32=None, out_bf16=None):
+        self._launches += 1
+        y = dy.float() * self.keep_mask(dy.shape, p_drop, seed_dev, site, dy.device) / (1.0 - p_drop)
+        if out_f32 is not None:
+            out_f32.copy_(y)
+        if out_bf16 is not None:
+            out_bf16.copy_(y)
+
+    def _text_attn(self, q, k, v, key_bias, scale, p_drop, seed_dev, site, H):
+        B, S, _ = q.shape
+        qh, kh, vh = (t.float().reshape(B, S, H, 64).permute(0, 2, 1, 3) for t in (q, k, v))
+        sc = scale * (qh @ kh.transpose(-1, -2))
+        if key_bias is not None:
+            sc = sc + key_bias.reshape(B, 1, 1, S).clamp_min(-3.0e38)
+        pr = torch.softmax(sc, -1)
+        keep = None
+        if p_drop > 0:
+            keep = self.keep_mask((B, H, S, S), p_drop, seed_dev, site, q.device) / (1.0 - p_drop)
+        return qh, kh, vh, sc, pr, keep
+
+    def text_attention_fwd(self, q, k, v, key_bias, scale, p_drop, seed_dev, site, H, o, lse):
+        self._launches += 1
+        B, S, _ = q.shape
+        qh, kh, vh, sc, pr, keep = self._text_attn(q, k, v, key_bias, scale, p_drop, seed_dev, site, H)
+        lse.copy_(torch.logsumexp(sc, -1).reshape(lse.shape))
+        pd = pr if keep is None else pr * keep
+        o.copy_((pd @ vh).permute(0, 2, 1, 3).reshape(B, S, H * 64))
+
+    def text_attention_bwd(self, q, k, v, key_bias, scale, p_drop, seed_dev, site, H, lse, d_o, dq, dk, dv):
+        self._launches += 1
+        B, S, _ = q.shape
+        qh, kh, vh, sc, pr, keep = self._text_attn(q, k, v, key_bias, scale, p_drop, seed_dev, site, H)
+        g = d_o.float().reshape(B, S, H, 64).permute(0, 2, 1, 3)
+        pd = pr if keep is None else pr * keep
+        dpd = g @ vh.transpose(-1, -2)
+        dp = dpd if keep is None else dpd * keep
+        ds = pr * (dp - (pr * dp).sum(-1, keepdim=True)) * scale
+        back = lambda t: t.permute(0, 2, 1, 3).reshape(B, S, H * 64)  # noqa: E731
+        dq.copy_(back(ds @ kh))
+        dk.copy_(back(ds.transpose(-1, -2) @ qh))
+        dv.copy_(back(pd.transpose(-1, -2) @ g))
+
+    def xattn_row_softmax(self, scores, ld_s, rows, rows_per_batch, s_bstride, n, P, ld_p, p_bstride, lse, p_drop=0.0,
+                          seed_dev=None, site=0, rsum=None):
         self._launches += 1
         nb = rows // rows_per_batch
         sv = scores.as_strided((nb, rows_per_batch, n), (s_bstride, ld_s, 1), scores.storage_offset()).float()
         lse.reshape(-1)[:rows].copy_(torch.logsumexp(sv, -1).reshape(-1))
         pr = torch.softmax(sv, -1)
         if p_drop > 0:
-            keep = self._keep_rows(rows, n, p_drop, seed, scores.device).reshape(nb, rows_per_batch, n)
+            keep = self._keep_rows(rows, n, p_drop, seed_dev, site, scores.device).reshape(nb, rows_per_batch, n)
             pr = pr * keep / (1.0 - p_drop)
         P.as_strided((nb, rows_per_batch, n), (p_bstride, ld_p, 1), P.storage_offset()).copy_(pr)
         if rsum is not None:
             rsum.reshape(-1)[:rows].copy_((pr.sum(-1) if p_drop > 0 else torch.ones_like(pr[..., 0])).reshape(-1))
 
     def xattn_row_dsoftmax(self, scores, ld_s, rows, rows_per_batch, s_bstride, n, lse, dP, ld_dp, dp_bstride, dS, ld_ds,
-                           ds_bstride, p_drop=0.0, seed=0, row_const=None):
+                           ds_bstride, p_drop=0.0, seed_dev=None, site=0, row_const=None):
         self._launches += 1
         nb = rows // rows_per_batch
         sv = scores.as_strided((nb, rows_per_batch, n), (s_bstride, ld_s, 1), scores.storage_offset()).float()
@@ -481,7 +550,7 @@ class FakeKernels:
         if row_const is not None:
             g = g + row_const.reshape(nb, rows_per_batch, 1)
         if p_drop > 0:
-            keep = self._keep_rows(rows, n, p_drop, seed, scores.device).reshape(nb, rows_per_batch, n)
+            keep = self._keep_rows(rows, n, p_drop, seed_dev, site, scores.device).reshape(nb, rows_per_batch, n)
             g = g * keep / (1.0 - p_drop)
         ds = pr * (g - (pr * g).sum(-1, keepdim=True))
         dS.as_strided((nb, rows_per_batch, n), (ds_bstride, ld_ds, 1), dS.storage_offset()).copy_(ds)

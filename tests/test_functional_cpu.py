@@ -98,9 +98,32 @@ def test_video_block(sd, mode, fused):
         assert r <= tol(mode, True), (n, r)
 
 
-@pytest.mark.parametrize("fused", [False, True])
+class DropoutReplay:
+    """oracle.DROPOUT hook: replays the Philox keep masks of the product's dropout sites (functional.drop_site) at the
+    reference's dropout sites"""
+
+    def __init__(self, seed_dev, p, base=None):
+        self.seed_dev, self.p, self.base, self.pass_id, self.calls = seed_dev, p, base, 0, 0
+
+    def __call__(self, kind, slot, x):
+        if kind == 0:
+            self.pass_id += 1
+        base = self.base if self.base is not None else self.pass_id << 16
+        keep = FakeKernels().keep_mask(tuple(x.shape), self.p, self.seed_dev, base + slot * 16 + kind, x.device)
+        self.calls += 1
+        return x * keep / (1.0 - self.p)
+
+
+@pytest.mark.parametrize("fused", [False, True, "dropout", "dropout_fused"])
 def test_text_layer(sd, mode, fused):
+    """'dropout*': train mode -- dropout (p = 0.1) on the attention probabilities and after the dense outputs, the
+    cross-attention included; the oracle replays the very same Philox masks at the reference's dropout sites."""
+    import types
     K = FakeKernels()
+    drop = None
+    if isinstance(fused, str):
+        drop = types.SimpleNamespace(p=0.1, p_attn=0.1, seed=torch.tensor([424242]), base=3 << 16)
+        fused = fused == "dropout_fused"
     prefix = "text_model.encoder.layer.6."
     names = Fn.TEXT_LAYER_PARAMS + (Fn.TEXT_FUSE_PARAMS if fused else [])
     p = block_params(sd, prefix, names)
@@ -118,12 +141,18 @@ def test_text_layer(sd, mode, fused):
     video = torch.randn(B, N, C, generator=g) if fused else None
     am, kb = mask_bias([S, 6, 2])
     d_out = torch.randn(B, S, C, generator=g)
-    out, saved = Fn.text_layer_fwd(K, h, kb, p, w, HEADS, video=video)
+    out, saved = Fn.text_layer_fwd(K, h, kb, p, w, HEADS, video=video, drop=drop, layer=6)
     dh, dvid, grads = Fn.text_layer_bwd(K, saved, d_out, p, w, HEADS)
     sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     hr = h.clone().requires_grad_(True)
     vr = video.clone().requires_grad_(True) if fused else None
-    ref = O.roberta_layer(hr, O.extended_mask(am), sdr, prefix, HEADS, video=vr)
+    if drop is not None:
+        O.DROPOUT = DropoutReplay(drop.seed, drop.p, base=drop.base)
+    try:
+        ref = O.roberta_layer(hr, O.extended_mask(am), sdr, prefix, HEADS, video=vr)
+    finally:
+        hook, O.DROPOUT = O.DROPOUT, None
+    assert drop is None or hook.calls == (5 if fused else 3)
     ref.backward(d_out)
     assert rel(out, ref) <= tol(mode), rel(out, ref)
     assert rel(dh, hr.grad) <= tol(mode, True), rel(dh, hr.grad)
@@ -367,7 +396,7 @@ def test_reassociated_t2i(sd, mode, p_drop):
     cast = lambda t: t.to(Fn.BF16)  # noqa: E731
     ox = torch.empty(B * S, C, dtype=Fn.BF16)
     saved = XR.t2i_fwd(K, cast(q).reshape(B * S, C), cast(x).reshape(B * N, C), cast(wk), cast(wv), bv, ox, B, N, HEADS,
-                       p_drop=p_drop, seed=77)
+                       p_drop=p_drop, seed_dev=None, site=77)
     dwk, dwv, dbv, dx = torch.zeros(C, C), torch.zeros(C, C), torch.zeros(C), torch.empty(B * N, C)
     dq = XR.t2i_bwd(K, saved, cast(dctx).reshape(B * S, C), cast(wk), cast(wv), bv, dwk, dwv, dbv, dx)
     r = {k: v.clone().requires_grad_(True) for k, v in dict(q=q, x=x, wk=wk, bk=bk, wv=wv, bv=bv).items()}
@@ -377,7 +406,7 @@ def test_reassociated_t2i(sd, mode, p_drop):
     pr = torch.softmax(qh @ kh.transpose(-1, -2) / d ** 0.5, dim=-1)          # [B, H, S, N]
     if p_drop > 0:
         rows = torch.arange(B * HEADS * S).reshape(B, HEADS, S, 1)                 # kernel row order: (clip, head, query)
-        keep = FakeKernels.philox_keep(77, rows * N + torch.arange(N), p_drop)
+        keep = FakeKernels.philox_keep(FakeKernels.philox_key(None, 77), rows * N + torch.arange(N), p_drop)
         pr = pr * keep / (1 - p_drop)
     ref = O._merge(pr @ vh)
     ref.backward(dctx)

@@ -749,12 +749,13 @@ def test_xattn_row_kernels(K, R):
     Sc = rnd(B, HS, Np, dtype=torch.float32, scale=3.0, seed=21)
     dP = rnd(B, HS, Np, dtype=torch.float32, seed=22)
     rc = rnd(B, HS, dtype=torch.float32, seed=23)
+    seed_dev = torch.tensor([987654321012345], dtype=torch.int64, device=DEV)
     for p_drop in (0.0, 0.1):
         def run(k):
             PdS = torch.zeros(B, 2, HS, Np, dtype=torch.bfloat16, device=DEV)
             lse, rsum = torch.zeros(B * HS, device=DEV), torch.zeros(B * HS, device=DEV)
-            k.xattn_row_softmax(Sc, Np, B * HS, HS, HS * Np, N, PdS, Np, 2 * HS * Np, lse, p_drop, 1234, rsum)
-            k.xattn_row_dsoftmax(Sc, Np, B * HS, HS, HS * Np, N, lse, dP, Np, HS * Np, PdS[:, 1], Np, 2 * HS * Np, p_drop, 1234,
+            k.xattn_row_softmax(Sc, Np, B * HS, HS, HS * Np, N, PdS, Np, 2 * HS * Np, lse, p_drop, seed_dev, 1234, rsum)
+            k.xattn_row_dsoftmax(Sc, Np, B * HS, HS, HS * Np, N, lse, dP, Np, HS * Np, PdS[:, 1], Np, 2 * HS * Np, p_drop, seed_dev, 1234,
                                  row_const=rc if p_drop > 0 else None)
             return PdS[:, 0, :, :N].contiguous(), PdS[:, 1, :, :N].contiguous(), lse, rsum
         (P, dS, lse, rs), (P_r, dS_r, lse_r, rs_r) = _both(K, R, run)
@@ -818,10 +819,55 @@ def test_reassociated_cross_attention_full_size(K, R):
     for p_drop in (0.0, 0.1):
         def run_t2i(k):
             ox = torch.empty(B * S, C, dtype=torch.bfloat16, device=DEV)
-            s = XR.t2i_fwd(k, q, x, wk, wv, bv, ox, B, N, H, p_drop=p_drop, seed=99)
+            s = XR.t2i_fwd(k, q, x, wk, wv, bv, ox, B, N, H, p_drop=p_drop, seed_dev=None, site=99)
             dwk, dwv, dbv = (torch.zeros(n, device=DEV) for n in ((C, C), (C, C), (C,)))
             dx = torch.empty(B * N, C, device=DEV)
             dq = XR.t2i_bwd(k, s, dox, wk, wv, bv, dwk, dwv, dbv, dx)
             return ox, dq, dx, dwk, dwv, dbv
         for name, a, b in zip(("ox", "dq", "dx", "dwk", "dwv", "dbv"), *_both(K, R, run_t2i)):
             check(a, b, 1.5e-2, "t2i p=%g %s" % (p_drop, name))
+
+
+# ------------------------------------------------------------------------------------------- train-mode dropout (csrc/dropout.cu)
+def test_dropout_kernels_and_text_attention(K, R):
+    """Philox masks identical to the host restatement (bit-for-bit: zero patterns compared exactly), dense-output dropout +
+    residual, its backward, the step-seed advance, and the 32-token self-attention with dropout on the probabilities."""
+    seed = torch.tensor([0x1234567890ABCDE], dtype=torch.int64, device=DEV)
+    seed_r = seed.clone()
+    K.rng_advance(seed)
+    R.rng_advance(seed_r)
+    assert int(seed) == int(seed_r)
+    M, C = 256, 768
+    x32, xb = rnd(M, C, dtype=torch.float32, seed=51), rnd(M, C, seed=52)
+    res = rnd(M, C, dtype=torch.float32, seed=53)
+    alpha = torch.tensor([0.25], device=DEV)
+    for x in (x32, xb):
+        def run(k):
+            o32, o16 = torch.zeros(M, C, device=DEV), torch.zeros(M, C, dtype=torch.bfloat16, device=DEV)
+            k.dropout_add(x, res, 0.1, seed, 77, out_f32=o32, out_bf16=o16, scale=2.0, scale_dev=alpha)
+            g32, g16 = torch.zeros(M, C, device=DEV), torch.zeros(M, C, dtype=torch.bfloat16, device=DEV)
+            k.dropout_bwd(x, 0.1, seed, 77, out_f32=g32, out_bf16=g16)
+            return o32, o16, g32, g16
+        (o32, o16, g32, g16), (o32r, o16r, g32r, g16r) = _both(K, R, run)
+        assert ((o16 == 0) == (o16r == 0)).all() and ((g32 == 0) == (g32r == 0)).all(), "dropout mask differs from Philox restatement"
+        assert abs((o16 == 0).float().mean().item() - 0.1) < 0.01
+        check(o32, o32r, 1e-5, "dropout_add f32")
+        check(o16, o16r, 4e-3, "dropout_add bf16")
+        check(g32, g32r, 1e-5, "dropout_bwd f32")
+        check(g16, g16r, 4e-3, "dropout_bwd bf16")
+    for (B, S, H, p) in ((8, 32, 12, 0.1), (3, 17, 2, 0.1), (2, 64, 12, 0.0)):
+        Cq = H * 64
+        qkv = rnd(B, S, 3 * Cq, seed=54)
+        kb = torch.zeros(B, S, device=DEV)
+        kb[0, S // 2:] = torch.finfo(torch.float32).min
+        d_o = rnd(B, S, Cq, seed=55)
+
+        def run_attn(k):
+            o, lse = torch.zeros(B, S, Cq, dtype=torch.bfloat16, device=DEV), torch.zeros(B * H * S, device=DEV)
+            k.text_attention_fwd(qkv[:, :, :Cq], qkv[:, :, Cq:2 * Cq], qkv[:, :, 2 * Cq:], kb, 0.125, p, seed, 5, H, o, lse)
+            dqkv = torch.zeros(B, S, 3 * Cq, dtype=torch.bfloat16, device=DEV)
+            k.text_attention_bwd(qkv[:, :, :Cq], qkv[:, :, Cq:2 * Cq], qkv[:, :, 2 * Cq:], kb, 0.125, p, seed, 5, H, lse, d_o,
+                                 dqkv[:, :, :Cq], dqkv[:, :, Cq:2 * Cq], dqkv[:, :, 2 * Cq:])
+            return o, lse, dqkv
+        for name, a, b in zip(("o", "lse", "dqkv"), *_both(K, R, run_attn)):
+            check(a, b, 1e-5 if name == "lse" else 6e-3, "text attention S=%d p=%g %s" % (S, p, name))

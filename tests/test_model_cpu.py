@@ -693,3 +693,51 @@ def test_pretrain_step_at_text_length_32_vs_oracle(golden_dir, fake_kernels, mod
         # heads of this 4-clip toy batch are the noisiest tensors (0.45 measured)
         loose = 0.6 if ("txt_proj" in k or "vid_proj" in k) else 0.4
         assert err <= (5e-3 if mode == "exact" else loose), (k, err)
+
+
+def test_train_mode_dropout_step_replayed_through_oracle(golden_dir, fake_kernels):
+    """model.train(): the text tower applies the reference's dropouts (p = 0.1: roberta.py:203,313,342,422, the
+    text->video cross-attention included) from the Philox stream of egovlpv2_b200/rng.py.  The oracle replays the same
+    masks at the reference's dropout sites (three text-tower invocations per step, in the reference's order): losses and
+    every parameter gradient must agree (exact-arithmetic mode), and differ from the eval-mode step."""
+    from egovlpv2_b200 import rng
+    from tests.test_functional_cpu import DropoutReplay
+    old = Fn.BF16
+    Fn.BF16 = torch.float32
+    try:
+        fx, c, shapes, sd, data, plan = _golden(golden_dir)
+        model = build_tiny(c)
+        model.load_state_dict(sd, strict=False)
+        model.train()
+        rng.manual_seed(20240607, "cpu")
+        loss, loss_dict, ret = _step(model, data, plan)
+        loss.backward()
+        seed = rng.seed_tensor("cpu").clone()          # the step seed the forward used (advanced once at its start)
+        assert int(seed) != 20240607
+        sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        O.DROPOUT = DropoutReplay(seed, 0.1)
+        try:
+            ref = O.pretrain_step(data, sdr, c["heads"], c["depth"], c["n_fuse"], plan)
+        finally:
+            hook, O.DROPOUT = O.DROPOUT, None
+        assert hook.pass_id == 3 and hook.calls == 3 * (1 + 3 * c["depth"]) + 2 * 2 * c["n_fuse"]
+        ref["loss_total"].backward()
+        for k in ("EgoNCE", "loss_mlm", "loss_itm", "loss_total"):
+            assert abs(float(loss_dict[k]) - float(ref[k])) <= 3e-4 * max(1.0, abs(float(ref[k]))), (k, float(loss_dict[k]), float(ref[k]))
+        assert abs(float(loss_dict["loss_total"]) - float(fx["loss_total"])) > 1e-3, "train mode equals eval mode: dropout did not run"
+        params = dict(model.named_parameters())
+        for k, v in sdr.items():
+            if v.grad is None or k not in params or v.grad.norm().item() < 1e-5:
+                continue
+            err = ((params[k].grad - v.grad).norm() / v.grad.norm()).item()
+            assert err <= 5e-3, (k, err)
+        # a second step draws different masks (the step seed advanced)
+        model.zero_grad()
+        loss2, _, _ = _step(model, data, plan)
+        assert abs(float(loss2) - float(loss)) > 1e-5
+        # eval mode is untouched by all this
+        model.eval()
+        loss3, _, _ = _step(model, data, plan)
+        assert abs(float(loss3) - float(fx["loss_total"])) <= 3e-4 * abs(float(fx["loss_total"]))
+    finally:
+        Fn.BF16 = old

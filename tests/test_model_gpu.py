@@ -314,3 +314,44 @@ def test_egomcq_style_validation_gpu(golden_dir):
     assert (vtc.cpu() - ovtc).abs().max().item() <= 1.5e-2
     assert (vtm.cpu() - ovtm).abs().max().item() <= 1.5e-2
     assert torch.equal(vtc.argmax(1).cpu(), ovtc.argmax(1)) or (ovtc.topk(2, 1).values.diff(dim=1).abs().min() < 3e-2)
+
+
+def test_train_mode_dropout_step_vs_oracle_replay(golden_dir):
+    """model.train() on the GPU: the text tower's dropouts come from the Philox stream (csrc/dropout.cu, csrc/xattn.cu);
+    the fp32 oracle replays the same masks (tests/test_functional_cpu.py::DropoutReplay) -- same tolerances as the
+    eval-mode golden step; and the step must differ from the eval-mode one."""
+    from egovlpv2_b200 import rng
+    from tests.test_functional_cpu import DropoutReplay
+    fx, c, shapes, sd, data, plan = _golden(golden_dir)
+    model = build_tiny(c)
+    model.load_state_dict(sd, strict=False)
+    model.train().to(DEV)
+    model.itm_plan = plan
+    d = {k: v.to(DEV) for k, v in data.items()}
+    batch = {"video": d["video"], "text": {"input_ids": d["input_ids"], "attention_mask": d["attention_mask"]},
+             "text_mlm_ids": d["text_mlm_ids"], "text_mlm_labels": d["text_mlm_labels"]}
+    args = types.SimpleNamespace(world_size=1, rank=0)
+    rng.manual_seed(777, DEV)
+    loss, loss_dict, ret = model(batch, d["noun_vec"], d["verb_vec"], lambda t, n, a: t, 1, args, {"loss": {"type": "EgoNCE"}},
+                                 EgoNCE(), 0, task_names="EgoNCE_MLM_ITM")
+    loss.backward()
+    torch.cuda.synchronize()
+    seed = rng.seed_tensor(DEV).cpu()
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    O.DROPOUT = DropoutReplay(seed, 0.1)
+    try:
+        ref = O.pretrain_step(data, sdr, c["heads"], c["depth"], c["n_fuse"], plan)
+    finally:
+        O.DROPOUT = None
+    ref["loss_total"].backward()
+    for k in ("EgoNCE", "loss_mlm", "loss_itm", "loss_total"):
+        a, b = float(loss_dict[k]), float(ref[k])
+        assert abs(a - b) <= 2e-2 * max(1.0, abs(b)), (k, a, b)
+    assert abs(float(loss_dict["loss_total"]) - float(fx["loss_total"])) > 1e-3, "train mode equals eval mode"
+    assert (ret["sim_v2t"].cpu() - ref["sim_v2t"].detach()).abs().max().item() <= 1.5e-2
+    params = dict(model.named_parameters())
+    for k in ("text_model.encoder.layer.7.crossattention_t2i.self.query.weight", "text_model.encoder.layer.6.output.dense.weight",
+              "text_model.encoder.layer.0.attention.self.value.weight", "text_model.embeddings.LayerNorm.weight",
+              "mlm_score.decoder.weight", "video_model.blocks.7.attn.qkv_text_i2t.weight"):
+        e = rel(params[k].grad.cpu(), sdr[k].grad)
+        assert e <= 0.4, (k, e)
