@@ -15,9 +15,16 @@ _seeds = {}
 _pass = 0
 
 
+def _norm(device):
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
 def seed_tensor(device):
     """the device-resident step seed (created from torch's global seed on first use)"""
-    device = torch.device(device)
+    device = _norm(device)
     key = (device.type, device.index)
     t = _seeds.get(key)
     if t is None:
@@ -26,11 +33,12 @@ def seed_tensor(device):
 
 
 def manual_seed(seed, device=None):
-    for key, t in list(_seeds.items()):
-        if device is None or key == (torch.device(device).type, torch.device(device).index):
-            t.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
+    """set the step seed of `device` (default: of every device seen so far)"""
     if device is not None:
         seed_tensor(device).fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
+        return
+    for t in _seeds.values():
+        t.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
 
 
 def advance(device):
