@@ -1139,8 +1139,11 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
   const bool small = n_rows <= 32 && n_str <= 64 && groups >= 1024;
   cudaError_t e = cudaSuccess;
   {
-    // large contiguous groups (space attention): group-resident TMA-fed kernels (attention_group.cu)
-    const int r = launch_group_attention(MODE, a, stream);
+    // large contiguous groups (space attention): tcgen05 / TMEM kernel (attention_tc.cu), else the group-resident
+    // TMA-fed mma.sync kernels (attention_group.cu)
+    int r = launch_tc_attention(MODE, a, stream);
+    if (r != 0) return r < 0 ? r : EGV_OK;
+    r = launch_group_attention(MODE, a, stream);
     if (r != 0) return r < 0 ? r : EGV_OK;
   }
   if (small) {
@@ -1281,6 +1284,7 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
 
 using namespace egv;
 
+extern "C" void egv_attention_set_tc(int mode) { set_tc_attention_mode(mode); }
 extern "C" void egv_attention_set_tiny(int mode) { set_tiny_mode(mode); }
 
 extern "C" int64_t egv_attention_workspace_bytes(const egv_attn_args* x) {

@@ -85,6 +85,11 @@ EGV_DEVINL void g_stage(uint8_t* stg, const float (&c)[8][4], float mul0, float 
 // eligible (the caller falls back to the generic kernels), < 0 on error.
 int launch_group_attention(int mode, const AttnP& a, cudaStream_t stream);
 
+// attention_tc.cu: tcgen05 / TMEM kernel for the same problems (space attention, forward).  Same return convention; tried
+// first, the mma.sync kernels of attention_group.cu remain the fallback for shapes it does not cover.
+int launch_tc_attention(int mode, const AttnP& a, cudaStream_t stream);
+void set_tc_attention_mode(int mode);
+
 // gemm.cu: cached bf16 2-D tensor map (`inner` contiguous elements, `outer` rows `ld` elements apart, 128B swizzle)
 int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
                    CUtensorMap* out);

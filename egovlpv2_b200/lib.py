@@ -184,6 +184,9 @@ class Kernels:
     def set_attention_tiny(self, mode):
         self.lib.egv_attention_set_tiny(int(mode))
 
+    def set_attention_tc(self, mode):
+        self.lib.egv_attention_set_tc(int(mode))
+
     def set_plan(self, mode):
         self.lib.egv_gemm_set_plan(int(mode))
 

@@ -239,6 +239,9 @@ int egv_attention_bwd(const egv_attn_args* a, egv_stream_t stream);
 /* fused tiny-group kernels (time attention; csrc/attention_tiny.cu): bit 0 = forward, bit 1 = backward.  Default 3
  * (env EGV_ATTN_TINY); 0 routes those shapes through the generic warp-per-group kernels. */
 void egv_attention_set_tiny(int mode);
+/* tcgen05 / TMEM space-attention kernel (csrc/attention_tc.cu): bit 0 = forward.  Default 1 (env EGV_ATTN_TC); 0 routes
+ * those shapes through the mma.sync group kernels (csrc/attention_group.cu). */
+void egv_attention_set_tc(int mode);
 /* dk/dv row `cls_row` of every batch (+)= the fp32 accumulators dkv_cls [B,H,2,64] filled by egv_attention_bwd */
 int egv_attention_cls_finalize(const float* dkv_cls, void* dk, void* dv, int64_t lddkv, int64_t kv_bstride, int cls_row,
                                int B, int H, int accumulate, egv_stream_t stream);
