@@ -122,6 +122,12 @@ EGV_DEVINL void tma_load_2d(void* dst, const void* tmap, uint64_t* bar, int c0, 
       : "memory");
 }
 
+// Prefetch a 2-D tile into L2 (no shared-memory destination, no completion tracking): turns the HBM latency of data a
+// later phase reads with ordinary loads -- the fp32 residual tile of a GEMM epilogue -- into L2 latency.
+EGV_DEVINL void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
+
 // 2-D tiled load multicast to every CTA of the cluster selected by `mask`: the tile lands at the same CTA-relative
 // shared-memory offset in each destination and completes bytes on the mbarrier at the same offset there.
 EGV_DEVINL void tma_load_2d_mc(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {

@@ -53,6 +53,7 @@ struct GemmParams {
   int vec_ok;  // N % 4 == 0, every row stride % 4 == 0 and every pointer aligned for 4-element vector access
   float* colsum;  // optional [N]: += column sums of the final value (bias gradients), fp32 atomics
   int fast;       // lean full-tile epilogues: 1 / 5 fc1 forward (GELU, pre or derivative saved), 2 / 6 its backward, 3 bf16, 4 residual
+  int prefetch_res;   // the producer prefetches each tile's fp32 residual block into L2 while the tile's mainloop runs
 };
 
 EGV_DEVINL float rcp_approx(float x) {
@@ -411,7 +412,7 @@ struct GemmCfg {
 template <int BN, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
   using Cfg = GemmCfg<BN, CL>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -476,6 +477,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int n0 = (tile % p.num_n_tiles) * BN;
         const int kb0 = ks * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+        // The epilogue of this tile will read its fp32 residual block with ordinary loads, 4 KB in flight per warp: from
+        // HBM that is latency-bound (measured 3.6 TB/s on the out-projections).  Pull the block into L2 now.
+        if (p.prefetch_res && ks == 0) tma_prefetch_l2_2d(&tmap_res, n0, m0);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 64);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -781,13 +785,14 @@ int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
   return EGV_OK;
 }
 
-// bf16 tensor map of rank 2..4 with 128B swizzle: dims[0] = contiguous elements, byte strides of dims 1.. in
-// strides[0..rank-2], box extents per dimension (box[0] must be 64 elements = one swizzle row).
-int get_tensor_map_nd(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                      CUtensorMap* out) {
+// tensor map of rank 2..4: dims[0] = contiguous elements, byte strides of dims 1.. in strides[0..rank-2], box extents per
+// dimension.  f32 = 0: bf16 elements, 128B swizzle (box[0] must be 64 elements = one swizzle row: MMA operand tiles);
+// f32 = 1: fp32 elements, no swizzle (L2 prefetch boxes of the residual stream).
+int get_tensor_map_nd_ex(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                         int f32, CUtensorMap* out) {
   struct Key {
     const void* ptr;
-    int rank;
+    int rank, f32;
     uint64_t d[4], s[3];
     uint32_t b[4];
     bool operator==(const Key& o) const { return memcmp(this, &o, sizeof(Key)) == 0; }
@@ -807,6 +812,7 @@ int get_tensor_map_nd(const void* ptr, int rank, const uint64_t* dims, const uin
   memset(&key, 0, sizeof(key));
   key.ptr = ptr;
   key.rank = rank;
+  key.f32 = f32;
   for (int i = 0; i < rank; ++i) {
     key.d[i] = dims[i];
     key.b[i] = box[i];
@@ -830,8 +836,9 @@ int get_tensor_map_nd(const void* ptr, int rank, const uint64_t* dims, const uin
     es[i] = 1;
     if (i + 1 < rank) st[i] = strides_bytes[i];
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = enc(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                   const_cast<void*>(ptr), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   f32 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(EGV_ERR_CUDA, "cuTensorMapEncodeTiled (rank %d) failed (%d) ptr=%p", rank, (int)r, ptr);
   std::lock_guard<std::mutex> lock(mu);
@@ -840,8 +847,43 @@ int get_tensor_map_nd(const void* ptr, int rank, const uint64_t* dims, const uin
   return EGV_OK;
 }
 
+int get_tensor_map_nd(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      CUtensorMap* out) {
+  return get_tensor_map_nd_ex(ptr, rank, dims, strides_bytes, box, 0, out);
+}
+
+// fp32 2-D tensor map without swizzle (L2 prefetch boxes of the residual stream)
+static int get_tensor_map_f32(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                              CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return EGV_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(EGV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EGV_ERR_CUDA, "cuTensorMapEncodeTiled (f32) failed (%d)", (int)r);
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache[key] = *out;
+  return EGV_OK;
+}
+
 template <int BN, bool A_MN, bool B_MN, int CL>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CL>;
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL>;
@@ -853,7 +895,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   const int units = sm_count() / CL;   // persistent: one CTA (or CTA pair) per SM (pair)
   const int grid = (p.total_items < units ? p.total_items : units) * CL;
   if (CL == 1) {
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tr, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -867,19 +909,19 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tr, p);
     if (e != cudaSuccess) return fail(EGV_ERR_CUDA, "gemm cluster launch: %s", cudaGetErrorString(e));
   }
   return check_launch("gemm_tc_kernel");
 }
 
 template <int BN, int CL>
-static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                          cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch_tc<BN, false, false, CL>(ta, tb, p, s);
-  if (!a_mn && b_mn) return launch_tc<BN, false, true, CL>(ta, tb, p, s);
-  if (a_mn && b_mn) return launch_tc<BN, true, true, CL>(ta, tb, p, s);
-  return launch_tc<BN, true, false, CL>(ta, tb, p, s);
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr,
+                          const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false, CL>(ta, tb, tr, p, s);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true, CL>(ta, tb, tr, p, s);
+  if (a_mn && b_mn) return launch_tc<BN, true, true, CL>(ta, tb, tr, p, s);
+  return launch_tc<BN, true, false, CL>(ta, tb, tr, p, s);
 }
 
 static int g_force_simt = 0;
@@ -925,6 +967,7 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   }
   p.colsum = a->colsum;
   p.fast = 0;
+  p.prefetch_res = 0;
   static const bool no_fast = getenv("EGV_GEMM_NO_FAST") != nullptr;
   if (!no_fast && p.vec_ok && split_k == 1 && !a->accumulate) {
     const bool unit = !a->scale_dev && a->scale == 1.0f;
@@ -1050,16 +1093,29 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
   else rc = get_tensor_map(a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, (uint32_t)(pair ? BN / 2 : BN), &tb);
   if (rc) return rc;
 
+  // L2 prefetch of the fp32 residual blocks (one TMA prefetch per tile, issued by the producer; a hint: results are
+  // unaffected).  OFF by default: measured on B200 (round 2, tools/bgemm_vs_gemm.py) the out-projection shape
+  // M = 25096, N = 768, K = 384 with an fp32 residual got SLOWER (49.2 -> 55.3 us) and the step lost 2 % -- the prefetch
+  // competes with the operand stream for the same L2 -> SM path instead of hiding latency.  EGV_GEMM_RES_PREFETCH=1 enables it.
+  CUtensorMap tr = ta;
+  p.prefetch_res = 0;
+  static const bool no_prefetch = getenv("EGV_GEMM_RES_PREFETCH") == nullptr;
+  if (!no_prefetch && a->residual && (((uintptr_t)a->residual) & 15) == 0 && a->ld_res % 4 == 0 &&
+      (long long)a->M * a->N >= (1ll << 20)) {
+    rc = get_tensor_map_f32(a->residual, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ld_res, (uint32_t)(BN < a->N ? BN : a->N),
+                            BM, &tr);
+    if (rc == EGV_OK) p.prefetch_res = 1;
+  }
   if (pair) {
     switch (BN) {
-      case 256: return dispatch_major<256, 2>(a_mn, b_mn, ta, tb, p, stream);
-      default: return dispatch_major<128, 2>(a_mn, b_mn, ta, tb, p, stream);
+      case 256: return dispatch_major<256, 2>(a_mn, b_mn, ta, tb, tr, p, stream);
+      default: return dispatch_major<128, 2>(a_mn, b_mn, ta, tb, tr, p, stream);
     }
   }
   switch (BN) {
-    case 256: return dispatch_major<256, 1>(a_mn, b_mn, ta, tb, p, stream);
-    case 192: return dispatch_major<192, 1>(a_mn, b_mn, ta, tb, p, stream);
-    case 128: return dispatch_major<128, 1>(a_mn, b_mn, ta, tb, p, stream);
-    default: return dispatch_major<64, 1>(a_mn, b_mn, ta, tb, p, stream);
+    case 256: return dispatch_major<256, 1>(a_mn, b_mn, ta, tb, tr, p, stream);
+    case 192: return dispatch_major<192, 1>(a_mn, b_mn, ta, tb, tr, p, stream);
+    case 128: return dispatch_major<128, 1>(a_mn, b_mn, ta, tb, tr, p, stream);
+    default: return dispatch_major<64, 1>(a_mn, b_mn, ta, tb, tr, p, stream);
   }
 }

@@ -25,6 +25,8 @@ namespace egv {
 
 int get_tensor_map_nd(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                       CUtensorMap* out);
+int get_tensor_map_nd_ex(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                         int f32, CUtensorMap* out);
 
 namespace xg {
 
@@ -50,6 +52,7 @@ struct Params {
   float* colsum; long long scol0, scol1;
   float* dot_out;
   int accumulate, epilogue;
+  int prefetch_res, r_z0, r_z1;   // L2 prefetch of each tile's fp32 residual block by the producer (see gemm.cu)
 };
 
 template <int BN>
@@ -70,6 +73,10 @@ EGV_DEVINL void tma_load_4d(void* dst, const void* tmap, uint64_t* bar, int c0, 
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+EGV_DEVINL void tma_prefetch_l2_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 EGV_DEVINL float ex2(float x) {
   float y;
@@ -181,7 +188,8 @@ EGV_DEVINL void readback(const Params& p, const ItemPtrs& q, const float* stg, i
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
-bgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+bgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const __grid_constant__ CUtensorMap tmap_res, const Params p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -238,6 +246,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const int kb0 = ks * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
         const int az0 = z0 * p.a_z0, az1 = z1 * p.a_z1, bz0 = z0 * p.b_z0, bz1 = z1 * p.b_z1;
+        if (p.prefetch_res && ks == 0) tma_prefetch_l2_4d(&tmap_res, n0, m0, z0 * p.r_z0, z1 * p.r_z1);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 64);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -394,7 +403,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const Params& p, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured = false;
   auto kern = bgemm_kernel<BN, A_MN, B_MN>;
@@ -404,15 +413,15 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
     configured = true;
   }
   const int grid = p.total_items < sm_count() ? p.total_items : sm_count();
-  kern<<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tr, p);
   return check_launch("bgemm_kernel");
 }
 
 template <int BN>
-static int dispatch(int layout, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
-  if (layout == EGV_GEMM_NT) return launch<BN, false, false>(ta, tb, p, s);
-  if (layout == EGV_GEMM_NN) return launch<BN, false, true>(ta, tb, p, s);
-  return launch<BN, true, true>(ta, tb, p, s);
+static int dispatch(int layout, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const Params& p, cudaStream_t s) {
+  if (layout == EGV_GEMM_NT) return launch<BN, false, false>(ta, tb, tr, p, s);
+  if (layout == EGV_GEMM_NN) return launch<BN, false, true>(ta, tb, tr, p, s);
+  return launch<BN, true, true>(ta, tb, tr, p, s);
 }
 
 }  // namespace xg
@@ -520,10 +529,21 @@ extern "C" int egv_bgemm_bf16(const egv_bgemm_args* a, egv_stream_t stream_) {
   if (b_mn) rc = make_map(a->B, (uint64_t)a->N, (uint64_t)a->K, a->ldb, a->sb0, a->sb1, p.b_z0, p.b_z1, xg::BK, &tb);
   else rc = make_map(a->B, (uint64_t)a->K, (uint64_t)a->N, a->ldb, a->sb0, a->sb1, p.b_z0, p.b_z1, (uint32_t)BN, &tb);
   if (rc) return rc;
+  CUtensorMap tr = ta;
+  p.prefetch_res = 0;
+  p.r_z0 = (a->nb0 > 1 && a->sres0 != 0) ? 1 : 0;
+  p.r_z1 = (a->nb1 > 1 && a->sres1 != 0) ? 1 : 0;
+  static const bool res_prefetch = getenv("EGV_GEMM_RES_PREFETCH") != nullptr;   // off by default: see gemm.cu
+  if (res_prefetch && a->residual && (long long)a->M * a->N * batches >= (1ll << 20)) {
+    uint64_t dims[4] = {(uint64_t)a->N, (uint64_t)a->M, (uint64_t)(p.r_z0 ? a->nb0 : 1), (uint64_t)(p.r_z1 ? a->nb1 : 1)};
+    uint64_t st[3] = {(uint64_t)a->ld_res * 4, (uint64_t)(p.r_z0 ? a->sres0 : a->ld_res) * 4, (uint64_t)(p.r_z1 ? a->sres1 : a->ld_res) * 4};
+    uint32_t box[4] = {(uint32_t)(BN < a->N ? BN : a->N), (uint32_t)xg::BM, 1, 1};
+    if (get_tensor_map_nd_ex(a->residual, 4, dims, st, box, 1, &tr) == EGV_OK) p.prefetch_res = 1;
+  }
   switch (BN) {
-    case 256: return xg::dispatch<256>(a->layout, ta, tb, p, stream);
-    case 192: return xg::dispatch<192>(a->layout, ta, tb, p, stream);
-    case 128: return xg::dispatch<128>(a->layout, ta, tb, p, stream);
-    default: return xg::dispatch<64>(a->layout, ta, tb, p, stream);
+    case 256: return xg::dispatch<256>(a->layout, ta, tb, tr, p, stream);
+    case 192: return xg::dispatch<192>(a->layout, ta, tb, tr, p, stream);
+    case 128: return xg::dispatch<128>(a->layout, ta, tb, tr, p, stream);
+    default: return xg::dispatch<64>(a->layout, ta, tb, tr, p, stream);
   }
 }
