@@ -26,10 +26,14 @@ def _sinks(names, params):
     """name -> slice of the flat gradient arena for every parameter that lives in the arena (weights.ParamArena);
     the backward kernels then accumulate in place and autograd gets None for those parameters."""
     from .weights import cache
-    arena = cache().arena
-    if arena is None:
-        return {}
-    return {n: arena.grad_view(p) for n, p in zip(names, params) if id(p) in arena.offsets}
+    out = {}
+    c = cache()
+    for n, p in zip(names, params):
+        arena = c._arena_of(p)
+        if arena is not None:
+            arena.touch(p)
+            out[n] = arena.grad_view(p)
+    return out
 
 
 def _ret(g, name, shape):
@@ -130,8 +134,8 @@ class TextLayerFn(torch.autograd.Function):
         sink = _sinks(cfg.names, params)
         # concatenated q/k/v (and cross k/v) gradients: only when the arena laid the parts out back to back
         from .weights import cache
-        arena = cache().arena
         byname = dict(zip(cfg.names, params))
+        arena = cache()._arena_of(params[0]) if params else None
         cat = {"qkv": ("attention.self.", ("query", "key", "value")),
                "cross.kv": ("crossattention_t2i.self.", ("key", "value"))}
         for key, (pre, parts) in cat.items():

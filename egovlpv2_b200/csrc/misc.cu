@@ -585,6 +585,38 @@ extern "C" int egv_text_embed_bwd(const float* d_out, const int64_t* ids, int B,
   return egv_colsum(d_out, 0, (int64_t)B * S, C, C, d_type0, 1, 1.0f, nullptr, stream);
 }
 
+// Step-dependent scalars of the optimiser, computed ON THE DEVICE from a device-resident step counter: bumps the counter
+// and writes {cosine-with-warm-up LR multiplier (get_cosine_schedule_with_warmup, set_optim_schedule.py:115-119),
+// 1 - beta1^t, 1 - beta2^t}.  Part of the captured step: no host buffer that a later step could overwrite while an earlier
+// replay is still in flight.
+__global__ void adamw_schedule_kernel(long long* __restrict__ step, float* __restrict__ hyper, int warmup_steps, int max_steps,
+                                      float beta1, float beta2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  long long s = step[0];   // optimiser steps completed so far
+  double scale = 1.0;
+  if (max_steps > 0) {
+    if (s < warmup_steps) {
+      scale = (double)s / (double)(warmup_steps > 1 ? warmup_steps : 1);
+    } else {
+      const int span = max_steps - warmup_steps;
+      const double prog = (double)(s - warmup_steps) / (double)(span > 1 ? span : 1);
+      scale = fmax(0.0, 0.5 * (1.0 + cos(3.14159265358979323846 * fmin(1.0, prog))));
+    }
+  }
+  s += 1;
+  step[0] = s;
+  hyper[0] = (float)scale;
+  hyper[1] = (float)(1.0 - pow((double)beta1, (double)s));
+  hyper[2] = (float)(1.0 - pow((double)beta2, (double)s));
+}
+
+extern "C" int egv_adamw_schedule(int64_t* step_dev, float* hyper_dev, int warmup_steps, int max_steps, float beta1, float beta2,
+                                  egv_stream_t stream) {
+  if (!step_dev || !hyper_dev) return fail(EGV_ERR_ARG, "adamw_schedule: null pointer");
+  adamw_schedule_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((long long*)step_dev, hyper_dev, warmup_steps, max_steps, beta1, beta2);
+  return check_launch("adamw_schedule_kernel");
+}
+
 extern "C" int egv_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
                          float beta2, float eps, float weight_decay, float bias_c1, float bias_c2, float grad_scale,
                          const float* hyper_dev, egv_stream_t stream) {

@@ -587,6 +587,12 @@ class Kernels:
                                        c_float(1.0 - beta1 ** step), c_float(1.0 - beta2 ** step), c_float(grad_scale),
                                        _p(hyper_dev), self._stream()))
 
+    def adamw_schedule(self, step_dev, hyper_dev, warmup_steps, max_steps, beta1, beta2):
+        """device-side step counter += 1; hyper_dev <- {LR multiplier, 1 - beta1^t, 1 - beta2^t} (capturable)"""
+        assert step_dev.dtype == torch.int64 and step_dev.numel() == 1 and hyper_dev.dtype == torch.float32 and hyper_dev.numel() == 3
+        self._check(self.lib.egv_adamw_schedule(_p(step_dev), _p(hyper_dev), int(warmup_steps), int(max_steps or 0),
+                                                c_float(beta1), c_float(beta2), self._stream()))
+
     # ------------------------------------------------------------------ NVSwitch P2P all-gather
     def p2p_alloc(self, nbytes):
         ptr = C.c_void_p()

@@ -46,8 +46,9 @@ def _load_yaml_config():
             import yaml
             with open(path) as f:
                 cfg.update(yaml.load(f, Loader=yaml.FullLoader) or {})
-        except Exception:
-            pass
+        except Exception as e:   # the reference would fail at import; falling back silently would hide a broken config
+            import warnings
+            warnings.warn("egovlpv2_b200: could not read %s (%r); using the built-in defaults of EgoNCE_MLM_ITM_Config.yml" % (path, e))
     return cfg
 
 
@@ -103,7 +104,8 @@ class FrozenInTime(nn.Module):
 
         if self.text_params['model'].startswith('roberta'):
             tcfg = dict(text_params.get('config') or {})
-            self.text_model = RobertaModel.from_pretrained(text_params.get('checkpoint', "roberta-base"), **tcfg)
+            self.text_model = RobertaModel.from_pretrained(text_params.get('checkpoint', "roberta-base"),
+                                                           allow_random_init=text_params.get('allow_random_init', False), **tcfg)
         else:
             raise NotImplementedError(f"{text_params['model']} not implemented")
         self.text_model.train()
@@ -367,6 +369,10 @@ class FrozenInTime(nn.Module):
 
         if 'MLM' in task_names:
             ret = self.infer(data, task_names='MLM', ret=ret)
+            if "_mlm_loss_sum" not in ret:   # forward() under torch.no_grad(): infer() produced logits only
+                lg = ret["cross_attn_mlm_logits"]
+                ls, cnt = A.XentFn.apply(lg.reshape(-1, lg.shape[-1]).float(), data['text_mlm_labels'].reshape(-1))
+                ret.update({"_mlm_loss_sum": ls, "_mlm_count": cnt})
             loss_mlm = self._global_mean(ret.pop("_mlm_loss_sum"), ret.pop("_mlm_count"))
             loss = loss + loss_mlm
             loss_dict.update({"loss_mlm": loss_mlm})

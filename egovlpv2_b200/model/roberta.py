@@ -233,16 +233,36 @@ class RobertaModel(nn.Module):
             module.weight.data.fill_(1.0)
 
     @classmethod
-    def from_pretrained(cls, name_or_path="roberta-base", state_dict=None, **kw):
-        """roberta-base architecture.  Weights: `state_dict` or a local file `name_or_path` (torch.save'd state_dict);
-        with neither, the model keeps its random init (there is no network access to the HF hub here)."""
+    def from_pretrained(cls, name_or_path="roberta-base", state_dict=None, allow_random_init=False, **kw):
+        """roberta-base architecture.  Weights, in this order: `state_dict`; a local file `name_or_path` (torch.save'd
+        state_dict); the Hugging Face cache / hub through `transformers` when it is importable (the reference always
+        starts from pretrained roberta-base: model.py:69).  If none of them yields weights the model keeps its random
+        init and says so LOUDLY (a warning; silence it with allow_random_init=True -- synthetic benchmarks and tests)."""
         import os
+        import warnings
+        allow_random_init = allow_random_init or os.environ.get("EGV_ALLOW_RANDOM_INIT", "0") == "1"
         model = cls(RobertaConfig(**kw))
         if state_dict is None and isinstance(name_or_path, str) and os.path.isfile(name_or_path):
             state_dict = torch.load(name_or_path, map_location="cpu")
+        if state_dict is None and not allow_random_init and model.config.hidden_size == 768 and model.config.num_hidden_layers == 12:
+            try:
+                os.environ.setdefault("HF_HUB_OFFLINE", "1")     # never block on the network
+                from transformers import RobertaModel as _HF
+                state_dict = _HF.from_pretrained(name_or_path, add_pooling_layer=False).state_dict()
+            except Exception:
+                state_dict = None
         if state_dict is not None:
             state_dict = {k[len("roberta."):] if k.startswith("roberta.") else k: v for k, v in state_dict.items()}
-            model.load_state_dict(state_dict, strict=False)
+            missing, unexpected = model.load_state_dict(state_dict, strict=False)
+            missing = [k for k in missing if "crossattention_t2i" not in k and "alpha_t2i" not in k and "position_ids" not in k]
+            if missing or unexpected:
+                warnings.warn("RobertaModel.from_pretrained(%r): %d missing keys (e.g. %s), %d unexpected keys (e.g. %s)"
+                              % (name_or_path, len(missing), missing[:3], len(unexpected), list(unexpected)[:3]))
+        elif not allow_random_init:
+            warnings.warn("RobertaModel.from_pretrained(%r): no pretrained weights found (no local file, no Hugging Face cache): "
+                          "the text tower keeps its RANDOM initialisation, unlike the reference, which starts from "
+                          "roberta-base.  Pass state_dict= / a local path, or allow_random_init=True to silence this."
+                          % (name_or_path,))
         return model
 
     def get_input_embeddings(self):

@@ -57,19 +57,22 @@ class FusedAdamW:
         self.groups = [g for g in param_groups(model, lr, weight_decay, lr_mult_head, lr_mult_cross_modal) if g["params"]]
         # a run of adjacent parameters must live inside one hyper-parameter group (q/k/v weights always do)
         self.arena = ParamArena([(g["name"], g["params"]) for g in self.groups], adjacent=adjacency_runs(model))
-        cache().arena = self.arena
-        cache().clear()
+        cache().add_arena(self.arena)
         self.m = torch.zeros_like(self.arena.master)
         self.v = torch.zeros_like(self.arena.master)
         self.betas, self.eps = betas, eps
-        self.step_count = 0
-        # {lr multiplier, 1-beta1^t, 1-beta2^t} on the device: lets a captured CUDA graph serve every step
-        self.hyper_dev = torch.ones(3, dtype=torch.float32, device=self.arena.master.device)
-        self.hyper_host = torch.ones(3, dtype=torch.float32)
-        if self.arena.master.is_cuda:
-            self.hyper_host = self.hyper_host.pin_memory()
+        self.step_count = 0      # host mirror of step_dev (exact in eager use; PretrainStep keeps it in step with graph replays)
+        dev = self.arena.master.device
+        # the step counter and {lr multiplier, 1-beta1^t, 1-beta2^t} live on the device and are advanced by a kernel
+        # (egv_adamw_schedule): a captured CUDA graph serves every step and no host buffer can be overwritten under a
+        # replay that is still in flight
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.hyper_dev = torch.ones(3, dtype=torch.float32, device=dev)
         self.max_steps, self.warmup_steps = max_steps, warmup_steps
         self.arena.bind_grads()
+        # a checkpoint loaded AFTER the optimiser exists (the reference's _resume_checkpoint order) writes the fp32 masters in
+        # place: refresh the bf16 operand shadow right behind it
+        self._hook = model.register_load_state_dict_post_hook(lambda module, incompatible: self.arena.refresh_shadow())
 
     def lr_scale(self):
         """get_cosine_schedule_with_warmup (set_optim_schedule.py:115-119)."""
@@ -84,24 +87,61 @@ class FusedAdamW:
     def zero_grad(self):
         _lib.kernels().zero(self.arena.grad)
         self.arena.bind_grads()
+        self.arena.touched.clear()
 
     def advance(self):
-        """Host part of a step: bump the counter and upload the step-dependent scalars (async H2D, outside any graph)."""
-        scale = self.lr_scale()
+        """Start of an optimiser step (capturable: one tiny kernel): device step counter += 1, schedule scalars refreshed."""
         self.step_count += 1
-        self.hyper_host[0] = scale
-        self.hyper_host[1] = 1.0 - self.betas[0] ** self.step_count
-        self.hyper_host[2] = 1.0 - self.betas[1] ** self.step_count
-        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
+        _lib.kernels().adamw_schedule(self.step_dev, self.hyper_dev, self.warmup_steps, self.max_steps, self.betas[0], self.betas[1])
+
+    def active_ranges(self):
+        """Per hyper-parameter group, the maximal runs of parameters that took part in a forward pass since the last
+        zero_grad() (weights.ParamArena.touch).  The reference's optimiser skips parameters whose .grad is None
+        (transformers.AdamW): e.g. the fusion layers and the MLM / ITM heads under task_names='Dual' get neither an Adam
+        update nor weight decay.  When every parameter was used this is one range per group."""
+        a = self.arena
+        if not a.touched or len(a.touched) == len(a.params):
+            return [(g, lo, hi) for g, (name, lo, hi) in zip(self.groups, a.ranges)]
+        out = []
+        for g in self.groups:
+            run = None
+            for o, n, pid in sorted((a.offsets[id(p)][0], a.offsets[id(p)][1], id(p)) for p in g["params"]):
+                end = (o + n + a.ALIGN - 1) // a.ALIGN * a.ALIGN
+                if pid in a.touched:
+                    if run is not None and o <= run[1]:
+                        run = (run[0], max(run[1], end))
+                    else:
+                        if run is not None:
+                            out.append((g, run[0], run[1]))
+                        run = (o, end)
+                elif run is not None:
+                    out.append((g, run[0], run[1]))
+                    run = None
+            if run is not None:
+                out.append((g, run[0], run[1]))
+        return out
 
     def launch(self, grad_scale=1.0):
-        """Device part of a step (capturable): one fused AdamW launch per hyper-parameter group."""
+        """Device part of a step (capturable): one fused AdamW launch per hyper-parameter group (per run of used parameters)."""
         K = _lib.kernels()
         a = self.arena
-        for g, (name, lo, hi) in zip(self.groups, a.ranges):
+        for g, lo, hi in self.active_ranges():
             K.adamw(a.master[lo:hi], a.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], a.shadow[lo:hi], g["lr"],
                     self.betas[0], self.betas[1], self.eps, g["weight_decay"], 1, grad_scale=grad_scale,
                     hyper_dev=self.hyper_dev)
+
+    # ------------------------------------------------------------------ checkpointing (base_trainer.py:_save / _resume_checkpoint)
+    def state_dict(self):
+        return {"m": self.m.clone(), "v": self.v.clone(), "step": int(self.step_dev.item()), "numel": self.arena.numel,
+                "layout": [(name, lo, hi) for name, lo, hi in self.arena.ranges]}
+
+    def load_state_dict(self, sd):
+        if sd["numel"] != self.arena.numel or [tuple(x) for x in sd["layout"]] != [tuple(x) for x in self.arena.ranges]:
+            raise ValueError("optimizer state was saved for a different parameter layout")
+        self.m.copy_(sd["m"])
+        self.v.copy_(sd["v"])
+        self.step_dev.fill_(int(sd["step"]))
+        self.step_count = int(sd["step"])
 
     def step(self, grad_scale=1.0):
         self.advance()

@@ -25,7 +25,7 @@ def build_model(T=16, img=224, C=768, heads=12, depth=12, n_fuse=6, vocab=50265,
     return FrozenInTime(
         video_params=dict(model="SpaceTimeTransformer", arch_config="base_patch16_224", num_frames=T, pretrained=True,
                           time_init="zeros", img_size=img, embed_dim=C, depth=depth, num_heads=heads),
-        text_params=dict(model="roberta-base", pretrained=True, input="text",
+        text_params=dict(model="roberta-base", pretrained=True, input="text", allow_random_init=True,   # synthetic benchmarks / tests
                          config=dict(hidden_size=C, num_hidden_layers=depth, num_attention_heads=heads,
                                      intermediate_size=4 * C, vocab_size=vocab)),
         projection_dim=proj, config=model_config(C, heads, depth, n_fuse, vocab), task_names=tasks, embed_dim=C)
@@ -88,7 +88,6 @@ class PretrainStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                self.opt.advance()
                 self._device_step(self.static)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
@@ -104,7 +103,7 @@ class PretrainStep:
         for k, v in batch.items():
             if v is not self.static[k]:
                 self.static[k].copy_(v, non_blocking=True)
-        self.opt.advance()
+        self.opt.step_count += 1     # host mirror; the device counter advances inside the graph
         self.graph.replay()
         return self.static_loss, self.static_loss_dict
 
@@ -133,17 +132,17 @@ class PretrainStep:
         for k, v in self._staging.items():
             self.static[k].copy_(v, non_blocking=True)
         self._staging_free.record(main)
-        self.opt.advance()
+        self.opt.step_count += 1
         self.graph.replay()
         return self.static_loss, self.static_loss_dict
 
     def step(self, dev_batch):
         """forward + backward + (all-reduce) + AdamW, eager launches; returns the detached total loss (device scalar)."""
-        self.opt.advance()
         return self._device_step(dev_batch)
 
     def _device_step(self, dev_batch):
         d = dev_batch
+        self.opt.advance()      # device-side step counter / schedule scalars: a kernel, captured with the step
         data = {"video": d["video"], "text": {"input_ids": d["input_ids"], "attention_mask": d["attention_mask"]},
                 "text_mlm_ids": d["text_mlm_ids"], "text_mlm_labels": d["text_mlm_labels"]}
         self.opt.zero_grad()
@@ -166,7 +165,7 @@ def build_dual_model(T=16, img=224, C=768, heads=12, depth=12, n_fuse=6, vocab=5
     return DualFrozenInTime(
         video_params=dict(model="SpaceTimeTransformer", arch_config="base_patch16_224", num_frames=T, pretrained=True,
                           time_init="zeros", drop_path_rate=0.0, img_size=img, embed_dim=C, depth=depth, num_heads=heads),
-        text_params=dict(model="roberta-base", pretrained=True, input="text",
+        text_params=dict(model="roberta-base", pretrained=True, input="text", allow_random_init=True,
                          config=dict(hidden_size=C, num_hidden_layers=depth, num_attention_heads=heads,
                                      intermediate_size=4 * C, vocab_size=vocab)),
         projection="minimal", config=model_config(C, heads, depth, n_fuse, vocab), task_names="EgoNCE_ITM_MLM", embed_dim=C)

@@ -10,6 +10,8 @@ trainer_egoclip.py:143).  Here every GEMM reads a persistent bf16 copy:
   operands in a single launch per hyper-parameter group, and q/k/v (and cross-attention k/v) weights are laid out
   adjacently so their concatenations are plain views.
 """
+import weakref
+
 import torch
 
 from . import functional as _F
@@ -17,14 +19,54 @@ from . import lib as _lib
 
 
 class WeightCache:
+    """Freshness: a copy is reused while the parameter object is the SAME (weak reference: a recycled id() of a freed
+    model never matches), its autograd version counter is unchanged and its storage has not moved.  An update that goes
+    through `p.data` or a raw pointer (older HF AdamW, apex / DeepSpeed fused optimisers, EMA via p.data.copy_) does not bump
+    the version counter: call `invalidate()` after such a step, or `attach(optimizer)` once -- it registers a post-step
+    hook that does."""
+
     def __init__(self):
         self._single = {}
         self._cat = {}
-        self.arena = None
+        self._arenas = []
+
+    @property
+    def arena(self):
+        """the most recently created live parameter arena (FusedAdamW), or None"""
+        self._arenas = [r for r in self._arenas if r() is not None]
+        return self._arenas[-1]() if self._arenas else None
+
+    @arena.setter
+    def arena(self, a):   # tests reset with `cache().arena = None`
+        self._arenas = [] if a is None else [weakref.ref(a)]
+
+    def add_arena(self, a):
+        """several models / optimisers may be alive at once: every arena serves its own parameters"""
+        self._arenas = [r for r in self._arenas if r() is not None] + [weakref.ref(a)]
+        self.clear()
+
+    def _arena_of(self, p):
+        for r in reversed(self._arenas):
+            a = r()
+            if a is not None and a.owns(p):
+                return a
+        return None
 
     def clear(self):
         self._single.clear()
         self._cat.clear()
+
+    def invalidate(self):
+        """forget every cached copy (next use re-casts) and refresh the arenas' bf16 shadows from their fp32 masters"""
+        self.clear()
+        for r in self._arenas:
+            a = r()
+            if a is not None:
+                a.refresh_shadow()
+
+    def attach(self, optimizer):
+        """keep the copies fresh under an external torch optimiser, whatever way it writes the parameters"""
+        return optimizer.register_step_post_hook(lambda *_: self.invalidate())
 
     @staticmethod
     def _stamp(p):
@@ -32,30 +74,48 @@ class WeightCache:
 
     def bf16(self, p, shape2d=None):
         """bf16 copy of parameter `p` (optionally viewed as 2-D `shape2d`)."""
-        if self.arena is not None:
-            v = self.arena.bf16_view(p)
-            if v is not None:
-                return v.view(shape2d) if shape2d is not None else v
+        a = self._arena_of(p)
+        if a is not None:
+            a.touch(p)
+            v = a.bf16_view(p)
+            return v.view(shape2d) if shape2d is not None else v
         key = id(p)
         ent = self._single.get(key)
         st = self._stamp(p)
+        if ent is not None and ent[2]() is not p:
+            ent = None        # id() recycled by another tensor
         if ent is None or ent[0] != st:
             buf = ent[1] if ent is not None and ent[1].numel() == p.numel() and ent[1].device == p.device else \
                 torch.empty(p.shape, dtype=_F.BF16, device=p.device)
             _lib.kernels().cast(p.detach().contiguous(), buf)
-            ent = (st, buf)
+            ent = (st, buf, weakref.ref(p))
             self._single[key] = ent
         return ent[1].view(shape2d) if shape2d is not None else ent[1]
 
+    def _cat_arena(self, params, bf16):
+        a = self._arena_of(params[0])
+        if a is None:
+            return None
+        v = a.cat_view(params, bf16=bf16)
+        if v is not None:
+            for p in params:
+                a.touch(p)
+        return v
+
+    @staticmethod
+    def _same(ent, params):
+        return ent is not None and all(r() is p for r, p in zip(ent[2], params))
+
     def cat_bf16(self, params):
         """bf16 copy of torch.cat(params, 0) (2-D weights with equal inner size)."""
-        if self.arena is not None:
-            v = self.arena.cat_view(params, bf16=True)
-            if v is not None:
-                return v
+        v = self._cat_arena(params, True)
+        if v is not None:
+            return v
         key = tuple(id(p) for p in params)
         st = tuple(self._stamp(p) for p in params)
         ent = self._cat.get(key)
+        if not self._same(ent, params):
+            ent = None
         if ent is None or ent[0] != st:
             rows = sum(p.shape[0] for p in params)
             buf = ent[1] if ent is not None else torch.empty((rows,) + tuple(params[0].shape[1:]), dtype=_F.BF16,
@@ -64,21 +124,22 @@ class WeightCache:
             for p in params:
                 _lib.kernels().cast(p.detach().contiguous(), buf[r:r + p.shape[0]])
                 r += p.shape[0]
-            ent = (st, buf)
+            ent = (st, buf, [weakref.ref(p) for p in params])
             self._cat[key] = ent
         return ent[1]
 
     def cat_f32(self, params):
         """fp32 torch.cat(params, 0) of small vectors (biases); a view when the arena laid them out adjacently."""
-        if self.arena is not None:
-            v = self.arena.cat_view(params, bf16=False)
-            if v is not None:
-                return v
+        v = self._cat_arena(params, False)
+        if v is not None:
+            return v
         key = ("f32",) + tuple(id(p) for p in params)
         st = tuple(self._stamp(p) for p in params)
         ent = self._cat.get(key)
+        if not self._same(ent, params):
+            ent = None
         if ent is None or ent[0] != st:
-            ent = (st, torch.cat([p.detach() for p in params], 0))
+            ent = (st, torch.cat([p.detach() for p in params], 0), [weakref.ref(p) for p in params])
             self._cat[key] = ent
         return ent[1]
 
@@ -126,13 +187,24 @@ class ParamArena:
         self.shadow = torch.zeros(off, dtype=_F.BF16, device=device)
         self.grad = torch.zeros(off, dtype=torch.float32, device=device)
         self.params = [p for _, ps in groups for p in ps]
+        self._refs = {id(p): weakref.ref(p) for p in self.params}
+        self.touched = set()      # ids of the parameters used by a forward pass since the last zero_grad()
         for p in self.params:
             o, n, shp = self.offsets[id(p)]
             self.master[o:o + n].copy_(p.detach().reshape(-1))
             p.data = self.master[o:o + n].view(shp)
         self.refresh_shadow()
 
+    def owns(self, p):
+        r = self._refs.get(id(p))
+        return r is not None and r() is p
+
+    def touch(self, p):
+        self.touched.add(id(p))
+
     def refresh_shadow(self):
+        """bf16 operand shadow <- fp32 masters (after anything but the fused AdamW kernel wrote the parameters:
+        load_state_dict, re-initialisation, an external optimiser)"""
         _lib.kernels().cast(self.master, self.shadow)
 
     def bf16_view(self, p):

@@ -342,6 +342,12 @@ int egv_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_
               float beta2, float eps, float weight_decay, float bias_c1, float bias_c2, float grad_scale,
               const float* hyper_dev, egv_stream_t stream);
 
+/* step_dev[0] (device int64: optimiser steps completed) += 1 and hyper_dev = {LR multiplier of the HF cosine schedule with
+ * warm-up (set_optim_schedule.py:115-119; 1 when max_steps <= 0), 1 - beta1^t, 1 - beta2^t} for the new step t -- computed
+ * on the device so that the whole step, schedule included, replays from one CUDA graph. */
+int egv_adamw_schedule(int64_t* step_dev, float* hyper_dev, int warmup_steps, int max_steps, float beta1, float beta2,
+                       egv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -584,6 +584,20 @@ class FakeKernels:
             dbq.reshape(H, 64).add_((g * kk).sum(0))
 
     # ------------------------------------------------------------------ optimiser
+    def adamw_schedule(self, step_dev, hyper_dev, warmup_steps, max_steps, beta1, beta2):
+        self._launches += 1
+        s = int(step_dev.item())
+        scale = 1.0
+        if max_steps and max_steps > 0:
+            if s < warmup_steps:
+                scale = s / max(1, warmup_steps)
+            else:
+                prog = (s - warmup_steps) / max(1, max_steps - warmup_steps)
+                scale = max(0.0, 0.5 * (1.0 + math.cos(math.pi * min(1.0, prog))))
+        s += 1
+        step_dev.fill_(s)
+        hyper_dev.copy_(torch.tensor([scale, 1.0 - beta1 ** s, 1.0 - beta2 ** s], dtype=torch.float32))
+
     def adamw(self, p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, hyper_dev=None):
         self._launches += 1
         if hyper_dev is not None:

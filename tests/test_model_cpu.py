@@ -741,3 +741,83 @@ def test_train_mode_dropout_step_replayed_through_oracle(golden_dir, fake_kernel
         assert abs(float(loss3) - float(fx["loss_total"])) <= 3e-4 * abs(float(fx["loss_total"]))
     finally:
         Fn.BF16 = old
+
+
+def test_weight_copies_stay_fresh_and_optimizer_state_round_trips(golden_dir, fake_kernels):
+    """Advisor findings of round 1, pinned:
+    (1) an EXTERNAL optimiser that writes parameters through `.data` (no autograd version bump) is covered by
+        WeightCache.attach(); a recycled id() never resurrects a stale copy (weak-reference identity);
+    (2) load_state_dict() AFTER the fused optimiser exists (the reference's resume order) refreshes the bf16 operand
+        shadow of the arena;
+    (3) the device-side schedule kernel reproduces the host cosine-with-warm-up rule and the Adam bias corrections, and
+        FusedAdamW.state_dict / load_state_dict restore m, v and the step counter;
+    (4) parameters that took no part in the step (the MLM / ITM heads and fusion layers under task_names='EgoNCE') get
+        neither an update nor weight decay, like transformers.AdamW skips p.grad is None."""
+    from egovlpv2_b200.optim import FusedAdamW
+    from egovlpv2_b200.trainer import PretrainStep
+    old = Fn.BF16
+    Fn.BF16 = torch.float32
+    try:
+        fx, c, shapes, sd, data, plan = _golden(golden_dir)
+        # ---- (1) external optimiser writing through .data
+        lin = torch.nn.Linear(8, 8)
+        cache = weights.cache()
+        w0 = cache.bf16(lin.weight).clone()
+
+        class DataSGD(torch.optim.Optimizer):
+            def __init__(self, params):
+                super().__init__(params, {})
+
+            def step(self):
+                for g in self.param_groups:
+                    for p in g["params"]:
+                        p.data.add_(1.0)       # leaves p._version untouched
+
+        opt = DataSGD(lin.parameters())
+        v0 = lin.weight._version
+        opt.step()
+        assert lin.weight._version == v0 and torch.equal(cache.bf16(lin.weight), w0), "precondition: the stale copy is what the version check sees"
+        handle = cache.attach(opt)
+        opt.step()
+        assert torch.allclose(cache.bf16(lin.weight).float(), lin.weight.detach(), atol=1e-6)
+        handle.remove()
+        ent_key = id(lin.weight)
+        del lin, opt
+        other = torch.nn.Parameter(torch.zeros(8, 8))
+        cache._single[id(other)] = cache._single.get(ent_key, (None, torch.ones(8, 8), lambda: None))   # simulate a recycled id
+        assert torch.equal(cache.bf16(other).float(), torch.zeros(8, 8)), "a recycled id() must not return another tensor's copy"
+        cache.clear()
+        # ---- (2) + (3) + (4)
+        model = build_tiny(c)
+        model.eval()
+        step = PretrainStep(model, torch.device("cpu"), lr=1e-3, weight_decay=0.1, tasks="EgoNCE", max_steps=10, warmup_steps=3)
+        model.load_state_dict(sd, strict=False)               # after the optimiser: masters written in place
+        a = step.opt.arena
+        assert torch.equal(a.shadow.float(), a.master), "bf16 shadow not refreshed by load_state_dict"
+        batch = {k: v for k, v in data.items()}
+        head0 = model.mlm_score.decoder.weight.detach().clone()
+        fuse0 = model.video_model.blocks[7].attn.proj_i2t.weight.detach().clone()
+        proj0 = model.txt_proj[0].weight.detach().clone()
+        scales = []
+        for i in range(5):
+            step.step(batch)
+            scales.append(float(step.opt.hyper_dev[0]))
+            want = step.opt.step_count - 1
+            host = FusedAdamW.lr_scale(types.SimpleNamespace(max_steps=10, warmup_steps=3, step_count=want))
+            assert abs(scales[-1] - host) <= 1e-6, (i, scales[-1], host)
+            assert abs(float(step.opt.hyper_dev[1]) - (1 - 0.9 ** step.opt.step_count)) <= 1e-6
+            assert abs(float(step.opt.hyper_dev[2]) - (1 - 0.98 ** step.opt.step_count)) <= 1e-6
+        assert int(step.opt.step_dev) == 5 == step.opt.step_count
+        assert torch.equal(model.mlm_score.decoder.weight.detach(), head0), "unused head was decayed"
+        assert torch.equal(model.video_model.blocks[7].attn.proj_i2t.weight.detach(), fuse0), "unused fusion layer was decayed"
+        assert not torch.equal(model.txt_proj[0].weight.detach(), proj0)
+        state = step.opt.state_dict()
+        m_saved = state["m"].clone()
+        step.step(batch)
+        assert not torch.equal(step.opt.m, m_saved)
+        step.opt.load_state_dict(state)
+        assert torch.equal(step.opt.m, m_saved) and int(step.opt.step_dev) == 5 and step.opt.step_count == 5
+    finally:
+        Fn.BF16 = old
+        weights.cache().arena = None
+        weights.cache().clear()
