@@ -175,7 +175,11 @@ class RobertaEncoder(nn.Module):
         self.layer = nn.ModuleList([RobertaLayer(config, layer_index=i) for i in range(config.num_hidden_layers)])
 
     def forward(self, hidden_states, attention_mask=None, **unused):
+        from .. import reduce as _reduce
+        red = _reduce.active()
         for layer in self.layer:
+            if red is not None:
+                red.watch(hidden_states, layer)   # EgoNCE pass: see reduce.OverlappedGradReducer
             hidden_states = layer(hidden_states, attention_mask)[0]
         return types.SimpleNamespace(last_hidden_state=hidden_states)
 

@@ -242,7 +242,11 @@ class SpaceTimeTransformer(nn.Module):
         b, curr_frames = x.shape[:2]
         x = self.tokens(x)
         n, f = self.patches_per_frame, curr_frames
+        from .. import reduce as _reduce
+        red = _reduce.active()
         for i, blk in enumerate(self.blocks):
+            if red is not None:
+                red.watch(x, blk)     # EgoNCE pass: block i's parameter gradients are final once d(loss)/dx_i exists
             # only the CLS row of the last block is consumed below: its per-token tail is skipped
             x = blk(x, self.einops_from_space, self.einops_to_space, self.einops_from_time, self.einops_to_time,
                     time_n=n, space_f=f, cls_only=CLS_ONLY_LAST_BLOCK and i == len(self.blocks) - 1)

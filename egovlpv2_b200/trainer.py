@@ -72,6 +72,12 @@ class PretrainStep:
         else:
             self.allgather = lambda t, n=None, a=None: t
         self.cfg = {"loss": {"type": "EgoNCE"}}
+        # gradient all-reduce in buckets on a communication stream, overlapped with the backward (reduce.py);
+        # EGV_OVERLAP_ALLREDUCE=0: one all-reduce of the whole flat buffer after the backward (round 1)
+        import os
+        from .reduce import OverlappedGradReducer
+        self.reducer = OverlappedGradReducer(self.model, self.opt.arena,
+                                             enabled=os.environ.get("EGV_OVERLAP_ALLREDUCE", "1") != "0") if self.world > 1 else None
         self.two_streams = streams.enable(True)   # text tower on a side stream (env EGV_TEXT_STREAM=0 turns it off)
 
     def to_device(self, host_batch):
@@ -146,13 +152,15 @@ class PretrainStep:
         data = {"video": d["video"], "text": {"input_ids": d["input_ids"], "attention_mask": d["attention_mask"]},
                 "text_mlm_ids": d["text_mlm_ids"], "text_mlm_labels": d["text_mlm_labels"]}
         self.opt.zero_grad()
+        if self.reducer is not None:
+            self.reducer.begin_step()
         loss, loss_dict, _ = self.model(data, d["noun_vec"], d["verb_vec"], self.allgather, self.world, self.args, self.cfg,
                                         self.loss_fn, self.rank, task_names=self.tasks)
         loss.backward()
         # the backward of the text tower ran on the side stream and wrote into the gradient arena directly
         streams.join()
         if self.world > 1:
-            dist.all_reduce(self.opt.arena.grad)          # DDP semantics: average over ranks (base_trainer.py:269)
+            self.reducer.finish()                         # DDP semantics: average over ranks (base_trainer.py:269)
             self.opt.launch(grad_scale=1.0 / self.world)
         else:
             self.opt.launch()

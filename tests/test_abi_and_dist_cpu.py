@@ -223,6 +223,66 @@ def test_two_rank_ddp_static_graph_training_call(golden_dir):
     assert all(r[1].startswith("ok") for r in res), res
 
 
+def _reducer_worker(rank, world, port, q, golden_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from egovlpv2_b200 import functional as Fn
+        from egovlpv2_b200 import lib as L
+        from egovlpv2_b200 import weights
+        from egovlpv2_b200.trainer import PretrainStep
+        from oracle import egovlp_oracle as O
+        from tests.fake_kernels import FakeKernels
+        from tests.test_model_cpu import _golden, build_tiny
+        L.set_kernels(FakeKernels())
+        Fn.BF16 = torch.float32
+        torch.set_num_threads(2)
+        fx, c, shapes, sd, _, _ = _golden(golden_dir)
+        batch = O.synthetic_batch(2, c["T"], c["img"], c["S"], seed=50 + rank)
+        grads = {}
+        for mode in ("1", "0"):
+            os.environ["EGV_OVERLAP_ALLREDUCE"] = mode
+            weights.cache().arena = None
+            model = build_tiny(c)
+            model.load_state_dict(sd, strict=False)
+            model.eval()
+            step = PretrainStep(model, torch.device("cpu"), lr=0.0, weight_decay=0.0, gather="nccl")
+            model.itm_plan = dict(labels=torch.tensor([1., 0.]), swap_video=torch.tensor([False, True]), neg_idx=torch.tensor([1 - rank, 2 * (1 - rank)]))
+            step.step(batch)
+            grads[mode] = step.opt.arena.grad.clone()
+            if mode == "1":
+                calls, done = step.reducer.calls, step.reducer.done
+                assert calls > 2 * c["depth"], calls       # per block / layer buckets, not one call
+                covered = sorted(done)
+                assert covered[0][0] == 0 and max(hi for _, hi in covered) == step.opt.arena.numel
+        # the bucketed, overlapped reduction == one all-reduce of the whole buffer, bit for bit (2 ranks: a + b commutes)
+        assert torch.equal(grads["1"], grads["0"]), (grads["1"] - grads["0"]).abs().max().item()
+        assert grads["1"].abs().sum().item() > 0
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_overlapped_gradient_reduction_equals_single_allreduce(golden_dir):
+    """reduce.OverlappedGradReducer (buckets all-reduced from backward hooks of the EgoNCE pass) on two gloo
+    ranks through trainer.PretrainStep: identical to the single all-reduce of the flat gradient buffer after the backward,
+    i.e. no bucket is sent before its gradients are final (the ITM / MLM passes back-propagate first)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q, golden_dir)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1].startswith("ok") for r in res), res
+
+
 def test_bench_reference_arm_line():
     """`bench.py --impl reference` (the CPU port of the path on the host cores) prints ONE JSON line with the contract's
     keys: impl, metric / unit of our arm, cpu_baseline{kind, cores, sample, value == the line's}, e2e with zero copy bytes."""

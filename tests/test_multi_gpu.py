@@ -33,3 +33,4 @@ def test_p2p_gather_and_multi_rank_step_parity(world):
     assert r.returncode == 0, out[-3000:]
     assert "p2p all-gather == nccl all_gather: ok (%d ranks)" % world in out, out[-2000:]
     assert "multi-rank step parity ok" in out, out[-2000:]
+    assert "overlapped gradient all-reduce == single all-reduce: ok" in out, out[-2000:]
