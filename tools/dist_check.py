@@ -110,10 +110,9 @@ for mode in ("0", "1"):
         ref_grad = gsum
     else:
         assert st.reducer.calls > 2 * c["depth"], st.reducer.calls
-        if world == 2:     # a + b commutes: bit-identical; more ranks: NCCL's reduction order may differ per message size
-            assert torch.equal(gsum, ref_grad), ("overlapped all-reduce differs", (gsum - ref_grad).abs().max().item())
-        else:
-            assert (gsum - ref_grad).norm().item() <= 1e-5 * ref_grad.norm().item()
+        # (the backward itself is not bit-reproducible run to run on the GPU -- split-K / bias-gradient atomics -- so the two
+        # runs are compared to rounding noise; the 2-rank gloo test on CPU pins bit-equality of the reduction logic)
+        assert (gsum - ref_grad).norm().item() <= 1e-5 * ref_grad.norm().item(), (gsum - ref_grad).abs().max().item()
         # and through the captured CUDA graph (the bench path)
         st.capture(loc, warmup=1)
         st.step_graph(loc)
