@@ -188,7 +188,7 @@ def i2t_prep_fwd(K, y, y_bias, p, w, H):
     -> ((Mt, U, bias1), saved)."""
     B, S, Ct = y.shape
     C = w["attn.qkv_i2t.weight"].shape[0]
-    K.mark("xattn_i2t_prep")
+    K.mark("xattn_i2t_fwd_prep")
     s = types.SimpleNamespace(B=B, S=S, Ct=Ct)
     s.y_bf = _e(y, (B * S, Ct), BF16)
     K.cast(y.reshape(B * S, Ct).contiguous(), s.y_bf)
@@ -202,7 +202,7 @@ def i2t_prep_bwd(K, s, dM_b, dU_b, dbias1, p, w, H, G):
     """Backward of i2t_prep_fwd; parameter gradients go into the Grads collector G.  -> dy [B,S,Ct] f32."""
     B, S, Ct = s.B, s.S, s.Ct
     C = w["attn.qkv_i2t.weight"].shape[0]
-    K.mark("xattn_i2t_prep_bwd")
+    K.mark("xattn_i2t_bwd_prep")
     dkv_f = XR.i2t_prep_bwd(K, s.kv_t, w["attn.qkv_i2t.weight"], p["attn.qkv_i2t.bias"], w["attn.proj_i2t.weight"], dM_b, dU_b,
                             dbias1, G.full("attn.qkv_i2t.weight", (C, C)), G.full("attn.qkv_i2t.bias", (C,)),
                             G.full("attn.proj_i2t.weight", (C, C)), B, H)
@@ -249,7 +249,10 @@ def video_block_fwd(K, x, p, w, H, T, Nf, y=None, y_bias=None, eps=1e-5, save=Tr
         xa = _e(x, (M, C), F32)
         K.gemm(GEMM_NT, s.o_s.view(M, C), w["attn.proj.weight"], bias=p["attn.proj.bias"], residual=x2, out_f32=xa,
                out_pre=s.a)
-        K.mark("xattn_i2t_fwd")
+        Sx = 32 if prep is not None else y.shape[1]
+        Ctx = C if prep is not None else y.shape[2]
+        s.alg = float(B) * (4.0 * N * C * C + 4.0 * Sx * Ctx * C + 4.0 * N * Sx * C)   # xattn_i2t per launch
+        K.mark("xattn_i2t_fwd", alg=s.alg)
         s.lnc, s.meanc, s.rstdc = _e(x, (M, C), BF16), _e(x, (M,), F32), _e(x, (M,), F32)
         K.layernorm_fwd(s.a, p["attn.norm_i2t_i.weight"], p["attn.norm_i2t_i.bias"], eps, y_bf16=s.lnc, mean=s.meanc,
                         rstd=s.rstdc)
@@ -322,7 +325,7 @@ def video_block_bwd(K, s, d_out, p, w, H, T, Nf, need_dx=True, sink=None):
     d_s_bf = d_sr_bf
     if s.fused:
         alpha = p["attn.alpha_i2t"]
-        K.mark("xattn_i2t_bwd")
+        K.mark("xattn_i2t_bwd", alg=2.0 * s.alg)
         # sr = x + a + alpha * c,  c = proj_i2t(attention)
         G.bias_from("attn.proj_i2t.bias", cs_sr, scale_dev=alpha)
         if s.reassoc:
@@ -616,7 +619,8 @@ def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True, dro
         K.dropout_add(so_f, h2.contiguous(), drop.p, drop.seed, site(DROP_SELF_OUT), out_f32=sh, out_bf16=s.so_bf)
     if s.fused:
         Bv, N, Cv = video.shape
-        K.mark("xattn_t2i_fwd")
+        s.alg = float(Bv) * (4.0 * S * C * C + 4.0 * N * Cv * C + 4.0 * S * N * C)   # xattn_t2i per launch
+        K.mark("xattn_t2i_fwd", alg=s.alg)
         s.vshape = (Bv, N, Cv)
         s.x_bf = _e(h, (Bv * N, Cv), BF16)
         K.cast(video.reshape(Bv * N, Cv).contiguous(), s.x_bf)
@@ -712,7 +716,7 @@ def text_layer_bwd(K, s, d_out, p, w, H, need_dh=True, sink=None):
     if s.fused:
         Bv, N, Cv = s.vshape
         alpha = p["alpha_t2i"]
-        K.mark("xattn_t2i_bwd")
+        K.mark("xattn_t2i_bwd", alg=2.0 * s.alg)
         G.scalar_dot("alpha_t2i", d_sh, s.c)
         d_c_bf = d_sh_bf
         if drop is not None:

@@ -131,15 +131,20 @@ class Kernels:
     def __init__(self):
         self.lib = _load()
         self.profile = None      # list of (region, kind, work, start_event, stop_event) when profiling is on
+        self.alg = {}            # region -> algorithmic FLOPs of the reference formulation (see mark)
         self._region = "other"
 
     # ------------------------------------------------------------------ per-launch timing (bench.py roofline)
-    def mark(self, region):
-        """Label the kernels launched from here on (cheap; only read while profiling)."""
+    def mark(self, region, alg=0.0):
+        """Label the kernels launched from here on (cheap; only read while profiling).  `alg`: ALGORITHMIC FLOPs of the
+        reference formulation of the region being entered, summed per region while profiling."""
         self._region = region
+        if self.profile is not None and alg:
+            self.alg[region] = self.alg.get(region, 0.0) + alg
 
     def start_profile(self):
         self.profile = []
+        self.alg = {}
 
     def stop_profile(self):
         """-> {(region, kind): (seconds, work, launches)}; call after a stream synchronize."""

@@ -58,7 +58,7 @@ class FakeKernels:
     def force_simt(self, on):
         pass
 
-    def mark(self, region):
+    def mark(self, region, alg=0.0):
         pass
 
     # ------------------------------------------------------------------ GEMM

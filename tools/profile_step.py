@@ -14,7 +14,7 @@ dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 model = build_model(T=T)
 randomize_gates(model)
-model.eval()
+model.train()   # the reference's step runs in train mode (text-tower dropout)
 step = PretrainStep(model, dev)
 batch = step.to_device(synthetic_batch(B, T, 224, 32, seed=1234))
 for _ in range(int(os.environ.get("PROF_WARMUP", "2"))):
