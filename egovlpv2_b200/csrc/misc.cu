@@ -235,6 +235,31 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
   }
 }
 
+// Any patch size (TimeSformer-L/14: p = 14, im2col depth 3 * 14^2 = 588 -- not a multiple of the 8 elements a TMA row stride
+// needs): rows of `ld_out` >= Cin*p*p elements, the tail columns zero-filled (the GEMM runs over the padded depth against a
+// zero-padded weight).  One thread per (patch, channel, patch row): p pixels.
+__global__ void __launch_bounds__(256) patchify_padded_kernel(const float* __restrict__ video, int BT, int Cin, int H, int W,
+                                                              int p, long long ld_out, bf16* __restrict__ out) {
+  const int gw = W / p, gh = H / p;
+  const int Kc = Cin * p * p;
+  const long long total = (long long)BT * gh * gw * Cin * p;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int iy = (int)(i % p);
+    long long r = i / p;
+    const int c = (int)(r % Cin);
+    r /= Cin;                                  // patch index (bt, gy, gx)
+    const int gx = (int)(r % gw);
+    const int gy = (int)((r / gw) % gh);
+    const int bt = (int)(r / ((long long)gw * gh));
+    const float* src = video + (((long long)bt * Cin + c) * H + gy * p + iy) * W + gx * p;
+    bf16* dst = out + r * ld_out + (c * p + iy) * p;
+    for (int j = 0; j < p; ++j) dst[j] = __float2bfloat16(src[j]);
+    if (c == 0 && iy == 0)
+      for (long long j = Kc; j < ld_out; ++j) out[r * ld_out + j] = __float2bfloat16(0.f);
+  }
+}
+
 // Same im2col straight from the decoder's uint8 frames: the reference's loader computes
 // frames.float() / 255 (base_dataset.py:248,300) and NormalizeVideo's (x - mean[c]) / std[c] (transforms.py:49) on the host
 // and ships fp32; here the H2D copy stays uint8 (4x fewer bytes) and the per-channel 256-entry table of
@@ -532,6 +557,16 @@ extern "C" int egv_patchify(const float* video, int BT, int Cin, int H, int W, i
   const long long total = (long long)BT * Cin * H * (W / 8);
   patchify_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(video, BT, Cin, H, W, p, (bf16*)out_bf16);
   return check_launch("patchify_kernel");
+}
+
+extern "C" int egv_patchify_padded(const float* video, int BT, int Cin, int H, int W, int p, int64_t ld_out, void* out_bf16,
+                                   egv_stream_t stream) {
+  if (!video || !out_bf16) return fail(EGV_ERR_ARG, "patchify_padded: null pointer");
+  if (p <= 0 || H % p || W % p) return fail(EGV_ERR_UNSUPPORTED, "patchify_padded: the patch size must divide H and W");
+  if (ld_out < (int64_t)Cin * p * p) return fail(EGV_ERR_ARG, "patchify_padded: row stride shorter than the im2col depth");
+  const long long total = (long long)BT * (H / p) * (W / p) * Cin * p;
+  patchify_padded_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(video, BT, Cin, H, W, p, ld_out, (bf16*)out_bf16);
+  return check_launch("patchify_padded_kernel");
 }
 
 extern "C" int egv_patchify_u8(const uint8_t* video, int BT, int Cin, int H, int W, int p, const float* mean, const float* stdv,

@@ -787,18 +787,27 @@ def video_tokens_fwd(K, video, p, w, cls_token, patch, save=True, norm=None):
     Nf = (Hh // patch) * (Ww // patch)
     C = w["patch_embed.proj.weight"].shape[0]
     K.mark("embed")
-    cols = _e(video, (B * T * Nf, Cin * patch * patch), BF16)
+    Kc = Cin * patch * patch
+    Kp = (Kc + 7) // 8 * 8          # TMA row strides are multiples of 8 elements: patch 14 (TimeSformer-L/14) pads 588 -> 592
+    cols = _e(video, (B * T * Nf, Kp), BF16)
+    wpe = w["patch_embed.proj.weight"]
+    if Kp != Kc:
+        wpad = _z(video, (C, Kp), wpe.dtype)
+        wpad[:, :Kc].copy_(wpe)      # data movement only: the zero-padded operand copy of the convolution weight
+        wpe = wpad
     if video.dtype == torch.uint8:
+        if Kp != Kc:
+            raise NotImplementedError("uint8 frames need a patch size that is a multiple of 8")
         mean, std = norm if norm is not None else (VIDEO_NORM_MEAN, VIDEO_NORM_STD)
         K.patchify_u8(video.reshape(B * T, Cin, Hh, Ww).contiguous(), patch, cols, mean, std)
     else:
         K.patchify(video.reshape(B * T, Cin, Hh, Ww).contiguous(), patch, cols)
     pe = _e(video, (B * T * Nf, C), F32)
-    K.gemm(GEMM_NT, cols, w["patch_embed.proj.weight"], bias=p["patch_embed.proj.bias"], out_f32=pe)
+    K.gemm(GEMM_NT, cols, wpe, bias=p["patch_embed.proj.bias"], out_f32=pe)
     tokens = _e(video, (B, 1 + T * Nf, C), F32)
     K.assemble_tokens(pe, cls_token.reshape(-1).contiguous(), p["pos_embed"].reshape(1 + Nf, C),
                       p["temporal_embed"].reshape(-1, C)[:T].contiguous(), B, T, Nf, tokens)
-    s = types.SimpleNamespace(cols=cols, B=B, T=T, Nf=Nf, C=C, t_max=p["temporal_embed"].shape[1]) if save else None
+    s = types.SimpleNamespace(cols=cols, B=B, T=T, Nf=Nf, C=C, Kc=Kc, t_max=p["temporal_embed"].shape[1]) if save else None
     return tokens, s
 
 
@@ -810,7 +819,12 @@ def video_tokens_bwd(K, s, d_tokens, sink=None):
     d_patch = _e(d_tokens, (B * T * Nf, C), BF16)
     K.assemble_tokens_bwd(d_tokens.contiguous(), B, T, Nf, d_patch, G.full("cls_token", (C,)), G.full("pos_embed", (1 + Nf, C)),
                           G.full("temporal_embed", (s.t_max, C)))
-    G.weight("patch_embed.proj.weight", d_patch, s.cols)
+    if s.cols.shape[1] == s.Kc:
+        G.weight("patch_embed.proj.weight", d_patch, s.cols)
+    else:   # padded im2col depth: the gradient of the real weight is the leading Kc columns
+        dwp = _e(d_tokens, (C, s.cols.shape[1]), F32)
+        K.gemm(GEMM_TN, d_patch, s.cols, out_f32=dwp)
+        K.axpy_rows(G.full("patch_embed.proj.weight", (C, s.Kc)), dwp[:, :s.Kc])
     G.bias("patch_embed.proj.bias", d_patch)
     return G.g
 

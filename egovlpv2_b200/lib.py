@@ -504,10 +504,17 @@ class Kernels:
 
     # ------------------------------------------------------------------ embeddings
     def patchify(self, video, p, out):
+        """im2col of [BT, Cin, H, W] fp32 frames into out [BT*gh*gw, ld] bf16 (ld = Cin*p*p, or that rounded up to 8 with
+        zero-filled tail columns when the patch size is not a multiple of 8)"""
         BT, Cin, H, W = video.shape
-        assert video.dtype == torch.float32 and video.is_contiguous() and out.dtype == torch.bfloat16
-        assert out.is_contiguous() and out.numel() == video.numel()
-        self._check(self.lib.egv_patchify(_p(video), BT, Cin, H, W, p, _p(out), self._stream()))
+        assert video.dtype == torch.float32 and video.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+        Kc = Cin * p * p
+        rows = BT * (H // p) * (W // p)
+        assert out.dim() == 2 and out.shape[0] == rows and out.shape[1] >= Kc
+        if out.shape[1] == Kc and p % 8 == 0:
+            self._check(self.lib.egv_patchify(_p(video), BT, Cin, H, W, p, _p(out), self._stream()))
+        else:
+            self._check(self.lib.egv_patchify_padded(_p(video), BT, Cin, H, W, p, c_int64(out.shape[1]), _p(out), self._stream()))
 
     def patchify_u8(self, video, p, out, mean, std):
         """uint8 frames -> normalised bf16 patches; mean / std: per-channel sequences (transforms.py:49)."""

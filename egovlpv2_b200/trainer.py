@@ -21,10 +21,10 @@ def model_config(C=768, heads=12, depth=12, n_fuse=6, vocab=50265):
                 num_layers=depth, num_fuse_block=n_fuse, vocab_size=vocab)
 
 
-def build_model(T=16, img=224, C=768, heads=12, depth=12, n_fuse=6, vocab=50265, proj=4096, tasks="EgoNCE_ITM_MLM"):
+def build_model(T=16, img=224, C=768, heads=12, depth=12, n_fuse=6, vocab=50265, proj=4096, tasks="EgoNCE_ITM_MLM", patch=16):
     return FrozenInTime(
         video_params=dict(model="SpaceTimeTransformer", arch_config="base_patch16_224", num_frames=T, pretrained=True,
-                          time_init="zeros", img_size=img, embed_dim=C, depth=depth, num_heads=heads),
+                          time_init="zeros", img_size=img, patch_size=patch, embed_dim=C, depth=depth, num_heads=heads),
         text_params=dict(model="roberta-base", pretrained=True, input="text", allow_random_init=True,   # synthetic benchmarks / tests
                          config=dict(hidden_size=C, num_hidden_layers=depth, num_attention_heads=heads,
                                      intermediate_size=4 * C, vocab_size=vocab)),

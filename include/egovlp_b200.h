@@ -272,6 +272,10 @@ int egv_add_rows_f32(float* y, int64_t ldy, const float* x, int64_t ldx, int row
 /* Patch embedding (video_transformer.py:78-83, 354-372; model.py:211-232) -------------------------
  * im2col: video f32 [BT, 3, H, W] -> bf16 [BT*gh*gw, 3*p*p] (column order c,i,j = Conv2d weight order) */
 int egv_patchify(const float* video, int BT, int Cin, int H, int W, int p, void* out_bf16, egv_stream_t stream);
+/* any patch size (e.g. 14: TimeSformer-L/14, BASELINE cfg 5): rows of ld_out >= Cin*p*p elements (a multiple of 8 for the
+ * GEMM's TMA maps), columns beyond Cin*p*p zero-filled; the GEMM then runs over the padded depth against a zero-padded weight */
+int egv_patchify_padded(const float* video, int BT, int Cin, int H, int W, int p, int64_t ld_out, void* out_bf16,
+                        egv_stream_t stream);
 /* the same im2col from uint8 frames, fused with the loader's frames.float() / 255 (base/base_dataset.py:248,300) and
  * NormalizeVideo's (x - mean[c]) / std[c] (data_loader/transforms.py:49): video u8 [BT, Cin, H, W]; mean / std = HOST
  * arrays of Cin floats (Cin <= 4).  Output bit-identical to egv_patchify on the host-normalised fp32 frames. */

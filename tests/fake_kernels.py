@@ -254,7 +254,11 @@ class FakeKernels:
         BT, Cin, H, W = video.shape
         gh, gw = H // p, W // p
         x = video.reshape(BT, Cin, gh, p, gw, p).permute(0, 2, 4, 1, 3, 5).reshape(BT * gh * gw, Cin * p * p)
-        out.copy_(x.reshape(out.shape))
+        if out.shape[-1] == Cin * p * p:
+            out.copy_(x.reshape(out.shape))
+        else:   # padded im2col depth (patch sizes that are not multiples of 8): zero tail columns
+            out.zero_()
+            out[:, :Cin * p * p] = x.to(out.dtype)
 
     def patchify_u8(self, video, p, out, mean, std):
         # the reference's host pipeline: frames.float() / 255 (base_dataset.py:248), NormalizeVideo (transforms.py:49)

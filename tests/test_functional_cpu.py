@@ -415,3 +415,32 @@ def test_reassociated_t2i(sd, mode, p_drop):
         e = rel(got.reshape(-1), r[name].grad.reshape(-1))
         assert e <= tol(mode, True), (name, e)
     assert r["bk"].grad.abs().max().item() <= 1e-5 or p_drop > 0    # the key bias is softmax-invariant without dropout
+
+
+def test_video_tokens_patch14_padded_im2col(mode):
+    """TimeSformer-L/14 (BASELINE cfg 5): patch 14 gives an im2col depth of 3 * 14^2 = 588, not a multiple of the 8 elements
+    a TMA row stride needs; the patch GEMM runs over the depth padded to 592 against a zero-padded weight
+    (egv_patchify_padded).  Tokens and every gradient against the oracle's Conv2d."""
+    K = FakeKernels()
+    T14, IMG14, P14 = 2, 28, 14
+    shapes = O.key_shapes(C=C, heads=HEADS, depth=7, n_fuse=1, T=T14, img=IMG14, patch=P14, vocab=97, proj=256)
+    sd14 = O.seeded_state(shapes, seed=5)
+    g = torch.Generator().manual_seed(4)
+    video = torch.randn(B, T14, 3, IMG14, IMG14, generator=g)
+    vp = "video_model."
+    p = {k: sd14[vp + k] for k in ("patch_embed.proj.bias", "pos_embed", "temporal_embed")}
+    w = {"patch_embed.proj.weight": sd14[vp + "patch_embed.proj.weight"].reshape(C, -1).to(Fn.BF16)}
+    assert w["patch_embed.proj.weight"].shape[1] == 588
+    tokens, saved = Fn.video_tokens_fwd(K, video, p, w, sd14["cls_token"], P14)
+    assert saved.cols.shape[1] == 592 and float(saved.cols[:, 588:].float().abs().max()) == 0.0
+    n14 = 1 + T14 * (IMG14 // P14) ** 2
+    d_tok = torch.randn(B, n14, C, generator=g)
+    grads = Fn.video_tokens_bwd(K, saved, d_tok)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd14.items()}
+    ref = O.video_tokens(video, sdr, sdr["cls_token"])
+    ref.backward(d_tok)
+    assert rel(tokens, ref) <= tol(mode)
+    assert rel(grads["patch_embed.proj.weight"].reshape(-1), sdr[vp + "patch_embed.proj.weight"].grad.reshape(-1)) <= tol(mode, True)
+    for k, name in (("patch_embed.proj.bias", vp + "patch_embed.proj.bias"), ("pos_embed", vp + "pos_embed"),
+                    ("temporal_embed", vp + "temporal_embed"), ("cls_token", "cls_token")):
+        assert rel(grads[k].reshape(-1), sdr[name].grad.reshape(-1)) <= tol(mode, True), k
