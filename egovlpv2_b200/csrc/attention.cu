@@ -532,6 +532,7 @@ EGV_DEVINL void attn_unit(const AttnP& a, long long item, uint8_t* smem_unit, in
 // CTA-per-item variant (large groups): NW warps cooperate on one item.
 template <int MODE, int NW, int KC, int NCH = 1, bool SPLIT = false>
 __global__ void __launch_bounds__(NW * 32) attn_cta_kernel(const AttnP a) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t smem_attn[];
   for (long long item = blockIdx.x; item < a.items; item += gridDim.x) {
     attn_unit<MODE, NW, KC, NCH, SPLIT>(a, item, smem_attn, threadIdx.x);
@@ -542,6 +543,7 @@ __global__ void __launch_bounds__(NW * 32) attn_cta_kernel(const AttnP a) {
 // Warp-per-item variant (small groups): 4 independent warps per CTA, no block-level sync.
 template <int MODE, int KC>
 __global__ void __launch_bounds__(128) attn_warp_kernel(const AttnP a) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int warp = threadIdx.x >> 5;
   uint8_t* mine = smem_attn + warp * AttnSmem<MODE, 1, KC>::BYTES;
@@ -559,6 +561,7 @@ __global__ void __launch_bounds__(128) attn_warp_kernel(const AttnP a) {
 constexpr int SQ_WARPS = 16;
 
 __global__ void __launch_bounds__(SQ_WARPS * 32) attn_single_fwd_kernel(const AttnP a) {
+  pdl_enter();
   __shared__ float sm_m[SQ_WARPS], sm_l[SQ_WARPS];
   __shared__ float sm_o[SQ_WARPS][HD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -634,6 +637,7 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) attn_single_fwd_kernel(const At
 // Backward of the single-query attention: P_j = exp2(s_j - lse), dP_j = dO . v_j, dS_j = P_j (dP_j - delta);
 // dq = scale * sum_j dS_j k_j;  dk_j (+)= scale * dS_j q;  dv_j (+)= P_j dO.  The shared CLS key goes to dkv_cls.
 __global__ void __launch_bounds__(SQ_WARPS * 32) attn_single_bwd_kernel(const AttnP a) {
+  pdl_enter();
   __shared__ float sm_q[SQ_WARPS][HD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = blockIdx.x % a.G;
@@ -746,6 +750,7 @@ EGV_DEVINL float red8(float s) {   // sum over the 8 lanes that share a head
 // partial layout: part[((b * n_split + split) * H + h) * 66 + {0: m, 1: l, 2..65: o}]
 template <int NG>
 __global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_fwd_heads_kernel(const AttnP a, float* __restrict__ part) {
+  pdl_enter();
   __shared__ float sm_m[SQH_WARPS][NG * 4], sm_l[SQH_WARPS][NG * 4];
   __shared__ float sm_o[SQH_WARPS][NG * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -831,6 +836,7 @@ __global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_fwd_heads_kernel(c
 }
 
 __global__ void __launch_bounds__(64) attn_single_combine_kernel(const AttnP a, const float* __restrict__ part) {
+  pdl_enter();
   __shared__ float sm_f[SQ_SPLITS_MAX];   // 2^(m_s - M) per split
   __shared__ float sm_ml[2];
   const int h = blockIdx.x % a.H, b = blockIdx.x / a.H;
@@ -867,6 +873,7 @@ __global__ void __launch_bounds__(64) attn_single_combine_kernel(const AttnP a, 
 // out by attn_single_dq_finalize_kernel.
 template <int NG>
 __global__ void __launch_bounds__(SQH_WARPS * 32) attn_single_bwd_heads_kernel(const AttnP a, float* dq_acc, int* counters) {
+  pdl_enter();
   __shared__ float sm_q[SQH_WARPS][NG * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int split = blockIdx.x % a.n_split, b = blockIdx.x / a.n_split;
@@ -1022,6 +1029,7 @@ static bool single_heads_ok(const AttnP& a) {
 // fp32 CLS accumulators -> bf16 rows of the dk / dv tensors
 __global__ void attn_cls_finalize_kernel(const float* __restrict__ dkv_cls, bf16* dk, bf16* dv, long long lddkv,
                                          long long kv_bstride, int cls_row, int B, int H, int accumulate) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H * HD) return;
   const int d = idx % HD, h = (idx / HD) % H, b = idx / (HD * H);
@@ -1039,6 +1047,7 @@ __global__ void attn_cls_finalize_kernel(const float* __restrict__ dkv_cls, bf16
 // Merge the per-split partials of attn_unit (n_split > 1): one 64-thread block per (item, row).
 template <int MODE>
 __global__ void __launch_bounds__(64) attn_split_finalize_kernel(const AttnP a, int rows_cap) {
+  pdl_enter();
   constexpr int W = MODE == MODE_FWD ? 66 : (MODE == MODE_DQ ? 64 : 128);
   const int n_rows = (MODE == MODE_DKV) ? a.LkT : a.Lq;
   const long long item_ns = blockIdx.x / rows_cap;
@@ -1160,7 +1169,7 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
     long long grid = cdiv(a.items, 4);
     const long long cap = (long long)sm_count() * 64;
     if (grid > cap) grid = cap;
-    if (e == cudaSuccess) kern<<<(unsigned)grid, 128, smem, stream>>>(a);
+    if (e == cudaSuccess) launch_k(kern, dim3((unsigned)grid), dim3(128), smem, stream, a);
   } else if (n_rows <= 16) {
     // few rows, long stream (CLS query; tiny text batches): one warp is all the row side can use
     constexpr int KC = 64;
@@ -1181,11 +1190,11 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
       cfg = true;
     }
     long long grid = std::min<long long>(a.items, (long long)sm_count() * 32);
-    if (e == cudaSuccess) kern<<<(unsigned)grid, 32, smem, stream>>>(a);
+    if (e == cudaSuccess) launch_k(kern, dim3((unsigned)grid), dim3(32), smem, stream, a);
     if (e == cudaSuccess && a.n_split > 1) {
       int rc = check_launch("attention kernel");
       if (rc) return rc;
-      attn_split_finalize_kernel<MODE><<<(unsigned)(a.items / a.n_split * 16), 64, 0, stream>>>(a, 16);
+      launch_k(attn_split_finalize_kernel<MODE>, dim3((unsigned)(a.items / a.n_split * 16)), dim3(64), 0, stream, a, 16);
     }
   } else if (n_rows <= 32) {
     constexpr int KC = 64;
@@ -1206,11 +1215,11 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
       cfg = true;
     }
     long long grid = std::min<long long>(a.items, (long long)sm_count() * 16);
-    if (e == cudaSuccess) kern<<<(unsigned)grid, 64, smem, stream>>>(a);
+    if (e == cudaSuccess) launch_k(kern, dim3((unsigned)grid), dim3(64), smem, stream, a);
     if (e == cudaSuccess && a.n_split > 1) {
       int rc = check_launch("attention kernel");
       if (rc) return rc;
-      attn_split_finalize_kernel<MODE><<<(unsigned)(a.items / a.n_split * 32), 64, 0, stream>>>(a, 32);
+      launch_k(attn_split_finalize_kernel<MODE>, dim3((unsigned)(a.items / a.n_split * 32)), dim3(64), 0, stream, a, 32);
     }
   } else {
     // tile shapes: 4 warps x 64-row chunks, or 7 warps x 112-row chunks when that wastes fewer MMA slots
@@ -1234,7 +1243,7 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
         cfg = true;
       }
       long long grid = std::min<long long>(a.items, (long long)sm_count() * 4);
-      if (e == cudaSuccess) kern<<<(unsigned)grid, NWR * 32, smem, stream>>>(a);
+      if (e == cudaSuccess) launch_k(kern, dim3((unsigned)grid), dim3(NWR * 32), smem, stream, a);
     } else if (n_str <= 32) {
       constexpr int KC = 32;
       a.row_tiles = (int)cdiv(n_rows, 64);
@@ -1247,7 +1256,7 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
         cfg = true;
       }
       long long grid = std::min<long long>(a.items, (long long)sm_count() * 8);
-      if (e == cudaSuccess) kern<<<(unsigned)grid, 128, smem, stream>>>(a);
+      if (e == cudaSuccess) launch_k(kern, dim3((unsigned)grid), dim3(128), smem, stream, a);
     } else if (wide) {
       constexpr int KC = 112;
       a.row_tiles = (int)cdiv(n_rows, 112);
@@ -1260,7 +1269,7 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
         cfg = true;
       }
       long long grid = std::min<long long>(a.items, (long long)sm_count() * 4);
-      if (e == cudaSuccess) kern<<<(unsigned)grid, 224, smem, stream>>>(a);
+      if (e == cudaSuccess) launch_k(kern, dim3((unsigned)grid), dim3(224), smem, stream, a);
     } else {
       constexpr int KC = 64;
       a.row_tiles = (int)cdiv(n_rows, 64);
@@ -1273,7 +1282,7 @@ static int launch_mode(AttnP a, cudaStream_t stream) {
         cfg = true;
       }
       long long grid = std::min<long long>(a.items, (long long)sm_count() * 8);
-      if (e == cudaSuccess) kern<<<(unsigned)grid, 128, smem, stream>>>(a);
+      if (e == cudaSuccess) launch_k(kern, dim3((unsigned)grid), dim3(128), smem, stream, a);
     }
   }
   if (e != cudaSuccess) return fail(EGV_ERR_CUDA, "attention smem attribute: %s", cudaGetErrorString(e));
@@ -1315,19 +1324,19 @@ extern "C" int egv_attention_fwd(const egv_attn_args* x, egv_stream_t stream) {
     const unsigned grid = (unsigned)(a.B * a.n_split);
     cudaStream_t s = (cudaStream_t)stream;
     switch (a.H / 4) {
-      case 1: attn_single_fwd_heads_kernel<1><<<grid, SQH_WARPS * 32, 0, s>>>(a, part); break;
-      case 2: attn_single_fwd_heads_kernel<2><<<grid, SQH_WARPS * 32, 0, s>>>(a, part); break;
-      case 3: attn_single_fwd_heads_kernel<3><<<grid, SQH_WARPS * 32, 0, s>>>(a, part); break;
-      default: attn_single_fwd_heads_kernel<4><<<grid, SQH_WARPS * 32, 0, s>>>(a, part); break;
+      case 1: launch_k(attn_single_fwd_heads_kernel<1>, dim3(grid), dim3(SQH_WARPS * 32), 0, s, a, part); break;
+      case 2: launch_k(attn_single_fwd_heads_kernel<2>, dim3(grid), dim3(SQH_WARPS * 32), 0, s, a, part); break;
+      case 3: launch_k(attn_single_fwd_heads_kernel<3>, dim3(grid), dim3(SQH_WARPS * 32), 0, s, a, part); break;
+      default: launch_k(attn_single_fwd_heads_kernel<4>, dim3(grid), dim3(SQH_WARPS * 32), 0, s, a, part); break;
     }
     int rc2 = check_launch("attn_single_fwd_heads_kernel");
     if (rc2) return rc2;
     // (merging the splits in the last CTA of each batch element instead was measured 5 us SLOWER: a serial tail)
-    attn_single_combine_kernel<<<(unsigned)(a.B * a.H), 64, 0, s>>>(a, part);
+    launch_k(attn_single_combine_kernel, dim3((unsigned)(a.B * a.H)), dim3(64), 0, s, a, part);
     return check_launch("attn_single_combine_kernel");
   }
   if (a.Lq == 1) {
-    attn_single_fwd_kernel<<<(unsigned)(a.B * a.H * a.G), SQ_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    launch_k(attn_single_fwd_kernel, dim3((unsigned)(a.B * a.H * a.G)), dim3(SQ_WARPS * 32), 0, (cudaStream_t)stream, a);
     return check_launch("attn_single_fwd_kernel");
   }
   {
@@ -1350,15 +1359,15 @@ extern "C" int egv_attention_bwd(const egv_attn_args* x, egv_stream_t stream) {
     a.n_split = single_query_splits(a);
     const unsigned grid = (unsigned)(a.B * a.n_split);
     switch (a.H / 4) {
-      case 1: attn_single_bwd_heads_kernel<1><<<grid, SQH_WARPS * 32, 0, s>>>(a, acc, counters); break;
-      case 2: attn_single_bwd_heads_kernel<2><<<grid, SQH_WARPS * 32, 0, s>>>(a, acc, counters); break;
-      case 3: attn_single_bwd_heads_kernel<3><<<grid, SQH_WARPS * 32, 0, s>>>(a, acc, counters); break;
-      default: attn_single_bwd_heads_kernel<4><<<grid, SQH_WARPS * 32, 0, s>>>(a, acc, counters); break;
+      case 1: launch_k(attn_single_bwd_heads_kernel<1>, dim3(grid), dim3(SQH_WARPS * 32), 0, s, a, acc, counters); break;
+      case 2: launch_k(attn_single_bwd_heads_kernel<2>, dim3(grid), dim3(SQH_WARPS * 32), 0, s, a, acc, counters); break;
+      case 3: launch_k(attn_single_bwd_heads_kernel<3>, dim3(grid), dim3(SQH_WARPS * 32), 0, s, a, acc, counters); break;
+      default: launch_k(attn_single_bwd_heads_kernel<4>, dim3(grid), dim3(SQH_WARPS * 32), 0, s, a, acc, counters); break;
     }
     return check_launch("attn_single_bwd_heads_kernel");
   }
   if (a.Lq == 1) {
-    attn_single_bwd_kernel<<<(unsigned)(a.B * a.H * a.G), SQ_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    launch_k(attn_single_bwd_kernel, dim3((unsigned)(a.B * a.H * a.G)), dim3(SQ_WARPS * 32), 0, (cudaStream_t)stream, a);
     return check_launch("attn_single_bwd_kernel");
   }
   {
@@ -1374,7 +1383,6 @@ extern "C" int egv_attention_cls_finalize(const float* dkv_cls, void* dk, void* 
                                           int cls_row, int B, int H, int accumulate, egv_stream_t stream) {
   if (!dkv_cls || !dk || !dv) return fail(EGV_ERR_ARG, "cls_finalize: null pointer");
   const int n = B * H * HD;
-  attn_cls_finalize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dkv_cls, (bf16*)dk, (bf16*)dv, lddkv,
-                                                                             kv_bstride, cls_row, B, H, accumulate);
+  launch_k(attn_cls_finalize_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, dkv_cls, (bf16*)dk, (bf16*)dv, lddkv, kv_bstride, cls_row, B, H, accumulate);
   return check_launch("attn_cls_finalize_kernel");
 }

@@ -4,6 +4,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#define EGV_PDL_CLASS 4
 #include "host_common.h"
 
 namespace egv {

@@ -260,6 +260,7 @@ attn_group_kernel(const __grid_constant__ GroupMaps maps, const AttnP a, const G
     tma_prefetch_desc(&maps.str[1]);
   }
   __syncthreads();
+  pdl_wait();    // programmatic dependent launch (common.cuh): shared memory zeroed, barriers up; global accesses from here
 
   const int HG = a.H * a.G;
   if (warp == GW) {
@@ -488,7 +489,7 @@ static int launch_group(const GroupMaps& maps, const AttnP& a, const GroupP& gp,
     cfg = true;
   }
   const long long grid = gp.total < sm_count() ? gp.total : sm_count();
-  kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(maps, a, gp);
+  launch_k(kern, dim3((unsigned)grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, maps, a, gp);
   int rc = check_launch("attn_group_kernel");
   return rc ? rc : 1;
 }

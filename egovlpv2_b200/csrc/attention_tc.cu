@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int HG = a.H * a.G;
+  pdl_wait();     // programmatic dependent launch (common.cuh): before any global access; dependents start when this CTA exits
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
@@ -348,7 +349,7 @@ int launch_tc_attention(int mode, const AttnP& a, cudaStream_t stream) {
     cfg = true;
   }
   const long long grid = pr.total < sm_count() ? pr.total : sm_count();
-  attn_tc_fwd_kernel<<<(unsigned)grid, THREADS, SMEM_BYTES, stream>>>(maps, a, pr);
+  launch_k(attn_tc_fwd_kernel, dim3((unsigned)grid), dim3(THREADS), SMEM_BYTES, stream, maps, a, pr);
   rc = check_launch("attn_tc_fwd_kernel");
   return rc ? rc : 1;
 }

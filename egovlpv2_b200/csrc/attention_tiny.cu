@@ -156,6 +156,7 @@ attn_tiny_kernel(const __grid_constant__ TinyMaps maps, const AttnP a, const Tin
     }
     __syncwarp();
   }
+  pdl_wait();    // programmatic dependent launch (common.cuh): global accesses from here on; dependents start at exit
 
   // contiguous range of (batch, head, group) items per warp: consecutive items share (batch, head)
   const long long nwarps = (long long)gridDim.x * WARPS;
@@ -424,7 +425,7 @@ static int launch_tiny(const TinyMaps& maps, const AttnP& a, const TinyP& tp, cu
   }
   long long grid = cdiv(tp.items, (long long)Cfg::WARPS * 4);   // >= 4 items per warp
   if (grid > sm_count()) grid = sm_count();
-  kern<<<(unsigned)grid, Cfg::WARPS * 32, Cfg::SMEM_BYTES, stream>>>(maps, a, tp);
+  launch_k(kern, dim3((unsigned)grid), dim3(Cfg::WARPS * 32), Cfg::SMEM_BYTES, stream, maps, a, tp);
   int rc = check_launch("attn_tiny_kernel");
   return rc ? rc : 1;
 }

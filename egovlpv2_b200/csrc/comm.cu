@@ -26,6 +26,7 @@ struct PeerTable {
 // The sequence number lives on the device so that a captured CUDA graph can replay the gather.
 __global__ void __launch_bounds__(256) p2p_allgather_kernel(const uint4* __restrict__ src, long long n16, long long slot_bytes,
                                                             long long half_bytes, PeerTable peers, int rank, int world) {
+  pdl_enter();
   unsigned int* my_flags = peers.flags[rank];
   const unsigned int seq = *reinterpret_cast<volatile unsigned int*>(my_flags + 31) + 1u;
   const long long parity_off = (long long)(seq & 1u) * half_bytes;   // consecutive gathers alternate slot sets
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(256) p2p_allgather_kernel(const uint4* __restr
 __global__ void __launch_bounds__(256) p2p_collect_kernel(uint4* __restrict__ out, const uint8_t* __restrict__ slots,
                                                           const unsigned int* __restrict__ flags, long long n16,
                                                           long long slot_bytes, long long half_bytes, int world) {
+  pdl_enter();
   const unsigned int seq = flags[31];
   const uint8_t* base = slots + (long long)(seq & 1u) * half_bytes;
   const long long total = n16 * world;
@@ -142,13 +144,12 @@ extern "C" int egv_p2p_allgather(const void* src, int64_t bytes, int64_t slot_by
   if (bpp < 1) bpp = 1;
   if (bpp > 8) bpp = 8;
   cudaStream_t s = (cudaStream_t)stream;
-  p2p_allgather_kernel<<<bpp * world, 256, 0, s>>>((const uint4*)src, n16, slot_bytes, half, t, rank, world);
+  launch_k(p2p_allgather_kernel, dim3(bpp * world), dim3(256), 0, s, (const uint4*)src, n16, slot_bytes, half, t, rank, world);
   int rc = check_launch("p2p_allgather_kernel");
   if (rc) return rc;
   int cb = (int)cdiv(n16 * world, 256 * 4);
   if (cb < 1) cb = 1;
   if (cb > 64) cb = 64;
-  p2p_collect_kernel<<<cb, 256, 0, s>>>((uint4*)out, (const uint8_t*)slots[rank], (const unsigned int*)flags[rank], n16,
-                                        slot_bytes, half, world);
+  launch_k(p2p_collect_kernel, dim3(cb), dim3(256), 0, s, (uint4*)out, (const uint8_t*)slots[rank], (const unsigned int*)flags[rank], n16, slot_bytes, half, world);
   return check_launch("p2p_collect_kernel");
 }

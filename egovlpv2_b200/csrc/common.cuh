@@ -26,6 +26,17 @@ EGV_DEVINL bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch (host side: egv::launch_k in host_common.h).  Every kernel is launched with the
+// programmatic stream-serialisation attribute and calls pdl_wait() before its first global memory access: the kernel may be
+// scheduled as soon as every CTA of its predecessor in the stream has exited, without waiting for the grid-completion
+// flush; pdl_wait() returns once the predecessor's memory operations are visible.  A no-op without the attribute.
+// Measured on B200 inside the captured step (tools/pdl_sweep.sh, profiles/r02_c_pdl_sweep.md): -0.6 ms of 92 ms.  An EXPLICIT
+// early trigger (griddepcontrol.launch_dependents at kernel entry, or at a persistent CTA's last tile) was 3.7-4.5 ms
+// SLOWER per step in every kernel class: successor CTAs parked on the SMs next to the running kernel cost more than the
+// launch latency they hide -- so no kernel issues it.
+EGV_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+EGV_DEVINL void pdl_enter() { pdl_wait(); }
+
 EGV_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -25,6 +25,7 @@ constexpr int SMAX = 64;
 constexpr int ATT_THREADS = 128;
 
 __global__ void rng_advance_kernel(unsigned long long* state) {
+  pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) state[0] += 0x9E3779B97F4A7C15ull;
 }
 
@@ -32,6 +33,7 @@ template <bool X_BF16>
 __global__ void dropout_add_kernel(const void* __restrict__ x_, const float* __restrict__ res, float scale,
                                    const float* __restrict__ scale_dev, float p_drop, const unsigned long long* __restrict__ seed_dev,
                                    unsigned long long site, float* __restrict__ out_f32, bf16* __restrict__ out_bf16, long long n) {
+  pdl_enter();
   const unsigned long long key = philox_key(seed_dev, site);
   const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.0f);
   const float ks = 1.0f / (1.0f - p_drop);
@@ -54,6 +56,7 @@ __global__ void dropout_add_kernel(const void* __restrict__ x_, const float* __r
 template <bool X_BF16>
 __global__ void dropout_bwd_kernel(const void* __restrict__ dy_, float p_drop, const unsigned long long* __restrict__ seed_dev,
                                    unsigned long long site, float* __restrict__ out_f32, bf16* __restrict__ out_bf16, long long n) {
+  pdl_enter();
   const unsigned long long key = philox_key(seed_dev, site);
   const float ks = 1.0f / (1.0f - p_drop);
   for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < n; i4 += (long long)gridDim.x * blockDim.x) {
@@ -86,6 +89,7 @@ struct AttP {
 // shared layout (floats): Kt [64][SMAX+1] (transposed keys), V [SMAX][64], Q / dO rows, P / dS [SMAX][SMAX+1]
 template <bool BWD>
 __global__ void __launch_bounds__(ATT_THREADS) text_attention_kernel(const AttP a) {
+  pdl_enter();
   extern __shared__ float sm[];
   const int S = a.S;
   float* Kt = sm;                          // [64][SMAX + 1]
@@ -210,7 +214,7 @@ using namespace egv;
 
 extern "C" int egv_rng_advance(uint64_t* state, egv_stream_t stream) {
   if (!state) return fail(EGV_ERR_ARG, "rng_advance: null state");
-  dr::rng_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long*)state);
+  launch_k(dr::rng_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (unsigned long long*)state);
   return check_launch("rng_advance_kernel");
 }
 
@@ -221,9 +225,9 @@ extern "C" int egv_dropout_add(const void* x, int x_is_bf16, const float* res, f
   if (p_drop < 0.f || p_drop >= 1.f) return fail(EGV_ERR_ARG, "dropout_add: probability %f", p_drop);
   const unsigned grid = (unsigned)std::min<long long>(cdiv(cdiv(n, 4), 256), 148 * 8);
   if (x_is_bf16)
-    dr::dropout_add_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, res, scale, scale_dev, p_drop, (const unsigned long long*)seed_dev, site, out_f32, (bf16*)out_bf16, n);
+    launch_k(dr::dropout_add_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, res, scale, scale_dev, p_drop, (const unsigned long long*)seed_dev, site, out_f32, (bf16*)out_bf16, n);
   else
-    dr::dropout_add_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, res, scale, scale_dev, p_drop, (const unsigned long long*)seed_dev, site, out_f32, (bf16*)out_bf16, n);
+    launch_k(dr::dropout_add_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, res, scale, scale_dev, p_drop, (const unsigned long long*)seed_dev, site, out_f32, (bf16*)out_bf16, n);
   return check_launch("dropout_add_kernel");
 }
 
@@ -232,9 +236,9 @@ extern "C" int egv_dropout_bwd(const void* dy, int dy_is_bf16, float p_drop, con
   if (!dy || !seed_dev || n <= 0 || (!out_f32 && !out_bf16)) return fail(EGV_ERR_ARG, "dropout_bwd: bad arguments");
   const unsigned grid = (unsigned)std::min<long long>(cdiv(cdiv(n, 4), 256), 148 * 8);
   if (dy_is_bf16)
-    dr::dropout_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, p_drop, (const unsigned long long*)seed_dev, site, out_f32, (bf16*)out_bf16, n);
+    launch_k(dr::dropout_bwd_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dy, p_drop, (const unsigned long long*)seed_dev, site, out_f32, (bf16*)out_bf16, n);
   else
-    dr::dropout_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, p_drop, (const unsigned long long*)seed_dev, site, out_f32, (bf16*)out_bf16, n);
+    launch_k(dr::dropout_bwd_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dy, p_drop, (const unsigned long long*)seed_dev, site, out_f32, (bf16*)out_bf16, n);
   return check_launch("dropout_bwd_kernel");
 }
 
@@ -256,8 +260,8 @@ static int text_attention(const egv_text_attn_args* t, bool bwd, cudaStream_t st
     cudaFuncSetAttribute(dr::text_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dr::ATT_SMEM);
     configured = true;
   }
-  if (bwd) dr::text_attention_kernel<true><<<(unsigned)(t->B * t->H), dr::ATT_THREADS, dr::ATT_SMEM, stream>>>(a);
-  else dr::text_attention_kernel<false><<<(unsigned)(t->B * t->H), dr::ATT_THREADS, dr::ATT_SMEM, stream>>>(a);
+  if (bwd) launch_k(dr::text_attention_kernel<true>, dim3((unsigned)(t->B * t->H)), dim3(dr::ATT_THREADS), dr::ATT_SMEM, stream, a);
+  else launch_k(dr::text_attention_kernel<false>, dim3((unsigned)(t->B * t->H)), dim3(dr::ATT_THREADS), dr::ATT_SMEM, stream, a);
   return check_launch("text_attention_kernel");
 }
 

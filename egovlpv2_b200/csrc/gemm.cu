@@ -21,6 +21,7 @@
 #include <unordered_map>
 
 #include "common.cuh"
+#define EGV_PDL_CLASS 1
 #include "host_common.h"
 
 namespace egv {
@@ -464,6 +465,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers initialised, tensor memory allocated: from here on the kernel touches global memory (programmatic dependent
+  // launch: the predecessor's results must be complete; the successor may start its own prologue)
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -669,6 +673,7 @@ struct SimtStrides {
 };
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, SimtStrides st, const GemmParams p) {
+  pdl_enter();
   __shared__ float sA[32][33];
   __shared__ float sB[32][33];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -894,24 +899,9 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   }
   const int units = sm_count() / CL;   // persistent: one CTA (or CTA pair) per SM (pair)
   const int grid = (p.total_items < units ? p.total_items : units) * CL;
-  if (CL == 1) {
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tr, p);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tr, p);
-    if (e != cudaSuccess) return fail(EGV_ERR_CUDA, "gemm cluster launch: %s", cudaGetErrorString(e));
-  }
+  cudaError_t e = CL == 1 ? launch_k(kern, dim3((unsigned)grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, tr, p)
+                          : launch_cluster_k(kern, CL, dim3((unsigned)grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, tr, p);
+  if (e != cudaSuccess) return fail(EGV_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_tc_kernel");
 }
 
@@ -1004,7 +994,7 @@ extern "C" int egv_gemm_bf16(const egv_gemm_args* a, egv_stream_t stream_) {
     sk = (int)cdiv(a->K, per);
     p.split_k = sk; p.k_blocks_per_split = per; p.k_blocks_total = 0; p.num_n_tiles = 0; p.total_items = 0;
     dim3 grid((unsigned)cdiv(a->N, 32), (unsigned)cdiv(a->M, 32), (unsigned)sk);
-    gemm_simt_kernel<<<grid, 256, 0, stream>>>((const bf16*)a->A, (const bf16*)a->B, st, p);
+    launch_k(gemm_simt_kernel, dim3(grid), dim3(256), 0, stream, (const bf16*)a->A, (const bf16*)a->B, st, p);
     return check_launch("gemm_simt_kernel");
   }
 

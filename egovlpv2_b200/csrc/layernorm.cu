@@ -3,6 +3,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#define EGV_PDL_CLASS 8
 #include "host_common.h"
 
 namespace egv {
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x,
                                                      const float* __restrict__ beta, float eps, long long rows, int C,
                                                      bf16* __restrict__ y_bf16, float* __restrict__ y_f32,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const void* __restrict__
                                                      const float* add, float* dx, int bf16_total, bf16* __restrict__ dx_bf16,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      float* __restrict__ out_colsum) {
+  pdl_enter();
   extern __shared__ __align__(16) float ln_smem[];   // [8 warps][3][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long warp0 = (long long)blockIdx.x * 8 + warp;
@@ -208,9 +211,9 @@ extern "C" int egv_layernorm_fwd(const void* x, int x_is_bf16, const float* gamm
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   if (x_is_bf16)
-    ln_fwd_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, rows, C, (bf16*)y_bf16, y_f32, mean, rstd);
+    launch_k(ln_fwd_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, gamma, beta, eps, rows, C, (bf16*)y_bf16, y_f32, mean, rstd);
   else
-    ln_fwd_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, rows, C, (bf16*)y_bf16, y_f32, mean, rstd);
+    launch_k(ln_fwd_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, gamma, beta, eps, rows, C, (bf16*)y_bf16, y_f32, mean, rstd);
   return check_launch("ln_fwd_kernel");
 }
 
@@ -234,8 +237,7 @@ extern "C" int egv_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, 
       cudaFuncSetAttribute(ln_bwd_kernel<DYB, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4);   \
       cfg = true;                                                                                                    \
     }                                                                                                                \
-    ln_bwd_kernel<DYB, XB><<<(unsigned)blocks, 256, smem, s>>>(dy, x, gamma, mean, rstd, rows, C, add, dx,           \
-                                                               bf16_total, (bf16*)dx_bf16, dgamma, dbeta, out_colsum); \
+    launch_k(ln_bwd_kernel<DYB, XB>, dim3((unsigned)blocks), dim3(256), smem, s, dy, x, gamma, mean, rstd, rows, C, add, dx, bf16_total, (bf16*)dx_bf16, dgamma, dbeta, out_colsum); \
   } while (0)
   if (dy_is_bf16 && x_is_bf16) EGV_LN_BWD(true, true);
   else if (dy_is_bf16) EGV_LN_BWD(true, false);

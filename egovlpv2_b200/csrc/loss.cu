@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256) xent_kernel(const float* __restrict__ log
                                                    const long long* __restrict__ labels, int V, int ignore_index,
                                                    float* __restrict__ loss_sum, float* __restrict__ count,
                                                    DT* __restrict__ dlogits, long long ld_d) {
+  pdl_enter();
   __shared__ float red[8];
   const long long row = blockIdx.x;
   const long long label = labels[row];
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(256) xent_kernel(const float* __restrict__ log
 
 // loss = loss_sum / max(count,1); inv_count = 1 / max(count,1)
 __global__ void xent_finalize_kernel(const float* loss_sum, const float* count, float* loss, float* inv_count) {
+  pdl_enter();
   const float c = fmaxf(count[0], 1.0f);
   if (loss) loss[0] = loss_sum[0] / c;
   if (inv_count) inv_count[0] = 1.0f / c;
@@ -78,6 +80,7 @@ __global__ void xent_finalize_kernel(const float* loss_sum, const float* count, 
 // xn = x / max(||x||, eps); inv[i] = 1 / max(||x_i||, eps)
 __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ x, int P, float eps, float* __restrict__ xn,
                                                       float* __restrict__ inv) {
+  pdl_enter();
   __shared__ float red[8];
   const long long row = blockIdx.x;
   float s = 0.f;
@@ -94,6 +97,7 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
 // out[i, j] = sum_p a[i,p] * b[j,p]; one warp per (i,j)
 __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, int Ga, int Gb,
                                                      int P, float* __restrict__ out) {
+  pdl_enter();
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (w >= Ga * Gb) return;
   const int i = w / Gb, j = w % Gb;
@@ -110,6 +114,7 @@ __global__ void __launch_bounds__(256) egonce_loss_kernel(const float* __restric
                                                           const float* __restrict__ simn, int G, float tau,
                                                           uint8_t* __restrict__ mask, float* __restrict__ loss,
                                                           float* __restrict__ dsim) {
+  pdl_enter();
   __shared__ float red[8];
   const float it = 1.0f / tau;
   for (int e = threadIdx.x; e < G * G; e += 256) {
@@ -169,6 +174,7 @@ __global__ void __launch_bounds__(256) egonce_loss_kernel(const float* __restric
 __global__ void __launch_bounds__(256) dual_loss_kernel(const float* __restrict__ sim, int G, int kind, float param,
                                                         const float* __restrict__ weight, int fix_norm,
                                                         float* __restrict__ loss, float* __restrict__ dsim) {
+  pdl_enter();
   __shared__ float red[8];
   for (int e = threadIdx.x; e < G * G; e += 256) dsim[e] = 0.f;
   __syncthreads();
@@ -227,6 +233,7 @@ __global__ void __launch_bounds__(256) egonce_grad_kernel(const float* __restric
                                                           const float* __restrict__ vn, const float* __restrict__ inv_t,
                                                           const float* __restrict__ inv_v, int G, int P, int row0,
                                                           float* __restrict__ dt, float* __restrict__ dv) {
+  pdl_enter();
   __shared__ float red[8];
   extern __shared__ float coef[];  // G coefficients
   const int r = blockIdx.x, which = blockIdx.y;
@@ -262,17 +269,15 @@ extern "C" int egv_softmax_xent(const float* logits, int64_t ld, const int64_t* 
   if (!logits || !labels || !loss_sum || !count) return fail(EGV_ERR_ARG, "softmax_xent: null pointer");
   if (rows <= 0) return EGV_OK;
   if (dlogits_is_f32)
-    xent_kernel<float><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, (const long long*)labels, V, ignore_index,
-                                                                          loss_sum, count, (float*)dlogits, ld_d);
+    launch_k(xent_kernel<float>, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream, logits, ld, (const long long*)labels, V, ignore_index, loss_sum, count, (float*)dlogits, ld_d);
   else
-    xent_kernel<bf16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, (const long long*)labels, V, ignore_index,
-                                                                         loss_sum, count, (bf16*)dlogits, ld_d);
+    launch_k(xent_kernel<bf16>, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream, logits, ld, (const long long*)labels, V, ignore_index, loss_sum, count, (bf16*)dlogits, ld_d);
   return check_launch("xent_kernel");
 }
 
 extern "C" int egv_xent_finalize(const float* loss_sum, const float* count, float* loss, float* inv_count, egv_stream_t stream) {
   if (!loss_sum || !count) return fail(EGV_ERR_ARG, "xent_finalize: null pointer");
-  xent_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(loss_sum, count, loss, inv_count);
+  launch_k(xent_finalize_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, loss_sum, count, loss, inv_count);
   return check_launch("xent_finalize_kernel");
 }
 
@@ -297,26 +302,26 @@ extern "C" int egv_egonce(const float* t, const float* v, int G, int P, const fl
   float* simn = simv + (long long)G * G;
   float* dsim = simn + (long long)G * G;
   int rc;
-  rownorm_kernel<<<G, 256, 0, s>>>(t, P, 1e-8f, tn, inv_t);
+  launch_k(rownorm_kernel, dim3(G), dim3(256), 0, s, t, P, 1e-8f, tn, inv_t);
   if ((rc = check_launch("rownorm_kernel"))) return rc;
-  rownorm_kernel<<<G, 256, 0, s>>>(v, P, 1e-8f, vn, inv_v);
+  launch_k(rownorm_kernel, dim3(G), dim3(256), 0, s, v, P, 1e-8f, vn, inv_v);
   if ((rc = check_launch("rownorm_kernel"))) return rc;
-  rownorm_kernel<<<G, 256, 0, s>>>(noun, Dn, 1e-8f, nn, nullptr);
+  launch_k(rownorm_kernel, dim3(G), dim3(256), 0, s, noun, Dn, 1e-8f, nn, nullptr);
   if ((rc = check_launch("rownorm_kernel"))) return rc;
-  rownorm_kernel<<<G, 256, 0, s>>>(verb, Dv, 1e-8f, vb, nullptr);
+  launch_k(rownorm_kernel, dim3(G), dim3(256), 0, s, verb, Dv, 1e-8f, vb, nullptr);
   if ((rc = check_launch("rownorm_kernel"))) return rc;
   const unsigned gb = (unsigned)cdiv((long long)G * G, 8);
-  rowdot_kernel<<<gb, 256, 0, s>>>(tn, vn, G, G, P, sim);
+  launch_k(rowdot_kernel, dim3(gb), dim3(256), 0, s, tn, vn, G, G, P, sim);
   if ((rc = check_launch("rowdot_kernel"))) return rc;
-  rowdot_kernel<<<gb, 256, 0, s>>>(nn, nn, G, G, Dn, simn);
+  launch_k(rowdot_kernel, dim3(gb), dim3(256), 0, s, nn, nn, G, G, Dn, simn);
   if ((rc = check_launch("rowdot_kernel"))) return rc;
-  rowdot_kernel<<<gb, 256, 0, s>>>(vb, vb, G, G, Dv, simv);
+  launch_k(rowdot_kernel, dim3(gb), dim3(256), 0, s, vb, vb, G, G, Dv, simv);
   if ((rc = check_launch("rowdot_kernel"))) return rc;
-  egonce_loss_kernel<<<1, 256, 0, s>>>(sim, simv, simn, G, temperature, mask, loss, dsim);
+  launch_k(egonce_loss_kernel, dim3(1), dim3(256), 0, s, sim, simv, simn, G, temperature, mask, loss, dsim);
   if ((rc = check_launch("egonce_loss_kernel"))) return rc;
   if (grad_rows > 0 && (dt || dv)) {
     dim3 grid((unsigned)grad_rows, 2);
-    egonce_grad_kernel<<<grid, 256, G * sizeof(float), s>>>(dsim, tn, vn, inv_t, inv_v, G, P, grad_row0, dt, dv);
+    launch_k(egonce_grad_kernel, dim3(grid), dim3(256), G * sizeof(float), s, dsim, tn, vn, inv_t, inv_v, G, P, grad_row0, dt, dv);
     if ((rc = check_launch("egonce_grad_kernel"))) return rc;
   }
   return EGV_OK;
@@ -340,17 +345,17 @@ extern "C" int egv_dual_loss(const float* t, const float* v, int G, int P, int k
   float* inv_v = inv_t + G;
   float* dsim = inv_v + G;
   int rc;
-  rownorm_kernel<<<G, 256, 0, s>>>(t, P, 1e-8f, tn, inv_t);
+  launch_k(rownorm_kernel, dim3(G), dim3(256), 0, s, t, P, 1e-8f, tn, inv_t);
   if ((rc = check_launch("rownorm_kernel"))) return rc;
-  rownorm_kernel<<<G, 256, 0, s>>>(v, P, 1e-8f, vn, inv_v);
+  launch_k(rownorm_kernel, dim3(G), dim3(256), 0, s, v, P, 1e-8f, vn, inv_v);
   if ((rc = check_launch("rownorm_kernel"))) return rc;
-  rowdot_kernel<<<(unsigned)cdiv((long long)G * G, 8), 256, 0, s>>>(tn, vn, G, G, P, sim);
+  launch_k(rowdot_kernel, dim3((unsigned)cdiv((long long)G * G, 8)), dim3(256), 0, s, tn, vn, G, G, P, sim);
   if ((rc = check_launch("rowdot_kernel"))) return rc;
-  dual_loss_kernel<<<1, 256, 0, s>>>(sim, G, kind, param, weight, fix_norm, loss, dsim);
+  launch_k(dual_loss_kernel, dim3(1), dim3(256), 0, s, sim, G, kind, param, weight, fix_norm, loss, dsim);
   if ((rc = check_launch("dual_loss_kernel"))) return rc;
   if (grad_rows > 0 && (dt || dv)) {
     dim3 grid((unsigned)grad_rows, 2);
-    egonce_grad_kernel<<<grid, 256, G * sizeof(float), s>>>(dsim, tn, vn, inv_t, inv_v, G, P, grad_row0, dt, dv);
+    launch_k(egonce_grad_kernel, dim3(grid), dim3(256), G * sizeof(float), s, dsim, tn, vn, inv_t, inv_v, G, P, grad_row0, dt, dv);
     if ((rc = check_launch("egonce_grad_kernel"))) return rc;
   }
   return EGV_OK;

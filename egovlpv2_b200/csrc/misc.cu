@@ -18,6 +18,7 @@ static inline unsigned grid_for(long long work_items, int per_block, int max_wav
 
 // ------------------------------------------------------------------------------------------- casts
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
     y[i] = __float2bfloat16(x[i]);
 }
 __global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -46,6 +48,7 @@ __global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restri
 __global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha,
                                                    const float* __restrict__ alpha_dev, float* __restrict__ y,
                                                    bf16* __restrict__ y_bf16, long long n) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const float al = alpha * (alpha_dev ? __ldg(alpha_dev) : 1.0f);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -58,6 +61,7 @@ __global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ a, 
 // y[r, c] += x[r, c] for r < rows, c < C with independent row strides (the CLS rows of a [B, N, C] tensor).
 __global__ void __launch_bounds__(256) add_rows_kernel(float* __restrict__ y, long long ldy, const float* __restrict__ x,
                                                        long long ldx, int rows, int C) {
+  pdl_enter();
   const long long n = (long long)rows * C;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -72,6 +76,7 @@ template <bool XBF>
 __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x, long long rows, int C, long long ld,
                                                      float* __restrict__ out, float scale,
                                                      const float* __restrict__ scale_dev) {
+  pdl_enter();
   __shared__ float red[8][65];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 64 + 2 * tx;
@@ -110,6 +115,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x,
 __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16* __restrict__ x, long long rows, int C, long long ld,
                                                             float* __restrict__ out, float scale,
                                                             const float* __restrict__ scale_dev) {
+  pdl_enter();
   __shared__ float red[8][256 + 8];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + 8 * tx;
@@ -161,6 +167,7 @@ template <bool DYBF>
 __global__ void __launch_bounds__(256) act_grad_kernel(const void* __restrict__ dy, const bf16* __restrict__ aux, int act,
                                                        float scale, const float* __restrict__ scale_dev,
                                                        bf16* __restrict__ out, long long n) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.0f);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -176,6 +183,7 @@ __global__ void __launch_bounds__(256) act_grad_kernel(const void* __restrict__ 
 }
 
 __global__ void zero_f32_kernel(float* p, long long n) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = 0.f;
 }
@@ -184,6 +192,7 @@ __global__ void zero_f32_kernel(float* p, long long n) {
 template <bool ABF, bool BBF>
 __global__ void __launch_bounds__(256) dot_kernel(const void* __restrict__ a, const void* __restrict__ b, long long n,
                                                   float* __restrict__ out) {
+  pdl_enter();
   __shared__ float red[8];
   const long long stride = (long long)gridDim.x * blockDim.x;
   float s = 0.f;
@@ -209,6 +218,7 @@ __global__ void __launch_bounds__(256) dot_kernel(const void* __restrict__ a, co
 // One thread moves 8 contiguous pixels (32 B read, 16 B write); threads walk the image row-major -> coalesced reads.
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ video, int BT, int Cin, int H, int W,
                                                        int p, bf16* __restrict__ out) {
+  pdl_enter();
   const int gw = W / p, gh = H / p;
   const int w8 = W >> 3;
   const long long total = (long long)BT * Cin * H * w8;
@@ -240,6 +250,7 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
 // zero-padded weight).  One thread per (patch, channel, patch row): p pixels.
 __global__ void __launch_bounds__(256) patchify_padded_kernel(const float* __restrict__ video, int BT, int Cin, int H, int W,
                                                               int p, long long ld_out, bf16* __restrict__ out) {
+  pdl_enter();
   const int gw = W / p, gh = H / p;
   const int Kc = Cin * p * p;
   const long long total = (long long)BT * gh * gw * Cin * p;
@@ -270,6 +281,7 @@ struct U8Norm {
 };
 __global__ void __launch_bounds__(256) patchify_u8_kernel(const uint8_t* __restrict__ video, int BT, int Cin, int H, int W,
                                                           int p, U8Norm nrm, bf16* __restrict__ out) {
+  pdl_enter();
   __shared__ unsigned short lut[4 * 256];
   for (int t = threadIdx.x; t < Cin * 256; t += blockDim.x) {
     const int c = t >> 8;
@@ -307,6 +319,7 @@ __global__ void __launch_bounds__(256) patchify_u8_kernel(const uint8_t* __restr
 __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
                                                               const float* __restrict__ pos, const float* __restrict__ temporal,
                                                               int B, int T, int Nf, int C, float* __restrict__ tokens) {
+  pdl_enter();
   const int c4n = C >> 2;
   const long long N = 1 + (long long)T * Nf;
   const long long total = (long long)B * N * c4n;
@@ -337,6 +350,7 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
 __global__ void __launch_bounds__(256) assemble_tokens_bwd_kernel(const float* __restrict__ d_tokens, int B, int T, int Nf,
                                                                   int C, bf16* __restrict__ d_patch, float* __restrict__ d_cls,
                                                                   float* __restrict__ d_pos, float* __restrict__ d_temporal) {
+  pdl_enter();
   const long long N = 1 + (long long)T * Nf;
   const int job = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -368,6 +382,7 @@ __global__ void __launch_bounds__(256) assemble_tokens_bwd_kernel(const float* _
 __global__ void __launch_bounds__(128) text_embed_kernel(const long long* __restrict__ ids, int B, int S, int C, int pad_id,
                                                          const float* __restrict__ word, const float* __restrict__ pos,
                                                          const float* __restrict__ type0, float* __restrict__ out) {
+  pdl_enter();
   const int tok = blockIdx.x;
   const int b = tok / S, s = tok % S;
   const long long id = ids[tok];
@@ -380,6 +395,7 @@ __global__ void __launch_bounds__(128) text_embed_kernel(const long long* __rest
 __global__ void __launch_bounds__(128) text_embed_bwd_kernel(const float* __restrict__ d_out, const long long* __restrict__ ids,
                                                              int B, int S, int C, int pad_id, float* __restrict__ d_word,
                                                              float* __restrict__ d_pos) {
+  pdl_enter();
   const int tok = blockIdx.x;
   const int b = tok / S, s = tok % S;
   const long long id = ids[tok];
@@ -400,6 +416,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                     float* __restrict__ v, bf16* __restrict__ p_bf16, long long n, float lr,
                                                     float beta1, float beta2, float eps, float wd, float bias_c1, float bias_c2,
                                                     float grad_scale, const float* __restrict__ hyper) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   if (hyper) {  // step-dependent scalars live on the device so that a captured CUDA graph stays valid across steps
     lr *= hyper[0];
@@ -459,33 +476,33 @@ extern "C" int egv_cast_f32_bf16(const float* x, void* y, int64_t n, egv_stream_
   if (n <= 0) return EGV_OK;
   if (!x || !y) return fail(EGV_ERR_ARG, "cast: null pointer");
   if ((((uintptr_t)x) & 15) || (((uintptr_t)y) & 7)) return fail(EGV_ERR_ARG, "cast: unaligned pointer");
-  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, n);
+  launch_k(cast_f32_bf16_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, (cudaStream_t)stream, x, (bf16*)y, n);
   return check_launch("cast_f32_bf16_kernel");
 }
 extern "C" int egv_cast_bf16_f32(const void* x, float* y, int64_t n, egv_stream_t stream) {
   if (n <= 0) return EGV_OK;
   if (!x || !y) return fail(EGV_ERR_ARG, "cast: null pointer");
   if ((((uintptr_t)y) & 15) || (((uintptr_t)x) & 7)) return fail(EGV_ERR_ARG, "cast: unaligned pointer");
-  cast_bf16_f32_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, y, n);
+  launch_k(cast_bf16_f32_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, y, n);
   return check_launch("cast_bf16_f32_kernel");
 }
 extern "C" int egv_axpy_f32(const float* a, const float* b, float alpha, const float* alpha_dev, float* y, void* y_bf16,
                             int64_t n, egv_stream_t stream) {
   if (n <= 0) return EGV_OK;
   if (!b || (!y && !y_bf16)) return fail(EGV_ERR_ARG, "axpy: null pointer");
-  axpy_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(a, b, alpha, alpha_dev, y, (bf16*)y_bf16, n);
+  launch_k(axpy_kernel, dim3(grid_for(n, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, a, b, alpha, alpha_dev, y, (bf16*)y_bf16, n);
   return check_launch("axpy_kernel");
 }
 extern "C" int egv_add_rows_f32(float* y, int64_t ldy, const float* x, int64_t ldx, int rows, int C, egv_stream_t stream) {
   if (rows <= 0 || C <= 0) return EGV_OK;
   if (!y || !x) return fail(EGV_ERR_ARG, "add_rows: null pointer");
-  add_rows_kernel<<<grid_for((long long)rows * C, 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, x, ldx, rows, C);
+  launch_k(add_rows_kernel, dim3(grid_for((long long)rows * C, 256)), dim3(256), 0, (cudaStream_t)stream, y, ldy, x, ldx, rows, C);
   return check_launch("add_rows_kernel");
 }
 extern "C" int egv_zero_f32(float* p, int64_t n, egv_stream_t stream) {
   if (n <= 0) return EGV_OK;
   if (!p) return fail(EGV_ERR_ARG, "zero: null pointer");
-  zero_f32_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(p, n);
+  launch_k(zero_f32_kernel, dim3(grid_for(n, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, p, n);
   return check_launch("zero_f32_kernel");
 }
 
@@ -496,9 +513,9 @@ extern "C" int egv_act_grad(const void* dy, int dy_is_bf16, const void* aux_bf16
   if (act != EGV_ACT_NONE && (act < EGV_ACT_GELU_BWD || act > EGV_ACT_TANH_BWD || !aux_bf16))
     return fail(EGV_ERR_ARG, "act_grad: act must be NONE or a *_BWD code with aux");
   if (dy_is_bf16)
-    act_grad_kernel<true><<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(dy, (const bf16*)aux_bf16, act, scale, scale_dev, (bf16*)out_bf16, n);
+    launch_k(act_grad_kernel<true>, dim3(grid_for(n, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, dy, (const bf16*)aux_bf16, act, scale, scale_dev, (bf16*)out_bf16, n);
   else
-    act_grad_kernel<false><<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(dy, (const bf16*)aux_bf16, act, scale, scale_dev, (bf16*)out_bf16, n);
+    launch_k(act_grad_kernel<false>, dim3(grid_for(n, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, dy, (const bf16*)aux_bf16, act, scale, scale_dev, (bf16*)out_bf16, n);
   return check_launch("act_grad_kernel");
 }
 
@@ -507,7 +524,7 @@ extern "C" int egv_colsum(const void* x, int x_is_bf16, int64_t rows, int C, int
   if (!x || !out || C <= 0) return fail(EGV_ERR_ARG, "colsum: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   if (!accumulate) {
-    zero_f32_kernel<<<grid_for(C, 256), 256, 0, s>>>(out, C);
+    launch_k(zero_f32_kernel, dim3(grid_for(C, 256)), dim3(256), 0, s, out, C);
     int rc = check_launch("zero_f32_kernel");
     if (rc) return rc;
   }
@@ -518,7 +535,7 @@ extern "C" int egv_colsum(const void* x, int x_is_bf16, int64_t rows, int C, int
     const long long cap8 = cdiv((long long)sm_count() * 6, gx8);
     if (gy8 > cap8) gy8 = cap8;
     dim3 grid8(gx8, (unsigned)gy8);
-    colsum_bf16x8_kernel<<<grid8, 256, 0, s>>>((const bf16*)x, rows, C, ld, out, scale, scale_dev);
+    launch_k(colsum_bf16x8_kernel, dim3(grid8), dim3(256), 0, s, (const bf16*)x, rows, C, ld, out, scale, scale_dev);
     return check_launch("colsum_bf16x8_kernel");
   }
   const unsigned gx = (unsigned)cdiv(C, 64);
@@ -527,8 +544,8 @@ extern "C" int egv_colsum(const void* x, int x_is_bf16, int64_t rows, int C, int
   if (gy > cap) gy = cap;
   if (gy < 1) gy = 1;
   dim3 grid(gx, (unsigned)gy);
-  if (x_is_bf16) colsum_kernel<true><<<grid, 256, 0, s>>>(x, rows, C, ld, out, scale, scale_dev);
-  else colsum_kernel<false><<<grid, 256, 0, s>>>(x, rows, C, ld, out, scale, scale_dev);
+  if (x_is_bf16) launch_k(colsum_kernel<true>, dim3(grid), dim3(256), 0, s, x, rows, C, ld, out, scale, scale_dev);
+  else launch_k(colsum_kernel<false>, dim3(grid), dim3(256), 0, s, x, rows, C, ld, out, scale, scale_dev);
   return check_launch("colsum_kernel");
 }
 
@@ -537,16 +554,16 @@ extern "C" int egv_dot(const void* a, int a_is_bf16, const void* b, int b_is_bf1
   if (!a || !b || !out) return fail(EGV_ERR_ARG, "dot: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   if (!accumulate) {
-    zero_f32_kernel<<<1, 32, 0, s>>>(out, 1);
+    launch_k(zero_f32_kernel, dim3(1), dim3(32), 0, s, out, 1);
     int rc = check_launch("zero_f32_kernel");
     if (rc) return rc;
   }
   if (n <= 0) return EGV_OK;
   const unsigned grid = grid_for(n, 256 * 8, 4);
-  if (a_is_bf16 && b_is_bf16) dot_kernel<true, true><<<grid, 256, 0, s>>>(a, b, n, out);
-  else if (a_is_bf16) dot_kernel<true, false><<<grid, 256, 0, s>>>(a, b, n, out);
-  else if (b_is_bf16) dot_kernel<false, true><<<grid, 256, 0, s>>>(a, b, n, out);
-  else dot_kernel<false, false><<<grid, 256, 0, s>>>(a, b, n, out);
+  if (a_is_bf16 && b_is_bf16) launch_k(dot_kernel<true, true>, dim3(grid), dim3(256), 0, s, a, b, n, out);
+  else if (a_is_bf16) launch_k(dot_kernel<true, false>, dim3(grid), dim3(256), 0, s, a, b, n, out);
+  else if (b_is_bf16) launch_k(dot_kernel<false, true>, dim3(grid), dim3(256), 0, s, a, b, n, out);
+  else launch_k(dot_kernel<false, false>, dim3(grid), dim3(256), 0, s, a, b, n, out);
   return check_launch("dot_kernel");
 }
 
@@ -555,7 +572,7 @@ extern "C" int egv_patchify(const float* video, int BT, int Cin, int H, int W, i
   if (p % 8 || H % p || W % p || W % 8) return fail(EGV_ERR_UNSUPPORTED, "patchify: patch size must be a multiple of 8 and divide H, W");
   if ((((uintptr_t)video) & 15) || (((uintptr_t)out_bf16) & 15)) return fail(EGV_ERR_ARG, "patchify: unaligned pointer");
   const long long total = (long long)BT * Cin * H * (W / 8);
-  patchify_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(video, BT, Cin, H, W, p, (bf16*)out_bf16);
+  launch_k(patchify_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, video, BT, Cin, H, W, p, (bf16*)out_bf16);
   return check_launch("patchify_kernel");
 }
 
@@ -565,7 +582,7 @@ extern "C" int egv_patchify_padded(const float* video, int BT, int Cin, int H, i
   if (p <= 0 || H % p || W % p) return fail(EGV_ERR_UNSUPPORTED, "patchify_padded: the patch size must divide H and W");
   if (ld_out < (int64_t)Cin * p * p) return fail(EGV_ERR_ARG, "patchify_padded: row stride shorter than the im2col depth");
   const long long total = (long long)BT * (H / p) * (W / p) * Cin * p;
-  patchify_padded_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(video, BT, Cin, H, W, p, ld_out, (bf16*)out_bf16);
+  launch_k(patchify_padded_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, video, BT, Cin, H, W, p, ld_out, (bf16*)out_bf16);
   return check_launch("patchify_padded_kernel");
 }
 
@@ -583,7 +600,7 @@ extern "C" int egv_patchify_u8(const uint8_t* video, int BT, int Cin, int H, int
   }
   const long long total = (long long)BT * Cin * H * (W / 8);
   if (total == 0) return EGV_OK;
-  patchify_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(video, BT, Cin, H, W, p, nrm, (bf16*)out_bf16);
+  launch_k(patchify_u8_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, video, BT, Cin, H, W, p, nrm, (bf16*)out_bf16);
   return check_launch("patchify_u8_kernel");
 }
 
@@ -592,29 +609,28 @@ extern "C" int egv_assemble_tokens(const float* patch, const float* cls, const f
   if (!patch || !cls || !pos || !temporal || !tokens) return fail(EGV_ERR_ARG, "assemble_tokens: null pointer");
   if (C % 4) return fail(EGV_ERR_UNSUPPORTED, "assemble_tokens: C must be a multiple of 4");
   const long long total = (long long)B * (1 + (long long)T * Nf) * (C / 4);
-  assemble_tokens_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(patch, cls, pos, temporal, B, T, Nf, C, tokens);
+  launch_k(assemble_tokens_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, patch, cls, pos, temporal, B, T, Nf, C, tokens);
   return check_launch("assemble_tokens_kernel");
 }
 
 extern "C" int egv_assemble_tokens_bwd(const float* d_tokens, int B, int T, int Nf, int C, void* d_patch_bf16, float* d_cls,
                                        float* d_pos, float* d_temporal, egv_stream_t stream) {
   if (!d_tokens) return fail(EGV_ERR_ARG, "assemble_tokens_bwd: null pointer");
-  assemble_tokens_bwd_kernel<<<1 + Nf, 256, 0, (cudaStream_t)stream>>>(d_tokens, B, T, Nf, C, (bf16*)d_patch_bf16, d_cls,
-                                                                          d_pos, d_temporal);
+  launch_k(assemble_tokens_bwd_kernel, dim3(1 + Nf), dim3(256), 0, (cudaStream_t)stream, d_tokens, B, T, Nf, C, (bf16*)d_patch_bf16, d_cls, d_pos, d_temporal);
   return check_launch("assemble_tokens_bwd_kernel");
 }
 
 extern "C" int egv_text_embed(const int64_t* ids, int B, int S, int C, int pad_id, const float* word, const float* pos,
                               const float* type0, float* out, egv_stream_t stream) {
   if (!ids || !word || !pos || !type0 || !out) return fail(EGV_ERR_ARG, "text_embed: null pointer");
-  text_embed_kernel<<<B * S, 128, 0, (cudaStream_t)stream>>>((const long long*)ids, B, S, C, pad_id, word, pos, type0, out);
+  launch_k(text_embed_kernel, dim3(B * S), dim3(128), 0, (cudaStream_t)stream, (const long long*)ids, B, S, C, pad_id, word, pos, type0, out);
   return check_launch("text_embed_kernel");
 }
 
 extern "C" int egv_text_embed_bwd(const float* d_out, const int64_t* ids, int B, int S, int C, int pad_id, float* d_word,
                                   float* d_pos, float* d_type0, egv_stream_t stream) {
   if (!d_out || !ids) return fail(EGV_ERR_ARG, "text_embed_bwd: null pointer");
-  text_embed_bwd_kernel<<<B * S, 128, 0, (cudaStream_t)stream>>>(d_out, (const long long*)ids, B, S, C, pad_id, d_word, d_pos);
+  launch_k(text_embed_bwd_kernel, dim3(B * S), dim3(128), 0, (cudaStream_t)stream, d_out, (const long long*)ids, B, S, C, pad_id, d_word, d_pos);
   int rc = check_launch("text_embed_bwd_kernel");
   if (rc || !d_type0) return rc;
   return egv_colsum(d_out, 0, (int64_t)B * S, C, C, d_type0, 1, 1.0f, nullptr, stream);
@@ -626,6 +642,7 @@ extern "C" int egv_text_embed_bwd(const float* d_out, const int64_t* ids, int B,
 // replay is still in flight.
 __global__ void adamw_schedule_kernel(long long* __restrict__ step, float* __restrict__ hyper, int warmup_steps, int max_steps,
                                       float beta1, float beta2) {
+  pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   long long s = step[0];   // optimiser steps completed so far
   double scale = 1.0;
@@ -648,7 +665,7 @@ __global__ void adamw_schedule_kernel(long long* __restrict__ step, float* __res
 extern "C" int egv_adamw_schedule(int64_t* step_dev, float* hyper_dev, int warmup_steps, int max_steps, float beta1, float beta2,
                                   egv_stream_t stream) {
   if (!step_dev || !hyper_dev) return fail(EGV_ERR_ARG, "adamw_schedule: null pointer");
-  adamw_schedule_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((long long*)step_dev, hyper_dev, warmup_steps, max_steps, beta1, beta2);
+  launch_k(adamw_schedule_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (long long*)step_dev, hyper_dev, warmup_steps, max_steps, beta1, beta2);
   return check_launch("adamw_schedule_kernel");
 }
 
@@ -657,7 +674,6 @@ extern "C" int egv_adamw(float* p, const float* g, float* m, float* v, void* p_b
                          const float* hyper_dev, egv_stream_t stream) {
   if (n <= 0) return EGV_OK;
   if (!p || !g || !m || !v) return fail(EGV_ERR_ARG, "adamw: null pointer");
-  adamw_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)p_bf16, n, lr, beta1, beta2, eps,
-                                                                      weight_decay, bias_c1, bias_c2, grad_scale, hyper_dev);
+  launch_k(adamw_kernel, dim3(grid_for(n / 4 + 1, 256, 8)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (bf16*)p_bf16, n, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2, grad_scale, hyper_dev);
   return check_launch("adamw_kernel");
 }

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
 row_softmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_per_batch, long long s_bstride, int n,
                    bf16* __restrict__ P, long long ld_p, long long p_bstride, float* __restrict__ lse, float p_drop,
                    const unsigned long long* __restrict__ seed_dev, unsigned long long site, float* __restrict__ rsum) {
+  pdl_enter();
   __shared__ float red[ROW_THREADS / 32];
   const long long r = blockIdx.x;
   const long long b = r / rows_per_batch, lr = r % rows_per_batch;
@@ -94,6 +95,7 @@ row_dsoftmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_p
                     const float* __restrict__ lse, const float* __restrict__ dP, long long ld_dp, long long dp_bstride,
                     bf16* __restrict__ dS, long long ld_ds, long long ds_bstride, float p_drop,
                     const unsigned long long* __restrict__ seed_dev, unsigned long long site, const float* __restrict__ row_const) {
+  pdl_enter();
   __shared__ float red[ROW_THREADS / 32];
   const long long r = blockIdx.x;
   const long long b = r / rows_per_batch, lr = r % rows_per_batch;
@@ -130,6 +132,7 @@ row_dsoftmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_p
 // bias1[b, h*S + s] = scale * sum_j k[b*S+s, h*64+j] * bq[h*64+j] + mask[b, s]      one warp per (b, s, h)
 __global__ void qbias_fwd_kernel(const bf16* __restrict__ k, long long ldk, const float* __restrict__ bq,
                                  const float* __restrict__ mask, float scale, int B, int S, int H, float* __restrict__ out) {
+  pdl_enter();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= B * S * H) return;
   const int h = gw % H, bs = gw / H;
@@ -146,6 +149,7 @@ __global__ void qbias_fwd_kernel(const bf16* __restrict__ k, long long ldk, cons
 __global__ void qbias_bwd_kernel(const bf16* __restrict__ k, long long ldk, const float* __restrict__ bq,
                                  const float* __restrict__ dbias, float scale, int B, int S, int H, float* __restrict__ dk,
                                  long long lddk, float* __restrict__ dbq) {
+  pdl_enter();
   const int h = blockIdx.x, j = threadIdx.x;
   const float q = bq[h * 64 + j];
   float acc = 0.f;
@@ -163,6 +167,7 @@ __global__ void qbias_bwd_kernel(const bf16* __restrict__ k, long long ldk, cons
 // ox[b*S+s, h*64+j] += rsum[b, h*S+s] * bv[h*64+j]   (value bias under dropout: the dropped probabilities do not sum to 1)
 __global__ void rowscale_bias_kernel(bf16* __restrict__ ox, long long ld, const float* __restrict__ rsum,
                                      const float* __restrict__ bv, int B, int S, int H) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int Cw = H * 64;
   if (i >= B * S * Cw) return;
@@ -173,6 +178,7 @@ __global__ void rowscale_bias_kernel(bf16* __restrict__ ox, long long ld, const 
 // dbv[h*64+j] += sum_{b,s} rsum[b, h*S+s] * d_ox[b*S+s, h*64+j]
 __global__ void rowscale_bias_bwd_kernel(const bf16* __restrict__ d_ox, long long ld, const float* __restrict__ rsum,
                                          float* __restrict__ dbv, int B, int S, int H) {
+  pdl_enter();
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= H * 64) return;
   const int h = col / 64;
@@ -193,8 +199,7 @@ extern "C" int egv_xattn_row_softmax(const float* scores, int64_t ld_s, int64_t 
   if (!scores || !P || rows <= 0 || n <= 0 || rows_per_batch <= 0) return fail(EGV_ERR_ARG, "row_softmax: bad arguments");
   if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD) return fail(EGV_ERR_UNSUPPORTED, "row_softmax: %d columns > %d", n, xa::ROW_THREADS * xa::MAX_PER_THREAD);
   if (p_drop < 0.f || p_drop >= 1.f) return fail(EGV_ERR_ARG, "row_softmax: dropout probability %f", p_drop);
-  xa::row_softmax_kernel<<<(unsigned)rows, xa::ROW_THREADS, 0, (cudaStream_t)stream>>>(
-      scores, ld_s, rows_per_batch, s_bstride, n, (bf16*)P, ld_p, p_bstride, lse, p_drop, (const unsigned long long*)seed_dev, site, rsum);
+  launch_k(xa::row_softmax_kernel, dim3((unsigned)rows), dim3(xa::ROW_THREADS), 0, (cudaStream_t)stream,  scores, ld_s, rows_per_batch, s_bstride, n, (bf16*)P, ld_p, p_bstride, lse, p_drop, (const unsigned long long*)seed_dev, site, rsum);
   return check_launch("row_softmax_kernel");
 }
 
@@ -204,8 +209,7 @@ extern "C" int egv_xattn_row_dsoftmax(const float* scores, int64_t ld_s, int64_t
                                       const float* row_const, egv_stream_t stream) {
   if (!scores || !lse || !dP || !dS || rows <= 0 || n <= 0 || rows_per_batch <= 0) return fail(EGV_ERR_ARG, "row_dsoftmax: bad arguments");
   if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD) return fail(EGV_ERR_UNSUPPORTED, "row_dsoftmax: %d columns > %d", n, xa::ROW_THREADS * xa::MAX_PER_THREAD);
-  xa::row_dsoftmax_kernel<<<(unsigned)rows, xa::ROW_THREADS, 0, (cudaStream_t)stream>>>(
-      scores, ld_s, rows_per_batch, s_bstride, n, lse, dP, ld_dp, dp_bstride, (bf16*)dS, ld_ds, ds_bstride, p_drop, (const unsigned long long*)seed_dev, site, row_const);
+  launch_k(xa::row_dsoftmax_kernel, dim3((unsigned)rows), dim3(xa::ROW_THREADS), 0, (cudaStream_t)stream,  scores, ld_s, rows_per_batch, s_bstride, n, lse, dP, ld_dp, dp_bstride, (bf16*)dS, ld_ds, ds_bstride, p_drop, (const unsigned long long*)seed_dev, site, row_const);
   return check_launch("row_dsoftmax_kernel");
 }
 
@@ -213,14 +217,14 @@ extern "C" int egv_xattn_qbias_fwd(const void* k, int64_t ldk, const float* bq, 
                                    int H, float* out, egv_stream_t stream) {
   if (!k || !bq || !out || B <= 0 || S <= 0 || H <= 0) return fail(EGV_ERR_ARG, "qbias_fwd: bad arguments");
   const long long warps = (long long)B * S * H;
-  xa::qbias_fwd_kernel<<<(unsigned)cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)k, ldk, bq, mask, scale, B, S, H, out);
+  launch_k(xa::qbias_fwd_kernel, dim3((unsigned)cdiv(warps, 8)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)k, ldk, bq, mask, scale, B, S, H, out);
   return check_launch("qbias_fwd_kernel");
 }
 
 extern "C" int egv_xattn_qbias_bwd(const void* k, int64_t ldk, const float* bq, const float* dbias, float scale, int B, int S,
                                    int H, float* dk, int64_t lddk, float* dbq, egv_stream_t stream) {
   if (!k || !bq || !dbias || B <= 0 || S <= 0 || H <= 0) return fail(EGV_ERR_ARG, "qbias_bwd: bad arguments");
-  xa::qbias_bwd_kernel<<<dim3((unsigned)H, (unsigned)cdiv((long long)B * S, 32)), 64, 0, (cudaStream_t)stream>>>((const bf16*)k, ldk, bq, dbias, scale, B, S, H, dk, lddk, dbq);
+  launch_k(xa::qbias_bwd_kernel, dim3(dim3((unsigned)H, (unsigned)cdiv((long long)B * S, 32))), dim3(64), 0, (cudaStream_t)stream, (const bf16*)k, ldk, bq, dbias, scale, B, S, H, dk, lddk, dbq);
   return check_launch("qbias_bwd_kernel");
 }
 
@@ -228,13 +232,13 @@ extern "C" int egv_xattn_rowscale_bias(void* ox, int64_t ld, const float* rsum, 
                                        egv_stream_t stream) {
   if (!ox || !rsum || !bv || B <= 0 || S <= 0 || H <= 0) return fail(EGV_ERR_ARG, "rowscale_bias: bad arguments");
   const long long n = (long long)B * S * H * 64;
-  xa::rowscale_bias_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((bf16*)ox, ld, rsum, bv, B, S, H);
+  launch_k(xa::rowscale_bias_kernel, dim3((unsigned)cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, (bf16*)ox, ld, rsum, bv, B, S, H);
   return check_launch("rowscale_bias_kernel");
 }
 
 extern "C" int egv_xattn_rowscale_bias_bwd(const void* d_ox, int64_t ld, const float* rsum, float* dbv, int B, int S, int H,
                                            egv_stream_t stream) {
   if (!d_ox || !rsum || !dbv || B <= 0 || S <= 0 || H <= 0) return fail(EGV_ERR_ARG, "rowscale_bias_bwd: bad arguments");
-  xa::rowscale_bias_bwd_kernel<<<(unsigned)cdiv(H * 64, 64), 64, 0, (cudaStream_t)stream>>>((const bf16*)d_ox, ld, rsum, dbv, B, S, H);
+  launch_k(xa::rowscale_bias_bwd_kernel, dim3((unsigned)cdiv(H * 64, 64)), dim3(64), 0, (cudaStream_t)stream, (const bf16*)d_ox, ld, rsum, dbv, B, S, H);
   return check_launch("rowscale_bias_bwd_kernel");
 }

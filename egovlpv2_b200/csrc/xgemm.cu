@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#define EGV_PDL_CLASS 2
 #include "host_common.h"
 
 namespace egv {
@@ -229,6 +230,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // programmatic dependent launch (common.cuh): before any global access
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -413,7 +415,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     configured = true;
   }
   const int grid = p.total_items < sm_count() ? p.total_items : sm_count();
-  kern<<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tr, p);
+  launch_k(kern, dim3(grid), dim3(THREADS), C::SMEM_BYTES, stream, ta, tb, tr, p);
   return check_launch("bgemm_kernel");
 }
 
