@@ -38,6 +38,24 @@ EGV_DEVINL float block_reduce(float v, float* red) {
 // One CTA per row r of scores [rows, ld_s] (row r = batch r / rows_per_batch, local row r % rows_per_batch; output
 // rows of batch b start at b * p_bstride elements).  P = softmax(scores) in bf16, lse = log sum exp (natural log).
 // Dropout (p_drop > 0): P_out = keep ? P / (1 - p) : 0, with `rsum` = the row sum of the dropped probabilities.
+// Column mapping: element (r, c) has the flat dropout index r * n + c and one Philox4x32 call decides four consecutive
+// indices, so a thread owns the columns of whole Philox counters (pass i, thread t: counter (r * n) / 4 + i * 256 + t) --
+// one generator call per four probabilities instead of one per probability (the first version spent its 54 us per launch
+// at cfg 3 on 9.6 M ten-round Philox calls).
+constexpr int QUADS = MAX_PER_THREAD / 4;
+
+struct RowMap {
+  long long ctr0;   // first Philox counter that overlaps the row
+  int shift;        // (r * n) % 4: column of the counter's word w is 4 * (ctr - ctr0) + w - shift
+};
+EGV_DEVINL RowMap row_map(long long r, int n) {
+  const unsigned long long first = (unsigned long long)r * (unsigned long long)n;
+  RowMap m;
+  m.ctr0 = (long long)(first >> 2);
+  m.shift = (int)(first & 3ull);
+  return m;
+}
+
 __global__ void __launch_bounds__(ROW_THREADS)
 row_softmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_per_batch, long long s_bstride, int n,
                    bf16* __restrict__ P, long long ld_p, long long p_bstride, float* __restrict__ lse, float p_drop,
@@ -48,20 +66,24 @@ row_softmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_pe
   const long long b = r / rows_per_batch, lr = r % rows_per_batch;
   const float* src = scores + b * s_bstride + lr * ld_s;
   bf16* dst = P + b * p_bstride + lr * ld_p;
+  const RowMap rm = row_map(r, n);
   float x[MAX_PER_THREAD];
   float mx = -3.0e38f;
 #pragma unroll
-  for (int i = 0; i < MAX_PER_THREAD; ++i) {
-    const int c = threadIdx.x + i * ROW_THREADS;
-    x[i] = c < n ? __ldg(src + c) : -3.0e38f;
-    mx = fmaxf(mx, x[i]);
+  for (int i = 0; i < QUADS; ++i) {
+    const int c0 = 4 * (threadIdx.x + i * ROW_THREADS) - rm.shift;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int c = c0 + w;
+      x[4 * i + w] = (c >= 0 && c < n) ? __ldg(src + c) : -3.0e38f;
+      mx = fmaxf(mx, x[4 * i + w]);
+    }
   }
   mx = block_reduce<true>(mx, red);
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < MAX_PER_THREAD; ++i) {
-    const int c = threadIdx.x + i * ROW_THREADS;
-    x[i] = c < n ? ex2((x[i] - mx) * LOG2E) : 0.f;
+    x[i] = x[i] > -1.0e38f ? ex2((x[i] - mx) * LOG2E) : 0.f;
     sum += x[i];
   }
   sum = block_reduce<false>(sum, red);
@@ -70,15 +92,27 @@ row_softmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_pe
   const unsigned long long seed = p_drop > 0.f ? philox_key(seed_dev, site) : 0ull;
   float dsum = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_PER_THREAD; ++i) {
-    const int c = threadIdx.x + i * ROW_THREADS;
-    if (c < n) {
-      float pv = x[i] * inv;
-      if (p_drop > 0.f) {
-        pv = philox_keep(seed, (unsigned long long)r * (unsigned long long)n + c, p_drop) ? pv * keep_scale : 0.f;
-        dsum += pv;
+  for (int i = 0; i < QUADS; ++i) {
+    const int q = threadIdx.x + i * ROW_THREADS;
+    const int c0 = 4 * q - rm.shift;
+    if (c0 >= n) continue;
+    uint32_t rw[4] = {0u, 0u, 0u, 0u};
+    if (p_drop > 0.f) {
+      const unsigned long long ctr = (unsigned long long)(rm.ctr0 + q);
+      const uint4 rr = philox4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+      rw[0] = rr.x; rw[1] = rr.y; rw[2] = rr.z; rw[3] = rr.w;
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int c = c0 + w;
+      if (c >= 0 && c < n) {
+        float pv = x[4 * i + w] * inv;
+        if (p_drop > 0.f) {
+          pv = philox_keep_word(rw[w], p_drop) ? pv * keep_scale : 0.f;
+          dsum += pv;
+        }
+        dst[c] = __float2bfloat16(pv);
       }
-      dst[c] = __float2bfloat16(pv);
     }
   }
   if (threadIdx.x == 0 && lse) lse[r] = mx + logf(sum);
@@ -89,7 +123,8 @@ row_softmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_pe
 }
 
 // Backward of row_softmax_kernel: dS = P * (dP~ - sum_c P dP~), where P = exp(scores - lse) is recomputed from the saved
-// scores and dP~ = dP * keep / (1 - p) undoes the dropout (the mask is regenerated from the Philox stream).
+// scores and dP~ = dP * keep / (1 - p) undoes the dropout (the mask is regenerated from the Philox stream; same column
+// mapping as the forward).
 __global__ void __launch_bounds__(ROW_THREADS)
 row_dsoftmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_per_batch, long long s_bstride, int n,
                     const float* __restrict__ lse, const float* __restrict__ dP, long long ld_dp, long long dp_bstride,
@@ -106,26 +141,42 @@ row_dsoftmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_p
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   const float rc = row_const ? row_const[r] : 0.f;   // value-bias term d_ox_h . bv_h (cancels unless dropout is on)
   const unsigned long long seed = p_drop > 0.f ? philox_key(seed_dev, site) : 0ull;
+  const RowMap rm = row_map(r, n);
   float pr[MAX_PER_THREAD], g[MAX_PER_THREAD];
   float dot = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_PER_THREAD; ++i) {
-    const int c = threadIdx.x + i * ROW_THREADS;
-    pr[i] = 0.f;
-    g[i] = 0.f;
-    if (c < n) {
-      pr[i] = ex2(fmaf(__ldg(src + c), LOG2E, -l2));
-      float gv = __ldg(dp + c) + rc;
-      if (p_drop > 0.f) gv = philox_keep(seed, (unsigned long long)r * (unsigned long long)n + c, p_drop) ? gv * keep_scale : 0.f;
-      g[i] = gv;
-      dot = fmaf(pr[i], gv, dot);
+  for (int i = 0; i < QUADS; ++i) {
+    const int q = threadIdx.x + i * ROW_THREADS;
+    const int c0 = 4 * q - rm.shift;
+    uint32_t rw[4] = {0u, 0u, 0u, 0u};
+    if (p_drop > 0.f && c0 < n) {
+      const unsigned long long ctr = (unsigned long long)(rm.ctr0 + q);
+      const uint4 rr = philox4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+      rw[0] = rr.x; rw[1] = rr.y; rw[2] = rr.z; rw[3] = rr.w;
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int c = c0 + w;
+      pr[4 * i + w] = 0.f;
+      g[4 * i + w] = 0.f;
+      if (c >= 0 && c < n) {
+        pr[4 * i + w] = ex2(fmaf(__ldg(src + c), LOG2E, -l2));
+        float gv = __ldg(dp + c) + rc;
+        if (p_drop > 0.f) gv = philox_keep_word(rw[w], p_drop) ? gv * keep_scale : 0.f;
+        g[4 * i + w] = gv;
+        dot = fmaf(pr[4 * i + w], gv, dot);
+      }
     }
   }
   dot = block_reduce<false>(dot, red);
 #pragma unroll
-  for (int i = 0; i < MAX_PER_THREAD; ++i) {
-    const int c = threadIdx.x + i * ROW_THREADS;
-    if (c < n) dst[c] = __float2bfloat16(pr[i] * (g[i] - dot));
+  for (int i = 0; i < QUADS; ++i) {
+    const int c0 = 4 * (threadIdx.x + i * ROW_THREADS) - rm.shift;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int c = c0 + w;
+      if (c >= 0 && c < n) dst[c] = __float2bfloat16(pr[4 * i + w] * (g[4 * i + w] - dot));
+    }
   }
 }
 
@@ -175,17 +226,19 @@ __global__ void rowscale_bias_kernel(bf16* __restrict__ ox, long long ld, const 
   bf16* o = ox + (long long)bs * ld + col;
   *o = __float2bfloat16(__bfloat162float(*o) + rsum[(long long)b * H * S + h * S + s] * bv[col]);
 }
-// dbv[h*64+j] += sum_{b,s} rsum[b, h*S+s] * d_ox[b*S+s, h*64+j]
+// dbv[h*64+j] += sum_{b,s} rsum[b, h*S+s] * d_ox[b*S+s, h*64+j]     grid (H*64 / 64, ceil(B*S / 16)): 16 rows per CTA + one atomic
 __global__ void rowscale_bias_bwd_kernel(const bf16* __restrict__ d_ox, long long ld, const float* __restrict__ rsum,
                                          float* __restrict__ dbv, int B, int S, int H) {
   pdl_enter();
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= H * 64) return;
   const int h = col / 64;
+  const int r0 = blockIdx.y * 16, r1 = min(r0 + 16, B * S);
   float acc = 0.f;
-  for (int bs = 0; bs < B * S; ++bs)
+#pragma unroll 4
+  for (int bs = r0; bs < r1; ++bs)
     acc = fmaf(rsum[(long long)(bs / S) * H * S + h * S + (bs % S)], __bfloat162float(d_ox[(long long)bs * ld + col]), acc);
-  dbv[col] += acc;
+  atomicAdd(dbv + col, acc);
 }
 
 }  // namespace xa
@@ -197,7 +250,7 @@ extern "C" int egv_xattn_row_softmax(const float* scores, int64_t ld_s, int64_t 
                                      int n, void* P, int64_t ld_p, int64_t p_bstride, float* lse, float p_drop,
                                      const uint64_t* seed_dev, uint64_t site, float* rsum, egv_stream_t stream) {
   if (!scores || !P || rows <= 0 || n <= 0 || rows_per_batch <= 0) return fail(EGV_ERR_ARG, "row_softmax: bad arguments");
-  if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD) return fail(EGV_ERR_UNSUPPORTED, "row_softmax: %d columns > %d", n, xa::ROW_THREADS * xa::MAX_PER_THREAD);
+  if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD - 3) return fail(EGV_ERR_UNSUPPORTED, "row_softmax: %d columns > %d", n, xa::ROW_THREADS * xa::MAX_PER_THREAD - 3);
   if (p_drop < 0.f || p_drop >= 1.f) return fail(EGV_ERR_ARG, "row_softmax: dropout probability %f", p_drop);
   launch_k(xa::row_softmax_kernel, dim3((unsigned)rows), dim3(xa::ROW_THREADS), 0, (cudaStream_t)stream,  scores, ld_s, rows_per_batch, s_bstride, n, (bf16*)P, ld_p, p_bstride, lse, p_drop, (const unsigned long long*)seed_dev, site, rsum);
   return check_launch("row_softmax_kernel");
@@ -208,7 +261,7 @@ extern "C" int egv_xattn_row_dsoftmax(const float* scores, int64_t ld_s, int64_t
                                       int64_t ld_ds, int64_t ds_bstride, float p_drop, const uint64_t* seed_dev, uint64_t site,
                                       const float* row_const, egv_stream_t stream) {
   if (!scores || !lse || !dP || !dS || rows <= 0 || n <= 0 || rows_per_batch <= 0) return fail(EGV_ERR_ARG, "row_dsoftmax: bad arguments");
-  if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD) return fail(EGV_ERR_UNSUPPORTED, "row_dsoftmax: %d columns > %d", n, xa::ROW_THREADS * xa::MAX_PER_THREAD);
+  if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD - 3) return fail(EGV_ERR_UNSUPPORTED, "row_dsoftmax: %d columns > %d", n, xa::ROW_THREADS * xa::MAX_PER_THREAD - 3);
   launch_k(xa::row_dsoftmax_kernel, dim3((unsigned)rows), dim3(xa::ROW_THREADS), 0, (cudaStream_t)stream,  scores, ld_s, rows_per_batch, s_bstride, n, lse, dP, ld_dp, dp_bstride, (bf16*)dS, ld_ds, ds_bstride, p_drop, (const unsigned long long*)seed_dev, site, row_const);
   return check_launch("row_dsoftmax_kernel");
 }
@@ -239,6 +292,6 @@ extern "C" int egv_xattn_rowscale_bias(void* ox, int64_t ld, const float* rsum, 
 extern "C" int egv_xattn_rowscale_bias_bwd(const void* d_ox, int64_t ld, const float* rsum, float* dbv, int B, int S, int H,
                                            egv_stream_t stream) {
   if (!d_ox || !rsum || !dbv || B <= 0 || S <= 0 || H <= 0) return fail(EGV_ERR_ARG, "rowscale_bias_bwd: bad arguments");
-  launch_k(xa::rowscale_bias_bwd_kernel, dim3((unsigned)cdiv(H * 64, 64)), dim3(64), 0, (cudaStream_t)stream, (const bf16*)d_ox, ld, rsum, dbv, B, S, H);
+  launch_k(xa::rowscale_bias_bwd_kernel, dim3((unsigned)cdiv(H * 64, 64), (unsigned)cdiv(B * S, 16)), dim3(64), 0, (cudaStream_t)stream, (const bf16*)d_ox, ld, rsum, dbv, B, S, H);
   return check_launch("rowscale_bias_bwd_kernel");
 }
