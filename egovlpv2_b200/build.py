@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libegovlp_b200.so")
-SOURCES = ["misc.cu", "gemm.cu", "xgemm.cu", "xattn.cu", "dropout.cu", "attention.cu", "attention_group.cu", "attention_tc.cu", "attention_tiny.cu", "layernorm.cu", "loss.cu", "comm.cu"]
+SOURCES = ["misc.cu", "gemm.cu", "xgemm.cu", "xattn.cu", "dropout.cu", "attention.cu", "attention_group.cu", "attention_tc.cu", "attention_tc_bwd.cu", "attention_tiny.cu", "layernorm.cu", "loss.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]

@@ -1374,6 +1374,10 @@ extern "C" int egv_attention_bwd(const egv_attn_args* x, egv_stream_t stream) {
     const int r = launch_tiny_attention(1, a, (cudaStream_t)stream);   // fused single-launch backward for tiny groups
     if (r != 0) return r < 0 ? r : EGV_OK;
   }
+  {
+    const int r = launch_tc_attention_bwd(a, (cudaStream_t)stream);    // space attention: one tcgen05 launch
+    if (r != 0) return r < 0 ? r : EGV_OK;
+  }
   rc = launch_mode<MODE_DQ>(a, (cudaStream_t)stream);   // also produces delta
   if (rc) return rc;
   return launch_mode<MODE_DKV>(a, (cudaStream_t)stream);

@@ -90,6 +90,9 @@ int launch_group_attention(int mode, const AttnP& a, cudaStream_t stream);
 // first, the mma.sync kernels of attention_group.cu remain the fallback for shapes it does not cover.
 int launch_tc_attention(int mode, const AttnP& a, cudaStream_t stream);
 void set_tc_attention_mode(int mode);
+// attention_tc_bwd.cu: the whole backward (dQ, dK, dV) of the same problems in one tcgen05 launch; the caller zeroes
+// dkv_cls (the shared CLS key's fp32 accumulators) and finalises it as for the mma.sync kernels.
+int launch_tc_attention_bwd(const AttnP& a, cudaStream_t stream);
 
 // gemm.cu: cached bf16 2-D tensor map (`inner` contiguous elements, `outer` rows `ld` elements apart, 128B swizzle)
 int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,

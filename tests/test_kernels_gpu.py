@@ -333,7 +333,9 @@ def _attn_case(name, B=2, H=2):
                                 k_gstride=Nf2, k_istride=1, has_cls_key=True, cls_row=0, scale=sc), False
     if name.startswith("grp"):   # group-resident kernels (attention_group.cu): contiguous groups of 64..224 rows
         Lq, Lk, cls, G = {"grp_nocls": (100, 150, False, 3), "grp112": (112, 112, True, 2), "grp64": (64, 70, True, 3),
-                          "grp224": (224, 207, True, 2), "grp_q196_k40": (196, 40, False, 2)}[name]
+                          "grp224": (224, 207, True, 2), "grp_q196_k40": (196, 40, False, 2),
+                          # edges of the tcgen05 backward (attention_tc_bwd.cu): full tiles / a 2-row second query tile
+                          "grp_tc256": (256, 255, True, 2), "grp_tc130": (130, 140, True, 2)}[name]
         nq, nk = 1 + G * Lq, 1 + G * Lk
         return nq, nk, L.AttnSpec(H=H, G=G, Lq=Lq, Lk=Lk, q_row0=1, q_gstride=Lq, q_istride=1, k_row0=1, k_gstride=Lk,
                                   k_istride=1, has_cls_key=cls, cls_row=0, scale=sc), False
@@ -352,7 +354,7 @@ def _attn_case(name, B=2, H=2):
 
 
 @pytest.mark.parametrize("name", ["time", "space", "cls", "cls_h12", "i2t", "t2i", "text", "space196", "time16", "grp_nocls",
-                                  "grp112", "grp64", "grp224", "grp_q196_k40", "tiny12_nocls", "tiny8_cls", "tiny16_g8", "tiny_time16", "t2i_long", "t2i_11", "i2t_long"])
+                                  "grp112", "grp64", "grp224", "grp_q196_k40", "grp_tc256", "grp_tc130", "tiny12_nocls", "tiny8_cls", "tiny16_g8", "tiny_time16", "t2i_long", "t2i_11", "i2t_long"])
 def test_attention_fwd_bwd(K, R, name):
     B, H = (3, 3) if name == "time16" else ((3, 12) if name == "cls_h12" else (2, 2))
     if name.startswith("tiny"):
