@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: bare UTCHMMA instead of a convergence loop per MMA
       const uint32_t idesc_s = umma_idesc_bf16(128, pr.npad, 0, 0);
       const uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);
       const int ksteps = pr.npad / 16;

@@ -471,7 +471,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = first_item; w < p.total_items; w += item_stride) {
@@ -532,7 +532,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {   // pair: the leader issues for both CTAs
+    // elect.sync, not `lane == 0`: ptxas then knows one thread runs the region and emits bare UTCHMMA / UTCBAR instead of
+    // an ELECT / PLOP3 / BRA.U.ANY convergence loop around each of them (see attention_tc_bwd.cu)
+    if (cta_rank == 0 && elect_one()) {   // pair: the leader issues for both CTAs
       constexpr uint32_t idesc = umma_idesc_bf16(BM * CL, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // encoded (>>4) start-address advance per UMMA_K step
       constexpr uint32_t a_adv = A_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;

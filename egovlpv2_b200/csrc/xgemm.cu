@@ -234,7 +234,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
@@ -276,7 +276,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       constexpr uint32_t a_adv = A_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
       constexpr uint32_t b_adv = B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
