@@ -97,6 +97,13 @@ EGV_DEVINL bool mbar_test(uint64_t* bar, uint32_t parity) {
 
 // global load that the compiler may not sink below later code (the lse values are fetched a phase ahead of their use; an
 // invariant __ldg load gets moved down to its first use)
+// 32-byte global store (STG.256): the accumulator drains write one key / query row per lane, i.e. every store instruction
+// costs 32 memory transactions whatever its width -- half as many instructions as with 16-byte stores
+EGV_DEVINL void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 EGV_DEVINL float ldg_now_f32(const float* p) {
   float v;
   asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
@@ -408,14 +415,17 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
 
     // dK_j / dV_j: 128 key rows x 64 columns each; this warp: its 32 rows x 32 columns of dK (cq 0, 1) or dV (cq 2, 3)
+    bool trd = false;
     auto drain_dkv = [&](int j, int b, int h, long long k_first) {
       mbar_wait_sleep(dkv_full, (uint32_t)j, 32);
+      ATB_TR(trd, 56 + j);
       tc_fence_after();
       uint32_t acc[2][16];
       const uint32_t col = (cq < 2 ? COL_DK : COL_DV) + (uint32_t)((cq & 1) * 32);
       tmem_ld_32x16(lane_addr + col, acc[0]);
       tmem_ld_32x16(lane_addr + col + 16u, acc[1]);
       tmem_ld_wait();
+      ATB_TR(trd, 58 + j);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dkv_free);
@@ -431,15 +441,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
       } else if (row < nkeys) {
         bf16* dst = (cq < 2 ? a.dk : a.dv) + (k_first + 128 * j + row) * a.lddkv + h * HD + (cq & 1) * 32;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh)
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t pk[8];
 #pragma unroll
-          for (int c8 = 0; c8 < 2; ++c8) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              pk[e] = pack_bf16(__uint_as_float(acc[hh][c8 * 8 + 2 * e]) * mul, __uint_as_float(acc[hh][c8 * 8 + 2 * e + 1]) * mul);
-            *reinterpret_cast<uint4*>(dst + 16 * hh + 8 * c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
+          for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(__uint_as_float(acc[hh][2 * e]) * mul, __uint_as_float(acc[hh][2 * e + 1]) * mul);
+          stg256(dst + 16 * hh, pk);
+        }
       }
     };
     // dQ_w: 128 query rows x 64 columns; this warp: its 32 rows x 16 columns
@@ -455,14 +462,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
       const int rows_tile = w == 0 ? 128 : pr.rows1;
       if (row < rows_tile) {
         bf16* dst = a.dq + (q_first + 128 * w + row) * a.lddq + h * HD + cq * 16;
+        uint32_t pk[8];
 #pragma unroll
-        for (int c8 = 0; c8 < 2; ++c8) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            pk[e] = pack_bf16(__uint_as_float(acc[c8 * 8 + 2 * e]) * a.scale, __uint_as_float(acc[c8 * 8 + 2 * e + 1]) * a.scale);
-          *reinterpret_cast<uint4*>(dst + 8 * c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
+        for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(__uint_as_float(acc[2 * e]) * a.scale, __uint_as_float(acc[2 * e + 1]) * a.scale);
+        stg256(dst, pk);
       }
     };
 
@@ -476,6 +479,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
     bool pending = false;
     for (long long p = blockIdx.x; p < pr.total; p += gridDim.x, ph ^= 1, ++it) {
       const bool tr = it == 2 && threadIdx.x == 128;
+      trd = tr;
       ATB_TR(tr, 40);
       const int h = (int)(p % a.H), g = (int)((p / a.H) % a.G), b = (int)(p / HG);
       const long long q_first = (long long)b * a.q_bstride + a.q_row0 + (long long)g * a.q_gstride;
@@ -600,7 +604,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
         // ---- deferred drains (see above)
         if (t == 0 && pending) {
           drain_dkv(1, pb, phd, pk_first);
+          ATB_TR(tr, 60);
           drain_dq(1, ph ^ 1, phd, pq_first);
+          ATB_TR(tr, 61);
         }
         if (t == 2) {
           drain_dkv(0, b, h, k_first);
@@ -641,7 +647,8 @@ int launch_tc_attention_bwd(const AttnP& a, cudaStream_t stream) {
   if (a.key_bias || a.q_istride != 1 || a.k_istride != 1 || !a.has_cls || a.dkv_accumulate || !a.dkv_cls) return 0;
   const int lk = a.LkT - 1;
   if (a.Lq <= 128 || a.Lq > 224 || lk <= 128 || a.LkT > 256) return 0;   // (the O staging buffer holds 128 + 96 rows)
-  if ((a.ldq % 8) || (a.ldkv % 8) || (a.ldo % 8) || (a.lddq % 8) || (a.lddkv % 8)) return 0;
+  if ((a.ldq % 8) || (a.ldkv % 8) || (a.ldo % 8) || (a.lddq % 16) || (a.lddkv % 16)) return 0;
+  if (((uintptr_t)a.dq | (uintptr_t)a.dk | (uintptr_t)a.dv) & 31) return 0;   // 32-byte row stores
   Prm pr;
   pr.rows1 = a.Lq - 128;
   pr.keys1 = lk - 128;
@@ -712,6 +719,8 @@ int launch_tc_attention_bwd(const AttnP& a, cudaStream_t stream) {
     names[33] = "dkv_full(0)"; names[35] = "dkv_full(1)"; names[38] = "dq_full(0)"; names[39] = "dq_full(1)";
     names[48] = "producer: K0 V0 issue"; names[49] = "producer: Q0 dO0 issue"; names[50] = "producer: Q1 dO1 issue";
     names[51] = "producer: K1 V1 issue"; names[52] = "producer: CLS rows copied"; names[53] = "producer: O issue";
+    names[56] = "drain dkv(0): full"; names[57] = "drain dkv(1 prev): full"; names[58] = "drain dkv(0): tmem read"; names[59] = "drain dkv(1 prev): tmem read";
+    names[60] = "drain dkv(1 prev) done"; names[61] = "drain dq(1 prev) done";
     names[40] = "problem start"; names[41] = "sync 1"; names[43] = "dO landed"; names[44] = "stats written"; names[42] = "sync 2";
     fprintf(stderr, "attn_tc_bwd trace (SM clocks since the problem's start):\n");
     for (int pass = 0; pass < 1; ++pass) {
