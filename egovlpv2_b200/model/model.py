@@ -410,7 +410,12 @@ class FrozenInTime(nn.Module):
         bsz, dev = video.shape[0], video.device
         world = getattr(args, 'world_size', 1) if (dist.is_available() and dist.is_initialized()) else 1
         if world > 1:
-            all_video, all_ids, all_am = allgather(video, n_gpu, args), allgather(ids, n_gpu, args), allgather(am, n_gpu, args)
+            # The reference gathers the raw fp32 clips of every rank (model.py:430) to use at most B/2 of them.  The patch
+            # embedding rounds every pixel to bf16 before its GEMM (egv_patchify), and bf16 -> fp32 -> bf16 is the
+            # identity, so gathering the clips in bf16 gives bit-identical ITM inputs at half the bytes (uint8 frames
+            # travel as they are).
+            vg = video.to(torch.bfloat16) if video.dtype == torch.float32 else video
+            all_video, all_ids, all_am = allgather(vg, n_gpu, args), allgather(ids, n_gpu, args), allgather(am, n_gpu, args)
         else:
             all_video, all_ids, all_am = video, ids, am
         rows = slice(bsz * rank, bsz * (rank + 1))
@@ -433,7 +438,10 @@ class FrozenInTime(nn.Module):
         is_neg = labels == 0
         vid_idx = torch.where(is_neg & swap_video, neg_v, own)
         txt_idx = torch.where(is_neg & ~swap_video, neg_t, own)
-        data_itm = {'video': all_video.index_select(0, vid_idx),
+        vid_sel = all_video.index_select(0, vid_idx)
+        if vid_sel.dtype != video.dtype:
+            vid_sel = vid_sel.to(video.dtype)
+        data_itm = {'video': vid_sel,
                     'text': {'input_ids': all_ids.index_select(0, txt_idx), 'attention_mask': all_am.index_select(0, txt_idx)}}
         return data_itm, labels
 
