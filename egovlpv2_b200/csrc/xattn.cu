@@ -180,6 +180,102 @@ row_dsoftmax_kernel(const float* __restrict__ scores, long long ld_s, int rows_p
   }
 }
 
+// Rows longer than the 4093 columns the register-resident kernels hold (TimeSformer-L/14 at 32 frames: 18 433 video tokens
+// per clip): the same arithmetic and the same Philox column mapping, streaming the row from global memory (it stays in L2)
+// in three passes (max, sum, write) / two passes (dot, write).
+__global__ void __launch_bounds__(ROW_THREADS)
+row_softmax_long_kernel(const float* __restrict__ scores, long long ld_s, int rows_per_batch, long long s_bstride, int n,
+                        bf16* __restrict__ P, long long ld_p, long long p_bstride, float* __restrict__ lse, float p_drop,
+                        const unsigned long long* __restrict__ seed_dev, unsigned long long site, float* __restrict__ rsum) {
+  pdl_enter();
+  __shared__ float red[ROW_THREADS / 32];
+  const long long r = blockIdx.x;
+  const long long b = r / rows_per_batch, lr = r % rows_per_batch;
+  const float* src = scores + b * s_bstride + lr * ld_s;
+  bf16* dst = P + b * p_bstride + lr * ld_p;
+  const RowMap rm = row_map(r, n);
+  float mx = -3.0e38f;
+  for (int c = threadIdx.x; c < n; c += ROW_THREADS) mx = fmaxf(mx, __ldg(src + c));
+  mx = block_reduce<true>(mx, red);
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < n; c += ROW_THREADS) sum += ex2((__ldg(src + c) - mx) * LOG2E);
+  sum = block_reduce<false>(sum, red);
+  const float inv = 1.0f / sum;
+  const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const unsigned long long seed = p_drop > 0.f ? philox_key(seed_dev, site) : 0ull;
+  float dsum = 0.f;
+  for (int q = threadIdx.x; 4 * q - rm.shift < n; q += ROW_THREADS) {
+    const int c0 = 4 * q - rm.shift;
+    uint32_t rw[4] = {0u, 0u, 0u, 0u};
+    if (p_drop > 0.f) {
+      const unsigned long long ctr = (unsigned long long)(rm.ctr0 + q);
+      const uint4 rr = philox4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+      rw[0] = rr.x; rw[1] = rr.y; rw[2] = rr.z; rw[3] = rr.w;
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int c = c0 + w;
+      if (c >= 0 && c < n) {
+        float pv = ex2((__ldg(src + c) - mx) * LOG2E) * inv;
+        if (p_drop > 0.f) {
+          pv = philox_keep_word(rw[w], p_drop) ? pv * keep_scale : 0.f;
+          dsum += pv;
+        }
+        dst[c] = __float2bfloat16(pv);
+      }
+    }
+  }
+  if (threadIdx.x == 0 && lse) lse[r] = mx + logf(sum);
+  if (rsum) {
+    dsum = block_reduce<false>(dsum, red);
+    if (threadIdx.x == 0) rsum[r] = p_drop > 0.f ? dsum : 1.0f;
+  }
+}
+
+__global__ void __launch_bounds__(ROW_THREADS)
+row_dsoftmax_long_kernel(const float* __restrict__ scores, long long ld_s, int rows_per_batch, long long s_bstride, int n,
+                         const float* __restrict__ lse, const float* __restrict__ dP, long long ld_dp, long long dp_bstride,
+                         bf16* __restrict__ dS, long long ld_ds, long long ds_bstride, float p_drop,
+                         const unsigned long long* __restrict__ seed_dev, unsigned long long site,
+                         const float* __restrict__ row_const) {
+  pdl_enter();
+  __shared__ float red[ROW_THREADS / 32];
+  const long long r = blockIdx.x;
+  const long long b = r / rows_per_batch, lr = r % rows_per_batch;
+  const float* src = scores + b * s_bstride + lr * ld_s;
+  const float* dp = dP + b * dp_bstride + lr * ld_dp;
+  bf16* dst = dS + b * ds_bstride + lr * ld_ds;
+  const float l2 = lse[r] * LOG2E;
+  const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const float rc = row_const ? row_const[r] : 0.f;
+  const unsigned long long seed = p_drop > 0.f ? philox_key(seed_dev, site) : 0ull;
+  const RowMap rm = row_map(r, n);
+  float dot = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) dot = block_reduce<false>(dot, red);
+    for (int q = threadIdx.x; 4 * q - rm.shift < n; q += ROW_THREADS) {
+      const int c0 = 4 * q - rm.shift;
+      uint32_t rw[4] = {0u, 0u, 0u, 0u};
+      if (p_drop > 0.f) {
+        const unsigned long long ctr = (unsigned long long)(rm.ctr0 + q);
+        const uint4 rr = philox4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+        rw[0] = rr.x; rw[1] = rr.y; rw[2] = rr.z; rw[3] = rr.w;
+      }
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int c = c0 + w;
+        if (c >= 0 && c < n) {
+          const float pr = ex2(fmaf(__ldg(src + c), LOG2E, -l2));
+          float gv = __ldg(dp + c) + rc;
+          if (p_drop > 0.f) gv = philox_keep_word(rw[w], p_drop) ? gv * keep_scale : 0.f;
+          if (pass == 0) dot = fmaf(pr, gv, dot);
+          else dst[c] = __float2bfloat16(pr * (gv - dot));
+        }
+      }
+    }
+  }
+}
+
 // bias1[b, h*S + s] = scale * sum_j k[b*S+s, h*64+j] * bq[h*64+j] + mask[b, s]      one warp per (b, s, h)
 __global__ void qbias_fwd_kernel(const bf16* __restrict__ k, long long ldk, const float* __restrict__ bq,
                                  const float* __restrict__ mask, float scale, int B, int S, int H, float* __restrict__ out) {
@@ -250,8 +346,11 @@ extern "C" int egv_xattn_row_softmax(const float* scores, int64_t ld_s, int64_t 
                                      int n, void* P, int64_t ld_p, int64_t p_bstride, float* lse, float p_drop,
                                      const uint64_t* seed_dev, uint64_t site, float* rsum, egv_stream_t stream) {
   if (!scores || !P || rows <= 0 || n <= 0 || rows_per_batch <= 0) return fail(EGV_ERR_ARG, "row_softmax: bad arguments");
-  if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD - 3) return fail(EGV_ERR_UNSUPPORTED, "row_softmax: %d columns > %d", n, xa::ROW_THREADS * xa::MAX_PER_THREAD - 3);
   if (p_drop < 0.f || p_drop >= 1.f) return fail(EGV_ERR_ARG, "row_softmax: dropout probability %f", p_drop);
+  if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD - 3) {   // long rows: streaming variant
+    launch_k(xa::row_softmax_long_kernel, dim3((unsigned)rows), dim3(xa::ROW_THREADS), 0, (cudaStream_t)stream, scores, ld_s, rows_per_batch, s_bstride, n, (bf16*)P, ld_p, p_bstride, lse, p_drop, (const unsigned long long*)seed_dev, site, rsum);
+    return check_launch("row_softmax_long_kernel");
+  }
   launch_k(xa::row_softmax_kernel, dim3((unsigned)rows), dim3(xa::ROW_THREADS), 0, (cudaStream_t)stream,  scores, ld_s, rows_per_batch, s_bstride, n, (bf16*)P, ld_p, p_bstride, lse, p_drop, (const unsigned long long*)seed_dev, site, rsum);
   return check_launch("row_softmax_kernel");
 }
@@ -261,7 +360,10 @@ extern "C" int egv_xattn_row_dsoftmax(const float* scores, int64_t ld_s, int64_t
                                       int64_t ld_ds, int64_t ds_bstride, float p_drop, const uint64_t* seed_dev, uint64_t site,
                                       const float* row_const, egv_stream_t stream) {
   if (!scores || !lse || !dP || !dS || rows <= 0 || n <= 0 || rows_per_batch <= 0) return fail(EGV_ERR_ARG, "row_dsoftmax: bad arguments");
-  if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD - 3) return fail(EGV_ERR_UNSUPPORTED, "row_dsoftmax: %d columns > %d", n, xa::ROW_THREADS * xa::MAX_PER_THREAD - 3);
+  if (n > xa::ROW_THREADS * xa::MAX_PER_THREAD - 3) {   // long rows: streaming variant
+    launch_k(xa::row_dsoftmax_long_kernel, dim3((unsigned)rows), dim3(xa::ROW_THREADS), 0, (cudaStream_t)stream, scores, ld_s, rows_per_batch, s_bstride, n, lse, dP, ld_dp, dp_bstride, (bf16*)dS, ld_ds, ds_bstride, p_drop, (const unsigned long long*)seed_dev, site, row_const);
+    return check_launch("row_dsoftmax_long_kernel");
+  }
   launch_k(xa::row_dsoftmax_kernel, dim3((unsigned)rows), dim3(xa::ROW_THREADS), 0, (cudaStream_t)stream,  scores, ld_s, rows_per_batch, s_bstride, n, lse, dP, ld_dp, dp_bstride, (bf16*)dS, ld_ds, ds_bstride, p_drop, (const unsigned long long*)seed_dev, site, row_const);
   return check_launch("row_dsoftmax_kernel");
 }

@@ -37,7 +37,7 @@ _REASSOC = None
 def reassoc_enabled():
     """The re-associated cross-attention (xattn_reassoc.py) is the default; EGV_XATTN_REASSOC=0 selects the round-1
     formulation (separate query / key / value projections + the strided attention kernels), kept for shapes the
-    re-associated kernels do not cover (text length != 32, more than 4096 video tokens per clip)."""
+    re-associated kernels do not cover (video->text: text length != 32; text->video: text length > 128)."""
     global _REASSOC
     if _REASSOC is None:
         import os
@@ -636,7 +636,7 @@ def text_layer_fwd(K, h, key_bias, p, w, H, video=None, eps=1e-5, save=True, dro
                               site=0 if drop is None else site(DROP_CROSS_PROBS))
         elif drop is not None:
             raise NotImplementedError("train-mode dropout of the text->video cross-attention needs the re-associated path "
-                                      "(text length <= 128, <= 4096 video tokens per clip)")
+                                      "(text length <= 128, <= 65536 video tokens per clip)")
         else:
             s.kv = _e(h, (Bv * N, 2 * C), BF16)
             K.gemm(GEMM_NT, s.x_bf, w["cross.kv"], bias=p["cross.kv.bias"], out_bf16=s.kv)

@@ -44,7 +44,7 @@ def i2t_supported(S, C, H):
 
 
 def t2i_supported(S, N, C, H):
-    return C == H * HD and N <= 4093 and S <= 128
+    return C == H * HD and N <= 65536 and S <= 128     # rows of more than 4093 video tokens take the streaming row kernels
 
 
 # ----------------------------------------------------------------------------------------------------------------------
