@@ -32,9 +32,17 @@ METRIC = "pretrain_clips_per_sec"
 UNIT = "clips/s"
 
 
+# model / input dimensions per BASELINE.json config; cfg3 is the headline workload (the default), cfg5 the stress case
+CONFIGS = {
+    "cfg3": dict(name="TimeSformer-B/16 + RoBERTa-base", img=224, patch=16, C=768, heads=12, depth=12, n_fuse=6),
+    "cfg5": dict(name="TimeSformer-L/14 + RoBERTa-large", img=336, patch=14, C=1024, heads=16, depth=24, n_fuse=6),
+}
+
+
 def workload_name(a):
-    return ("TimeSformer-B/16 + RoBERTa-base, %d frames 224^2, seq=%d, per-GPU batch %d, fusion ON (top-6), "
-            "EgoNCE+MLM+ITM, fwd+bwd+AdamW" % (a.frames, a.seq, a.batch))
+    m = CONFIGS[a.config]
+    return ("%s, %d frames %d^2, seq=%d, per-GPU batch %d, fusion ON (top-6), EgoNCE+MLM+ITM, fwd+bwd+AdamW"
+            % (m["name"], a.frames, m["img"], a.seq, a.batch))
 
 
 def peaks():
@@ -161,12 +169,13 @@ def run_ours(a, rank, world, local_rank):
     torch.cuda.set_device(dev)
     K = L.kernels()   # raises if the CUDA library is missing: there is no fallback
     torch.manual_seed(0)
-    model = build_model(T=a.frames)
+    m = CONFIGS[a.config]
+    model = build_model(T=a.frames, img=m["img"], C=m["C"], heads=m["heads"], depth=m["depth"], n_fuse=m["n_fuse"], patch=m["patch"])
     randomize_gates(model)
     model.train()     # the reference's step runs in train mode: text-tower dropout (p = 0.1) is part of the timed work
     use_graph = not a.no_graph
     step = PretrainStep(model, dev, max_steps=10000, warmup_steps=100, gather=a.gather)
-    host = synthetic_batch(a.batch, a.frames, 224, a.seq, seed=1234 + rank, pin=True)
+    host = synthetic_batch(a.batch, a.frames, m["img"], a.seq, seed=1234 + rank, pin=True)
     if a.input_dtype == "u8":
         # decoder-format frames: the loader's / 255 + NormalizeVideo run inside the im2col kernel,
         # the H2D copy carries 1 byte per sample instead of 4
@@ -223,20 +232,8 @@ def run_ours(a, rank, world, local_rank):
     for i in range(max(a.warmup, 3)):
         step.step(dev_batch)
         note("eager warm-up step %d done" % i)
-    if use_graph:
-        step.capture(dev_batch, warmup=1)
-        note("graph captured")
-        for _ in range(2):
-            step.step_graph(dev_batch)
-        note("graph replays ok")
-    launches0 = K.launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms, _ = timed(a.steps, e2e=False)
-    launches = (step.launches_per_step * a.steps) if use_graph else (K.launch_count() - launches0)
-    ms_e2e, last_loss = timed(a.steps, e2e=True)
-    clocks = sampler.stop() if sampler else None
-
-    # instrumented extra step: per-launch CUDA events -> GEMM / attention time and work (not part of the timed region)
+    # instrumented extra step: per-launch CUDA events -> GEMM / attention time and work (not part of the timed region;
+    # run before the graph capture: its eager allocations and the graph's private pool do not fit side by side at cfg 5)
     # (every rank runs it -- a step contains collectives -- but only rank 0 keeps the timings)
     prof = None
     torch.cuda.synchronize()
@@ -252,13 +249,29 @@ def run_ours(a, rank, world, local_rank):
     streams.enable(two_streams)
     if world > 1:
         dist.barrier()
+    if use_graph:
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()   # the eager warm-up's cached blocks would sit next to the graph's private pool (cfg 5: 57 + 119 GB)
+        step.capture(dev_batch, warmup=1)
+        note("graph captured")
+        for _ in range(2):
+            step.step_graph(dev_batch)
+        note("graph replays ok")
+    launches0 = K.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, _ = timed(a.steps, e2e=False)
+    launches = (step.launches_per_step * a.steps) if use_graph else (K.launch_count() - launches0)
+    ms_e2e, last_loss = timed(a.steps, e2e=True)
+    clocks = sampler.stop() if sampler else None
+
     if rank != 0:
         return
 
     clips = a.batch * world * a.steps
     value = clips / (ms * 1e-3)
     e2e_value = clips / (ms_e2e * 1e-3)
-    flops, parts = step_flops(a.batch, a.frames, S=a.seq)
+    flops, parts = step_flops(a.batch, a.frames, img=m["img"], patch=m["patch"], S=a.seq, C=m["C"], depth=m["depth"], n_fuse=m["n_fuse"])
     executed = sum(w for (t, w, n) in prof.values())      # FLOPs of the products actually issued (exact shortcuts Q6 / Q7 and
     #                                                        the re-associated cross-attention make it smaller than `flops`)
     ref_gpu = None
@@ -300,7 +313,7 @@ def run_ours(a, rank, world, local_rank):
 
     cpu_val, cores, cpu_dt = (None, None, None)
     cpu_desc = None
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and a.config == "cfg3":   # (the fp32 port of a cfg-5 clip would take many minutes)
         n_cpu = a.cpu_sample if a.cpu_sample > 0 else a.batch     # default: the workload's own per-GPU batch, one step
         cpu_val, cores, cpu_dt = cpu_port_clips_per_sec(a, n_cpu)
         cpu_desc = ("B=%d clips of the workload, 1 step fwd+bwd (no optimizer), fp32 oracle port, %d torch threads, %.1f s"
@@ -316,7 +329,7 @@ def run_ours(a, rank, world, local_rank):
                    "step_tflop_executed": round(executed / 1e12, 2),
                    "step_frac_of_sustained_peak_executed": round(executed / (ms / a.steps * 1e-3) / 1e12 / sustained, 4),
                    "train_mode": True,
-                   "reference_gpu_eager": None if ref_gpu is None or world != 1 or a.batch != 8 or a.frames != 16 else {
+                   "reference_gpu_eager": None if ref_gpu is None or world != 1 or a.batch != 8 or a.frames != 16 or a.config != "cfg3" else {
                        "clips_per_sec": round(ref_gpu["value"], 3), "ms_per_step": round(ref_gpu["ms_per_step"], 1),
                        "what": "UNMODIFIED reference, 1 B200 of this pool, fp16 autocast + GradScaler, yaml defaults "
                                "(use_checkpoint: True), DDP static_graph, torch AdamW -- tools/bench_ref_gpu.py, "
@@ -367,9 +380,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
-    ap.add_argument("--frames", type=int, default=16)
-    ap.add_argument("--seq", type=int, default=32)
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS),
+                    help="BASELINE.json config: cfg3 = the headline workload; cfg5 = TimeSformer-L/14 + RoBERTa-large, 32 frames "
+                         "336^2, seq 64, per-GPU batch 2 (bs 16 over 8 GPUs)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8 for cfg3, 2 for cfg5)")
+    ap.add_argument("--frames", type=int, default=0)
+    ap.add_argument("--seq", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, dest="cpu_sample",
                     help="clips per step of the CPU port; 0 = the workload's batch (8) for the cpu_baseline of the default arm "
                          "(one step, ~38 s on 16 host threads) and 3 for every step of --impl reference")
@@ -379,6 +395,8 @@ def main():
     ap.add_argument("--input-dtype", default="f32", choices=["f32", "u8"], dest="input_dtype",
                     help="video frames as the reference's loader ships them (f32, normalised) or as decoded (uint8)")
     a = ap.parse_args()
+    dflt = dict(cfg3=(8, 16, 32), cfg5=(2, 32, 64))[a.config]
+    a.batch, a.frames, a.seq = a.batch or dflt[0], a.frames or dflt[1], a.seq or dflt[2]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -97,6 +97,9 @@ class PretrainStep:
                 self._device_step(self.static)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        # the warm-up's cached blocks belong to the side stream's pool; the capture allocates a private pool of the same
+        # size next to them (cfg 5 at B = 2: 57 + 119 GB): give them back first
+        torch.cuda.empty_cache()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.kernels().launch_count()
         with torch.cuda.graph(self.graph):

@@ -745,8 +745,9 @@ def test_bgemm_per_clip_reductions_over_tokens(K, R):
         check(a, b, 6e-3, "per-clip " + name)
 
 
-def test_xattn_row_kernels(K, R):
-    B, HS, N = 2, 384, 3137
+@pytest.mark.parametrize("N", [3137, 18433])   # cfg 3 rows (register-resident kernels); cfg 5 rows (streaming variants)
+def test_xattn_row_kernels(K, R, N):
+    B, HS = (2, 384) if N < 4094 else (1, 96)
     Np = (N + 7) // 8 * 8
     Sc = rnd(B, HS, Np, dtype=torch.float32, scale=3.0, seed=21)
     dP = rnd(B, HS, Np, dtype=torch.float32, seed=22)
@@ -770,6 +771,8 @@ def test_xattn_row_kernels(K, R):
         check(dS, dS_r, 8e-3, "row dsoftmax p=%g" % p_drop)
         check(lse, lse_r, 1e-5, "lse")
         check(rs, rs_r, 5e-3, "rsum")
+    if N != 3137:
+        return
     # query-bias kernels and the value bias under dropout
     Bc, S, H, C = 3, 32, 12, 768
     kv = rnd(Bc * S, 2 * C, seed=24)

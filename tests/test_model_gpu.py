@@ -390,3 +390,54 @@ def test_benchmarked_config_step_vs_oracle(cfg_id):
         assert v["finite"], k
         assert v["ours"] <= max(3e-2, 10.0 * v["fp16"]), (k, v)
         assert v["ours"] <= 0.6, (k, v)
+
+
+def test_cfg5_width_patch14_step_vs_oracle():
+    """BASELINE cfg 5 geometry at toy depth: TimeSformer-L/14 + RoBERTa-large widths (C = 1024, 16 heads of 64, patch 14:
+    the zero-padded im2col depth 588 -> 592), text length 64 (video->text cross-attention through the non-re-associated
+    path, S != 32), fusion in the top 2 of 8 layers -- a full EgoNCE + MLM + ITM step, forward and sampled gradients,
+    against the fp32 oracle (the reference's FrozenInTime hard-codes base_patch16_224: the oracle is the checker here,
+    SURVEY.md Q12)."""
+    from egovlpv2_b200.trainer import build_model
+    c = dict(C=1024, heads=16, depth=8, n_fuse=2, T=3, img=56, patch=14, S=64, B=4, proj=256, vocab=50265)
+    shapes = O.key_shapes(C=c["C"], heads=c["heads"], depth=c["depth"], n_fuse=c["n_fuse"], T=c["T"], img=c["img"],
+                          patch=c["patch"], vocab=c["vocab"], proj=c["proj"])
+    sd = O.seeded_state(shapes, 0)
+    data = O.synthetic_batch(c["B"], c["T"], c["img"], c["S"], seed=77)
+    plan = O.synthetic_itm_plan(c["B"], seed=78)
+    model = build_model(T=c["T"], img=c["img"], C=c["C"], heads=c["heads"], depth=c["depth"], n_fuse=c["n_fuse"],
+                        vocab=c["vocab"], proj=c["proj"], patch=c["patch"])
+    model.load_state_dict(sd, strict=False)
+    model.eval().to(DEV)
+    model.itm_plan = plan
+    d = {k: v.to(DEV) for k, v in data.items()}
+    batch = {"video": d["video"], "text": {"input_ids": d["input_ids"], "attention_mask": d["attention_mask"]},
+             "text_mlm_ids": d["text_mlm_ids"], "text_mlm_labels": d["text_mlm_labels"]}
+    args = types.SimpleNamespace(world_size=1, rank=0)
+    loss, loss_dict, ret = model(batch, d["noun_vec"], d["verb_vec"], lambda t, n, a: t, 1, args, {"loss": {"type": "EgoNCE"}},
+                                 EgoNCE(), 0, task_names="EgoNCE_MLM_ITM")
+    loss.backward()
+    torch.cuda.synchronize()
+    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    ref = O.pretrain_step(data, sdr, c["heads"], c["depth"], c["n_fuse"], plan)
+    ref["loss_total"].backward()
+    for k in ("EgoNCE", "loss_mlm", "loss_itm", "loss_total"):
+        a, b = float(loss_dict[k]), float(ref[k])
+        assert abs(a - b) <= 2e-2 * max(1.0, abs(b)), (k, a, b)
+    assert (ret["sim_v2t"].cpu() - ref["sim_v2t"].detach()).abs().max().item() <= 1.5e-2
+    params = dict(model.named_parameters())
+    names = ["video_model.patch_embed.proj.weight", "video_model.blocks.7.attn.qkv_i2t.weight",
+             "video_model.blocks.6.attn.proj_i2t.weight", "text_model.encoder.layer.7.crossattention_t2i.self.key.weight",
+             "text_model.encoder.layer.2.intermediate.dense.weight", "mlm_score.decoder.weight", "itm_score.fc.weight"]
+    errs = {}
+    for k in names:
+        mine, g = params[k].grad.cpu(), sdr[k].grad
+        assert torch.isfinite(mine).all(), k
+        if mine.numel() > 70000:
+            mine, g = mine.flatten()[::37], g.flatten()[::37]
+        # text / fusion / head tensors are MLM- / ITM-driven (well conditioned); the patch embedding is EgoNCE-driven (see
+        # test_benchmarked_config_step_vs_oracle for why that one is loose at random init)
+        tol = 0.4 if k.startswith("video_model.patch_embed") else 0.1
+        errs[k] = (rel(mine, g), tol)
+    print("cfg5-width gradient rel-L2:", {k: round(v[0], 4) for k, v in errs.items()})
+    assert all(e <= t for e, t in errs.values()), errs
