@@ -6,6 +6,8 @@ import os
 import sys
 import types
 
+import faulthandler
+faulthandler.dump_traceback_later(int(os.environ.get("DIST_CHECK_WATCHDOG_S", "240")), exit=True)   # a hang ends with a traceback, not with the caller's timeout
 import torch
 import torch.distributed as dist
 
@@ -102,7 +104,7 @@ for mode in ("0", "1"):
     for p in m2.parameters():
         dist.broadcast(p.data, 0)
     st = PretrainStep(m2, dev, lr=0.0, weight_decay=0.0)
-    m2.itm_plan = dict(labels=labels[sl], swap_video=swap[sl], neg_idx=neg[sl])
+    m2.itm_plan = dict(labels=labels[sl].to(dev), swap_video=swap[sl].to(dev), neg_idx=neg[sl].to(dev))   # on the device: the step is captured below
     st.step(loc)
     torch.cuda.synchronize()
     gsum = st.opt.arena.grad.clone()
@@ -114,12 +116,19 @@ for mode in ("0", "1"):
         # runs are compared to rounding noise; the 2-rank gloo test on CPU pins bit-equality of the reduction logic)
         assert (gsum - ref_grad).norm().item() <= 1e-5 * ref_grad.norm().item(), (gsum - ref_grad).abs().max().item()
         # and through the captured CUDA graph (the bench path)
+        print("[rank %d] capturing the step" % rank, flush=True)
         st.capture(loc, warmup=1)
+        print("[rank %d] captured; replaying" % rank, flush=True)
         st.step_graph(loc)
         torch.cuda.synchronize()
+        print("[rank %d] replay done" % rank, flush=True)
         g2 = st.opt.arena.grad
         assert (g2 - ref_grad).norm().item() <= 1e-5 * ref_grad.norm().item(), "graph replay of the overlapped reduction differs"
 if rank == 0:
     print("overlapped gradient all-reduce == single all-reduce: ok (%d buckets)" % st.reducer.calls)
 dist.barrier()
-dist.destroy_process_group()
+torch.cuda.synchronize()
+sys.stdout.flush()
+# (no destroy_process_group: tearing the NCCL communicator down while a captured graph that holds its collectives is alive
+#  blocks in ncclCommDestroy; the process ends here)
+os._exit(0)
