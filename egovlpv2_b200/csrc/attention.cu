@@ -1130,6 +1130,7 @@ static int fill_params(const egv_attn_args* x, AttnP& a, bool bwd) {
   a.d_o = (const bf16*)x->d_o; a.dq = (bf16*)x->dq; a.lddq = x->lddq;
   a.dk = (bf16*)x->dk; a.dv = (bf16*)x->dv; a.lddkv = x->lddkv;
   a.delta = x->delta; a.dkv_cls = x->dkv_cls; a.dkv_accumulate = x->dkv_accumulate;
+  a.lse_cls = bwd ? x->lse_cls : nullptr; a.dq_cls = bwd ? x->dq_cls : nullptr;
   a.n_split = 1; a.ws = (float*)x->workspace; a.ws_floats = x->workspace_bytes / 4;
   if (bwd) {
     if (!x->d_o || !x->dq || !x->dk || !x->dv || !x->delta) return fail(EGV_ERR_ARG, "attention bwd: null gradient buffer");
@@ -1350,6 +1351,7 @@ extern "C" int egv_attention_bwd(const egv_attn_args* x, egv_stream_t stream) {
   AttnP a;
   int rc = fill_params(x, a, true);
   if (rc) return rc;
+  if (x->cls_query_folded) *x->cls_query_folded = 0;
   if (single_heads_ok(a)) {
     const size_t n = (size_t)a.B * a.H * HD;
     float* acc = sq_zeroed<float, 1>(n);            // zero between calls: the last CTA per batch element re-zeroes it
@@ -1375,12 +1377,31 @@ extern "C" int egv_attention_bwd(const egv_attn_args* x, egv_stream_t stream) {
     if (r != 0) return r < 0 ? r : EGV_OK;
   }
   {
-    const int r = launch_tc_attention_bwd(a, (cudaStream_t)stream);    // space attention: one tcgen05 launch
+    int folded = 0;
+    const int r = launch_tc_attention_bwd(a, (cudaStream_t)stream, &folded);    // space attention: one tcgen05 launch
+    if (r > 0 && x->cls_query_folded) *x->cls_query_folded = folded;
     if (r != 0) return r < 0 ? r : EGV_OK;
   }
   rc = launch_mode<MODE_DQ>(a, (cudaStream_t)stream);   // also produces delta
   if (rc) return rc;
   return launch_mode<MODE_DKV>(a, (cudaStream_t)stream);
+}
+
+__global__ void attn_cls_query_finalize_kernel(const float* __restrict__ dq_cls, bf16* dq, long long lddq, long long q_bstride,
+                                               int cls_row, int B, int H) {
+  pdl_enter();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H * HD) return;
+  const int b = idx / (H * HD), c = idx % (H * HD);
+  dq[((long long)b * q_bstride + cls_row) * lddq + c] = __float2bfloat16(dq_cls[idx]);
+}
+
+extern "C" int egv_attention_cls_query_finalize(const float* dq_cls, void* dq, int64_t lddq, int64_t q_bstride, int cls_row, int B,
+                                                int H, egv_stream_t stream) {
+  if (!dq_cls || !dq) return fail(EGV_ERR_ARG, "cls_query_finalize: null pointer");
+  const int n = B * H * HD;
+  launch_k(attn_cls_query_finalize_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, dq_cls, (bf16*)dq, lddq, q_bstride, cls_row, B, H);
+  return check_launch("attn_cls_query_finalize_kernel");
 }
 
 extern "C" int egv_attention_cls_finalize(const float* dkv_cls, void* dk, void* dv, int64_t lddkv, int64_t kv_bstride,

@@ -36,6 +36,8 @@ struct AttnP {
   float* delta;
   float* dkv_cls;
   int dkv_accumulate;
+  const float* lse_cls;   // optional CLS-query fold (egv_attn_args): that query's lse [B, H], its dq accumulator [B, H, 64]
+  float* dq_cls;
   int row_tiles;       // tiles of the row side per group
   long long items;     // B*G*H*row_tiles*n_split
   // stream-side split (few rows, long stream: text->video attention and the key side of video->text attention):
@@ -92,7 +94,7 @@ int launch_tc_attention(int mode, const AttnP& a, cudaStream_t stream);
 void set_tc_attention_mode(int mode);
 // attention_tc_bwd.cu: the whole backward (dQ, dK, dV) of the same problems in one tcgen05 launch; the caller zeroes
 // dkv_cls (the shared CLS key's fp32 accumulators) and finalises it as for the mma.sync kernels.
-int launch_tc_attention_bwd(const AttnP& a, cudaStream_t stream);
+int launch_tc_attention_bwd(const AttnP& a, cudaStream_t stream, int* cls_query_folded);
 
 // gemm.cu: cached bf16 2-D tensor map (`inner` contiguous elements, `outer` rows `ld` elements apart, 128B swizzle)
 int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(const __grid_co
         const int h = (int)(p % a.H), g = (int)((p / a.H) % a.G), b = (int)(p / HG);
         const long long o_first = (long long)b * a.o_bstride + a.q_row0 + (long long)g * a.q_gstride + 128 * w;
         const long long stat_base = (((long long)b * a.H + h) * a.G + g) * a.Lq + 128 * w;
-        mbar_wait(&s_full[w], ph);
+        mbar_wait_sleep(&s_full[w], ph, 32);   // sleeping polls: 16 tightly polling warps take issue slots from the MMA issuer and the producer
         tc_fence_after();
         float inv = 0.f;
         if (warp_live) {
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(const __grid_co
         if (lane == 0) mbar_arrive(&p_ready[w]);
         // ---- output: O_w / rowsum -> bf16 -> the 32 rows of the staging tile these two warps share (= P_w sub-tile 0, free
         // once PV retired); this half converts 32 of the 64 columns and stores 16 of the 32 rows
-        mbar_wait(&o_full[w], ph);
+        mbar_wait_sleep(&o_full[w], ph, 32);
         tc_fence_after();
         if (warp_live) {
           uint32_t v[32];

@@ -25,6 +25,13 @@
 //   warp 2        TMEM allocator (512 columns)
 //   warps 4-19    compute: TMEM lane quadrant (warp % 4) x 32-column quarter; tcgen05.ld -> exp2 -> swizzled bf16 stores;
 //                 accumulator drains (bf16 rows of dq / dk / dv; the shared CLS key row goes to the fp32 dkv_cls accumulators)
+// CLS query (video_transformer.py:134-150: the CLS token attends every token of the clip).  In the transposed form its
+// backward is almost free: its q / dO / O rows are copied into the first unused query slot of tile 1 (196 queries = 128 + 68:
+// slot 68 of the 80-wide tile), its log-sum-exp (over ALL keys of the clip, from the forward) into the statistics; the score
+// products then deliver S^T[key, 68] = k . q_cls and dP^T[key, 68] = v . dO_cls, the exponentials its global probabilities,
+// and the dV / dK products add its contribution to every key row -- no separate pass over K and V (attn_single_bwd_heads:
+// 49 us per call).  Its dQ partial (this frame's keys) is accumulated with atomics; the (CLS key, CLS query) pair, which
+// every frame's problem sees, is counted in frame 0 only.
 // Eligibility (else the mma.sync kernels of attention_group.cu run): contiguous groups with the shared CLS key,
 // 128 < queries <= 224, 129 < keys + 1 <= 256, no key bias.
 #include <cuda.h>
@@ -64,6 +71,7 @@ struct Prm {
   uint32_t smem_base;   // shared-window address of the 1024-aligned tile area, probed once by the host (see launch): the MMA
                         // issuer builds every operand descriptor from this kernel PARAMETER, i.e. in uniform registers
   uint32_t* probe;      // non-null: write that address here and exit
+  int fold;             // 1: the clip's CLS QUERY rides along as query slot `rows1` of tile 1 (see "CLS query" below)
   int trace;       // debugging: EGV_ATB_TRACE=1 records SM clock stamps of the third problem of CTA 0 (printed by the host)
 };
 
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int w = 0; w < 2; ++w) {
-      mbar_init(&qdo_full[w], 1);
+      mbar_init(&qdo_full[w], w == 1 && pr.fold ? 2 : 1);   // tile 1: + the CLS query's row copies
       mbar_init(&qdo_empty[w], 2);   // both MMA issuers read Q_w / dO_w
       mbar_init(&kv_empty[w], 1);
       mbar_init(&dq_full[w], 1);
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
     mbar_init(p_free, 2);          // both MMA issuers read P^T / dS^T
     mbar_init(dkv_full, 1);
     mbar_init(dkv_free, 16);
-    mbar_init(o_full, 1);
+    mbar_init(o_full, pr.fold ? 2 : 1);
     mbar_init(o_free, 1);
     fence_barrier_init();
   }
@@ -263,6 +271,14 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
         tma_load_2d(smem + OFF_O, &maps.o0, o_full, h * HD, o_first);
         tma_load_2d(smem + OFF_O + TILE, &maps.o1, o_full, h * HD, o_first + 128);
       }
+      const long long qcls_off = ((long long)b * a.q_bstride + a.cls_row) * a.ldq + h * HD + (lane & 7) * 8;
+      const long long ocls_off = ((long long)b * a.o_bstride + a.cls_row) * a.ldo + h * HD + (lane & 7) * 8;
+      const int cls_slot = pr.rows1 * 128 + (((lane & 7) ^ (pr.rows1 & 7)) << 4);   // query slot rows1 of tile 1, swizzled like a TMA row
+      if (pr.fold) {
+        if (lane < 8) *reinterpret_cast<uint4*>(smem + OFF_O + TILE + cls_slot) = *reinterpret_cast<const uint4*>(a.o + ocls_off);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_full);
+      }
       // order of first use: K_0 V_0 Q_0 dO_0 (step (0,0)), Q_1 dO_1 (step (0,1)), K_1 V_1 (step (1,0))
       mbar_wait_sleep(&kv_empty[0], ph ^ 1, 64);
       ATB_TR(ptr, 48);
@@ -279,6 +295,16 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
           mbar_arrive_expect_tx(&qdo_full[w], 2u * (uint32_t)rows * 128u);
           tma_load_2d(smem + OFF_Q + w * TILE, w == 0 ? &maps.q0 : &maps.q1, &qdo_full[w], h * HD, q_first + 128 * w);
           tma_load_2d(smem + OFF_DO + w * TILE, w == 0 ? &maps.do0 : &maps.do1, &qdo_full[w], h * HD, o_first + 128 * w);
+        }
+        if (w == 1 && pr.fold) {   // the CLS query's q and dO rows
+          if (lane < 16) {
+            const bool is_q = lane < 8;
+            const uint4 val = *reinterpret_cast<const uint4*>(is_q ? a.q + qcls_off : a.d_o + ocls_off);
+            *reinterpret_cast<uint4*>(smem + (is_q ? OFF_Q : OFF_DO) + TILE + cls_slot) = val;
+          }
+          fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&qdo_full[1]);
         }
       }
       mbar_wait_sleep(&kv_empty[1], ph ^ 1, 64);
@@ -450,7 +476,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
       }
     };
     // dQ_w: 128 query rows x 64 columns; this warp: its 32 rows x 16 columns
-    auto drain_dq = [&](int w, uint32_t phase, int h, long long q_first) {
+    auto drain_dq = [&](int w, uint32_t phase, int b, int h, long long q_first) {
       mbar_wait_sleep(&dq_full[w], phase, 32);
       tc_fence_after();
       uint32_t acc[16];
@@ -466,6 +492,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
 #pragma unroll
         for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(__uint_as_float(acc[2 * e]) * a.scale, __uint_as_float(acc[2 * e + 1]) * a.scale);
         stg256(dst, pk);
+      } else if (pr.fold && w == 1 && row == pr.rows1) {   // the CLS query's dQ: this frame's keys' share
+        float* dst = a.dq_cls + ((long long)b * a.H + h) * HD + cq * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(dst + i, __uint_as_float(acc[i]) * a.scale);
       }
     };
 
@@ -492,11 +522,13 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
       // dO rows.  Query tile 0 before step 0; tile 1 (whose dO rows land last) before step 1, the first step that reads it.
       ATB_TR(tr, 41);
       float lse_r = 1.0e30f;                // slots beyond the group: P = exp2(-huge) = 0
-      if (ct < a.Lq) lse_r = ldg_now_f32(a.lse + stat_base + ct);     // (Lq <= 256)
+      const bool cls_slot_thread = pr.fold && ct == a.Lq;             // query slot rows1 of tile 1 carries the CLS query
+      if (ct < a.Lq) lse_r = ldg_now_f32(a.lse + stat_base + ct);     // (Lq <= 224)
+      else if (cls_slot_thread) lse_r = ldg_now_f32(a.lse_cls + (long long)b * a.H + h);
       auto stats_rows = [&](int tile) {
         if ((ct >> 7) == tile) {
           float dl = 0.f;
-          if (ct < a.Lq) {
+          if (ct < a.Lq || cls_slot_thread) {
             mbar_wait_sleep(&qdo_full[tile], ph, 32);
             mbar_wait_sleep(o_full, ph, 32);
             ATB_TR(tr, 43);
@@ -515,7 +547,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
                 dl = fmaf(x.y, y.y, dl);
               }
             }
-            if (a.delta) a.delta[stat_base + ct] = dl;
+            if (a.delta && ct < a.Lq) a.delta[stat_base + ct] = dl;
           }
           s_lse[ct] = lse_r;
           s_delta[ct] = dl;
@@ -597,6 +629,13 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
             }
           }
         }
+        if (pr.fold && t == 3 && g != 0 && row == pr.keys1 && pr.rows1 >= c0 && pr.rows1 < c0 + 32) {
+          // (CLS key, CLS query): every frame's problem sees the pair; it is counted in frame 0 only
+          const int c = pr.rows1;
+          uint8_t* el = smem + OFF_P + (c >> 6) * TILE + row * 128 + ((((c & 63) >> 3) ^ (row & 7)) << 4) + (c & 7) * 2;
+          *reinterpret_cast<uint16_t*>(el) = 0;
+          *reinterpret_cast<uint16_t*>(el + (OFF_DS - OFF_P)) = 0;
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
@@ -605,7 +644,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
         if (t == 0 && pending) {
           drain_dkv(1, pb, phd, pk_first);
           ATB_TR(tr, 60);
-          drain_dq(1, ph ^ 1, phd, pq_first);
+          drain_dq(1, ph ^ 1, pb, phd, pq_first);
           ATB_TR(tr, 61);
         }
         if (t == 2) {
@@ -613,7 +652,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
           ATB_TR(tr, 33);
         }
         if (t == 3) {
-          drain_dq(0, ph, h, q_first);
+          drain_dq(0, ph, b, h, q_first);
           ATB_TR(tr, 38);
         }
       }
@@ -625,7 +664,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
     }
     if (pending) {
       drain_dkv(1, pb, phd, pk_first);
-      drain_dq(1, ph ^ 1, phd, pq_first);
+      drain_dq(1, ph ^ 1, pb, phd, pq_first);
     }
   }
   tc_fence_before();
@@ -639,7 +678,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(const __grid_co
 }  // namespace atb
 
 // returns 1 when it launched the tcgen05 backward for this problem, 0 when the problem is not eligible, < 0 on error
-int launch_tc_attention_bwd(const AttnP& a, cudaStream_t stream) {
+int launch_tc_attention_bwd(const AttnP& a, cudaStream_t stream, int* cls_query_folded) {
   using namespace atb;
   static int mode = -1;   // env EGV_ATTN_TC: bit 1 = backward (default on)
   if (mode < 0) mode = getenv("EGV_ATTN_TC") ? atoi(getenv("EGV_ATTN_TC")) : 3;
@@ -657,6 +696,11 @@ int launch_tc_attention_bwd(const AttnP& a, cudaStream_t stream) {
   pr.nk1 = (pr.keys1 + 1 + 15) / 16 * 16;
   pr.total = (long long)a.B * a.G * a.H;
   if (pr.total <= 0) return 0;
+  // the CLS query takes the first unused query slot of tile 1, if there is one (and the O staging buffer has that row)
+  static int fold_mode = -1;   // env EGV_ATTN_FOLD_CLS=0 keeps the separate single-query backward
+  if (fold_mode < 0) fold_mode = getenv("EGV_ATTN_FOLD_CLS") ? atoi(getenv("EGV_ATTN_FOLD_CLS")) : 1;
+  pr.fold = (fold_mode && a.lse_cls && a.dq_cls && pr.rows1 < pr.nq1 && pr.rows1 < 96) ? 1 : 0;
+  if (cls_query_folded) *cls_query_folded = pr.fold;
   Maps maps;
   const uint64_t width = (uint64_t)a.H * HD;
   const uint64_t q_rows = (uint64_t)a.B * a.q_bstride, kv_rows = (uint64_t)a.B * a.kv_bstride, o_rows = (uint64_t)a.B * a.o_bstride;

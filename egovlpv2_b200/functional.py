@@ -160,10 +160,23 @@ def divided_attention_bwd(K, qkv, o, lses, d_o, H, T, Nf, mode):
     lse, lse_cls = lses
     d_qkv = _e(qkv, (B, N, C3), BF16)
     dq, dk, dv = d_qkv[:, :, :C], d_qkv[:, :, C:2 * C], d_qkv[:, :, 2 * C:]
-    dkv_cls = _z(qkv, (B * H * 128,))
-    K.attention_bwd(spec, q, k, v, o, lse, d_o, dq, dk, dv, _e(qkv, lse.shape, F32), dkv_cls=dkv_cls)
-    K.attention_bwd(cls, q, k, v, o, lse_cls, d_o, dq, dk, dv, _e(qkv, lse_cls.shape, F32), dkv_cls=dkv_cls,
-                    dkv_accumulate=True)
+    # the CLS query (video_transformer.py:134-150) rides along in the space-attention backward when the kernel can take it
+    # (csrc/attention_tc_bwd.cu); its dq accumulator shares the zero fill of the CLS key's accumulators
+    try_fold = mode == "space" and getattr(K, "supports_cls_fold", False)
+    acc = _z(qkv, (B * H * (192 if try_fold else 128),))
+    dkv_cls = acc[:B * H * 128]
+    folded = False
+    if try_fold:
+        dq_cls = acc[B * H * 128:]
+        folded = K.attention_bwd(spec, q, k, v, o, lse, d_o, dq, dk, dv, _e(qkv, lse.shape, F32), dkv_cls=dkv_cls,
+                                 lse_cls=lse_cls, dq_cls=dq_cls)
+    else:
+        K.attention_bwd(spec, q, k, v, o, lse, d_o, dq, dk, dv, _e(qkv, lse.shape, F32), dkv_cls=dkv_cls)
+    if folded:
+        K.attention_cls_query_finalize(dq_cls, dq, H, cls_row=0)
+    else:
+        K.attention_bwd(cls, q, k, v, o, lse_cls, d_o, dq, dk, dv, _e(qkv, lse_cls.shape, F32), dkv_cls=dkv_cls,
+                        dkv_accumulate=True)
     K.attention_cls_finalize(dkv_cls, dk, dv, H, cls_row=0, accumulate=False)
     return d_qkv
 

@@ -79,7 +79,8 @@ class AttnArgs(C.Structure):
                 ("d_o", c_void_p), ("dq", c_void_p), ("lddq", c_int64),
                 ("dk", c_void_p), ("dv", c_void_p), ("lddkv", c_int64),
                 ("delta", c_void_p), ("dkv_cls", c_void_p), ("dkv_accumulate", c_int),
-                ("workspace", c_void_p), ("workspace_bytes", c_int64)]
+                ("workspace", c_void_p), ("workspace_bytes", c_int64),
+                ("lse_cls", c_void_p), ("dq_cls", c_void_p), ("cls_query_folded", C.POINTER(c_int))]
 
 
 @dataclasses.dataclass(frozen=True)
@@ -433,8 +434,13 @@ class Kernels:
         work = 4.0 * a.B * spec.H * spec.G * spec.Lq * (spec.Lk + int(spec.has_cls_key)) * 64
         self._timed("attn_fwd", work, lambda: self._check(self.lib.egv_attention_fwd(C.byref(a), self._stream())))
 
+    supports_cls_fold = True    # attention_bwd(..., lse_cls=, dq_cls=) may take the clip's CLS query along (egv_attn_args)
+
     def attention_bwd(self, spec, q, k, v, o, lse, d_o, dq, dk, dv, delta, dkv_cls=None, dkv_accumulate=False,
-                      key_bias=None):
+                      key_bias=None, lse_cls=None, dq_cls=None):
+        """-> True when the kernel also handled the CLS query (lse_cls [B*H] f32 from the single-query forward, dq_cls
+        [B*H*64] f32 zeroed accumulator given): the caller then skips the single-query backward and calls
+        attention_cls_query_finalize."""
         a = self._attn_args(spec, q, k, v, o, lse, key_bias)
         assert self._rows3(d_o, "d_o") == (a.ldo, a.o_bstride)
         a.lddq, bq = self._rows3(dq, "dq")
@@ -447,8 +453,19 @@ class Kernels:
             assert dkv_cls.dtype == torch.float32 and dkv_cls.numel() == a.B * spec.H * 128
             a.dkv_cls = _p(dkv_cls)
         a.dkv_accumulate = int(bool(dkv_accumulate))
+        folded = c_int(0)
+        if lse_cls is not None and dq_cls is not None:
+            assert lse_cls.dtype == torch.float32 and lse_cls.numel() == a.B * spec.H and lse_cls.is_contiguous()
+            assert dq_cls.dtype == torch.float32 and dq_cls.numel() == a.B * spec.H * 64 and dq_cls.is_contiguous()
+            a.lse_cls, a.dq_cls, a.cls_query_folded = _p(lse_cls), _p(dq_cls), C.pointer(folded)
         work = 8.0 * a.B * spec.H * spec.G * spec.Lq * (spec.Lk + int(spec.has_cls_key)) * 64
         self._timed("attn_bwd", work, lambda: self._check(self.lib.egv_attention_bwd(C.byref(a), self._stream())))
+        return bool(folded.value)
+
+    def attention_cls_query_finalize(self, dq_cls, dq, H, cls_row=0):
+        ld, bs = self._rows3(dq, "dq")
+        self._check(self.lib.egv_attention_cls_query_finalize(_p(dq_cls), _p(dq), c_int64(ld), c_int64(bs), cls_row, dq.shape[0], H,
+                                                              self._stream()))
 
     def attention_cls_finalize(self, dkv_cls, dk, dv, H, cls_row=0, accumulate=False):
         ld, bs = self._rows3(dk, "dk")

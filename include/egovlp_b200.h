@@ -227,6 +227,15 @@ typedef struct egv_attn_args {
   /* optional scratch for the split-stream path (few rows x long stream, e.g. 32 text queries x 3137 video keys):
    * egv_attention_workspace_bytes() bytes of device memory, contents undefined; NULL = never split */
   void* workspace; int64_t workspace_bytes;
+  /* optional, backward of the grouped problems only: fold the CLS QUERY of the divided attention into the group kernel
+   * (video_transformer.py:134-150: the CLS token attends every token of the clip, i.e. every group).  lse_cls f32 [B, H] =
+   * that query's log-sum-exp as egv_attention_fwd of the single-query problem wrote it; dq_cls f32 [B, H, 64] = accumulator
+   * (zeroed by the caller) for its query gradient; its q / o / d_o rows are row `cls_row` of each batch.  When the kernel
+   * takes the fold it adds the query's contribution to dk / dv (and to dkv_cls) itself, and *cls_query_folded (a HOST int)
+   * is set to 1: the caller then skips the separate single-query backward and calls egv_attention_cls_query_finalize. */
+  const float* lse_cls;
+  float* dq_cls;
+  int* cls_query_folded;
 } egv_attn_args;
 int64_t egv_attention_workspace_bytes(const egv_attn_args* a);
 /* Threading: the entry points are stream-ordered and may be issued on several streams concurrently, with ONE exception:
@@ -245,6 +254,9 @@ void egv_attention_set_tc(int mode);
 /* dk/dv row `cls_row` of every batch (+)= the fp32 accumulators dkv_cls [B,H,2,64] filled by egv_attention_bwd */
 int egv_attention_cls_finalize(const float* dkv_cls, void* dk, void* dv, int64_t lddkv, int64_t kv_bstride, int cls_row,
                                int B, int H, int accumulate, egv_stream_t stream);
+/* dq row `cls_row` of every batch = bf16 of the fp32 accumulator dq_cls [B, H, 64] of a folded CLS query (see egv_attn_args) */
+int egv_attention_cls_query_finalize(const float* dq_cls, void* dq, int64_t lddq, int64_t q_bstride, int cls_row, int B, int H,
+                                     egv_stream_t stream);
 
 /* Elementwise / reductions --------------------------------------------------------------------- */
 /* fp32 -> bf16 cast (weights, activations); n elements */

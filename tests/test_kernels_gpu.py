@@ -12,6 +12,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+from egovlpv2_b200 import functional as Fn  # noqa: E402
 from egovlpv2_b200 import lib as L  # noqa: E402
 from tests.fake_kernels import FakeKernels  # noqa: E402
 
@@ -396,6 +397,37 @@ def test_attention_fwd_bwd(K, R, name):
     for n, a, r in zip("o lse dq dk dv delta".split(), outs[0], outs[1]):
         tol = {"dq": 1.2e-2, "dk": 1.2e-2, "dv": 1.2e-2, "o": 8e-3, "delta": 2e-2, "lse": 1e-4}[n]
         check(a, r, tol, "attention %s %s" % (name, n))
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 3, 196), (2, 12, 2, 196), (1, 4, 2, 170)])
+def test_space_attention_backward_folds_cls_query(K, R, shape):
+    """functional.divided_attention_bwd in space mode: the tcgen05 backward (csrc/attention_tc_bwd.cu) takes the clip's CLS
+    query along (its q / dO / O rows in the first unused query slot of tile 1, its global lse in the statistics) instead of
+    a separate pass over all keys -- against the restatement, which runs the two backward calls of the reference
+    formulation (video_transformer.py:134-150).  Every element of d_qkv incl. the CLS row."""
+    B, H, T, Nf = shape
+    C = H * 64
+    N = 1 + T * Nf
+    qkv = rnd(B, N, 3 * C, seed=91)
+    d_o = rnd(B, N, C, seed=92)
+    outs = []
+    for impl in (K, R):
+        o, lses = Fn.divided_attention_fwd(impl, qkv, H, T, Nf, "space")
+        n0 = impl.launch_count() if impl is K else 0
+        d_qkv = Fn.divided_attention_bwd(impl, qkv, o, lses, d_o, H, T, Nf, "space")
+        if impl is K:
+            # tcgen05 backward + CLS-query finalize + CLS-key finalize (+ nothing else): the single-query backward is gone
+            assert K.launch_count() - n0 == 3, K.launch_count() - n0
+        outs.append((o, d_qkv))
+    check(outs[0][0], outs[1][0], 8e-3, "space attention o")
+    dq, dk, dv = (outs[0][1][:, :, i * C:(i + 1) * C] for i in range(3))
+    rq, rk, rv = (outs[1][1][:, :, i * C:(i + 1) * C] for i in range(3))
+    check(dq[:, 1:], rq[:, 1:], 1.2e-2, "dq patches")
+    check(dq[:, :1], rq[:, :1], 1.2e-2, "dq of the CLS query (folded)")
+    check(dk[:, 1:], rk[:, 1:], 1.2e-2, "dk patches (incl. the CLS query's share)")
+    check(dv[:, 1:], rv[:, 1:], 1.2e-2, "dv patches (incl. the CLS query's share)")
+    check(dk[:, :1], rk[:, :1], 1.2e-2, "dk of the CLS key")
+    check(dv[:, :1], rv[:, :1], 1.2e-2, "dv of the CLS key")
 
 
 @pytest.mark.parametrize("case", ["cls", "cls_h12"])
