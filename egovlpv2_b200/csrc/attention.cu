@@ -1131,6 +1131,7 @@ static int fill_params(const egv_attn_args* x, AttnP& a, bool bwd) {
   a.dk = (bf16*)x->dk; a.dv = (bf16*)x->dv; a.lddkv = x->lddkv;
   a.delta = x->delta; a.dkv_cls = x->dkv_cls; a.dkv_accumulate = x->dkv_accumulate;
   a.lse_cls = bwd ? x->lse_cls : nullptr; a.dq_cls = bwd ? x->dq_cls : nullptr;
+  a.cls_part = nullptr; a.fold_out = nullptr;
   a.n_split = 1; a.ws = (float*)x->workspace; a.ws_floats = x->workspace_bytes / 4;
   if (bwd) {
     if (!x->d_o || !x->dq || !x->dk || !x->dv || !x->delta) return fail(EGV_ERR_ARG, "attention bwd: null gradient buffer");
@@ -1344,7 +1345,27 @@ extern "C" int egv_attention_fwd(const egv_attn_args* x, egv_stream_t stream) {
     const int r = launch_tiny_attention(0, a, (cudaStream_t)stream);   // many tiny groups (time attention)
     if (r != 0) return r < 0 ? r : EGV_OK;
   }
-  return launch_mode<MODE_FWD>(a, (cudaStream_t)stream);
+  // optional: the group kernel takes the clip's CLS query along (egv_attn_args::lse_cls is the OUTPUT here): per-frame
+  // partials in the library's single-query scratch, merged by the single-query combine kernel
+  int folded = 0;
+  if (x->cls_query_folded) *x->cls_query_folded = 0;
+  if (x->lse_cls && x->cls_query_folded && a.has_cls && a.G <= SQ_SPLITS_MAX && a.H % 4 == 0 && a.H <= 16) {
+    a.cls_part = sq_workspace((size_t)a.B * SQ_SPLITS_MAX * a.H * 66);
+    a.fold_out = &folded;
+  }
+  rc = launch_mode<MODE_FWD>(a, (cudaStream_t)stream);
+  if (rc || !folded) return rc;
+  AttnP c = a;     // the CLS query as a single-query problem whose G key splits are the frames
+  c.n_split = a.G;
+  c.G = 1;
+  c.Lq = 1;
+  c.q_row0 = a.cls_row;
+  c.q_gstride = 0;
+  c.lse = const_cast<float*>(x->lse_cls);
+  launch_k(attn_single_combine_kernel, dim3((unsigned)(a.B * a.H)), dim3(64), 0, (cudaStream_t)stream, c, (const float*)a.cls_part);
+  rc = check_launch("attn_single_combine_kernel");
+  if (!rc) *x->cls_query_folded = 1;
+  return rc;
 }
 
 extern "C" int egv_attention_bwd(const egv_attn_args* x, egv_stream_t stream) {

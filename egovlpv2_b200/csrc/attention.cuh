@@ -38,6 +38,8 @@ struct AttnP {
   int dkv_accumulate;
   const float* lse_cls;   // optional CLS-query fold (egv_attn_args): that query's lse [B, H], its dq accumulator [B, H, 64]
   float* dq_cls;
+  float* cls_part;        // forward fold: per-frame partials [B, G, H, 66] (library scratch), else NULL
+  int* fold_out;          // HOST pointer: set to 1 by the kernel launcher that took the CLS query along
   int row_tiles;       // tiles of the row side per group
   long long items;     // B*G*H*row_tiles*n_split
   // stream-side split (few rows, long stream: text->video attention and the key side of video->text attention):

@@ -48,6 +48,10 @@ struct Prm {
   int lk;          // regular keys (the CLS key is row lk of the K / V tiles)
   int npad;        // keys + 1 rounded up to a multiple of 16
   long long total;
+  int fold;        // 1: the clip's CLS QUERY rides along as query slot `rows1` of m-tile 1 (video_transformer.py:134-150: it
+                   // attends every token of the clip): per-frame partial (max, sum, unnormalised O) into `part`, merged by
+                   // attn_single_combine_kernel; the (CLS query, CLS key) pair is counted in frame 0 only
+  float* part;     // [B, G, H, 66] f32
 };
 
 EGV_DEVINL void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[32]) {
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int w = 0; w < 2; ++w) {
-      mbar_init(&q_full[w], 1);
+      mbar_init(&q_full[w], w == 1 && pr.fold ? 2 : 1);   // m-tile 1: + the CLS query's row copy
       mbar_init(&q_empty[w], 1);
       mbar_init(&s_full[w], 1);
       mbar_init(&p_ready[w], 8);
@@ -123,6 +127,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(const __grid_co
           const int rows = w == 0 ? (a.Lq < 128 ? a.Lq : 128) : pr.rows1;
           mbar_arrive_expect_tx(&q_full[w], (uint32_t)rows * 128u);
           tma_load_2d(smem + OFF_Q + w * QT_BYTES, w == 0 ? &maps.q0 : &maps.q1, &q_full[w], h * HD, q_first + 128 * w);
+        }
+        if (w == 1 && pr.fold) {   // the CLS query's row: slot rows1 of m-tile 1, 128B-swizzled like the TMA rows
+          if (lane < 8) {
+            const uint4 val = *reinterpret_cast<const uint4*>(a.q + ((long long)b * a.q_bstride + a.cls_row) * a.ldq + h * HD + lane * 8);
+            *reinterpret_cast<uint4*>(smem + OFF_Q + QT_BYTES + pr.rows1 * 128 + ((lane ^ (pr.rows1 & 7)) << 4)) = val;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&q_full[1]);
         }
       }
 #pragma unroll
@@ -190,8 +203,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(const __grid_co
     if (w < pr.n_mt) {
       const int row = quad * 32 + lane;       // row of the m-tile = TMEM lane
       const int rows_tile = w == 0 ? (a.Lq < 128 ? a.Lq : 128) : pr.rows1;
-      const bool warp_live = quad * 32 < rows_tile;    // warp-uniform: any valid row in this warp
-      const int nkey = pr.lk + 1;
+      const bool cls_q = pr.fold && w == 1 && row == pr.rows1;           // this thread's row is the CLS query
+      const bool warp_live = quad * 32 < rows_tile + (w == 1 ? pr.fold : 0);    // warp-uniform: any valid row in this warp
       const float sl2 = a.scale * LOG2E;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(w * 256);
       uint8_t* pw = smem + OFF_P + w * P_BYTES;
@@ -205,6 +218,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(const __grid_co
         const int h = (int)(p % a.H), g = (int)((p / a.H) % a.G), b = (int)(p / HG);
         const long long o_first = (long long)b * a.o_bstride + a.q_row0 + (long long)g * a.q_gstride + 128 * w;
         const long long stat_base = (((long long)b * a.H + h) * a.G + g) * a.Lq + 128 * w;
+        const int nkey = pr.lk + ((cls_q && g != 0) ? 0 : 1);   // the CLS query meets the CLS key in frame 0 only
+        float* cpart = pr.part + (((long long)b * a.G + g) * a.H + h) * 66;
         mbar_wait_sleep(&s_full[w], ph, 32);   // sleeping polls: 16 tightly polling warps take issue slots from the MMA issuer and the producer
         tc_fence_after();
         float inv = 0.f;
@@ -264,6 +279,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(const __grid_co
           sum += xch[512 + (half ^ 1) * 128 + row];
           inv = 1.0f / sum;
           if (half == 0 && row < rows_tile) a.lse[stat_base + row] = m2 + log2f(sum);
+          if (half == 0 && cls_q) {
+            cpart[0] = m2;
+            cpart[1] = sum;
+          }
         }
         fence_proxy_async();
         tc_fence_before();
@@ -277,6 +296,11 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(const __grid_co
           uint32_t v[32];
           tmem_ld_32x32(taddr + (uint32_t)(half * 32), v);
           tmem_ld_wait();
+          if (cls_q) {   // unnormalised partial output of the CLS query over this frame's keys
+#pragma unroll
+            for (int j = 0; j < 32; j += 2)   // (part rows are 66 floats: 8-byte alignment)
+              *reinterpret_cast<float2*>(cpart + 2 + half * 32 + j) = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+          }
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             uint32_t pk[4];
@@ -320,6 +344,7 @@ void set_tc_attention_mode(int mode) { atc::g_tc_mode = mode; }
 
 // returns 1 when it launched the tcgen05 kernel for this problem, 0 when the problem is not eligible, < 0 on error
 int launch_tc_attention(int mode, const AttnP& a, cudaStream_t stream) {
+  if (a.fold_out) *a.fold_out = 0;
   using namespace atc;
   if (g_tc_mode < 0) g_tc_mode = getenv("EGV_ATTN_TC") ? atoi(getenv("EGV_ATTN_TC")) : 1;
   if (mode != MODE_FWD || !(g_tc_mode & 1)) return 0;
@@ -334,6 +359,11 @@ int launch_tc_attention(int mode, const AttnP& a, cudaStream_t stream) {
   pr.npad = (a.LkT + 15) / 16 * 16;
   pr.total = (long long)a.B * a.G * a.H;
   if (pr.total <= 0) return 0;
+  static int fold_mode = -1;   // env EGV_ATTN_FOLD_CLS=0 keeps the separate single-query kernels
+  if (fold_mode < 0) fold_mode = getenv("EGV_ATTN_FOLD_CLS") ? atoi(getenv("EGV_ATTN_FOLD_CLS")) : 1;
+  pr.part = a.cls_part;
+  pr.fold = (fold_mode && a.cls_part && pr.n_mt == 2 && pr.rows1 < 128) ? 1 : 0;
+  if (a.fold_out) *a.fold_out = pr.fold;
   Maps maps;
   const uint64_t width = (uint64_t)a.H * HD;
   const uint64_t q_rows = (uint64_t)a.B * a.q_bstride, kv_rows = (uint64_t)a.B * a.kv_bstride;

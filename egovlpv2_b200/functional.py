@@ -145,8 +145,15 @@ def divided_attention_fwd(K, qkv, H, T, Nf, mode):
     o = _e(qkv, (B, N, C), BF16)
     lse = _e(qkv, (B * H * spec.G * spec.Lq,), F32)
     lse_cls = _e(qkv, (B * H,), F32)
-    K.attention_fwd(spec, q, k, v, o, lse)
-    K.attention_fwd(cls, q, k, v, o, lse_cls)
+    # the CLS query rides along in the space-attention kernel when it can take it (csrc/attention_tc.cu: per-frame partials
+    # + the single-query combine); else the separate single-query pass over all keys
+    folded = False
+    if mode == "space" and getattr(K, "supports_cls_fold", False):
+        folded = K.attention_fwd(spec, q, k, v, o, lse, lse_cls=lse_cls)
+    else:
+        K.attention_fwd(spec, q, k, v, o, lse)
+    if not folded:
+        K.attention_fwd(cls, q, k, v, o, lse_cls)
     return o, (lse, lse_cls)
 
 

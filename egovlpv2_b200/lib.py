@@ -429,10 +429,17 @@ class Kernels:
             a.workspace, a.workspace_bytes = _p(a._ws), nbytes
         return a
 
-    def attention_fwd(self, spec, q, k, v, o, lse, key_bias=None):
+    def attention_fwd(self, spec, q, k, v, o, lse, key_bias=None, lse_cls=None):
+        """lse_cls [B*H] f32 given: the kernel may take the clip's CLS query along (o row cls_row and lse_cls written);
+        -> True when it did (the caller then skips the single-query forward)."""
         a = self._attn_args(spec, q, k, v, o, lse, key_bias)
+        folded = c_int(0)
+        if lse_cls is not None:
+            assert lse_cls.dtype == torch.float32 and lse_cls.numel() == a.B * spec.H and lse_cls.is_contiguous()
+            a.lse_cls, a.cls_query_folded = _p(lse_cls), C.pointer(folded)
         work = 4.0 * a.B * spec.H * spec.G * spec.Lq * (spec.Lk + int(spec.has_cls_key)) * 64
         self._timed("attn_fwd", work, lambda: self._check(self.lib.egv_attention_fwd(C.byref(a), self._stream())))
+        return bool(folded.value)
 
     supports_cls_fold = True    # attention_bwd(..., lse_cls=, dq_cls=) may take the clip's CLS query along (egv_attn_args)
 

@@ -232,7 +232,10 @@ typedef struct egv_attn_args {
    * that query's log-sum-exp as egv_attention_fwd of the single-query problem wrote it; dq_cls f32 [B, H, 64] = accumulator
    * (zeroed by the caller) for its query gradient; its q / o / d_o rows are row `cls_row` of each batch.  When the kernel
    * takes the fold it adds the query's contribution to dk / dv (and to dkv_cls) itself, and *cls_query_folded (a HOST int)
-   * is set to 1: the caller then skips the separate single-query backward and calls egv_attention_cls_query_finalize. */
+   * is set to 1: the caller then skips the separate single-query backward and calls egv_attention_cls_query_finalize.
+   * egv_attention_fwd takes the same fold with lse_cls as an OUTPUT (dq_cls unused): when *cls_query_folded comes back 1,
+   * o row `cls_row` of each batch and lse_cls [B, H] hold the CLS query's attention over all keys of the clip and the
+   * caller skips the separate single-query forward. */
   const float* lse_cls;
   float* dq_cls;
   int* cls_query_folded;

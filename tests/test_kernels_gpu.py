@@ -412,14 +412,19 @@ def test_space_attention_backward_folds_cls_query(K, R, shape):
     d_o = rnd(B, N, C, seed=92)
     outs = []
     for impl in (K, R):
+        n0 = impl.launch_count() if impl is K else 0
         o, lses = Fn.divided_attention_fwd(impl, qkv, H, T, Nf, "space")
+        if impl is K:   # tcgen05 forward with the CLS query folded + the combine of its per-frame partials
+            assert K.launch_count() - n0 == 2, K.launch_count() - n0
         n0 = impl.launch_count() if impl is K else 0
         d_qkv = Fn.divided_attention_bwd(impl, qkv, o, lses, d_o, H, T, Nf, "space")
         if impl is K:
             # tcgen05 backward + CLS-query finalize + CLS-key finalize (+ nothing else): the single-query backward is gone
             assert K.launch_count() - n0 == 3, K.launch_count() - n0
-        outs.append((o, d_qkv))
-    check(outs[0][0], outs[1][0], 8e-3, "space attention o")
+        outs.append((o, d_qkv, lses[1]))
+    check(outs[0][0][:, 1:], outs[1][0][:, 1:], 8e-3, "space attention o")
+    check(outs[0][0][:, :1], outs[1][0][:, :1], 8e-3, "o of the CLS query (folded)")
+    check(outs[0][2], outs[1][2], 1e-4, "lse of the CLS query (folded)")
     dq, dk, dv = (outs[0][1][:, :, i * C:(i + 1) * C] for i in range(3))
     rq, rk, rv = (outs[1][1][:, :, i * C:(i + 1) * C] for i in range(3))
     check(dq[:, 1:], rq[:, 1:], 1.2e-2, "dq patches")
