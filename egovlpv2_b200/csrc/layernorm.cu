@@ -224,7 +224,9 @@ extern "C" int egv_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, 
   if (!dy || !x || !gamma || !mean || !rstd) return fail(EGV_ERR_ARG, "layernorm_bwd: null pointer");
   if (C % 4 || C > 128 * LN_MAXV || C <= 0) return fail(EGV_ERR_UNSUPPORTED, "layernorm: C=%d must be a multiple of 4 and <= 1024", C);
   if (rows <= 0) return EGV_OK;
-  long long blocks = cdiv(rows, 8 * 8);  // >= 8 rows per warp amortises the column-sum atomics
+  // >= 8 rows per warp amortises the column-sum atomics of the big (video) calls; the 256-row text-tower calls are latency
+  // bound instead: 4 CTAs walking 8 rows per warp one after the other took 30 us -- one row per warp there
+  long long blocks = rows <= 4096 ? cdiv(rows, 8) : cdiv(rows, 8 * 8);
   const long long cap = (long long)sm_count() * 2;   // measured: 3 resident blocks per SM are slower (129 vs 93 us at cfg 3)
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
