@@ -46,6 +46,13 @@ class P2PAllGather:
                 self.peer_flags.append(K.p2p_open(hf))
         dist.barrier()
 
+    def check(self):
+        """Raise if a gather of this rank ever gave up waiting for a peer (the kernel leaves a sticky error word instead of
+        trapping: the CUDA context survives).  Synchronous 4-byte read: call it where the trainer synchronises anyway."""
+        err = self.K.p2p_error(self.flags_ptr)
+        if err:
+            raise RuntimeError("P2P all-gather: rank %d timed out waiting for rank %d" % (self.rank, err & 0xFF))
+
     def __call__(self, tensor, n_gpu=None, args=None):
         t = tensor.contiguous()
         nbytes = t.numel() * t.element_size()

@@ -56,9 +56,9 @@ __global__ void __launch_bounds__(256) p2p_allgather_kernel(const uint4* __restr
     volatile unsigned int* f = my_flags + threadIdx.x;
     unsigned long long spins = 0;
     while ((int)(*f - seq) < 0) {
-      if (++spins > (1ull << 26)) {   // ~10 s: a lost peer must fail fast, not hang the box
-        printf("egv: p2p all-gather timeout rank %d waiting for %d\n", rank, threadIdx.x);
-        __trap();
+      if (++spins > (1ull << 26)) {   // ~10 s: a lost peer must fail fast, not hang the box -- and not kill the context:
+        atomicExch(my_flags + 28, 0x100u | (unsigned int)threadIdx.x);   // sticky error word, read by egv_p2p_error()
+        break;                        // the gathered rows of that peer are stale; the trainer decides what to do
       }
     }
     __threadfence_system();
@@ -152,4 +152,13 @@ extern "C" int egv_p2p_allgather(const void* src, int64_t bytes, int64_t slot_by
   if (cb > 64) cb = 64;
   launch_k(p2p_collect_kernel, dim3(cb), dim3(256), 0, s, (uint4*)out, (const uint8_t*)slots[rank], (const unsigned int*)flags[rank], n16, slot_bytes, half, world);
   return check_launch("p2p_collect_kernel");
+}
+
+extern "C" int egv_p2p_error(const void* flags_local, int* err) {
+  if (!flags_local || !err) return fail(EGV_ERR_ARG, "p2p_error: null pointer");
+  unsigned int w = 0;
+  cudaError_t e = cudaMemcpy(&w, reinterpret_cast<const unsigned int*>(flags_local) + 28, sizeof(w), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return fail(EGV_ERR_CUDA, "p2p_error: %s", cudaGetErrorString(e));
+  *err = (int)w;
+  return EGV_OK;
 }

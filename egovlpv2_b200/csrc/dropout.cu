@@ -22,7 +22,7 @@ namespace dr {
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int HD = 64;
 constexpr int SMAX = 64;
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_THREADS = 512;   // 16 warps: two query rows per warp at S = 32 (4 warps walking 8 rows each were latency-bound: 59 us backward)
 
 __global__ void rng_advance_kernel(unsigned long long* state) {
   pdl_enter();

@@ -641,6 +641,12 @@ class Kernels:
         self._check(self.lib.egv_p2p_open(C.c_char_p(handle), C.byref(ptr)))
         return ptr.value
 
+    def p2p_error(self, flags_ptr):
+        """0, or 0x100 | peer rank when a gather of this rank timed out waiting for that peer (sticky)"""
+        err = c_int(0)
+        self._check(self.lib.egv_p2p_error(c_void_p(flags_ptr), C.byref(err)))
+        return err.value
+
     def p2p_allgather(self, src, nbytes, slot_bytes, slots, flags, rank, world, out):
         arr_s = (C.c_void_p * world)(*slots)
         arr_f = (C.c_void_p * world)(*flags)

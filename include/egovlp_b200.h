@@ -352,6 +352,10 @@ int egv_p2p_close(void* ptr);
 int egv_p2p_free(void* ptr);
 int egv_p2p_allgather(const void* src, int64_t bytes, int64_t slot_bytes, void* const* slots, void* const* flags, int rank,
                       int world, void* out, egv_stream_t stream);
+/* A rank that waits ~10 s for a peer's flag gives up WITHOUT killing the CUDA context: it leaves a sticky word in its own
+ * flags buffer.  *err = 0: no gather of this rank ever timed out; else 0x100 | (rank it was waiting for).  Synchronous
+ * 4-byte device-to-host read: call it at a point where the trainer synchronises anyway. */
+int egv_p2p_error(const void* flags_local, int* err);
 
 /* Optimiser (next row f-1): fused AdamW (transformers.AdamW semantics, set_optim_schedule.py:108) on one flat fp32
  * tensor; also refreshes the bf16 weight copy.  hyper_dev (optional, device float[3]) = {lr multiplier, 1-beta1^t,
