@@ -292,7 +292,7 @@ __global__ void qbias_fwd_kernel(const bf16* __restrict__ k, long long ldk, cons
 }
 
 // dk[b*S+s, h*64+j] += scale * dbias[b, h*S+s] * bq[h*64+j];   dbq[h*64+j] += scale * sum_{b,s} k[..] * dbias[..]
-// grid (H, ceil(B*S / 32)), 64 threads (j): a CTA owns 32 rows of one head and adds its partial dbq with one atomic per j
+// grid (H, ceil(B*S / 4)), 64 threads (j): a CTA owns 4 rows of one head and adds its partial dbq with one atomic per j
 __global__ void qbias_bwd_kernel(const bf16* __restrict__ k, long long ldk, const float* __restrict__ bq,
                                  const float* __restrict__ dbias, float scale, int B, int S, int H, float* __restrict__ dk,
                                  long long lddk, float* __restrict__ dbq) {
@@ -300,7 +300,7 @@ __global__ void qbias_bwd_kernel(const bf16* __restrict__ k, long long ldk, cons
   const int h = blockIdx.x, j = threadIdx.x;
   const float q = bq[h * 64 + j];
   float acc = 0.f;
-  const int r0 = blockIdx.y * 32, r1 = min(r0 + 32, B * S);
+  const int r0 = blockIdx.y * 4, r1 = min(r0 + 4, B * S);   // 4 rows per CTA: the loop is a chain of dependent global round trips (32 rows: 29 us)
 #pragma unroll 4
   for (int bs = r0; bs < r1; ++bs) {
     const int b = bs / S, s = bs % S;
@@ -379,7 +379,7 @@ extern "C" int egv_xattn_qbias_fwd(const void* k, int64_t ldk, const float* bq, 
 extern "C" int egv_xattn_qbias_bwd(const void* k, int64_t ldk, const float* bq, const float* dbias, float scale, int B, int S,
                                    int H, float* dk, int64_t lddk, float* dbq, egv_stream_t stream) {
   if (!k || !bq || !dbias || B <= 0 || S <= 0 || H <= 0) return fail(EGV_ERR_ARG, "qbias_bwd: bad arguments");
-  launch_k(xa::qbias_bwd_kernel, dim3(dim3((unsigned)H, (unsigned)cdiv((long long)B * S, 32))), dim3(64), 0, (cudaStream_t)stream, (const bf16*)k, ldk, bq, dbias, scale, B, S, H, dk, lddk, dbq);
+  launch_k(xa::qbias_bwd_kernel, dim3(dim3((unsigned)H, (unsigned)cdiv((long long)B * S, 4))), dim3(64), 0, (cudaStream_t)stream, (const bf16*)k, ldk, bq, dbias, scale, B, S, H, dk, lddk, dbq);
   return check_launch("qbias_bwd_kernel");
 }
 
