@@ -10,7 +10,14 @@ all-reduced on a communication stream while the backward carries on.  `finish()`
 embedding, ...) and joins the streams.  The arena is flat, so a bucket is a list of slices: no copies, no flattening.
 
 Works without CUDA too (gloo, synchronous): the 2-rank CPU tests pin that the bucketed result equals one all-reduce of the
-whole buffer bit for bit."""
+whole buffer bit for bit.
+
+EGV_ALLREDUCE_BF16=1 (opt-in, off by default): every bucket travels as bf16 -- half the bytes over NVLink -- and is written
+back into the fp32 gradient buffer (AdamW keeps accumulating in fp32).  This changes the reduction's rounding (each rank's
+partial gradient is rounded to 8 mantissa bits before the sum; the reference's DDP reduces fp32), so it is not the default;
+the 2-rank CPU test bounds the difference.  Not measured at N = 8."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -29,6 +36,7 @@ class OverlappedGradReducer:
         self.comm = torch.cuda.Stream(device=arena.grad.device) if self.cuda else None
         self.done = []
         self.calls = 0
+        self.bf16 = os.environ.get("EGV_ALLREDUCE_BF16", "0") == "1"
         names = {id(p): n for n, p in model.named_parameters()}
         fused = [p for p in arena.params if any(s in names.get(id(p), "") for s in FUSED_ONLY)
                  or names.get(id(p), "") in ("cls_token", "norm.weight", "norm.bias")]
@@ -106,11 +114,19 @@ class OverlappedGradReducer:
                 self.comm.wait_stream(streams._side_stream())
             with torch.cuda.stream(self.comm):
                 for lo, hi in ranges:
-                    dist.all_reduce(g[lo:hi])
+                    self._all_reduce(g[lo:hi])
         else:
             for lo, hi in ranges:
-                dist.all_reduce(g[lo:hi])
+                self._all_reduce(g[lo:hi])
         self.calls += len(ranges)
+
+    def _all_reduce(self, view):
+        if self.bf16:
+            t = view.to(torch.bfloat16)
+            dist.all_reduce(t)
+            view.copy_(t)
+        else:
+            dist.all_reduce(view)
 
     def finish(self):
         """after loss.backward() (and streams.join()): reduce the rest, make the main stream wait for the communication"""

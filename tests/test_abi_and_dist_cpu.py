@@ -259,6 +259,24 @@ def _reducer_worker(rank, world, port, q, golden_dir):
         # the bucketed, overlapped reduction == one all-reduce of the whole buffer, bit for bit (2 ranks: a + b commutes)
         assert torch.equal(grads["1"], grads["0"]), (grads["1"] - grads["0"]).abs().max().item()
         assert grads["1"].abs().sum().item() > 0
+        # opt-in bf16 buckets (EGV_ALLREDUCE_BF16=1): same buckets, payload rounded to bf16 before the sum -- the result
+        # differs from the fp32 reduction by bf16 rounding only (rel-L2 <= 2^-8), and is written back into the fp32 buffer
+        os.environ["EGV_OVERLAP_ALLREDUCE"] = "1"
+        os.environ["EGV_ALLREDUCE_BF16"] = "1"
+        try:
+            weights.cache().arena = None
+            model = build_tiny(c)
+            model.load_state_dict(sd, strict=False)
+            model.eval()
+            step = PretrainStep(model, torch.device("cpu"), lr=0.0, weight_decay=0.0, gather="nccl")
+            model.itm_plan = dict(labels=torch.tensor([1., 0.]), swap_video=torch.tensor([False, True]), neg_idx=torch.tensor([1 - rank, 2 * (1 - rank)]))
+            step.step(batch)
+            g16 = step.opt.arena.grad
+            assert g16.dtype == torch.float32 and step.reducer.bf16
+            err = ((g16 - grads["0"]).norm() / grads["0"].norm()).item()
+            assert 0.0 < err <= 2.0 ** -8, err
+        finally:
+            os.environ["EGV_ALLREDUCE_BF16"] = "0"
         q.put((rank, "ok"))
     except Exception:  # pragma: no cover
         import traceback
